@@ -1,0 +1,350 @@
+// C ABI (include/recsys_b200.h): engine lifetime, parameter binding, train steps, evaluation.
+#include <math.h>
+#include <new>
+#include "common.cuh"
+
+// launchers from the other translation units
+int launch_fill_i32(rec_engine *e, int32_t *p, int64_t n, int32_t v);
+int launch_td(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int n_q, float alpha_eff,
+              float *q_loss_rows);
+int launch_loss_reduce(rec_engine *e, int B, const float *q_loss_rows, float *out);
+int launch_eval_metrics(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, int kmax,
+                        const rec_eval_accum *acc, double *rowm, int32_t *topk_ids, float *topk_scores);
+size_t head_bwd_smem_bytes(int D);
+
+static char g_err[512] = "";
+
+struct EngineExtra {
+  float *q_loss_rows;
+  double *rowm;
+};
+static EngineExtra &extra(rec_engine *e) { return *reinterpret_cast<EngineExtra *>(e + 1); }
+
+#define ALLOC(e, ptr, type, count)                                                      \
+  do {                                                                                  \
+    cudaError_t _st = cudaMalloc((void **)&(ptr), sizeof(type) * (size_t)(count));      \
+    if (_st != cudaSuccess) {                                                           \
+      snprintf(g_err, sizeof(g_err), "cudaMalloc(%s, %zu B) failed: %s", #ptr,          \
+               sizeof(type) * (size_t)(count), cudaGetErrorString(_st));                \
+      rec_destroy(e);                                                                   \
+      return REC_ENOMEM;                                                                \
+    }                                                                                   \
+  } while (0)
+
+extern "C" int rec_abi_version(void) { return REC_ABI_VERSION; }
+
+extern "C" const char *rec_last_error(const rec_engine *e) { return e ? e->err : g_err; }
+
+extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out) {
+  if (!cfg || !out) { snprintf(g_err, sizeof(g_err), "rec_create: null argument"); return REC_EINVAL; }
+  *out = nullptr;
+  int dev = 0;
+  cudaError_t st = cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (st == cudaSuccess) st = cudaGetDeviceProperties(&prop, dev);
+  if (st != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "rec_create: no CUDA device (%s); this library has no CPU fallback",
+             cudaGetErrorString(st));
+    return REC_ENODEV;
+  }
+  if (prop.major != 10) {
+    snprintf(g_err, sizeof(g_err), "rec_create: device %s is sm_%d%d; this library is built for sm_100a (B200) only",
+             prop.name, prop.major, prop.minor);
+    return REC_ENODEV;
+  }
+  const rec_config &c = *cfg;
+  if (c.embedding_dim % 4 || c.hidden_dim % 4 || c.embedding_dim <= 0 || c.hidden_dim <= 0) {
+    snprintf(g_err, sizeof(g_err), "rec_create: embedding_dim (%d) and hidden_dim (%d) must be positive multiples of 4",
+             c.embedding_dim, c.hidden_dim);
+    return REC_EINVAL;
+  }
+  if (c.n_heads < 1 || c.n_heads > REC_MAX_HEADS || c.n_heads == 3 || c.n_nets < 1 || c.n_nets > REC_MAX_NETS ||
+      c.max_batch < 1 || c.state_size < 1 || c.item_num < 1 || c.action_dim < 1 || c.vocab_lo < 0 ||
+      c.vocab_hi > c.action_dim || c.vocab_lo >= c.vocab_hi || c.max_topk < 1 || c.max_topk > REC_MAX_TOPK) {
+    snprintf(g_err, sizeof(g_err), "rec_create: invalid configuration");
+    return REC_EINVAL;
+  }
+  void *mem = calloc(1, sizeof(rec_engine) + sizeof(EngineExtra));
+  if (!mem) return REC_ENOMEM;
+  rec_engine *e = new (mem) rec_engine;
+  memset((void *)e, 0, sizeof(rec_engine) + sizeof(EngineExtra));
+  e->cfg = c;
+  e->stream = (cudaStream_t)stream;
+  e->dirs = c.bidirectional ? 2 : 1;
+  e->D = c.hidden_dim * e->dirs;
+  e->Vloc = c.vocab_hi - c.vocab_lo;
+  e->sm_count = prop.multiProcessorCount;
+  if (head_bwd_smem_bytes(e->D) > 220 * 1024) {
+    snprintf(g_err, sizeof(g_err), "rec_create: head width D=%d exceeds the shared-memory budget of the backward kernel", e->D);
+    free(mem);
+    return REC_EINVAL;
+  }
+  const int64_t mb = c.max_batch, L = c.state_size, H = c.hidden_dim, E = c.embedding_dim, G = 3 * H;
+  const int dirs = e->dirs, D = e->D;
+  for (int i = 0; i < 3; ++i) ALLOC(e, e->h_state[i], float, mb * D);
+  ALLOC(e, e->gates_save, float, mb * L * dirs * 4 * H);
+  ALLOC(e, e->hprev_save, float, mb * L * dirs * H);
+  ALLOC(e, e->dgi, float, mb * L * dirs * G);
+  ALLOC(e, e->dgh, float, mb * L * dirs * G);
+  ALLOC(e, e->dx, float, mb * L * dirs * E);
+  ALLOC(e, e->dh, float, mb * D);
+  const int n_tiles = (e->Vloc + 63) / 64;
+  e->n_dh_part = (n_tiles < 2 * e->sm_count ? n_tiles : 2 * e->sm_count) + 1;
+  ALLOC(e, e->dh_part, float, (int64_t)e->n_dh_part * mb * D);
+  e->wgrad_splits = 16;
+  const int64_t KS = (E > H ? E : H) + 1;
+  ALLOC(e, e->wgrad_part, float, (int64_t)e->wgrad_splits * dirs * 2 * G * KS);
+  ALLOC(e, e->emb_keys, int32_t, mb * L);
+  ALLOC(e, e->emb_slot, int32_t, (int64_t)c.item_num + 1);
+  ALLOC(e, e->emb_grad_rows, float, mb * L * E);
+  e->part_stride = 72;
+  e->n_split_max = 2 * e->sm_count;
+  ALLOC(e, e->part, float, ((int64_t)e->n_split_max * 64 + 2 * mb) * e->part_stride);
+  ALLOC(e, e->row_stats, float, mb * 8);
+  ALLOC(e, e->row_ids, int32_t, mb * REC_MAX_TOPK);
+  ALLOC(e, e->row_topv, float, mb * REC_MAX_TOPK);
+  ALLOC(e, e->q_sa, float, mb * 3);
+  ALLOC(e, e->q_boot, float, mb * 3);
+  ALLOC(e, e->dq, float, mb * 3);
+  ALLOC(e, e->rewards, float, mb * 3);
+  ALLOC(e, e->loss_buf, float, 8);
+  ALLOC(e, e->astar, int32_t, mb);
+  ALLOC(e, extra(e).q_loss_rows, float, mb);
+  ALLOC(e, extra(e).rowm, double, mb * (3 * REC_MAX_KLIST + 3));
+  for (int n = 0; n < c.n_nets; ++n)
+    for (int d = 0; d < dirs; ++d) {
+      ALLOC(e, e->nets[n].w_ihT[d], float, G * E);
+      ALLOC(e, e->nets[n].w_hhT[d], float, G * H);
+    }
+  for (int i = 0; i < 6; ++i) cudaEventCreate(&e->ev[i]);
+  if (launch_fill_i32(e, e->emb_slot, (int64_t)c.item_num + 1, -1) != REC_OK) {
+    snprintf(g_err, sizeof(g_err), "%s", e->err);
+    rec_destroy(e);
+    return REC_ECUDA;
+  }
+  cudaMemsetAsync(e->q_sa, 0, sizeof(float) * mb * 3, e->stream);
+  cudaMemsetAsync(e->q_boot, 0, sizeof(float) * mb * 3, e->stream);
+  cudaMemsetAsync(e->dq, 0, sizeof(float) * mb * 3, e->stream);
+  e->err[0] = 0;
+  *out = e;
+  return REC_OK;
+}
+
+extern "C" void rec_destroy(rec_engine *e) {
+  if (!e) return;
+  cudaStreamSynchronize(e->stream);
+  void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
+                  e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
+                  e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
+                  extra(e).q_loss_rows, extra(e).rowm};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  for (int n = 0; n < REC_MAX_NETS; ++n)
+    for (int d = 0; d < 2; ++d) {
+      if (e->nets[n].w_ihT[d]) cudaFree(e->nets[n].w_ihT[d]);
+      if (e->nets[n].w_hhT[d]) cudaFree(e->nets[n].w_hhT[d]);
+    }
+  for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  free(e);
+}
+
+static int check_net(rec_engine *e, int net_id, bool need_opt) {
+  if (!e) return REC_EINVAL;
+  if (net_id < 0 || net_id >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "net_id %d out of range", net_id);
+  if (!e->nets[net_id].bound) REC_FAIL(e, REC_EINVAL, "net %d has no bound parameters (call rec_bind_params)", net_id);
+  if (need_opt && !e->nets[net_id].p.emb_m) REC_FAIL(e, REC_EINVAL, "net %d was bound without Adam state", net_id);
+  return REC_OK;
+}
+
+extern "C" int rec_bind_params(rec_engine *e, int net_id, const rec_net_params *p) {
+  if (!e || !p) return REC_EINVAL;
+  if (net_id < 0 || net_id >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "net_id %d out of range", net_id);
+  if (!p->emb) REC_FAIL(e, REC_EINVAL, "rec_bind_params: emb is null");
+  for (int d = 0; d < e->dirs; ++d)
+    if (!p->w_ih[d] || !p->w_hh[d] || !p->b_ih[d] || !p->b_hh[d]) REC_FAIL(e, REC_EINVAL, "rec_bind_params: GRU pointer null (dir %d)", d);
+  for (int h = 0; h < e->cfg.n_heads; ++h)
+    if (!p->head_w[h] || !p->head_b[h]) REC_FAIL(e, REC_EINVAL, "rec_bind_params: head %d pointer null", h);
+  NetBind &nb = e->nets[net_id];
+  nb.p = *p;
+  nb.bound = true;
+  return launch_gru_transpose(e, net_id);
+}
+
+extern "C" int rec_set_adam_step(rec_engine *e, int net_id, int64_t step) {
+  if (!e || net_id < 0 || net_id >= e->cfg.n_nets) return REC_EINVAL;
+  e->nets[net_id].adam_step = step;
+  return REC_OK;
+}
+extern "C" int64_t rec_get_adam_step(const rec_engine *e, int net_id) {
+  if (!e || net_id < 0 || net_id >= e->cfg.n_nets) return -1;
+  return e->nets[net_id].adam_step;
+}
+
+extern "C" int64_t rec_launch_count(const rec_engine *e) { return e ? e->launches : -1; }
+extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) { if (!e) return REC_EINVAL; e->timing = on != 0; return REC_OK; }
+extern "C" float rec_last_kernel_ms(rec_engine *e, int which) {
+  if (!e || which < 0 || which > 2) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(e->ev[2 * which + 1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+static int check_batch(rec_engine *e, const rec_batch *b, bool q) {
+  if (!b || !b->s || !b->a || !b->true_len) REC_FAIL(e, REC_EINVAL, "batch: s/a/true_len must be non-null");
+  if (b->B < 1 || b->B > e->cfg.max_batch) REC_FAIL(e, REC_EINVAL, "batch size %d outside [1, max_batch=%d]", b->B, e->cfg.max_batch);
+  if (q && (!b->r || !b->s_next || !b->true_next_len || !b->is_end)) REC_FAIL(e, REC_EINVAL, "batch: r/s_next/true_next_len/is_end must be non-null");
+  return REC_OK;
+}
+
+extern "C" int rec_forward_state(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B, float *h_out) {
+  int rc = check_net(e, net_id, false);
+  if (rc) return rc;
+  if (!s || !lengths || !h_out || B < 1) REC_FAIL(e, REC_EINVAL, "rec_forward_state: bad argument");
+  return launch_gru_forward(e, net_id, s, lengths, B, h_out, false);
+}
+
+extern "C" int rec_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld) {
+  int rc = check_net(e, net_id, false);
+  if (rc) return rc;
+  if (head < 0 || head >= e->cfg.n_heads || !h || !logits || ld < e->Vloc) REC_FAIL(e, REC_EINVAL, "rec_head_logits: bad argument");
+  return launch_head_logits(e, net_id, head, h, B, logits, ld);
+}
+
+static void adam_scalars(rec_engine *e, int net_id, const rec_train_hparams *hp, float *step_size, float *bc2_sqrt) {
+  // torch.optim.Adam (single-tensor/foreach, capturable=False): python-double scalars
+  int64_t t = ++e->nets[net_id].adam_step;
+  double bc1 = 1.0 - pow((double)hp->beta1, (double)t);
+  double bc2 = 1.0 - pow((double)hp->beta2, (double)t);
+  *step_size = (float)((double)hp->lr / bc1);
+  *bc2_sqrt = (float)sqrt(bc2);
+}
+
+extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out) {
+  int rc = check_net(e, 0, true);
+  if (rc) return rc;
+  if ((rc = check_batch(e, b, false))) return rc;
+  if (!hp || !loss_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_supervised: null argument");
+  const int B = b->B;
+  if ((rc = launch_gru_forward(e, 0, b->s, b->true_len, B, e->h_state[0], true))) return rc;
+  HeadStatsArgs a = {};
+  a.net_id = 0; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
+  int n_split = 0;
+  if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+  if ((rc = launch_head_merge(e, e->part, n_split, B, 0, true, false))) return rc;
+  if ((rc = launch_loss_reduce(e, B, nullptr, e->loss_buf))) return rc;
+  REC_CUDA(e, cudaMemcpyAsync(loss_out, e->loss_buf, sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  float step_size, bc2_sqrt;
+  adam_scalars(e, 0, hp, &step_size, &bc2_sqrt);
+  if ((rc = launch_head_backward_adam(e, 0, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
+  if ((rc = launch_gru_backward(e, 0, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp))) return rc;
+  return launch_embedding_update(e, 0, b->s, b->true_len, B, step_size, bc2_sqrt, hp);
+}
+
+extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out) {
+  if (!e) return REC_EINVAL;
+  if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q needs a twin-net engine with Q heads");
+  if (main_net != 0 && main_net != 1) REC_FAIL(e, REC_EINVAL, "main_net must be 0 or 1");
+  int rc = check_net(e, main_net, true);
+  if (rc) return rc;
+  if ((rc = check_net(e, 1 - main_net, false))) return rc;
+  if ((rc = check_batch(e, b, true))) return rc;
+  if (!hp || !losses_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_q: null argument");
+  const int B = b->B, boot = 1 - main_net, n_q = e->cfg.n_heads - 1;
+  if (n_q == 3) {
+    if (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 || hp->div_dim < 1 ||
+        hp->topk_div > e->cfg.max_topk || hp->topk_nov > e->cfg.max_topk)
+      REC_FAIL(e, REC_EINVAL, "SMORL step needs div_emb, unpopular and 1 <= topk_div/topk_nov <= max_topk");
+  }
+  // three GRU passes: main(s, len) [saved], main(s', len'), boot(s', len)  -- (q1) boot sees true_len
+  if ((rc = launch_gru_forward(e, main_net, b->s, b->true_len, B, e->h_state[0], true))) return rc;
+  if ((rc = launch_gru_forward(e, main_net, b->s_next, b->true_next_len, B, e->h_state[1], false))) return rc;
+  if ((rc = launch_gru_forward(e, boot, b->s_next, b->true_len, B, e->h_state[2], false))) return rc;
+  // supervised head statistics (+ top-k of the supervised logits for the SMORL rewards)
+  HeadStatsArgs a = {};
+  a.net_id = main_net; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
+  a.topk = (n_q == 3) ? (hp->topk_div > hp->topk_nov ? hp->topk_div : hp->topk_nov) : 0;
+  int n_split = 0;
+  if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+  if ((rc = launch_head_merge(e, e->part, n_split, B, a.topk, true, false))) return rc;
+  // greedy action a* = argmax_a sum_h w_h Q_h(s', a) on the main net
+  HeadStatsArgs g = {};
+  g.net_id = main_net; g.h = e->h_state[1]; g.B = B; g.n_arg = n_q;
+  g.w[0] = n_q == 3 ? hp->q_weights[0] : 1.f; g.w[1] = hp->q_weights[1]; g.w[2] = hp->q_weights[2];
+  if ((rc = launch_head_stats(e, g, &n_split))) return rc;
+  if ((rc = launch_head_merge(e, e->part, n_split, B, 0, false, true))) return rc;
+  // Q(s,a) on main, Q_boot(s',a*) on boot: row gather-dots
+  if ((rc = launch_row_dots(e, main_net, e->h_state[0], b->a, nullptr, B, 1, n_q, e->q_sa))) return rc;
+  if ((rc = launch_row_dots(e, boot, e->h_state[2], nullptr, e->astar, B, 1, n_q, e->q_boot))) return rc;
+  const float alpha_eff = (n_q == 3) ? hp->alpha : 1.f;
+  if ((rc = launch_td(e, b, hp, n_q, alpha_eff, extra(e).q_loss_rows))) return rc;
+  if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
+  REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  float step_size, bc2_sqrt;
+  adam_scalars(e, main_net, hp, &step_size, &bc2_sqrt);
+  if ((rc = launch_head_backward_adam(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
+  if ((rc = launch_gru_backward(e, main_net, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp))) return rc;
+  return launch_embedding_update(e, main_net, b->s, b->true_len, B, step_size, bc2_sqrt, hp);
+}
+
+static int eval_kmax(const rec_eval_opts *o) {
+  int k = 1;
+  for (int i = 0; i < o->n_k; ++i) k = o->ks[i] > k ? o->ks[i] : k;
+  for (int i = 0; i < o->n_cov; ++i) k = o->cov_ks[i] > k ? o->cov_ks[i] : k;
+  if (o->div_emb && o->topk_div > k) k = o->topk_div;
+  if (o->unpopular && o->topk_nov > k) k = o->topk_nov;
+  return k;
+}
+
+extern "C" int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, const rec_eval_opts *o,
+                              const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores) {
+  int rc = check_net(e, net_id, false);
+  if (rc) return rc;
+  if ((rc = check_batch(e, b, false))) return rc;
+  if (!o || !acc || !acc->hits || !acc->ndcg || !acc->reps || !acc->div_sum || !acc->nov_sum || !acc->loss_sum || !acc->cov_bits)
+    REC_FAIL(e, REC_EINVAL, "rec_eval_batch: null option/accumulator");
+  if (o->head_idx < 0 || o->head_idx >= e->cfg.n_heads || o->n_k < 0 || o->n_k > REC_MAX_KLIST || o->n_cov < 0 || o->n_cov > REC_MAX_KLIST)
+    REC_FAIL(e, REC_EINVAL, "rec_eval_batch: bad head_idx / k lists");
+  const int kmax = eval_kmax(o);
+  if (kmax > e->cfg.max_topk) REC_FAIL(e, REC_EINVAL, "rec_eval_batch: k=%d exceeds max_topk=%d", kmax, e->cfg.max_topk);
+  if (e->cfg.vocab_lo != 0 || e->cfg.vocab_hi != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "rec_eval_batch on a sharded engine: use rec_eval_shard_candidates + rec_eval_merge");
+  const int B = b->B;
+  if ((rc = launch_gru_forward(e, net_id, b->s, b->true_len, B, e->h_state[0], false))) return rc;
+  HeadStatsArgs a = {};
+  a.net_id = net_id; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = o->head_idx; a.target = b->a; a.topk = kmax;
+  int n_split = 0;
+  if (e->timing) cudaEventRecord(e->ev[2], e->stream);
+  if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+  if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+  if ((rc = launch_head_merge(e, e->part, n_split, B, kmax, true, false))) return rc;
+  return launch_eval_metrics(e, b, o, kmax, acc, extra(e).rowm, topk_ids, topk_scores);
+}
+
+// ---- sharded / phase-split entry points (see DESIGN.md section "multi-GPU") ---------------------
+extern "C" int rec_eval_shard_candidates(rec_engine *e, int net_id, const rec_batch *b, int head_idx, int kmax,
+                                         float *h_out, float *cand_scores, int32_t *cand_ids, float *stats) {
+  (void)net_id; (void)b; (void)head_idx; (void)kmax; (void)h_out; (void)cand_scores; (void)cand_ids; (void)stats;
+  REC_FAIL(e, REC_EINVAL, "rec_eval_shard_candidates: not implemented in this build");
+}
+extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, int n_shards, int kmax,
+                              const float *cand_scores, const int32_t *cand_ids, const float *stats,
+                              const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores) {
+  (void)b; (void)o; (void)n_shards; (void)kmax; (void)cand_scores; (void)cand_ids; (void)stats; (void)acc; (void)topk_ids; (void)topk_scores;
+  REC_FAIL(e, REC_EINVAL, "rec_eval_merge: not implemented in this build");
+}
+extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
+                                 float **partials, int64_t *partials_floats) {
+  (void)b; (void)hp; (void)main_net; (void)partials; (void)partials_floats;
+  REC_FAIL(e, REC_EINVAL, "rec_train_phase_a: not implemented in this build");
+}
+extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float **boot_q, int64_t *boot_q_floats) {
+  (void)gathered; (void)n_shards; (void)boot_q; (void)boot_q_floats;
+  REC_FAIL(e, REC_EINVAL, "rec_train_phase_b: not implemented in this build");
+}
+extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, float *losses_out, float **dh, int64_t *dh_floats) {
+  (void)boot_q_reduced; (void)losses_out; (void)dh; (void)dh_floats;
+  REC_FAIL(e, REC_EINVAL, "rec_train_phase_c: not implemented in this build");
+}
+extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
+  (void)dh_reduced;
+  REC_FAIL(e, REC_EINVAL, "rec_train_phase_d: not implemented in this build");
+}

@@ -1,0 +1,141 @@
+// Shared device helpers + the engine structure behind the opaque rec_engine handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/recsys_b200.h"
+
+#define REC_NEG_INF (-3.402823466e+38f)
+
+struct NetBind {
+  rec_net_params p;
+  bool bound;
+  int64_t adam_step;
+  // engine-owned transposed copies of the GRU weights: WiT[E][3H], WhT[H][3H] per direction
+  float *w_ihT[2], *w_hhT[2];
+};
+
+// Per-pass GRU buffers: which (net, sequence, lengths) produced which final state.
+struct rec_engine {
+  rec_config cfg;
+  cudaStream_t stream;
+  char err[512];
+  NetBind nets[REC_MAX_NETS];
+  int D, dirs, Vloc;
+  int sm_count;
+  int64_t launches;
+
+  // ---- workspace (device) ----
+  float *h_state[3];     // [maxB, D] final states: main(s), main(s'), boot(s')
+  float *gates_save;     // [maxB, L, dirs, 4, H]  r,z,n,pre_h_n of main(s)
+  float *hprev_save;     // [maxB, L, dirs, H]
+  float *dgi, *dgh;      // [maxB, L, dirs, 3H]
+  float *dx;             // [maxB, L, dirs, E]
+  float *dh;             // [maxB, D]
+  float *dh_part;        // [n_part, maxB, D]
+  int n_dh_part;
+  float *wgrad_part;     // [splits][dirs][3H][E+H+2]
+  int wgrad_splits;
+  int32_t *emb_keys;     // [maxB*L] row id or -1
+  int32_t *emb_slot;     // [N+1] slot of the leader position or -1
+  float *emb_grad_rows;  // [maxB*L, E]
+  // head statistics partials: [n_split][maxB][PART_STRIDE]
+  float *part;
+  int part_stride, n_split_max;
+  float *row_stats;      // [maxB][ROW_STRIDE] merged per-row results
+  int32_t *row_ids;      // [maxB][REC_MAX_TOPK] merged top-k ids / argmax
+  float *row_topv;       // [maxB][REC_MAX_TOPK]
+  float *q_sa;           // [maxB][3]
+  float *q_boot;         // [maxB][3]
+  float *dq;             // [maxB][3]
+  float *rewards;        // [maxB][3]
+  float *loss_buf;       // [8]
+  int32_t *astar;        // [maxB]
+  // saved call context for the phase-split API
+  rec_batch cur_batch;
+  rec_train_hparams cur_hp;
+  int cur_main;
+  bool timing;
+  cudaEvent_t ev[6];
+  float last_ms[3];
+};
+
+#define REC_FAIL(e, code, ...)                          \
+  do {                                                  \
+    if (e) snprintf((e)->err, sizeof((e)->err), __VA_ARGS__); \
+    return (code);                                      \
+  } while (0)
+
+#define REC_CUDA(e, call)                                                                 \
+  do {                                                                                    \
+    cudaError_t _st = (call);                                                             \
+    if (_st != cudaSuccess) {                                                             \
+      if (e) snprintf((e)->err, sizeof((e)->err), "%s failed: %s (%s:%d)", #call,         \
+                      cudaGetErrorString(_st), __FILE__, __LINE__);                       \
+      return REC_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+
+#define REC_LAUNCH_CHECK(e)                                                               \
+  do {                                                                                    \
+    (e)->launches++;                                                                      \
+    cudaError_t _st = cudaGetLastError();                                                 \
+    if (_st != cudaSuccess) {                                                             \
+      snprintf((e)->err, sizeof((e)->err), "kernel launch failed: %s (%s:%d)",            \
+               cudaGetErrorString(_st), __FILE__, __LINE__);                              \
+      return REC_ECUDA;                                                                   \
+    }                                                                                     \
+  } while (0)
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// (score desc, id asc): is candidate (v, i) strictly better than (w, j)?
+__device__ __forceinline__ bool better(float v, int i, float w, int j) {
+  return (v > w) || (v == w && i < j);
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- launchers implemented in the .cu files -------------------------------------------------
+// gru.cu
+int launch_gru_forward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
+                       float *h_out, bool save);
+int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
+                        const float *dh, float step_size, float bc2_sqrt, const rec_train_hparams *hp);
+int launch_gru_transpose(rec_engine *e, int net_id);
+// embed.cu
+int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
+                            float step_size, float bc2_sqrt, const rec_train_hparams *hp);
+// heads.cu
+struct HeadStatsArgs {
+  int net_id;
+  const float *h;         // [B, D]
+  int B;
+  int do_stats;           // 1: online (max,sumexp) + target logit of head `stats_head`
+  int stats_head;         // head whose logits feed stats / top-k
+  const int64_t *target;  // [B] global action ids (target logit)
+  int topk;               // >0: running top-k of `stats_head` (score desc, id asc)
+  int n_arg;              // >0: argmax over sum_j w[j] * Q_{1+j}, j < n_arg
+  float w[3];
+};
+int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
+int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats,
+                      bool has_argmax);
+int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld);
+int launch_row_dots(rec_engine *e, int net_id, const float *h, const int64_t *ids, const int32_t *ids32,
+                    int B, int first_head, int n, float *out);
+int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B,
+                              float step_size, float bc2_sqrt, const rec_train_hparams *hp, float inv_B);

@@ -1,0 +1,675 @@
+// Full-vocabulary heads, CUDA-core (fp32 FFMA) path: generic in B, D and V.
+//
+// Replaces nn.Linear heads + CrossEntropyLoss + argmax/gather/topk of the reference
+// (models/SQN/sqn_gru.py:78-85,107-110,221-242; models/SMORL/smorl_gru.py:85-137,272-295;
+// utils/tensor_operations.py:4-84; evaluate/*.py `torch.topk` call sites).  Logits are never
+// written to HBM on the hot path: every consumer is an epilogue of the tile GEMM
+//   * head_stats_kernel  : online (max, sum-exp) + target logit, running top-k (score desc, id asc),
+//                          running argmax of sum_h w_h Q_h  -> per-(vocab split,row) partials
+//   * head_merge_kernel  : combines the partials of all splits (and, multi-GPU, all shards)
+//   * head_bwd_adam_kernel: recomputes the tile, forms dlogits = (softmax - onehot)/B on the fly,
+//                          dW/db tile + dh partial, and applies Adam to the tile in the same pass
+//                          (W, m, v are read once and written once per step: 24 B/param).
+#include "common.cuh"
+
+#define TM 64   // batch rows per tile
+#define TN 64   // vocabulary rows per tile
+#define KC 32   // k-chunk of the logits GEMM
+#define KP 36   // padded k stride (floats) -> conflict-free LDS.128
+#define PART_TOPK_OFF 5
+
+// ---- tile GEMM: acc[a][c] += sum_k A[ty+16a][k] * B[tx+16c][k] over one staged chunk ------------
+__device__ __forceinline__ void tile_fma(const float (*As)[KP], const float (*Bs)[KP], int ty, int tx,
+                                         float acc[4][4]) {
+#pragma unroll
+  for (int k4 = 0; k4 < KC / 4; ++k4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = *reinterpret_cast<const float4 *>(&As[ty + 16 * i][k4 * 4]);
+      b[i] = *reinterpret_cast<const float4 *>(&Bs[tx + 16 * i][k4 * 4]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+        acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+        acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+        acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+      }
+  }
+}
+
+// stage rows [r0, r0+64) x cols [k0, k0+32) of a row-major [nrows, ld] matrix (zero fill outside)
+__device__ __forceinline__ void stage_chunk(float (*dst)[KP], const float *__restrict__ src, int r0, int nrows,
+                                            int ld, int k0, int kmax, int tid) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int e = tid + q * 256;
+    int r = e >> 3, k4 = e & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = k0 + k4 * 4;
+    if (r0 + r < nrows && k < kmax) v = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(r0 + r) * ld + k));
+    *reinterpret_cast<float4 *>(&dst[r][k4 * 4]) = v;
+  }
+}
+
+// logits tile of one head: acc = h[bb*64.., :] . W[v0.., :]^T  (D multiple of 4)
+__device__ __forceinline__ void logits_tile(float (*As)[KP], float (*Bs)[KP], const float *__restrict__ h, int b0,
+                                            int B, const float *__restrict__ W, int v0, int Vloc, int D, int tid,
+                                            int ty, int tx, float acc[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < D; k0 += KC) {
+    stage_chunk(As, h, b0, B, D, k0, D, tid);
+    stage_chunk(Bs, W, v0, Vloc, D, k0, D, tid);
+    __syncthreads();
+    tile_fma(As, Bs, ty, tx, acc);
+    __syncthreads();
+  }
+}
+
+struct HeadPtrs {
+  const float *w[REC_MAX_HEADS];
+  const float *b[REC_MAX_HEADS];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Statistics pass.  grid = (n_split, ceil(B/64)), block 256.  CTA (sp, bb) walks vocabulary tiles
+// [t_lo, t_hi) of the local shard for batch block bb and keeps running per-row results.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_stats_kernel(HeadPtrs hp, const float *__restrict__ h, int B, int D,
+                                                         int Vloc, int vocab_lo, int n_tiles, int do_stats,
+                                                         int stats_head, const int64_t *__restrict__ target,
+                                                         int topk, int n_arg, float w0, float w1, float w2,
+                                                         float *__restrict__ part, int part_stride) {
+  __shared__ __align__(16) float As[TM][KP];
+  __shared__ __align__(16) float Bs[TN][KP];
+  __shared__ float Ct[TM][TN + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const int sp = blockIdx.x, n_split = gridDim.x, bb = blockIdx.y;
+  const int b0 = bb * TM;
+  const int per = (n_tiles + n_split - 1) / n_split;
+  const int t_lo = sp * per, t_hi = min(n_tiles, t_lo + per);
+
+  float m_run[4], s_run[4], tgt[4], av[4];
+  int ai[4];
+  int64_t trow[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    m_run[a] = REC_NEG_INF; s_run[a] = 0.f; tgt[a] = REC_NEG_INF; av[a] = REC_NEG_INF; ai[a] = 0x7fffffff;
+    int row = b0 + ty + 16 * a;
+    trow[a] = (do_stats && target && row < B) ? target[row] - vocab_lo : -1;
+  }
+  float lv[8];
+  int li[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) { lv[r] = REC_NEG_INF; li[r] = 0x7fffffff; }
+  const float wq[3] = {w0, w1, w2};
+
+  for (int t = t_lo; t < t_hi; ++t) {
+    const int v0 = t * TN;
+    float acc[4][4];
+    if (do_stats || topk > 0) {
+      logits_tile(As, Bs, h, b0, B, hp.w[stats_head], v0, Vloc, D, tid, ty, tx, acc);
+      float bias[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int col = v0 + tx + 16 * c;
+        bias[c] = col < Vloc ? __ldg(hp.b[stats_head] + col) : 0.f;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float l[4];
+        float tmax = REC_NEG_INF;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int col = v0 + tx + 16 * c;
+          l[c] = col < Vloc ? acc[a][c] + bias[c] : REC_NEG_INF;
+          tmax = fmaxf(tmax, l[c]);
+          if ((int64_t)col == trow[a]) tgt[a] = l[c];
+          if (topk > 0) Ct[ty + 16 * a][tx + 16 * c] = l[c];
+        }
+        if (do_stats) {
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+          float nm = fmaxf(m_run[a], tmax);
+          float ps = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ps += (l[c] > REC_NEG_INF) ? __expf(l[c] - nm) : 0.f;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+          s_run[a] = s_run[a] * __expf(m_run[a] - nm) + ps;
+          m_run[a] = nm;
+        }
+      }
+      if (topk > 0) {
+        __syncthreads();
+        // warp w owns rows 8w..8w+7; lane r of the warp holds the r-th best (value,id) of a row
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int row = warp * 8 + r;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            int col = v0 + lane + 32 * half;
+            float cand = (col < Vloc) ? Ct[row][lane + 32 * half] : REC_NEG_INF;
+            float tau = __shfl_sync(0xffffffffu, lv[r], topk - 1);
+            unsigned mask = __ballot_sync(0xffffffffu, cand > tau);
+            while (mask) {
+              int l = __ffs(mask) - 1;
+              mask &= mask - 1;
+              float cv = __shfl_sync(0xffffffffu, cand, l);
+              int ci = vocab_lo + v0 + l + 32 * half;
+              tau = __shfl_sync(0xffffffffu, lv[r], topk - 1);
+              if (cv > tau) {
+                int pos = __popc(__ballot_sync(0xffffffffu, lv[r] >= cv));
+                float uv = __shfl_up_sync(0xffffffffu, lv[r], 1);
+                int ui = __shfl_up_sync(0xffffffffu, li[r], 1);
+                if (lane > pos) { lv[r] = uv; li[r] = ui; }
+                if (lane == pos) { lv[r] = cv; li[r] = ci; }
+                if (lane >= topk) { lv[r] = REC_NEG_INF; li[r] = 0x7fffffff; }
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (n_arg > 0) {
+      float q[4][4];
+      for (int hq = 0; hq < n_arg; ++hq) {
+        logits_tile(As, Bs, h, b0, B, hp.w[1 + hq], v0, Vloc, D, tid, ty, tx, acc);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int col = v0 + tx + 16 * c;
+          float bias = col < Vloc ? __ldg(hp.b[1 + hq] + col) : 0.f;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            float val = acc[a][c] + bias;
+            if (n_arg > 1) val *= wq[hq];  // get_weighted_q_target: sum_h q_h * w_h in head order
+            q[a][c] = (hq == 0) ? val : q[a][c] + val;
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float bv = REC_NEG_INF;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int col = v0 + tx + 16 * c;
+          if (col < Vloc && better(q[a][c], vocab_lo + col, bv, bi)) { bv = q[a][c]; bi = vocab_lo + col; }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (better(bv, bi, av[a], ai[a])) { av[a] = bv; ai[a] = bi; }
+      }
+    }
+  }
+  // publish partials
+  if (tx == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int row = b0 + ty + 16 * a;
+      if (row < B) {
+        float *o = part + ((int64_t)sp * B + row) * part_stride;
+        o[0] = m_run[a]; o[1] = s_run[a]; o[3] = av[a]; o[4] = __int_as_float(ai[a]);
+      }
+    }
+  }
+  // the target logit lives in exactly one lane of the 16: reduce with max
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float tv = tgt[a];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) tv = fmaxf(tv, __shfl_xor_sync(0xffffffffu, tv, o));
+    int row = b0 + ty + 16 * a;
+    if (tx == 0 && row < B) part[((int64_t)sp * B + row) * part_stride + 2] = tv;
+  }
+  if (topk > 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int row = b0 + warp * 8 + r;
+      if (row < B && lane < topk) {
+        float *o = part + ((int64_t)sp * B + row) * part_stride + PART_TOPK_OFF;
+        o[lane] = lv[r];
+        o[REC_MAX_TOPK + lane] = __int_as_float(li[r]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Merge of n_split partial records per row (one warp per row).
+// row_stats[b] = {lse, target_logit, argmax_val, argmax_id(bits), ce_row, max, sumexp, -}
+// ------------------------------------------------------------------------------------------------
+#define ROW_STRIDE 8
+__global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict__ part, int part_stride, int n_split,
+                                                         int B, int topk, int has_stats, int has_arg,
+                                                         float *__restrict__ row_stats, int32_t *__restrict__ row_ids,
+                                                         float *__restrict__ row_topv, int32_t *__restrict__ astar) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  float *rs = row_stats + (int64_t)row * ROW_STRIDE;
+  if (has_stats) {
+    float m = REC_NEG_INF, tg = REC_NEG_INF;
+    for (int sp = lane; sp < n_split; sp += 32) {
+      const float *o = part + ((int64_t)sp * B + row) * part_stride;
+      m = fmaxf(m, o[0]);
+      tg = fmaxf(tg, o[2]);
+    }
+    m = warp_max(m);
+    tg = warp_max(tg);
+    float ssum = 0.f;
+    for (int sp = lane; sp < n_split; sp += 32) {
+      const float *o = part + ((int64_t)sp * B + row) * part_stride;
+      if (o[1] > 0.f) ssum += o[1] * __expf(o[0] - m);
+    }
+    ssum = warp_sum(ssum);
+    if (lane == 0) {
+      float lse = m + logf(ssum);
+      rs[0] = lse; rs[1] = tg; rs[4] = lse - tg; rs[5] = m; rs[6] = ssum;
+    }
+  }
+  if (has_arg) {
+    float bv = REC_NEG_INF;
+    int bi = 0x7fffffff;
+    for (int sp = lane; sp < n_split; sp += 32) {
+      const float *o = part + ((int64_t)sp * B + row) * part_stride;
+      float v = o[3];
+      int i = __float_as_int(o[4]);
+      if (better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { rs[2] = bv; rs[3] = __int_as_float(bi); astar[row] = bi; }
+  }
+  if (topk > 0) {
+    // K selection rounds over n_split*topk candidates; "taken" = not after the last pick in the order
+    float lastv = 3.402823466e+38f;
+    int lasti = -1;
+    const int n = n_split * topk;
+    for (int k = 0; k < topk; ++k) {
+      float bv = REC_NEG_INF;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < n; c += 32) {
+        int sp = c / topk, j = c - sp * topk;
+        const float *o = part + ((int64_t)sp * B + row) * part_stride + PART_TOPK_OFF;
+        float v = o[j];
+        int i = __float_as_int(o[REC_MAX_TOPK + j]);
+        if (i != 0x7fffffff && better(lastv, lasti, v, i) && better(v, i, bv, bi)) { bv = v; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv; }
+      lastv = bv; lasti = bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plain logits (API compatibility with `model(s, lengths)`): logits[b, v] = h[b].W[v] + bias[v].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_logits_kernel(const float *__restrict__ W, const float *__restrict__ bias,
+                                                          const float *__restrict__ h, int B, int D, int Vloc,
+                                                          float *__restrict__ out, int64_t ld) {
+  __shared__ __align__(16) float As[TM][KP];
+  __shared__ __align__(16) float Bs[TN][KP];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int v0 = blockIdx.x * TN, b0 = blockIdx.y * TM;
+  float acc[4][4];
+  logits_tile(As, Bs, h, b0, B, W, v0, Vloc, D, tid, ty, tx, acc);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int row = b0 + ty + 16 * a;
+    if (row >= B) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int col = v0 + tx + 16 * c;
+      if (col < Vloc) out[(int64_t)row * ld + col] = acc[a][c] + __ldg(bias + col);
+    }
+  }
+}
+
+// out[b, j] = h[b] . W_{first+j}[id_b - vocab_lo] + bias (0 when the row is on another shard).
+__global__ void __launch_bounds__(256) row_dots_kernel(HeadPtrs hp, const float *__restrict__ h,
+                                                       const int64_t *__restrict__ ids64,
+                                                       const int32_t *__restrict__ ids32, int B, int D, int Vloc,
+                                                       int vocab_lo, int first, int n, float *__restrict__ out,
+                                                       int out_stride) {
+  const int lane = threadIdx.x & 31;
+  const int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wi >= B * n) return;
+  const int b = wi / n, j = wi - b * n;
+  int64_t id = ids64 ? ids64[b] : (int64_t)ids32[b];
+  int64_t loc = id - vocab_lo;
+  float acc = 0.f;
+  if (loc >= 0 && loc < Vloc) {
+    const float *wr = hp.w[first + j] + loc * D;
+    const float *hr = h + (int64_t)b * D;
+    for (int k = lane; k < D; k += 32) acc = fmaf(hr[k], __ldg(wr + k), acc);
+    acc = warp_sum(acc);
+    acc += __ldg(hp.b[first + j] + loc);
+  }
+  if (lane == 0) out[(int64_t)b * out_stride + j] = acc;
+}
+
+// dh_q[b, :] = sum_j dq[b, j] * W_{1+j}[a_b]  (Q heads only touch row a_b) -- runs BEFORE Adam.
+__global__ void __launch_bounds__(256) q_dh_kernel(HeadPtrs hp, const int64_t *__restrict__ a,
+                                                   const float *__restrict__ dq, int B, int D, int Vloc, int vocab_lo,
+                                                   int n_q, float *__restrict__ dh_slice) {
+  const int b = blockIdx.x;
+  int64_t loc = a[b] - vocab_lo;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    float acc = 0.f;
+    if (loc >= 0 && loc < Vloc)
+      for (int j = 0; j < n_q; ++j) acc = fmaf(dq[b * 3 + j], __ldg(hp.w[1 + j] + loc * D + k), acc);
+    dh_slice[(int64_t)b * D + k] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward + Adam.  grid = (n_cta, n_heads), block 256, dynamic smem.  blockIdx.y = head.
+//   head 0     : dense path (recompute logits, dlogits, dW/db, dh partial)
+//   heads >= 1 : sparse path (only rows a_b carry gradient dq[b,head-1] * h[b])
+// Every CTA then applies Adam to the [64, D] weight tile + bias it owns.  Persistent over tiles.
+// ------------------------------------------------------------------------------------------------
+struct HeadTrainPtrs {
+  float *w[REC_MAX_HEADS], *wm[REC_MAX_HEADS], *wv[REC_MAX_HEADS];
+  float *b[REC_MAX_HEADS], *bm[REC_MAX_HEADS], *bv[REC_MAX_HEADS];
+};
+
+__device__ __forceinline__ void adam1(float &p, float &m, float &v, float g, float b1, float b2, float eps,
+                                      float step_size, float bc2_sqrt) {
+  m = m + (g - m) * (1.f - b1);
+  v = v * b2 + ((1.f - b2) * g) * g;
+  p = p + (-step_size * m) / (sqrtf(v) / bc2_sqrt + eps);
+}
+
+__global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, const float *__restrict__ h,
+                                                            const int64_t *__restrict__ target,
+                                                            const float *__restrict__ row_stats,
+                                                            const float *__restrict__ dq, int B, int D, int Vloc,
+                                                            int vocab_lo, int n_tiles, float inv_B,
+                                                            float *__restrict__ dh_part, float b1, float b2,
+                                                            float eps, float step_size, float bc2_sqrt) {
+  extern __shared__ __align__(16) float dyn[];
+  const int DP = D + 4;
+  float *dW = dyn;                                   // [TN][DP]
+  float *db = dW + TN * DP;                          // [TN]
+  float(*As)[KP] = reinterpret_cast<float(*)[KP]>(db + TN);     // [TM][KP]
+  float(*Bs)[KP] = As + TM;                                      // [TN][KP]
+  float(*DL)[TN + 4] = reinterpret_cast<float(*)[TN + 4]>(Bs + TN);   // [TM][TN+4]  dl[m][n]
+  float(*DLT)[TM + 4] = reinterpret_cast<float(*)[TM + 4]>(DL + TM);  // [TN][TM+4]  dl[n][m]
+  float(*Hc)[TN + 4] = reinterpret_cast<float(*)[TN + 4]>(DLT + TN);  // [64][68] h chunk / W chunk
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int head = blockIdx.y;
+  float *__restrict__ W = hp.w[head];
+  float *dh_slice = dh_part + (int64_t)blockIdx.x * B * D;
+  bool first_tile = true;
+
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int v0 = t * TN;
+    for (int i = tid; i < TN * DP; i += 256) dW[i] = 0.f;
+    if (tid < TN) db[tid] = 0.f;
+    __syncthreads();
+    if (head == 0) {
+      for (int b0 = 0; b0 < B; b0 += TM) {
+        float acc[4][4];
+        logits_tile(As, Bs, h, b0, B, W, v0, Vloc, D, tid, ty, tx, acc);
+        // dlogits tile
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          int m = ty + 16 * a, row = b0 + m;
+          float lse = row < B ? row_stats[(int64_t)row * ROW_STRIDE] : 0.f;
+          int64_t trow = row < B ? target[row] - vocab_lo : -1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            int n = tx + 16 * c, col = v0 + n;
+            float dl = 0.f;
+            if (row < B && col < Vloc) {
+              float l = acc[a][c] + __ldg(hp.b[0] + col);
+              dl = (__expf(l - lse) - ((int64_t)col == trow ? 1.f : 0.f)) * inv_B;
+            }
+            DL[m][n] = dl;
+            DLT[n][m] = dl;
+          }
+        }
+        __syncthreads();
+        if (tid < TN) {
+          float sacc = 0.f;
+          for (int m = 0; m < TM; ++m) sacc += DL[m][tid];
+          db[tid] += sacc;
+        }
+        for (int d0 = 0; d0 < D; d0 += 64) {
+          // ---- dW[n][d0+kd] += sum_m dl[m][n] * h[b0+m][d0+kd] ----
+          for (int e = tid; e < 64 * 16; e += 256) {
+            int r = e >> 4, c4 = e & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + r < B && d0 + c4 * 4 < D) v = __ldg(reinterpret_cast<const float4 *>(h + (int64_t)(b0 + r) * D + d0) + c4);
+            *reinterpret_cast<float4 *>(&Hc[r][c4 * 4]) = v;
+          }
+          __syncthreads();
+          {
+            float g[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) g[i][j] = 0.f;
+#pragma unroll 8
+            for (int m = 0; m < TM; ++m) {
+              float4 a4 = *reinterpret_cast<const float4 *>(&DL[m][ty * 4]);
+              float4 b4 = *reinterpret_cast<const float4 *>(&Hc[m][tx * 4]);
+              float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[i][j] = fmaf(av[i], bv[j], g[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                int kd = d0 + tx * 4 + j;
+                if (kd < D) dW[(ty * 4 + i) * DP + kd] += g[i][j];
+              }
+          }
+          __syncthreads();
+          // ---- dh[b0+m][d0+kd] (+)= sum_n dl[m][n] * W[v0+n][d0+kd] ----
+          for (int e = tid; e < 64 * 16; e += 256) {
+            int r = e >> 4, c4 = e & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v0 + r < Vloc && d0 + c4 * 4 < D) v = *(reinterpret_cast<const float4 *>(W + (int64_t)(v0 + r) * D + d0) + c4);
+            *reinterpret_cast<float4 *>(&Hc[r][c4 * 4]) = v;
+          }
+          __syncthreads();
+          {
+            float g[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) g[i][j] = 0.f;
+#pragma unroll 8
+            for (int n = 0; n < TN; ++n) {
+              float4 a4 = *reinterpret_cast<const float4 *>(&DLT[n][ty * 4]);
+              float4 b4 = *reinterpret_cast<const float4 *>(&Hc[n][tx * 4]);
+              float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[i][j] = fmaf(av[i], bv[j], g[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              int row = b0 + ty * 4 + i;
+              if (row >= B) continue;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                int kd = d0 + tx * 4 + j;
+                if (kd < D) {
+                  float *dst = dh_slice + (int64_t)row * D + kd;
+                  *dst = first_tile ? g[i][j] : (*dst + g[i][j]);
+                }
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+    } else {
+      // sparse rows: deterministic order over b
+      for (int b = 0; b < B; ++b) {
+        int64_t loc = target[b] - vocab_lo - v0;
+        if (loc >= 0 && loc < TN && v0 + loc < Vloc) {
+          float g = dq[b * 3 + head - 1];
+          for (int k = tid; k < D; k += 256) dW[(int)loc * DP + k] += g * h[(int64_t)b * D + k];
+          if (tid == 0) db[loc] += g;
+        }
+      }
+      __syncthreads();
+    }
+    first_tile = false;
+    // ---- Adam on the tile (coalesced over d) ----
+    const int D4 = D >> 2;
+    for (int e = tid; e < TN * D4; e += 256) {
+      int n = e / D4, c4 = e - n * D4;
+      if (v0 + n >= Vloc) continue;
+      int64_t off = ((int64_t)(v0 + n) * D >> 2) + c4;
+      float4 p = reinterpret_cast<float4 *>(W)[off];
+      float4 m = reinterpret_cast<float4 *>(hp.wm[head])[off];
+      float4 v = reinterpret_cast<float4 *>(hp.wv[head])[off];
+      const float *g = dW + n * DP + c4 * 4;
+      adam1(p.x, m.x, v.x, g[0], b1, b2, eps, step_size, bc2_sqrt);
+      adam1(p.y, m.y, v.y, g[1], b1, b2, eps, step_size, bc2_sqrt);
+      adam1(p.z, m.z, v.z, g[2], b1, b2, eps, step_size, bc2_sqrt);
+      adam1(p.w, m.w, v.w, g[3], b1, b2, eps, step_size, bc2_sqrt);
+      reinterpret_cast<float4 *>(W)[off] = p;
+      reinterpret_cast<float4 *>(hp.wm[head])[off] = m;
+      reinterpret_cast<float4 *>(hp.wv[head])[off] = v;
+    }
+    if (tid < TN && v0 + tid < Vloc) {
+      float p = hp.b[head][v0 + tid], m = hp.bm[head][v0 + tid], v = hp.bv[head][v0 + tid];
+      adam1(p, m, v, db[tid], b1, b2, eps, step_size, bc2_sqrt);
+      hp.b[head][v0 + tid] = p; hp.bm[head][v0 + tid] = m; hp.bv[head][v0 + tid] = v;
+    }
+    __syncthreads();
+  }
+  // a CTA of the dense head that owned no tile must still define its dh slice
+  if (head == 0 && first_tile)
+    for (int64_t i = tid; i < (int64_t)B * D; i += 256) dh_slice[i] = 0.f;
+}
+
+// dh[b,d] = sum over slices (fixed order)
+__global__ void dh_reduce_kernel(const float *__restrict__ dh_part, int n_slices, int64_t n, float *__restrict__ dh) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int s = 0; s < n_slices; ++s) acc += dh_part[(int64_t)s * n + i];
+  dh[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+static HeadPtrs head_ptrs(const rec_engine *e, int net_id) {
+  HeadPtrs hp;
+  for (int i = 0; i < REC_MAX_HEADS; ++i) { hp.w[i] = e->nets[net_id].p.head_w[i]; hp.b[i] = e->nets[net_id].p.head_b[i]; }
+  return hp;
+}
+
+int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
+  const int n_tiles = cdiv(e->Vloc, TN), nb = cdiv(a.B, TM);
+  int n_split = cdiv(2 * e->sm_count, nb);
+  if (n_split > n_tiles) n_split = n_tiles;
+  if (n_split > e->n_split_max) n_split = e->n_split_max;
+  if (n_split < 1) n_split = 1;
+  // make every split non-empty
+  int per = cdiv(n_tiles, n_split);
+  n_split = cdiv(n_tiles, per);
+  dim3 grid(n_split, nb);
+  head_stats_kernel<<<grid, 256, 0, e->stream>>>(head_ptrs(e, a.net_id), a.h, a.B, e->D, e->Vloc, e->cfg.vocab_lo, n_tiles,
+                                                a.do_stats, a.stats_head, a.target, a.topk, a.n_arg, a.w[0], a.w[1],
+                                                a.w[2], e->part, e->part_stride);
+  REC_LAUNCH_CHECK(e);
+  *n_split_out = n_split;
+  return REC_OK;
+}
+
+int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats, bool has_arg) {
+  head_merge_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(part, e->part_stride, n_split, B, topk, has_stats ? 1 : 0,
+                                                      has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv, e->astar);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld) {
+  dim3 grid(cdiv(e->Vloc, TN), cdiv(B, TM));
+  const rec_net_params &p = e->nets[net_id].p;
+  head_logits_kernel<<<grid, 256, 0, e->stream>>>(p.head_w[head], p.head_b[head], h, B, e->D, e->Vloc, logits, ld);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+int launch_row_dots(rec_engine *e, int net_id, const float *h, const int64_t *ids, const int32_t *ids32, int B,
+                    int first_head, int n, float *out) {
+  row_dots_kernel<<<cdiv(B * n, 8), 256, 0, e->stream>>>(head_ptrs(e, net_id), h, ids, ids32, B, e->D, e->Vloc,
+                                                        e->cfg.vocab_lo, first_head, n, out, 3);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+size_t head_bwd_smem_bytes(int D) {
+  return sizeof(float) * ((size_t)TN * (D + 4) + TN + 2 * TM * KP + TM * (TN + 4) + TN * (TM + 4) + 64 * (TN + 4));
+}
+
+int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                              float bc2_sqrt, const rec_train_hparams *hp, float inv_B) {
+  const rec_net_params &p = e->nets[net_id].p;
+  HeadTrainPtrs t;
+  for (int i = 0; i < REC_MAX_HEADS; ++i) {
+    t.w[i] = p.head_w[i]; t.wm[i] = p.head_w_m[i]; t.wv[i] = p.head_w_v[i];
+    t.b[i] = p.head_b[i]; t.bm[i] = p.head_b_m[i]; t.bv[i] = p.head_b_v[i];
+  }
+  const int n_tiles = cdiv(e->Vloc, TN);
+  const int n_q = e->cfg.n_heads - 1;
+  int n_cta = e->n_dh_part - 1;
+  if (n_cta > n_tiles) n_cta = n_tiles;
+  size_t smem = head_bwd_smem_bytes(e->D);
+  if (smem > 220 * 1024) REC_FAIL(e, REC_EINVAL, "head backward needs %zu B of shared memory (D=%d too large)", smem, e->D);
+  static bool attr_set = false;
+  if (!attr_set) {
+    REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  // Q heads: dh contribution of rows a_b, computed before Adam touches W (slice index n_cta)
+  float *q_slice = e->dh_part + (int64_t)n_cta * B * e->D;
+  if (n_q > 0) {
+    q_dh_kernel<<<B, 128, 0, e->stream>>>(head_ptrs(e, net_id), b->a, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo, n_q, q_slice);
+    REC_LAUNCH_CHECK(e);
+  }
+  if (e->timing) cudaEventRecord(e->ev[0], e->stream);
+  dim3 grid(n_cta, e->cfg.n_heads);
+  head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
+                                                      n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
+                                                      step_size, bc2_sqrt);
+  REC_LAUNCH_CHECK(e);
+  if (e->timing) cudaEventRecord(e->ev[1], e->stream);
+  int64_t n = (int64_t)B * e->D;
+  dh_reduce_kernel<<<(int)cdiv64(n, 256), 256, 0, e->stream>>>(e->dh_part, n_cta + (n_q > 0 ? 1 : 0), n, e->dh);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}

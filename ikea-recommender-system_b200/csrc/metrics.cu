@@ -1,0 +1,230 @@
+// Small fused kernels around the heads: SMORL online rewards, double-Q TD target/loss, and the
+// on-device evaluation metrics (HR/NDCG@k, coverage bitmaps, diversity, novelty, repetitions).
+//
+// Reference semantics: evaluate/diversity.py:4-73, evaluate/novelty.py:12-47,
+// evaluate/eval_protocol.py:26-100,123-263, evaluate/coverage.py:24-74,
+// evaluate/repetitiveness.py:21-57, models/SQN/sqn_gru.py:231-245, models/SMORL/smorl_gru.py:291-325,
+// utils/tensor_operations.py:36-47.
+#include "common.cuh"
+
+#define ROW_STRIDE 8
+
+__device__ __forceinline__ int last_action_of(const int64_t *s, const int64_t *lens, int b, int L, int N,
+                                              int pad_pos_end) {
+  int64_t it;
+  if (pad_pos_end) {
+    int64_t l = lens[b];
+    l = l < 1 ? 1 : (l > L ? L : l);
+    it = s[(int64_t)b * L + (l - 1)];
+  } else {
+    it = s[(int64_t)b * L + (L - 1)];
+  }
+  return (int)(it < 0 ? 0 : (it > N ? N : it));
+}
+
+// 1 - mean_j cos(E[last], E[map(id_j)]), j < k   (CosineSimilarity(dim=2, eps=1e-6)); warp-cooperative
+__device__ __forceinline__ float diversity_reward_warp(const float *__restrict__ E, int dim, int last,
+                                                       const int32_t *ids, int k, const int64_t *out_to_in,
+                                                       int N, int lane) {
+  const float eps = 1e-6f;
+  const float *x = E + (int64_t)last * dim;
+  float nx = 0.f;
+  for (int d = lane; d < dim; d += 32) nx = fmaf(x[d], x[d], nx);
+  nx = fmaxf(sqrtf(warp_sum(nx)), eps);
+  float sim_sum = 0.f;
+  for (int j = 0; j < k; ++j) {
+    int64_t id = ids[j];
+    if (out_to_in) id = out_to_in[id];
+    id = id < 0 ? 0 : (id > N ? N : id);
+    const float *y = E + id * dim;
+    float ny = 0.f, dot = 0.f;
+    for (int d = lane; d < dim; d += 32) { ny = fmaf(y[d], y[d], ny); dot = fmaf(x[d], y[d], dot); }
+    ny = fmaxf(sqrtf(warp_sum(ny)), eps);
+    dot = warp_sum(dot);
+    sim_sum += dot / (nx * ny);
+  }
+  return 1.f - sim_sum / (float)k;
+}
+
+// ---- training-time rewards + TD target + Q loss gradient ------------------------------------------
+// One warp per row.  rewards r = [r_acc, r_div, r_nov] (SMORL, n_q = 3) or [r] (SQN, n_q = 1).
+__global__ void __launch_bounds__(256) td_kernel(int B, int L, int N, int n_q, const float *__restrict__ r_acc,
+                                                 const uint8_t *__restrict__ is_end,
+                                                 const float *__restrict__ q_sa, const float *__restrict__ q_boot,
+                                                 const int64_t *__restrict__ s, const int64_t *__restrict__ div_lens,
+                                                 const int32_t *__restrict__ row_ids, rec_train_hparams hp,
+                                                 float alpha_eff, float *__restrict__ dq,
+                                                 float *__restrict__ q_loss_rows, float *__restrict__ rewards) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float r[3] = {r_acc[b], 0.f, 0.f};
+  if (n_q == 3) {
+    const int32_t *ids = row_ids + (int64_t)b * REC_MAX_TOPK;
+    int last = last_action_of(s, div_lens, b, L, N, hp.pad_pos_end);
+    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, N, lane);
+    float nov = 0.f;
+    for (int j = 0; j < hp.topk_nov; ++j) nov += hp.unpopular[ids[j]] ? hp.nov_reward : 0.f;
+    r[2] = nov / (float)hp.topk_nov;
+  }
+  if (lane == 0) {
+    const bool end = is_end[b] != 0;
+    float loss = 0.f;
+    for (int j = 0; j < n_q; ++j) {
+      float boot = end ? 0.f : q_boot[b * 3 + j];
+      float y = r[j] + hp.gamma * boot;
+      float diff = y - q_sa[b * 3 + j];
+      float w = (n_q == 3) ? hp.q_weights[j] : 1.f;
+      loss += diff * diff * w;
+      dq[b * 3 + j] = alpha_eff * w * 2.f * (-diff) / (float)B;
+      rewards[b * 3 + j] = r[j];
+    }
+    q_loss_rows[b] = loss;
+  }
+}
+
+// out[0] = mean(ce_row), out[1] = mean(q_loss_rows): single CTA, fixed-order tree (deterministic)
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float *__restrict__ row_stats,
+                                                          const float *__restrict__ q_loss_rows, int B,
+                                                          float *__restrict__ out) {
+  __shared__ float sh[2][256];
+  float a = 0.f, q = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    a += row_stats[(int64_t)b * ROW_STRIDE + 4];
+    if (q_loss_rows) q += q_loss_rows[b];
+  }
+  sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh[0][0] / (float)B; out[1] = sh[1][0] / (float)B; }
+}
+
+// ---- evaluation metrics ----------------------------------------------------------------------------
+// One warp per row -> per-row metric record rowm[b][0..M): hits[n_k], ndcg[n_k], reps[n_k], div, nov, ce
+__global__ void __launch_bounds__(256) eval_rows_kernel(int B, int L, int N, int V, const int64_t *__restrict__ s,
+                                                        const int64_t *__restrict__ a,
+                                                        const int64_t *__restrict__ lens,
+                                                        const int32_t *__restrict__ row_ids,
+                                                        const float *__restrict__ row_stats, rec_eval_opts o,
+                                                        int kmax, uint32_t *__restrict__ cov_bits, int cov_words,
+                                                        double *__restrict__ rowm, int M) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int32_t *ids = row_ids + (int64_t)b * REC_MAX_TOPK;
+  const int my = lane < kmax ? ids[lane] : -1;
+  double *out = rowm + (int64_t)b * M;
+  // HR / NDCG: rank of the true action inside the top-k list
+  const int64_t truth = a[b];
+  unsigned hit = __ballot_sync(0xffffffffu, lane < kmax && (int64_t)my == truth);
+  int pos = hit ? (__ffs(hit) - 1) : 1 << 30;
+  // repetitions: matches between every state token and the (remapped) top-k ids
+  int64_t mapped = my;
+  if (my >= 0 && o.out_to_in) mapped = o.out_to_in[my];
+  int reps[REC_MAX_KLIST];
+#pragma unroll
+  for (int i = 0; i < REC_MAX_KLIST; ++i) reps[i] = 0;
+  for (int t = 0; t < L; ++t) {
+    int64_t sv = s[(int64_t)b * L + t];
+    unsigned mm = __ballot_sync(0xffffffffu, my >= 0 && mapped == sv);
+#pragma unroll
+    for (int i = 0; i < REC_MAX_KLIST; ++i)
+      if (i < o.n_k) reps[i] += __popc(mm & (o.ks[i] >= 32 ? 0xffffffffu : ((1u << o.ks[i]) - 1u)));
+  }
+  // coverage bitmaps (integer OR: order independent)
+  for (int i = 0; i < o.n_cov; ++i)
+    if (lane < o.cov_ks[i] && my >= 0) atomicOr(cov_bits + (int64_t)i * cov_words + (my >> 5), 1u << (my & 31));
+  // diversity / novelty
+  float div = 0.f;
+  if (o.div_emb) {
+    int last = last_action_of(s, lens, b, L, N, o.pad_pos_end);
+    div = diversity_reward_warp(o.div_emb, o.div_dim, last, ids, o.topk_div, o.out_to_in, N, lane);
+  }
+  if (lane == 0) {
+    for (int i = 0; i < o.n_k; ++i) {
+      bool in = pos < o.ks[i];
+      out[i] = in ? 1.0 : 0.0;
+      out[o.n_k + i] = in ? 1.0 / log2((double)pos + 2.0) : 0.0;
+      out[2 * o.n_k + i] = (double)reps[i];
+    }
+    double nov = 0.0;
+    if (o.unpopular) {
+      int cnt = 0;
+      for (int j = 0; j < o.topk_nov; ++j) cnt += o.unpopular[ids[j]] ? 1 : 0;
+      nov = (double)cnt * (double)o.nov_reward / (double)o.topk_nov;
+    }
+    out[3 * o.n_k] = (double)div;
+    out[3 * o.n_k + 1] = nov;
+    out[3 * o.n_k + 2] = (double)row_stats[(int64_t)b * ROW_STRIDE + 4];
+  }
+}
+
+// column sums of rowm in a fixed order, added to the sweep accumulators. grid = M, block 256.
+__global__ void __launch_bounds__(256) eval_reduce_kernel(const double *__restrict__ rowm, int B, int M, int n_k,
+                                                          rec_eval_accum acc) {
+  __shared__ double sh[256];
+  const int m = blockIdx.x;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < B; b += 256) v += rowm[(int64_t)b * M + m];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double tot = sh[0];
+    if (m < n_k) acc.hits[m] += tot;
+    else if (m < 2 * n_k) acc.ndcg[m - n_k] += tot;
+    else if (m < 3 * n_k) acc.reps[m - 2 * n_k] += tot;
+    else if (m == 3 * n_k) acc.div_sum[0] += tot;
+    else if (m == 3 * n_k + 1) acc.nov_sum[0] += tot;
+    else acc.loss_sum[0] += tot / (double)B;  // mean of batch means (eval_protocol.py:182,250)
+  }
+}
+
+__global__ void copy_topk_kernel(const int32_t *__restrict__ row_ids, const float *__restrict__ row_topv, int B,
+                                 int kmax, int32_t *__restrict__ ids_out, float *__restrict__ sc_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * kmax) return;
+  int b = i / kmax, j = i - b * kmax;
+  if (ids_out) ids_out[i] = row_ids[(int64_t)b * REC_MAX_TOPK + j];
+  if (sc_out) sc_out[i] = row_topv[(int64_t)b * REC_MAX_TOPK + j];
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_td(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int n_q, float alpha_eff,
+              float *q_loss_rows) {
+  td_kernel<<<cdiv(b->B, 8), 256, 0, e->stream>>>(b->B, e->cfg.state_size, e->cfg.item_num, n_q, b->r, b->is_end, e->q_sa,
+                                                 e->q_boot, b->s, b->true_next_len, e->row_ids, *hp, alpha_eff, e->dq,
+                                                 q_loss_rows, e->rewards);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+int launch_loss_reduce(rec_engine *e, int B, const float *q_loss_rows, float *out) {
+  loss_reduce_kernel<<<1, 256, 0, e->stream>>>(e->row_stats, q_loss_rows, B, out);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+int launch_eval_metrics(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, int kmax,
+                        const rec_eval_accum *acc, double *rowm, int32_t *topk_ids, float *topk_scores) {
+  const int M = 3 * o->n_k + 3;
+  const int cov_words = (e->cfg.action_dim + 31) / 32;
+  eval_rows_kernel<<<cdiv(b->B, 8), 256, 0, e->stream>>>(b->B, e->cfg.state_size, e->cfg.item_num, e->cfg.action_dim, b->s,
+                                                        b->a, b->true_len, e->row_ids, e->row_stats, *o, kmax,
+                                                        acc->cov_bits, cov_words, rowm, M);
+  REC_LAUNCH_CHECK(e);
+  eval_reduce_kernel<<<M, 256, 0, e->stream>>>(rowm, b->B, M, o->n_k, *acc);
+  REC_LAUNCH_CHECK(e);
+  if (topk_ids || topk_scores) {
+    copy_topk_kernel<<<cdiv(b->B * kmax, 256), 256, 0, e->stream>>>(e->row_ids, e->row_topv, b->B, kmax, topk_ids,
+                                                                   topk_scores);
+    REC_LAUNCH_CHECK(e);
+  }
+  return REC_OK;
+}

@@ -1,0 +1,213 @@
+"""Python handle around one native engine (one per GPU / process).
+
+PyTorch is plumbing here: it owns the device memory of parameters / optimizer state / batches and
+the CUDA stream; every computation is a call through the C ABI (`_native.py`).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class NetTensors:
+    """Flat view of one net's parameters (+ optional Adam state) in the engine's order."""
+
+    def __init__(self, emb, w_ih, w_hh, b_ih, b_hh, head_w, head_b):
+        self.emb = emb
+        self.w_ih, self.w_hh, self.b_ih, self.b_hh = list(w_ih), list(w_hh), list(b_ih), list(b_hh)
+        self.head_w, self.head_b = list(head_w), list(head_b)
+        self.m: Optional["NetTensors"] = None
+        self.v: Optional["NetTensors"] = None
+
+    def all(self) -> List[torch.Tensor]:
+        return [self.emb, *self.w_ih, *self.w_hh, *self.b_ih, *self.b_hh, *self.head_w, *self.head_b]
+
+    def zeros_like(self) -> "NetTensors":
+        z = torch.zeros_like
+        return NetTensors(z(self.emb), [z(t) for t in self.w_ih], [z(t) for t in self.w_hh],
+                          [z(t) for t in self.b_ih], [z(t) for t in self.b_hh],
+                          [z(t) for t in self.head_w], [z(t) for t in self.head_b])
+
+    def signature(self):
+        sig = tuple(t.data_ptr() for t in self.all())
+        if self.m is not None:
+            sig += tuple(t.data_ptr() for t in self.m.all()) + tuple(t.data_ptr() for t in self.v.all())
+        return sig
+
+
+class Engine:
+    """One native engine: static shapes + workspace.  Grows (re-creates) when a larger batch arrives."""
+
+    def __init__(self, *, item_num, action_dim, embedding_dim, hidden_dim, state_size, bidirectional,
+                 n_heads, n_nets, use_packed_seq, frozen_pad_row, device, max_batch=256, max_topk=N.REC_MAX_TOPK,
+                 vocab_lo=0, vocab_hi=None):
+        self.lib = N.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"the B200 engine runs on CUDA devices only (got device={device!r}); "
+                               "there is no CPU fallback")
+        self.cfg = dict(item_num=int(item_num), action_dim=int(action_dim), embedding_dim=int(embedding_dim),
+                        hidden_dim=int(hidden_dim), state_size=int(state_size), bidirectional=int(bool(bidirectional)),
+                        n_heads=int(n_heads), n_nets=int(n_nets), use_packed_seq=int(bool(use_packed_seq)),
+                        frozen_pad_row=int(frozen_pad_row), max_batch=int(max_batch), vocab_lo=int(vocab_lo),
+                        vocab_hi=int(action_dim if vocab_hi is None else vocab_hi), max_topk=int(max_topk))
+        self.handle = None
+        self._bound: Dict[int, tuple] = {}
+        self._nets: Dict[int, NetTensors] = {}
+        self._adam_steps: Dict[int, int] = {}
+        self._keep = []  # keeps ctypes structs / tensors of the last call alive
+        self._create()
+
+    # -- lifetime ----------------------------------------------------------------------------
+    def _create(self):
+        cfg = N.RecConfig(**self.cfg)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            rc = self.lib.rec_create(C.byref(cfg), C.c_void_p(stream), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"rec_create failed (rc={rc}): {N.last_error(self.lib, None)}")
+        self.handle = h
+        self._stream = stream
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.rec_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def max_batch(self):
+        return self.cfg["max_batch"]
+
+    def ensure_batch(self, B: int):
+        if B <= self.cfg["max_batch"]:
+            return
+        steps = {i: int(self.lib.rec_get_adam_step(self.handle, i)) for i in self._nets}
+        self.close()
+        self.cfg["max_batch"] = int(max(B, 2 * self.cfg["max_batch"]))
+        self._create()
+        self._bound.clear()
+        for i, nt in self._nets.items():
+            self.bind(i, nt, force=True)
+            self.lib.rec_set_adam_step(self.handle, i, steps[i])
+
+    # -- parameters --------------------------------------------------------------------------
+    def bind(self, net_id: int, nt: NetTensors, force: bool = False):
+        self._nets[net_id] = nt
+        sig = nt.signature()
+        if not force and self._bound.get(net_id) == sig:
+            return
+        for t in nt.all():
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("engine parameters must be contiguous fp32 tensors on the engine's device")
+        p = N.RecNetParams()
+        p.emb = nt.emb.data_ptr()
+        if nt.m is not None:
+            p.emb_m, p.emb_v = nt.m.emb.data_ptr(), nt.v.emb.data_ptr()
+        for name in ("w_ih", "w_hh", "b_ih", "b_hh", "head_w", "head_b"):
+            for i, t in enumerate(getattr(nt, name)):
+                getattr(p, name)[i] = t.data_ptr()
+                if nt.m is not None:
+                    getattr(p, name + "_m")[i] = getattr(nt.m, name)[i].data_ptr()
+                    getattr(p, name + "_v")[i] = getattr(nt.v, name)[i].data_ptr()
+        N.check(self.lib, self.handle, self.lib.rec_bind_params(self.handle, net_id, C.byref(p)), "rec_bind_params")
+        self._bound[net_id] = sig
+
+    def adam_step(self, net_id):
+        return int(self.lib.rec_get_adam_step(self.handle, net_id))
+
+    def set_adam_step(self, net_id, step):
+        self.lib.rec_set_adam_step(self.handle, net_id, int(step))
+
+    # -- calls -------------------------------------------------------------------------------
+    def _batch(self, B, s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
+        b = N.RecBatch()
+        b.B = int(B)
+        b.s, b.a, b.true_len = s.data_ptr(), a.data_ptr(), true_len.data_ptr()
+        if r is not None:
+            b.r, b.s_next = r.data_ptr(), s_next.data_ptr()
+            b.true_next_len, b.is_end = true_next_len.data_ptr(), is_end.data_ptr()
+        return b
+
+    def forward_state(self, net_id, s, lengths):
+        B = s.shape[0]
+        self.ensure_batch(B)
+        D = self.cfg["hidden_dim"] * (2 if self.cfg["bidirectional"] else 1)
+        h = torch.empty(B, D, device=self.device, dtype=torch.float32)
+        N.check(self.lib, self.handle,
+                self.lib.rec_forward_state(self.handle, net_id, _ptr(s), _ptr(lengths), B, _ptr(h)),
+                "rec_forward_state")
+        return h
+
+    def head_logits(self, net_id, head, h):
+        B = h.shape[0]
+        V = self.cfg["vocab_hi"] - self.cfg["vocab_lo"]
+        out = torch.empty(B, V, device=self.device, dtype=torch.float32)
+        N.check(self.lib, self.handle,
+                self.lib.rec_head_logits(self.handle, net_id, head, _ptr(h), B, _ptr(out), V), "rec_head_logits")
+        return out
+
+    def train_step_supervised(self, batch: N.RecBatch, hp: N.RecTrainHparams, loss_out: torch.Tensor):
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_step_supervised(self.handle, C.byref(batch), C.byref(hp), _ptr(loss_out)),
+                "rec_train_step_supervised")
+
+    def train_step_q(self, batch: N.RecBatch, hp: N.RecTrainHparams, main_net: int, losses_out: torch.Tensor):
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_step_q(self.handle, C.byref(batch), C.byref(hp), main_net, _ptr(losses_out)),
+                "rec_train_step_q")
+
+    def eval_batch(self, net_id, batch: N.RecBatch, opts: N.RecEvalOpts, acc: N.RecEvalAccum, topk_ids=None,
+                   topk_scores=None):
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_eval_batch(self.handle, net_id, C.byref(batch), C.byref(opts), C.byref(acc),
+                                        _ptr(topk_ids), _ptr(topk_scores)), "rec_eval_batch")
+
+    def launch_count(self):
+        return int(self.lib.rec_launch_count(self.handle))
+
+    def enable_kernel_timing(self, on=True):
+        self.lib.rec_enable_kernel_timing(self.handle, int(on))
+
+    def last_kernel_ms(self, which):
+        return float(self.lib.rec_last_kernel_ms(self.handle, which))
+
+
+class EvalAccumulators:
+    """Device accumulators of one evaluation sweep (zeroed at construction)."""
+
+    def __init__(self, device, action_dim):
+        self.words = (action_dim + 31) // 32
+        self.f64 = torch.zeros(3 * N.REC_MAX_KLIST + 3, dtype=torch.float64, device=device)
+        self.cov = torch.zeros(N.REC_MAX_KLIST * self.words, dtype=torch.int32, device=device)
+        K = N.REC_MAX_KLIST
+        base = self.f64.data_ptr()
+        self.struct = N.RecEvalAccum(hits=base, ndcg=base + 8 * K, reps=base + 16 * K, div_sum=base + 24 * K,
+                                     nov_sum=base + 24 * K + 8, loss_sum=base + 24 * K + 16,
+                                     cov_bits=self.cov.data_ptr())
+
+    def read(self):
+        f = self.f64.cpu().numpy()
+        K = N.REC_MAX_KLIST
+        cov = self.cov.cpu().numpy().view(np.uint32).reshape(K, self.words)
+        return dict(hits=f[:K], ndcg=f[K:2 * K], reps=f[2 * K:3 * K], div_sum=f[3 * K], nov_sum=f[3 * K + 1],
+                    loss_sum=f[3 * K + 2], cov_bits=cov)

@@ -1,0 +1,301 @@
+"""Shared host logic of the drop-in model / trainer classes.
+
+The classes in `recommenders/models/*` keep the reference package's names, constructor arguments,
+attributes and `state_dict()` keys; none of them computes anything in PyTorch.  The nn.Embedding /
+nn.GRU / nn.Linear sub-modules exist only as *parameter containers* (same names, same seeded init
+order as the reference => identical `state_dict`), their storage is handed to the native engine by
+pointer.  `forward`, `train_step`, `evaluate` are calls through the C ABI.
+"""
+
+from __future__ import annotations
+
+import random
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from ..engine import Engine, NetTensors
+
+ADAM_BETAS = (0.9, 0.999)
+ADAM_EPS = 1e-8
+
+
+class NativeSessionNet(nn.Module):
+    """embedding -> GRU -> heads, executed by the native engine.
+
+    family: "gru4rec" | "bidir" | "sqn" | "smorl" | "bidir_sqn"
+    """
+
+    _TRUNK = {"gru4rec": "gru", "bidir": "gru", "sqn": "base_model", "smorl": "base_model", "bidir_sqn": "base_model"}
+    _HEADS = {
+        "gru4rec": ["output"],
+        "bidir": ["output"],
+        "sqn": ["sup_head_output", "q_head_output"],
+        "bidir_sqn": ["sup_head_output", "q_head_output"],
+        "smorl": ["sup_head_output", "q_head_acc", "q_head_div", "q_head_nov"],
+    }
+
+    def _build(self, family, hidden_dim, embedding_dim, item_num, state_size, action_dim, gru_layers,
+               use_packed_seq, train_pad_embed, padding_idx, dropout=0.0):
+        self._family = family
+        self.hidden_dim = hidden_dim
+        self.embedding_dim = embedding_dim
+        self.item_num = int(item_num)
+        self.state_size = state_size
+        self.action_dim = action_dim
+        self.use_packed_seq = use_packed_seq
+        self.gru_layers = gru_layers
+        self._bidirectional = family in ("bidir", "bidir_sqn")
+        rl = family in ("sqn", "smorl", "bidir_sqn")
+        pad = self.item_num if padding_idx is None else padding_idx
+        if rl and use_packed_seq:
+            train_pad_embed = True  # sqn_gru.py:46-47
+        self._frozen_pad_row = -1 if train_pad_embed else int(pad)
+        # parameter containers -- construction order == reference (seeded init is bit-identical)
+        self.embedding = nn.Embedding(self.item_num + 1, embedding_dim, padding_idx=None if train_pad_embed else pad)
+        self.embedding.weight.data.normal_(mean=0, std=0.01)
+        if not train_pad_embed:
+            with torch.no_grad():
+                self.embedding.weight[pad] = torch.zeros(embedding_dim)
+        trunk = nn.GRU(input_size=embedding_dim, hidden_size=hidden_dim, num_layers=gru_layers, bias=True,
+                       batch_first=True, bidirectional=self._bidirectional)
+        setattr(self, self._TRUNK[family], trunk)
+        if family == "bidir":
+            self.dropout = nn.Dropout(p=dropout)
+        d = hidden_dim * (2 if self._bidirectional else 1)
+        for name in self._HEADS[family]:
+            setattr(self, name, nn.Linear(in_features=d, out_features=action_dim))
+        for p in self.parameters():
+            p.requires_grad_(False)  # gradients never exist as tensors: Adam is fused into the kernels
+        self._engine: Optional[Engine] = None
+        self._net_id = 0
+        self._opt_m: Optional[NetTensors] = None
+        self._opt_v: Optional[NetTensors] = None
+
+    # -- engine plumbing -------------------------------------------------------------------
+    @property
+    def _trunk(self) -> nn.GRU:
+        return getattr(self, self._TRUNK[self._family])
+
+    def _head_modules(self) -> List[nn.Linear]:
+        return [getattr(self, n) for n in self._HEADS[self._family]]
+
+    def _net_tensors(self) -> NetTensors:
+        g = self._trunk
+        sfx = ["", "_reverse"] if self._bidirectional else [""]
+        nt = NetTensors(
+            self.embedding.weight.data,
+            [getattr(g, f"weight_ih_l0{s}").data for s in sfx], [getattr(g, f"weight_hh_l0{s}").data for s in sfx],
+            [getattr(g, f"bias_ih_l0{s}").data for s in sfx], [getattr(g, f"bias_hh_l0{s}").data for s in sfx],
+            [h.weight.data for h in self._head_modules()], [h.bias.data for h in self._head_modules()])
+        nt.m, nt.v = self._opt_m, self._opt_v
+        return nt
+
+    def _param_device(self):
+        return self.embedding.weight.device
+
+    def _attach(self, engine: Engine, net_id: int):
+        self._engine, self._net_id = engine, net_id
+
+    def _ready(self, batch_hint: int = 256) -> Engine:
+        dev = self._param_device()
+        if dev.type != "cuda":
+            raise RuntimeError("this model executes on a B200 through the native engine; move it to a CUDA "
+                               "device first (model.to('cuda') / trainer.send_to_device()). No CPU fallback.")
+        if self._engine is None or self._engine.device != dev:
+            self._engine = Engine(item_num=self.item_num, action_dim=self.action_dim,
+                                  embedding_dim=self.embedding_dim, hidden_dim=self.hidden_dim,
+                                  state_size=self.state_size, bidirectional=self._bidirectional,
+                                  n_heads=len(self._HEADS[self._family]), n_nets=1,
+                                  use_packed_seq=self.use_packed_seq, frozen_pad_row=self._frozen_pad_row,
+                                  device=dev, max_batch=max(256, batch_hint))
+            self._net_id = 0
+        self._engine.bind(self._net_id, self._net_tensors())
+        return self._engine
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        if self._engine is not None:  # GRU transposes inside the engine are stale now
+            self._engine.bind(self._net_id, self._net_tensors(), force=True)
+        return out
+
+    def _dev_inputs(self, s, lengths):
+        dev = self._param_device()
+        if not isinstance(lengths, torch.Tensor):
+            lengths = torch.as_tensor(lengths)
+        if self.use_packed_seq and lengths.device.type == "cpu" and bool((lengths <= 0).any()):
+            # same failure mode as pack_padded_sequence in the reference forward
+            raise RuntimeError("Length of all samples has to be greater than 0, but found an element in "
+                               "'lengths' that is <= 0")
+        s = s.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        lengths = lengths.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        return s, lengths
+
+    def final_state(self, s, lengths):
+        eng = self._ready(int(s.shape[0]))
+        s, lengths = self._dev_inputs(s, lengths)
+        return eng.forward_state(self._net_id, s, lengths)
+
+    def _all_logits(self, s, lengths):
+        eng = self._ready(int(s.shape[0]))
+        s, lengths = self._dev_inputs(s, lengths)
+        h = eng.forward_state(self._net_id, s, lengths)
+        if self._family == "bidir" and self.training and self.dropout.p > 0:
+            raise NotImplementedError("BidirGRU4Rec dropout > 0 in training mode is not implemented natively yet")
+        return [eng.head_logits(self._net_id, i, h) for i in range(len(self._HEADS[self._family]))]
+
+    def forward(self, s, lengths):
+        outs = self._all_logits(s, lengths)
+        if len(outs) == 1:
+            return outs[0]
+        if len(outs) == 2:
+            return outs[0], outs[1]
+        return outs[0], torch.stack(outs[1:], dim=1)
+
+
+# ---------------------------------------------------------------------------------------------
+class BatchStager:
+    """Packs one replay-buffer batch into a pinned host buffer and ships it with ONE H2D copy."""
+
+    def __init__(self, device, L, depth=4):
+        self.device, self.L, self.depth = device, L, depth
+        self.cap = 0
+        self.slots = []
+        self.i = 0
+        self.h2d_bytes = 0
+
+    def _alloc(self, B):
+        self.cap = B
+        n64 = B * (2 * self.L + 3)
+        self.nbytes = n64 * 8 + B * 4 + B
+        self.nbytes = (self.nbytes + 15) // 16 * 16
+        self.slots = []
+        for _ in range(self.depth):
+            host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+            dev = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+            self.slots.append((host, dev, torch.cuda.Event()))
+
+    def _views(self, buf, B):
+        L = self.L
+        i64 = buf[: B * (2 * L + 3) * 8].view(torch.int64)
+        o = 0
+        s = i64[o:o + B * L].view(B, L); o += B * L
+        sn = i64[o:o + B * L].view(B, L); o += B * L
+        a = i64[o:o + B]; o += B
+        ln = i64[o:o + B]; o += B
+        nl = i64[o:o + B]; o += B
+        off = B * (2 * L + 3) * 8
+        r = buf[off: off + 4 * B].view(torch.float32)
+        e = buf[off + 4 * B: off + 5 * B]
+        return s, sn, a, ln, nl, r, e
+
+    def stage(self, s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
+        B = int(s.shape[0])
+        if s.is_cuda:  # already resident: no staging, just dtype/contiguity
+            f = lambda t, dt: None if t is None else t.to(device=self.device, dtype=dt).contiguous()
+            return (f(s, torch.int64), f(s_next, torch.int64), f(a, torch.int64), f(true_len, torch.int64),
+                    f(true_next_len, torch.int64), f(r, torch.float32),
+                    None if is_end is None else is_end.to(device=self.device, dtype=torch.uint8).contiguous())
+        if B > self.cap:
+            self._alloc(B)
+        host, dev, ev = self.slots[self.i]
+        self.i = (self.i + 1) % self.depth
+        ev.synchronize()  # the copy that last used this slot has finished
+        hs, hsn, ha, hln, hnl, hr, he = self._views(host, B)
+        hs.copy_(s); ha.copy_(a); hln.copy_(true_len)
+        if r is not None:
+            hsn.copy_(s_next); hnl.copy_(true_next_len); hr.copy_(r.reshape(-1)); he.copy_(is_end)
+        n = B * (2 * self.L + 3) * 8 + 5 * B
+        dev[:n].copy_(host[:n], non_blocking=True)
+        ev.record()
+        self.h2d_bytes = n
+        ds, dsn, da, dln, dnl, dr, de = self._views(dev, B)
+        if r is None:
+            return ds, None, da, dln, None, None, None
+        return ds, dsn, da, dln, dnl, dr, de
+
+
+def make_hparams(lr, gamma=0.0, alpha=1.0, q_weights=(1.0, 0.0, 0.0)):
+    hp = N.RecTrainHparams()
+    hp.lr, hp.beta1, hp.beta2, hp.eps = lr, ADAM_BETAS[0], ADAM_BETAS[1], ADAM_EPS
+    hp.gamma, hp.alpha = gamma, alpha
+    for i in range(3):
+        hp.q_weights[i] = float(q_weights[i]) if i < len(q_weights) else 0.0
+    hp.pad_pos_end = 1
+    return hp
+
+
+class NativeTrainerBase:
+    """Owns the engine, the twin nets' Adam state and the batch stager."""
+
+    def _setup(self, nets: List[NativeSessionNet], device, learning_rate, torch_rand_seed=None, python_rand_seed=None):
+        self._nets = nets
+        self.device = device
+        self.learning_rate = learning_rate
+        self.cross_entropy_loss = nn.CrossEntropyLoss(weight=None, reduction="mean")
+        self._engine: Optional[Engine] = None
+        self._stager: Optional[BatchStager] = None
+        self._loss_dev = None
+        self._pending_steps = [0 for _ in nets]
+
+    @staticmethod
+    def _seed(torch_rand_seed, python_rand_seed):
+        torch.manual_seed(torch_rand_seed)
+        random.seed(python_rand_seed)
+
+    def send_to_device(self):
+        for n in self._nets:
+            n.to(self.device)
+        self._engine = None  # pointers changed
+
+    def _ready(self, B) -> Engine:
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"device={self.device!r}: the native trainers run on a B200 only (no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if self._nets[0]._param_device() != dev:
+            for n in self._nets:
+                n.to(dev)
+            self._engine = None
+        if self._engine is None:
+            n0 = self._nets[0]
+            self._engine = Engine(item_num=n0.item_num, action_dim=n0.action_dim, embedding_dim=n0.embedding_dim,
+                                  hidden_dim=n0.hidden_dim, state_size=n0.state_size,
+                                  bidirectional=n0._bidirectional, n_heads=len(n0._HEADS[n0._family]),
+                                  n_nets=len(self._nets), use_packed_seq=n0.use_packed_seq,
+                                  frozen_pad_row=n0._frozen_pad_row, device=dev, max_batch=max(256, B))
+            for i, n in enumerate(self._nets):
+                if n._opt_m is None or n._opt_m.emb.device != dev:
+                    base = n._net_tensors()
+                    n._opt_m, n._opt_v = base.zeros_like(), base.zeros_like()
+                n._attach(self._engine, i)
+                self._engine.bind(i, n._net_tensors(), force=True)
+                self._engine.set_adam_step(i, self._pending_steps[i])
+            self._stager = BatchStager(dev, n0.state_size)
+            self._loss_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+        else:
+            for i, n in enumerate(self._nets):
+                self._engine.bind(i, n._net_tensors())
+        return self._engine
+
+    def _set_mode(self, train: bool):
+        for n in self._nets:
+            n.train(train)
+
+    def set_train(self):
+        self._set_mode(True)
+
+    def set_eval(self):
+        self._set_mode(False)
+
+    # optimizer state for checkpoint/resume (the reference never saves it; offered as an extension)
+    def optimizer_state(self):
+        out = []
+        for i, n in enumerate(self._nets):
+            step = self._engine.adam_step(i) if self._engine is not None else self._pending_steps[i]
+            out.append(dict(step=step, exp_avg=None if n._opt_m is None else [t.clone() for t in n._opt_m.all()],
+                            exp_avg_sq=None if n._opt_v is None else [t.clone() for t in n._opt_v.all()]))
+        return out

@@ -1,0 +1,161 @@
+"""Drop-in for `recommenders/evaluate/eval_protocol.py` (reference :123-359): `evaluate` and
+`update_train_metrics` with the reference's keyword arguments and return types, executed on the B200.
+
+One fused pass per batch (GRU forward -> head GEMM with running top-k and online log-sum-exp ->
+metric kernels) replaces the reference's forward + five `torch.topk` calls + a B x V device-to-host copy;
+only accumulators, coverage bitmaps and (for update_train_metrics) the [B, k] id list leave the GPU.
+Top-k order is (score desc, id asc) -- `torch.topk` leaves ties unspecified.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ... import _native as N
+from ...engine import EvalAccumulators
+
+_cache = {}
+
+
+def _as_div_table(diversity_embedding, device):
+    """Frozen nn.Embedding (or tensor) -> contiguous fp32 table on `device` (cached by storage)."""
+    w = diversity_embedding.weight if hasattr(diversity_embedding, "weight") else diversity_embedding
+    key = ("div", w.data_ptr(), str(device))
+    if key not in _cache:
+        _cache[key] = (w, w.detach().to(device=device, dtype=torch.float32).contiguous())
+    return _cache[key][1]
+
+
+def _unpopular_bitmap(unpopular_actions_set, action_dim, device):
+    """python set -> uint8[V] membership table on the device (novelty.py:5-9 `in unpopular_items`)."""
+    key = ("unpop", id(unpopular_actions_set), len(unpopular_actions_set), action_dim, str(device))
+    if key not in _cache:
+        bm = np.zeros(action_dim, dtype=np.uint8)
+        ids = np.fromiter((int(i) for i in unpopular_actions_set), dtype=np.int64, count=len(unpopular_actions_set))
+        ids = ids[(ids >= 0) & (ids < action_dim)]
+        bm[ids] = 1
+        _cache[key] = (unpopular_actions_set, torch.from_numpy(bm).to(device))
+    return _cache[key][1]
+
+
+def _token_lut(input_tokenizer, output_tokenizer, action_dim, device):
+    """`input_tokenizer.stoi(output_tokenizer.itos(x))` (diversity.py:55-60) as an int64[V] table."""
+    if input_tokenizer is None:
+        return None
+    key = ("lut", id(input_tokenizer), id(output_tokenizer), action_dim, str(device))
+    if key not in _cache:
+        lut = np.fromiter((input_tokenizer.stoi(output_tokenizer.itos(x)) for x in range(action_dim)),
+                          dtype=np.int64, count=action_dim)
+        _cache[key] = ((input_tokenizer, output_tokenizer), torch.from_numpy(lut).to(device))
+    return _cache[key][1]
+
+
+def _opts(model, device, head_idx, topk_hr_ndcg, topk_div, topk_nov, topk_cov, nov_rew, padding_pos,
+          diversity_embedding, unpopular_actions_set, input_tokenizer, output_tokenizer):
+    if len(topk_hr_ndcg) > N.REC_MAX_KLIST or len(topk_cov) > N.REC_MAX_KLIST:
+        raise ValueError(f"at most {N.REC_MAX_KLIST} entries per top-k list")
+    kmax = max([*topk_hr_ndcg, *topk_cov, topk_div, topk_nov])
+    if kmax > N.REC_MAX_TOPK:
+        raise ValueError(f"top-k up to {N.REC_MAX_TOPK} is supported, got {kmax}")
+    o = N.RecEvalOpts()
+    o.head_idx = head_idx
+    o.n_k = len(topk_hr_ndcg)
+    for i, k in enumerate(topk_hr_ndcg):
+        o.ks[i] = int(k)
+    o.n_cov = len(topk_cov)
+    for i, k in enumerate(topk_cov):
+        o.cov_ks[i] = int(k)
+    o.topk_div, o.topk_nov, o.nov_reward = int(topk_div), int(topk_nov), float(nov_rew)
+    div = _as_div_table(diversity_embedding, device)
+    unpop = _unpopular_bitmap(unpopular_actions_set, model.action_dim, device)
+    lut = _token_lut(input_tokenizer, output_tokenizer, model.action_dim, device)
+    o.div_emb, o.div_dim = div.data_ptr(), int(div.shape[1])
+    o.unpopular = unpop.data_ptr()
+    o.out_to_in = None if lut is None else lut.data_ptr()
+    o.pad_pos_end = 1 if padding_pos == "end" else 0
+    return o, kmax, (div, unpop, lut)
+
+
+def _check_loss(loss_function):
+    if loss_function is not None and not isinstance(loss_function, torch.nn.CrossEntropyLoss):
+        raise NotImplementedError("the fused evaluation computes nn.CrossEntropyLoss(reduction='mean') only")
+
+
+def get_preds(states, true_len, model, head_idx):
+    """reference :103-120 (materialises logits; API compatibility only)."""
+    out = model(states, true_len)
+    return out[head_idx] if isinstance(out, tuple) else out
+
+
+def _coverage(cov_bits, topk_cov, unpop_bitmap_np, num_actions, n_unpop):
+    res = {}
+    for i, k in enumerate(topk_cov):
+        bits = np.unpackbits(cov_bits[i].view(np.uint8), bitorder="little")[:num_actions]
+        res[k] = (int((bits & unpop_bitmap_np).sum()) / n_unpop, int(bits.sum()) / num_actions)
+    return res
+
+
+def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, diversity_embedding,
+             unpopular_actions_set, head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1,
+             topk_to_consider_nov=1, topk_to_consider_cov=[1, 5, 10], novelty_rew_signal=1, input_tokenizer=None,
+             output_tokenizer=None):
+    """Returns (loss, hr, ndcg, coverage_res, avg_diversity_rew, avg_novelty_rew, repetitions) with the
+    reference's types: torch scalar, np.ndarray, np.ndarray, {k: (unpop_cov, all_cov)}, torch scalar,
+    np.float64, np.ndarray."""
+    _check_loss(loss_function)
+    model.eval()
+    eng = model._ready()
+    dev = model._param_device()
+    o, kmax, keep = _opts(model, dev, head_idx, topk_hr_ndcg, topk_to_consider_div, topk_to_consider_nov,
+                          topk_to_consider_cov, novelty_rew_signal, padding_pos, diversity_embedding,
+                          unpopular_actions_set, input_tokenizer, output_tokenizer)
+    acc = EvalAccumulators(dev, model.action_dim)
+    n_total, n_batches = 0, 0
+    for s, a, s_len in evaluation_data_loader:
+        B = int(s.shape[0])
+        ds, dl = model._dev_inputs(s, s_len)
+        da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        eng = model._ready(B)
+        eng.eval_batch(model._net_id, eng._batch(B, ds, da, dl), o, acc.struct)
+        n_total += B
+        n_batches += 1
+    r = acc.read()
+    nk = len(topk_hr_ndcg)
+    hr = r["hits"][:nk] / n_total
+    ndcg = r["ndcg"][:nk] / n_total
+    reps = r["reps"][:nk] / n_total
+    loss = torch.tensor(r["loss_sum"] / n_batches, dtype=torch.float32, device=dev)
+    avg_div = torch.tensor(r["div_sum"] / n_total, dtype=torch.float32, device=dev)
+    avg_nov = np.float64(r["nov_sum"] / n_total)
+    unpop_np = keep[1].cpu().numpy()
+    cov = _coverage(r["cov_bits"], topk_to_consider_cov, unpop_np, model.action_dim, len(unpopular_actions_set))
+    return loss, hr, ndcg, cov, avg_div, avg_nov, reps
+
+
+def update_train_metrics(s, a, s_len, model, device, padding_pos, diversity_embedding, unpopular_actions_set,
+                         actions_covered_topk_dict, head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1,
+                         topk_to_consider_nov=1, topk_to_consider_cov=[1, 5, 10], novelty_rew_signal=1,
+                         input_tokenizer=None, output_tokenizer=None):
+    """One batch (reference :266-359): returns (hr_batch, ndcg_batch, actions_covered_topk_dict,
+    batch_div_rew, batch_nov_rew, batch_repetitions) -- sums, not means."""
+    model.eval()
+    B = int(s.shape[0])
+    eng = model._ready(B)
+    dev = model._param_device()
+    o, kmax, keep = _opts(model, dev, head_idx, topk_hr_ndcg, topk_to_consider_div, topk_to_consider_nov,
+                          topk_to_consider_cov, novelty_rew_signal, padding_pos, diversity_embedding,
+                          unpopular_actions_set, input_tokenizer, output_tokenizer)
+    acc = EvalAccumulators(dev, model.action_dim)
+    ds, dl = model._dev_inputs(s, s_len)
+    da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+    ids = torch.empty(B, kmax, dtype=torch.int32, device=dev)
+    eng.eval_batch(model._net_id, eng._batch(B, ds, da, dl), o, acc.struct, topk_ids=ids)
+    r = acc.read()
+    nk = len(topk_hr_ndcg)
+    ids_h = ids.cpu().numpy()
+    for k in topk_to_consider_cov:  # python sets, as the reference returns them (coverage.py:46-51)
+        actions_covered_topk_dict[k] = actions_covered_topk_dict[k].union(ids_h[:, :k].flatten().tolist())
+    div = torch.tensor(r["div_sum"], dtype=torch.float32, device=dev)
+    return (r["hits"][:nk].copy(), r["ndcg"][:nk].copy(), actions_covered_topk_dict, div, np.float64(r["nov_sum"]),
+            r["reps"][:nk].copy())

@@ -1,0 +1,207 @@
+/*
+ * recsys_b200.h -- C ABI of the B200-native GRU4Rec / BidirGRU4Rec / SQN / SMORL hot path.
+ *
+ * Drop-in boundary for the PyTorch path of adam-walsh-data/IKEA-Recommender-System
+ * (`recommenders/`).  The reference is pure Python: the "FFI" a maintainer would add is a
+ * ctypes binding; each entry point below cites the reference interface
+ * it replaces (paths relative to the reference root, `recommenders/...`).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is DEVICE memory owned by the caller
+ *     (the engine owns only its opaque handle + private workspace);
+ *   - all calls are asynchronous on the `stream` given at creation (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream) unless documented otherwise;
+ *   - return 0 on success, negative REC_E* on failure, never throws across the ABI; the message
+ *     is available from rec_last_error();
+ *   - not thread-safe per handle; one handle per (GPU, process);
+ *   - no CPU fallback: rec_create fails unless the device is compute capability 10.x.
+ *
+ * Tensor layouts are PyTorch's: embedding [N+1,E]; weight_ih [3H,E], weight_hh [3H,H], biases [3H]
+ * with gate order (r,z,n); head weight [V,D], bias [V]; all fp32, contiguous.  Index tensors are
+ * int64 exactly as the reference's DataLoader yields them.
+ */
+#ifndef RECSYS_B200_H
+#define RECSYS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REC_ABI_VERSION 1
+#define REC_MAX_HEADS 4   /* supervised + up to 3 Q heads (SMORL) */
+#define REC_MAX_NETS 2    /* double-Q twins */
+#define REC_MAX_TOPK 32   /* largest k of any top-k consumer */
+#define REC_MAX_KLIST 8   /* entries in topk_hr_ndcg / topk_cov lists */
+
+#define REC_OK 0
+#define REC_EINVAL (-22)
+#define REC_ENOMEM (-12)
+#define REC_ENODEV (-19)
+#define REC_ECUDA (-5)
+
+typedef struct rec_engine rec_engine; /* opaque */
+
+/* Static shape of one model family.
+ * Replaces the constructor arguments of GRU4Rec / BidirGRU4Rec / SQN_Network / SMORL_GRU_Net
+ * (models/GRU4Rec/model.py:6-60, models/BidirGRU4Rec/model.py:7-68, models/SQN/sqn_gru.py:10-85,
+ *  models/SMORL/smorl_gru.py:14-102). */
+typedef struct rec_config {
+  int32_t item_num;       /* N; the embedding table has N+1 rows */
+  int32_t action_dim;     /* V, global vocabulary of every head */
+  int32_t embedding_dim;  /* E (multiple of 4) */
+  int32_t hidden_dim;     /* H (multiple of 4) */
+  int32_t state_size;     /* L */
+  int32_t bidirectional;  /* 0 | 1 ; D = H * (1 + bidirectional) */
+  int32_t n_heads;        /* 1 supervised only | 2 SQN (sup,q) | 4 SMORL (sup,q_acc,q_div,q_nov) */
+  int32_t n_nets;         /* 1 | 2 (double-Q twins) */
+  int32_t use_packed_seq; /* 1: final state after exactly len tokens (pack_padded_sequence) */
+  int32_t frozen_pad_row; /* -1: every embedding row trainable; else row that never gets gradient */
+  int32_t max_batch;      /* largest B of any later call */
+  int32_t vocab_lo;       /* head rows [vocab_lo, vocab_hi) live on this engine (vocabulary shard); */
+  int32_t vocab_hi;       /*   0 / V for an unsharded engine                                          */
+  int32_t max_topk;       /* largest k any call will ask for (<= REC_MAX_TOPK) */
+} rec_config;
+
+/* Parameter + Adam-state pointers of one net (nn.Module.state_dict() of the reference modules;
+ * Adam state of torch.optim.Adam(lr) as in sqn_gru.py:173-181).  Head pointers address the LOCAL
+ * shard rows [vocab_lo,vocab_hi).  m/v may be NULL for a net that is only evaluated. */
+typedef struct rec_net_params {
+  float *emb, *emb_m, *emb_v;                            /* [N+1,E] */
+  float *w_ih[2], *w_ih_m[2], *w_ih_v[2];                /* [3H,E]  per direction */
+  float *w_hh[2], *w_hh_m[2], *w_hh_v[2];                /* [3H,H] */
+  float *b_ih[2], *b_ih_m[2], *b_ih_v[2];                /* [3H] */
+  float *b_hh[2], *b_hh_m[2], *b_hh_v[2];                /* [3H] */
+  float *head_w[REC_MAX_HEADS], *head_w_m[REC_MAX_HEADS], *head_w_v[REC_MAX_HEADS]; /* [Vloc,D] */
+  float *head_b[REC_MAX_HEADS], *head_b_m[REC_MAX_HEADS], *head_b_v[REC_MAX_HEADS]; /* [Vloc] */
+} rec_net_params;
+
+/* One replay-buffer batch, the tuple of ikea/data_utils/replay_buffer.py:65-74 (device copies). */
+typedef struct rec_batch {
+  int32_t B;
+  const int64_t *s;              /* [B,L] */
+  const int64_t *a;              /* [B] */
+  const float *r;                /* [B]   offline accuracy reward (NULL for supervised) */
+  const int64_t *s_next;         /* [B,L] (NULL for supervised) */
+  const int64_t *true_len;       /* [B] */
+  const int64_t *true_next_len;  /* [B] (NULL for supervised) */
+  const uint8_t *is_end;         /* [B] bool (NULL for supervised) */
+} rec_batch;
+
+/* Hyper-parameters of a train step: Adam defaults of torch.optim.Adam (betas .9/.999, eps 1e-8);
+ * gamma / q_weights / alpha of sqn_gru.py:238-245 and smorl_gru.py:317-325. */
+typedef struct rec_train_hparams {
+  float lr, beta1, beta2, eps;
+  float gamma;
+  float alpha;        /* SMORL: loss = sup + alpha*q ; SQN: loss = q + sup (alpha ignored, =1) */
+  float q_weights[3]; /* SMORL scalarisation weights w (SQN: {1,0,0}) */
+  /* SMORL online rewards (evaluate/diversity.py:15-73, evaluate/novelty.py:12-47) */
+  const float *div_emb;        /* frozen E_div [N+1, div_dim] */
+  int32_t div_dim;
+  int32_t topk_div, topk_nov;
+  float nov_reward;
+  const uint8_t *unpopular;    /* bitmap-as-bytes [V]: 1 if action id is in the unpopular set */
+  const int64_t *out_to_in;    /* optional LUT [V]: output-token id -> input-token id (NULL = identity) */
+  int32_t pad_pos_end;         /* 1: "end" padding (last action = s[len-1]); 0: "beg" (s[L-1]) */
+} rec_train_hparams;
+
+/* Options of one evaluation sweep: the keyword arguments of evaluate()/update_train_metrics()
+ * (evaluate/eval_protocol.py:123-139, 266-284). */
+typedef struct rec_eval_opts {
+  int32_t head_idx;                  /* which head's logits are scored (0 = supervised) */
+  int32_t n_k, ks[REC_MAX_KLIST];    /* topk_hr_ndcg */
+  int32_t n_cov, cov_ks[REC_MAX_KLIST]; /* topk_to_consider_cov */
+  int32_t topk_div, topk_nov;
+  float nov_reward;
+  const float *div_emb;
+  int32_t div_dim;
+  const uint8_t *unpopular;          /* [V] */
+  const int64_t *out_to_in;          /* optional [V] */
+  int32_t pad_pos_end;
+} rec_eval_opts;
+
+/* Device-side accumulators of an evaluation sweep (caller allocates, zero-initialises). */
+typedef struct rec_eval_accum {
+  double *hits;        /* [REC_MAX_KLIST] */
+  double *ndcg;        /* [REC_MAX_KLIST] */
+  double *reps;        /* [REC_MAX_KLIST] */
+  double *div_sum;     /* [1] */
+  double *nov_sum;     /* [1] */
+  double *loss_sum;    /* [1] sum of per-batch mean CE (eval_protocol.py:182,250) */
+  uint32_t *cov_bits;  /* [REC_MAX_KLIST][ceil(V/32)] coverage bitmaps per k */
+} rec_eval_accum;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int rec_abi_version(void);
+/* Creates an engine on the current CUDA device. */
+int rec_create(const rec_config *cfg, void *stream, rec_engine **out);
+void rec_destroy(rec_engine *e);
+const char *rec_last_error(const rec_engine *e); /* valid until the next call on e; e may be NULL */
+
+/* Binds caller-owned parameter storage to net `net_id` (replaces holding an nn.Module). Must be
+ * called again after the caller rewrites GRU weights out-of-band (load_state_dict). */
+int rec_bind_params(rec_engine *e, int net_id, const rec_net_params *p);
+/* Number of optimizer steps taken for a net (torch.optim.Adam state['step']). */
+int rec_set_adam_step(rec_engine *e, int net_id, int64_t step);
+int64_t rec_get_adam_step(const rec_engine *e, int net_id);
+
+/* ---- forward (replaces model(s, lengths): GRU4Rec/model.py:62-82, sqn_gru.py:87-112) -------- */
+/* Final layer-0 GRU state h_out[B, D].  `lengths` is a DEVICE copy of the CPU lengths tensor. */
+int rec_forward_state(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
+                      float *h_out);
+/* Full logits of one head for the local vocabulary shard: logits[B, Vloc] (row stride ld). Only
+ * for API compatibility with `model(s, lengths)`; the hot path never materialises logits. */
+int rec_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits,
+                    int64_t ld);
+
+/* ---- training (replaces *_trainer.train_step) ----------------------------------------------- */
+/* GRU4Rec_trainer/BidirGRU4Rec_trainer.train_step (GRU4Rec/model.py:129-155): writes the batch-mean
+ * CE loss to loss_out[0] (device). */
+int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp,
+                              float *loss_out);
+/* SQN_trainer.train_step (sqn_gru.py:183-254) / SMORL_trainer.train_step (smorl_gru.py:233-334):
+ * `main_net` in {0,1} is the twin picked by the caller's python RNG (sqn_gru.py:207-216).
+ * losses_out[0] = sup_loss, losses_out[1] = q_loss (device). */
+int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
+                     float *losses_out);
+
+/* Phase-split variant of the same step for vocabulary-sharded multi-GPU runs; the caller runs the
+ * (tiny) collectives between phases.  Unsharded engines may call rec_train_step_* instead.
+ *   phase A: GRU forwards + per-shard head statistics  -> partials (engine-owned device buffer)
+ *   phase B: given the all-gathered partials of all shards, finish statistics, Q(s',a*) rows
+ *   phase C: losses, head backward + fused Adam on the shard -> partial dh (engine-owned)
+ *   phase D: given the all-reduced dh, GRU BPTT, GRU/embedding gradients + Adam */
+int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
+                      float **partials, int64_t *partials_floats);
+int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float **boot_q,
+                      int64_t *boot_q_floats);
+int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, float *losses_out, float **dh,
+                      int64_t *dh_floats);
+int rec_train_phase_d(rec_engine *e, const float *dh_reduced);
+
+/* ---- evaluation (replaces evaluate()/update_train_metrics(), eval_protocol.py:123-359) ------ */
+/* One batch: forward, fused top-k (score desc, id asc), CE, and every metric accumulated on the
+ * device.  topk_ids[B,kmax] (int32, global action ids) and topk_scores[B,kmax] may be NULL. */
+int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, const rec_eval_opts *o,
+                   const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores);
+/* Per-shard candidates for sharded evaluation: cand_scores/cand_ids [B,kmax] of the local shard
+ * plus (max, sumexp, target-logit-or--inf) per row in stats[B,3]. */
+int rec_eval_shard_candidates(rec_engine *e, int net_id, const rec_batch *b, int head_idx, int kmax,
+                              float *h_out, float *cand_scores, int32_t *cand_ids, float *stats);
+/* Merge n_shards candidate lists [n_shards,B,kmax] (+stats [n_shards,B,3]) and accumulate metrics. */
+int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, int n_shards, int kmax,
+                   const float *cand_scores, const int32_t *cand_ids, const float *stats,
+                   const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+/* Number of kernels this engine launched since creation (bench.py's gpu_launches). */
+int64_t rec_launch_count(const rec_engine *e);
+/* CUDA-event time (ms) of the most recent dominant-kernel launch when profiling is enabled. */
+int rec_enable_kernel_timing(rec_engine *e, int on);
+float rec_last_kernel_ms(rec_engine *e, int which); /* which: 0 head-bwd+adam, 1 head-fwd stats, 2 emb adam */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECSYS_B200_H */

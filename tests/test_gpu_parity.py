@@ -1,0 +1,339 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI by the
+drop-in classes, against (a) the CPU oracle on the same seeded inputs and (b) the golden fixtures
+produced from the real reference.  Tolerances: indices / top-k ids exact; loss, Q-values, parameters
+after Adam within 1e-3 relative (north_star), atol 2e-5 for near-zero parameters."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import (load_golden, sd_from_golden, rows_from_golden, assert_close, assert_state_close,
+                     synced_random, RTOL)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ATOL_P = 2e-5
+
+
+def _syn():
+    from ikea_recommender_system_b200 import synthetic
+    return synthetic
+
+
+def _batches(rows, B, steps):
+    return [_syn().as_torch_batch(rows, i * B, (i + 1) * B) for i in range(steps)]
+
+
+def _meta(g):
+    m = g["meta"]
+    return dict(item_num=int(m[0]), action_dim=int(m[1]), embedding_dim=int(m[2]), hidden_dim=int(m[3]),
+                state_size=int(m[4])), int(m[5]), int(m[6]), bool(m[7]), bool(m[8]), int(m[9])
+
+
+def test_native_library_is_loaded(pkg):
+    import ctypes
+    assert pkg.LIB.rec_abi_version() == 1
+    with open("/proc/self/maps") as f:
+        assert "librecsys_b200.so" in f.read()
+
+
+# ------------------------------------------------------------------------------------ forward
+@pytest.mark.parametrize("family,packed,E,H", [("gru4rec", True, 64, 64), ("gru4rec", False, 12, 20),
+                                                ("bidir", True, 16, 24), ("sqn", True, 64, 64),
+                                                ("smorl", True, 32, 64), ("bidir_sqn", True, 64, 64)])
+def test_forward_matches_oracle(pkg, family, packed, E, H):
+    torch.manual_seed(5)
+    N, L, B = 333, 9, 37
+    kw = dict(hidden_dim=H, embedding_dim=E, item_num=N, state_size=L, action_dim=N, gru_layers=1,
+              use_packed_seq=packed)
+    onet = oracle.SessionNet(family=family, **kw)
+    with torch.no_grad():
+        onet.embedding.weight.mul_(20.0)  # make the recurrence non-trivial
+    if family == "gru4rec":
+        net = pkg.GRU4Rec(hidden_size=H, embedding_dim=E, item_num=N, state_size=L, action_dim=N, use_packed_seq=packed)
+    elif family == "bidir":
+        net = pkg.BidirGRU4Rec(hidden_size=H, embedding_dim=E, item_num=N, state_size=L, action_dim=N, use_packed_seq=packed)
+    elif family in ("sqn", "bidir_sqn"):
+        net = pkg.SQN_Network(hidden_dim=H, item_num=N, state_size=L, action_dim=N, gamma=0.5, gru_layers=1,
+                              embedding_dim=E, use_packed_seq=packed, bidirectional=family == "bidir_sqn")
+    else:
+        net = pkg.SMORL_GRU_Net(hidden_dim=H, embedding_dim=E, item_num=N, state_size=L, action_dim=N,
+                                q_weights=torch.ones(3), gamma=0.5, use_packed_seq=packed)
+    assert list(net.state_dict().keys()) == list(onet.state_dict().keys())
+    net.load_state_dict(onet.state_dict())
+    net.to(DEV).eval()
+    onet.eval()
+    rows = _syn().make_replay_rows(B, N, L, seed=2)
+    s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
+    with torch.no_grad():
+        want = onet(s, ln)
+        h_want = onet.final_state(s, ln)
+    got = net(s, ln)
+    assert_close(net.final_state(s, ln), h_want, rtol=1e-4, atol=1e-6, what="final state")
+    if isinstance(want, tuple):
+        for g_, w_ in zip(got, want):
+            assert g_.shape == w_.shape
+            assert_close(g_, w_, rtol=1e-4, atol=1e-5, what="logits")
+    else:
+        assert_close(got, want, rtol=1e-4, atol=1e-5, what="logits")
+
+
+def test_zero_length_raises_like_pack_padded_sequence(pkg):
+    net = pkg.GRU4Rec(hidden_size=8, embedding_dim=8, item_num=10, state_size=4, action_dim=10).to(DEV)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 4, dtype=torch.long), torch.tensor([1, 0]))
+
+
+# ------------------------------------------------------------------------------------ supervised
+SUP = [("gru4rec_small", "gru4rec"), ("gru4rec_unpacked_frozenpad", "gru4rec"), ("gru4rec_2layer", "gru4rec"),
+       ("bidir_small", "bidir"), ("bidir_unpacked", "bidir")]
+
+
+@pytest.mark.parametrize("name,family", SUP)
+def test_supervised_train_steps_match_reference_fixture(pkg, name, family):
+    g = load_golden(name)
+    cfg, B, steps, packed, train_pad, layers = _meta(g)
+    kw = dict(hidden_dim=cfg["hidden_dim"], embedding_dim=cfg["embedding_dim"], gru_layers=layers,
+              train_pad_embed=train_pad, use_packed_seq=packed, learning_rate=0.01, item_num=cfg["item_num"],
+              state_size=cfg["state_size"], action_dim=cfg["action_dim"], device=DEV)
+    t = pkg.BidirGRU4Rec_trainer(dropout=0.0, **kw) if family == "bidir" else pkg.GRU4Rec_trainer(**kw)
+    # the drop-in's seeded init IS the reference's init (same RNG consumption)
+    assert_state_close(t.gru_model.state_dict(), sd_from_golden(g, "init"), rtol=0, atol=0)
+    t.send_to_device()
+    t.set_train()
+    batches = _batches(rows_from_golden(g), B, steps)
+    s, a, _, _, ln, _, _ = batches[0]
+    assert_close(t.gru_model(s, ln), g["fwd_logits0"], rtol=1e-4, atol=1e-5, what="fwd logits")
+    losses = [t.train_step(b[0], b[1], b[4]) for b in batches]
+    assert_close(losses, g["losses"], rtol=RTOL, atol=1e-6, what="losses")
+    assert_state_close(t.gru_model.state_dict(), sd_from_golden(g, "final"), rtol=RTOL, atol=ATOL_P)
+
+
+# ------------------------------------------------------------------------------------ SQN / SMORL
+@pytest.mark.parametrize("name", ["sqn_small", "sqn_unpacked", "sqn_64"])
+def test_sqn_train_steps_match_reference_fixture(pkg, name):
+    g = load_golden(name)
+    cfg, B, steps, packed, train_pad, layers = _meta(g)
+    t = pkg.SQN_trainer(hidden_dim=cfg["hidden_dim"], embedding_dim=cfg["embedding_dim"], train_pad_embed=train_pad,
+                        use_packed_seq=packed, learning_rate=0.01, item_num=cfg["item_num"],
+                        state_size=cfg["state_size"], action_dim=cfg["action_dim"], gamma=0.5, gru_layers=layers,
+                        device=DEV)
+    assert_state_close(t.DQN_1.state_dict(), sd_from_golden(g, "init1"), rtol=0, atol=0)
+    assert_state_close(t.DQN_2.state_dict(), sd_from_golden(g, "init2"), rtol=0, atol=0)
+    t.send_to_device()
+    losses, mains = [], []
+    for b in _batches(rows_from_golden(g), B, steps):
+        losses.append(t.train_step(*b))
+        mains.append(t.last_main)
+    assert mains == list(g["mains"])
+    assert_close(losses, g["losses"], rtol=RTOL, atol=1e-5, what="(sup, q) losses")
+    assert_state_close(t.DQN_1.state_dict(), sd_from_golden(g, "final1"), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.DQN_2.state_dict(), sd_from_golden(g, "final2"), rtol=RTOL, atol=ATOL_P)
+
+
+def test_smorl_train_steps_match_oracle_fixture(pkg):
+    g = load_golden("smorl_small")
+    cfg, B, steps, *_ = _meta(g)
+    unpop = set(int(i) for i in g["unpop"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.from_numpy(g["e_div"]), freeze=True)
+    t = pkg.SMORL_trainer(hidden_dim=cfg["hidden_dim"], embedding_dim=cfg["embedding_dim"], padding_pos="end",
+                          train_pad_embed=True, use_packed_seq=True, learning_rate=0.01, item_num=cfg["item_num"],
+                          state_size=cfg["state_size"], action_dim=cfg["action_dim"], gamma=0.5, gru_layers=1,
+                          q_weights=torch.tensor([1.0, 0.7, 0.4]), alpha=0.8, div_embedding=e_div,
+                          unpopular_actions_set=unpop, topk_div=3, device=DEV, topk_nov=2, nov_rew_sig=1.0)
+    assert_state_close(t.SMORL_1.state_dict(), sd_from_golden(g, "init1"), rtol=0, atol=0)
+    t.send_to_device()
+    batches = _batches(rows_from_golden(g), B, steps)
+    s, a, _, _, ln, _, _ = batches[0]
+    sup, q = t.SMORL_1(s, ln)
+    assert q.shape == (B, 3, cfg["action_dim"])
+    assert_close(sup, g["fwd_sup0"], rtol=1e-4, atol=1e-5)  # real reference net output
+    assert_close(q, g["fwd_q0"], rtol=1e-4, atol=1e-5)
+    losses, mains = [], []
+    for b in batches:
+        losses.append(t.train_step(*b))
+        mains.append(t.last_main)
+    assert mains == list(g["mains"])
+    assert_close(losses, g["losses"], rtol=RTOL, atol=1e-5, what="(sup, q) losses")
+    assert_state_close(t.SMORL_1.state_dict(), sd_from_golden(g, "final1"), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.SMORL_2.state_dict(), sd_from_golden(g, "final2"), rtol=RTOL, atol=ATOL_P)
+
+
+def test_sqn_cfg2_shapes_against_live_oracle(pkg):
+    """BASELINE cfg2 shapes (V=N=70852, B=256, L=10, E=H=64): 2 steps against the oracle run live."""
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=70852, state_size=10, action_dim=70852, gamma=0.5, gru_layers=1)
+    ref = oracle.SQNTrainer(**kw)
+    t = pkg.SQN_trainer(device=DEV, **kw)
+    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=0, atol=0)
+    t.send_to_device()
+    rows = _syn().make_replay_rows_fast(512, 70852, 10, seed=4)
+    rng = synced_random()
+    for i in range(2):
+        b = _syn().as_torch_batch(rows, i * 256, (i + 1) * 256)
+        rng.replay(); want = ref.train_step(*b)
+        rng.replay(); got = t.train_step(*b)
+        rng.advance()
+        assert t.last_main == ref.last_main
+        assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} losses")
+    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.DQN_2.state_dict(), ref.DQN_2.state_dict(), rtol=RTOL, atol=ATOL_P)
+
+
+def test_bidir_sqn_cfg3_like(pkg):
+    """cfg3 family (bidirectional trunk under the SQN heads) at a reduced catalogue, H=E=128, L=20."""
+    kw = dict(hidden_dim=128, embedding_dim=128, train_pad_embed=True, use_packed_seq=True, learning_rate=0.005,
+              item_num=3000, state_size=20, action_dim=3000, gamma=0.5, gru_layers=1)
+    ref = oracle.SQNTrainer(family="bidir_sqn", **kw)
+    t = pkg.SQN_trainer(device=DEV, bidirectional=True, **kw)
+    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=0, atol=0)
+    t.send_to_device()
+    rows = _syn().make_replay_rows(3 * 48, 3000, 20, seed=6)
+    rng = synced_random()
+    for i in range(3):
+        b = _syn().as_torch_batch(rows, i * 48, (i + 1) * 48)
+        rng.replay(); want = ref.train_step(*b)
+        rng.replay(); got = t.train_step(*b)
+        rng.advance()
+        assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} losses")
+    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.DQN_2.state_dict(), ref.DQN_2.state_dict(), rtol=RTOL, atol=ATOL_P)
+
+
+# ------------------------------------------------------------------------------------ evaluation
+def _eval_loader(rows, n, bs):
+    out = []
+    for lo in range(0, n, bs):
+        s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, lo, min(lo + bs, n))
+        out.append((s, a, ln))
+    return out
+
+
+def test_evaluate_matches_reference_fixture(pkg):
+    g = load_golden("eval_sqn64")
+    net = pkg.SQN_Network(hidden_dim=64, item_num=500, state_size=10, action_dim=500, gamma=0.5, gru_layers=1,
+                          embedding_dim=64, use_packed_seq=True)
+    net.load_state_dict(sd_from_golden(g, "net"))
+    net.to(DEV)
+    loader = _eval_loader(rows_from_golden(g), 90, 32)
+    unpop = set(int(i) for i in g["unpop"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.from_numpy(g["e_div"]), freeze=True)
+    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=3, topk_to_consider_nov=2,
+              topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+    loss, hr, ndcg, cov, div, nov, reps = pkg.evaluate(loader, net, DEV, torch.nn.CrossEntropyLoss(), "end", e_div,
+                                                       unpop, **kw)
+    assert isinstance(loss, torch.Tensor) and isinstance(hr, np.ndarray) and isinstance(cov, dict)
+    assert_close(loss, g["loss"], rtol=1e-4)
+    assert np.array_equal(hr, g["hr"]), (hr, g["hr"])
+    assert np.allclose(ndcg, g["ndcg"], rtol=1e-12)
+    assert np.array_equal(reps, g["reps"])
+    assert np.allclose([cov[k] for k in sorted(cov)], g["cov_vals"], rtol=0, atol=0)
+    assert_close(div, g["div"], rtol=1e-4)
+    assert np.isclose(nov, g["nov"], rtol=1e-12)
+    # update_train_metrics on the first batch
+    s, a, ln = loader[0]
+    out = pkg.update_train_metrics(s, a, ln, net, DEV, "end", e_div, unpop, {k: set() for k in [1, 5, 10, 20]}, **kw)
+    assert np.array_equal(out[0], g["utm_hr"]) and np.allclose(out[1], g["utm_ndcg"]) and np.array_equal(out[5], g["utm_reps"])
+    assert_close(out[3], g["utm_div"], rtol=1e-4)
+    assert np.isclose(out[4], g["utm_nov"])
+    assert all(isinstance(v, set) for v in out[2].values())
+
+
+def test_topk_ties_lowest_id_first(pkg):
+    """Exact ties: zero head weights, bias with repeated values -> logits == bias for every session."""
+    N, V, B, K = 50, 300, 70, 20
+    net = pkg.GRU4Rec(hidden_size=8, embedding_dim=8, item_num=N, state_size=5, action_dim=V)
+    rng = np.random.default_rng(0)
+    bias = torch.from_numpy(rng.integers(0, 6, size=V).astype(np.float32))
+    with torch.no_grad():
+        net.output.weight.zero_()
+        net.output.bias.copy_(bias)
+    net.to(DEV)
+    eng = net._ready(B)
+    rows = _syn().make_replay_rows(B, N, 5, seed=1)
+    s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
+    want = oracle.stable_topk(bias.repeat(B, 1), K)
+    ids = torch.empty(B, K, dtype=torch.int32, device=DEV)
+    sc = torch.empty(B, K, dtype=torch.float32, device=DEV)
+    from ikea_recommender_system_b200 import _native as N_
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    o = N_.RecEvalOpts()
+    o.head_idx, o.n_k, o.n_cov = 0, 1, 0
+    o.ks[0] = K
+    acc = EvalAccumulators(torch.device(DEV), V)
+    ds, dl = net._dev_inputs(s, ln)
+    da = (a % V).to(DEV)
+    eng.eval_batch(0, eng._batch(B, ds, da, dl), o, acc.struct, topk_ids=ids, topk_scores=sc)
+    assert torch.equal(ids.cpu().long(), want)
+    assert torch.equal(sc.cpu(), bias[want])
+
+
+def test_evaluate_large_catalog_against_live_oracle(pkg):
+    """V = 70852, one batch of 300 sessions: ids exact, metrics equal."""
+    torch.manual_seed(11)
+    N = 70852
+    onet = oracle.make_gru4rec(hidden_dim=64, embedding_dim=64, item_num=N, state_size=10, action_dim=N,
+                               gru_layers=1, use_packed_seq=True)
+    with torch.no_grad():
+        onet.embedding.weight.mul_(30.0)
+        onet.output.weight.mul_(20.0)
+    net = pkg.GRU4Rec(hidden_size=64, embedding_dim=64, item_num=N, state_size=10, action_dim=N)
+    net.load_state_dict(onet.state_dict())
+    net.to(DEV)
+    rows = _syn().make_replay_rows_fast(300, N, 10, seed=9)
+    loader = _eval_loader(rows, 300, 300)
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    torch.manual_seed(1)
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(N + 1, 16), freeze=True)
+    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=2, topk_to_consider_nov=1,
+              topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+    want = oracle.evaluate(loader, onet, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **kw)
+    got = pkg.evaluate(loader, net, DEV, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **kw)
+    assert_close(got[0], want[0], rtol=1e-4)
+    assert np.array_equal(got[1], want[1]) and np.allclose(got[2], want[2]) and np.array_equal(got[6], want[6])
+    assert got[3] == want[3]
+    assert_close(got[4], want[4], rtol=1e-4)
+    assert np.isclose(got[5], want[5])
+
+
+def test_eval_properties_at_1m_items(pkg):
+    """cfg5 size (V = 1M): size-independent properties -- sorted scores, unique ids, idempotence,
+    consistency of HR with the materialised logits of a few rows."""
+    N = 1_000_000
+    torch.manual_seed(3)
+    net = pkg.GRU4Rec(hidden_size=64, embedding_dim=64, item_num=N, state_size=10, action_dim=N)
+    with torch.no_grad():
+        net.embedding.weight.mul_(30.0)
+        net.output.weight.mul_(10.0)
+    net.to(DEV)
+    B, K = 128, 20
+    rows = _syn().make_replay_rows_fast(B, N, 10, seed=5)
+    s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
+    from ikea_recommender_system_b200 import _native as N_
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    eng = net._ready(B)
+    o = N_.RecEvalOpts()
+    o.head_idx, o.n_k, o.n_cov = 0, 1, 1
+    o.ks[0] = K
+    o.cov_ks[0] = K
+    ds, dl = net._dev_inputs(s, ln)
+    da = a.to(DEV)
+    res = []
+    for _ in range(2):
+        acc = EvalAccumulators(torch.device(DEV), N)
+        ids = torch.empty(B, K, dtype=torch.int32, device=DEV)
+        sc = torch.empty(B, K, dtype=torch.float32, device=DEV)
+        eng.eval_batch(0, eng._batch(B, ds, da, dl), o, acc.struct, topk_ids=ids, topk_scores=sc)
+        res.append((ids.cpu(), sc.cpu(), acc.read()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])  # idempotent
+    ids, sc, r = res[0]
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+    assert all(len(set(row.tolist())) == K for row in ids)
+    logits = net(s[:8], ln[:8]).cpu()
+    tv, ti = torch.topk(logits, K, dim=1)
+    assert torch.equal(ti, ids[:8].long())  # random fp32 scores: no ties
+    assert_close(sc[:8], tv, rtol=1e-5, atol=1e-5)
+    covered = int(np.unpackbits(r["cov_bits"][0].view(np.uint8)).sum())
+    assert covered == len(set(ids.flatten().tolist()))

@@ -1,0 +1,169 @@
+"""CPU suite for the host side: the C-ABI library loads and exports every symbol the header declares,
+fails loudly without a GPU, and the drop-in classes mirror the reference interface."""
+import ctypes
+import inspect
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "recsys_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rec_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from ikea_recommender_system_b200 import _native
+    declared = _declared_functions()
+    assert declared, "no functions parsed from the header"
+    assert sorted(_native.SYMBOLS) == declared  # binding table == header
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (rec_[a-z_0-9]+)", out))
+    assert set(declared) <= exported, set(declared) - exported
+    for name in declared:
+        assert hasattr(pkg.LIB, name)
+
+
+def test_struct_sizes_match_header(pkg):
+    """sizeof() of the ctypes mirrors against a C translation unit compiled from the header."""
+    from ikea_recommender_system_b200 import _native as N
+    import tempfile
+    code = '#include <stdio.h>\n#include "recsys_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
+           'sizeof(rec_config),sizeof(rec_net_params),sizeof(rec_batch),sizeof(rec_train_hparams),' \
+           'sizeof(rec_eval_opts),sizeof(rec_eval_accum));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write(code)
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    mine = [ctypes.sizeof(c) for c in (N.RecConfig, N.RecNetParams, N.RecBatch, N.RecTrainHparams, N.RecEvalOpts,
+                                       N.RecEvalAccum)]
+    assert mine == sizes
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(pkg):
+    from ikea_recommender_system_b200 import _native as N
+    cfg = N.RecConfig(item_num=10, action_dim=10, embedding_dim=8, hidden_dim=8, state_size=4, bidirectional=0,
+                      n_heads=1, n_nets=1, use_packed_seq=1, frozen_pad_row=-1, max_batch=4, vocab_lo=0, vocab_hi=10,
+                      max_topk=8)
+    h = ctypes.c_void_p()
+    rc = pkg.LIB.rec_create(ctypes.byref(cfg), None, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no CUDA device" in pkg.LIB.rec_last_error(None) or b"sm_" in pkg.LIB.rec_last_error(None)
+    net = pkg.GRU4Rec(hidden_size=8, embedding_dim=8, item_num=10, state_size=4, action_dim=10)
+    with pytest.raises(RuntimeError, match="No CPU fallback|no CPU fallback"):
+        net(torch.zeros(2, 4, dtype=torch.long), torch.ones(2, dtype=torch.long))
+    t = pkg.GRU4Rec_trainer(hidden_dim=8, embedding_dim=8, gru_layers=1, train_pad_embed=True, use_packed_seq=True,
+                            learning_rate=0.01, item_num=10, state_size=4, action_dim=10, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        t.train_step(torch.zeros(2, 4, dtype=torch.long), torch.zeros(2, dtype=torch.long), torch.ones(2, dtype=torch.long))
+
+
+def test_product_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "ikea-recommender-system_b200")
+    for dp, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+FAMILIES = [
+    ("gru4rec", lambda p: p.GRU4Rec(hidden_size=8, embedding_dim=12, item_num=30, state_size=4, action_dim=30, gru_layers=2)),
+    ("bidir", lambda p: p.BidirGRU4Rec(hidden_size=8, embedding_dim=12, item_num=30, state_size=4, action_dim=30)),
+    ("sqn", lambda p: p.SQN_Network(hidden_dim=8, item_num=30, state_size=4, action_dim=30, gamma=0.5, gru_layers=1, embedding_dim=12)),
+    ("smorl", lambda p: p.SMORL_GRU_Net(hidden_dim=8, embedding_dim=12, item_num=30, state_size=4, action_dim=30, q_weights=[1, 1, 1], gamma=0.5)),
+]
+
+
+@pytest.mark.parametrize("family,ctor", FAMILIES)
+def test_state_dict_keys_and_seeded_init_match_oracle(pkg, family, ctor):
+    torch.manual_seed(42)
+    mine = ctor(pkg)
+    torch.manual_seed(42)
+    layers = 2 if family == "gru4rec" else 1
+    ref = oracle.SessionNet(family=family, hidden_dim=8, embedding_dim=12, item_num=30, state_size=4, action_dim=30,
+                            gru_layers=layers, use_packed_seq=mine.use_packed_seq)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    for attr in ("hidden_dim", "item_num", "action_dim", "state_size", "embedding_dim"):  # read by SaveBestModel
+        assert getattr(mine, attr) == getattr(ref, attr)
+
+
+def test_trainer_signatures_match_reference(pkg):
+    """Constructor / train_step parameter names of the reference classes."""
+    want = {
+        pkg.GRU4Rec_trainer: ["hidden_dim", "embedding_dim", "gru_layers", "train_pad_embed", "use_packed_seq",
+                              "learning_rate", "item_num", "state_size", "action_dim", "device", "padding_idx",
+                              "torch_rand_seed", "python_rand_seed"],
+        pkg.BidirGRU4Rec_trainer: ["hidden_dim", "embedding_dim", "gru_layers", "dropout", "train_pad_embed",
+                                   "use_packed_seq", "learning_rate", "item_num", "state_size", "action_dim", "device",
+                                   "padding_idx", "torch_rand_seed", "python_rand_seed"],
+        pkg.SQN_trainer: ["hidden_dim", "embedding_dim", "train_pad_embed", "use_packed_seq", "learning_rate",
+                          "item_num", "state_size", "action_dim", "gamma", "gru_layers", "device", "padding_idx",
+                          "torch_rand_seed", "python_rand_seed", "name_1", "name_2"],
+        pkg.SMORL_trainer: ["hidden_dim", "embedding_dim", "padding_pos", "train_pad_embed", "use_packed_seq",
+                            "learning_rate", "item_num", "state_size", "action_dim", "gamma", "gru_layers", "q_weights",
+                            "alpha", "div_embedding", "unpopular_actions_set", "topk_div", "device", "input_tokenizer",
+                            "output_tokenizer", "padding_idx", "torch_rand_seed", "python_rand_seed", "name_1", "name_2"],
+    }
+    for cls, names in want.items():
+        got = [p for p in inspect.signature(cls.__init__).parameters if p != "self"]
+        assert got[:len(names)] == names, cls
+    assert list(inspect.signature(pkg.SQN_trainer.train_step).parameters)[1:] == \
+        ["s", "a", "r", "s_next", "true_len", "true_next_len", "is_end"]
+    assert list(inspect.signature(pkg.GRU4Rec_trainer.train_step).parameters)[1:] == ["s", "a", "true_len"]
+    ev = list(inspect.signature(pkg.evaluate).parameters)
+    assert ev == ["evaluation_data_loader", "model", "device", "loss_function", "padding_pos", "diversity_embedding",
+                  "unpopular_actions_set", "head_idx", "topk_hr_ndcg", "topk_to_consider_div", "topk_to_consider_nov",
+                  "topk_to_consider_cov", "novelty_rew_signal", "input_tokenizer", "output_tokenizer"]
+    for t in (pkg.GRU4Rec_trainer, pkg.SQN_trainer, pkg.SMORL_trainer):
+        for m in ("set_train", "set_eval", "send_to_device"):
+            assert hasattr(t, m)
+
+
+def test_batch_stager_layout(pkg):
+    from ikea_recommender_system_b200.recommenders._base import BatchStager
+    st = BatchStager("cpu", L=5)
+    B = 7
+    buf = torch.zeros(B * (2 * 5 + 3) * 8 + 5 * B + 16, dtype=torch.uint8)
+    s, sn, a, ln, nl, r, e = st._views(buf, B)
+    assert s.shape == (B, 5) and sn.shape == (B, 5) and a.shape == (B,) and r.dtype == torch.float32
+    s.fill_(1); sn.fill_(2); a.fill_(3); ln.fill_(4); nl.fill_(5); r.fill_(0.5); e.fill_(1)
+    s2, sn2, a2, ln2, nl2, r2, e2 = st._views(buf, B)  # disjoint views of one buffer
+    assert int(s2.sum()) == 35 and int(sn2.sum()) == 70 and int(a2.sum()) == 21 and int(ln2.sum()) == 28
+    assert int(nl2.sum()) == 35 and float(r2.sum()) == 3.5 and int(e2.sum()) == 7
+
+
+def test_synthetic_rows_follow_the_replay_buffer_contract(pkg):
+    from ikea_recommender_system_b200 import synthetic
+    for maker in (synthetic.make_replay_rows, synthetic.make_replay_rows_fast):
+        rows = maker(500, 100, 6, seed=1)
+        s, ns, a = rows["state"], rows["next_state"], rows["action"]
+        ln, nl = rows["true_state_len"], rows["true_next_state_len"]
+        assert s.shape == (500, 6) and ns.shape == (500, 6) and s.dtype == np.int64
+        assert ln.min() >= 1 and ln.max() <= 6 and nl.min() >= 1 and nl.max() <= 6
+        assert ((s >= 0) & (s <= 100)).all() and (a < 100).all()
+        n_real = (s != 100).sum(1)
+        assert (np.maximum(n_real, 1) == ln).all()          # "end" padding, len forced to >= 1
+        assert ((ns != 100).sum(1) == nl).all()
+        last = ns[np.arange(500), nl - 1]
+        assert (last == a).all()                             # next_state ends with the action
+        assert set(np.unique(rows["r_act"]).tolist()) <= {np.float32(0.2), np.float32(1.0)}
+    a1 = synthetic.make_replay_rows(50, 100, 6, seed=1)
+    a2 = synthetic.make_replay_rows(50, 100, 6, seed=1)
+    assert all(np.array_equal(a1[k], a2[k]) for k in a1)
