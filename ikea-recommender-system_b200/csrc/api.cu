@@ -256,9 +256,14 @@ extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_tra
       REC_FAIL(e, REC_EINVAL, "SMORL step needs div_emb, unpopular and 1 <= topk_div/topk_nov <= max_topk");
   }
   // three GRU passes: main(s, len) [saved], main(s', len'), boot(s', len)  -- (q1) boot sees true_len
-  if ((rc = launch_gru_forward(e, main_net, b->s, b->true_len, B, e->h_state[0], true))) return rc;
-  if ((rc = launch_gru_forward(e, main_net, b->s_next, b->true_next_len, B, e->h_state[1], false))) return rc;
-  if ((rc = launch_gru_forward(e, boot, b->s_next, b->true_len, B, e->h_state[2], false))) return rc;
+  {
+    const int nets[3] = {main_net, main_net, boot};
+    const int64_t *ss[3] = {b->s, b->s_next, b->s_next};
+    const int64_t *ll[3] = {b->true_len, b->true_next_len, b->true_len};
+    float *hh[3] = {e->h_state[0], e->h_state[1], e->h_state[2]};
+    const bool sv[3] = {true, false, false};
+    if ((rc = launch_gru_forward_multi(e, 3, nets, ss, ll, hh, sv, B))) return rc;
+  }
   // supervised head statistics (+ top-k of the supervised logits for the SMORL rewards)
   HeadStatsArgs a = {};
   a.net_id = main_net; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;

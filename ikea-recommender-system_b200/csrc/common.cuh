@@ -113,6 +113,8 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // gru.cu
 int launch_gru_forward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
                        float *h_out, bool save);
+int launch_gru_forward_multi(rec_engine *e, int n_pass, const int *net_ids, const int64_t *const *s,
+                             const int64_t *const *lengths, float *const *h_out, const bool *save, int B);
 int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
                         const float *dh, float step_size, float bc2_sqrt, const rec_train_hparams *hp);
 int launch_gru_transpose(rec_engine *e, int net_id);

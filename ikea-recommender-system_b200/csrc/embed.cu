@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restr
                                                           float *__restrict__ grad_rows,
                                                           int32_t *__restrict__ slot_of_row, int use_smem) {
   extern __shared__ int32_t skeys[];
+  constexpr int LISTCAP = 160;
+  __shared__ int plist[8][LISTCAP];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int32_t *kp = keys;
   if (use_smem) {
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restr
     const int Ec = min(256, E - e0);
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    float2 acc2 = make_float2(0.f, 0.f);
     auto add_chunk = [&](int q) {
       for (int d = 0; d < dirs; ++d) {
         const float *src = dx + ((int64_t)q * dirs + d) * E + e0;
@@ -61,15 +64,51 @@ __global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restr
         }
       }
     };
-    add_chunk(p);
+    const bool fast = (E <= 64 && dirs == 1);
+    int cnt = 0;
+    auto flush_list = [&]() {
+      for (int i0 = 0; i0 < cnt; i0 += 16) {
+        float2 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          v[u] = make_float2(0.f, 0.f);
+          if (i0 + u < cnt && 2 * lane < E)
+            v[u] = *reinterpret_cast<const float2 *>(dx + (int64_t)plist[wid][i0 + u] * E + 2 * lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (i0 + u < cnt) { acc2.x += v[u].x; acc2.y += v[u].y; }
+      }
+      __syncwarp();
+      cnt = 0;
+    };
+    if (fast) { if (2 * lane < E) acc2 = *reinterpret_cast<const float2 *>(dx + (int64_t)p * E + 2 * lane); }
+    else add_chunk(p);
     for (int q0 = p + 1; q0 < P; q0 += 32) {
       int q = q0 + lane;
       unsigned m = __ballot_sync(0xffffffffu, (q < P) && (kp[q] == row));
-      while (m) {
-        int l = __ffs(m) - 1;
-        m &= m - 1;
-        add_chunk(q0 + l);
+      if (fast) {
+        // Hot rows (Zipf head) have hundreds of duplicates.  Pass 1 only records matching positions
+        // in a per-warp list; flush_list() then loads 16 rows at a time (independent loads, overlapped
+        // latency) and adds them strictly in position order.
+        if (m) {
+          if (m & (1u << lane)) plist[wid][cnt + __popc(m & ((1u << lane) - 1u))] = q;
+          cnt += __popc(m);
+          __syncwarp();
+          if (cnt > LISTCAP - 32) { flush_list(); }
+        }
+      } else {
+        while (m) {
+          int l = __ffs(m) - 1;
+          m &= m - 1;
+          add_chunk(q0 + l);
+        }
       }
+    }
+    if (fast) {
+      flush_list();
+      if (2 * lane < E) *reinterpret_cast<float2 *>(grad_rows + (int64_t)p * E + 2 * lane) = acc2;
+      continue;
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {

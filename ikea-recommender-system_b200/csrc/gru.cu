@@ -134,6 +134,207 @@ __global__ void __launch_bounds__(256) gru_fwd_kernel(const float *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast forward path for E = H = 64 (every headline config).  192 threads = one gate row each; the
+// thread keeps its rows of W_ih and W_hh (2 x 64 floats) in REGISTERS for the whole sequence, x_t and
+// h live in shared memory and are read as broadcast float4.  Up to 3 independent passes (main(s),
+// main(s'), boot(s')) run as one launch: grid = (ceil(B/2), dirs, n_pass).
+// ------------------------------------------------------------------------------------------------
+struct GruPass {
+  const float *emb;
+  GruWeights w;
+  const int64_t *s, *lens;
+  float *h_out;
+  int save;
+};
+struct GruPasses { GruPass p[3]; };
+
+#define FR 2
+__global__ void __launch_bounds__(192, 2) gru_fwd64_kernel(GruPasses ps, int B, int L, int N, int packed,
+                                                           float *__restrict__ gates_save,
+                                                           float *__restrict__ hprev_save) {
+  constexpr int H = 64, E = 64, G = 192;
+  const GruPass &P = ps.p[blockIdx.z];
+  const int dir = blockIdx.y, dirs = gridDim.y;
+  const int b0 = blockIdx.x * FR;
+  const int tid = threadIdx.x;
+  __shared__ __align__(16) float xs[FR][E];
+  __shared__ __align__(16) float hs[FR][H];
+  __shared__ float pre_i[FR][G];
+  __shared__ float pre_h[FR][G];
+  __shared__ int len_s[FR];
+  __shared__ int tok_s[FR][64];  // L <= 64 on this path
+
+  float wi[E], wh[H];
+  {
+    const float4 *ri = reinterpret_cast<const float4 *>(P.w.wi[dir] + (int64_t)tid * E);
+    const float4 *rh = reinterpret_cast<const float4 *>(P.w.wh[dir] + (int64_t)tid * H);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float4 a = __ldg(ri + k), b = __ldg(rh + k);
+      wi[4 * k] = a.x; wi[4 * k + 1] = a.y; wi[4 * k + 2] = a.z; wi[4 * k + 3] = a.w;
+      wh[4 * k] = b.x; wh[4 * k + 1] = b.y; wh[4 * k + 2] = b.z; wh[4 * k + 3] = b.w;
+    }
+  }
+  const float bij = P.w.bi[dir][tid], bhj = P.w.bh[dir][tid];
+  if (tid < FR) len_s[tid] = (b0 + tid < B) ? eff_len(P.lens, b0 + tid, L, packed) : 0;
+  for (int i = tid; i < FR * L; i += 192) {
+    int r = i / L, t = i - r * L;
+    int64_t it = (b0 + r < B) ? P.s[(int64_t)(b0 + r) * L + t] : 0;
+    tok_s[r][t] = (int)(it < 0 ? 0 : (it > N ? N : it));
+  }
+  if (tid < FR * H) hs[tid / H][tid % H] = 0.f;
+  __syncthreads();
+  const int maxlen = max(len_s[0], len_s[1]);
+  // x loader: threads [0, FR*16) own one float4 of one row
+  const int xr = tid >> 4, xc = tid & 15;
+  auto load_x = [&](int i) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < FR * 16 && i < len_s[xr]) {
+      int tok = dir ? (len_s[xr] - 1 - i) : i;
+      v = __ldg(reinterpret_cast<const float4 *>(P.emb + (int64_t)tok_s[xr][tok] * E) + xc);
+    }
+    return v;
+  };
+  if (tid < FR * 16) reinterpret_cast<float4 *>(&xs[xr][0])[xc] = load_x(0);
+  __syncthreads();
+  for (int i = 0; i < maxlen; ++i) {
+    float4 xnext = load_x(i + 1);  // prefetch, consumed after the gate phase
+    float ai[FR][2], ah[FR][2];
+#pragma unroll
+    for (int r = 0; r < FR; ++r) { ai[r][0] = bij; ai[r][1] = 0.f; ah[r][0] = bhj; ah[r][1] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+#pragma unroll
+      for (int r = 0; r < FR; ++r) {
+        float4 x = reinterpret_cast<const float4 *>(&xs[r][0])[k];
+        float4 hv = reinterpret_cast<const float4 *>(&hs[r][0])[k];
+        ai[r][0] = fmaf(wi[4 * k], x.x, ai[r][0]); ai[r][1] = fmaf(wi[4 * k + 1], x.y, ai[r][1]);
+        ai[r][0] = fmaf(wi[4 * k + 2], x.z, ai[r][0]); ai[r][1] = fmaf(wi[4 * k + 3], x.w, ai[r][1]);
+        ah[r][0] = fmaf(wh[4 * k], hv.x, ah[r][0]); ah[r][1] = fmaf(wh[4 * k + 1], hv.y, ah[r][1]);
+        ah[r][0] = fmaf(wh[4 * k + 2], hv.z, ah[r][0]); ah[r][1] = fmaf(wh[4 * k + 3], hv.w, ah[r][1]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < FR; ++r) { pre_i[r][tid] = ai[r][0] + ai[r][1]; pre_h[r][tid] = ah[r][0] + ah[r][1]; }
+    __syncthreads();
+    if (tid < FR * H) {
+      const int r = tid >> 6, u = tid & 63;
+      if (i < len_s[r]) {
+        float rg = sigmoidf_(pre_i[r][u] + pre_h[r][u]);
+        float zg = sigmoidf_(pre_i[r][H + u] + pre_h[r][H + u]);
+        float phn = pre_h[r][2 * H + u];
+        float ng = tanhf(pre_i[r][2 * H + u] + rg * phn);
+        float hold = hs[r][u];
+        if (P.save) {
+          int tok = dir ? (len_s[r] - 1 - i) : i;
+          int64_t base = ((int64_t)(b0 + r) * L + tok) * dirs + dir;
+          float *g = gates_save + base * 4 * H;
+          g[u] = rg; g[H + u] = zg; g[2 * H + u] = ng; g[3 * H + u] = phn;
+          hprev_save[base * H + u] = hold;
+        }
+        hs[r][u] = (1.f - zg) * ng + zg * hold;
+      }
+    }
+    if (tid < FR * 16) reinterpret_cast<float4 *>(&xs[xr][0])[xc] = xnext;
+    __syncthreads();
+  }
+  if (tid < FR * H) {
+    const int r = tid >> 6, u = tid & 63;
+    if (b0 + r < B) P.h_out[(int64_t)(b0 + r) * (dirs * H) + dir * H + u] = hs[r][u];
+  }
+}
+
+// Fast BPTT for E = H = 64: 128 threads; thread c < 64 owns COLUMN c of W_hh (192 registers) and
+// produces dh_prev[c]; thread 64 + c owns column c of W_ih and produces dx[c].  grid = (ceil(B/2), dirs).
+__global__ void __launch_bounds__(128, 2) gru_bwd64_kernel(GruWeights w, const int64_t *__restrict__ lens, int B,
+                                                           int L, int packed, const float *__restrict__ dh_in,
+                                                           const float *__restrict__ gates_save,
+                                                           const float *__restrict__ hprev_save,
+                                                           float *__restrict__ dgi, float *__restrict__ dgh,
+                                                           float *__restrict__ dx) {
+  constexpr int H = 64, E = 64, G = 192;
+  const int dir = blockIdx.y, dirs = gridDim.y;
+  const int b0 = blockIdx.x * FR;
+  const int tid = threadIdx.x;
+  __shared__ float dhs[FR][H];
+  __shared__ float dhd[FR][H];
+  __shared__ __align__(16) float dai[FR][G];
+  __shared__ __align__(16) float dah[FR][G];
+  __shared__ int len_s[FR];
+  const bool is_h = tid < 64;
+  const int c = tid & 63;
+  float wc[G];
+  {
+    const float *src = is_h ? (w.wh[dir] + c) : (w.wi[dir] + c);
+#pragma unroll
+    for (int j = 0; j < G; ++j) wc[j] = __ldg(src + (int64_t)j * 64);
+  }
+  if (tid < FR) len_s[tid] = (b0 + tid < B) ? eff_len(lens, b0 + tid, L, packed) : 0;
+  {
+    const int r = tid >> 6, u = tid & 63;
+    dhs[r][u] = (b0 + r < B) ? dh_in[(int64_t)(b0 + r) * (dirs * H) + dir * H + u] : 0.f;
+  }
+  __syncthreads();
+  const int maxlen = max(len_s[0], len_s[1]);
+  for (int i = maxlen - 1; i >= 0; --i) {
+    {
+      const int r = tid >> 6, u = tid & 63;
+      float a_r = 0.f, a_z = 0.f, a_n = 0.f, h_n = 0.f, direct = dhs[r][u];
+      if (i < len_s[r]) {
+        int tok = dir ? (len_s[r] - 1 - i) : i;
+        int64_t base = ((int64_t)(b0 + r) * L + tok) * dirs + dir;
+        const float *g = gates_save + base * 4 * H;
+        float rg = g[u], zg = g[H + u], ng = g[2 * H + u], phn = g[3 * H + u];
+        float hp = hprev_save[base * H + u];
+        float dhv = direct;
+        float dn = dhv * (1.f - zg);
+        float dz = dhv * (hp - ng);
+        a_n = dn * (1.f - ng * ng);
+        float dr = a_n * phn;
+        a_r = dr * rg * (1.f - rg);
+        a_z = dz * zg * (1.f - zg);
+        h_n = a_n * rg;
+        direct = dhv * zg;
+        float *gi = dgi + base * G, *gh = dgh + base * G;
+        gi[u] = a_r; gi[H + u] = a_z; gi[2 * H + u] = a_n;
+        gh[u] = a_r; gh[H + u] = a_z; gh[2 * H + u] = h_n;
+      }
+      dai[r][u] = a_r; dai[r][H + u] = a_z; dai[r][2 * H + u] = a_n;
+      dah[r][u] = a_r; dah[r][H + u] = a_z; dah[r][2 * H + u] = h_n;
+      dhd[r][u] = direct;
+    }
+    __syncthreads();
+    {
+      float acc[FR][2];
+#pragma unroll
+      for (int r = 0; r < FR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+#pragma unroll
+      for (int j4 = 0; j4 < G / 4; ++j4) {
+#pragma unroll
+        for (int r = 0; r < FR; ++r) {
+          float4 d = is_h ? reinterpret_cast<const float4 *>(&dah[r][0])[j4]
+                          : reinterpret_cast<const float4 *>(&dai[r][0])[j4];
+          acc[r][0] = fmaf(d.x, wc[4 * j4], acc[r][0]); acc[r][1] = fmaf(d.y, wc[4 * j4 + 1], acc[r][1]);
+          acc[r][0] = fmaf(d.z, wc[4 * j4 + 2], acc[r][0]); acc[r][1] = fmaf(d.w, wc[4 * j4 + 3], acc[r][1]);
+        }
+      }
+      // dhs is only read in the elementwise phase above (already past the barrier): safe to update
+#pragma unroll
+      for (int r = 0; r < FR; ++r) {
+        float v = acc[r][0] + acc[r][1];
+        if (is_h) {
+          dhs[r][c] = dhd[r][c] + v;  // inactive rows: dah = 0 -> dhs unchanged
+        } else if (i < len_s[r]) {
+          int tok = dir ? (len_s[r] - 1 - i) : i;
+          dx[(((int64_t)(b0 + r) * L + tok) * dirs + dir) * E + c] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // BPTT.  grid = (ceil(B/R), dirs), block = 256.  Writes d(pre-activations) per token and dx.
 // ------------------------------------------------------------------------------------------------
 template <int R>
@@ -389,9 +590,47 @@ int launch_gru_transpose(rec_engine *e, int net_id) {
   return REC_OK;
 }
 
+static GruPass make_pass(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, float *h_out, bool save) {
+  GruPass p;
+  p.emb = e->nets[net_id].p.emb; p.w = gru_weights(e, net_id); p.s = s; p.lens = lengths; p.h_out = h_out;
+  p.save = save ? 1 : 0;
+  return p;
+}
+
+static bool gru_fast_path(const rec_engine *e) {
+  return e->cfg.embedding_dim == 64 && e->cfg.hidden_dim == 64 && e->cfg.state_size <= 64;
+}
+
+// Up to three independent passes in one launch (fast path) or back-to-back launches (generic path).
+int launch_gru_forward_multi(rec_engine *e, int n_pass, const int *net_ids, const int64_t *const *s,
+                             const int64_t *const *lengths, float *const *h_out, const bool *save, int B) {
+  const rec_config &c = e->cfg;
+  if (gru_fast_path(e)) {
+    GruPasses ps;
+    for (int i = 0; i < 3; ++i) ps.p[i] = make_pass(e, net_ids[i < n_pass ? i : 0], s[i < n_pass ? i : 0],
+                                                    lengths[i < n_pass ? i : 0], h_out[i < n_pass ? i : 0],
+                                                    save[i < n_pass ? i : 0]);
+    dim3 grid(cdiv(B, FR), e->dirs, n_pass);
+    gru_fwd64_kernel<<<grid, 192, 0, e->stream>>>(ps, B, c.state_size, c.item_num, c.use_packed_seq, e->gates_save,
+                                                 e->hprev_save);
+    REC_LAUNCH_CHECK(e);
+    return REC_OK;
+  }
+  for (int i = 0; i < n_pass; ++i) {
+    int rc = launch_gru_forward(e, net_ids[i], s[i], lengths[i], B, h_out[i], save[i]);
+    if (rc) return rc;
+  }
+  return REC_OK;
+}
+
 int launch_gru_forward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
                        float *h_out, bool save) {
   const rec_config &c = e->cfg;
+  if (gru_fast_path(e)) {
+    const int64_t *sa[1] = {s}, *la[1] = {lengths};
+    float *ha[1] = {h_out};
+    return launch_gru_forward_multi(e, 1, &net_id, sa, la, ha, &save, B);
+  }
   const int E = c.embedding_dim, H = c.hidden_dim, L = c.state_size;
   size_t smem = (size_t)GRU_R * (E + H + 6 * H) * sizeof(float) + (size_t)GRU_R * (1 + L) * sizeof(int);
   static bool attr_set = false;
@@ -418,10 +657,16 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
     REC_CUDA(e, cudaFuncSetAttribute(gru_bwd_kernel<GRU_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  dim3 grid(cdiv(B, GRU_R), e->dirs);
-  gru_bwd_kernel<GRU_R><<<grid, 256, smem, e->stream>>>(gru_weights(e, net_id), lengths, B, L, E, H,
-                                                       c.use_packed_seq, dh, e->gates_save, e->hprev_save,
-                                                       e->dgi, e->dgh, e->dx);
+  if (gru_fast_path(e)) {
+    dim3 grid(cdiv(B, FR), e->dirs);
+    gru_bwd64_kernel<<<grid, 128, 0, e->stream>>>(gru_weights(e, net_id), lengths, B, L, c.use_packed_seq, dh,
+                                                 e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx);
+  } else {
+    dim3 grid(cdiv(B, GRU_R), e->dirs);
+    gru_bwd_kernel<GRU_R><<<grid, 256, smem, e->stream>>>(gru_weights(e, net_id), lengths, B, L, E, H,
+                                                         c.use_packed_seq, dh, e->gates_save, e->hprev_save,
+                                                         e->dgi, e->dgh, e->dx);
+  }
   REC_LAUNCH_CHECK(e);
   // weight gradients (split over token positions) + Adam on the GRU parameters
   const int KS = (E > H ? E : H) + 1;
