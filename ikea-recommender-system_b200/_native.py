@@ -76,15 +76,15 @@ SYMBOLS = {
     "rec_head_logits": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int64]),
     "rec_train_step_supervised": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), _P]),
     "rec_train_step_q": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
-    "rec_train_phase_a": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int,
-                                    C.POINTER(_P), C.POINTER(C.c_int64)]),
-    "rec_train_phase_b": (C.c_int, [_P, _P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int64)]),
-    "rec_train_phase_c": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "rec_record_floats": (C.c_int, [_P]),
+    "rec_train_phase_a": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
+    "rec_train_phase_b": (C.c_int, [_P, _P, C.c_int, _P]),
+    "rec_train_phase_c": (C.c_int, [_P, _P, _P, _P]),
     "rec_train_phase_d": (C.c_int, [_P, _P]),
     "rec_eval_batch": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.POINTER(RecEvalOpts),
                                  C.POINTER(RecEvalAccum), _P, _P]),
-    "rec_eval_shard_candidates": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.c_int, C.c_int, _P, _P, _P, _P]),
-    "rec_eval_merge": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecEvalOpts), C.c_int, C.c_int, _P, _P, _P,
+    "rec_eval_shard_candidates": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.c_int, C.c_int, _P]),
+    "rec_eval_merge": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecEvalOpts), _P, C.c_int,
                                  C.POINTER(RecEvalAccum), _P, _P]),
     "rec_launch_count": (C.c_int64, [_P]),
     "rec_enable_kernel_timing": (C.c_int, [_P, C.c_int]),

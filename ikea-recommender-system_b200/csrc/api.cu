@@ -110,6 +110,8 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->loss_buf, float, 8);
   ALLOC(e, e->astar, int32_t, mb);
   ALLOC(e, extra(e).q_loss_rows, float, mb);
+  ALLOC(e, e->summary, float, mb * e->part_stride);
+  ALLOC(e, e->qpack, float, 2 * mb * 3);
   ALLOC(e, extra(e).rowm, double, mb * (3 * REC_MAX_KLIST + 3));
   for (int n = 0; n < c.n_nets; ++n)
     for (int d = 0; d < dirs; ++d) {
@@ -136,7 +138,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
@@ -224,6 +226,7 @@ extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, cons
   if (rc) return rc;
   if ((rc = check_batch(e, b, false))) return rc;
   if (!hp || !loss_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_supervised: null argument");
+  if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
   const int B = b->B;
   if ((rc = launch_gru_forward(e, 0, b->s, b->true_len, B, e->h_state[0], true))) return rc;
   HeadStatsArgs a = {};
@@ -249,6 +252,7 @@ extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_tra
   if ((rc = check_net(e, 1 - main_net, false))) return rc;
   if ((rc = check_batch(e, b, true))) return rc;
   if (!hp || !losses_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_q: null argument");
+  if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
   const int B = b->B, boot = 1 - main_net, n_q = e->cfg.n_heads - 1;
   if (n_q == 3) {
     if (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 || hp->div_dim < 1 ||
@@ -324,32 +328,142 @@ extern "C" int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, con
   return launch_eval_metrics(e, b, o, kmax, acc, extra(e).rowm, topk_ids, topk_scores);
 }
 
-// ---- sharded / phase-split entry points (see DESIGN.md section "multi-GPU") ---------------------
-extern "C" int rec_eval_shard_candidates(rec_engine *e, int net_id, const rec_batch *b, int head_idx, int kmax,
-                                         float *h_out, float *cand_scores, int32_t *cand_ids, float *stats) {
-  (void)net_id; (void)b; (void)head_idx; (void)kmax; (void)h_out; (void)cand_scores; (void)cand_ids; (void)stats;
-  REC_FAIL(e, REC_EINVAL, "rec_eval_shard_candidates: not implemented in this build");
+// ---- sharded / phase-split entry points (see DESIGN.md "multi-GPU") --------------------------------
+// Every rank holds the FULL (all-gathered) batch, a replica of embedding + GRU, and rows
+// [vocab_lo, vocab_hi) of every head.  Collectives are run by the caller between the phases.
+
+static int shard_head_pass(rec_engine *e, int net_id, const float *h, const rec_batch *b, int stats_head, int topk,
+                           int n_q, const float *w, bool want_stats, float *summary) {
+  // per-shard statistics -> local merge -> one record per row in e->summary
+  int rc, n_split = 0;
+  if (want_stats || topk > 0) {
+    HeadStatsArgs a = {};
+    a.net_id = net_id; a.h = h; a.B = b->B; a.do_stats = want_stats ? 1 : 0; a.stats_head = stats_head; a.target = b->a;
+    a.topk = topk;
+    if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+    if ((rc = launch_head_merge(e, e->part, n_split, b->B, topk, want_stats, false, summary))) return rc;
+  }
+  if (n_q > 0) {
+    HeadStatsArgs g = {};
+    g.net_id = net_id; g.h = e->h_state[1]; g.B = b->B; g.n_arg = n_q;
+    g.w[0] = w[0]; g.w[1] = w[1]; g.w[2] = w[2];
+    if ((rc = launch_head_stats(e, g, &n_split))) return rc;
+    if ((rc = launch_head_merge(e, e->part, n_split, b->B, 0, false, true, summary))) return rc;
+  }
+  return REC_OK;
 }
-extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, int n_shards, int kmax,
-                              const float *cand_scores, const int32_t *cand_ids, const float *stats,
-                              const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores) {
-  (void)b; (void)o; (void)n_shards; (void)kmax; (void)cand_scores; (void)cand_ids; (void)stats; (void)acc; (void)topk_ids; (void)topk_scores;
-  REC_FAIL(e, REC_EINVAL, "rec_eval_merge: not implemented in this build");
-}
+
+extern "C" int rec_record_floats(const rec_engine *e) { return e ? e->part_stride : -1; }
+
 extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
-                                 float **partials, int64_t *partials_floats) {
-  (void)b; (void)hp; (void)main_net; (void)partials; (void)partials_floats;
-  REC_FAIL(e, REC_EINVAL, "rec_train_phase_a: not implemented in this build");
+                                 float *records_out) {
+  if (!e) return REC_EINVAL;
+  if (!b || !hp || !records_out) REC_FAIL(e, REC_EINVAL, "rec_train_phase_a: null argument");
+  const int n_q = e->cfg.n_heads - 1;
+  if (main_net < 0 || main_net >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "main_net out of range");
+  int rc = check_net(e, main_net, true);
+  if (rc) return rc;
+  if ((rc = check_batch(e, b, n_q > 0))) return rc;
+  if (n_q > 0 && e->cfg.n_nets != 2) REC_FAIL(e, REC_EINVAL, "Q heads need a twin-net engine");
+  if (n_q == 3 && (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 ||
+                   hp->topk_div > e->cfg.max_topk || hp->topk_nov > e->cfg.max_topk))
+    REC_FAIL(e, REC_EINVAL, "SMORL step needs div_emb, unpopular and 1 <= topk_div/topk_nov <= max_topk");
+  const int B = b->B, boot = 1 - main_net;
+  e->cur_batch = *b; e->cur_hp = *hp; e->cur_main = main_net; e->cur_phase = 1;
+  e->cur_topk = (n_q == 3) ? (hp->topk_div > hp->topk_nov ? hp->topk_div : hp->topk_nov) : 0;
+  REC_CUDA(e, cudaMemsetAsync(records_out, 0, sizeof(float) * (size_t)B * e->part_stride, e->stream));
+  if (n_q > 0) {
+    if ((rc = check_net(e, boot, false))) return rc;
+    const int nets[3] = {main_net, main_net, boot};
+    const int64_t *ss[3] = {b->s, b->s_next, b->s_next};
+    const int64_t *ll[3] = {b->true_len, b->true_next_len, b->true_len};
+    float *hh[3] = {e->h_state[0], e->h_state[1], e->h_state[2]};
+    const bool sv[3] = {true, false, false};
+    if ((rc = launch_gru_forward_multi(e, 3, nets, ss, ll, hh, sv, B))) return rc;
+  } else {
+    if ((rc = launch_gru_forward(e, main_net, b->s, b->true_len, B, e->h_state[0], true))) return rc;
+  }
+  float w[3] = {n_q == 3 ? hp->q_weights[0] : 1.f, hp->q_weights[1], hp->q_weights[2]};
+  return shard_head_pass(e, main_net, e->h_state[0], b, 0, e->cur_topk, n_q, w, true, records_out);
 }
-extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float **boot_q, int64_t *boot_q_floats) {
-  (void)gathered; (void)n_shards; (void)boot_q; (void)boot_q_floats;
-  REC_FAIL(e, REC_EINVAL, "rec_train_phase_b: not implemented in this build");
+
+extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float *q_out) {
+  if (!e) return REC_EINVAL;
+  if (e->cur_phase != 1) REC_FAIL(e, REC_EINVAL, "rec_train_phase_b called out of order");
+  if (!gathered || n_shards < 1 || (!q_out && e->cfg.n_heads > 1)) REC_FAIL(e, REC_EINVAL, "rec_train_phase_b: bad argument");
+  const rec_batch *b = &e->cur_batch;
+  const int B = b->B, n_q = e->cfg.n_heads - 1, main_net = e->cur_main;
+  int rc;
+  if ((rc = launch_head_merge(e, gathered, n_shards, B, e->cur_topk, true, n_q > 0, nullptr))) return rc;
+  if (n_q > 0) {
+    // this shard's contribution to Q(s,a) and Q_boot(s',a*) (zero when the row lives elsewhere)
+    if ((rc = launch_row_dots(e, main_net, e->h_state[0], b->a, nullptr, B, 1, n_q, q_out))) return rc;
+    if ((rc = launch_row_dots(e, 1 - main_net, e->h_state[2], nullptr, e->astar, B, 1, n_q, q_out + (int64_t)B * 3))) return rc;
+  }
+  e->cur_phase = 2;
+  return REC_OK;
 }
-extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, float *losses_out, float **dh, int64_t *dh_floats) {
-  (void)boot_q_reduced; (void)losses_out; (void)dh; (void)dh_floats;
-  REC_FAIL(e, REC_EINVAL, "rec_train_phase_c: not implemented in this build");
+
+extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, float *losses_out, float *dh_out) {
+  if (!e) return REC_EINVAL;
+  if (e->cur_phase != 2) REC_FAIL(e, REC_EINVAL, "rec_train_phase_c called out of order");
+  if (!losses_out || !dh_out) REC_FAIL(e, REC_EINVAL, "rec_train_phase_c: null argument");
+  const rec_batch *b = &e->cur_batch;
+  const rec_train_hparams *hp = &e->cur_hp;
+  const int B = b->B, n_q = e->cfg.n_heads - 1, main_net = e->cur_main;
+  int rc;
+  if (n_q > 0) {
+    if (!boot_q_reduced) REC_FAIL(e, REC_EINVAL, "rec_train_phase_c: reduced Q buffer is null");
+    REC_CUDA(e, cudaMemcpyAsync(e->q_sa, boot_q_reduced, sizeof(float) * (size_t)B * 3, cudaMemcpyDeviceToDevice, e->stream));
+    REC_CUDA(e, cudaMemcpyAsync(e->q_boot, boot_q_reduced + (int64_t)B * 3, sizeof(float) * (size_t)B * 3,
+                                cudaMemcpyDeviceToDevice, e->stream));
+    const float alpha_eff = (n_q == 3) ? hp->alpha : 1.f;
+    if ((rc = launch_td(e, b, hp, n_q, alpha_eff, extra(e).q_loss_rows))) return rc;
+  }
+  if ((rc = launch_loss_reduce(e, B, n_q > 0 ? extra(e).q_loss_rows : nullptr, e->loss_buf))) return rc;
+  REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, (n_q > 0 ? 2 : 1) * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  adam_scalars(e, main_net, hp, &e->cur_step_size, &e->cur_bc2_sqrt);
+  if ((rc = launch_head_backward_adam(e, main_net, e->h_state[0], b, B, e->cur_step_size, e->cur_bc2_sqrt, hp, 1.f / (float)B))) return rc;
+  REC_CUDA(e, cudaMemcpyAsync(dh_out, e->dh, sizeof(float) * (size_t)B * e->D, cudaMemcpyDeviceToDevice, e->stream));
+  e->cur_phase = 3;
+  return REC_OK;
 }
+
 extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
-  (void)dh_reduced;
-  REC_FAIL(e, REC_EINVAL, "rec_train_phase_d: not implemented in this build");
+  if (!e) return REC_EINVAL;
+  if (e->cur_phase != 3) REC_FAIL(e, REC_EINVAL, "rec_train_phase_d called out of order");
+  if (!dh_reduced) REC_FAIL(e, REC_EINVAL, "rec_train_phase_d: null argument");
+  const rec_batch *b = &e->cur_batch;
+  const int main_net = e->cur_main;
+  e->cur_phase = 0;
+  int rc;
+  if ((rc = launch_gru_backward(e, main_net, b->s, b->true_len, b->B, dh_reduced, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp))) return rc;
+  return launch_embedding_update(e, main_net, b->s, b->true_len, b->B, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp);
+}
+
+// Sharded evaluation: per-shard record (max, sumexp, target logit, top-k candidates) per row ...
+extern "C" int rec_eval_shard_candidates(rec_engine *e, int net_id, const rec_batch *b, int head_idx, int kmax,
+                                         float *records_out) {
+  int rc = check_net(e, net_id, false);
+  if (rc) return rc;
+  if ((rc = check_batch(e, b, false))) return rc;
+  if (!records_out || head_idx < 0 || head_idx >= e->cfg.n_heads || kmax < 1 || kmax > e->cfg.max_topk)
+    REC_FAIL(e, REC_EINVAL, "rec_eval_shard_candidates: bad argument");
+  REC_CUDA(e, cudaMemsetAsync(records_out, 0, sizeof(float) * (size_t)b->B * e->part_stride, e->stream));
+  if ((rc = launch_gru_forward(e, net_id, b->s, b->true_len, b->B, e->h_state[0], false))) return rc;
+  float w[3] = {1.f, 0.f, 0.f};
+  return shard_head_pass(e, net_id, e->h_state[0], b, head_idx, kmax, 0, w, true, records_out);
+}
+
+// ... and the merge of the all-gathered records of all shards + metric accumulation (replicated).
+extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, const float *gathered,
+                              int n_shards, const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores) {
+  if (!e) return REC_EINVAL;
+  int rc = check_batch(e, b, false);
+  if (rc) return rc;
+  if (!o || !acc || !gathered || n_shards < 1) REC_FAIL(e, REC_EINVAL, "rec_eval_merge: bad argument");
+  const int kmax = eval_kmax(o);
+  if (kmax > e->cfg.max_topk) REC_FAIL(e, REC_EINVAL, "rec_eval_merge: k=%d exceeds max_topk=%d", kmax, e->cfg.max_topk);
+  if ((rc = launch_head_merge(e, gathered, n_shards, b->B, kmax, true, false, nullptr))) return rc;
+  return launch_eval_metrics(e, b, o, kmax, acc, extra(e).rowm, topk_ids, topk_scores);
 }

@@ -55,7 +55,10 @@ struct rec_engine {
   // saved call context for the phase-split API
   rec_batch cur_batch;
   rec_train_hparams cur_hp;
-  int cur_main;
+  int cur_main, cur_topk, cur_phase;
+  float cur_step_size, cur_bc2_sqrt;
+  float *summary;        // [maxB][part_stride] per-row record of this shard
+  float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;
   cudaEvent_t ev[6];
   float last_ms[3];
@@ -135,7 +138,7 @@ struct HeadStatsArgs {
 };
 int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats,
-                      bool has_argmax);
+                      bool has_argmax, float *summary = nullptr);
 int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld);
 int launch_row_dots(rec_engine *e, int net_id, const float *h, const int64_t *ids, const int32_t *ids32,
                     int B, int first_head, int n, float *out);

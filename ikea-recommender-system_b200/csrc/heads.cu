@@ -254,11 +254,16 @@ __global__ void __launch_bounds__(256) head_stats_kernel(HeadPtrs hp, const floa
 __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict__ part, int part_stride, int n_split,
                                                          int B, int topk, int has_stats, int has_arg,
                                                          float *__restrict__ row_stats, int32_t *__restrict__ row_ids,
-                                                         float *__restrict__ row_topv, int32_t *__restrict__ astar) {
+                                                         float *__restrict__ row_topv, int32_t *__restrict__ astar,
+                                                         float *__restrict__ summary) {
+  // `summary` (optional): the merged result re-packed as ONE record per row in the partial-record
+  // format, so that a second merge over the all-gathered summaries of all vocabulary shards
+  // (n_split = number of shards) finishes the reduction across GPUs with this same kernel.
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   float *rs = row_stats + (int64_t)row * ROW_STRIDE;
+  float *sm = summary ? summary + (int64_t)row * part_stride : nullptr;
   if (has_stats) {
     float m = REC_NEG_INF, tg = REC_NEG_INF;
     for (int sp = lane; sp < n_split; sp += 32) {
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
     if (lane == 0) {
       float lse = m + logf(ssum);
       rs[0] = lse; rs[1] = tg; rs[4] = lse - tg; rs[5] = m; rs[6] = ssum;
+      if (sm) { sm[0] = m; sm[1] = ssum; sm[2] = tg; }
     }
   }
   if (has_arg) {
@@ -294,7 +300,10 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
       int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
-    if (lane == 0) { rs[2] = bv; rs[3] = __int_as_float(bi); astar[row] = bi; }
+    if (lane == 0) {
+      rs[2] = bv; rs[3] = __int_as_float(bi); astar[row] = bi;
+      if (sm) { sm[3] = bv; sm[4] = __int_as_float(bi); }
+    }
   }
   if (topk > 0) {
     // K selection rounds over n_split*topk candidates; "taken" = not after the last pick in the order
@@ -317,7 +326,10 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
         int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
       }
-      if (lane == 0) { row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv; }
+      if (lane == 0) {
+        row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv;
+        if (sm) { sm[PART_TOPK_OFF + k] = bv; sm[PART_TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(bi); }
+      }
       lastv = bv; lasti = bi;
     }
   }
@@ -609,9 +621,11 @@ int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
   return REC_OK;
 }
 
-int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats, bool has_arg) {
+int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats, bool has_arg,
+                      float *summary) {
   head_merge_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(part, e->part_stride, n_split, B, topk, has_stats ? 1 : 0,
-                                                      has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv, e->astar);
+                                                      has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv, e->astar,
+                                                      summary);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
 }
@@ -625,7 +639,7 @@ int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int 
 }
 
 int launch_row_dots(rec_engine *e, int net_id, const float *h, const int64_t *ids, const int32_t *ids32, int B,
-                    int first_head, int n, float *out) {
+                    int first_head, int n, float *out) {  // out is [B, 3]
   row_dots_kernel<<<cdiv(B * n, 8), 256, 0, e->stream>>>(head_ptrs(e, net_id), h, ids, ids32, B, e->D, e->Vloc,
                                                         e->cfg.vocab_lo, first_head, n, out, 3);
   REC_LAUNCH_CHECK(e);

@@ -182,6 +182,39 @@ class Engine:
                 self.lib.rec_eval_batch(self.handle, net_id, C.byref(batch), C.byref(opts), C.byref(acc),
                                         _ptr(topk_ids), _ptr(topk_scores)), "rec_eval_batch")
 
+    # -- vocabulary-sharded (multi-GPU) phases; collectives run by the caller in between --------
+    def record_floats(self):
+        return int(self.lib.rec_record_floats(self.handle))
+
+    def train_phase_a(self, batch, hp, main_net, records_out):
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_phase_a(self.handle, C.byref(batch), C.byref(hp), main_net, _ptr(records_out)),
+                "rec_train_phase_a")
+
+    def train_phase_b(self, gathered, n_shards, q_out):
+        N.check(self.lib, self.handle, self.lib.rec_train_phase_b(self.handle, _ptr(gathered), n_shards, _ptr(q_out)),
+                "rec_train_phase_b")
+
+    def train_phase_c(self, q_reduced, losses_out, dh_out):
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_phase_c(self.handle, _ptr(q_reduced), _ptr(losses_out), _ptr(dh_out)),
+                "rec_train_phase_c")
+
+    def train_phase_d(self, dh_reduced):
+        N.check(self.lib, self.handle, self.lib.rec_train_phase_d(self.handle, _ptr(dh_reduced)), "rec_train_phase_d")
+
+    def eval_shard_candidates(self, net_id, batch, head_idx, kmax, records_out):
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_eval_shard_candidates(self.handle, net_id, C.byref(batch), head_idx, kmax,
+                                                   _ptr(records_out)), "rec_eval_shard_candidates")
+
+    def eval_merge(self, batch, opts, gathered, n_shards, acc, topk_ids=None, topk_scores=None):
+        N.check(self.lib, self.handle,
+                self.lib.rec_eval_merge(self.handle, C.byref(batch), C.byref(opts), _ptr(gathered), n_shards,
+                                        C.byref(acc), _ptr(topk_ids), _ptr(topk_scores)), "rec_eval_merge")
+
     def launch_count(self):
         return int(self.lib.rec_launch_count(self.handle))
 

@@ -73,6 +73,23 @@ class NativeSessionNet(nn.Module):
         self._net_id = 0
         self._opt_m: Optional[NetTensors] = None
         self._opt_v: Optional[NetTensors] = None
+        self._vocab_lo, self._vocab_hi = 0, int(action_dim)
+        self._group = None
+
+    def shard_vocabulary(self, lo: int, hi: int, group=None):
+        """Keep only rows [lo, hi) of every head on this rank (vocabulary sharding, multi-GPU).
+        Call on the freshly constructed (CPU) module so every rank starts from the same seeded init."""
+        assert 0 <= lo < hi <= self.action_dim
+        with torch.no_grad():
+            for h in self._head_modules():
+                h.weight.data = h.weight.data[lo:hi].clone().contiguous()
+                h.bias.data = h.bias.data[lo:hi].clone().contiguous()
+        self._vocab_lo, self._vocab_hi, self._group = int(lo), int(hi), group
+        self._engine = None
+
+    @property
+    def is_sharded(self):
+        return (self._vocab_lo, self._vocab_hi) != (0, int(self.action_dim))
 
     # -- engine plumbing -------------------------------------------------------------------
     @property
@@ -110,7 +127,8 @@ class NativeSessionNet(nn.Module):
                                   state_size=self.state_size, bidirectional=self._bidirectional,
                                   n_heads=len(self._HEADS[self._family]), n_nets=1,
                                   use_packed_seq=self.use_packed_seq, frozen_pad_row=self._frozen_pad_row,
-                                  device=dev, max_batch=max(256, batch_hint))
+                                  device=dev, max_batch=max(256, batch_hint), vocab_lo=self._vocab_lo,
+                                  vocab_hi=self._vocab_hi)
             self._net_id = 0
         self._engine.bind(self._net_id, self._net_tensors())
         return self._engine
@@ -139,6 +157,7 @@ class NativeSessionNet(nn.Module):
         return eng.forward_state(self._net_id, s, lengths)
 
     def _all_logits(self, s, lengths):
+        """Materialised logits of every head; on a sharded module: the LOCAL columns [lo, hi)."""
         eng = self._ready(int(s.shape[0]))
         s, lengths = self._dev_inputs(s, lengths)
         h = eng.forward_state(self._net_id, s, lengths)
@@ -239,6 +258,7 @@ class NativeTrainerBase:
         self._stager: Optional[BatchStager] = None
         self._loss_dev = None
         self._pending_steps = [0 for _ in nets]
+        self._shard = None
 
     @staticmethod
     def _seed(torch_rand_seed, python_rand_seed):
@@ -266,7 +286,8 @@ class NativeTrainerBase:
                                   hidden_dim=n0.hidden_dim, state_size=n0.state_size,
                                   bidirectional=n0._bidirectional, n_heads=len(n0._HEADS[n0._family]),
                                   n_nets=len(self._nets), use_packed_seq=n0.use_packed_seq,
-                                  frozen_pad_row=n0._frozen_pad_row, device=dev, max_batch=max(256, B))
+                                  frozen_pad_row=n0._frozen_pad_row, device=dev, max_batch=max(256, B),
+                                  vocab_lo=n0._vocab_lo, vocab_hi=n0._vocab_hi)
             for i, n in enumerate(self._nets):
                 if n._opt_m is None or n._opt_m.emb.device != dev:
                     base = n._net_tensors()
@@ -280,6 +301,16 @@ class NativeTrainerBase:
             for i, n in enumerate(self._nets):
                 self._engine.bind(i, n._net_tensors())
         return self._engine
+
+    def shard_vocabulary(self, rank: int, world: int, group=None):
+        """Vocabulary-shard every head of every net over `world` ranks (call before send_to_device)."""
+        from ..sharded import shard_bounds
+        V = self._nets[0].action_dim
+        lo, hi = shard_bounds(V, rank, world)
+        for n in self._nets:
+            n.shard_vocabulary(lo, hi, group)
+        self._shard = (rank, world, group)
+        self._engine = None
 
     def _set_mode(self, train: bool):
         for n in self._nets:

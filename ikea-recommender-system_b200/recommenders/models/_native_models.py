@@ -15,12 +15,33 @@ def supervised_train_step(trainer, s, a, true_len) -> torch.Tensor:
     if net._family == "bidir" and net.training and net.dropout.p > 0:
         raise NotImplementedError("BidirGRU4Rec dropout > 0 in training mode is not implemented natively yet")
     B = int(s.shape[0])
+    hp = make_hparams(trainer.learning_rate)
+    if trainer._shard is not None:
+        return _sharded_step(trainer, hp, 0, s, a, true_len)[0]
     eng = trainer._ready(B)
     ds, _, da, dln, _, _, _ = trainer._stager.stage(s, a, true_len)
     batch = eng._batch(B, ds, da, dln)
-    hp = make_hparams(trainer.learning_rate)
     eng.train_step_supervised(batch, hp, trainer._loss_dev)
     return trainer._loss_dev[0]
+
+
+def _sharded_step(trainer, hp, main, s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
+    """Vocabulary-sharded step: all-gather the local batches, then phases A-D with their collectives."""
+    from ...sharded import ShardedStep, pack_rows, unpack_rows, all_gather_rows
+    rank, world, group = trainer._shard
+    B = int(s.shape[0])
+    eng = trainer._ready(B * world)
+    ds, dsn, da, dln, dnl, dr, de = trainer._stager.stage(s, a, true_len, r, s_next, true_next_len, is_end)
+    rows = all_gather_rows(pack_rows(ds, da, dln, dr, dsn, dnl, de), group)
+    L = int(ds.shape[1])
+    gs, ga, gln, gr, gsn, gnl, ge = unpack_rows(rows, L, with_q=r is not None)
+    batch = eng._batch(B * world, gs, ga, gln, gr, gsn, gnl, ge)
+    if getattr(trainer, "_sharded_step", None) is None or trainer._sharded_step.eng is not eng:
+        n0 = trainer._nets[0]
+        trainer._sharded_step = ShardedStep(eng, world, group, n0.hidden_dim * (2 if n0._bidirectional else 1))
+    trainer._keep_batch = (gs, ga, gln, gr, gsn, gnl, ge)  # phases read these after this function returns
+    trainer._sharded_step.run(batch, hp, main, trainer._loss_dev, has_q=r is not None)
+    return trainer._loss_dev[:2]
 
 
 def pick_main(trainer):
@@ -31,10 +52,12 @@ def pick_main(trainer):
 def q_train_step(trainer, hp, s, a, r, s_next, true_len, true_next_len, is_end, main=None) -> torch.Tensor:
     """SQN_trainer / SMORL_trainer.train_step; returns device tensor [sup_loss, q_loss]."""
     B = int(s.shape[0])
-    eng = trainer._ready(B)
     if main is None:
         main = pick_main(trainer)
     trainer.last_main = main + 1
+    if trainer._shard is not None:
+        return _sharded_step(trainer, hp, main, s, a, true_len, r, s_next, true_next_len, is_end)
+    eng = trainer._ready(B)
     ds, dsn, da, dln, dnl, dr, de = trainer._stager.stage(s, a, true_len, r, s_next, true_next_len, is_end)
     batch = eng._batch(B, ds, da, dln, dr, dsn, dnl, de)
     eng.train_step_q(batch, hp, main, trainer._loss_dev)

@@ -1,0 +1,93 @@
+"""Vocabulary-sharded multi-GPU execution (one process per GPU, torch.distributed for the plumbing).
+
+Partitioning: rank g of G owns rows [V*g/G, V*(g+1)/G) of EVERY head (weights,
+bias and their Adam state) -- the dominant HBM term (24 B/param/step of dense Adam) scales 1/G.
+Embedding table and GRU are replicated and updated identically on every rank.  Sessions are
+data-parallel at the input: each rank contributes its local batch, the (tiny) batches are all-gathered
+and every rank multiplies the full batch by its vocabulary slice.
+
+Collectives per train step (all <= 1 MB, latency-bound):
+    1. all_gather  packed int64 batch rows                     [G*B, 2L+4]
+    2. all_gather  per-shard head records (max, sum-exp, target logit, argmax, top-k candidates)
+    3. all_reduce  Q(s,a) / Q_boot(s',a*) contributions         [2, G*B, 3]
+    4. all_reduce  dL/dh partials                                [G*B, D]
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(V: int, rank: int, world: int):
+    """Balanced contiguous split of [0, V) (the same on every rank, no communication)."""
+    return V * rank // world, V * (rank + 1) // world
+
+
+# ---- packed batch rows: one int64 row per session ------------------------------------------------
+def pack_rows(s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
+    """[B, 2L+4] int64: s | s_next | a | len | next_len | (r bits | is_end << 32)."""
+    B, L = s.shape
+    out = torch.zeros(B, 2 * L + 4, dtype=torch.int64, device=s.device)
+    out[:, :L] = s
+    out[:, 2 * L] = a
+    out[:, 2 * L + 1] = true_len
+    if r is not None:
+        out[:, L:2 * L] = s_next
+        out[:, 2 * L + 2] = true_next_len
+        rbits = r.to(torch.float32).contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        out[:, 2 * L + 3] = rbits | (is_end.to(torch.int64) << 32)
+    return out
+
+
+def unpack_rows(rows, L, with_q=True):
+    s = rows[:, :L].contiguous()
+    a = rows[:, 2 * L].contiguous()
+    ln = rows[:, 2 * L + 1].contiguous()
+    if not with_q:
+        return s, a, ln, None, None, None, None
+    sn = rows[:, L:2 * L].contiguous()
+    nl = rows[:, 2 * L + 2].contiguous()
+    last = rows[:, 2 * L + 3]
+    r = (last & 0xFFFFFFFF).to(torch.int32).view(torch.float32).contiguous()
+    e = ((last >> 32) & 1).to(torch.uint8).contiguous()
+    return s, a, ln, r, sn, nl, e
+
+
+def all_gather_rows(local_rows, group=None):
+    world = dist.get_world_size(group)
+    out = torch.empty(world * local_rows.shape[0], local_rows.shape[1], dtype=local_rows.dtype,
+                      device=local_rows.device)
+    dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
+    return out
+
+
+class ShardedStep:
+    """Drives rec_train_phase_a..d of one engine with the three collectives in between."""
+
+    def __init__(self, engine, world, group, D):
+        self.eng, self.world, self.group, self.D = engine, world, group, D
+        self.rec = engine.record_floats()
+        self.cap = 0
+
+    def _alloc(self, Bg, dev):
+        self.cap = Bg
+        self.records = torch.empty(Bg, self.rec, dtype=torch.float32, device=dev)
+        self.gathered = torch.empty(self.world, Bg, self.rec, dtype=torch.float32, device=dev)
+        self.q = torch.zeros(2, Bg, 3, dtype=torch.float32, device=dev)
+        self.dh = torch.empty(Bg, self.D, dtype=torch.float32, device=dev)
+
+    def run(self, batch, hp, main_net, losses_out, has_q):
+        Bg = batch.B
+        dev = losses_out.device
+        if Bg != self.cap:
+            self._alloc(Bg, dev)
+        eng = self.eng
+        eng.train_phase_a(batch, hp, main_net, self.records)
+        dist.all_gather_into_tensor(self.gathered, self.records, group=self.group)
+        eng.train_phase_b(self.gathered, self.world, self.q)
+        if has_q:
+            dist.all_reduce(self.q, group=self.group)
+        eng.train_phase_c(self.q, losses_out, self.dh)
+        dist.all_reduce(self.dh, group=self.group)
+        eng.train_phase_d(self.dh)

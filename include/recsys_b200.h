@@ -166,18 +166,23 @@ int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train
 int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
                      float *losses_out);
 
-/* Phase-split variant of the same step for vocabulary-sharded multi-GPU runs; the caller runs the
- * (tiny) collectives between phases.  Unsharded engines may call rec_train_step_* instead.
- *   phase A: GRU forwards + per-shard head statistics  -> partials (engine-owned device buffer)
- *   phase B: given the all-gathered partials of all shards, finish statistics, Q(s',a*) rows
- *   phase C: losses, head backward + fused Adam on the shard -> partial dh (engine-owned)
- *   phase D: given the all-reduced dh, GRU BPTT, GRU/embedding gradients + Adam */
+/* Phase-split variant of the same step for vocabulary-sharded multi-GPU runs: every rank holds the full
+ * (all-gathered) batch, replicas of embedding + GRU and rows [vocab_lo,vocab_hi) of every head; the caller
+ * runs the three (tiny) collectives between the phases.  All buffers are caller-owned device memory.
+ *   phase A: GRU forwards + per-shard head statistics -> records_out[B, rec_record_floats()]: per row
+ *            (max, sum-exp, target logit, argmax value/id of sum_h w_h Q_h(s',.), top-k candidates)
+ *            -> caller ALL-GATHERS the records of all shards into gathered[n_shards, B, record]
+ *   phase B: merges the gathered records (log-sum-exp combine; (score desc, id asc) order), then this
+ *            shard's contribution to Q(s,a) and Q_boot(s',a*) -> q_out[2, B, 3] (zeros for rows owned by
+ *            another shard) -> caller ALL-REDUCES (sum) q_out
+ *   phase C: rewards, TD target, losses (losses_out[0]=sup, [1]=q), head backward + fused Adam on the
+ *            shard -> dh_out[B, D] partial -> caller ALL-REDUCES (sum) dh_out
+ *   phase D: GRU BPTT, GRU / embedding gradients + Adam (replicated, bit-identical on every rank). */
+int rec_record_floats(const rec_engine *e);
 int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
-                      float **partials, int64_t *partials_floats);
-int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float **boot_q,
-                      int64_t *boot_q_floats);
-int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, float *losses_out, float **dh,
-                      int64_t *dh_floats);
+                      float *records_out);
+int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float *q_out);
+int rec_train_phase_c(rec_engine *e, const float *q_reduced, float *losses_out, float *dh_out);
 int rec_train_phase_d(rec_engine *e, const float *dh_reduced);
 
 /* ---- evaluation (replaces evaluate()/update_train_metrics(), eval_protocol.py:123-359) ------ */
@@ -185,14 +190,15 @@ int rec_train_phase_d(rec_engine *e, const float *dh_reduced);
  * device.  topk_ids[B,kmax] (int32, global action ids) and topk_scores[B,kmax] may be NULL. */
 int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, const rec_eval_opts *o,
                    const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores);
-/* Per-shard candidates for sharded evaluation: cand_scores/cand_ids [B,kmax] of the local shard
- * plus (max, sumexp, target-logit-or--inf) per row in stats[B,3]. */
+/* Sharded evaluation (vocabulary-sharded heads over several GPUs): each shard produces one record per
+ * row -- (max, sum-exp, target logit, top-kmax candidates as score/id lists) -- in the caller's device
+ * buffer records_out[B, rec_record_floats()]; the caller all-gathers the records of all shards ... */
 int rec_eval_shard_candidates(rec_engine *e, int net_id, const rec_batch *b, int head_idx, int kmax,
-                              float *h_out, float *cand_scores, int32_t *cand_ids, float *stats);
-/* Merge n_shards candidate lists [n_shards,B,kmax] (+stats [n_shards,B,3]) and accumulate metrics. */
-int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, int n_shards, int kmax,
-                   const float *cand_scores, const int32_t *cand_ids, const float *stats,
-                   const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores);
+                              float *records_out);
+/* ... and every rank merges the gathered [n_shards, B, record_floats] records (score desc, id asc;
+ * log-sum-exp combine) and accumulates the metrics exactly like rec_eval_batch. */
+int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, const float *gathered,
+                   int n_shards, const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores);
 
 /* ---- introspection -------------------------------------------------------------------------- */
 /* Number of kernels this engine launched since creation (bench.py's gpu_launches). */
