@@ -349,7 +349,8 @@ def _virtual_rank_step(trainers, hp_fn, batch, main, has_q=True):
     Bg, L = s.shape
     engs = [t._ready(Bg) for t in trainers]
     rec = engs[0].record_floats()
-    b = engs[0]._batch(Bg, s, a, ln, r.float(), sn, nl, e.to(torch.uint8))
+    r32, e8 = r.float().contiguous(), e.to(torch.uint8).contiguous()  # must outlive all four phases
+    b = engs[0]._batch(Bg, s, a, ln, r32, sn, nl, e8)
     records = [torch.empty(Bg, rec, device=DEV) for _ in range(G)]
     for g in range(G):
         engs[g].train_phase_a(b, hp_fn(trainers[g]), main, records[g])
