@@ -1,0 +1,146 @@
+// Blackwell (sm_100a) tensor-core plumbing written as inline PTX: tcgen05.mma with TMEM accumulators,
+// shared-memory matrix descriptors, mbarrier completion, TMEM allocation and tcgen05.ld.
+//
+// Operand tiles in shared memory all have ONE physical form: blocks of [rows][64 bf16] (128-byte rows)
+// with the 128-byte swizzle (16-byte chunk index XOR (row % 8)), 1024-byte aligned.  The same bytes can
+// be described to the tensor core either as a K-major operand (MN = rows, K = the 64 columns) or as an
+// MN-major operand (MN = the 64 columns, K = rows) -- which is what lets h, W and dlogits each live in
+// shared memory once while feeding three different GEMMs (logits, dW, dh).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a lost completion traps (fails the launch) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
+    if (spins > (1u << 24)) __trap();
+}
+
+// ---- proxies / fences ----------------------------------------------------------------------------
+// generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM ----------------------------------------------------------------------------------------
+// one full warp allocates `cols` (power of two >= 32) columns; base address is written to *dst (smem)
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (32*(warp%4) + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ---------------------------------------------------------------------------------
+// 64-bit shared-memory matrix descriptor (PTX "matrix descriptor", Blackwell version = 1, SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
+  return d;
+}
+// K-major operand: MN = rows of the block (8-row groups 1024 B apart), K = 64 columns of the block
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t block_saddr, int k16) {
+  return smem_desc(block_saddr + k16 * 32, 16, 1024);
+}
+// MN-major operand: MN = columns (next 64 at `mn_block_stride` bytes), K = rows (16 rows per MMA = 2048 B)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t block_saddr, int k16, uint32_t mn_block_stride) {
+  return smem_desc(block_saddr + k16 * 2048, mn_block_stride, 1024);
+}
+// 32-bit instruction descriptor: bf16 x bf16 -> fp32, dense
+__device__ __forceinline__ uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                         // D format F32
+  d |= 1u << 7;                         // A format BF16
+  d |= 1u << 10;                        // B format BF16
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- operand staging -----------------------------------------------------------------------------
+// byte offset of element (row, col) inside a [rows][64 bf16] SWIZZLE_128B block
+__device__ __forceinline__ uint32_t sw128_off(int row, int col) {
+  return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
+}
+// split fp32 into bf16 hi + bf16 lo (x ~= hi + lo, |err| ~ 2^-17 |x|)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// 8 consecutive fp32 (one 16-byte bf16 chunk) -> hi/lo chunks at (row, col8*8) of two blocks
+__device__ __forceinline__ void store_split8(uint8_t *blk_hi, uint8_t *blk_lo, int row, int chunk, const float4 &a,
+                                             const float4 &b) {
+  __nv_bfloat16 h[8], l[8];
+  split_bf16(a.x, h[0], l[0]); split_bf16(a.y, h[1], l[1]); split_bf16(a.z, h[2], l[2]); split_bf16(a.w, h[3], l[3]);
+  split_bf16(b.x, h[4], l[4]); split_bf16(b.y, h[5], l[5]); split_bf16(b.z, h[6], l[6]); split_bf16(b.w, h[7], l[7]);
+  uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+  *reinterpret_cast<uint4 *>(blk_hi + off) = *reinterpret_cast<const uint4 *>(h);
+  *reinterpret_cast<uint4 *>(blk_lo + off) = *reinterpret_cast<const uint4 *>(l);
+}
+
+}  // namespace tc

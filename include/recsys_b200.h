@@ -207,6 +207,11 @@ int64_t rec_launch_count(const rec_engine *e);
 int rec_enable_kernel_timing(rec_engine *e, int on);
 float rec_last_kernel_ms(rec_engine *e, int which); /* which: 0 head-bwd+adam, 1 head-fwd stats, 2 emb adam */
 
+/* Self-test of the tcgen05/TMEM plumbing (bf16x3 split GEMM of one 128-row tile; see csrc/tc_selftest.cu):
+ * mode 0: C[128,128] = A[128,64].B[128,64]^T ; mode 1: C[128,64] = P[128,128]^T.Q[128,64] ;
+ * mode 2: C[128,64] = P[128,128].R[128,64].  Device pointers, fp32. */
+int rec_debug_tc_gemm(int mode, const float *A, const float *B, float *C, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
