@@ -14,6 +14,10 @@ size_t head_bwd_smem_bytes(int D);
 
 static char g_err[512] = "";
 
+static int head_stats_dispatch(rec_engine *e, const HeadStatsArgs &a, int *n_split) {
+  return tc_heads_supported(e) ? launch_head_stats_tc(e, a, n_split) : launch_head_stats(e, a, n_split);
+}
+
 struct EngineExtra {
   float *q_loss_rows;
   double *rowm;
@@ -74,6 +78,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   e->D = c.hidden_dim * e->dirs;
   e->Vloc = c.vocab_hi - c.vocab_lo;
   e->sm_count = prop.multiProcessorCount;
+  e->use_tc = true;
   if (head_bwd_smem_bytes(e->D) > 220 * 1024) {
     snprintf(g_err, sizeof(g_err), "rec_create: head width D=%d exceeds the shared-memory budget of the backward kernel", e->D);
     free(mem);
@@ -99,7 +104,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->emb_grad_rows, float, mb * L * E);
   e->part_stride = 72;
   e->n_split_max = 2 * e->sm_count;
-  ALLOC(e, e->part, float, ((int64_t)e->n_split_max * 64 + 2 * mb) * e->part_stride);
+  ALLOC(e, e->part, float, ((int64_t)e->sm_count * 4 * 128 + 4 * mb) * e->part_stride);
   ALLOC(e, e->row_stats, float, mb * 8);
   ALLOC(e, e->row_ids, int32_t, mb * REC_MAX_TOPK);
   ALLOC(e, e->row_topv, float, mb * REC_MAX_TOPK);
@@ -181,6 +186,11 @@ extern "C" int64_t rec_get_adam_step(const rec_engine *e, int net_id) {
   return e->nets[net_id].adam_step;
 }
 
+extern "C" int rec_set_tensor_cores(rec_engine *e, int on) {
+  if (!e) return REC_EINVAL;
+  e->use_tc = on != 0;
+  return REC_OK;
+}
 extern "C" int64_t rec_launch_count(const rec_engine *e) { return e ? e->launches : -1; }
 extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) { if (!e) return REC_EINVAL; e->timing = on != 0; return REC_OK; }
 extern "C" float rec_last_kernel_ms(rec_engine *e, int which) {
@@ -232,7 +242,7 @@ extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, cons
   HeadStatsArgs a = {};
   a.net_id = 0; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
   int n_split = 0;
-  if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+  if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
   if ((rc = launch_head_merge(e, e->part, n_split, B, 0, true, false))) return rc;
   if ((rc = launch_loss_reduce(e, B, nullptr, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(loss_out, e->loss_buf, sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
@@ -273,13 +283,13 @@ extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_tra
   a.net_id = main_net; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
   a.topk = (n_q == 3) ? (hp->topk_div > hp->topk_nov ? hp->topk_div : hp->topk_nov) : 0;
   int n_split = 0;
-  if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+  if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
   if ((rc = launch_head_merge(e, e->part, n_split, B, a.topk, true, false))) return rc;
   // greedy action a* = argmax_a sum_h w_h Q_h(s', a) on the main net
   HeadStatsArgs g = {};
   g.net_id = main_net; g.h = e->h_state[1]; g.B = B; g.n_arg = n_q;
   g.w[0] = n_q == 3 ? hp->q_weights[0] : 1.f; g.w[1] = hp->q_weights[1]; g.w[2] = hp->q_weights[2];
-  if ((rc = launch_head_stats(e, g, &n_split))) return rc;
+  if ((rc = head_stats_dispatch(e, g, &n_split))) return rc;
   if ((rc = launch_head_merge(e, e->part, n_split, B, 0, false, true))) return rc;
   // Q(s,a) on main, Q_boot(s',a*) on boot: row gather-dots
   if ((rc = launch_row_dots(e, main_net, e->h_state[0], b->a, nullptr, B, 1, n_q, e->q_sa))) return rc;
@@ -322,7 +332,7 @@ extern "C" int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, con
   a.net_id = net_id; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = o->head_idx; a.target = b->a; a.topk = kmax;
   int n_split = 0;
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
-  if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+  if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
   if (e->timing) cudaEventRecord(e->ev[3], e->stream);
   if ((rc = launch_head_merge(e, e->part, n_split, B, kmax, true, false))) return rc;
   return launch_eval_metrics(e, b, o, kmax, acc, extra(e).rowm, topk_ids, topk_scores);
@@ -340,14 +350,14 @@ static int shard_head_pass(rec_engine *e, int net_id, const float *h, const rec_
     HeadStatsArgs a = {};
     a.net_id = net_id; a.h = h; a.B = b->B; a.do_stats = want_stats ? 1 : 0; a.stats_head = stats_head; a.target = b->a;
     a.topk = topk;
-    if ((rc = launch_head_stats(e, a, &n_split))) return rc;
+    if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
     if ((rc = launch_head_merge(e, e->part, n_split, b->B, topk, want_stats, false, summary))) return rc;
   }
   if (n_q > 0) {
     HeadStatsArgs g = {};
     g.net_id = net_id; g.h = e->h_state[1]; g.B = b->B; g.n_arg = n_q;
     g.w[0] = w[0]; g.w[1] = w[1]; g.w[2] = w[2];
-    if ((rc = launch_head_stats(e, g, &n_split))) return rc;
+    if ((rc = head_stats_dispatch(e, g, &n_split))) return rc;
     if ((rc = launch_head_merge(e, e->part, n_split, b->B, 0, false, true, summary))) return rc;
   }
   return REC_OK;

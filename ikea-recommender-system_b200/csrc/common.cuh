@@ -60,6 +60,7 @@ struct rec_engine {
   float *summary;        // [maxB][part_stride] per-row record of this shard
   float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;
+  bool use_tc;           // tensor-core (tcgen05) head kernels when D == 64
   cudaEvent_t ev[6];
   float last_ms[3];
 };
@@ -137,6 +138,8 @@ struct HeadStatsArgs {
   float w[3];
 };
 int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
+bool tc_heads_supported(const rec_engine *e);
+int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats,
                       bool has_argmax, float *summary = nullptr);
 int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld);

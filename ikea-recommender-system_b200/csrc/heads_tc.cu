@@ -1,0 +1,239 @@
+// Full-vocabulary heads on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), D = 64.
+//
+// head_stats_tc_kernel -- forward statistics of one 128-session block against a range of 128-row
+// vocabulary tiles, logits never leave TMEM/registers:
+//     logits tile  L[128 x 128] = h[128 x 64] . W_tile[128 x 64]^T          (tcgen05.mma, K-major x K-major)
+//     epilogue     online (max, sum-exp) + target logit | running top-k (score desc, id asc)
+//                  | running argmax of sum_j w_j Q_j (the heads accumulate into ONE TMEM tile, W_j is
+//                  scaled by w_j while it is converted)
+// fp32 master weights stream from HBM once per pass; each thread converts its slice to a bf16 hi + bf16 lo
+// pair on the way into shared memory (128-byte-swizzled UMMA layout) and the product is evaluated as
+// hi*hi + hi*lo + lo*hi with fp32 accumulation ("bf16x3", ~1e-5 relative error -- parity with the fp32
+// oracle at 1e-3 needs more than one bf16 pass, and with K = 64 the extra MMAs are nearly free).
+// Software pipeline per CTA (all 8 warps cooperate, one elected thread issues the MMAs):
+//     convert W(u+1) -> smem[(u+1)&1]  ||  tensor core runs MMA(u)  ;  barrier ;
+//     issue MMA(u+1) -> TMEM[(g+1)&1]  ;  wait MMA(u) ; epilogue(u) from TMEM[g&1]
+#include "common.cuh"
+#include "tc.cuh"
+
+#define PART_TOPK_OFF 5
+constexpr int BLK = 128 * 128;  // bytes of one [128 rows][64 bf16] operand block
+
+struct TcHeadPtrs {
+  const float *w[REC_MAX_HEADS];
+  const float *b[REC_MAX_HEADS];
+};
+
+// fp32 [rows, 64] row-major (rows r0.. of a matrix with nrows rows) -> hi/lo swizzled blocks, 256 threads
+__device__ __forceinline__ void stage_rows64(uint8_t *blk_hi, uint8_t *blk_lo, const float *__restrict__ src, int r0,
+                                             int nrows, float scale, int tid) {
+  float4 a[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = tid + 256 * i, row = c >> 3, ch = c & 7;
+    a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b[i] = a[i];
+    if (r0 + row < nrows) {
+      const float4 *p = reinterpret_cast<const float4 *>(src + (int64_t)(r0 + row) * 64 + ch * 8);
+      a[i] = p[0];
+      b[i] = p[1];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = tid + 256 * i, row = c >> 3, ch = c & 7;
+    if (scale != 1.f) {
+      a[i].x *= scale; a[i].y *= scale; a[i].z *= scale; a[i].w *= scale;
+      b[i].x *= scale; b[i].y *= scale; b[i].z *= scale; b[i].w *= scale;
+    }
+    tc::store_split8(blk_hi, blk_lo, row, ch, a[i], b[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
+                                                               int vocab_lo, int n_tiles, int do_stats, int first_head,
+                                                               int upg, float w0, float w1, float w2,
+                                                               const int64_t *__restrict__ target, int topk,
+                                                               float *__restrict__ part, int part_stride) {
+  extern __shared__ uint8_t raw[];
+  uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *h_hi = sm, *h_lo = sm + BLK;
+  uint8_t *w_st = sm + 2 * BLK;                                   // stage s: hi at w_st + s*2*BLK, lo at + BLK
+  float *bias_g = reinterpret_cast<float *>(sm + 6 * BLK);       // [3][128] (3-deep: a thread may run one barrier ahead)
+  float *tv = bias_g + 384;                                       // [topk][256]
+  int *ti = reinterpret_cast<int *>(tv + (size_t)topk * 256);     // [topk][256]
+  __shared__ uint64_t mbar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, ch = warp >> 2;  // TMEM lane quarter, column half
+  const int sp = blockIdx.x, n_split = gridDim.x, bb = blockIdx.y;
+  const int b0 = bb * 128;
+  const int per = (n_tiles + n_split - 1) / n_split;
+  const int t_lo = sp * per, t_hi = min(n_tiles, t_lo + per);
+  const int n_groups = max(0, t_hi - t_lo), n_units = n_groups * upg;
+  const float wq[3] = {w0, w1, w2};
+  const bool argmode = !do_stats && topk == 0;
+
+  if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  stage_rows64(h_hi, h_lo, h, b0, B, 1.f, tid);
+
+  auto load_unit = [&](int u) {
+    const int g = u / upg, hh = u - g * upg, head = first_head + hh, v0 = (t_lo + g) * 128, s = u & 1;
+    const float scale = argmode && upg > 1 ? wq[hh] : 1.f;
+    stage_rows64(w_st + s * 2 * BLK, w_st + s * 2 * BLK + BLK, hp.w[head], v0, Vloc, scale, tid);
+    if (tid < 128) {
+      float bv = (v0 + tid < Vloc) ? __ldg(hp.b[head] + v0 + tid) * scale : 0.f;
+      float *dst = bias_g + (g % 3) * 128 + tid;
+      *dst = (hh == 0) ? bv : (*dst + bv);
+    }
+  };
+  auto issue_unit = [&](int u) {  // one thread
+    const int g = u / upg, hh = u - g * upg, s = u & 1;
+    const uint32_t d = tmem_base_s + (uint32_t)(g & 1) * 128;
+    const uint32_t ah = tc::smem_u32(h_hi), al = tc::smem_u32(h_lo);
+    const uint32_t bh = tc::smem_u32(w_st + s * 2 * BLK), bl = bh + BLK;
+    const uint32_t id = tc::instr_desc(128, 128, 0, 0);
+    bool acc = hh > 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { tc::mma_bf16(d, tc::desc_kmajor(a, k), tc::desc_kmajor(b, k), id, acc); acc = true; }
+    }
+    tc::mma_commit(&mbar[s]);
+  };
+
+  // per-thread running state: this thread owns batch row (b0 + q*32 + lane), tile columns [ch*64, ch*64+64)
+  const int row = b0 + q * 32 + lane;
+  float m_run = REC_NEG_INF, s_run = 0.f, tgt = REC_NEG_INF, av = REC_NEG_INF, tau = REC_NEG_INF;
+  int ai = 0x7fffffff, cnt = 0;
+  const int64_t trow = (do_stats && target && row < B) ? target[row] - vocab_lo : -1;
+
+  if (n_units > 0) load_unit(0);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (n_units > 0 && tid == 0) issue_unit(0);
+
+  for (int u = 0; u < n_units; ++u) {
+    if (u + 1 < n_units) {
+      if (u >= 1) tc::mbar_wait(&mbar[(u + 1) & 1], ((u - 1) >> 1) & 1);  // MMA(u-1) done: its smem stage is free
+      load_unit(u + 1);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (u + 1 < n_units && tid == 0) issue_unit(u + 1);
+    const int g = u / upg;
+    if (u - g * upg != upg - 1) continue;  // accumulate the remaining heads of this group first
+    tc::mbar_wait(&mbar[u & 1], (u >> 1) & 1);
+    tc::tc_fence_after();
+    // ---- epilogue of group g ----
+    const int v0 = (t_lo + g) * 128, c_lo = v0 + ch * 64;
+    float l[64];
+    const uint32_t taddr = tmem_base_s + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * 128 + ch * 64);
+    tc::tmem_ld32(taddr, l);
+    tc::tmem_ld32(taddr + 32, l + 32);
+    tc::tmem_ld_wait();
+    const float *bg = bias_g + (g % 3) * 128 + ch * 64;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      float4 b4 = *reinterpret_cast<const float4 *>(bg + j);
+      l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
+    }
+    if (c_lo + 64 > Vloc) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
+    }
+    if (do_stats) {
+      float tmax = REC_NEG_INF;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) tmax = fmaxf(tmax, l[j]);
+      const float nm = fmaxf(m_run, tmax);
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) ps += __expf(l[j] - nm);
+      s_run = s_run * __expf(m_run - nm) + ps;
+      m_run = nm;
+      if (trow >= c_lo && trow < c_lo + 64) {
+        const int tj = (int)(trow - c_lo);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) if (j == tj) tgt = l[j];
+      }
+    }
+    if (topk > 0) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float v = l[j];
+        if (v > tau) {
+          int p = cnt < topk ? cnt : topk - 1;
+          while (p > 0 && tv[(p - 1) * 256 + tid] < v) {
+            tv[p * 256 + tid] = tv[(p - 1) * 256 + tid];
+            ti[p * 256 + tid] = ti[(p - 1) * 256 + tid];
+            --p;
+          }
+          tv[p * 256 + tid] = v;
+          ti[p * 256 + tid] = vocab_lo + c_lo + j;
+          if (cnt < topk) ++cnt;
+          tau = cnt == topk ? tv[(topk - 1) * 256 + tid] : REC_NEG_INF;
+        }
+      }
+    }
+    if (argmode) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j)
+        if (l[j] > av) { av = l[j]; ai = vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+    }
+  }
+
+  // publish: record (sp*2 + ch) of this row
+  if (row < B) {
+    float *o = part + ((int64_t)(sp * 2 + ch) * B + row) * part_stride;
+    o[0] = m_run; o[1] = s_run; o[2] = tgt; o[3] = av; o[4] = __int_as_float(ai);
+    for (int k = 0; k < topk; ++k) {
+      o[PART_TOPK_OFF + k] = k < cnt ? tv[k * 256 + tid] : REC_NEG_INF;
+      o[PART_TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(k < cnt ? ti[k * 256 + tid] : 0x7fffffff);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+static TcHeadPtrs tc_head_ptrs(const rec_engine *e, int net_id) {
+  TcHeadPtrs hp;
+  for (int i = 0; i < REC_MAX_HEADS; ++i) { hp.w[i] = e->nets[net_id].p.head_w[i]; hp.b[i] = e->nets[net_id].p.head_b[i]; }
+  return hp;
+}
+
+bool tc_heads_supported(const rec_engine *e) { return e->D == 64 && e->use_tc; }
+
+// Same contract as launch_head_stats (heads.cu); *n_split_out counts RECORDS per row (2 per CTA column).
+int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
+  const int n_tiles = cdiv(e->Vloc, 128), nb = cdiv(a.B, 128);
+  int n_split = cdiv(e->sm_count, nb);
+  if (n_split > n_tiles) n_split = n_tiles;
+  if (n_split < 1) n_split = 1;
+  int per = cdiv(n_tiles, n_split);
+  n_split = cdiv(n_tiles, per);
+  const size_t smem = 1024 + 6 * (size_t)BLK + 1536 + (size_t)a.topk * 256 * 8;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    REC_CUDA(e, cudaFuncSetAttribute(head_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  dim3 grid(n_split, nb);
+  const bool arg = a.n_arg > 0;
+  head_stats_tc_kernel<<<grid, 256, smem, e->stream>>>(tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo, n_tiles,
+                                                      arg ? 0 : a.do_stats, arg ? 1 : a.stats_head, arg ? a.n_arg : 1,
+                                                      a.w[0], a.w[1], a.w[2], a.target, arg ? 0 : a.topk, e->part,
+                                                      e->part_stride);
+  REC_LAUNCH_CHECK(e);
+  *n_split_out = 2 * n_split;
+  return REC_OK;
+}

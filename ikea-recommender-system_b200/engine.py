@@ -215,6 +215,9 @@ class Engine:
                 self.lib.rec_eval_merge(self.handle, C.byref(batch), C.byref(opts), _ptr(gathered), n_shards,
                                         C.byref(acc), _ptr(topk_ids), _ptr(topk_scores)), "rec_eval_merge")
 
+    def set_tensor_cores(self, on: bool):
+        self.lib.rec_set_tensor_cores(self.handle, int(on))
+
     def launch_count(self):
         return int(self.lib.rec_launch_count(self.handle))
 

@@ -201,6 +201,8 @@ int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, co
                    int n_shards, const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores);
 
 /* ---- introspection -------------------------------------------------------------------------- */
+/* Debug/A-B switch: 0 forces the generic CUDA-core head kernels even when the tcgen05 path applies (D == 64). */
+int rec_set_tensor_cores(rec_engine *e, int on);
 /* Number of kernels this engine launched since creation (bench.py's gpu_launches). */
 int64_t rec_launch_count(const rec_engine *e);
 /* CUDA-event time (ms) of the most recent dominant-kernel launch when profiling is enabled. */

@@ -241,10 +241,11 @@ def test_evaluate_matches_reference_fixture(pkg):
     assert all(isinstance(v, set) for v in out[2].values())
 
 
-def test_topk_ties_lowest_id_first(pkg):
+@pytest.mark.parametrize("hidden", [8, 64])  # 8: CUDA-core head kernels, 64: tcgen05 head kernels
+def test_topk_ties_lowest_id_first(pkg, hidden):
     """Exact ties: zero head weights, bias with repeated values -> logits == bias for every session."""
     N, V, B, K = 50, 300, 70, 20
-    net = pkg.GRU4Rec(hidden_size=8, embedding_dim=8, item_num=N, state_size=5, action_dim=V)
+    net = pkg.GRU4Rec(hidden_size=hidden, embedding_dim=hidden, item_num=N, state_size=5, action_dim=V)
     rng = np.random.default_rng(0)
     bias = torch.from_numpy(rng.integers(0, 6, size=V).astype(np.float32))
     with torch.no_grad():
@@ -425,3 +426,37 @@ def test_multi_gpu_equals_oracle_when_two_gpus_present(pkg):
            "127.0.0.1", "--master-port", "29613", os.path.join(root, "tests", "dist_equivalence.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "dist_equivalence ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_tensor_core_heads_agree_with_cuda_core_heads(pkg):
+    """A/B on the same engine: tcgen05 (bf16x3) head statistics vs the fp32 CUDA-core kernels."""
+    from ikea_recommender_system_b200 import _native as N_
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    torch.manual_seed(4)
+    N, B, K = 20000, 333, 20
+    net = pkg.GRU4Rec(hidden_size=64, embedding_dim=64, item_num=N, state_size=10, action_dim=N)
+    with torch.no_grad():
+        net.embedding.weight.mul_(30.0)
+        net.output.weight.mul_(15.0)
+    net.to(DEV)
+    eng = net._ready(B)
+    rows = _syn().make_replay_rows_fast(B, N, 10, seed=2)
+    s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
+    ds, dl = net._dev_inputs(s, ln)
+    da = a.to(DEV)
+    o = N_.RecEvalOpts()
+    o.head_idx, o.n_k, o.n_cov = 0, 1, 0
+    o.ks[0] = K
+    out = {}
+    for on in (True, False):
+        eng.set_tensor_cores(on)
+        acc = EvalAccumulators(torch.device(DEV), N)
+        ids = torch.empty(B, K, dtype=torch.int32, device=DEV)
+        sc = torch.empty(B, K, dtype=torch.float32, device=DEV)
+        eng.eval_batch(0, eng._batch(B, ds, da, dl), o, acc.struct, topk_ids=ids, topk_scores=sc)
+        out[on] = (ids.cpu(), sc.cpu(), acc.read())
+    eng.set_tensor_cores(True)
+    assert torch.equal(out[True][0], out[False][0])
+    assert_close(out[True][1], out[False][1], rtol=1e-4, atol=1e-4)
+    assert abs(out[True][2]["loss_sum"] - out[False][2]["loss_sum"]) <= 1e-4 * abs(out[False][2]["loss_sum"])
+    assert np.array_equal(out[True][2]["hits"], out[False][2]["hits"])
