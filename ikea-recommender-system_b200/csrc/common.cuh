@@ -140,6 +140,9 @@ struct HeadStatsArgs {
 int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 bool tc_heads_supported(const rec_engine *e);
 int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
+bool tc_bwd_supported(const rec_engine *e, int B);
+int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                            float bc2_sqrt, const rec_train_hparams *hp, float inv_B, int *n_slices);
 int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats,
                       bool has_argmax, float *summary = nullptr);
 int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld);

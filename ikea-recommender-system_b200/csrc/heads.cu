@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, co
                                                             const float *__restrict__ dq, int B, int D, int Vloc,
                                                             int vocab_lo, int n_tiles, float inv_B,
                                                             float *__restrict__ dh_part, float b1, float b2,
-                                                            float eps, float step_size, float bc2_sqrt) {
+                                                            float eps, float step_size, float bc2_sqrt,
+                                                            int head_begin) {
   extern __shared__ __align__(16) float dyn[];
   const int DP = D + 4;
   float *dW = dyn;                                   // [TN][DP]
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, co
   float(*DLT)[TM + 4] = reinterpret_cast<float(*)[TM + 4]>(DL + TM);  // [TN][TM+4]  dl[n][m]
   float(*Hc)[TN + 4] = reinterpret_cast<float(*)[TN + 4]>(DLT + TN);  // [64][68] h chunk / W chunk
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int head = blockIdx.y;
+  const int head = blockIdx.y + head_begin;
   float *__restrict__ W = hp.w[head];
   float *dh_slice = dh_part + (int64_t)blockIdx.x * B * D;
   bool first_tile = true;
@@ -676,14 +677,33 @@ int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const r
     REC_LAUNCH_CHECK(e);
   }
   if (e->timing) cudaEventRecord(e->ev[0], e->stream);
-  dim3 grid(n_cta, e->cfg.n_heads);
-  head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
-                                                      n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
-                                                      step_size, bc2_sqrt);
-  REC_LAUNCH_CHECK(e);
+  int n_dense_slices = n_cta;
+  if (tc_bwd_supported(e, B)) {
+    // supervised head on the tensor cores; the Q heads (row-sparse gradients) keep the streaming kernel
+    int rc = launch_head_bwd_adam_tc(e, net_id, h, b, B, step_size, bc2_sqrt, hp, inv_B, &n_dense_slices);
+    if (rc) return rc;
+    if (n_q > 0) {
+      dim3 grid(n_cta, n_q);
+      head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
+                                                          n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
+                                                          step_size, bc2_sqrt, 1);
+      REC_LAUNCH_CHECK(e);
+    }
+    if (n_q > 0 && n_dense_slices != n_cta) {
+      // keep the Q-head dh slice adjacent to the dense slices
+      REC_CUDA(e, cudaMemcpyAsync(e->dh_part + (int64_t)n_dense_slices * B * e->D, q_slice, sizeof(float) * (size_t)B * e->D,
+                                  cudaMemcpyDeviceToDevice, e->stream));
+    }
+  } else {
+    dim3 grid(n_cta, e->cfg.n_heads);
+    head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
+                                                        n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
+                                                        step_size, bc2_sqrt, 0);
+    REC_LAUNCH_CHECK(e);
+  }
   if (e->timing) cudaEventRecord(e->ev[1], e->stream);
   int64_t n = (int64_t)B * e->D;
-  dh_reduce_kernel<<<(int)cdiv64(n, 256), 256, 0, e->stream>>>(e->dh_part, n_cta + (n_q > 0 ? 1 : 0), n, e->dh);
+  dh_reduce_kernel<<<(int)cdiv64(n, 256), 256, 0, e->stream>>>(e->dh_part, n_dense_slices + (n_q > 0 ? 1 : 0), n, e->dh);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
 }

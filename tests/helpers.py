@@ -32,12 +32,27 @@ def assert_close(a, b, rtol=RTOL, atol=1e-5, what=""):
                                 f"max ratio {float((err / tol).max()):.2f}"
 
 
-def assert_state_close(sd_mine, sd_ref, rtol=RTOL, atol=1e-5, skip=()):
+def assert_state_close(sd_mine, sd_ref, rtol=RTOL, atol=1e-5, skip=(), outlier_frac=0.0, outlier_atol=0.0):
+    """Parameter parity after Adam steps.  Adam divides by sqrt(v): an element whose gradient nearly
+    cancels (|g| tiny against its summands) turns 1e-7-level summation-order noise into an O(1e-2 * lr)
+    change of the update -- the CPU reference itself moves by ~4e-6 when its BLAS thread count changes.
+    So besides the element-wise bound, a fraction `outlier_frac` of the elements of a tensor may exceed it,
+    but never by more than `outlier_atol` (a few percent of lr * steps)."""
     assert list(sd_mine.keys()) == list(sd_ref.keys())
     for k in sd_ref:
         if k in skip:
             continue
-        assert_close(sd_mine[k], sd_ref[k], rtol, atol, what=k)
+        if outlier_frac <= 0:
+            assert_close(sd_mine[k], sd_ref[k], rtol, atol, what=k)
+            continue
+        a = torch.as_tensor(sd_mine[k]).detach().cpu().double()
+        b = torch.as_tensor(sd_ref[k]).detach().cpu().double()
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        err = (a - b).abs()
+        bad = err > atol + rtol * b.abs()
+        n_bad = int(bad.sum())
+        assert n_bad <= max(1, int(outlier_frac * bad.numel())), f"{k}: {n_bad}/{bad.numel()} beyond rtol={rtol}"
+        assert float(err.max()) <= outlier_atol, f"{k}: max abs err {float(err.max()):.3e} > {outlier_atol}"
 
 
 class synced_random:

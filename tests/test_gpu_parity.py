@@ -15,6 +15,8 @@ from helpers import (load_golden, sd_from_golden, rows_from_golden, assert_close
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ATOL_P = 2e-5
+# outliers (see helpers.assert_state_close): <= 0.1 % of a tensor, each within 2 % of lr * steps
+OUT = dict(outlier_frac=1e-3, outlier_atol=0.02 * 0.01 * 4)
 
 
 def _syn():
@@ -108,7 +110,7 @@ def test_supervised_train_steps_match_reference_fixture(pkg, name, family):
     assert_close(t.gru_model(s, ln), g["fwd_logits0"], rtol=1e-4, atol=1e-5, what="fwd logits")
     losses = [t.train_step(b[0], b[1], b[4]) for b in batches]
     assert_close(losses, g["losses"], rtol=RTOL, atol=1e-6, what="losses")
-    assert_state_close(t.gru_model.state_dict(), sd_from_golden(g, "final"), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.gru_model.state_dict(), sd_from_golden(g, "final"), rtol=RTOL, atol=ATOL_P, **OUT)
 
 
 # ------------------------------------------------------------------------------------ SQN / SMORL
@@ -129,8 +131,8 @@ def test_sqn_train_steps_match_reference_fixture(pkg, name):
         mains.append(t.last_main)
     assert mains == list(g["mains"])
     assert_close(losses, g["losses"], rtol=RTOL, atol=1e-5, what="(sup, q) losses")
-    assert_state_close(t.DQN_1.state_dict(), sd_from_golden(g, "final1"), rtol=RTOL, atol=ATOL_P)
-    assert_state_close(t.DQN_2.state_dict(), sd_from_golden(g, "final2"), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.DQN_1.state_dict(), sd_from_golden(g, "final1"), rtol=RTOL, atol=ATOL_P, **OUT)
+    assert_state_close(t.DQN_2.state_dict(), sd_from_golden(g, "final2"), rtol=RTOL, atol=ATOL_P, **OUT)
 
 
 def test_smorl_train_steps_match_oracle_fixture(pkg):
@@ -157,8 +159,8 @@ def test_smorl_train_steps_match_oracle_fixture(pkg):
         mains.append(t.last_main)
     assert mains == list(g["mains"])
     assert_close(losses, g["losses"], rtol=RTOL, atol=1e-5, what="(sup, q) losses")
-    assert_state_close(t.SMORL_1.state_dict(), sd_from_golden(g, "final1"), rtol=RTOL, atol=ATOL_P)
-    assert_state_close(t.SMORL_2.state_dict(), sd_from_golden(g, "final2"), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.SMORL_1.state_dict(), sd_from_golden(g, "final1"), rtol=RTOL, atol=ATOL_P, **OUT)
+    assert_state_close(t.SMORL_2.state_dict(), sd_from_golden(g, "final2"), rtol=RTOL, atol=ATOL_P, **OUT)
 
 
 def test_sqn_cfg2_shapes_against_live_oracle(pkg):
@@ -178,8 +180,8 @@ def test_sqn_cfg2_shapes_against_live_oracle(pkg):
         rng.advance()
         assert t.last_main == ref.last_main
         assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} losses")
-    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=RTOL, atol=ATOL_P)
-    assert_state_close(t.DQN_2.state_dict(), ref.DQN_2.state_dict(), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=RTOL, atol=ATOL_P, **OUT)
+    assert_state_close(t.DQN_2.state_dict(), ref.DQN_2.state_dict(), rtol=RTOL, atol=ATOL_P, **OUT)
 
 
 def test_bidir_sqn_cfg3_like(pkg):
@@ -198,8 +200,8 @@ def test_bidir_sqn_cfg3_like(pkg):
         rng.replay(); got = t.train_step(*b)
         rng.advance()
         assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} losses")
-    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=RTOL, atol=ATOL_P)
-    assert_state_close(t.DQN_2.state_dict(), ref.DQN_2.state_dict(), rtol=RTOL, atol=ATOL_P)
+    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=RTOL, atol=ATOL_P, **OUT)
+    assert_state_close(t.DQN_2.state_dict(), ref.DQN_2.state_dict(), rtol=RTOL, atol=ATOL_P, **OUT)
 
 
 # ------------------------------------------------------------------------------------ evaluation
@@ -406,9 +408,8 @@ def test_vocab_sharded_phases_equal_unsharded_and_oracle(pkg):
         for g in range(G):
             lo, hi = shard_bounds(V, g, G)
             mine = shards[g]._nets[net_i].state_dict()
-            for k in sd:
-                want_k = sd[k][lo:hi] if ("head" in k) else sd[k]
-                assert_close(mine[k], want_k, rtol=RTOL, atol=ATOL_P, what=f"net{net_i} rank{g} {k}")
+            want_sd = {k: (sd[k][lo:hi] if ("head" in k) else sd[k]) for k in sd}
+            assert_state_close(mine, want_sd, rtol=RTOL, atol=ATOL_P, outlier_frac=1e-3, outlier_atol=0.02 * 0.01 * 3)
         # replicated tensors stay bit-identical across ranks
         for k in ("embedding.weight", "base_model.weight_hh_l0"):
             assert torch.equal(shards[0]._nets[net_i].state_dict()[k], shards[1]._nets[net_i].state_dict()[k])
@@ -460,3 +461,53 @@ def test_tensor_core_heads_agree_with_cuda_core_heads(pkg):
     assert_close(out[True][1], out[False][1], rtol=1e-4, atol=1e-4)
     assert abs(out[True][2]["loss_sum"] - out[False][2]["loss_sum"]) <= 1e-4 * abs(out[False][2]["loss_sum"])
     assert np.array_equal(out[True][2]["hits"], out[False][2]["hits"])
+
+
+def test_head_gradient_wrt_state_matches_autograd(pkg):
+    """dL/dh of the fused head backward (tensor-core path at D = 64) against torch autograd on the oracle:
+    the 'gradients within 1e-3' clause of the north star, checked directly (phase C exposes dh)."""
+    V, B, L = 3000, 96, 10
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=V, state_size=L, action_dim=V, gamma=0.5, gru_layers=1)
+    ref = oracle.SQNTrainer(**kw)
+    t = pkg.SQN_trainer(device=DEV, **kw)
+    with torch.no_grad():
+        for n in (ref.DQN_1, ref.DQN_2):
+            n.embedding.weight.mul_(25.0)
+            n.sup_head_output.weight.mul_(8.0)
+            n.q_head_output.weight.mul_(8.0)
+    t.DQN_1.load_state_dict(ref.DQN_1.state_dict())
+    t.DQN_2.load_state_dict(ref.DQN_2.state_dict())
+    t.send_to_device()
+    rows = _syn().make_replay_rows(B, V, L, seed=12)
+    s, a, r, sn, ln, nl, e = _syn().as_torch_batch(rows, 0, B)
+    # oracle: loss as a function of the final state of main(s)
+    main, boot = ref.DQN_1, ref.DQN_2
+    h = main.final_state(s, ln).detach().requires_grad_(True)
+    sup, q = main.sup_head_output(h), main.q_head_output(h)
+    with torch.no_grad():
+        a_star = torch.argmax(main(sn, nl)[1], dim=1, keepdim=True)
+        bv = boot(sn, ln)[1].gather(1, a_star)
+        bv[e] = 0.0
+    loss = torch.mean((r.unsqueeze(1) + 0.5 * bv - q.gather(1, a.unsqueeze(1))) ** 2) + torch.nn.functional.cross_entropy(sup, a)
+    want = torch.autograd.grad(loss, h)[0]
+    # native: phases A-C on the unsharded engine (one "shard")
+    eng = t._ready(B)
+    d = lambda x, dt: x.to(DEV, dt).contiguous()
+    ds, da, dr, dsn, dln, dnl, de = d(s, torch.int64), d(a, torch.int64), d(r, torch.float32), d(sn, torch.int64), \
+        d(ln, torch.int64), d(nl, torch.int64), d(e, torch.uint8)
+    batch = eng._batch(B, ds, da, dln, dr, dsn, dnl, de)
+    rec = torch.empty(B, eng.record_floats(), device=DEV)
+    eng.train_phase_a(batch, t._hp(), 0, rec)
+    qb = torch.zeros(2, B, 3, device=DEV)
+    eng.train_phase_b(rec.unsqueeze(0).contiguous(), 1, qb)
+    losses = torch.zeros(8, device=DEV)
+    dh = torch.empty(B, 64, device=DEV)
+    eng.train_phase_c(qb, losses, dh)
+    eng.train_phase_d(dh)
+    torch.cuda.synchronize()
+    got = dh.cpu()
+    scale = want.abs().max(dim=1, keepdim=True).values
+    assert float(((got - want).abs() / scale).max()) <= 1e-3
+    ce = float(torch.nn.functional.cross_entropy(sup, a).detach())
+    assert_close(losses[:2], [ce, float(loss.detach()) - ce], rtol=RTOL, atol=1e-5)
