@@ -116,6 +116,9 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->astar, int32_t, mb);
   ALLOC(e, extra(e).q_loss_rows, float, mb);
   ALLOC(e, e->summary, float, mb * e->part_stride);
+  ALLOC(e, e->q_grad_rows, float, mb * 3 * D);
+  ALLOC(e, e->q_bgrad, float, mb * 3);
+  ALLOC(e, e->q_slot, int32_t, e->Vloc);
   ALLOC(e, e->qpack, float, 2 * mb * 3);
   ALLOC(e, extra(e).rowm, double, mb * (3 * REC_MAX_KLIST + 3));
   for (int n = 0; n < c.n_nets; ++n)
@@ -123,8 +126,9 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
       ALLOC(e, e->nets[n].w_ihT[d], float, G * E);
       ALLOC(e, e->nets[n].w_hhT[d], float, G * H);
     }
-  for (int i = 0; i < 6; ++i) cudaEventCreate(&e->ev[i]);
-  if (launch_fill_i32(e, e->emb_slot, (int64_t)c.item_num + 1, -1) != REC_OK) {
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&e->ev[i]);
+  if (launch_fill_i32(e, e->emb_slot, (int64_t)c.item_num + 1, -1) != REC_OK ||
+      launch_fill_i32(e, e->q_slot, e->Vloc, -1) != REC_OK) {
     snprintf(g_err, sizeof(g_err), "%s", e->err);
     rec_destroy(e);
     return REC_ECUDA;
@@ -143,14 +147,14 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
       if (e->nets[n].w_ihT[d]) cudaFree(e->nets[n].w_ihT[d]);
       if (e->nets[n].w_hhT[d]) cudaFree(e->nets[n].w_hhT[d]);
     }
-  for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   free(e);
 }
 
@@ -194,7 +198,7 @@ extern "C" int rec_set_tensor_cores(rec_engine *e, int on) {
 extern "C" int64_t rec_launch_count(const rec_engine *e) { return e ? e->launches : -1; }
 extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) { if (!e) return REC_EINVAL; e->timing = on != 0; return REC_OK; }
 extern "C" float rec_last_kernel_ms(rec_engine *e, int which) {
-  if (!e || which < 0 || which > 2) return -1.f;
+  if (!e || which < 0 || which > 3) return -1.f;
   float ms = -1.f;
   if (cudaEventSynchronize(e->ev[2 * which + 1]) != cudaSuccess) return -1.f;
   if (cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) return -1.f;

@@ -57,11 +57,14 @@ struct rec_engine {
   rec_train_hparams cur_hp;
   int cur_main, cur_topk, cur_phase;
   float cur_step_size, cur_bc2_sqrt;
+  float *q_grad_rows;    // [maxB][n_q][D] row-sparse Q-head gradients
+  float *q_bgrad;        // [maxB][n_q]
+  int32_t *q_slot;       // [Vloc] leader batch row of each action or -1
   float *summary;        // [maxB][part_stride] per-row record of this shard
   float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;
   bool use_tc;           // tensor-core (tcgen05) head kernels when D == 64
-  cudaEvent_t ev[6];
+  cudaEvent_t ev[8];
   float last_ms[3];
 };
 
@@ -125,6 +128,8 @@ int launch_gru_transpose(rec_engine *e, int net_id);
 // embed.cu
 int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
                             float step_size, float bc2_sqrt, const rec_train_hparams *hp);
+int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                        float bc2_sqrt, const rec_train_hparams *hp);
 // heads.cu
 struct HeadStatsArgs {
   int net_id;

@@ -129,23 +129,138 @@ __device__ __forceinline__ void adam_update4(float4 &p, float4 &m, float4 &v, co
 #undef REC_AD1
 }
 
-// Dense Adam sweep over the table; one float4 per thread, grid-stride.
-__global__ void __launch_bounds__(256) emb_adam_kernel(float4 *__restrict__ p, float4 *__restrict__ m,
-                                                       float4 *__restrict__ v,
-                                                       const int32_t *__restrict__ slot_of_row,
-                                                       const float4 *__restrict__ grad_rows, int64_t n4, int E4,
-                                                       float b1, float b2, float eps, float step_size,
-                                                       float bc2_sqrt) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = i / E4;
-    int c = (int)(i - row * E4);
-    int slot = __ldg(slot_of_row + row);
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (slot >= 0) g = __ldg(grad_rows + (int64_t)slot * E4 + c);
-    float4 pv = p[i], mv = m[i], vv = v[i];
-    adam_update4(pv, mv, vv, g, b1, b2, eps, step_size, bc2_sqrt);
-    p[i] = pv; m[i] = mv; v[i] = vv;
+// Dense Adam sweep over a [rows, D] matrix whose gradient is row-sparse: row r has gradient
+// grad_rows[slot_of_row[r] * grad_stride4 + c] when slot_of_row[r] >= 0, else 0.  HBM-bound streaming
+// kernel (24 B/param): every thread keeps UNROLL independent (p, m, v) float4 triples in flight.
+// Optional bias vector (one element per row) is updated by the thread that owns column chunk 0.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) adam_stream_kernel(float4 *__restrict__ p, float4 *__restrict__ m,
+                                                          float4 *__restrict__ v,
+                                                          const int32_t *__restrict__ slot_of_row,
+                                                          const float4 *__restrict__ grad_rows, int grad_stride4,
+                                                          int64_t n4, int D4, float *__restrict__ bp,
+                                                          float *__restrict__ bm, float *__restrict__ bv,
+                                                          const float *__restrict__ bgrad, int bgrad_stride,
+                                                          float b1, float b2, float eps, float step_size,
+                                                          float bc2_sqrt) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
+    float4 pv[UNROLL], mv[UNROLL], vv[UNROLL], g[UNROLL];
+    int slot[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        pv[u] = p[i]; mv[u] = m[i]; vv[u] = v[i];
+        slot[u] = __ldg(slot_of_row + i / D4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        const int64_t row = i / D4;
+        const int c = (int)(i - row * D4);
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (slot[u] >= 0) g[u] = __ldg(grad_rows + (int64_t)slot[u] * grad_stride4 + c);
+        adam_update4(pv[u], mv[u], vv[u], g[u], b1, b2, eps, step_size, bc2_sqrt);
+        p[i] = pv[u]; m[i] = mv[u]; v[i] = vv[u];
+        if (bp && c == 0) {
+          float gb = slot[u] >= 0 ? bgrad[(int64_t)slot[u] * bgrad_stride] : 0.f;
+          float4 P = make_float4(bp[row], 0.f, 0.f, 0.f), M = make_float4(bm[row], 0.f, 0.f, 0.f), V = make_float4(bv[row], 0.f, 0.f, 0.f);
+          adam_update4(P, M, V, make_float4(gb, 0.f, 0.f, 0.f), b1, b2, eps, step_size, bc2_sqrt);
+          bp[row] = P.x; bm[row] = M.x; bv[row] = V.x;
+        }
+      }
+    }
   }
+}
+
+int launch_adam_stream(rec_engine *e, float *p, float *m, float *v, int64_t rows, int D, const int32_t *slot_of_row,
+                       const float *grad_rows, int grad_stride, float *bp, float *bm, float *bv, const float *bgrad,
+                       int bgrad_stride, const rec_train_hparams *hp, float step_size, float bc2_sqrt) {
+  const int64_t n4 = rows * (D / 4);
+  constexpr int UNROLL = 4;
+  int64_t want = cdiv64(n4, 256 * UNROLL);
+  int blocks = (int)(want < (int64_t)e->sm_count * 8 ? want : (int64_t)e->sm_count * 8);
+  if (blocks < 1) blocks = 1;
+  adam_stream_kernel<UNROLL><<<blocks, 256, 0, e->stream>>>((float4 *)p, (float4 *)m, (float4 *)v, slot_of_row,
+                                                            (const float4 *)grad_rows, grad_stride / 4, n4, D / 4, bp, bm,
+                                                            bv, bgrad, bgrad_stride, hp->beta1, hp->beta2, hp->eps,
+                                                            step_size, bc2_sqrt);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+// ---- row-sparse gradients of the Q heads --------------------------------------------------------
+// dW_{1+j}[a_b] += dq[b,j] * h[b], db_{1+j}[a_b] += dq[b,j]: one warp per batch row; the lowest b of each
+// distinct action is the leader and sums its duplicates in batch order (deterministic, no atomics).
+// grad_rows[(b*n_q + j), 0:D], bgrad[b*n_q + j], slot_of_row[a_b - vocab_lo] = b.
+__global__ void __launch_bounds__(256) q_grad_rows_kernel(const int64_t *__restrict__ a, const float *__restrict__ dq,
+                                                          const float *__restrict__ h, int B, int D, int n_q, int Vloc,
+                                                          int vocab_lo, float *__restrict__ grad_rows,
+                                                          float *__restrict__ bgrad, int32_t *__restrict__ slot_of_row) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int64_t key = a[b];
+  const int64_t loc = key - vocab_lo;
+  if (loc < 0 || loc >= Vloc) return;
+  for (int q0 = 0; q0 < b; q0 += 32) {
+    int q = q0 + lane;
+    if (__ballot_sync(0xffffffffu, q < b && a[q] == key)) return;
+  }
+  for (int j = 0; j < n_q; ++j) {
+    for (int d0 = 0; d0 < D; d0 += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float bsum = 0.f;
+      const int col = d0 + lane * 4;
+      for (int q0 = b; q0 < B; q0 += 32) {
+        int q = q0 + lane;
+        unsigned mm = __ballot_sync(0xffffffffu, q < B && a[q] == key);
+        while (mm) {
+          int l = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const float g = dq[(q0 + l) * 3 + j];
+          bsum += g;
+          if (col < D) {
+            const float4 hv = *reinterpret_cast<const float4 *>(h + (int64_t)(q0 + l) * D + col);
+            acc.x = fmaf(g, hv.x, acc.x); acc.y = fmaf(g, hv.y, acc.y); acc.z = fmaf(g, hv.z, acc.z); acc.w = fmaf(g, hv.w, acc.w);
+          }
+        }
+      }
+      if (col < D) *reinterpret_cast<float4 *>(grad_rows + ((int64_t)b * n_q + j) * D + col) = acc;
+      if (d0 == 0 && lane == 0) bgrad[b * n_q + j] = bsum;
+    }
+  }
+  if (lane == 0) slot_of_row[loc] = b;
+}
+
+__global__ void q_slot_reset_kernel(const int64_t *__restrict__ a, int B, int Vloc, int vocab_lo,
+                                    int32_t *__restrict__ slot_of_row) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int64_t loc = a[b] - vocab_lo;
+  if (loc >= 0 && loc < Vloc) slot_of_row[loc] = -1;
+}
+
+// Adam on every Q head (heads 1..n_q) of net `net_id`: streaming sweep with row-sparse gradients.
+int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                        float bc2_sqrt, const rec_train_hparams *hp) {
+  const int n_q = e->cfg.n_heads - 1, D = e->D;
+  const rec_net_params &p = e->nets[net_id].p;
+  q_grad_rows_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(b->a, e->dq, h, B, D, n_q, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
+                                                       e->q_bgrad, e->q_slot);
+  REC_LAUNCH_CHECK(e);
+  for (int j = 0; j < n_q; ++j) {
+    int rc = launch_adam_stream(e, p.head_w[1 + j], p.head_w_m[1 + j], p.head_w_v[1 + j], e->Vloc, D, e->q_slot,
+                                e->q_grad_rows + (int64_t)j * D, n_q * D, p.head_b[1 + j], p.head_b_m[1 + j],
+                                p.head_b_v[1 + j], e->q_bgrad + j, n_q, hp, step_size, bc2_sqrt);
+    if (rc) return rc;
+  }
+  q_slot_reset_kernel<<<cdiv(B, 256), 256, 0, e->stream>>>(b->a, B, e->Vloc, e->cfg.vocab_lo, e->q_slot);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
 }
 
 __global__ void emb_reset_kernel(const int32_t *__restrict__ keys, int P, int32_t *__restrict__ slot_of_row) {
@@ -181,14 +296,12 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
   emb_segment_kernel<<<cdiv(P, 8), 256, smem, e->stream>>>(e->emb_keys, P, E, e->dirs, e->dx, e->emb_grad_rows,
                                                           e->emb_slot, use_smem);
   REC_LAUNCH_CHECK(e);
-  const int64_t n4 = (int64_t)(c.item_num + 1) * (E / 4);
-  int blocks = (int)(cdiv64(n4, 256 * 4) < (int64_t)e->sm_count * 16 ? cdiv64(n4, 256 * 4) : (int64_t)e->sm_count * 16);
-  if (blocks < 1) blocks = 1;
   if (e->timing) cudaEventRecord(e->ev[4], e->stream);
-  emb_adam_kernel<<<blocks, 256, 0, e->stream>>>((float4 *)nb.p.emb, (float4 *)nb.p.emb_m, (float4 *)nb.p.emb_v,
-                                                e->emb_slot, (const float4 *)e->emb_grad_rows, n4, E / 4, hp->beta1,
-                                                hp->beta2, hp->eps, step_size, bc2_sqrt);
-  REC_LAUNCH_CHECK(e);
+  {
+    int rc = launch_adam_stream(e, nb.p.emb, nb.p.emb_m, nb.p.emb_v, (int64_t)c.item_num + 1, E, e->emb_slot,
+                                e->emb_grad_rows, E, nullptr, nullptr, nullptr, nullptr, 0, hp, step_size, bc2_sqrt);
+    if (rc) return rc;
+  }
   if (e->timing) cudaEventRecord(e->ev[5], e->stream);
   emb_reset_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(e->emb_keys, P, e->emb_slot);
   REC_LAUNCH_CHECK(e);

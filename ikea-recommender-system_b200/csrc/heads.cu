@@ -679,29 +679,28 @@ int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const r
   if (e->timing) cudaEventRecord(e->ev[0], e->stream);
   int n_dense_slices = n_cta;
   if (tc_bwd_supported(e, B)) {
-    // supervised head on the tensor cores; the Q heads (row-sparse gradients) keep the streaming kernel
     int rc = launch_head_bwd_adam_tc(e, net_id, h, b, B, step_size, bc2_sqrt, hp, inv_B, &n_dense_slices);
     if (rc) return rc;
-    if (n_q > 0) {
-      dim3 grid(n_cta, n_q);
-      head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
-                                                          n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
-                                                          step_size, bc2_sqrt, 1);
-      REC_LAUNCH_CHECK(e);
-    }
     if (n_q > 0 && n_dense_slices != n_cta) {
       // keep the Q-head dh slice adjacent to the dense slices
       REC_CUDA(e, cudaMemcpyAsync(e->dh_part + (int64_t)n_dense_slices * B * e->D, q_slice, sizeof(float) * (size_t)B * e->D,
                                   cudaMemcpyDeviceToDevice, e->stream));
     }
   } else {
-    dim3 grid(n_cta, e->cfg.n_heads);
+    dim3 grid(n_cta, 1);  // supervised head only; the Q heads stream below
     head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
                                                         n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
                                                         step_size, bc2_sqrt, 0);
     REC_LAUNCH_CHECK(e);
   }
   if (e->timing) cudaEventRecord(e->ev[1], e->stream);
+  if (n_q > 0) {
+    // row-sparse gradients of the Q heads + dense Adam: pure HBM streaming (24 B/param)
+    if (e->timing) cudaEventRecord(e->ev[6], e->stream);
+    int rc = launch_q_heads_adam(e, net_id, h, b, B, step_size, bc2_sqrt, hp);
+    if (rc) return rc;
+    if (e->timing) cudaEventRecord(e->ev[7], e->stream);
+  }
   int64_t n = (int64_t)B * e->D;
   dh_reduce_kernel<<<(int)cdiv64(n, 256), 256, 0, e->stream>>>(e->dh_part, n_dense_slices + (n_q > 0 ? 1 : 0), n, e->dh);
   REC_LAUNCH_CHECK(e);

@@ -207,7 +207,8 @@ int rec_set_tensor_cores(rec_engine *e, int on);
 int64_t rec_launch_count(const rec_engine *e);
 /* CUDA-event time (ms) of the most recent dominant-kernel launch when profiling is enabled. */
 int rec_enable_kernel_timing(rec_engine *e, int on);
-float rec_last_kernel_ms(rec_engine *e, int which); /* which: 0 head-bwd+adam, 1 head-fwd stats, 2 emb adam */
+float rec_last_kernel_ms(rec_engine *e, int which); /* which: 0 supervised-head bwd+Adam, 1 eval head statistics,
+                                                        2 embedding Adam sweep, 3 Q-heads Adam sweep */
 
 /* Self-test of the tcgen05/TMEM plumbing (bf16x3 split GEMM of one 128-row tile; see csrc/tc_selftest.cu):
  * mode 0: C[128,128] = A[128,64].B[128,64]^T ; mode 1: C[128,64] = P[128,128]^T.Q[128,64] ;
