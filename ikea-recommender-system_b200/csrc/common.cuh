@@ -108,6 +108,21 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// torch.optim.Adam element update (lerp / addcmul / addcdiv form).  sqrt and the final division use the
+// hardware approximations (<= 2 ulp): the update is HBM-bound streaming work and the IEEE sequences cost
+// ~10x the instructions; the difference is far inside the 1e-3 parity tolerance.
+__device__ __forceinline__ float fast_sqrtf(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g, float b1, float b2, float eps,
+                                          float step_size, float inv_bc2_sqrt) {
+  m = fmaf(g - m, 1.f - b1, m);
+  v = fmaf((1.f - b2) * g, g, v * b2);
+  p = p - __fdividef(step_size * m, fmaf(fast_sqrtf(v), inv_bc2_sqrt, eps));
+}
+
 // (score desc, id asc): is candidate (v, i) strictly better than (w, j)?
 __device__ __forceinline__ bool better(float v, int i, float w, int j) {
   return (v > w) || (v == w && i < j);

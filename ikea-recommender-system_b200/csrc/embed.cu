@@ -120,13 +120,11 @@ __global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restr
 }
 
 __device__ __forceinline__ void adam_update4(float4 &p, float4 &m, float4 &v, const float4 g, float b1, float b2,
-                                             float eps, float step_size, float bc2_sqrt) {
-#define REC_AD1(c)                                         \
-  m.c = m.c + (g.c - m.c) * (1.f - b1);                    \
-  v.c = v.c * b2 + ((1.f - b2) * g.c) * g.c;               \
-  p.c = p.c + (-step_size * m.c) / (sqrtf(v.c) / bc2_sqrt + eps);
-  REC_AD1(x) REC_AD1(y) REC_AD1(z) REC_AD1(w)
-#undef REC_AD1
+                                             float eps, float step_size, float inv_bc2_sqrt) {
+  adam_elem(p.x, m.x, v.x, g.x, b1, b2, eps, step_size, inv_bc2_sqrt);
+  adam_elem(p.y, m.y, v.y, g.y, b1, b2, eps, step_size, inv_bc2_sqrt);
+  adam_elem(p.z, m.z, v.z, g.z, b1, b2, eps, step_size, inv_bc2_sqrt);
+  adam_elem(p.w, m.w, v.w, g.w, b1, b2, eps, step_size, inv_bc2_sqrt);
 }
 
 // Dense Adam sweep over a [rows, D] matrix whose gradient is row-sparse: row r has gradient
@@ -138,57 +136,73 @@ __global__ void __launch_bounds__(256) adam_stream_kernel(float4 *__restrict__ p
                                                           float4 *__restrict__ v,
                                                           const int32_t *__restrict__ slot_of_row,
                                                           const float4 *__restrict__ grad_rows, int grad_stride4,
-                                                          int64_t n4, int D4, float *__restrict__ bp,
-                                                          float *__restrict__ bm, float *__restrict__ bv,
-                                                          const float *__restrict__ bgrad, int bgrad_stride,
-                                                          float b1, float b2, float eps, float step_size,
-                                                          float bc2_sqrt) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
-    float4 pv[UNROLL], mv[UNROLL], vv[UNROLL], g[UNROLL];
+                                                          uint32_t n4, int D4, int d4_shift, float b1, float b2,
+                                                          float eps, float step_size, float inv_bc2_sqrt) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
+    float4 pv[UNROLL], mv[UNROLL], vv[UNROLL];
     int slot[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const int64_t i = i0 + u * stride;
+      const uint32_t i = i0 + u * stride;
       if (i < n4) {
         pv[u] = p[i]; mv[u] = m[i]; vv[u] = v[i];
-        slot[u] = __ldg(slot_of_row + i / D4);
+        slot[u] = __ldg(slot_of_row + (d4_shift >= 0 ? (i >> d4_shift) : (i / (uint32_t)D4)));
       }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const int64_t i = i0 + u * stride;
+      const uint32_t i = i0 + u * stride;
       if (i < n4) {
-        const int64_t row = i / D4;
-        const int c = (int)(i - row * D4);
-        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (slot[u] >= 0) g[u] = __ldg(grad_rows + (int64_t)slot[u] * grad_stride4 + c);
-        adam_update4(pv[u], mv[u], vv[u], g[u], b1, b2, eps, step_size, bc2_sqrt);
-        p[i] = pv[u]; m[i] = mv[u]; v[i] = vv[u];
-        if (bp && c == 0) {
-          float gb = slot[u] >= 0 ? bgrad[(int64_t)slot[u] * bgrad_stride] : 0.f;
-          float4 P = make_float4(bp[row], 0.f, 0.f, 0.f), M = make_float4(bm[row], 0.f, 0.f, 0.f), V = make_float4(bv[row], 0.f, 0.f, 0.f);
-          adam_update4(P, M, V, make_float4(gb, 0.f, 0.f, 0.f), b1, b2, eps, step_size, bc2_sqrt);
-          bp[row] = P.x; bm[row] = M.x; bv[row] = V.x;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (slot[u] >= 0) {
+          const uint32_t c = d4_shift >= 0 ? (i & (uint32_t)(D4 - 1)) : (i % (uint32_t)D4);
+          g = __ldg(grad_rows + (size_t)slot[u] * grad_stride4 + c);
         }
+        adam_update4(pv[u], mv[u], vv[u], g, b1, b2, eps, step_size, inv_bc2_sqrt);
+        p[i] = pv[u]; m[i] = mv[u]; v[i] = vv[u];
       }
     }
   }
+}
+
+// bias vector of a head: one element per row, gradient through the same slot map
+__global__ void __launch_bounds__(256) adam_bias_kernel(float *__restrict__ bp, float *__restrict__ bm,
+                                                        float *__restrict__ bv, const int32_t *__restrict__ slot_of_row,
+                                                        const float *__restrict__ bgrad, int bgrad_stride, int rows,
+                                                        float b1, float b2, float eps, float step_size,
+                                                        float inv_bc2_sqrt) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int slot = slot_of_row[r];
+  float g = slot >= 0 ? bgrad[(size_t)slot * bgrad_stride] : 0.f;
+  float p = bp[r], m = bm[r], v = bv[r];
+  adam_elem(p, m, v, g, b1, b2, eps, step_size, inv_bc2_sqrt);
+  bp[r] = p; bm[r] = m; bv[r] = v;
 }
 
 int launch_adam_stream(rec_engine *e, float *p, float *m, float *v, int64_t rows, int D, const int32_t *slot_of_row,
                        const float *grad_rows, int grad_stride, float *bp, float *bm, float *bv, const float *bgrad,
                        int bgrad_stride, const rec_train_hparams *hp, float step_size, float bc2_sqrt) {
   const int64_t n4 = rows * (D / 4);
-  constexpr int UNROLL = 4;
+  if (n4 >= (int64_t)1 << 31) REC_FAIL(e, REC_EINVAL, "adam_stream: tensor too large (%lld float4)", (long long)n4);
+  constexpr int UNROLL = 2;
+  const int D4 = D / 4;
+  int shift = -1;
+  if ((D4 & (D4 - 1)) == 0) { shift = 0; while ((1 << shift) < D4) ++shift; }
   int64_t want = cdiv64(n4, 256 * UNROLL);
-  int blocks = (int)(want < (int64_t)e->sm_count * 8 ? want : (int64_t)e->sm_count * 8);
+  int blocks = (int)(want < (int64_t)e->sm_count * 16 ? want : (int64_t)e->sm_count * 16);
   if (blocks < 1) blocks = 1;
   adam_stream_kernel<UNROLL><<<blocks, 256, 0, e->stream>>>((float4 *)p, (float4 *)m, (float4 *)v, slot_of_row,
-                                                            (const float4 *)grad_rows, grad_stride / 4, n4, D / 4, bp, bm,
-                                                            bv, bgrad, bgrad_stride, hp->beta1, hp->beta2, hp->eps,
-                                                            step_size, bc2_sqrt);
+                                                            (const float4 *)grad_rows, grad_stride / 4, (uint32_t)n4, D4,
+                                                            shift, hp->beta1, hp->beta2, hp->eps, step_size,
+                                                            1.f / bc2_sqrt);
   REC_LAUNCH_CHECK(e);
+  if (bp) {
+    adam_bias_kernel<<<cdiv((int)rows, 256), 256, 0, e->stream>>>(bp, bm, bv, slot_of_row, bgrad, bgrad_stride, (int)rows,
+                                                                 hp->beta1, hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt);
+    REC_LAUNCH_CHECK(e);
+  }
   return REC_OK;
 }
 

@@ -519,10 +519,7 @@ __global__ void __launch_bounds__(256) gru_wgrad_kernel(const float *__restrict_
 
 __device__ __forceinline__ void adam_update(float &p, float &m, float &v, float g, float b1, float b2,
                                             float eps, float step_size, float bc2_sqrt) {
-  m = m + (g - m) * (1.f - b1);
-  v = v * b2 + ((1.f - b2) * g) * g;
-  float denom = sqrtf(v) / bc2_sqrt + eps;
-  p = p + (-step_size * m) / denom;
+  adam_elem(p, m, v, g, b1, b2, eps, step_size, 1.f / bc2_sqrt);
 }
 
 struct GruAdamPtrs {

@@ -409,9 +409,7 @@ struct HeadTrainPtrs {
 
 __device__ __forceinline__ void adam1(float &p, float &m, float &v, float g, float b1, float b2, float eps,
                                       float step_size, float bc2_sqrt) {
-  m = m + (g - m) * (1.f - b1);
-  v = v * b2 + ((1.f - b2) * g) * g;
-  p = p + (-step_size * m) / (sqrtf(v) / bc2_sqrt + eps);
+  adam_elem(p, m, v, g, b1, b2, eps, step_size, 1.f / bc2_sqrt);
 }
 
 __global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, const float *__restrict__ h,

@@ -50,7 +50,7 @@ __device__ __forceinline__ void stage_rows64(uint8_t *blk_hi, uint8_t *blk_lo, c
   }
 }
 
-__global__ void __launch_bounds__(256, 1) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
+__global__ void __launch_bounds__(256, 2) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
                                                                int vocab_lo, int n_tiles, int do_stats, int first_head,
                                                                int upg, float w0, float w1, float w2,
                                                                const int64_t *__restrict__ target, int topk,
@@ -72,21 +72,49 @@ __global__ void __launch_bounds__(256, 1) head_stats_tc_kernel(TcHeadPtrs hp, co
   const int per = (n_tiles + n_split - 1) / n_split;
   const int t_lo = sp * per, t_hi = min(n_tiles, t_lo + per);
   const int n_groups = max(0, t_hi - t_lo), n_units = n_groups * upg;
-  const float wq[3] = {w0, w1, w2};
   const bool argmode = !do_stats && topk == 0;
 
   if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_barrier_init(); }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
   stage_rows64(h_hi, h_lo, h, b0, B, 1.f, tid);
 
-  auto load_unit = [&](int u) {
-    const int g = u / upg, hh = u - g * upg, head = first_head + hh, v0 = (t_lo + g) * 128, s = u & 1;
-    const float scale = argmode && upg > 1 ? wq[hh] : 1.f;
-    stage_rows64(w_st + s * 2 * BLK, w_st + s * 2 * BLK + BLK, hp.w[head], v0, Vloc, scale, tid);
+  // unit u = (vocabulary tile g, head hh).  fetch(): global -> registers (in flight across a whole
+  // pipeline step); store(): registers -> bf16 hi/lo swizzled smem stage + bias tile.
+  float4 fa[4], fb[4];
+  float fbias = 0.f;
+  auto unit_scale = [&](int hh) { return (argmode && upg > 1) ? (hh == 0 ? w0 : (hh == 1 ? w1 : w2)) : 1.f; };
+  auto fetch = [&](int u) {
+    const int g = u / upg, hh = u - g * upg, head = first_head + hh, v0 = (t_lo + g) * 128;
+    const float *src = hp.w[head];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + 256 * i, row = c >> 3, c8 = c & 7;
+      fa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      fb[i] = fa[i];
+      if (v0 + row < Vloc) {
+        const float4 *p = reinterpret_cast<const float4 *>(src + (int64_t)(v0 + row) * 64 + c8 * 8);
+        fa[i] = p[0];
+        fb[i] = p[1];
+      }
+    }
+    fbias = (tid < 128 && v0 + tid < Vloc) ? __ldg(hp.b[head] + v0 + tid) : 0.f;
+  };
+  auto store = [&](int u) {
+    const int g = u / upg, hh = u - g * upg, s = u & 1;
+    const float scale = unit_scale(hh);
+    uint8_t *bh = w_st + s * 2 * BLK, *bl = bh + BLK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + 256 * i;
+      if (scale != 1.f) {
+        fa[i].x *= scale; fa[i].y *= scale; fa[i].z *= scale; fa[i].w *= scale;
+        fb[i].x *= scale; fb[i].y *= scale; fb[i].z *= scale; fb[i].w *= scale;
+      }
+      tc::store_split8(bh, bl, c >> 3, c & 7, fa[i], fb[i]);
+    }
     if (tid < 128) {
-      float bv = (v0 + tid < Vloc) ? __ldg(hp.b[head] + v0 + tid) * scale : 0.f;
       float *dst = bias_g + (g % 3) * 128 + tid;
-      *dst = (hh == 0) ? bv : (*dst + bv);
+      *dst = (hh == 0) ? fbias * scale : (*dst + fbias * scale);
     }
   };
   auto issue_unit = [&](int u) {  // one thread
@@ -109,9 +137,10 @@ __global__ void __launch_bounds__(256, 1) head_stats_tc_kernel(TcHeadPtrs hp, co
   const int row = b0 + q * 32 + lane;
   float m_run = REC_NEG_INF, s_run = 0.f, tgt = REC_NEG_INF, av = REC_NEG_INF, tau = REC_NEG_INF;
   int ai = 0x7fffffff, cnt = 0;
-  const int64_t trow = (do_stats && target && row < B) ? target[row] - vocab_lo : -1;
+  const int trow = (do_stats && target && row < B) ? (int)(target[row] - vocab_lo) : -1;
 
-  if (n_units > 0) load_unit(0);
+  if (n_units > 0) { fetch(0); store(0); }
+  if (n_units > 1) fetch(1);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -121,7 +150,8 @@ __global__ void __launch_bounds__(256, 1) head_stats_tc_kernel(TcHeadPtrs hp, co
   for (int u = 0; u < n_units; ++u) {
     if (u + 1 < n_units) {
       if (u >= 1) tc::mbar_wait(&mbar[(u + 1) & 1], ((u - 1) >> 1) & 1);  // MMA(u-1) done: its smem stage is free
-      load_unit(u + 1);
+      store(u + 1);
+      if (u + 2 < n_units) fetch(u + 2);  // lands while this step's barrier / MMA wait / epilogue run
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -132,61 +162,63 @@ __global__ void __launch_bounds__(256, 1) head_stats_tc_kernel(TcHeadPtrs hp, co
     if (u - g * upg != upg - 1) continue;  // accumulate the remaining heads of this group first
     tc::mbar_wait(&mbar[u & 1], (u >> 1) & 1);
     tc::tc_fence_after();
-    // ---- epilogue of group g ----
-    const int v0 = (t_lo + g) * 128, c_lo = v0 + ch * 64;
-    float l[64];
-    const uint32_t taddr = tmem_base_s + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * 128 + ch * 64);
-    tc::tmem_ld32(taddr, l);
-    tc::tmem_ld32(taddr + 32, l + 32);
-    tc::tmem_ld_wait();
-    const float *bg = bias_g + (g % 3) * 128 + ch * 64;
+    // ---- epilogue of group g: two chunks of 32 columns ----
+    const int v0 = (t_lo + g) * 128;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int c_lo = v0 + ch * 64 + half * 32;
+      float l[32];
+      tc::tmem_ld32(tmem_base_s + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * 128 + ch * 64 + half * 32), l);
+      tc::tmem_ld_wait();
+      const float *bg = bias_g + (g % 3) * 128 + ch * 64 + half * 32;
 #pragma unroll
-    for (int j = 0; j < 64; j += 4) {
-      float4 b4 = *reinterpret_cast<const float4 *>(bg + j);
-      l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
-    }
-    if (c_lo + 64 > Vloc) {
-#pragma unroll
-      for (int j = 0; j < 64; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
-    }
-    if (do_stats) {
-      float tmax = REC_NEG_INF;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) tmax = fmaxf(tmax, l[j]);
-      const float nm = fmaxf(m_run, tmax);
-      float ps = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) ps += __expf(l[j] - nm);
-      s_run = s_run * __expf(m_run - nm) + ps;
-      m_run = nm;
-      if (trow >= c_lo && trow < c_lo + 64) {
-        const int tj = (int)(trow - c_lo);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) if (j == tj) tgt = l[j];
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = *reinterpret_cast<const float4 *>(bg + j);
+        l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
       }
-    }
-    if (topk > 0) {
+      if (c_lo + 32 > Vloc) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float v = l[j];
-        if (v > tau) {
-          int p = cnt < topk ? cnt : topk - 1;
-          while (p > 0 && tv[(p - 1) * 256 + tid] < v) {
-            tv[p * 256 + tid] = tv[(p - 1) * 256 + tid];
-            ti[p * 256 + tid] = ti[(p - 1) * 256 + tid];
-            --p;
-          }
-          tv[p * 256 + tid] = v;
-          ti[p * 256 + tid] = vocab_lo + c_lo + j;
-          if (cnt < topk) ++cnt;
-          tau = cnt == topk ? tv[(topk - 1) * 256 + tid] : REC_NEG_INF;
+        for (int j = 0; j < 32; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
+      }
+      if (do_stats) {
+        float tmax = REC_NEG_INF;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
+        const float nm = fmaxf(m_run, tmax);
+        float ps = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ps += __expf(l[j] - nm);
+        s_run = s_run * __expf(m_run - nm) + ps;
+        m_run = nm;
+        if (trow >= c_lo && trow < c_lo + 32) {
+          const int tj = trow - c_lo;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j == tj) tgt = l[j];
         }
       }
-    }
-    if (argmode) {
+      if (topk > 0) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j)
-        if (l[j] > av) { av = l[j]; ai = vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+        for (int j = 0; j < 32; ++j) {
+          const float v = l[j];
+          if (v > tau) {
+            int p = cnt < topk ? cnt : topk - 1;
+            while (p > 0 && tv[(p - 1) * 256 + tid] < v) {
+              tv[p * 256 + tid] = tv[(p - 1) * 256 + tid];
+              ti[p * 256 + tid] = ti[(p - 1) * 256 + tid];
+              --p;
+            }
+            tv[p * 256 + tid] = v;
+            ti[p * 256 + tid] = vocab_lo + c_lo + j;
+            if (cnt < topk) ++cnt;
+            tau = cnt == topk ? tv[(topk - 1) * 256 + tid] : REC_NEG_INF;
+          }
+        }
+      }
+      if (argmode) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (l[j] > av) { av = l[j]; ai = vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+      }
     }
   }
 
@@ -216,7 +248,9 @@ bool tc_heads_supported(const rec_engine *e) { return e->D == 64 && e->use_tc; }
 // Same contract as launch_head_stats (heads.cu); *n_split_out counts RECORDS per row (2 per CTA column).
 int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
   const int n_tiles = cdiv(e->Vloc, 128), nb = cdiv(a.B, 128);
-  int n_split = cdiv(e->sm_count, nb);
+  const size_t smem_need = 1024 + 6 * (size_t)BLK + 1536 + (size_t)a.topk * 256 * 8;
+  const int ctas_per_sm = smem_need <= 110 * 1024 ? 2 : 1;
+  int n_split = cdiv(ctas_per_sm * e->sm_count, nb);
   if (n_split > n_tiles) n_split = n_tiles;
   if (n_split < 1) n_split = 1;
   int per = cdiv(n_tiles, n_split);
@@ -257,10 +291,8 @@ struct TcTrainPtrs {
 };
 
 __device__ __forceinline__ void adam_f(float &p, float &m, float &v, float g, float b1, float b2, float eps, float step_size,
-                                       float bc2_sqrt) {
-  m = m + (g - m) * (1.f - b1);
-  v = v * b2 + ((1.f - b2) * g) * g;
-  p = p + (-step_size * m) / (sqrtf(v) / bc2_sqrt + eps);
+                                       float inv_bc2_sqrt) {
+  adam_elem(p, m, v, g, b1, b2, eps, step_size, inv_bc2_sqrt);
 }
 
 __global__ void __launch_bounds__(256, 1) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const float *__restrict__ h,
@@ -521,7 +553,7 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
     attr_set = true;
   }
   head_bwd_adam_tc_kernel<<<n_cta, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles, inv_B,
-                                                          e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size, bc2_sqrt);
+                                                          e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt);
   REC_LAUNCH_CHECK(e);
   *n_slices = n_cta;
   return REC_OK;
