@@ -116,6 +116,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->astar, int32_t, mb);
   ALLOC(e, extra(e).q_loss_rows, float, mb);
   ALLOC(e, e->summary, float, mb * e->part_stride);
+  ALLOC(e, e->hpack, uint8_t, (size_t)((mb + 255) / 256) * 4 * 16384);
   ALLOC(e, e->q_grad_rows, float, mb * 3 * D);
   ALLOC(e, e->q_bgrad, float, mb * 3);
   ALLOC(e, e->q_slot, int32_t, e->Vloc);
@@ -147,7 +148,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {

@@ -60,6 +60,7 @@ struct rec_engine {
   float *q_grad_rows;    // [maxB][n_q][D] row-sparse Q-head gradients
   float *q_bgrad;        // [maxB][n_q]
   int32_t *q_slot;       // [Vloc] leader batch row of each action or -1
+  uint8_t *hpack;        // [ceil(maxB/128)][hi|lo][16 KB] packed bf16 image of h for the tensor-core backward
   float *summary;        // [maxB][part_stride] per-row record of this shard
   float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;

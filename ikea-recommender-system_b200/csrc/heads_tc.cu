@@ -295,32 +295,46 @@ __device__ __forceinline__ void adam_f(float &p, float &m, float &v, float g, fl
   adam_elem(p, m, v, g, b1, b2, eps, step_size, inv_bc2_sqrt);
 }
 
-__global__ void __launch_bounds__(256, 1) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const float *__restrict__ h,
+// h [B, 64] fp32 -> packed bf16 hi/lo image: block bb (128 rows) = [hi 16 KB | lo 16 KB], swizzled exactly as
+// the kernels want it in shared memory, so that (re)loading a block is a raw TMA bulk copy.
+__global__ void __launch_bounds__(256) h_prepack_kernel(const float *__restrict__ h, int B, uint8_t *__restrict__ out) {
+  const int bb = blockIdx.x, tid = threadIdx.x;
+  uint8_t *hi = out + (size_t)bb * 2 * BLK, *lo = hi + BLK;
+  stage_rows64(hi, lo, h, bb * 128, B, 1.f, tid);
+}
+
+__global__ void __launch_bounds__(256, 1) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const uint8_t *__restrict__ hpack,
                                                                   const int64_t *__restrict__ target,
                                                                   const float *__restrict__ row_stats, int B, int Vloc,
                                                                   int vocab_lo, int n_tiles, float inv_B,
                                                                   float *__restrict__ dh_part, float b1, float b2,
-                                                                  float eps, float step_size, float bc2_sqrt) {
+                                                                  float eps, float step_size, float inv_bc2_sqrt) {
   extern __shared__ uint8_t raw[];
   uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *h_blk = sm;                 // [bb][hi|lo] x BLK      (64 KB)
+  uint8_t *h_blk = sm;                 // chunk of 256 sessions: [bb][hi|lo] x BLK      (64 KB)
   uint8_t *w_hi = sm + 4 * BLK, *w_lo = sm + 5 * BLK;            // (32 KB)
   uint8_t *dl_hi = sm + 6 * BLK, *dl_lo = sm + 8 * BLK;          // each 2 blocks (v halves)  (64 KB)
-  uint8_t *ones = sm + 10 * BLK;                                  // 4 KB of bf16 1.0
+  float *w_stage = reinterpret_cast<float *>(sm + 10 * BLK);     // fp32 tile [128][64], TMA destination (32 KB)
+  uint8_t *ones = sm + 12 * BLK;                                  // 4 KB of bf16 1.0
   float *bias_s = reinterpret_cast<float *>(ones + 4096);        // [128]
-  float *dws = reinterpret_cast<float *>(dl_hi);                 // alias: [128][68] fp32 after the MMAs of a tile
   float *db_s = bias_s + 128;                                     // [128]
-  __shared__ uint64_t mbar[2];
+  float *lse_s = db_s + 128;                                      // [256]
+  int *tgt_s = reinterpret_cast<int *>(lse_s + 256);             // [256] target column relative to vocab_lo
+  float *dws = reinterpret_cast<float *>(dl_hi);                 // alias: [128][68] fp32 after the MMAs of a tile
+  __shared__ uint64_t mbar[4];  // 0: logits ready, 1: gradient MMAs done, 2: W tile landed, 3: h chunk landed
   __shared__ uint32_t tmem_base_s;
   constexpr uint32_t T_L = 0, T_DW = 128, T_DB = 192, T_DH = 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, ch = warp >> 2;
-  const int nbb = (B + 127) / 128;
+  const int n_chunks = (B + 255) / 256;
+  const bool resident = n_chunks == 1;  // dh stays in TMEM across all tiles of the CTA
 
-  if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_barrier_init(); }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&mbar[i], 1);
+    tc::fence_barrier_init();
+  }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
-  for (int bb = 0; bb < nbb; ++bb) stage_rows64(h_blk + bb * 2 * BLK, h_blk + bb * 2 * BLK + BLK, h, bb * 128, B, 1.f, tid);
   for (int i = tid; i < 4096 / 4; i += 256) reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;
   tc::fence_async_smem();
   tc::tc_fence_before();
@@ -329,191 +343,252 @@ __global__ void __launch_bounds__(256, 1) head_bwd_adam_tc_kernel(TcTrainPtrs hp
   const uint32_t tmem = tmem_base_s;
   const uint32_t s_h = tc::smem_u32(h_blk), s_wh = tc::smem_u32(w_hi), s_wl = tc::smem_u32(w_lo);
   const uint32_t s_dh = tc::smem_u32(dl_hi), s_dl = tc::smem_u32(dl_lo), s_one = tc::smem_u32(ones);
-  uint32_t phA = 0, phB = 0;  // phases of mbar[0] (logits ready) and mbar[1] (gradient MMAs done)
+  uint32_t phA = 0, phB = 0, phW = 0, phH = 0;
   bool first_tile = true;
+
+  auto tile_rows = [&](int t) { return min(128, Vloc - t * 128); };
+  auto prefetch_w = [&](int t) {  // one thread: TMA bulk copy of the fp32 tile
+    const uint32_t bytes = (uint32_t)tile_rows(t) * 256u;
+    tc::mbar_expect_tx(&mbar[2], bytes);
+    tc::bulk_g2s(w_stage, hp.w + (int64_t)t * 128 * 64, bytes, &mbar[2]);
+  };
+  auto load_chunk = [&](int c) {  // one thread: packed h chunk (1 or 2 blocks of 32 KB)
+    const int nb = min(2, (B - c * 256 + 127) / 128);
+    tc::mbar_expect_tx(&mbar[3], (uint32_t)nb * 2 * BLK);
+    tc::bulk_g2s(h_blk, hpack + (size_t)c * 4 * BLK, (uint32_t)nb * 2 * BLK, &mbar[3]);
+  };
+  auto issue_logits = [&](int bb) {
+    const uint32_t id = tc::instr_desc(128, 128, 0, 0);
+    const uint32_t hb = s_h + bb * 2 * BLK;
+    bool acc = false;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t a = hb + (pass == 2 ? BLK : 0), b = pass == 1 ? s_wl : s_wh;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tmem + T_L, tc::desc_kmajor(a, k), tc::desc_kmajor(b, k), id, acc); acc = true; }
+    }
+    tc::mma_commit(&mbar[0]);
+  };
+
+  if (blockIdx.x < n_tiles && tid == 0) {
+    prefetch_w(blockIdx.x);
+    load_chunk(0);
+  }
+  int chunk_loaded = 0;
 
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int v0 = t * 128;
-    // ---- W tile: fp32 -> registers (kept for Adam) -> bf16 hi/lo in smem -------------------------
+    // ---- W tile: staged fp32 (TMA) -> registers (kept for Adam) -> bf16 hi/lo in smem ---------------
+    tc::mbar_wait(&mbar[2], phW);
+    phW ^= 1;
     float4 pa[4], pb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int c = tid + 256 * i, row = c >> 3, c8 = c & 7;
+      const int c = tid + 256 * i, row = c >> 3, c8 = c & 7;
       pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       pb[i] = pa[i];
       if (v0 + row < Vloc) {
-        const float4 *p = reinterpret_cast<const float4 *>(hp.w + (int64_t)(v0 + row) * 64 + c8 * 8);
+        const float4 *p = reinterpret_cast<const float4 *>(w_stage + row * 64 + c8 * 8);
         pa[i] = p[0];
         pb[i] = p[1];
       }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int c = tid + 256 * i;
-      tc::store_split8(w_hi, w_lo, c >> 3, c & 7, pa[i], pb[i]);
+      tc::store_split8(w_hi, w_lo, row, c8, pa[i], pb[i]);
     }
     if (tid < 128) bias_s[tid] = (v0 + tid < Vloc) ? hp.b[v0 + tid] : 0.f;
     tc::fence_async_smem();
     tc::tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // staging buffer fully consumed, W operands visible
     tc::tc_fence_after();
-    if (tid == 0) {  // logits of block 0
-      const uint32_t id = tc::instr_desc(128, 128, 0, 0);
-      bool acc = false;
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = s_h + (pass == 2 ? BLK : 0), b = pass == 1 ? s_wl : s_wh;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { tc::mma_bf16(tmem + T_L, tc::desc_kmajor(a, k), tc::desc_kmajor(b, k), id, acc); acc = true; }
+    if (tid == 0 && t + (int)gridDim.x < n_tiles) prefetch_w(t + gridDim.x);  // lands during this tile
+
+    for (int c = 0; c < n_chunks; ++c) {
+      const int r0 = c * 256, nbb = min(2, (B - r0 + 127) / 128);
+      if (chunk_loaded != c) {  // only when the batch spans several chunks
+        if (tid == 0) load_chunk(c);
+        chunk_loaded = c;
+        tc::mbar_wait(&mbar[3], phH);
+        phH ^= 1;
+      } else if (first_tile && c == 0) {
+        tc::mbar_wait(&mbar[3], phH);
+        phH ^= 1;
       }
-      tc::mma_commit(&mbar[0]);
-    }
-    for (int bb = 0; bb < nbb; ++bb) {
-      tc::mbar_wait(&mbar[0], phA);  // logits(bb) ready; implies every earlier MMA finished -> dl smem is free
-      phA ^= 1;
-      tc::tc_fence_after();
-      // ---- epilogue 1: dlogits of (row, 64 columns) -> bf16 hi/lo, swizzled [batch][v] blocks -------
       {
-        const int r = q * 32 + lane, row = bb * 128 + r;
-        float l[64];
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + T_L + (uint32_t)(ch * 64);
-        tc::tmem_ld32(taddr, l);
-        tc::tmem_ld32(taddr + 32, l + 32);
-        tc::tmem_ld_wait();
-        const bool rv = row < B;
-        const float lse = rv ? row_stats[(int64_t)row * 8] : 0.f;
-        const int tj = rv ? (int)(target[row] - vocab_lo - v0 - ch * 64) : -1;
-        const float *bg = bias_s + ch * 64;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          float d = 0.f;
-          if (rv && v0 + ch * 64 + j < Vloc) d = (__expf(l[j] + bg[j] - lse) - (j == tj ? 1.f : 0.f)) * inv_B;
-          l[j] = d;
-        }
-#pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8)
-          tc::store_split8(dl_hi + ch * BLK, dl_lo + ch * BLK, r, c8, make_float4(l[c8 * 8], l[c8 * 8 + 1], l[c8 * 8 + 2], l[c8 * 8 + 3]),
-                           make_float4(l[c8 * 8 + 4], l[c8 * 8 + 5], l[c8 * 8 + 6], l[c8 * 8 + 7]));
+        const int row = r0 + tid;
+        lse_s[tid] = row < B ? row_stats[(int64_t)row * 8] : 0.f;
+        tgt_s[tid] = row < B ? (int)(target[row] - vocab_lo) : -1;
       }
-      tc::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) issue_logits(0);
+      for (int bb = 0; bb < nbb; ++bb) {
+        tc::mbar_wait(&mbar[0], phA);  // logits(bb) ready; implies every earlier MMA finished -> dl smem is free
+        phA ^= 1;
+        tc::tc_fence_after();
+        // ---- epilogue 1: dlogits of (row, 64 columns) -> bf16 hi/lo, swizzled [batch][v] blocks -----
+        {
+          const int r = q * 32 + lane, rl = bb * 128 + r, row = r0 + rl;
+          float l[64];
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + T_L + (uint32_t)(ch * 64);
+          tc::tmem_ld32(taddr, l);
+          tc::tmem_ld32(taddr + 32, l + 32);
+          tc::tmem_ld_wait();
+          const bool rv = row < B;
+          const float lse = lse_s[rl];
+          const int tj = tgt_s[rl] - v0 - ch * 64;
+          const float *bg = bias_s + ch * 64;
+          const int nvalid = rv ? min(64, Vloc - v0 - ch * 64) : 0;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            float d = (__expf(l[j] + bg[j] - lse) - (j == tj ? 1.f : 0.f)) * inv_B;
+            l[j] = j < nvalid ? d : 0.f;
+          }
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            tc::store_split8(dl_hi + ch * BLK, dl_lo + ch * BLK, r, c8,
+                             make_float4(l[c8 * 8], l[c8 * 8 + 1], l[c8 * 8 + 2], l[c8 * 8 + 3]),
+                             make_float4(l[c8 * 8 + 4], l[c8 * 8 + 5], l[c8 * 8 + 6], l[c8 * 8 + 7]));
+        }
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        if (tid == 0) {
+          const uint32_t hb = s_h + bb * 2 * BLK;
+          {  // dW += dl^T . h[bb]   (A: dl MN-major, M = v (2 blocks), K = batch;  B: h MN-major, N = d, K = batch)
+            const uint32_t id = tc::instr_desc(128, 64, 1, 1);
+            bool acc = !(c == 0 && bb == 0);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a = pass == 2 ? s_dl : s_dh, b = hb + (pass == 1 ? BLK : 0);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                tc::mma_bf16(tmem + T_DW, tc::desc_mnmajor(a, k, BLK), tc::desc_mnmajor(b, k, BLK), id, acc);
+                acc = true;
+              }
+            }
+          }
+          {  // db += dl^T . 1       (B: 16 rows of ones, K-major, two 64-wide K blocks of 2 KB)
+            const uint32_t id = tc::instr_desc(128, 16, 1, 0);
+            bool acc = !(c == 0 && bb == 0);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const uint32_t a = pass == 1 ? s_dl : s_dh;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                tc::mma_bf16(tmem + T_DB, tc::desc_mnmajor(a, k, BLK), tc::desc_kmajor(s_one + (k >> 2) * 2048, k & 3), id, acc);
+                acc = true;
+              }
+            }
+          }
+          {  // dh[bb] += dl . W     (A: dl K-major, M = batch, K = v (2 blocks);  B: W MN-major, N = d, K = v)
+            const uint32_t id = tc::instr_desc(128, 64, 0, 1);
+            bool acc = resident && !first_tile;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a = pass == 2 ? s_dl : s_dh, b = pass == 1 ? s_wl : s_wh;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                tc::mma_bf16(tmem + T_DH + bb * 64, tc::desc_kmajor(a + (k >> 2) * BLK, k & 3), tc::desc_mnmajor(b, k, BLK), id, acc);
+                acc = true;
+              }
+            }
+          }
+          if (bb + 1 < nbb) issue_logits(bb + 1);  // queues right behind the gradient MMAs
+          else tc::mma_commit(&mbar[1]);
+        }
+      }
+      // chunk done: all its MMAs complete when mbar[1] fires
+      const bool last_chunk = c + 1 == n_chunks;
+      float4 m0[4], m1[4], u0[4], u1[4];
+      if (last_chunk) {
+        // the epilogue registers are dead: start streaming m, v of this tile while the tensor core finishes
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = tid + 256 * i, row = cc >> 3, c8 = cc & 7;
+          if (v0 + row < Vloc) {
+            const int64_t off = (int64_t)(v0 + row) * 64 + c8 * 8;
+            m0[i] = *reinterpret_cast<const float4 *>(hp.wm + off); m1[i] = *reinterpret_cast<const float4 *>(hp.wm + off + 4);
+            u0[i] = *reinterpret_cast<const float4 *>(hp.wv + off); u1[i] = *reinterpret_cast<const float4 *>(hp.wv + off + 4);
+          }
+        }
+      }
+      tc::mbar_wait(&mbar[1], phB);
+      phB ^= 1;
+      tc::tc_fence_after();
+      if (!resident) {
+        // dh of this (tile, chunk): TMEM -> this CTA's slice (first tile stores, later tiles add)
+        float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
+        for (int bb = 0; bb < nbb; ++bb) {
+          const int row = r0 + bb * 128 + q * 32 + lane;
+          float g[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + ch * 32), g);
+          tc::tmem_ld_wait();
+          if (row < B) {
+            float4 *dst = reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+              if (!first_tile) { float4 p = dst[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+              dst[j] = o;
+            }
+          }
+        }
+        tc::tc_fence_before();
+        __syncthreads();  // TMEM dh region and lse/tgt smem are reused by the next chunk
+        tc::tc_fence_after();
+      }
+      if (!last_chunk) continue;
+      // ---- epilogue 2: dW (TMEM) -> smem fp32 [128][68]; db -> smem -------------------------------
+      {
+        const int r = q * 32 + lane;
+        float g[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + T_DW + (uint32_t)(ch * 32), g);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(dws + r * 68 + ch * 32 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+        if (ch == 0) {
+          float d16[16];
+          tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DB, d16);
+          tc::tmem_ld_wait();
+          db_s[r] = d16[0];
+        }
+      }
       tc::tc_fence_before();
       __syncthreads();
       tc::tc_fence_after();
-      if (tid == 0) {
-        const uint32_t hb = s_h + bb * 2 * BLK;
-        // dW += dl^T . h[bb]      (A: dl MN-major, M = v (2 blocks), K = batch;  B: h MN-major, N = d, K = batch)
-        {
-          const uint32_t id = tc::instr_desc(128, 64, 1, 1);
-          bool acc = bb > 0;
+      // ---- Adam on the tile, in the layout the weights were loaded in -----------------------------
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = pass == 2 ? s_dl : s_dh, b = hb + (pass == 1 ? BLK : 0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              tc::mma_bf16(tmem + T_DW, tc::desc_mnmajor(a, k, BLK), tc::desc_mnmajor(b, k, BLK), id, acc);
-              acc = true;
-            }
-          }
-        }
-        // db += dl^T . 1          (B: 16 rows of ones, K-major, two 64-wide K blocks of 2 KB)
-        {
-          const uint32_t id = tc::instr_desc(128, 16, 1, 0);
-          bool acc = bb > 0;
-#pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const uint32_t a = pass == 1 ? s_dl : s_dh;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              tc::mma_bf16(tmem + T_DB, tc::desc_mnmajor(a, k, BLK), tc::desc_kmajor(s_one + (k >> 2) * 2048, k & 3), id, acc);
-              acc = true;
-            }
-          }
-        }
-        // dh[bb] += dl . W        (A: dl K-major, M = batch, K = v (2 blocks);  B: W MN-major, N = d, K = v)
-        {
-          const uint32_t id = tc::instr_desc(128, 64, 0, 1);
-          bool acc = !first_tile;
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = pass == 2 ? s_dl : s_dh, b = pass == 1 ? s_wl : s_wh;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              tc::mma_bf16(tmem + T_DH + bb * 64, tc::desc_kmajor(a + (k >> 2) * BLK, k & 3), tc::desc_mnmajor(b, k, BLK), id, acc);
-              acc = true;
-            }
-          }
-        }
-        if (bb + 1 < nbb) {  // logits of the next block queue right behind
-          const uint32_t id = tc::instr_desc(128, 128, 0, 0);
-          const uint32_t hn = s_h + (bb + 1) * 2 * BLK;
-          bool acc = false;
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = hn + (pass == 2 ? BLK : 0), b = pass == 1 ? s_wl : s_wh;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { tc::mma_bf16(tmem + T_L, tc::desc_kmajor(a, k), tc::desc_kmajor(b, k), id, acc); acc = true; }
-          }
-          tc::mma_commit(&mbar[0]);
-        } else {
-          tc::mma_commit(&mbar[1]);
-        }
+      for (int i = 0; i < 4; ++i) {
+        const int cc = tid + 256 * i, row = cc >> 3, c8 = cc & 7;
+        if (v0 + row >= Vloc) continue;
+        const int64_t off = (int64_t)(v0 + row) * 64 + c8 * 8;
+        const float4 g0 = *reinterpret_cast<const float4 *>(dws + row * 68 + c8 * 8);
+        const float4 g1 = *reinterpret_cast<const float4 *>(dws + row * 68 + c8 * 8 + 4);
+        adam_f(pa[i].x, m0[i].x, u0[i].x, g0.x, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(pa[i].y, m0[i].y, u0[i].y, g0.y, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(pa[i].z, m0[i].z, u0[i].z, g0.z, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(pa[i].w, m0[i].w, u0[i].w, g0.w, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(pb[i].x, m1[i].x, u1[i].x, g1.x, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(pb[i].y, m1[i].y, u1[i].y, g1.y, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(pb[i].z, m1[i].z, u1[i].z, g1.z, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(pb[i].w, m1[i].w, u1[i].w, g1.w, b1, b2, eps, step_size, inv_bc2_sqrt);
+        *reinterpret_cast<float4 *>(hp.w + off) = pa[i];     *reinterpret_cast<float4 *>(hp.w + off + 4) = pb[i];
+        *reinterpret_cast<float4 *>(hp.wm + off) = m0[i];    *reinterpret_cast<float4 *>(hp.wm + off + 4) = m1[i];
+        *reinterpret_cast<float4 *>(hp.wv + off) = u0[i];    *reinterpret_cast<float4 *>(hp.wv + off + 4) = u1[i];
       }
+      if (tid < 128 && v0 + tid < Vloc) {
+        float p = hp.b[v0 + tid], m = hp.bm[v0 + tid], v = hp.bv[v0 + tid];
+        adam_f(p, m, v, db_s[tid], b1, b2, eps, step_size, inv_bc2_sqrt);
+        hp.b[v0 + tid] = p; hp.bm[v0 + tid] = m; hp.bv[v0 + tid] = v;
+      }
+      __syncthreads();  // dws (aliases dl) and w smem are rewritten by the next tile
     }
     first_tile = false;
-    tc::mbar_wait(&mbar[1], phB);  // all MMAs of this tile are complete
-    phB ^= 1;
-    tc::tc_fence_after();
-    // ---- epilogue 2: dW (TMEM) -> smem fp32 [128][68]; db -> smem ---------------------------------
-    {
-      const int r = q * 32 + lane;
-      float g[32];
-      tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + T_DW + (uint32_t)(ch * 32), g);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4 *>(dws + r * 68 + ch * 32 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-      if (ch == 0) {
-        float d16[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DB, d16);
-        tc::tmem_ld_wait();
-        db_s[r] = d16[0];
-      }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    // ---- Adam on the tile, in the layout the weights were loaded in -------------------------------
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int c = tid + 256 * i, row = c >> 3, c8 = c & 7;
-      if (v0 + row >= Vloc) continue;
-      const int64_t off = (int64_t)(v0 + row) * 64 + c8 * 8;
-      float4 m0 = *reinterpret_cast<const float4 *>(hp.wm + off), m1 = *reinterpret_cast<const float4 *>(hp.wm + off + 4);
-      float4 u0 = *reinterpret_cast<const float4 *>(hp.wv + off), u1 = *reinterpret_cast<const float4 *>(hp.wv + off + 4);
-      const float4 g0 = *reinterpret_cast<const float4 *>(dws + row * 68 + c8 * 8);
-      const float4 g1 = *reinterpret_cast<const float4 *>(dws + row * 68 + c8 * 8 + 4);
-      adam_f(pa[i].x, m0.x, u0.x, g0.x, b1, b2, eps, step_size, bc2_sqrt);
-      adam_f(pa[i].y, m0.y, u0.y, g0.y, b1, b2, eps, step_size, bc2_sqrt);
-      adam_f(pa[i].z, m0.z, u0.z, g0.z, b1, b2, eps, step_size, bc2_sqrt);
-      adam_f(pa[i].w, m0.w, u0.w, g0.w, b1, b2, eps, step_size, bc2_sqrt);
-      adam_f(pb[i].x, m1.x, u1.x, g1.x, b1, b2, eps, step_size, bc2_sqrt);
-      adam_f(pb[i].y, m1.y, u1.y, g1.y, b1, b2, eps, step_size, bc2_sqrt);
-      adam_f(pb[i].z, m1.z, u1.z, g1.z, b1, b2, eps, step_size, bc2_sqrt);
-      adam_f(pb[i].w, m1.w, u1.w, g1.w, b1, b2, eps, step_size, bc2_sqrt);
-      *reinterpret_cast<float4 *>(hp.w + off) = pa[i];  *reinterpret_cast<float4 *>(hp.w + off + 4) = pb[i];
-      *reinterpret_cast<float4 *>(hp.wm + off) = m0;    *reinterpret_cast<float4 *>(hp.wm + off + 4) = m1;
-      *reinterpret_cast<float4 *>(hp.wv + off) = u0;    *reinterpret_cast<float4 *>(hp.wv + off + 4) = u1;
-    }
-    if (tid < 128 && v0 + tid < Vloc) {
-      float p = hp.b[v0 + tid], m = hp.bm[v0 + tid], v = hp.bv[v0 + tid];
-      adam_f(p, m, v, db_s[tid], b1, b2, eps, step_size, bc2_sqrt);
-      hp.b[v0 + tid] = p; hp.bm[v0 + tid] = m; hp.bv[v0 + tid] = v;
-    }
-    __syncthreads();  // dws (aliases dl) and w smem are rewritten by the next tile
   }
-  // ---- dh of this CTA: TMEM -> its slice (zeros if the CTA owned no tile) ---------------------------
-  {
+  // ---- resident dh of this CTA: TMEM -> its slice ---------------------------------------------------
+  if (resident) {
     float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
+    const int nbb = (B + 127) / 128;
     for (int bb = 0; bb < nbb; ++bb) {
       const int row = bb * 128 + q * 32 + lane;
       float g[32];
@@ -536,7 +611,7 @@ __global__ void __launch_bounds__(256, 1) head_bwd_adam_tc_kernel(TcTrainPtrs hp
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-bool tc_bwd_supported(const rec_engine *e, int B) { return tc_heads_supported(e) && B <= 256; }
+bool tc_bwd_supported(const rec_engine *e, int B) { (void)B; return tc_heads_supported(e); }
 
 // Dense (supervised) head on tensor cores; returns the number of dh slices it wrote.
 int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
@@ -546,14 +621,17 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   const int n_tiles = cdiv(e->Vloc, 128);
   int n_cta = e->sm_count < n_tiles ? e->sm_count : n_tiles;
   if (n_cta > e->n_dh_part - 1) n_cta = e->n_dh_part - 1;
-  const size_t smem = 1024 + 10 * (size_t)BLK + 4096 + 1024;
+  const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072;
   static bool attr_set = false;
   if (!attr_set) {
     REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  head_bwd_adam_tc_kernel<<<n_cta, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles, inv_B,
-                                                          e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt);
+  h_prepack_kernel<<<cdiv(B, 128), 256, 0, e->stream>>>(h, B, e->hpack);
+  REC_LAUNCH_CHECK(e);
+  head_bwd_adam_tc_kernel<<<n_cta, 256, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles,
+                                                          inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size,
+                                                          1.f / bc2_sqrt);
   REC_LAUNCH_CHECK(e);
   *n_slices = n_cta;
   return REC_OK;

@@ -35,6 +35,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (spins > (1u << 24)) __trap();
 }
 
+// ---- TMA 1-D bulk copy global -> shared with mbarrier transaction count ---------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst/src 16-byte aligned, bytes a multiple of 16; completes on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- proxies / fences ----------------------------------------------------------------------------
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -511,3 +511,23 @@ def test_head_gradient_wrt_state_matches_autograd(pkg):
     assert float(((got - want).abs() / scale).max()) <= 1e-3
     ce = float(torch.nn.functional.cross_entropy(sup, a).detach())
     assert_close(losses[:2], [ce, float(loss.detach()) - ce], rtol=RTOL, atol=1e-5)
+
+
+@pytest.mark.parametrize("B", [300, 600])
+def test_large_batch_chunked_tensor_core_backward(pkg, B):
+    """B > 256 exercises the chunked (non TMEM-resident dh) path of the tcgen05 backward kernel."""
+    V, L = 3000, 10
+    kw = dict(hidden_dim=64, embedding_dim=64, gru_layers=1, train_pad_embed=True, use_packed_seq=True,
+              learning_rate=0.01, item_num=V, state_size=L, action_dim=V)
+    ref = oracle.GRUTrainer(**kw)
+    t = pkg.GRU4Rec_trainer(device=DEV, **kw)
+    assert_state_close(t.gru_model.state_dict(), ref.gru_model.state_dict(), rtol=0, atol=0)
+    t.send_to_device()
+    rows = _syn().make_replay_rows(2 * B, V, L, seed=15)
+    for i in range(2):
+        s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+        want = ref.train_step(s, a, ln)
+        got = t.train_step(s, a, ln)
+        assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} loss")
+    assert_state_close(t.gru_model.state_dict(), ref.gru_model.state_dict(), rtol=RTOL, atol=ATOL_P, outlier_frac=1e-3,
+                       outlier_atol=0.02 * 0.01 * 2)
