@@ -196,6 +196,11 @@ extern "C" int rec_set_tensor_cores(rec_engine *e, int on) {
   e->use_tc = on != 0;
   return REC_OK;
 }
+extern "C" int rec_debug_set_trace(rec_engine *e, long long *dev_buf) {
+  if (!e) return REC_EINVAL;
+  e->trace = dev_buf;
+  return REC_OK;
+}
 extern "C" int64_t rec_launch_count(const rec_engine *e) { return e ? e->launches : -1; }
 extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) { if (!e) return REC_EINVAL; e->timing = on != 0; return REC_OK; }
 extern "C" float rec_last_kernel_ms(rec_engine *e, int which) {

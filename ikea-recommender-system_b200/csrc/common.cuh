@@ -64,6 +64,7 @@ struct rec_engine {
   float *summary;        // [maxB][part_stride] per-row record of this shard
   float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;
+  long long *trace;      // optional device buffer for clock64 phase traces (debug)
   bool use_tc;           // tensor-core (tcgen05) head kernels when D == 64
   cudaEvent_t ev[8];
   float last_ms[3];

@@ -55,36 +55,49 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // ---- TMEM ----------------------------------------------------------------------------------------
 // one full warp allocates `cols` (power of two >= 32) columns; base address is written to *dst (smem)
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst, uint32_t cols) {
+  __syncwarp();
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  __syncwarp();
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 
-// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (32*(warp%4) + i)
+// TMEM -> registers.  32 lanes x N consecutive 32-bit columns: thread i of the warp gets lane
+// (32*(warp%4) + i).  tcgen05.ld is ASYNCHRONOUS: the destination registers are only valid after
+// tcgen05.wait::ld.  Both instructions live in ONE asm statement so that the compiler can never move,
+// copy or spill the destination registers between the load and the wait (it cannot see the asynchrony).
+// (.sync.aligned: the whole warp must execute them convergently -> __syncwarp first.)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  __syncwarp();
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  __syncwarp();
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
+      : "r"(taddr)
+      : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// kept for call sites that still pair an explicit wait with the loads above (now a no-op barrier)
+__device__ __forceinline__ void tmem_ld_wait() { __syncwarp(); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ---------------------------------------------------------------------------------
 // 64-bit shared-memory matrix descriptor (PTX "matrix descriptor", Blackwell version = 1, SWIZZLE_128B)
