@@ -96,7 +96,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   const int n_tiles = (e->Vloc + 63) / 64;
   e->n_dh_part = (n_tiles < 2 * e->sm_count ? n_tiles : 2 * e->sm_count) + 1;
   ALLOC(e, e->dh_part, float, (int64_t)e->n_dh_part * mb * D);
-  e->wgrad_splits = 16;
+  e->wgrad_splits = 64;
   const int64_t KS = (E > H ? E : H) + 1;
   ALLOC(e, e->wgrad_part, float, (int64_t)e->wgrad_splits * dirs * 2 * G * KS);
   ALLOC(e, e->emb_keys, int32_t, mb * L);

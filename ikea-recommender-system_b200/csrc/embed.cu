@@ -67,16 +67,16 @@ __global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restr
     const bool fast = (E <= 64 && dirs == 1);
     int cnt = 0;
     auto flush_list = [&]() {
-      for (int i0 = 0; i0 < cnt; i0 += 16) {
-        float2 v[16];
+      for (int i0 = 0; i0 < cnt; i0 += 32) {
+        float2 v[32];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < 32; ++u) {
           v[u] = make_float2(0.f, 0.f);
           if (i0 + u < cnt && 2 * lane < E)
             v[u] = *reinterpret_cast<const float2 *>(dx + (int64_t)plist[wid][i0 + u] * E + 2 * lane);
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
+        for (int u = 0; u < 32; ++u)
           if (i0 + u < cnt) { acc2.x += v[u].x; acc2.y += v[u].y; }
       }
       __syncwarp();
@@ -131,13 +131,21 @@ __device__ __forceinline__ void adam_update4(float4 &p, float4 &m, float4 &v, co
 // grad_rows[slot_of_row[r] * grad_stride4 + c] when slot_of_row[r] >= 0, else 0.  HBM-bound streaming
 // kernel (24 B/param): every thread keeps UNROLL independent (p, m, v) float4 triples in flight.
 // Optional bias vector (one element per row) is updated by the thread that owns column chunk 0.
+struct AdamStreamSet {  // up to 3 same-shaped tensors updated by one launch (blockIdx.y)
+  float4 *p[3], *m[3], *v[3];
+  const float4 *grad_rows[3];
+  float *bp[3], *bm[3], *bv[3];
+  const float *bgrad[3];
+};
+
 template <int UNROLL>
-__global__ void __launch_bounds__(256) adam_stream_kernel(float4 *__restrict__ p, float4 *__restrict__ m,
-                                                          float4 *__restrict__ v,
-                                                          const int32_t *__restrict__ slot_of_row,
-                                                          const float4 *__restrict__ grad_rows, int grad_stride4,
-                                                          uint32_t n4, int D4, int d4_shift, float b1, float b2,
-                                                          float eps, float step_size, float inv_bc2_sqrt) {
+__global__ void __launch_bounds__(256) adam_stream_kernel(AdamStreamSet ts, const int32_t *__restrict__ slot_of_row,
+                                                          int grad_stride4, uint32_t n4, int D4, int d4_shift, float b1,
+                                                          float b2, float eps, float step_size, float inv_bc2_sqrt) {
+  float4 *__restrict__ p = ts.p[blockIdx.y];
+  float4 *__restrict__ m = ts.m[blockIdx.y];
+  float4 *__restrict__ v = ts.v[blockIdx.y];
+  const float4 *__restrict__ grad_rows = ts.grad_rows[blockIdx.y];
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
     float4 pv[UNROLL], mv[UNROLL], vv[UNROLL];
@@ -166,24 +174,23 @@ __global__ void __launch_bounds__(256) adam_stream_kernel(float4 *__restrict__ p
   }
 }
 
-// bias vector of a head: one element per row, gradient through the same slot map
-__global__ void __launch_bounds__(256) adam_bias_kernel(float *__restrict__ bp, float *__restrict__ bm,
-                                                        float *__restrict__ bv, const int32_t *__restrict__ slot_of_row,
-                                                        const float *__restrict__ bgrad, int bgrad_stride, int rows,
-                                                        float b1, float b2, float eps, float step_size,
-                                                        float inv_bc2_sqrt) {
+// bias vectors of the same tensors: one element per row, gradient through the same slot map
+__global__ void __launch_bounds__(256) adam_bias_kernel(AdamStreamSet ts, const int32_t *__restrict__ slot_of_row,
+                                                        int bgrad_stride, int rows, float b1, float b2, float eps,
+                                                        float step_size, float inv_bc2_sqrt) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
+  float *bp = ts.bp[blockIdx.y], *bm = ts.bm[blockIdx.y], *bv = ts.bv[blockIdx.y];
   int slot = slot_of_row[r];
-  float g = slot >= 0 ? bgrad[(size_t)slot * bgrad_stride] : 0.f;
+  float g = slot >= 0 ? ts.bgrad[blockIdx.y][(size_t)slot * bgrad_stride] : 0.f;
   float p = bp[r], m = bm[r], v = bv[r];
   adam_elem(p, m, v, g, b1, b2, eps, step_size, inv_bc2_sqrt);
   bp[r] = p; bm[r] = m; bv[r] = v;
 }
 
-int launch_adam_stream(rec_engine *e, float *p, float *m, float *v, int64_t rows, int D, const int32_t *slot_of_row,
-                       const float *grad_rows, int grad_stride, float *bp, float *bm, float *bv, const float *bgrad,
-                       int bgrad_stride, const rec_train_hparams *hp, float step_size, float bc2_sqrt) {
+static int launch_adam_stream_set(rec_engine *e, const AdamStreamSet &ts, int n_tensors, bool with_bias, int64_t rows, int D,
+                                  const int32_t *slot_of_row, int grad_stride, int bgrad_stride,
+                                  const rec_train_hparams *hp, float step_size, float bc2_sqrt) {
   const int64_t n4 = rows * (D / 4);
   if (n4 >= (int64_t)1 << 31) REC_FAIL(e, REC_EINVAL, "adam_stream: tensor too large (%lld float4)", (long long)n4);
   constexpr int UNROLL = 2;
@@ -191,19 +198,29 @@ int launch_adam_stream(rec_engine *e, float *p, float *m, float *v, int64_t rows
   int shift = -1;
   if ((D4 & (D4 - 1)) == 0) { shift = 0; while ((1 << shift) < D4) ++shift; }
   int64_t want = cdiv64(n4, 256 * UNROLL);
-  int blocks = (int)(want < (int64_t)e->sm_count * 16 ? want : (int64_t)e->sm_count * 16);
+  int per = (e->sm_count * 16) / n_tensors;
+  int blocks = (int)(want < (int64_t)per ? want : (int64_t)per);
   if (blocks < 1) blocks = 1;
-  adam_stream_kernel<UNROLL><<<blocks, 256, 0, e->stream>>>((float4 *)p, (float4 *)m, (float4 *)v, slot_of_row,
-                                                            (const float4 *)grad_rows, grad_stride / 4, (uint32_t)n4, D4,
-                                                            shift, hp->beta1, hp->beta2, hp->eps, step_size,
-                                                            1.f / bc2_sqrt);
+  dim3 grid(blocks, n_tensors);
+  adam_stream_kernel<UNROLL><<<grid, 256, 0, e->stream>>>(ts, slot_of_row, grad_stride / 4, (uint32_t)n4, D4, shift, hp->beta1,
+                                                          hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt);
   REC_LAUNCH_CHECK(e);
-  if (bp) {
-    adam_bias_kernel<<<cdiv((int)rows, 256), 256, 0, e->stream>>>(bp, bm, bv, slot_of_row, bgrad, bgrad_stride, (int)rows,
-                                                                 hp->beta1, hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt);
+  if (with_bias) {
+    dim3 g2(cdiv((int)rows, 256), n_tensors);
+    adam_bias_kernel<<<g2, 256, 0, e->stream>>>(ts, slot_of_row, bgrad_stride, (int)rows, hp->beta1, hp->beta2, hp->eps, step_size,
+                                               1.f / bc2_sqrt);
     REC_LAUNCH_CHECK(e);
   }
   return REC_OK;
+}
+
+int launch_adam_stream(rec_engine *e, float *p, float *m, float *v, int64_t rows, int D, const int32_t *slot_of_row,
+                       const float *grad_rows, int grad_stride, float *bp, float *bm, float *bv, const float *bgrad,
+                       int bgrad_stride, const rec_train_hparams *hp, float step_size, float bc2_sqrt) {
+  AdamStreamSet ts = {};
+  ts.p[0] = (float4 *)p; ts.m[0] = (float4 *)m; ts.v[0] = (float4 *)v; ts.grad_rows[0] = (const float4 *)grad_rows;
+  ts.bp[0] = bp; ts.bm[0] = bm; ts.bv[0] = bv; ts.bgrad[0] = bgrad;
+  return launch_adam_stream_set(e, ts, 1, bp != nullptr, rows, D, slot_of_row, grad_stride, bgrad_stride, hp, step_size, bc2_sqrt);
 }
 
 // ---- row-sparse gradients of the Q heads --------------------------------------------------------
@@ -215,8 +232,9 @@ __global__ void __launch_bounds__(256) q_grad_rows_kernel(const int64_t *__restr
                                                           int vocab_lo, float *__restrict__ grad_rows,
                                                           float *__restrict__ bgrad, int32_t *__restrict__ slot_of_row) {
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= B) return;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per (batch row, Q head)
+  if (w >= B * n_q) return;
+  const int b = w / n_q, j = w - b * n_q;
   const int64_t key = a[b];
   const int64_t loc = key - vocab_lo;
   if (loc < 0 || loc >= Vloc) return;
@@ -224,30 +242,45 @@ __global__ void __launch_bounds__(256) q_grad_rows_kernel(const int64_t *__restr
     int q = q0 + lane;
     if (__ballot_sync(0xffffffffu, q < b && a[q] == key)) return;
   }
-  for (int j = 0; j < n_q; ++j) {
-    for (int d0 = 0; d0 < D; d0 += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float bsum = 0.f;
-      const int col = d0 + lane * 4;
-      for (int q0 = b; q0 < B; q0 += 32) {
-        int q = q0 + lane;
-        unsigned mm = __ballot_sync(0xffffffffu, q < B && a[q] == key);
-        while (mm) {
-          int l = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const float g = dq[(q0 + l) * 3 + j];
-          bsum += g;
-          if (col < D) {
-            const float4 hv = *reinterpret_cast<const float4 *>(h + (int64_t)(q0 + l) * D + col);
-            acc.x = fmaf(g, hv.x, acc.x); acc.y = fmaf(g, hv.y, acc.y); acc.z = fmaf(g, hv.z, acc.z); acc.w = fmaf(g, hv.w, acc.w);
+  for (int d0 = 0; d0 < D; d0 += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bsum = 0.f;
+    const int col = d0 + lane * 4;
+    for (int q0 = b; q0 < B; q0 += 32) {
+      const int q = q0 + lane;
+      const bool hit = q < B && a[q] == key;
+      const float gl = hit ? dq[q * 3 + j] : 0.f;  // coalesced, then broadcast by shuffle
+      unsigned mm = __ballot_sync(0xffffffffu, hit);
+      while (mm) {
+        int idx[4];
+        float4 hv[4];
+        int n = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          idx[u] = -1;
+          hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mm) {
+            idx[u] = __ffs(mm) - 1;
+            mm &= mm - 1;
+            if (col < D) hv[u] = *reinterpret_cast<const float4 *>(h + (int64_t)(q0 + idx[u]) * D + col);
+            n = u + 1;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u < n) {
+            const float g = __shfl_sync(0xffffffffu, gl, idx[u]);
+            bsum += g;
+            acc.x = fmaf(g, hv[u].x, acc.x); acc.y = fmaf(g, hv[u].y, acc.y);
+            acc.z = fmaf(g, hv[u].z, acc.z); acc.w = fmaf(g, hv[u].w, acc.w);
           }
         }
       }
-      if (col < D) *reinterpret_cast<float4 *>(grad_rows + ((int64_t)b * n_q + j) * D + col) = acc;
-      if (d0 == 0 && lane == 0) bgrad[b * n_q + j] = bsum;
     }
+    if (col < D) *reinterpret_cast<float4 *>(grad_rows + ((int64_t)b * n_q + j) * D + col) = acc;
+    if (d0 == 0 && lane == 0) bgrad[b * n_q + j] = bsum;
   }
-  if (lane == 0) slot_of_row[loc] = b;
+  if (lane == 0 && j == 0) slot_of_row[loc] = b;
 }
 
 __global__ void q_slot_reset_kernel(const int64_t *__restrict__ a, int B, int Vloc, int vocab_lo,
@@ -263,13 +296,18 @@ int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_bat
                         float bc2_sqrt, const rec_train_hparams *hp) {
   const int n_q = e->cfg.n_heads - 1, D = e->D;
   const rec_net_params &p = e->nets[net_id].p;
-  q_grad_rows_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(b->a, e->dq, h, B, D, n_q, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
+  q_grad_rows_kernel<<<cdiv(B * n_q, 8), 256, 0, e->stream>>>(b->a, e->dq, h, B, D, n_q, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
                                                        e->q_bgrad, e->q_slot);
   REC_LAUNCH_CHECK(e);
-  for (int j = 0; j < n_q; ++j) {
-    int rc = launch_adam_stream(e, p.head_w[1 + j], p.head_w_m[1 + j], p.head_w_v[1 + j], e->Vloc, D, e->q_slot,
-                                e->q_grad_rows + (int64_t)j * D, n_q * D, p.head_b[1 + j], p.head_b_m[1 + j],
-                                p.head_b_v[1 + j], e->q_bgrad + j, n_q, hp, step_size, bc2_sqrt);
+  {
+    AdamStreamSet ts = {};
+    for (int j = 0; j < n_q; ++j) {
+      ts.p[j] = (float4 *)p.head_w[1 + j]; ts.m[j] = (float4 *)p.head_w_m[1 + j]; ts.v[j] = (float4 *)p.head_w_v[1 + j];
+      ts.grad_rows[j] = (const float4 *)(e->q_grad_rows + (int64_t)j * D);
+      ts.bp[j] = p.head_b[1 + j]; ts.bm[j] = p.head_b_m[1 + j]; ts.bv[j] = p.head_b_v[1 + j];
+      ts.bgrad[j] = e->q_bgrad + j;
+    }
+    int rc = launch_adam_stream_set(e, ts, n_q, true, e->Vloc, D, e->q_slot, n_q * D, n_q, hp, step_size, bc2_sqrt);
     if (rc) return rc;
   }
   q_slot_reset_kernel<<<cdiv(B, 256), 256, 0, e->stream>>>(b->a, B, e->Vloc, e->cfg.vocab_lo, e->q_slot);

@@ -148,7 +148,8 @@ struct GruPass {
 };
 struct GruPasses { GruPass p[3]; };
 
-#define FR 2
+#define FR 3   // sessions per CTA in the forward fast path (FR * 64 == 192 threads in the gate-combine phase)
+#define BR 2   // sessions per CTA in the BPTT fast path
 __global__ void __launch_bounds__(192, 2) gru_fwd64_kernel(GruPasses ps, int B, int L, int N, int packed,
                                                            float *__restrict__ gates_save,
                                                            float *__restrict__ hprev_save) {
@@ -184,7 +185,9 @@ __global__ void __launch_bounds__(192, 2) gru_fwd64_kernel(GruPasses ps, int B, 
   }
   if (tid < FR * H) hs[tid / H][tid % H] = 0.f;
   __syncthreads();
-  const int maxlen = max(len_s[0], len_s[1]);
+  int maxlen = 0;
+#pragma unroll
+  for (int r = 0; r < FR; ++r) maxlen = max(maxlen, len_s[r]);
   // x loader: threads [0, FR*16) own one float4 of one row
   const int xr = tid >> 4, xc = tid & 15;
   auto load_x = [&](int i) -> float4 {
@@ -254,13 +257,13 @@ __global__ void __launch_bounds__(128, 2) gru_bwd64_kernel(GruWeights w, const i
                                                            float *__restrict__ dx) {
   constexpr int H = 64, E = 64, G = 192;
   const int dir = blockIdx.y, dirs = gridDim.y;
-  const int b0 = blockIdx.x * FR;
+  const int b0 = blockIdx.x * BR;
   const int tid = threadIdx.x;
-  __shared__ float dhs[FR][H];
-  __shared__ float dhd[FR][H];
-  __shared__ __align__(16) float dai[FR][G];
-  __shared__ __align__(16) float dah[FR][G];
-  __shared__ int len_s[FR];
+  __shared__ float dhs[BR][H];
+  __shared__ float dhd[BR][H];
+  __shared__ __align__(16) float dai[BR][G];
+  __shared__ __align__(16) float dah[BR][G];
+  __shared__ int len_s[BR];
   const bool is_h = tid < 64;
   const int c = tid & 63;
   float wc[G];
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(128, 2) gru_bwd64_kernel(GruWeights w, const i
 #pragma unroll
     for (int j = 0; j < G; ++j) wc[j] = __ldg(src + (int64_t)j * 64);
   }
-  if (tid < FR) len_s[tid] = (b0 + tid < B) ? eff_len(lens, b0 + tid, L, packed) : 0;
+  if (tid < BR) len_s[tid] = (b0 + tid < B) ? eff_len(lens, b0 + tid, L, packed) : 0;
   {
     const int r = tid >> 6, u = tid & 63;
     dhs[r][u] = (b0 + r < B) ? dh_in[(int64_t)(b0 + r) * (dirs * H) + dir * H + u] : 0.f;
@@ -305,13 +308,13 @@ __global__ void __launch_bounds__(128, 2) gru_bwd64_kernel(GruWeights w, const i
     }
     __syncthreads();
     {
-      float acc[FR][2];
+      float acc[BR][2];
 #pragma unroll
-      for (int r = 0; r < FR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+      for (int r = 0; r < BR; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
 #pragma unroll
       for (int j4 = 0; j4 < G / 4; ++j4) {
 #pragma unroll
-        for (int r = 0; r < FR; ++r) {
+        for (int r = 0; r < BR; ++r) {
           float4 d = is_h ? reinterpret_cast<const float4 *>(&dah[r][0])[j4]
                           : reinterpret_cast<const float4 *>(&dai[r][0])[j4];
           acc[r][0] = fmaf(d.x, wc[4 * j4], acc[r][0]); acc[r][1] = fmaf(d.y, wc[4 * j4 + 1], acc[r][1]);
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(128, 2) gru_bwd64_kernel(GruWeights w, const i
       }
       // dhs is only read in the elementwise phase above (already past the barrier): safe to update
 #pragma unroll
-      for (int r = 0; r < FR; ++r) {
+      for (int r = 0; r < BR; ++r) {
         float v = acc[r][0] + acc[r][1];
         if (is_h) {
           dhs[r][c] = dhd[r][c] + v;  // inactive rows: dah = 0 -> dhs unchanged
@@ -655,7 +658,7 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
     attr_set = true;
   }
   if (gru_fast_path(e)) {
-    dim3 grid(cdiv(B, FR), e->dirs);
+    dim3 grid(cdiv(B, BR), e->dirs);
     gru_bwd64_kernel<<<grid, 128, 0, e->stream>>>(gru_weights(e, net_id), lengths, B, L, c.use_packed_seq, dh,
                                                  e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx);
   } else {
