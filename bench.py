@@ -33,6 +33,13 @@ WORKLOADS = {
                  item_num=1_000_000, batch=256, L=10, E=64, H=64),
 }
 METRIC = "SMORL-SQN-GRU4Rec train sessions/s"
+EVAL_WORKLOADS = {
+    # BASELINE.json configs[4]: full-catalogue evaluation sweep over 1M items (HR/NDCG@{5,10,20} + coverage/div/nov)
+    "eval": dict(name="cfg5: evaluate() sweep, V=N=1000000, val batch 5000, HR/NDCG@{5,10,20}, cov@{1,5,10,20}, div, nov",
+                 item_num=1_000_000, batch=5000, L=10, E=64, H=64),
+    "eval70k": dict(name="evaluate() sweep, V=N=70852, val batch 2000 (SMORL_paper.yaml), HR/NDCG@{5,10,20}, cov@{1,5,10,20}",
+                    item_num=70852, batch=2000, L=10, E=64, H=64),
+}
 
 
 def _peaks():
@@ -265,16 +272,100 @@ def run_native(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def run_eval(args, wl):
+    """Secondary metric of BASELINE.json: full-catalogue top-k evaluation sessions/s (1 GPU)."""
+    import torch
+    import b200pkg
+    pkg = b200pkg.load()
+    from ikea_recommender_system_b200 import synthetic
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    N, B, L = wl["item_num"], wl["batch"], wl["L"]
+    n_batches = max(2, min(args.steps, 8))
+    rows = synthetic.make_replay_rows_fast(n_batches * B, N, L, seed=7)
+    unpop = synthetic.unpopular_set_from_actions(rows["action"])
+    g = torch.Generator().manual_seed(1)
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(N + 1, 64, generator=g), freeze=True)
+    torch.manual_seed(118)
+    net = pkg.SQN_Network(hidden_dim=wl["H"], item_num=N, state_size=L, action_dim=N, gamma=0.5, gru_layers=1,
+                          embedding_dim=wl["E"], use_packed_seq=True)
+    net.to(dev)
+    loader = []
+    for i in range(n_batches):
+        s_, a_, _, _, ln_, _, _ = synthetic.as_torch_batch(rows, i * B, (i + 1) * B)
+        loader.append((s_, a_, ln_))
+    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1, topk_to_consider_nov=1,
+              topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+    ce = torch.nn.CrossEntropyLoss()
+    for _ in range(max(1, args.warmup // 3)):
+        pkg.evaluate(loader[:2], net, dev, ce, "end", e_div, unpop, **kw)
+    torch.cuda.synchronize()
+    # e2e: the public evaluate() with host batches (H2D of s, a, len per batch; accumulators read back at the end)
+    reps = max(1, args.steps // n_batches)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = pkg.evaluate(loader, net, dev, ce, "end", e_div, unpop, **kw)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sessions = reps * n_batches * B
+    # device-resident: rec_eval_batch on batches already in HBM, CUDA events
+    from ikea_recommender_system_b200.recommenders.evaluate.eval_protocol import _opts
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    eng = net._ready(B)
+    o, kmax, keep = _opts(net, dev, 0, [5, 10, 20], 1, 1, [1, 5, 10, 20], 1, "end", e_div, unpop, None, None)
+    dev_b = []
+    for s_, a_, ln_ in loader:
+        ds, dl = net._dev_inputs(s_, ln_)
+        dev_b.append((ds, a_.to(dev), dl))
+    acc = EvalAccumulators(dev, N)
+    eng.enable_kernel_timing(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launch_count()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+        for ds, da, dl in dev_b:
+            eng.eval_batch(net._net_id, eng._batch(B, ds, da, dl), o, acc.struct)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - l0
+    head_ms = eng.last_kernel_ms(1)
+    value = sessions / (ms / 1e3)
+    flops = 2.0 * 64 * N * B * 3  # bf16x3: three tensor passes per logit
+    line = {"metric": "full-catalogue top-k evaluation sessions/s", "value": value, "unit": "sessions/s", "n_gpus": 1,
+            "steps": reps * n_batches, "warmup": args.warmup, "ms_per_step": ms / (reps * n_batches),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32 accumulate)",
+            "data": "synthetic", "config": {"workload": wl["name"], "l2_policy": "head weights (256 MB at 1M items) exceed L2"},
+            "e2e": {"value": sessions / e2e_s, "unit": "sessions/s", "h2d_bytes_per_step": B * (L + 2) * 8,
+                    "d2h_bytes_per_step": 8 * 27 + 4 * 8 * ((N + 31) // 32) // max(1, n_batches)},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "head_stats_tc_kernel (logits + online softmax + top-20)",
+                         "achieved": flops / (head_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+                         "traffic": None, "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / (reps * n_batches)),
+                         "note": "executed bf16 FLOPs (3 passes); algorithmic 2*D*V per session"},
+            "metrics_sample": {"hr": [float(x) for x in out[1]], "ndcg": [float(x) for x in out[2]]}}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        line["roofline"]["peak"] = pk["bf16_tflops_sustained"]
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / pk["bf16_tflops_sustained"]
+    except Exception:
+        pass
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + sorted(EVAL_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload in EVAL_WORKLOADS:
+        return run_eval(args, EVAL_WORKLOADS[args.workload])
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
