@@ -50,45 +50,92 @@ __device__ __forceinline__ void stage_rows64(uint8_t *blk_hi, uint8_t *blk_lo, c
   }
 }
 
-__global__ void __launch_bounds__(256, 2) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
-                                                               int vocab_lo, int n_tiles, int do_stats, int first_head,
-                                                               int upg, float w0, float w1, float w2,
-                                                               const int64_t *__restrict__ target, int topk,
-                                                               float *__restrict__ part, int part_stride) {
+// Slow path of the running top-k: insert the elements of one 32-column chunk that beat the k-th best into
+// the thread-private sorted list (shared memory, stride `stride` between ranks).  Ascending column order +
+// strict comparisons keep equal scores ordered by ascending id.
+__device__ __noinline__ void topk_insert_chunk(const float *lbuf, float *lv, int *li, int stride, int topk, int id0,
+                                               int &cnt, float &tau) {
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const float v = lbuf[j];
+    if (v > tau) {
+      int p = cnt < topk ? cnt : topk - 1;
+      while (p > 0 && lv[(p - 1) * stride] < v) {
+        lv[p * stride] = lv[(p - 1) * stride];
+        li[p * stride] = li[(p - 1) * stride];
+        --p;
+      }
+      lv[p * stride] = v;
+      li[p * stride] = id0 + j;
+      if (cnt < topk) ++cnt;
+      tau = cnt == topk ? lv[(topk - 1) * stride] : REC_NEG_INF;
+    }
+  }
+}
+
+// NB = 128-session blocks per CTA (they share every converted W tile), NT = threads (256: two 64-column
+// halves per row, 512: four 32-column quarters per row).  TMEM: NB x 2 accumulator tiles of 128 columns.
+template <int NB, int NT>
+__global__ void __launch_bounds__(NT, 1) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
+                                                              int vocab_lo, int n_tiles, int do_stats, int first_head,
+                                                              int upg, float w0, float w1, float w2,
+                                                              const int64_t *__restrict__ target, int topk,
+                                                              float *__restrict__ part, int part_stride,
+                                                              long long *__restrict__ trace) {
+  int tr_n = 0;
+#define STRACE(tag) do { if (trace && do_stats && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && tr_n < 120) { trace[2 * tr_n] = (tag); trace[2 * tr_n + 1] = clock64(); ++tr_n; } } while (0)
+  constexpr int CS = NT / 128;   // column splits per row
+  constexpr int CW = 128 / CS;   // columns per thread and tile
+  constexpr int TASKS = 1024 / NT;  // 16-byte chunk pairs per thread when staging a [128 x 64] fp32 tile
   extern __shared__ uint8_t raw[];
   uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *h_hi = sm, *h_lo = sm + BLK;
-  uint8_t *w_st = sm + 2 * BLK;                                   // stage s: hi at w_st + s*2*BLK, lo at + BLK
-  float *bias_g = reinterpret_cast<float *>(sm + 6 * BLK);       // [3][128] (3-deep: a thread may run one barrier ahead)
-  float *tv = bias_g + 384;                                       // [topk][256]
-  int *ti = reinterpret_cast<int *>(tv + (size_t)topk * 256);     // [topk][256]
+  uint8_t *h_blk = sm;                                            // [NB][hi|lo] x BLK
+  uint8_t *w_st = sm + NB * 2 * BLK;                              // stage s: hi at w_st + s*2*BLK, lo at + BLK
+  float *bias_g = reinterpret_cast<float *>(w_st + 4 * BLK);     // [3][128] (3-deep: a thread may run one barrier ahead)
+  float *xch = bias_g + 384;                                      // [NB][128][CS][5] end-of-kernel exchange
+  float *tv = xch + NB * 128 * CS * 5;                            // [NB][topk][NT]
+  int *ti = reinterpret_cast<int *>(tv + (size_t)NB * topk * NT); // [NB][topk][NT]
   __shared__ uint64_t mbar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, ch = warp >> 2;  // TMEM lane quarter, column half
-  const int sp = blockIdx.x, n_split = gridDim.x, bb = blockIdx.y;
-  const int b0 = bb * 128;
+  const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column split
+  const int sp = blockIdx.x, n_split = gridDim.x, bg = blockIdx.y;
+  const int b0 = bg * NB * 128;
   const int per = (n_tiles + n_split - 1) / n_split;
   const int t_lo = sp * per, t_hi = min(n_tiles, t_lo + per);
   const int n_groups = max(0, t_hi - t_lo), n_units = n_groups * upg;
   const bool argmode = !do_stats && topk == 0;
 
+  STRACE(19);
   if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_barrier_init(); }
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
-  stage_rows64(h_hi, h_lo, h, b0, B, 1.f, tid);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, NB * 256);
+  // h blocks of this CTA -> bf16 hi/lo (zero rows beyond B)
+  for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+    for (int i = 0; i < TASKS; ++i) {
+      const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (b0 + nb * 128 + row < B) {
+        const float4 *p = reinterpret_cast<const float4 *>(h + (int64_t)(b0 + nb * 128 + row) * 64 + c8 * 8);
+        a = p[0];
+        b = p[1];
+      }
+      tc::store_split8(h_blk + nb * 2 * BLK, h_blk + nb * 2 * BLK + BLK, row, c8, a, b);
+    }
+  }
 
   // unit u = (vocabulary tile g, head hh).  fetch(): global -> registers (in flight across a whole
   // pipeline step); store(): registers -> bf16 hi/lo swizzled smem stage + bias tile.
-  float4 fa[4], fb[4];
+  float4 fa[TASKS], fb[TASKS];
   float fbias = 0.f;
   auto unit_scale = [&](int hh) { return (argmode && upg > 1) ? (hh == 0 ? w0 : (hh == 1 ? w1 : w2)) : 1.f; };
   auto fetch = [&](int u) {
     const int g = u / upg, hh = u - g * upg, head = first_head + hh, v0 = (t_lo + g) * 128;
     const float *src = hp.w[head];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = tid + 256 * i, row = c >> 3, c8 = c & 7;
+    for (int i = 0; i < TASKS; ++i) {
+      const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
       fa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       fb[i] = fa[i];
       if (v0 + row < Vloc) {
@@ -104,8 +151,8 @@ __global__ void __launch_bounds__(256, 2) head_stats_tc_kernel(TcHeadPtrs hp, co
     const float scale = unit_scale(hh);
     uint8_t *bh = w_st + s * 2 * BLK, *bl = bh + BLK;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = tid + 256 * i;
+    for (int i = 0; i < TASKS; ++i) {
+      const int c = tid + NT * i;
       if (scale != 1.f) {
         fa[i].x *= scale; fa[i].y *= scale; fa[i].z *= scale; fa[i].w *= scale;
         fb[i].x *= scale; fb[i].y *= scale; fb[i].z *= scale; fb[i].w *= scale;
@@ -117,30 +164,44 @@ __global__ void __launch_bounds__(256, 2) head_stats_tc_kernel(TcHeadPtrs hp, co
       *dst = (hh == 0) ? fbias * scale : (*dst + fbias * scale);
     }
   };
-  auto issue_unit = [&](int u) {  // one thread
+  const uint32_t id_l = tc::instr_desc(128, 128, 0, 0);
+  auto issue_unit = [&](int u) {  // one thread: NB logits tiles against the same W stage
     const int g = u / upg, hh = u - g * upg, s = u & 1;
-    const uint32_t d = tmem_base_s + (uint32_t)(g & 1) * 128;
-    const uint32_t ah = tc::smem_u32(h_hi), al = tc::smem_u32(h_lo);
-    const uint32_t bh = tc::smem_u32(w_st + s * 2 * BLK), bl = bh + BLK;
-    const uint32_t id = tc::instr_desc(128, 128, 0, 0);
-    bool acc = hh > 0;
+    const uint64_t bh = tc::desc_kmajor(tc::smem_u32(w_st + s * 2 * BLK), 0), bl = tc::desc_kmajor(tc::smem_u32(w_st + s * 2 * BLK + BLK), 0);
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+    for (int nb = 0; nb < NB; ++nb) {
+      const uint32_t d = tmem_base_s + (uint32_t)((g & 1) * NB + nb) * 128;
+      const uint64_t ah = tc::desc_kmajor(tc::smem_u32(h_blk + nb * 2 * BLK), 0), al = tc::desc_kmajor(tc::smem_u32(h_blk + nb * 2 * BLK + BLK), 0);
+      bool acc = hh > 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { tc::mma_bf16(d, tc::desc_kmajor(a, k), tc::desc_kmajor(b, k), id, acc); acc = true; }
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tc::mma_bf16(d, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id_l, acc); acc = true; }
+      }
     }
     tc::mma_commit(&mbar[s]);
   };
 
-  // per-thread running state: this thread owns batch row (b0 + q*32 + lane), tile columns [ch*64, ch*64+64)
-  const int row = b0 + q * 32 + lane;
-  float m_run = REC_NEG_INF, s_run = 0.f, tgt = REC_NEG_INF, av = REC_NEG_INF, tau = REC_NEG_INF;
-  int ai = 0x7fffffff, cnt = 0;
-  const int trow = (do_stats && target && row < B) ? (int)(target[row] - vocab_lo) : -1;
+  // per-thread running state per block: row (b0 + nb*128 + q*32 + lane), tile columns [cq*CW, cq*CW + CW)
+  float m_run[NB], s_run[NB], tgt[NB], av[NB], tau[NB];
+  int ai[NB], cnt[NB], trow[NB];
+  float r_v0[NB], r_v1[NB];  // top-k <= 2 lives in registers (no warm-up cost when a CTA only sees a few tiles)
+  int r_i0[NB], r_i1[NB];
+  const bool smallk = topk > 0 && topk <= 2;
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    m_run[nb] = REC_NEG_INF; s_run[nb] = 0.f; tgt[nb] = REC_NEG_INF; av[nb] = REC_NEG_INF; tau[nb] = REC_NEG_INF;
+    ai[nb] = 0x7fffffff; cnt[nb] = 0;
+    r_v0[nb] = REC_NEG_INF; r_v1[nb] = REC_NEG_INF; r_i0[nb] = 0x7fffffff; r_i1[nb] = 0x7fffffff;
+    const int row = b0 + nb * 128 + q * 32 + lane;
+    trow[nb] = (do_stats && target && row < B) ? (int)(target[row] - vocab_lo) : -1;
+  }
 
+  STRACE(20);
   if (n_units > 0) { fetch(0); store(0); }
   if (n_units > 1) fetch(1);
+  STRACE(21);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -148,95 +209,178 @@ __global__ void __launch_bounds__(256, 2) head_stats_tc_kernel(TcHeadPtrs hp, co
   if (n_units > 0 && tid == 0) issue_unit(0);
 
   for (int u = 0; u < n_units; ++u) {
+    STRACE(1);
     if (u + 1 < n_units) {
       if (u >= 1) tc::mbar_wait(&mbar[(u + 1) & 1], ((u - 1) >> 1) & 1);  // MMA(u-1) done: its smem stage is free
+      STRACE(2);
       store(u + 1);
+      STRACE(3);
       if (u + 2 < n_units) fetch(u + 2);  // lands while this step's barrier / MMA wait / epilogue run
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    STRACE(4);
     if (u + 1 < n_units && tid == 0) issue_unit(u + 1);
+    STRACE(5);
     const int g = u / upg;
     if (u - g * upg != upg - 1) continue;  // accumulate the remaining heads of this group first
     tc::mbar_wait(&mbar[u & 1], (u >> 1) & 1);
     tc::tc_fence_after();
-    // ---- epilogue of group g: two chunks of 32 columns ----
+    STRACE(6);
+    // ---- epilogue of group g: NB blocks x CW columns in chunks of 32 ----
     const int v0 = (t_lo + g) * 128;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int c_lo = v0 + ch * 64 + half * 32;
-      float l[32];
-      tc::tmem_ld32(tmem_base_s + ((uint32_t)(q * 32) << 16) + (uint32_t)((g & 1) * 128 + ch * 64 + half * 32), l);
-      tc::tmem_ld_wait();
-      const float *bg = bias_g + (g % 3) * 128 + ch * 64 + half * 32;
+      for (int half = 0; half < CW / 32; ++half) {
+        const int c_lo = v0 + cq * CW + half * 32;
+        float l[32];
+        tc::tmem_ld32(tmem_base_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(((g & 1) * NB + nb) * 128 + cq * CW + half * 32), l);
+        const float *bgp = bias_g + (g % 3) * 128 + cq * CW + half * 32;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b4 = *reinterpret_cast<const float4 *>(bg + j);
-        l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
-      }
-      if (c_lo + 32 > Vloc) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
-      }
-      if (do_stats) {
-        float tmax = REC_NEG_INF;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
-        const float nm = fmaxf(m_run, tmax);
-        float ps = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ps += __expf(l[j] - nm);
-        s_run = s_run * __expf(m_run - nm) + ps;
-        m_run = nm;
-        if (trow >= c_lo && trow < c_lo + 32) {
-          const int tj = trow - c_lo;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j == tj) tgt = l[j];
+        for (int j = 0; j < 32; j += 4) {
+          float4 b4 = *reinterpret_cast<const float4 *>(bgp + j);
+          l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
         }
-      }
-      if (topk > 0) {
+        if (c_lo + 32 > Vloc) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = l[j];
-          if (v > tau) {
-            int p = cnt < topk ? cnt : topk - 1;
-            while (p > 0 && tv[(p - 1) * 256 + tid] < v) {
-              tv[p * 256 + tid] = tv[(p - 1) * 256 + tid];
-              ti[p * 256 + tid] = ti[(p - 1) * 256 + tid];
-              --p;
-            }
-            tv[p * 256 + tid] = v;
-            ti[p * 256 + tid] = vocab_lo + c_lo + j;
-            if (cnt < topk) ++cnt;
-            tau = cnt == topk ? tv[(topk - 1) * 256 + tid] : REC_NEG_INF;
+          for (int j = 0; j < 32; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
+        }
+        if (do_stats) {
+          float tmax = REC_NEG_INF;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
+          const float nm = fmaxf(m_run[nb], tmax);
+          float ps = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ps += __expf(l[j] - nm);
+          s_run[nb] = s_run[nb] * __expf(m_run[nb] - nm) + ps;
+          m_run[nb] = nm;
+          if (trow[nb] >= c_lo && trow[nb] < c_lo + 32) {
+            const int tj = trow[nb] - c_lo;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j == tj) tgt[nb] = l[j];
           }
         }
-      }
-      if (argmode) {
+        if (topk > 0) {
+          // fast path: nothing in this chunk beats the current k-th best (one compare against the chunk max);
+          // the insertion code exists once, out of line, and walks the chunk from local memory
+          float cmax = l[0];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (l[j] > av) { av = l[j]; ai = vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, l[j]);
+          if (smallk) {
+            if (cmax > tau[nb]) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = l[j];
+                const int id = vocab_lo + c_lo + j;
+                const bool g0 = v > r_v0[nb], g1 = v > r_v1[nb];
+                r_v1[nb] = g0 ? r_v0[nb] : (g1 ? v : r_v1[nb]);
+                r_i1[nb] = g0 ? r_i0[nb] : (g1 ? id : r_i1[nb]);
+                r_v0[nb] = g0 ? v : r_v0[nb];
+                r_i0[nb] = g0 ? id : r_i0[nb];
+              }
+              tau[nb] = topk == 1 ? r_v0[nb] : r_v1[nb];
+            }
+          } else if (cmax > tau[nb]) {
+            float lbuf[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lbuf[j] = l[j];
+            topk_insert_chunk(lbuf, tv + (size_t)nb * topk * NT + tid, ti + (size_t)nb * topk * NT + tid, NT, topk,
+                              vocab_lo + c_lo, cnt[nb], tau[nb]);
+          }
+        }
+        if (argmode) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (l[j] > av[nb]) { av[nb] = l[j]; ai[nb] = vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+        }
       }
     }
   }
 
-  // publish: record (sp*2 + ch) of this row
-  if (row < B) {
-    float *o = part + ((int64_t)(sp * 2 + ch) * B + row) * part_stride;
-    o[0] = m_run; o[1] = s_run; o[2] = tgt; o[3] = av; o[4] = __int_as_float(ai);
-    for (int k = 0; k < topk; ++k) {
-      o[PART_TOPK_OFF + k] = k < cnt ? tv[k * 256 + tid] : REC_NEG_INF;
-      o[PART_TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(k < cnt ? ti[k * 256 + tid] : 0x7fffffff);
+  STRACE(30);
+  // ---- combine the CS column splits of every row inside the CTA, then publish ONE record per row ----
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    float *x = xch + ((nb * 128 + q * 32 + lane) * CS + cq) * 5;
+    x[0] = m_run[nb]; x[1] = s_run[nb]; x[2] = tgt[nb]; x[3] = av[nb]; x[4] = __int_as_float(ai[nb]);
+    if (topk > 0) {  // pad the private list so that the merge below can read topk entries
+      float *lv = tv + (size_t)nb * topk * NT + tid;
+      int *li = ti + (size_t)nb * topk * NT + tid;
+      if (smallk) {
+        lv[0] = r_v0[nb]; li[0] = r_i0[nb];
+        if (topk > 1) { lv[NT] = r_v1[nb]; li[NT] = r_i1[nb]; }
+      } else {
+        for (int k = cnt[nb]; k < topk; ++k) { lv[k * NT] = REC_NEG_INF; li[k * NT] = 0x7fffffff; }
+      }
     }
   }
+  __syncthreads();
+  if (cq == 0) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const int r = q * 32 + lane, row = b0 + nb * 128 + r;
+      if (row >= B) continue;
+      const float *x = xch + ((nb * 128 + r) * CS) * 5;
+      float m = REC_NEG_INF, tg = REC_NEG_INF, bv = REC_NEG_INF;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) {
+        m = fmaxf(m, x[c * 5]);
+        tg = fmaxf(tg, x[c * 5 + 2]);
+        const float v = x[c * 5 + 3];
+        const int i = __float_as_int(x[c * 5 + 4]);
+        if (better(v, i, bv, bi)) { bv = v; bi = i; }
+      }
+      float ssum = 0.f;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) if (x[c * 5 + 1] > 0.f) ssum += x[c * 5 + 1] * __expf(x[c * 5] - m);
+      float *o = part + ((int64_t)sp * B + row) * part_stride;
+      o[0] = m; o[1] = ssum; o[2] = tg; o[3] = bv; o[4] = __int_as_float(bi);
+      if (topk > 0) {
+        // CS-way merge of the sorted private lists (ids of different splits are disjoint)
+        int pos[CS];
+#pragma unroll
+        for (int c = 0; c < CS; ++c) pos[c] = 0;
+        for (int k = 0; k < topk; ++k) {
+          float cv = REC_NEG_INF;
+          int ci = 0x7fffffff, cc = 0;
+#pragma unroll
+          for (int c = 0; c < CS; ++c) {
+            if (pos[c] < topk) {
+              const int t2 = (c * 4 + q) * 32 + lane;  // thread id of (q, cq = c, lane)
+              const float v = tv[((size_t)nb * topk + pos[c]) * NT + t2];
+              const int i = ti[((size_t)nb * topk + pos[c]) * NT + t2];
+              if (better(v, i, cv, ci)) { cv = v; ci = i; cc = c; }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CS; ++c) if (c == cc) ++pos[c];
+          o[PART_TOPK_OFF + k] = cv;
+          o[PART_TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(ci);
+        }
+      }
+    }
+  }
+  STRACE(31);
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 256);
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, NB * 256);
 }
 
 // ------------------------------------------------------------------------------------------------
+#include <stdlib.h>
+// debug: REC_TRACE_SEL=1 routes the phase trace (rec_debug_set_trace) to the statistics kernel instead of the
+// backward kernel
+static int trace_sel() {
+  static int sel = -1;
+  if (sel < 0) { const char *v = getenv("REC_TRACE_SEL"); sel = v ? atoi(v) : 0; }
+  return sel;
+}
+
 static TcHeadPtrs tc_head_ptrs(const rec_engine *e, int net_id) {
   TcHeadPtrs hp;
   for (int i = 0; i < REC_MAX_HEADS; ++i) { hp.w[i] = e->nets[net_id].p.head_w[i]; hp.b[i] = e->nets[net_id].p.head_b[i]; }
@@ -246,30 +390,40 @@ static TcHeadPtrs tc_head_ptrs(const rec_engine *e, int net_id) {
 bool tc_heads_supported(const rec_engine *e) { return e->D == 64 && e->use_tc; }
 
 // Same contract as launch_head_stats (heads.cu); *n_split_out counts RECORDS per row (2 per CTA column).
-int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
-  const int n_tiles = cdiv(e->Vloc, 128), nb = cdiv(a.B, 128);
-  const size_t smem_need = 1024 + 6 * (size_t)BLK + 1536 + (size_t)a.topk * 256 * 8;
-  const int ctas_per_sm = smem_need <= 110 * 1024 ? 2 : 1;
-  int n_split = cdiv(ctas_per_sm * e->sm_count, nb);
+template <int NB, int NT>
+static int launch_stats_tc_variant(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
+  const int n_tiles = cdiv(e->Vloc, 128), ng = cdiv(a.B, 128 * NB);
+  int n_split = e->sm_count / ng;  // one CTA per SM, a single wave
   if (n_split > n_tiles) n_split = n_tiles;
   if (n_split < 1) n_split = 1;
   int per = cdiv(n_tiles, n_split);
   n_split = cdiv(n_tiles, per);
-  const size_t smem = 1024 + 6 * (size_t)BLK + 1536 + (size_t)a.topk * 256 * 8;
+  const bool arg = a.n_arg > 0;
+  const int topk = arg ? 0 : a.topk;
+  const size_t smem = 1024 + (size_t)(NB * 2 + 4) * BLK + 1536 + (size_t)NB * 128 * (NT / 128) * 5 * 4 + (size_t)NB * topk * NT * 8;
+  if (smem > 227 * 1024) REC_FAIL(e, REC_EINVAL, "head statistics kernel needs %zu B of shared memory (top-k %d)", smem, topk);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    REC_CUDA(e, cudaFuncSetAttribute(head_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    REC_CUDA(e, cudaFuncSetAttribute(head_stats_tc_kernel<NB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  dim3 grid(n_split, nb);
-  const bool arg = a.n_arg > 0;
-  head_stats_tc_kernel<<<grid, 256, smem, e->stream>>>(tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo, n_tiles,
-                                                      arg ? 0 : a.do_stats, arg ? 1 : a.stats_head, arg ? a.n_arg : 1,
-                                                      a.w[0], a.w[1], a.w[2], a.target, arg ? 0 : a.topk, e->part,
-                                                      e->part_stride);
+  dim3 grid(n_split, ng);
+  head_stats_tc_kernel<NB, NT><<<grid, NT, smem, e->stream>>>(tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo,
+                                                             n_tiles, arg ? 0 : a.do_stats, arg ? 1 : a.stats_head,
+                                                             arg ? a.n_arg : 1, a.w[0], a.w[1], a.w[2], a.target, topk,
+                                                             e->part, e->part_stride, trace_sel() == 1 ? e->trace : nullptr);
   REC_LAUNCH_CHECK(e);
-  *n_split_out = 2 * n_split;
+  *n_split_out = n_split;
   return REC_OK;
+}
+
+// Same contract as launch_head_stats (heads.cu); *n_split_out = records per row.
+int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
+  const int topk = a.n_arg > 0 ? 0 : a.topk;
+  if (a.B <= 128) return launch_stats_tc_variant<1, 512>(e, a, n_split_out);
+  if (topk <= 8) return launch_stats_tc_variant<2, 512>(e, a, n_split_out);   // training: 16 warps, 32 columns/thread
+  if (topk <= 20) return launch_stats_tc_variant<2, 256>(e, a, n_split_out);  // evaluation: top-k lists dominate smem
+  return launch_stats_tc_variant<1, 256>(e, a, n_split_out);
 }
 
 // ================================================================================================
@@ -649,7 +803,7 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   REC_LAUNCH_CHECK(e);
   head_bwd_adam_tc_kernel<<<n_cta, BWD_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles,
                                                           inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size,
-                                                          1.f / bc2_sqrt, e->trace);
+                                                          1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr);
   REC_LAUNCH_CHECK(e);
   *n_slices = n_cta;
   return REC_OK;

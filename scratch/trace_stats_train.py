@@ -1,0 +1,25 @@
+import sys, torch, ctypes
+sys.path.insert(0, '/root/repo')
+import b200pkg; pkg = b200pkg.load()
+import bench
+wl = bench.WORKLOADS['cfg2']
+batches, unpop, e_div = bench._make_data(wl, 8)
+dev = torch.device('cuda:0')
+t = pkg.SMORL_trainer(device=dev, **bench._trainer_kwargs(wl, e_div, unpop)); t.send_to_device()
+db = [tuple(x.to(dev) for x in b) for b in batches]
+for i in range(4): t.train_step_async(*db[i])
+torch.cuda.synchronize()
+buf = torch.zeros(240, dtype=torch.int64, device=dev)
+eng = t._engine
+eng.lib.rec_debug_set_trace(eng.handle, ctypes.c_void_p(buf.data_ptr()))
+t.train_step_async(*db[5]); torch.cuda.synchronize()
+eng.lib.rec_debug_set_trace(eng.handle, None)
+v = buf.cpu().tolist()
+prev = None
+for i in range(0, 240, 2):
+    tag, clk = v[i], v[i+1]
+    if tag == 0: break
+    if tag in (1, 19): print()
+    print(tag, clk - (prev if prev else clk), end=" | ")
+    prev = clk
+print()
