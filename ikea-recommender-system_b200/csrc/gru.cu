@@ -530,23 +530,34 @@ struct GruAdamPtrs {
   float *wiT[2], *whT[2];
 };
 
-// One thread per GRU parameter: reduce the split partials in order, Adam, refresh transposes.
-__global__ void gru_adam_kernel(GruAdamPtrs q, const float *__restrict__ part, int splits, int dirs, int E,
-                                int H, int KS, float b1, float b2, float eps, float step_size,
-                                float bc2_sqrt) {
+// 64 GRU parameters per block x 4 split groups: partials are summed in a fixed order (group g takes splits
+// g, g+4, ...; groups are combined in order), then Adam + refresh of the transposed copies.
+__global__ void __launch_bounds__(256) gru_adam_kernel(GruAdamPtrs q, const float *__restrict__ part, int splits, int dirs,
+                                                       int E, int H, int KS, float b1, float b2, float eps,
+                                                       float step_size, float bc2_sqrt) {
+  __shared__ float sh[4][64];
   const int G = 3 * H;
   const int per_dir = G * E + G * H + 2 * G;
-  int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= per_dir * dirs) return;
-  int dir = gid / per_dir, o = gid - dir * per_dir;
-  int which, j, k, t;
-  if (o < G * E) { t = 0; which = 0; j = o / E; k = o - j * E; }
-  else if (o < G * E + G * H) { o -= G * E; t = 1; which = 1; j = o / H; k = o - j * H; }
-  else if (o < G * E + G * H + G) { o -= G * E + G * H; t = 2; which = 0; j = o; k = KS - 1; }
-  else { o -= G * E + G * H + G; t = 3; which = 1; j = o; k = KS - 1; }
-  float g = 0.f;
-  for (int sidx = 0; sidx < splits; ++sidx)
-    g += part[((((int64_t)sidx * dirs + dir) * 2 + which) * G + j) * KS + k];
+  const int o = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int gid = blockIdx.x * 64 + o;
+  const bool valid = gid < per_dir * dirs;
+  int dir = 0, which = 0, j = 0, k = 0, t = 0;
+  if (valid) {
+    dir = gid / per_dir;
+    int oo = gid - dir * per_dir;
+    if (oo < G * E) { t = 0; which = 0; j = oo / E; k = oo - j * E; }
+    else if (oo < G * E + G * H) { oo -= G * E; t = 1; which = 1; j = oo / H; k = oo - j * H; }
+    else if (oo < G * E + G * H + G) { oo -= G * E + G * H; t = 2; which = 0; j = oo; k = KS - 1; }
+    else { oo -= G * E + G * H + G; t = 3; which = 1; j = oo; k = KS - 1; }
+  }
+  float acc = 0.f;
+  if (valid)
+    for (int sidx = grp; sidx < splits; sidx += 4)
+      acc += part[((((int64_t)sidx * dirs + dir) * 2 + which) * G + j) * KS + k];
+  sh[grp][o] = acc;
+  __syncthreads();
+  if (grp != 0 || !valid) return;
+  const float g = ((sh[0][o] + sh[1][o]) + sh[2][o]) + sh[3][o];
   int64_t off = (t == 0) ? (int64_t)j * E + k : (t == 1) ? (int64_t)j * H + k : j;
   float p = q.p[dir][t][off], m = q.m[dir][t][off], v = q.v[dir][t][off];
   adam_update(p, m, v, g, b1, b2, eps, step_size, bc2_sqrt);
@@ -686,7 +697,7 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
     q.wiT[d] = nb.w_ihT[d]; q.whT[d] = nb.w_hhT[d];
   }
   int total = (G * E + G * H + 2 * G) * e->dirs;
-  gru_adam_kernel<<<cdiv(total, 256), 256, 0, e->stream>>>(q, e->wgrad_part, splits, e->dirs, E, H, KS, hp->beta1,
+  gru_adam_kernel<<<cdiv(total, 64), 256, 0, e->stream>>>(q, e->wgrad_part, splits, e->dirs, E, H, KS, hp->beta1,
                                                           hp->beta2, hp->eps, step_size, bc2_sqrt);
   REC_LAUNCH_CHECK(e);
   return REC_OK;

@@ -586,13 +586,19 @@ __global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, co
     for (int64_t i = tid; i < (int64_t)B * D; i += 256) dh_slice[i] = 0.f;
 }
 
-// dh[b,d] = sum over slices (fixed order)
-__global__ void dh_reduce_kernel(const float *__restrict__ dh_part, int n_slices, int64_t n, float *__restrict__ dh) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// dh[i] = sum over slices in a FIXED order: 4 slice groups per output run in parallel (group g takes slices
+// g, g+4, ...), then the 4 partial sums are added in group order.  block = 256 threads = 64 outputs x 4 groups.
+__global__ void __launch_bounds__(256) dh_reduce_kernel(const float *__restrict__ dh_part, int n_slices, int64_t n,
+                                                        float *__restrict__ dh) {
+  __shared__ float sh[4][64];
+  const int o = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * 64 + o;
   float acc = 0.f;
-  for (int s = 0; s < n_slices; ++s) acc += dh_part[(int64_t)s * n + i];
-  dh[i] = acc;
+  if (i < n)
+    for (int s = g; s < n_slices; s += 4) acc += dh_part[(int64_t)s * n + i];
+  sh[g][o] = acc;
+  __syncthreads();
+  if (g == 0 && i < n) dh[i] = ((sh[0][o] + sh[1][o]) + sh[2][o]) + sh[3][o];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -700,7 +706,7 @@ int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const r
     if (e->timing) cudaEventRecord(e->ev[7], e->stream);
   }
   int64_t n = (int64_t)B * e->D;
-  dh_reduce_kernel<<<(int)cdiv64(n, 256), 256, 0, e->stream>>>(e->dh_part, n_dense_slices + (n_q > 0 ? 1 : 0), n, e->dh);
+  dh_reduce_kernel<<<(int)cdiv64(n, 64), 256, 0, e->stream>>>(e->dh_part, n_dense_slices + (n_q > 0 ? 1 : 0), n, e->dh);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
 }
