@@ -81,6 +81,9 @@ SYMBOLS = {
     "rec_train_phase_b": (C.c_int, [_P, _P, C.c_int, _P]),
     "rec_train_phase_c": (C.c_int, [_P, _P, _P, _P]),
     "rec_train_phase_d": (C.c_int, [_P, _P]),
+    "rec_packed_batch_bytes": (C.c_int64, [_P, C.c_int]),
+    "rec_pack_batch": (C.c_int, [_P, C.POINTER(RecBatch), _P]),
+    "rec_unpack_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(RecBatch)]),
     "rec_eval_batch": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.POINTER(RecEvalOpts),
                                  C.POINTER(RecEvalAccum), _P, _P]),
     "rec_eval_shard_candidates": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.c_int, C.c_int, _P]),

@@ -11,6 +11,8 @@ int launch_loss_reduce(rec_engine *e, int B, const float *q_loss_rows, float *ou
 int launch_eval_metrics(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, int kmax,
                         const rec_eval_accum *acc, double *rowm, int32_t *topk_ids, float *topk_scores);
 size_t head_bwd_smem_bytes(int D);
+int launch_pack_batch(rec_engine *e, const rec_batch *b, uint8_t *out);
+int launch_unpack_batch(rec_engine *e, const uint8_t *gathered, int G, int Bl, size_t stride, const rec_batch *out);
 
 static char g_err[512] = "";
 
@@ -102,6 +104,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->emb_keys, int32_t, mb * L);
   ALLOC(e, e->emb_slot, int32_t, (int64_t)c.item_num + 1);
   ALLOC(e, e->emb_grad_rows, float, mb * L * E);
+  ALLOC(e, e->emb_leader, uint8_t, mb * L);
   e->part_stride = 72;
   e->n_split_max = 2 * e->sm_count;
   ALLOC(e, e->part, float, ((int64_t)e->sm_count * 4 * 128 + 4 * mb) * e->part_stride);
@@ -148,7 +151,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
@@ -486,4 +489,23 @@ extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_
   if (kmax > e->cfg.max_topk) REC_FAIL(e, REC_EINVAL, "rec_eval_merge: k=%d exceeds max_topk=%d", kmax, e->cfg.max_topk);
   if ((rc = launch_head_merge(e, gathered, n_shards, b->B, kmax, true, false, nullptr))) return rc;
   return launch_eval_metrics(e, b, o, kmax, acc, extra(e).rowm, topk_ids, topk_scores);
+}
+
+// ---- packed batches for the input all-gather of sharded runs ----------------------------------------------
+extern "C" int64_t rec_packed_batch_bytes(const rec_engine *e, int B) {
+  if (!e || B < 1) return -1;
+  int64_t n = (int64_t)B * (2 * e->cfg.state_size + 3) * 8 + (int64_t)B * 5;
+  return (n + 15) / 16 * 16;
+}
+extern "C" int rec_pack_batch(rec_engine *e, const rec_batch *b, void *packed_out) {
+  if (!e) return REC_EINVAL;
+  if (!b || !packed_out || !b->s || !b->a || !b->true_len || b->B < 1) REC_FAIL(e, REC_EINVAL, "rec_pack_batch: bad argument");
+  return launch_pack_batch(e, b, (uint8_t *)packed_out);
+}
+extern "C" int rec_unpack_batch(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *out) {
+  if (!e) return REC_EINVAL;
+  if (!gathered || n_ranks < 1 || B_local < 1 || !out || !out->s || !out->s_next || !out->a || !out->true_len ||
+      !out->true_next_len || !out->r || !out->is_end)
+    REC_FAIL(e, REC_EINVAL, "rec_unpack_batch: bad argument");
+  return launch_unpack_batch(e, (const uint8_t *)gathered, n_ranks, B_local, (size_t)rec_packed_batch_bytes(e, B_local), out);
 }

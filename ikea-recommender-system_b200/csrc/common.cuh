@@ -40,6 +40,7 @@ struct rec_engine {
   int32_t *emb_keys;     // [maxB*L] row id or -1
   int32_t *emb_slot;     // [N+1] slot of the leader position or -1
   float *emb_grad_rows;  // [maxB*L, E]
+  uint8_t *emb_leader;   // [maxB*L] chunk-leader flags (batches spanning several dedup chunks)
   // head statistics partials: [n_split][maxB][PART_STRIDE]
   float *part;
   int part_stride, n_split_max;

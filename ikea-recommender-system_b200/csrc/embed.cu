@@ -22,10 +22,21 @@ __global__ void emb_keys_kernel(const int64_t *__restrict__ s, const int64_t *__
 }
 
 // One warp per position.  keys are staged in shared memory when they fit.
-__global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restrict__ keys, int P, int E, int dirs,
+// Positions are processed in chunks of `chunk` (a multiple of 8): duplicates are combined inside a chunk here;
+// when the batch spans several chunks (large / multi-GPU global batches) emb_chunk_merge_kernel then folds
+// the chunk leaders together in chunk order, which keeps the whole reduction O(P * chunk) and deterministic.
+__global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restrict__ keys_all, int P_all, int E, int dirs,
                                                           const float *__restrict__ dx,
                                                           float *__restrict__ grad_rows,
-                                                          int32_t *__restrict__ slot_of_row, int use_smem) {
+                                                          int32_t *__restrict__ slot_of_row, int use_smem, int chunk,
+                                                          uint8_t *__restrict__ leader_flag) {
+  const int warps_per_chunk_blocks = chunk >> 3;                   // CTAs per chunk (8 warps = 8 positions per CTA)
+  const int cidx = blockIdx.x / warps_per_chunk_blocks;            // chunk of this CTA
+  const int c0 = cidx * chunk;
+  const int P = min(chunk, P_all - c0);                            // positions of this chunk
+  const int32_t *keys = keys_all + c0;
+  dx += (int64_t)c0 * dirs * E;
+  grad_rows += (int64_t)c0 * E;
   extern __shared__ int32_t skeys[];
   constexpr int LISTCAP = 160;
   __shared__ int plist[8][LISTCAP];
@@ -36,7 +47,7 @@ __global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restr
     __syncthreads();
     kp = skeys;
   }
-  const int p = blockIdx.x * (blockDim.x >> 5) + wid;
+  const int p = (blockIdx.x - cidx * warps_per_chunk_blocks) * (blockDim.x >> 5) + wid;  // position inside the chunk
   if (p >= P) return;
   const int row = kp[p];
   if (row < 0) return;
@@ -116,7 +127,28 @@ __global__ void __launch_bounds__(256) emb_segment_kernel(const int32_t *__restr
       if (col < Ec) grad_rows[(int64_t)p * E + e0 + col] = acc[c];
     }
   }
-  if (lane == 0) slot_of_row[row] = p;
+  if (lane == 0) {
+    if (leader_flag) leader_flag[c0 + p] = 1;   // several chunks: published by the merge pass
+    else slot_of_row[row] = p;
+  }
+}
+
+// Fold the leaders of chunk `cidx` into the global slot map: the first chunk that sees a row owns its
+// accumulator, later chunks add their partial row to it.  Rows are unique inside a chunk, so no two warps of
+// one launch touch the same accumulator; chunks are launched in order => fixed summation order.
+__global__ void __launch_bounds__(256) emb_chunk_merge_kernel(const int32_t *__restrict__ keys, const uint8_t *__restrict__ leader_flag,
+                                                              int c0, int c1, int E, float *__restrict__ grad_rows,
+                                                              int32_t *__restrict__ slot_of_row) {
+  const int lane = threadIdx.x & 31;
+  const int p = c0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= c1 || !leader_flag[p]) return;
+  const int row = keys[p];
+  const int prev = slot_of_row[row];
+  if (prev < 0) {
+    if (lane == 0) slot_of_row[row] = p;
+    return;
+  }
+  for (int c = lane; c < E; c += 32) grad_rows[(int64_t)prev * E + c] += grad_rows[(int64_t)p * E + c];
 }
 
 __device__ __forceinline__ void adam_update4(float4 &p, float4 &m, float4 &v, const float4 g, float b1, float b2,
@@ -338,16 +370,26 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
   emb_keys_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(s, lengths, B, L, c.item_num, c.use_packed_seq,
                                                       c.frozen_pad_row, e->emb_keys);
   REC_LAUNCH_CHECK(e);
-  int use_smem = (size_t)P * sizeof(int32_t) <= 96 * 1024;
-  size_t smem = use_smem ? (size_t)P * sizeof(int32_t) : 0;
+  const int chunk = 4096;
+  const int n_chunks = cdiv(P, chunk);
+  const int span = n_chunks > 1 ? chunk : P;
+  int use_smem = 1;
+  size_t smem = (size_t)span * sizeof(int32_t);
   static bool attr_set = false;
   if (!attr_set) {
     REC_CUDA(e, cudaFuncSetAttribute(emb_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  emb_segment_kernel<<<cdiv(P, 8), 256, smem, e->stream>>>(e->emb_keys, P, E, e->dirs, e->dx, e->emb_grad_rows,
-                                                          e->emb_slot, use_smem);
+  uint8_t *flags = n_chunks > 1 ? e->emb_leader : nullptr;
+  if (flags) REC_CUDA(e, cudaMemsetAsync(flags, 0, (size_t)P, e->stream));
+  emb_segment_kernel<<<n_chunks > 1 ? n_chunks * (chunk / 8) : cdiv(P, 8), 256, smem, e->stream>>>(
+      e->emb_keys, P, E, e->dirs, e->dx, e->emb_grad_rows, e->emb_slot, use_smem, n_chunks > 1 ? chunk : ((P + 7) / 8) * 8, flags);
   REC_LAUNCH_CHECK(e);
+  for (int c = 0; c < n_chunks && n_chunks > 1; ++c) {
+    const int c0 = c * chunk, c1 = c0 + chunk < P ? c0 + chunk : P;
+    emb_chunk_merge_kernel<<<cdiv(c1 - c0, 8), 256, 0, e->stream>>>(e->emb_keys, flags, c0, c1, E, e->emb_grad_rows, e->emb_slot);
+    REC_LAUNCH_CHECK(e);
+  }
   if (e->timing) cudaEventRecord(e->ev[4], e->stream);
   {
     int rc = launch_adam_stream(e, nb.p.emb, nb.p.emb_m, nb.p.emb_v, (int64_t)c.item_num + 1, E, e->emb_slot,

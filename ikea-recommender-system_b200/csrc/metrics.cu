@@ -228,3 +228,59 @@ int launch_eval_metrics(rec_engine *e, const rec_batch *b, const rec_eval_opts *
   }
   return REC_OK;
 }
+
+// ---- multi-GPU plumbing: packed batch <-> field arrays -------------------------------------------------
+// Packed layout of one rank's batch (bytes): int64 s[B,L] | s_next[B,L] | a[B] | true_len[B] | true_next_len[B]
+// | float r[B] | uint8 is_end[B], padded to 16.  One all-gather of this buffer replaces seven.
+__global__ void pack_batch_kernel(rec_batch b, int L, uint8_t *__restrict__ out) {
+  const int B = b.B;
+  int64_t *o64 = reinterpret_cast<int64_t *>(out);
+  const int n64 = B * (2 * L + 3);
+  float *of = reinterpret_cast<float *>(out + (size_t)n64 * 8);
+  uint8_t *oe = out + (size_t)n64 * 8 + (size_t)B * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n64 + 2 * B; i += gridDim.x * blockDim.x) {
+    if (i < B * L) o64[i] = b.s[i];
+    else if (i < 2 * B * L) o64[i] = b.s_next ? b.s_next[i - B * L] : 0;
+    else if (i < 2 * B * L + B) o64[i] = b.a[i - 2 * B * L];
+    else if (i < 2 * B * L + 2 * B) o64[i] = b.true_len[i - 2 * B * L - B];
+    else if (i < n64) o64[i] = b.true_next_len ? b.true_next_len[i - 2 * B * L - 2 * B] : 0;
+    else if (i < n64 + B) of[i - n64] = b.r ? b.r[i - n64] : 0.f;
+    else oe[i - n64 - B] = b.is_end ? b.is_end[i - n64 - B] : 0;
+  }
+}
+
+// gathered[G][stride bytes] (each segment in the packed layout with Bl rows) -> field arrays of G*Bl rows
+__global__ void unpack_batch_kernel(const uint8_t *__restrict__ gathered, int G, int Bl, int L, size_t stride,
+                                    int64_t *__restrict__ s, int64_t *__restrict__ s_next, int64_t *__restrict__ a,
+                                    int64_t *__restrict__ ln, int64_t *__restrict__ nl, float *__restrict__ r,
+                                    uint8_t *__restrict__ e) {
+  const int n64 = Bl * (2 * L + 3);
+  const int per = n64 + 2 * Bl;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per * G; i += gridDim.x * blockDim.x) {
+    const int g = i / per, j = i - g * per;
+    const uint8_t *seg = gathered + (size_t)g * stride;
+    const int64_t *i64 = reinterpret_cast<const int64_t *>(seg);
+    if (j < Bl * L) s[(int64_t)g * Bl * L + j] = i64[j];
+    else if (j < 2 * Bl * L) s_next[(int64_t)g * Bl * L + (j - Bl * L)] = i64[j];
+    else if (j < 2 * Bl * L + Bl) a[g * Bl + (j - 2 * Bl * L)] = i64[j];
+    else if (j < 2 * Bl * L + 2 * Bl) ln[g * Bl + (j - 2 * Bl * L - Bl)] = i64[j];
+    else if (j < n64) nl[g * Bl + (j - 2 * Bl * L - 2 * Bl)] = i64[j];
+    else if (j < n64 + Bl) r[g * Bl + (j - n64)] = reinterpret_cast<const float *>(seg + (size_t)n64 * 8)[j - n64];
+    else e[g * Bl + (j - n64 - Bl)] = seg[(size_t)n64 * 8 + (size_t)Bl * 4 + (j - n64 - Bl)];
+  }
+}
+
+int launch_pack_batch(rec_engine *e, const rec_batch *b, uint8_t *out) {
+  const int n = b->B * (2 * e->cfg.state_size + 5);
+  pack_batch_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(*b, e->cfg.state_size, out);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+int launch_unpack_batch(rec_engine *e, const uint8_t *gathered, int G, int Bl, size_t stride, const rec_batch *out) {
+  const int n = G * Bl * (2 * e->cfg.state_size + 5);
+  unpack_batch_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(gathered, G, Bl, e->cfg.state_size, stride, (int64_t *)out->s,
+                                                          (int64_t *)out->s_next, (int64_t *)out->a, (int64_t *)out->true_len,
+                                                          (int64_t *)out->true_next_len, (float *)out->r, (uint8_t *)out->is_end);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}

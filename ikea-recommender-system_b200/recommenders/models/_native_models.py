@@ -26,21 +26,34 @@ def supervised_train_step(trainer, s, a, true_len) -> torch.Tensor:
 
 
 def _sharded_step(trainer, hp, main, s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
-    """Vocabulary-sharded step: all-gather the local batches, then phases A-D with their collectives."""
-    from ...sharded import ShardedStep, pack_rows, unpack_rows, all_gather_rows
+    """Vocabulary-sharded step: ONE all-gather of the packed local batches, then phases A-D with their
+    three collectives (records all-gather, Q all-reduce, dh all-reduce)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from ...sharded import ShardedStep
+    from ... import _native as N
     rank, world, group = trainer._shard
     B = int(s.shape[0])
-    eng = trainer._ready(B * world)
+    Bg = B * world
+    eng = trainer._ready(Bg)
     ds, dsn, da, dln, dnl, dr, de = trainer._stager.stage(s, a, true_len, r, s_next, true_next_len, is_end)
-    rows = all_gather_rows(pack_rows(ds, da, dln, dr, dsn, dnl, de), group)
     L = int(ds.shape[1])
-    gs, ga, gln, gr, gsn, gnl, ge = unpack_rows(rows, L, with_q=r is not None)
-    batch = eng._batch(B * world, gs, ga, gln, gr, gsn, gnl, ge)
-    if getattr(trainer, "_sharded_step", None) is None or trainer._sharded_step.eng is not eng:
+    st = getattr(trainer, "_sharded_step", None)
+    if st is None or st.eng is not eng or st.B_local != B:
         n0 = trainer._nets[0]
-        trainer._sharded_step = ShardedStep(eng, world, group, n0.hidden_dim * (2 if n0._bidirectional else 1))
-    trainer._keep_batch = (gs, ga, gln, gr, gsn, gnl, ge)  # phases read these after this function returns
-    trainer._sharded_step.run(batch, hp, main, trainer._loss_dev, has_q=r is not None)
+        st = trainer._sharded_step = ShardedStep(eng, world, group, n0.hidden_dim * (2 if n0._bidirectional else 1))
+        st.alloc_inputs(B, L, ds.device)
+    local = eng._batch(B, ds, da, dln, dr, dsn, dnl, de)
+    N.check(eng.lib, eng.handle, eng.lib.rec_pack_batch(eng.handle, C.byref(local), C.c_void_p(st.packed.data_ptr())),
+            "rec_pack_batch")
+    dist.all_gather_into_tensor(st.gathered_in, st.packed, group=group)
+    gb = st.global_batch
+    N.check(eng.lib, eng.handle,
+            eng.lib.rec_unpack_batch(eng.handle, C.c_void_p(st.gathered_in.data_ptr()), world, B, C.byref(gb)),
+            "rec_unpack_batch")
+    if r is None:
+        gb = eng._batch(Bg, st.g_s, st.g_a, st.g_ln)
+    st.run(gb, hp, main, trainer._loss_dev, has_q=r is not None)
     return trainer._loss_dev[:2]
 
 

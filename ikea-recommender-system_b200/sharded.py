@@ -69,6 +69,21 @@ class ShardedStep:
         self.eng, self.world, self.group, self.D = engine, world, group, D
         self.rec = engine.record_floats()
         self.cap = 0
+        self.B_local = -1
+
+    def alloc_inputs(self, B_local, L, dev):
+        """Persistent buffers of the input all-gather (packed local batch, gathered bytes, global field arrays)."""
+        self.B_local = B_local
+        Bg = B_local * self.world
+        nbytes = int(self.eng.lib.rec_packed_batch_bytes(self.eng.handle, B_local))
+        self.packed = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.gathered_in = torch.zeros(self.world * nbytes, dtype=torch.uint8, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.g_s, self.g_sn = torch.zeros(Bg, L, **i64), torch.zeros(Bg, L, **i64)
+        self.g_a, self.g_ln, self.g_nl = torch.zeros(Bg, **i64), torch.zeros(Bg, **i64), torch.zeros(Bg, **i64)
+        self.g_r = torch.zeros(Bg, dtype=torch.float32, device=dev)
+        self.g_e = torch.zeros(Bg, dtype=torch.uint8, device=dev)
+        self.global_batch = self.eng._batch(Bg, self.g_s, self.g_a, self.g_ln, self.g_r, self.g_sn, self.g_nl, self.g_e)
 
     def _alloc(self, Bg, dev):
         self.cap = Bg

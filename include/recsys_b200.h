@@ -185,6 +185,13 @@ int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float 
 int rec_train_phase_c(rec_engine *e, const float *q_reduced, float *losses_out, float *dh_out);
 int rec_train_phase_d(rec_engine *e, const float *dh_reduced);
 
+/* Input plumbing of sharded runs: one rank's batch packed into ONE byte buffer (so a single all-gather moves
+ * every field), and the inverse for the gathered [n_ranks][rec_packed_batch_bytes] buffer -> field arrays of
+ * n_ranks*B_local rows (caller-owned; out->B is ignored). */
+int64_t rec_packed_batch_bytes(const rec_engine *e, int B);
+int rec_pack_batch(rec_engine *e, const rec_batch *b, void *packed_out);
+int rec_unpack_batch(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *out);
+
 /* ---- evaluation (replaces evaluate()/update_train_metrics(), eval_protocol.py:123-359) ------ */
 /* One batch: forward, fused top-k (score desc, id asc), CE, and every metric accumulated on the
  * device.  topk_ids[B,kmax] (int32, global action ids) and topk_scores[B,kmax] may be NULL. */
