@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,16 +77,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: bracket the timed region with two marks."""
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
+        rows = self.rows[lo:hi] if hi is not None and len(self.rows[lo:hi]) > 0 else self.rows[lo:] or self.rows
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -192,14 +198,18 @@ def run_native(args, wl):
     trainer.send_to_device()
     trainer.set_train()
     dev_batches = [tuple(t.to(dev) for t in b) for b in batches]
+    clocks = ClockSampler(local)
+    clocks.start()  # started before the warm-up (nvidia-smi needs ~100 ms to emit its first sample)
     for i in range(W):
         trainer.train_step_async(*dev_batches[i % n_b])
     torch.cuda.synchronize()
     eng = trainer._engine
+    while clocks.proc is not None and len(clocks.rows) == 0 and clocks.proc.poll() is None:
+        trainer.train_step_async(*dev_batches[0])  # keep the GPU under load until the sampler is live
+        torch.cuda.synchronize()
 
     # ---- value: device-resident inputs, CUDA events, no host sync inside -------------------------
-    clocks = ClockSampler(local)
-    clocks.start()
+    m0 = clocks.mark()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -210,7 +220,8 @@ def run_native(args, wl):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - l0
-    clk = clocks.stop()
+    m1 = clocks.mark()
+    clk = clocks.stop(m0, max(m1, m0 + 1))
     value = B * K / (ms / 1e3)
 
     # ---- roofline: dominant kernels timed live with CUDA events on the engine's stream ------------

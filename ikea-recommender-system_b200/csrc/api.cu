@@ -1,5 +1,6 @@
 // C ABI (include/recsys_b200.h): engine lifetime, parameter binding, train steps, evaluation.
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include "common.cuh"
 
@@ -119,6 +120,18 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->astar, int32_t, mb);
   ALLOC(e, extra(e).q_loss_rows, float, mb);
   ALLOC(e, e->summary, float, mb * e->part_stride);
+  ALLOC(e, e->d_sc, float, 4);
+  if (cudaMallocHost((void **)&e->h_sc, 4 * sizeof(float)) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMallocHost failed"); rec_destroy(e); return REC_ENOMEM; }
+  {
+    int64_t *p64 = nullptr; float *pf = nullptr; uint8_t *p8 = nullptr;
+    ALLOC(e, p64, int64_t, mb * (2 * L + 3));
+    ALLOC(e, pf, float, mb);
+    ALLOC(e, p8, uint8_t, mb);
+    e->own.s = p64; e->own.s_next = p64 + mb * L; e->own.a = p64 + 2 * mb * L; e->own.true_len = p64 + 2 * mb * L + mb;
+    e->own.true_next_len = p64 + 2 * mb * L + 2 * mb; e->own.r = pf; e->own.is_end = p8;
+  }
+  e->use_graph = getenv("REC_NO_GRAPH") == nullptr;
+  if (cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) e->use_graph = false;
   ALLOC(e, e->hpack, uint8_t, (size_t)((mb + 255) / 256) * 4 * 16384);
   ALLOC(e, e->q_grad_rows, float, mb * 3 * D);
   ALLOC(e, e->q_bgrad, float, mb * 3);
@@ -151,7 +164,8 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->d_sc, (void *)e->own.s,
+                  (void *)e->own.r, (void *)e->own.is_end};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
@@ -159,6 +173,9 @@ extern "C" void rec_destroy(rec_engine *e) {
       if (e->nets[n].w_hhT[d]) cudaFree(e->nets[n].w_hhT[d]);
     }
   for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < e->n_graphs; ++i) if (e->graphs[i].exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graphs[i].exec);
+  if (e->h_sc) cudaFreeHost(e->h_sc);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   free(e);
 }
 
@@ -194,6 +211,11 @@ extern "C" int64_t rec_get_adam_step(const rec_engine *e, int net_id) {
   return e->nets[net_id].adam_step;
 }
 
+extern "C" int rec_set_cuda_graphs(rec_engine *e, int on) {
+  if (!e) return REC_EINVAL;
+  e->use_graph = on != 0;
+  return REC_OK;
+}
 extern "C" int rec_set_tensor_cores(rec_engine *e, int on) {
   if (!e) return REC_EINVAL;
   e->use_tc = on != 0;
@@ -242,14 +264,104 @@ static void adam_scalars(rec_engine *e, int net_id, const rec_train_hparams *hp,
   double bc2 = 1.0 - pow((double)hp->beta2, (double)t);
   *step_size = (float)((double)hp->lr / bc1);
   *bc2_sqrt = (float)sqrt(bc2);
+  // the kernels read the scalars from device memory (so that a captured CUDA graph stays valid across steps)
+  e->h_sc[0] = *step_size;
+  e->h_sc[1] = 1.f / *bc2_sqrt;
 }
 
-extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out) {
-  int rc = check_net(e, 0, true);
-  if (rc) return rc;
-  if ((rc = check_batch(e, b, false))) return rc;
-  if (!hp || !loss_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_supervised: null argument");
-  if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
+static int upload_adam_scalars(rec_engine *e) {
+  REC_CUDA(e, cudaMemcpyAsync(e->d_sc, e->h_sc, 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  return REC_OK;
+}
+
+// ---- CUDA-graph replay of a whole train step --------------------------------------------------------------
+__global__ void copy_batch_kernel(rec_batch src, rec_batch dst, int L) {
+  const int B = src.B;
+  const int n = B * (2 * L + 5);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < B * L) ((int64_t *)dst.s)[i] = src.s[i];
+    else if (i < 2 * B * L) { if (src.s_next) ((int64_t *)dst.s_next)[i - B * L] = src.s_next[i - B * L]; }
+    else if (i < 2 * B * L + B) ((int64_t *)dst.a)[i - 2 * B * L] = src.a[i - 2 * B * L];
+    else if (i < 2 * B * L + 2 * B) ((int64_t *)dst.true_len)[i - 2 * B * L - B] = src.true_len[i - 2 * B * L - B];
+    else if (i < 2 * B * L + 3 * B) { if (src.true_next_len) ((int64_t *)dst.true_next_len)[i - 2 * B * L - 2 * B] = src.true_next_len[i - 2 * B * L - 2 * B]; }
+    else if (i < 2 * B * L + 4 * B) { if (src.r) ((float *)dst.r)[i - 2 * B * L - 3 * B] = src.r[i - 2 * B * L - 3 * B]; }
+    else { if (src.is_end) ((uint8_t *)dst.is_end)[i - 2 * B * L - 4 * B] = src.is_end[i - 2 * B * L - 4 * B]; }
+  }
+}
+
+static uint64_t fnv(uint64_t h, const void *p, size_t n) {
+  const unsigned char *c = (const unsigned char *)p;
+  for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// Runs `body(own_batch)` either directly or as a replay of its captured graph.  Everything that changes from
+// step to step lives in memory (engine-owned batch copy, Adam scalars), so one graph per (kind, main net, B,
+// hyper-parameters, output pointer) serves every later step.
+template <class Body>
+static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_batch *b, const rec_train_hparams *hp,
+                            float *out, Body body) {
+  if (!e->use_graph || e->timing || e->trace) {
+    int rc = upload_adam_scalars(e);
+    return rc ? rc : body(b);
+  }
+  rec_batch own = e->own;
+  own.B = b->B;
+  if (!b->r) { own.r = nullptr; own.s_next = nullptr; own.true_next_len = nullptr; own.is_end = nullptr; }
+  copy_batch_kernel<<<cdiv(b->B * (2 * e->cfg.state_size + 5), 256), 256, 0, e->stream>>>(*b, own, e->cfg.state_size);
+  REC_LAUNCH_CHECK(e);
+  uint64_t key = 1469598103934665603ull;
+  key = fnv(key, &kind, sizeof(kind)); key = fnv(key, &main_net, sizeof(main_net)); key = fnv(key, &b->B, sizeof(int));
+  key = fnv(key, hp, sizeof(*hp)); key = fnv(key, &out, sizeof(out));
+  for (int n = 0; n < e->cfg.n_nets; ++n) key = fnv(key, &e->nets[n].p, sizeof(rec_net_params));
+  rec_engine::GraphEntry *g = nullptr;
+  for (int i = 0; i < e->n_graphs; ++i) if (e->graphs[i].key == key) g = &e->graphs[i];
+  if (!g) {
+    if (e->n_graphs == 16) {  // recycle the oldest entry
+      if (e->graphs[0].exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graphs[0].exec);
+      for (int i = 1; i < 16; ++i) e->graphs[i - 1] = e->graphs[i];
+      e->n_graphs = 15;
+    }
+    g = &e->graphs[e->n_graphs++];
+    g->key = key; g->exec = nullptr; g->launches = 0; g->seen = 0;
+  }
+  if (!g->exec && g->seen < 1) {  // first sighting: run eagerly (also sets kernel attributes outside any capture)
+    g->seen++;
+    int rc = upload_adam_scalars(e);
+    return rc ? rc : body(&own);
+  }
+  if (!g->exec) {
+    const int64_t l0 = e->launches;
+    cudaGraph_t graph = nullptr;
+    // capture on the private stream (nothing executes); the instantiated graph is replayed on the caller's stream
+    cudaStream_t user_stream = e->stream;
+    REC_CUDA(e, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    e->stream = e->cap_stream;
+    int rc = upload_adam_scalars(e);
+    if (!rc) rc = body(&own);
+    cudaError_t st = cudaStreamEndCapture(e->cap_stream, &graph);
+    e->stream = user_stream;
+    if (rc || st != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      if (!rc) REC_FAIL(e, REC_ECUDA, "CUDA graph capture failed: %s", cudaGetErrorString(st));
+      return rc;
+    }
+    cudaGraphExec_t exec = nullptr;
+    st = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (st != cudaSuccess) REC_FAIL(e, REC_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(st));
+    g->exec = exec;
+    g->launches = (int)(e->launches - l0);
+    e->launches = l0;  // nothing ran during capture
+  }
+  REC_CUDA(e, cudaGraphLaunch((cudaGraphExec_t)g->exec, e->stream));
+  e->launches += g->launches;
+  return REC_OK;
+}
+
+static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out,
+                           float step_size, float bc2_sqrt) {
+  int rc;
   const int B = b->B;
   if ((rc = launch_gru_forward(e, 0, b->s, b->true_len, B, e->h_state[0], true))) return rc;
   HeadStatsArgs a = {};
@@ -259,29 +371,28 @@ extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, cons
   if ((rc = launch_head_merge(e, e->part, n_split, B, 0, true, false))) return rc;
   if ((rc = launch_loss_reduce(e, B, nullptr, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(loss_out, e->loss_buf, sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
-  float step_size, bc2_sqrt;
-  adam_scalars(e, 0, hp, &step_size, &bc2_sqrt);
   if ((rc = launch_head_backward_adam(e, 0, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
   if ((rc = launch_gru_backward(e, 0, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp))) return rc;
   return launch_embedding_update(e, 0, b->s, b->true_len, B, step_size, bc2_sqrt, hp);
 }
 
-extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out) {
-  if (!e) return REC_EINVAL;
-  if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q needs a twin-net engine with Q heads");
-  if (main_net != 0 && main_net != 1) REC_FAIL(e, REC_EINVAL, "main_net must be 0 or 1");
-  int rc = check_net(e, main_net, true);
+extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out) {
+  int rc = check_net(e, 0, true);
   if (rc) return rc;
-  if ((rc = check_net(e, 1 - main_net, false))) return rc;
-  if ((rc = check_batch(e, b, true))) return rc;
-  if (!hp || !losses_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_q: null argument");
+  if ((rc = check_batch(e, b, false))) return rc;
+  if (!hp || !loss_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_supervised: null argument");
   if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
+  float step_size, bc2_sqrt;
+  adam_scalars(e, 0, hp, &step_size, &bc2_sqrt);
+  return run_step_graphed(e, 0, 0, b, hp, loss_out, [&](const rec_batch *bb) {
+    return supervised_body(e, bb, hp, loss_out, step_size, bc2_sqrt);
+  });
+}
+
+static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out,
+                       float step_size, float bc2_sqrt) {
+  int rc;
   const int B = b->B, boot = 1 - main_net, n_q = e->cfg.n_heads - 1;
-  if (n_q == 3) {
-    if (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 || hp->div_dim < 1 ||
-        hp->topk_div > e->cfg.max_topk || hp->topk_nov > e->cfg.max_topk)
-      REC_FAIL(e, REC_EINVAL, "SMORL step needs div_emb, unpopular and 1 <= topk_div/topk_nov <= max_topk");
-  }
   // three GRU passes: main(s, len) [saved], main(s', len'), boot(s', len)  -- (q1) boot sees true_len
   {
     const int nets[3] = {main_net, main_net, boot};
@@ -311,11 +422,32 @@ extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_tra
   if ((rc = launch_td(e, b, hp, n_q, alpha_eff, extra(e).q_loss_rows))) return rc;
   if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
-  float step_size, bc2_sqrt;
-  adam_scalars(e, main_net, hp, &step_size, &bc2_sqrt);
   if ((rc = launch_head_backward_adam(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
   if ((rc = launch_gru_backward(e, main_net, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp))) return rc;
   return launch_embedding_update(e, main_net, b->s, b->true_len, B, step_size, bc2_sqrt, hp);
+}
+
+extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out) {
+  if (!e) return REC_EINVAL;
+  if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q needs a twin-net engine with Q heads");
+  if (main_net != 0 && main_net != 1) REC_FAIL(e, REC_EINVAL, "main_net must be 0 or 1");
+  int rc = check_net(e, main_net, true);
+  if (rc) return rc;
+  if ((rc = check_net(e, 1 - main_net, false))) return rc;
+  if ((rc = check_batch(e, b, true))) return rc;
+  if (!hp || !losses_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_q: null argument");
+  if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
+  const int n_q = e->cfg.n_heads - 1;
+  if (n_q == 3) {
+    if (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 || hp->div_dim < 1 ||
+        hp->topk_div > e->cfg.max_topk || hp->topk_nov > e->cfg.max_topk)
+      REC_FAIL(e, REC_EINVAL, "SMORL step needs div_emb, unpopular and 1 <= topk_div/topk_nov <= max_topk");
+  }
+  float step_size, bc2_sqrt;
+  adam_scalars(e, main_net, hp, &step_size, &bc2_sqrt);
+  return run_step_graphed(e, 1, main_net, b, hp, losses_out, [&](const rec_batch *bb) {
+    return q_step_body(e, bb, hp, main_net, losses_out, step_size, bc2_sqrt);
+  });
 }
 
 static int eval_kmax(const rec_eval_opts *o) {
@@ -446,6 +578,7 @@ extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, flo
   if ((rc = launch_loss_reduce(e, B, n_q > 0 ? extra(e).q_loss_rows : nullptr, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, (n_q > 0 ? 2 : 1) * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
   adam_scalars(e, main_net, hp, &e->cur_step_size, &e->cur_bc2_sqrt);
+  if ((rc = upload_adam_scalars(e))) return rc;
   if ((rc = launch_head_backward_adam(e, main_net, e->h_state[0], b, B, e->cur_step_size, e->cur_bc2_sqrt, hp, 1.f / (float)B))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(dh_out, e->dh, sizeof(float) * (size_t)B * e->D, cudaMemcpyDeviceToDevice, e->stream));
   e->cur_phase = 3;

@@ -65,6 +65,13 @@ struct rec_engine {
   float *summary;        // [maxB][part_stride] per-row record of this shard
   float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;
+  float *h_sc, *d_sc;    // Adam scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)}: pinned host copy -> device (read by every Adam kernel)
+  // CUDA-graph replay of the single-GPU train step (fixed engine-owned input buffers)
+  bool use_graph;
+  cudaStream_t cap_stream;  // private stream used only while capturing (the caller's stream may be the legacy default)
+  rec_batch own;         // engine-owned copy of the caller's batch
+  struct GraphEntry { uint64_t key; void *exec; int launches; int seen; } graphs[16];
+  int n_graphs;
   long long *trace;      // optional device buffer for clock64 phase traces (debug)
   bool use_tc;           // tensor-core (tcgen05) head kernels when D == 64
   cudaEvent_t ev[8];

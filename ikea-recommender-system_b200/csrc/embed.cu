@@ -173,7 +173,9 @@ struct AdamStreamSet {  // up to 3 same-shaped tensors updated by one launch (bl
 template <int UNROLL>
 __global__ void __launch_bounds__(256) adam_stream_kernel(AdamStreamSet ts, const int32_t *__restrict__ slot_of_row,
                                                           int grad_stride4, uint32_t n4, int D4, int d4_shift, float b1,
-                                                          float b2, float eps, float step_size, float inv_bc2_sqrt) {
+                                                          float b2, float eps, float step_size, float inv_bc2_sqrt,
+                                                          const float *__restrict__ sc) {
+  if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
   float4 *__restrict__ p = ts.p[blockIdx.y];
   float4 *__restrict__ m = ts.m[blockIdx.y];
   float4 *__restrict__ v = ts.v[blockIdx.y];
@@ -209,7 +211,8 @@ __global__ void __launch_bounds__(256) adam_stream_kernel(AdamStreamSet ts, cons
 // bias vectors of the same tensors: one element per row, gradient through the same slot map
 __global__ void __launch_bounds__(256) adam_bias_kernel(AdamStreamSet ts, const int32_t *__restrict__ slot_of_row,
                                                         int bgrad_stride, int rows, float b1, float b2, float eps,
-                                                        float step_size, float inv_bc2_sqrt) {
+                                                        float step_size, float inv_bc2_sqrt, const float *__restrict__ sc) {
+  if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float *bp = ts.bp[blockIdx.y], *bm = ts.bm[blockIdx.y], *bv = ts.bv[blockIdx.y];
@@ -235,12 +238,12 @@ static int launch_adam_stream_set(rec_engine *e, const AdamStreamSet &ts, int n_
   if (blocks < 1) blocks = 1;
   dim3 grid(blocks, n_tensors);
   adam_stream_kernel<UNROLL><<<grid, 256, 0, e->stream>>>(ts, slot_of_row, grad_stride / 4, (uint32_t)n4, D4, shift, hp->beta1,
-                                                          hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt);
+                                                          hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt, e->d_sc);
   REC_LAUNCH_CHECK(e);
   if (with_bias) {
     dim3 g2(cdiv((int)rows, 256), n_tensors);
     adam_bias_kernel<<<g2, 256, 0, e->stream>>>(ts, slot_of_row, bgrad_stride, (int)rows, hp->beta1, hp->beta2, hp->eps, step_size,
-                                               1.f / bc2_sqrt);
+                                               1.f / bc2_sqrt, e->d_sc);
     REC_LAUNCH_CHECK(e);
   }
   return REC_OK;

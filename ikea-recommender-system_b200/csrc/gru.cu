@@ -534,7 +534,8 @@ struct GruAdamPtrs {
 // g, g+4, ...; groups are combined in order), then Adam + refresh of the transposed copies.
 __global__ void __launch_bounds__(256) gru_adam_kernel(GruAdamPtrs q, const float *__restrict__ part, int splits, int dirs,
                                                        int E, int H, int KS, float b1, float b2, float eps,
-                                                       float step_size, float bc2_sqrt) {
+                                                       float step_size, float bc2_sqrt, const float *__restrict__ sc) {
+  if (sc) { step_size = sc[0]; bc2_sqrt = 1.f / sc[1]; }
   __shared__ float sh[4][64];
   const int G = 3 * H;
   const int per_dir = G * E + G * H + 2 * G;
@@ -698,7 +699,7 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
   }
   int total = (G * E + G * H + 2 * G) * e->dirs;
   gru_adam_kernel<<<cdiv(total, 64), 256, 0, e->stream>>>(q, e->wgrad_part, splits, e->dirs, E, H, KS, hp->beta1,
-                                                          hp->beta2, hp->eps, step_size, bc2_sqrt);
+                                                          hp->beta2, hp->eps, step_size, bc2_sqrt, e->d_sc);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
 }

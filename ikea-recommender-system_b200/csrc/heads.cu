@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, co
                                                             int vocab_lo, int n_tiles, float inv_B,
                                                             float *__restrict__ dh_part, float b1, float b2,
                                                             float eps, float step_size, float bc2_sqrt,
-                                                            int head_begin) {
+                                                            int head_begin, const float *__restrict__ sc) {
+  if (sc) { step_size = sc[0]; bc2_sqrt = 1.f / sc[1]; }
   extern __shared__ __align__(16) float dyn[];
   const int DP = D + 4;
   float *dW = dyn;                                   // [TN][DP]
@@ -694,7 +695,7 @@ int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const r
     dim3 grid(n_cta, 1);  // supervised head only; the Q heads stream below
     head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
                                                         n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
-                                                        step_size, bc2_sqrt, 0);
+                                                        step_size, bc2_sqrt, 0, e->d_sc);
     REC_LAUNCH_CHECK(e);
   }
   if (e->timing) cudaEventRecord(e->ev[1], e->stream);

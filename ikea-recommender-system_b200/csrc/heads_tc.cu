@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) head_bwd_adam_tc_kernel(TcTrai
                                                                           int vocab_lo, int n_tiles, float inv_B,
                                                                           float *__restrict__ dh_part, float b1, float b2,
                                                                           float eps, float step_size, float inv_bc2_sqrt,
-                                                                          long long *__restrict__ trace) {
+                                                                          long long *__restrict__ trace,
+                                                                          const float *__restrict__ sc) {
+  if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
   extern __shared__ uint8_t raw[];
   uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   int tr_n = 0;
@@ -803,7 +805,7 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   REC_LAUNCH_CHECK(e);
   head_bwd_adam_tc_kernel<<<n_cta, BWD_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles,
                                                           inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size,
-                                                          1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr);
+                                                          1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr, e->d_sc);
   REC_LAUNCH_CHECK(e);
   *n_slices = n_cta;
   return REC_OK;

@@ -34,14 +34,14 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
     trainer.send_to_device()
     trainer.set_train()
     dev_batches = [tuple(t.to(dev) for t in b) for b in batches]
-    for i in range(W):
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # before the warm-up: nvidia-smi needs ~100 ms to emit its first sample
+    for i in range(max(W, 30)):
         trainer.train_step_async(*dev_batches[i % n_b])
     torch.cuda.synchronize()
     eng = trainer._engine
-
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    m0 = clocks.mark()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
@@ -56,7 +56,7 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = eng.launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(m0, max(clocks.mark(), m0 + 1)) if rank == 0 else None
     value = B * world * K / (ms / 1e3)
 
     # dominant kernel on this rank (its shard of every head)

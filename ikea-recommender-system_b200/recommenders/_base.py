@@ -176,7 +176,11 @@ class NativeSessionNet(nn.Module):
 
 # ---------------------------------------------------------------------------------------------
 class BatchStager:
-    """Packs one replay-buffer batch into a pinned host buffer and ships it with ONE H2D copy."""
+    """Packs one replay-buffer batch into a pinned host buffer and ships it with ONE H2D copy.
+
+    Layout (bytes): int64 s[B,L] | s_next[B,L] | a[B] | true_len[B] | true_next_len[B] | float32 r[B] | uint8 is_end[B]
+    (the same layout rec_pack_batch produces).  Host-side packing uses numpy views of the pinned buffer
+    (sub-microsecond copies); `depth` slots rotate so that a slot is never rewritten while its copy is in flight."""
 
     def __init__(self, device, L, depth=4):
         self.device, self.L, self.depth = device, L, depth
@@ -187,14 +191,16 @@ class BatchStager:
 
     def _alloc(self, B):
         self.cap = B
-        n64 = B * (2 * self.L + 3)
-        self.nbytes = n64 * 8 + B * 4 + B
-        self.nbytes = (self.nbytes + 15) // 16 * 16
+        L = self.L
+        n64 = B * (2 * L + 3)
+        self.n_used = n64 * 8 + 5 * B
+        self.nbytes = (self.n_used + 15) // 16 * 16
         self.slots = []
         for _ in range(self.depth):
             host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
             dev = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
-            self.slots.append((host, dev, torch.cuda.Event()))
+            self.slots.append(dict(host=host, dev=dev, ev=torch.cuda.Event(), hv=self._np_views(host.numpy(), B),
+                                   dv=self._views(dev, B)))
 
     def _views(self, buf, B):
         L = self.L
@@ -210,27 +216,46 @@ class BatchStager:
         e = buf[off + 4 * B: off + 5 * B]
         return s, sn, a, ln, nl, r, e
 
+    def _np_views(self, arr, B):
+        import numpy as np
+        L = self.L
+        n64 = B * (2 * L + 3)
+        i64 = arr[: n64 * 8].view(np.int64)
+        o = 0
+        s = i64[o:o + B * L].reshape(B, L); o += B * L
+        sn = i64[o:o + B * L].reshape(B, L); o += B * L
+        a = i64[o:o + B]; o += B
+        ln = i64[o:o + B]; o += B
+        nl = i64[o:o + B]; o += B
+        r = arr[n64 * 8: n64 * 8 + 4 * B].view(np.float32)
+        e = arr[n64 * 8 + 4 * B: n64 * 8 + 5 * B]
+        return s, sn, a, ln, nl, r, e
+
     def stage(self, s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
+        import numpy as np
         B = int(s.shape[0])
         if s.is_cuda:  # already resident: no staging, just dtype/contiguity
             f = lambda t, dt: None if t is None else t.to(device=self.device, dtype=dt).contiguous()
             return (f(s, torch.int64), f(s_next, torch.int64), f(a, torch.int64), f(true_len, torch.int64),
                     f(true_next_len, torch.int64), f(r, torch.float32),
                     None if is_end is None else is_end.to(device=self.device, dtype=torch.uint8).contiguous())
-        if B > self.cap:
+        if B != self.cap:
+            if self.slots:
+                torch.cuda.synchronize(self.device)
             self._alloc(B)
-        host, dev, ev = self.slots[self.i]
+        slot = self.slots[self.i]
         self.i = (self.i + 1) % self.depth
-        ev.synchronize()  # the copy that last used this slot has finished
-        hs, hsn, ha, hln, hnl, hr, he = self._views(host, B)
-        hs.copy_(s); ha.copy_(a); hln.copy_(true_len)
+        slot["ev"].synchronize()  # the copy that last used this slot has finished
+        hs, hsn, ha, hln, hnl, hr, he = slot["hv"]
+        np.copyto(hs, s.numpy(), casting="unsafe"); np.copyto(ha, a.numpy(), casting="unsafe")
+        np.copyto(hln, true_len.numpy(), casting="unsafe")
         if r is not None:
-            hsn.copy_(s_next); hnl.copy_(true_next_len); hr.copy_(r.reshape(-1)); he.copy_(is_end)
-        n = B * (2 * self.L + 3) * 8 + 5 * B
-        dev[:n].copy_(host[:n], non_blocking=True)
-        ev.record()
-        self.h2d_bytes = n
-        ds, dsn, da, dln, dnl, dr, de = self._views(dev, B)
+            np.copyto(hsn, s_next.numpy(), casting="unsafe"); np.copyto(hnl, true_next_len.numpy(), casting="unsafe")
+            np.copyto(hr, r.numpy().reshape(-1), casting="unsafe"); np.copyto(he, is_end.numpy(), casting="unsafe")
+        slot["dev"].copy_(slot["host"], non_blocking=True)
+        slot["ev"].record()
+        self.h2d_bytes = self.n_used
+        ds, dsn, da, dln, dnl, dr, de = slot["dv"]
         if r is None:
             return ds, None, da, dln, None, None, None
         return ds, dsn, da, dln, dnl, dr, de
