@@ -106,6 +106,11 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->emb_slot, int32_t, (int64_t)c.item_num + 1);
   ALLOC(e, e->emb_grad_rows, float, mb * L * E);
   ALLOC(e, e->emb_leader, uint8_t, mb * L);
+  ALLOC(e, e->emb_sorted, int32_t, mb * L);
+  ALLOC(e, e->emb_seg, int32_t, mb * L + 2);
+  cudaMemsetAsync(e->emb_seg, 0, sizeof(int32_t) * (mb * L + 2), e->stream);
+  ALLOC(e, e->emb_carry, float, (mb * L / 32 + 1) * 64);
+  ALLOC(e, e->emb_tmeta, int32_t, (mb * L / 32 + 1) * 2);
   e->part_stride = 72;
   e->n_split_max = 2 * e->sm_count;
   ALLOC(e, e->part, float, ((int64_t)e->sm_count * 4 * 128 + 4 * mb) * e->part_stride);
@@ -164,7 +169,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->d_sc, (void *)e->own.s,
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_carry, e->emb_tmeta, e->d_sc, (void *)e->own.s,
                   (void *)e->own.r, (void *)e->own.is_end};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)

@@ -41,6 +41,10 @@ struct rec_engine {
   int32_t *emb_slot;     // [N+1] slot of the leader position or -1
   float *emb_grad_rows;  // [maxB*L, E]
   uint8_t *emb_leader;   // [maxB*L] chunk-leader flags (batches spanning several dedup chunks)
+  int32_t *emb_sorted;   // [maxB*L] positions sorted by (row, position)  (sort-based dedup, E = 64)
+  int32_t *emb_seg;      // [maxB*L + 2] row of each sorted entry; [cap] = valid entries, [cap+1] = finished-tile counter
+  float *emb_carry;      // [maxB*L/32 + 1, 64] partial sums of runs continued from the previous tile
+  int32_t *emb_tmeta;    // [maxB*L/32 + 1, 2] (tile starts inside a run, leader of the tile's last run)
   // head statistics partials: [n_split][maxB][PART_STRIDE]
   float *part;
   int part_stride, n_split_max;

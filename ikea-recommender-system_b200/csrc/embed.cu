@@ -365,11 +365,204 @@ int launch_fill_i32(rec_engine *e, int32_t *p, int64_t n, int32_t v) {
   return REC_OK;
 }
 
+
+// ---- sort-based duplicate combining (E = 64, one direction, P <= 8192) ------------------------------------
+// emb_rank_kernel orders the token positions by (row, position) (see below).
+// emb_tilesum64_kernel: one warp per tile of 32 sorted entries loads its 32 dx rows with independent loads and
+// walks them in sorted order; a row whose run continues from the previous tile leaves a carry that the last
+// warp to finish folds into the run's accumulator in tile order.  The summation order depends only on the
+// sorted order => deterministic, no float atomics.
+// Sorting by brute-force ranking: P <= 8192 keys means <= 67 M comparisons, spread over every SM, which beats
+// a single-CTA sorting network by far.  Every CTA recomputes the row of all positions into shared memory
+// (invalid positions get INT_MAX), 8 warps share 32 elements and count the entries ordered before each:
+// rank(i) = #{j : row_j < row_i} + #{j < i : row_j == row_i}.  Ranks are a permutation, so the scatter is
+// conflict-free.
+__global__ void __launch_bounds__(256) emb_rank_kernel(const int64_t *__restrict__ s, const int64_t *__restrict__ lens,
+                                                       int B, int L, int N, int packed, int frozen_row,
+                                                       int32_t *__restrict__ keys, int32_t *__restrict__ sorted_pos,
+                                                       int32_t *__restrict__ sorted_row, int cap) {
+  extern __shared__ int32_t srow[];
+  const int tid = threadIdx.x, P = B * L;
+  const int Ppad = (P + 15) & ~15;
+  int n_valid = 0;
+  for (int i0 = 0; i0 < Ppad; i0 += 4 * 256) {
+    int64_t itv[4], lv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // independent loads first: this phase is pure latency
+      const int i = i0 + u * 256 + tid;
+      itv[u] = 0;
+      lv[u] = L;
+      if (i < P) {
+        itv[u] = s[i];
+        if (packed) lv[u] = lens[i / L];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256 + tid;
+      if (i >= Ppad) continue;
+      int row = 0x7fffffff;
+      if (i < P) {
+        const int t = i - (i / L) * L;
+        const int len = (int)(lv[u] < 1 ? 1 : (lv[u] > L ? L : lv[u]));
+        int64_t it = itv[u];
+        it = it < 0 ? 0 : (it > N ? N : it);
+        const bool ok = (t < len && (int)it != frozen_row);
+        if (ok) { row = (int)it; ++n_valid; }
+        if (blockIdx.x == 0) keys[i] = ok ? row : -1;
+      }
+      srow[i] = row;
+    }
+  }
+  if (blockIdx.x == 0) {
+    __shared__ int nv[8];
+    for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    if ((tid & 31) == 0) nv[tid >> 5] = n_valid;
+    __syncthreads();
+    if (tid == 0) sorted_row[cap] = nv[0] + nv[1] + nv[2] + nv[3] + nv[4] + nv[5] + nv[6] + nv[7];
+  } else {
+    __syncthreads();
+  }
+  // lane = element, warp = 1/8 of the scan range: every shared-memory read is a warp-wide broadcast and the
+  // loop is branch-free (row_j is counted when it is below row_i + [j < i])
+  __shared__ int part_cnt[8][32];
+  const int lane = tid & 31, wid = tid >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int ri = i < P ? srow[i] : 0x7ffffffe;
+  const int Q = Ppad >> 3;                  // entries per warp (multiple of 2)
+  int cnt = 0;
+  const int2 *src = reinterpret_cast<const int2 *>(srow + wid * Q);
+  const int jb = wid * Q;
+#pragma unroll 4
+  for (int g = 0; g < (Q >> 1); ++g) {
+    const int2 r = src[g];
+    const int j0 = jb + 2 * g;
+    cnt += (r.x < ri + (j0 < i ? 1 : 0)) ? 1 : 0;
+    cnt += (r.y < ri + (j0 + 1 < i ? 1 : 0)) ? 1 : 0;
+  }
+  part_cnt[wid][lane] = cnt;
+  __syncthreads();
+  if (wid == 0 && i < P && ri != 0x7fffffff) {
+    int rank = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) rank += part_cnt[w][lane];
+    sorted_pos[rank] = i;
+    sorted_row[rank] = ri;
+  }
+}
+
+__global__ void __launch_bounds__(256) emb_tilesum64_kernel(const int32_t *__restrict__ sorted_pos, int32_t *__restrict__ sorted_row,
+                                                            int cap, const float *__restrict__ dx, float *__restrict__ grad_rows,
+                                                            int32_t *__restrict__ slot_of_row, float *__restrict__ carry,
+                                                            int32_t *__restrict__ tile_meta) {
+  const int lane = threadIdx.x & 31;
+  const int T = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_valid = sorted_row[cap];
+  const int n_tiles = (n_valid + 31) >> 5;
+  if (T >= n_tiles) return;
+  const int idx = 32 * T + lane;
+  const bool valid = idx < n_valid;
+  const int pos = valid ? sorted_pos[idx] : -1;
+  const int row = valid ? sorted_row[idx] : -2;
+  int prev = __shfl_up_sync(0xffffffffu, row, 1);
+  if (lane == 0) prev = idx > 0 ? sorted_row[idx - 1] : -1;
+  const bool head = valid && row != prev;
+  const unsigned hmask = __ballot_sync(0xffffffffu, head), vmask = __ballot_sync(0xffffffffu, valid);
+  if (head) slot_of_row[row] = pos;
+  float2 v[32];
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    const int pp = __shfl_sync(0xffffffffu, pos, u);
+    v[u] = make_float2(0.f, 0.f);
+    if (pp >= 0) v[u] = *reinterpret_cast<const float2 *>(dx + (int64_t)pp * 64 + 2 * lane);
+  }
+  float2 acc = make_float2(0.f, 0.f);
+  int cur = -1;  // leader position of the open run; -1 = run continued from the previous tile (-> carry)
+  auto flush = [&]() {
+    float *dst = cur < 0 ? carry + (int64_t)T * 64 : grad_rows + (int64_t)cur * 64;
+    *reinterpret_cast<float2 *>(dst + 2 * lane) = acc;
+  };
+#pragma unroll
+  for (int u = 0; u < 32; ++u) {
+    if ((vmask >> u) & 1u) {
+      if ((hmask >> u) & 1u) {
+        flush();
+        cur = __shfl_sync(0xffffffffu, pos, u);
+        acc = make_float2(0.f, 0.f);
+      }
+      acc.x += v[u].x;
+      acc.y += v[u].y;
+    }
+  }
+  flush();
+  if (lane == 0) {
+    tile_meta[2 * T] = (hmask & 1u) ? 0 : 1;
+    tile_meta[2 * T + 1] = cur;
+  }
+}
+
+// One warp per run that crosses a tile boundary (the warp of the run's first continuation tile): adds the
+// carries of the following tiles to the run's accumulator in tile order.
+__global__ void __launch_bounds__(256) emb_carry_kernel(const int32_t *__restrict__ sorted_row, int cap,
+                                                        float *__restrict__ grad_rows, const float *__restrict__ carry,
+                                                        const int32_t *__restrict__ tile_meta) {
+  const int lane = threadIdx.x & 31;
+  const int T = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_tiles = (sorted_row[cap] + 31) >> 5;
+  if (T < 1 || T >= n_tiles) return;
+  if (!tile_meta[2 * T]) return;                 // tile starts with a run head
+  const int leader = tile_meta[2 * (T - 1) + 1];
+  if (leader < 0) return;                        // previous tile is itself a continuation: not the first one
+  float2 *dst = reinterpret_cast<float2 *>(grad_rows + (int64_t)leader * 64 + 2 * lane);
+  float2 acc = *dst;
+  for (int T0 = T; T0 < n_tiles; T0 += 32) {
+    // tiles T0.. belong to the run while they start inside it; the run ends in the first tile that has a head
+    const int t = T0 + lane;
+    const bool cont = t < n_tiles && tile_meta[2 * t] != 0;
+    const bool ends = t < n_tiles && tile_meta[2 * t + 1] >= 0;
+    const unsigned nc = __ballot_sync(0xffffffffu, !cont), en = __ballot_sync(0xffffffffu, ends);
+    int n = nc ? __ffs(nc) - 1 : 32;             // tiles of this batch that continue the run
+    if (en && __ffs(en) - 1 < n) n = __ffs(en);  // the tile where the run ends still carries its tail
+    float2 v[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      v[u] = make_float2(0.f, 0.f);
+      if (u < n) v[u] = *reinterpret_cast<const float2 *>(carry + (int64_t)(T0 + u) * 64 + 2 * lane);
+    }
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      acc.x += v[u].x;
+      acc.y += v[u].y;
+    }
+    if (n < 32) break;
+  }
+  *dst = acc;
+}
+
 int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
                             float step_size, float bc2_sqrt, const rec_train_hparams *hp) {
   const rec_config &c = e->cfg;
   const int L = c.state_size, E = c.embedding_dim, P = B * L;
   NetBind &nb = e->nets[net_id];
+  if (E == 64 && e->dirs == 1 && P <= 8192) {
+    int rc;
+    emb_rank_kernel<<<cdiv(P, 32), 256, ((P + 15) & ~15) * sizeof(int32_t), e->stream>>>(
+        s, lengths, B, L, c.item_num, c.use_packed_seq, c.frozen_pad_row, e->emb_keys, e->emb_sorted, e->emb_seg, c.max_batch * L);
+    REC_LAUNCH_CHECK(e);
+    emb_tilesum64_kernel<<<cdiv(cdiv(P, 32), 8), 256, 0, e->stream>>>(e->emb_sorted, e->emb_seg, c.max_batch * L, e->dx,
+                                                                     e->emb_grad_rows, e->emb_slot, e->emb_carry, e->emb_tmeta);
+    REC_LAUNCH_CHECK(e);
+    emb_carry_kernel<<<cdiv(cdiv(P, 32), 8), 256, 0, e->stream>>>(e->emb_seg, c.max_batch * L, e->emb_grad_rows, e->emb_carry, e->emb_tmeta);
+    REC_LAUNCH_CHECK(e);
+    if (e->timing) cudaEventRecord(e->ev[4], e->stream);
+    rc = launch_adam_stream(e, nb.p.emb, nb.p.emb_m, nb.p.emb_v, (int64_t)c.item_num + 1, E, e->emb_slot,
+                            e->emb_grad_rows, E, nullptr, nullptr, nullptr, nullptr, 0, hp, step_size, bc2_sqrt);
+    if (rc) return rc;
+    if (e->timing) cudaEventRecord(e->ev[5], e->stream);
+    emb_reset_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(e->emb_keys, P, e->emb_slot);
+    REC_LAUNCH_CHECK(e);
+    return REC_OK;
+  }
   emb_keys_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(s, lengths, B, L, c.item_num, c.use_packed_seq,
                                                       c.frozen_pad_row, e->emb_keys);
   REC_LAUNCH_CHECK(e);
