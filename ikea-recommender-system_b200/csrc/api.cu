@@ -136,7 +136,20 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
     e->own.true_next_len = p64 + 2 * mb * L + 2 * mb; e->own.r = pf; e->own.is_end = p8;
   }
   e->use_graph = getenv("REC_NO_GRAPH") == nullptr;
-  if (cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) e->use_graph = false;
+  e->overlap = getenv("REC_NO_OVERLAP") == nullptr;
+  for (int i = 0; i < 2; ++i) {
+    e->side_dirty[i] = false;
+    if (cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_mark[i], cudaEventDisableTiming) != cudaSuccess)
+      e->overlap = false;
+  }
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  // the capture stream (main branch of the graph) outranks the side branch: the one-CTA-per-SM tensor-core
+  // kernels must get their SM slots before the streaming kernels fill the machine
+  if (cudaStreamCreateWithPriority(&e->cap_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) e->use_graph = false;
   ALLOC(e, e->hpack, uint8_t, (size_t)((mb + 255) / 256) * 4 * 16384);
   ALLOC(e, e->q_grad_rows, float, mb * 3 * D);
   ALLOC(e, e->q_bgrad, float, mb * 3);
@@ -181,6 +194,12 @@ extern "C" void rec_destroy(rec_engine *e) {
   for (int i = 0; i < e->n_graphs; ++i) if (e->graphs[i].exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graphs[i].exec);
   if (e->h_sc) cudaFreeHost(e->h_sc);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (e->side[i]) { cudaStreamSynchronize(e->side[i]); cudaStreamDestroy(e->side[i]); }
+    if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    if (e->ev_mark[i]) cudaEventDestroy(e->ev_mark[i]);
+  }
   free(e);
 }
 
@@ -364,6 +383,31 @@ static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_bat
   return REC_OK;
 }
 
+// GRU backward + embedding update with the two independent chains overlapped:
+//   main: BPTT -> weight gradients -> GRU Adam        side: duplicate sums (after BPTT) -> table Adam (after wgrad)
+// `ranked`: stage 1 of the embedding update was already issued (it needs only the batch).
+static int trunk_backward(rec_engine *e, int net, const int64_t *s, const int64_t *lens, int B, const float *dh,
+                          float step_size, float bc2_sqrt, const rec_train_hparams *hp, bool ranked) {
+  int rc;
+  if (!ranked) {
+    SideScope side(e, 1);
+    if ((rc = launch_embedding_update(e, net, s, lens, B, step_size, bc2_sqrt, hp, 1))) return rc;
+  }
+  if ((rc = launch_gru_backward(e, net, s, lens, B, dh, step_size, bc2_sqrt, hp, 1))) return rc;
+  {
+    SideScope side(e, 1);
+    if ((rc = launch_embedding_update(e, net, s, lens, B, step_size, bc2_sqrt, hp, 2))) return rc;
+  }
+  if ((rc = launch_gru_backward(e, net, s, lens, B, dh, step_size, bc2_sqrt, hp, 2))) return rc;
+  {
+    SideScope side(e, 1);  // the weight gradients read the table: its Adam sweep waits for them
+    if ((rc = launch_embedding_update(e, net, s, lens, B, step_size, bc2_sqrt, hp, 4))) return rc;
+  }
+  if ((rc = launch_gru_backward(e, net, s, lens, B, dh, step_size, bc2_sqrt, hp, 4))) return rc;
+  side_join(e, 1);
+  return REC_OK;
+}
+
 static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out,
                            float step_size, float bc2_sqrt) {
   int rc;
@@ -377,8 +421,7 @@ static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hp
   if ((rc = launch_loss_reduce(e, B, nullptr, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(loss_out, e->loss_buf, sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
   if ((rc = launch_head_backward_adam(e, 0, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
-  if ((rc = launch_gru_backward(e, 0, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp))) return rc;
-  return launch_embedding_update(e, 0, b->s, b->true_len, B, step_size, bc2_sqrt, hp);
+  return trunk_backward(e, 0, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp, false);
 }
 
 extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out) {
@@ -394,10 +437,20 @@ extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, cons
   });
 }
 
+// One fused SQN / SMORL step.  Branch structure (each branch is a stream; parallel branches under graph capture):
+//   main   : GRU fwd -> supervised stats -> [mark 0] -> greedy-action stats -> Q row dots -> TD / losses -> q_dh
+//            -> [mark 1] -> Q-head gradient rows + streaming Adam                                  (HBM-bound)
+//   side 0 : (after mark 0) supervised-head backward + Adam (tensor cores, latency-bound)
+//            -> (after mark 1) dh reduce -> GRU backward / weight update
+//   side 1 : token ordering (start of step), duplicate sums, embedding-table Adam               (see trunk_backward)
 static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out,
                        float step_size, float bc2_sqrt) {
   int rc;
   const int B = b->B, boot = 1 - main_net, n_q = e->cfg.n_heads - 1;
+  {  // ordering of the token positions for the embedding backward: needs only the batch
+    SideScope side(e, 1);
+    if ((rc = launch_embedding_update(e, main_net, b->s, b->true_len, B, step_size, bc2_sqrt, hp, 1))) return rc;
+  }
   // three GRU passes: main(s, len) [saved], main(s', len'), boot(s', len)  -- (q1) boot sees true_len
   {
     const int nets[3] = {main_net, main_net, boot};
@@ -414,11 +467,16 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
   int n_split = 0;
   if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
   if ((rc = launch_head_merge(e, e->part, n_split, B, a.topk, true, false))) return rc;
+  side_mark(e, 0);  // log-sum-exp of the supervised logits is final: its backward may start
   // greedy action a* = argmax_a sum_h w_h Q_h(s', a) on the main net
   HeadStatsArgs g = {};
   g.net_id = main_net; g.h = e->h_state[1]; g.B = B; g.n_arg = n_q;
   g.w[0] = n_q == 3 ? hp->q_weights[0] : 1.f; g.w[1] = hp->q_weights[1]; g.w[2] = hp->q_weights[2];
   if ((rc = head_stats_dispatch(e, g, &n_split))) return rc;
+  {  // issued after the greedy-action statistics so that those get the SMs first
+    SideScope side(e, 0, 0);
+    if ((rc = launch_sup_head_bwd(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
+  }
   if ((rc = launch_head_merge(e, e->part, n_split, B, 0, false, true))) return rc;
   // Q(s,a) on main, Q_boot(s',a*) on boot: row gather-dots
   if ((rc = launch_row_dots(e, main_net, e->h_state[0], b->a, nullptr, B, 1, n_q, e->q_sa))) return rc;
@@ -427,9 +485,16 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
   if ((rc = launch_td(e, b, hp, n_q, alpha_eff, extra(e).q_loss_rows))) return rc;
   if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
-  if ((rc = launch_head_backward_adam(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
-  if ((rc = launch_gru_backward(e, main_net, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp))) return rc;
-  return launch_embedding_update(e, main_net, b->s, b->true_len, B, step_size, bc2_sqrt, hp);
+  if ((rc = launch_q_dh(e, main_net, b, B))) return rc;
+  side_mark(e, 1);  // every dh slice of the Q heads is written
+  {
+    SideScope side(e, 0, 1);
+    if ((rc = launch_dh_reduce(e, B))) return rc;
+    if ((rc = trunk_backward(e, main_net, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp, true))) return rc;
+  }
+  if ((rc = launch_q_heads_update(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp))) return rc;
+  side_join(e, 0);
+  return REC_OK;
 }
 
 extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out) {
@@ -523,6 +588,8 @@ extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_tr
   if (main_net < 0 || main_net >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "main_net out of range");
   int rc = check_net(e, main_net, true);
   if (rc) return rc;
+  side_join(e, 0);  // a previous step abandoned after phase C may still have its Q-head sweep in flight
+  side_join(e, 1);
   if ((rc = check_batch(e, b, n_q > 0))) return rc;
   if (n_q > 0 && e->cfg.n_nets != 2) REC_FAIL(e, REC_EINVAL, "Q heads need a twin-net engine");
   if (n_q == 3 && (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 ||
@@ -598,8 +665,7 @@ extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
   const int main_net = e->cur_main;
   e->cur_phase = 0;
   int rc;
-  if ((rc = launch_gru_backward(e, main_net, b->s, b->true_len, b->B, dh_reduced, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp))) return rc;
-  return launch_embedding_update(e, main_net, b->s, b->true_len, b->B, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp);
+  return trunk_backward(e, main_net, b->s, b->true_len, b->B, dh_reduced, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, false);
 }
 
 // Sharded evaluation: per-shard record (max, sumexp, target logit, top-k candidates) per row ...

@@ -73,6 +73,12 @@ struct rec_engine {
   // CUDA-graph replay of the single-GPU train step (fixed engine-owned input buffers)
   bool use_graph;
   cudaStream_t cap_stream;  // private stream used only while capturing (the caller's stream may be the legacy default)
+  // Independent branches of the step (Q-head Adam sweep next to the supervised-head kernel, embedding chain
+  // next to the GRU weight update) run on a second stream; under graph capture they become parallel branches.
+  cudaStream_t side[2];
+  cudaEvent_t ev_fork[2], ev_join[2], ev_mark[2];
+  bool overlap;        // REC_NO_OVERLAP=1 serialises everything on the caller's stream
+  bool side_dirty[2];  // work was issued on side[i] since its last join
   rec_batch own;         // engine-owned copy of the caller's batch
   struct GraphEntry { uint64_t key; void *exec; int launches; int seen; } graphs[16];
   int n_graphs;
@@ -151,14 +157,47 @@ int launch_gru_forward(rec_engine *e, int net_id, const int64_t *s, const int64_
                        float *h_out, bool save);
 int launch_gru_forward_multi(rec_engine *e, int n_pass, const int *net_ids, const int64_t *const *s,
                              const int64_t *const *lengths, float *const *h_out, const bool *save, int B);
+// stages: 1 = BPTT (dgi, dgh, dx), 2 = weight gradients, 4 = Adam on the GRU parameters
 int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
-                        const float *dh, float step_size, float bc2_sqrt, const rec_train_hparams *hp);
+                        const float *dh, float step_size, float bc2_sqrt, const rec_train_hparams *hp, int stages = 7);
 int launch_gru_transpose(rec_engine *e, int net_id);
 // embed.cu
+// stages: 1 = order the token positions (needs only the batch), 2 = combine duplicate rows (needs dx),
+// 4 = dense Adam sweep + slot reset (must run after the GRU weight gradients, which read the table)
 int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
-                            float step_size, float bc2_sqrt, const rec_train_hparams *hp);
+                            float step_size, float bc2_sqrt, const rec_train_hparams *hp, int stages = 7);
+
 int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                         float bc2_sqrt, const rec_train_hparams *hp);
+
+// Launches issued while a SideScope is alive go to side stream `idx`, ordered after everything issued so far on
+// the current stream -- or, with `mark` >= 0, after the point remembered by side_mark(e, mark).  Scopes nest
+// (the current stream may itself be a side stream).  side_join() makes the current stream wait for side `idx`.
+// With overlap off the scope is a no-op and everything runs in program order on one stream.
+static inline bool side_enabled(const rec_engine *e) { return e->overlap && !e->timing && !e->trace; }
+static inline void side_mark(rec_engine *e, int k) {
+  if (side_enabled(e)) cudaEventRecord(e->ev_mark[k], e->stream);
+}
+struct SideScope {
+  rec_engine *e;
+  cudaStream_t main;
+  SideScope(rec_engine *e_, int idx, int mark = -1) : e(e_), main(e_->stream) {
+    if (side_enabled(e)) {
+      cudaEvent_t ev = mark >= 0 ? e->ev_mark[mark] : e->ev_fork[idx];
+      if (mark < 0) cudaEventRecord(ev, main);
+      cudaStreamWaitEvent(e->side[idx], ev, 0);
+      e->stream = e->side[idx];
+      e->side_dirty[idx] = true;
+    }
+  }
+  ~SideScope() { e->stream = main; }
+};
+static inline void side_join(rec_engine *e, int idx) {
+  if (!e->side_dirty[idx]) return;
+  cudaEventRecord(e->ev_join[idx], e->side[idx]);
+  cudaStreamWaitEvent(e->stream, e->ev_join[idx], 0);
+  e->side_dirty[idx] = false;
+}
 // heads.cu
 struct HeadStatsArgs {
   int net_id;
@@ -184,3 +223,11 @@ int launch_row_dots(rec_engine *e, int net_id, const float *h, const int64_t *id
                     int B, int first_head, int n, float *out);
 int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B,
                               float step_size, float bc2_sqrt, const rec_train_hparams *hp, float inv_B);
+int head_bwd_dense_slices(const rec_engine *e, int B);
+int tc_bwd_slices(const rec_engine *e);
+int launch_q_dh(rec_engine *e, int net_id, const rec_batch *b, int B);
+int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                        float bc2_sqrt, const rec_train_hparams *hp, float inv_B);
+int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                          float bc2_sqrt, const rec_train_hparams *hp);
+int launch_dh_reduce(rec_engine *e, int B);

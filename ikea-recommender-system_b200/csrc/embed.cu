@@ -540,60 +540,57 @@ __global__ void __launch_bounds__(256) emb_carry_kernel(const int32_t *__restric
 }
 
 int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
-                            float step_size, float bc2_sqrt, const rec_train_hparams *hp) {
+                            float step_size, float bc2_sqrt, const rec_train_hparams *hp, int stages) {
   const rec_config &c = e->cfg;
   const int L = c.state_size, E = c.embedding_dim, P = B * L;
   NetBind &nb = e->nets[net_id];
-  if (E == 64 && e->dirs == 1 && P <= 8192) {
-    int rc;
-    emb_rank_kernel<<<cdiv(P, 32), 256, ((P + 15) & ~15) * sizeof(int32_t), e->stream>>>(
-        s, lengths, B, L, c.item_num, c.use_packed_seq, c.frozen_pad_row, e->emb_keys, e->emb_sorted, e->emb_seg, c.max_batch * L);
+  const bool sorted_path = (E == 64 && e->dirs == 1 && P <= 8192);
+  if (stages & 1) {
+    if (sorted_path) {
+      emb_rank_kernel<<<cdiv(P, 32), 256, ((P + 15) & ~15) * sizeof(int32_t), e->stream>>>(
+          s, lengths, B, L, c.item_num, c.use_packed_seq, c.frozen_pad_row, e->emb_keys, e->emb_sorted, e->emb_seg, c.max_batch * L);
+    } else {
+      emb_keys_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(s, lengths, B, L, c.item_num, c.use_packed_seq,
+                                                          c.frozen_pad_row, e->emb_keys);
+    }
     REC_LAUNCH_CHECK(e);
+  }
+  if ((stages & 2) && sorted_path) {
     emb_tilesum64_kernel<<<cdiv(cdiv(P, 32), 8), 256, 0, e->stream>>>(e->emb_sorted, e->emb_seg, c.max_batch * L, e->dx,
                                                                      e->emb_grad_rows, e->emb_slot, e->emb_carry, e->emb_tmeta);
     REC_LAUNCH_CHECK(e);
     emb_carry_kernel<<<cdiv(cdiv(P, 32), 8), 256, 0, e->stream>>>(e->emb_seg, c.max_batch * L, e->emb_grad_rows, e->emb_carry, e->emb_tmeta);
     REC_LAUNCH_CHECK(e);
+  } else if (stages & 2) {
+    const int chunk = 4096;
+    const int n_chunks = cdiv(P, chunk);
+    const int span = n_chunks > 1 ? chunk : P;
+    int use_smem = 1;
+    size_t smem = (size_t)span * sizeof(int32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+      REC_CUDA(e, cudaFuncSetAttribute(emb_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    uint8_t *flags = n_chunks > 1 ? e->emb_leader : nullptr;
+    if (flags) REC_CUDA(e, cudaMemsetAsync(flags, 0, (size_t)P, e->stream));
+    emb_segment_kernel<<<n_chunks > 1 ? n_chunks * (chunk / 8) : cdiv(P, 8), 256, smem, e->stream>>>(
+        e->emb_keys, P, E, e->dirs, e->dx, e->emb_grad_rows, e->emb_slot, use_smem, n_chunks > 1 ? chunk : ((P + 7) / 8) * 8, flags);
+    REC_LAUNCH_CHECK(e);
+    for (int ch = 0; ch < n_chunks && n_chunks > 1; ++ch) {
+      const int c0 = ch * chunk, c1 = c0 + chunk < P ? c0 + chunk : P;
+      emb_chunk_merge_kernel<<<cdiv(c1 - c0, 8), 256, 0, e->stream>>>(e->emb_keys, flags, c0, c1, E, e->emb_grad_rows, e->emb_slot);
+      REC_LAUNCH_CHECK(e);
+    }
+  }
+  if (stages & 4) {
     if (e->timing) cudaEventRecord(e->ev[4], e->stream);
-    rc = launch_adam_stream(e, nb.p.emb, nb.p.emb_m, nb.p.emb_v, (int64_t)c.item_num + 1, E, e->emb_slot,
-                            e->emb_grad_rows, E, nullptr, nullptr, nullptr, nullptr, 0, hp, step_size, bc2_sqrt);
+    int rc = launch_adam_stream(e, nb.p.emb, nb.p.emb_m, nb.p.emb_v, (int64_t)c.item_num + 1, E, e->emb_slot,
+                                e->emb_grad_rows, E, nullptr, nullptr, nullptr, nullptr, 0, hp, step_size, bc2_sqrt);
     if (rc) return rc;
     if (e->timing) cudaEventRecord(e->ev[5], e->stream);
     emb_reset_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(e->emb_keys, P, e->emb_slot);
     REC_LAUNCH_CHECK(e);
-    return REC_OK;
   }
-  emb_keys_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(s, lengths, B, L, c.item_num, c.use_packed_seq,
-                                                      c.frozen_pad_row, e->emb_keys);
-  REC_LAUNCH_CHECK(e);
-  const int chunk = 4096;
-  const int n_chunks = cdiv(P, chunk);
-  const int span = n_chunks > 1 ? chunk : P;
-  int use_smem = 1;
-  size_t smem = (size_t)span * sizeof(int32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    REC_CUDA(e, cudaFuncSetAttribute(emb_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
-  uint8_t *flags = n_chunks > 1 ? e->emb_leader : nullptr;
-  if (flags) REC_CUDA(e, cudaMemsetAsync(flags, 0, (size_t)P, e->stream));
-  emb_segment_kernel<<<n_chunks > 1 ? n_chunks * (chunk / 8) : cdiv(P, 8), 256, smem, e->stream>>>(
-      e->emb_keys, P, E, e->dirs, e->dx, e->emb_grad_rows, e->emb_slot, use_smem, n_chunks > 1 ? chunk : ((P + 7) / 8) * 8, flags);
-  REC_LAUNCH_CHECK(e);
-  for (int c = 0; c < n_chunks && n_chunks > 1; ++c) {
-    const int c0 = c * chunk, c1 = c0 + chunk < P ? c0 + chunk : P;
-    emb_chunk_merge_kernel<<<cdiv(c1 - c0, 8), 256, 0, e->stream>>>(e->emb_keys, flags, c0, c1, E, e->emb_grad_rows, e->emb_slot);
-    REC_LAUNCH_CHECK(e);
-  }
-  if (e->timing) cudaEventRecord(e->ev[4], e->stream);
-  {
-    int rc = launch_adam_stream(e, nb.p.emb, nb.p.emb_m, nb.p.emb_v, (int64_t)c.item_num + 1, E, e->emb_slot,
-                                e->emb_grad_rows, E, nullptr, nullptr, nullptr, nullptr, 0, hp, step_size, bc2_sqrt);
-    if (rc) return rc;
-  }
-  if (e->timing) cudaEventRecord(e->ev[5], e->stream);
-  emb_reset_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(e->emb_keys, P, e->emb_slot);
-  REC_LAUNCH_CHECK(e);
   return REC_OK;
 }

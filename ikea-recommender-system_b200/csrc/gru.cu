@@ -660,7 +660,7 @@ int launch_gru_forward(rec_engine *e, int net_id, const int64_t *s, const int64_
 }
 
 int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
-                        const float *dh, float step_size, float bc2_sqrt, const rec_train_hparams *hp) {
+                        const float *dh, float step_size, float bc2_sqrt, const rec_train_hparams *hp, int stages) {
   const rec_config &c = e->cfg;
   const int E = c.embedding_dim, H = c.hidden_dim, L = c.state_size, G = 3 * H;
   size_t smem = (size_t)GRU_R * (2 * H + 2 * G) * sizeof(float) + GRU_R * sizeof(int);
@@ -669,25 +669,30 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
     REC_CUDA(e, cudaFuncSetAttribute(gru_bwd_kernel<GRU_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  if (gru_fast_path(e)) {
-    dim3 grid(cdiv(B, BR), e->dirs);
-    gru_bwd64_kernel<<<grid, 128, 0, e->stream>>>(gru_weights(e, net_id), lengths, B, L, c.use_packed_seq, dh,
-                                                 e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx);
-  } else {
-    dim3 grid(cdiv(B, GRU_R), e->dirs);
-    gru_bwd_kernel<GRU_R><<<grid, 256, smem, e->stream>>>(gru_weights(e, net_id), lengths, B, L, E, H,
-                                                         c.use_packed_seq, dh, e->gates_save, e->hprev_save,
-                                                         e->dgi, e->dgh, e->dx);
+  if (stages & 1) {
+    if (gru_fast_path(e)) {
+      dim3 grid(cdiv(B, BR), e->dirs);
+      gru_bwd64_kernel<<<grid, 128, 0, e->stream>>>(gru_weights(e, net_id), lengths, B, L, c.use_packed_seq, dh,
+                                                   e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx);
+    } else {
+      dim3 grid(cdiv(B, GRU_R), e->dirs);
+      gru_bwd_kernel<GRU_R><<<grid, 256, smem, e->stream>>>(gru_weights(e, net_id), lengths, B, L, E, H,
+                                                           c.use_packed_seq, dh, e->gates_save, e->hprev_save,
+                                                           e->dgi, e->dgh, e->dx);
+    }
+    REC_LAUNCH_CHECK(e);
   }
-  REC_LAUNCH_CHECK(e);
   // weight gradients (split over token positions) + Adam on the GRU parameters
   const int KS = (E > H ? E : H) + 1;
   const int splits = e->wgrad_splits;
-  dim3 g2(cdiv(G, 64), cdiv(E > H ? E : H, 64), e->dirs * 2 * splits);
-  gru_wgrad_kernel<<<g2, 256, 0, e->stream>>>(e->nets[net_id].p.emb, s, lengths, B, L, E, H, c.item_num,
-                                             c.use_packed_seq, e->dirs, splits, e->dgi, e->dgh, e->hprev_save,
-                                             e->wgrad_part, KS);
-  REC_LAUNCH_CHECK(e);
+  if (stages & 2) {
+    dim3 g2(cdiv(G, 64), cdiv(E > H ? E : H, 64), e->dirs * 2 * splits);
+    gru_wgrad_kernel<<<g2, 256, 0, e->stream>>>(e->nets[net_id].p.emb, s, lengths, B, L, E, H, c.item_num,
+                                               c.use_packed_seq, e->dirs, splits, e->dgi, e->dgh, e->hprev_save,
+                                               e->wgrad_part, KS);
+    REC_LAUNCH_CHECK(e);
+  }
+  if (!(stages & 4)) return REC_OK;
   NetBind &nb = e->nets[net_id];
   GruAdamPtrs q;
   for (int d = 0; d < 2; ++d) {

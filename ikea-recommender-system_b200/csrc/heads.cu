@@ -656,58 +656,86 @@ size_t head_bwd_smem_bytes(int D) {
   return sizeof(float) * ((size_t)TN * (D + 4) + TN + 2 * TM * KP + TM * (TN + 4) + TN * (TM + 4) + 64 * (TN + 4));
 }
 
-int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
-                              float bc2_sqrt, const rec_train_hparams *hp, float inv_B) {
-  const rec_net_params &p = e->nets[net_id].p;
-  HeadTrainPtrs t;
-  for (int i = 0; i < REC_MAX_HEADS; ++i) {
-    t.w[i] = p.head_w[i]; t.wm[i] = p.head_w_m[i]; t.wv[i] = p.head_w_v[i];
-    t.b[i] = p.head_b[i]; t.bm[i] = p.head_b_m[i]; t.bv[i] = p.head_b_v[i];
-  }
+// Number of per-CTA dh slices the supervised-head kernel writes; the Q heads' slice follows them.
+int head_bwd_dense_slices(const rec_engine *e, int B) {
+  if (tc_bwd_supported(e, B)) return tc_bwd_slices(e);
   const int n_tiles = cdiv(e->Vloc, TN);
-  const int n_q = e->cfg.n_heads - 1;
   int n_cta = e->n_dh_part - 1;
-  if (n_cta > n_tiles) n_cta = n_tiles;
-  size_t smem = head_bwd_smem_bytes(e->D);
-  if (smem > 220 * 1024) REC_FAIL(e, REC_EINVAL, "head backward needs %zu B of shared memory (D=%d too large)", smem, e->D);
-  static bool attr_set = false;
-  if (!attr_set) {
-    REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
-  // Q heads: dh contribution of rows a_b, computed before Adam touches W (slice index n_cta)
-  float *q_slice = e->dh_part + (int64_t)n_cta * B * e->D;
-  if (n_q > 0) {
-    q_dh_kernel<<<B, 128, 0, e->stream>>>(head_ptrs(e, net_id), b->a, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo, n_q, q_slice);
-    REC_LAUNCH_CHECK(e);
-  }
+  return n_cta > n_tiles ? n_tiles : n_cta;
+}
+
+// Q heads: dh contribution of rows a_b; must run before Adam touches the Q-head weights.
+int launch_q_dh(rec_engine *e, int net_id, const rec_batch *b, int B) {
+  const int n_q = e->cfg.n_heads - 1;
+  if (n_q <= 0) return REC_OK;
+  float *q_slice = e->dh_part + (int64_t)head_bwd_dense_slices(e, B) * B * e->D;
+  q_dh_kernel<<<B, 128, 0, e->stream>>>(head_ptrs(e, net_id), b->a, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo, n_q, q_slice);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+// Supervised head: backward + Adam fused (tensor-core kernel when the shape allows it).
+int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                        float bc2_sqrt, const rec_train_hparams *hp, float inv_B) {
   if (e->timing) cudaEventRecord(e->ev[0], e->stream);
-  int n_dense_slices = n_cta;
   if (tc_bwd_supported(e, B)) {
-    int rc = launch_head_bwd_adam_tc(e, net_id, h, b, B, step_size, bc2_sqrt, hp, inv_B, &n_dense_slices);
+    int n_slices = 0;
+    int rc = launch_head_bwd_adam_tc(e, net_id, h, b, B, step_size, bc2_sqrt, hp, inv_B, &n_slices);
     if (rc) return rc;
-    if (n_q > 0 && n_dense_slices != n_cta) {
-      // keep the Q-head dh slice adjacent to the dense slices
-      REC_CUDA(e, cudaMemcpyAsync(e->dh_part + (int64_t)n_dense_slices * B * e->D, q_slice, sizeof(float) * (size_t)B * e->D,
-                                  cudaMemcpyDeviceToDevice, e->stream));
-    }
   } else {
-    dim3 grid(n_cta, 1);  // supervised head only; the Q heads stream below
+    const rec_net_params &p = e->nets[net_id].p;
+    HeadTrainPtrs t;
+    for (int i = 0; i < REC_MAX_HEADS; ++i) {
+      t.w[i] = p.head_w[i]; t.wm[i] = p.head_w_m[i]; t.wv[i] = p.head_w_v[i];
+      t.b[i] = p.head_b[i]; t.bm[i] = p.head_b_m[i]; t.bv[i] = p.head_b_v[i];
+    }
+    const int n_tiles = cdiv(e->Vloc, TN);
+    size_t smem = head_bwd_smem_bytes(e->D);
+    if (smem > 220 * 1024) REC_FAIL(e, REC_EINVAL, "head backward needs %zu B of shared memory (D=%d too large)", smem, e->D);
+    static bool attr_set = false;
+    if (!attr_set) {
+      REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set = true;
+    }
+    dim3 grid(head_bwd_dense_slices(e, B), 1);
     head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
                                                         n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
                                                         step_size, bc2_sqrt, 0, e->d_sc);
     REC_LAUNCH_CHECK(e);
   }
   if (e->timing) cudaEventRecord(e->ev[1], e->stream);
-  if (n_q > 0) {
-    // row-sparse gradients of the Q heads + dense Adam: pure HBM streaming (24 B/param)
-    if (e->timing) cudaEventRecord(e->ev[6], e->stream);
-    int rc = launch_q_heads_adam(e, net_id, h, b, B, step_size, bc2_sqrt, hp);
-    if (rc) return rc;
-    if (e->timing) cudaEventRecord(e->ev[7], e->stream);
-  }
-  int64_t n = (int64_t)B * e->D;
-  dh_reduce_kernel<<<(int)cdiv64(n, 64), 256, 0, e->stream>>>(e->dh_part, n_dense_slices + (n_q > 0 ? 1 : 0), n, e->dh);
+  return REC_OK;
+}
+
+// Row-sparse gradients of the Q heads + dense Adam: pure HBM streaming (24 B/param).
+int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                          float bc2_sqrt, const rec_train_hparams *hp) {
+  if (e->cfg.n_heads < 2) return REC_OK;
+  if (e->timing) cudaEventRecord(e->ev[6], e->stream);
+  int rc = launch_q_heads_adam(e, net_id, h, b, B, step_size, bc2_sqrt, hp);
+  if (rc) return rc;
+  if (e->timing) cudaEventRecord(e->ev[7], e->stream);
+  return REC_OK;
+}
+
+int launch_dh_reduce(rec_engine *e, int B) {
+  const int64_t n = (int64_t)B * e->D;
+  const int slices = head_bwd_dense_slices(e, B) + (e->cfg.n_heads > 1 ? 1 : 0);
+  dh_reduce_kernel<<<(int)cdiv64(n, 64), 256, 0, e->stream>>>(e->dh_part, slices, n, e->dh);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
+}
+
+// The whole head backward in program order, with the Q-head sweep on a side stream next to the (latency-bound)
+// supervised-head kernel.  The fused single-GPU Q step orders the pieces itself (api.cu).
+int launch_head_backward_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                              float bc2_sqrt, const rec_train_hparams *hp, float inv_B) {
+  int rc;
+  if ((rc = launch_q_dh(e, net_id, b, B))) return rc;
+  {
+    SideScope side(e, 0);
+    if ((rc = launch_q_heads_update(e, net_id, h, b, B, step_size, bc2_sqrt, hp))) return rc;
+  }
+  if ((rc = launch_sup_head_bwd(e, net_id, h, b, B, step_size, bc2_sqrt, hp, inv_B))) return rc;
+  return launch_dh_reduce(e, B);
 }

@@ -458,7 +458,9 @@ __global__ void __launch_bounds__(256) h_prepack_kernel(const float *__restrict_
 }
 
 #define BWD_THREADS 512
-__global__ void __launch_bounds__(BWD_THREADS, 1) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const uint8_t *__restrict__ hpack,
+// 104 registers x 512 threads leaves room for one 256-thread CTA of the streaming Adam kernel (48 registers)
+// on the same SM (__maxnreg__ cannot be combined with __launch_bounds__).
+__global__ void __maxnreg__(104) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const uint8_t *__restrict__ hpack,
                                                                           const int64_t *__restrict__ target,
                                                                           const float *__restrict__ row_stats, int B, int Vloc,
                                                                           int vocab_lo, int n_tiles, float inv_B,
@@ -787,14 +789,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) head_bwd_adam_tc_kernel(TcTrai
 
 bool tc_bwd_supported(const rec_engine *e, int B) { (void)B; return tc_heads_supported(e); }
 
+int tc_bwd_slices(const rec_engine *e) {
+  const int n_tiles = cdiv(e->Vloc, 128);
+  int n_cta = e->sm_count < n_tiles ? e->sm_count : n_tiles;
+  if (n_cta > e->n_dh_part - 1) n_cta = e->n_dh_part - 1;
+  return n_cta;
+}
+
 // Dense (supervised) head on tensor cores; returns the number of dh slices it wrote.
 int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                             float bc2_sqrt, const rec_train_hparams *hp, float inv_B, int *n_slices) {
   const rec_net_params &p = e->nets[net_id].p;
   TcTrainPtrs t = {p.head_w[0], p.head_w_m[0], p.head_w_v[0], p.head_b[0], p.head_b_m[0], p.head_b_v[0]};
   const int n_tiles = cdiv(e->Vloc, 128);
-  int n_cta = e->sm_count < n_tiles ? e->sm_count : n_tiles;
-  if (n_cta > e->n_dh_part - 1) n_cta = e->n_dh_part - 1;
+  const int n_cta = tc_bwd_slices(e);
   const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072;
   static bool attr_set = false;
   if (!attr_set) {
