@@ -76,6 +76,8 @@ SYMBOLS = {
     "rec_head_logits": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int64]),
     "rec_train_step_supervised": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), _P]),
     "rec_train_step_q": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
+    "rec_train_step_supervised_host": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), _P]),
+    "rec_train_step_q_host": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
     "rec_record_floats": (C.c_int, [_P]),
     "rec_train_phase_a": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
     "rec_train_phase_b": (C.c_int, [_P, _P, C.c_int, _P]),

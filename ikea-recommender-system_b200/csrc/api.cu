@@ -128,12 +128,18 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->d_sc, float, 4);
   if (cudaMallocHost((void **)&e->h_sc, 4 * sizeof(float)) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMallocHost failed"); rec_destroy(e); return REC_ENOMEM; }
   {
-    int64_t *p64 = nullptr; float *pf = nullptr; uint8_t *p8 = nullptr;
-    ALLOC(e, p64, int64_t, mb * (2 * L + 3));
-    ALLOC(e, pf, float, mb);
-    ALLOC(e, p8, uint8_t, mb);
+    // engine-owned batch: ONE block [int64 s | s_next | a | true_len | true_next_len][float r][uint8 is_end] so
+    // that the host entry points fill it with a single H2D copy from the pinned mirror h_own
+    e->own_bytes = (size_t)mb * (2 * L + 3) * 8 + (size_t)mb * 4 + (size_t)mb;
+    ALLOC(e, e->own_block, uint8_t, (int64_t)e->own_bytes);
+    int64_t *p64 = (int64_t *)e->own_block;
     e->own.s = p64; e->own.s_next = p64 + mb * L; e->own.a = p64 + 2 * mb * L; e->own.true_len = p64 + 2 * mb * L + mb;
-    e->own.true_next_len = p64 + 2 * mb * L + 2 * mb; e->own.r = pf; e->own.is_end = p8;
+    e->own.true_next_len = p64 + 2 * mb * L + 2 * mb;
+    e->own.r = (float *)(p64 + mb * (2 * L + 3)); e->own.is_end = (uint8_t *)(e->own.r + mb);
+    if (cudaMallocHost((void **)&e->h_own, e->own_bytes) != cudaSuccess ||
+        cudaMallocHost((void **)&e->h_loss, 4 * sizeof(float)) != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "cudaMallocHost failed"); rec_destroy(e); return REC_ENOMEM;
+    }
   }
   e->use_graph = getenv("REC_NO_GRAPH") == nullptr;
   e->overlap = getenv("REC_NO_OVERLAP") == nullptr;
@@ -182,8 +188,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_carry, e->emb_tmeta, e->d_sc, (void *)e->own.s,
-                  (void *)e->own.r, (void *)e->own.is_end};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_carry, e->emb_tmeta, e->d_sc, (void *)e->own_block};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
@@ -194,6 +199,8 @@ extern "C" void rec_destroy(rec_engine *e) {
   for (int i = 0; i < e->n_graphs; ++i) if (e->graphs[i].exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graphs[i].exec);
   if (e->h_sc) cudaFreeHost(e->h_sc);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->h_own) cudaFreeHost(e->h_own);
+  if (e->h_loss) cudaFreeHost(e->h_loss);
   for (int i = 0; i < 2; ++i) {
     if (e->side[i]) { cudaStreamSynchronize(e->side[i]); cudaStreamDestroy(e->side[i]); }
     if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
@@ -323,17 +330,41 @@ static uint64_t fnv(uint64_t h, const void *p, size_t n) {
 // step to step lives in memory (engine-owned batch copy, Adam scalars), so one graph per (kind, main net, B,
 // hyper-parameters, output pointer) serves every later step.
 template <class Body>
+// `host`: b holds HOST pointers.  The batch is packed into the pinned mirror, the step starts with one H2D copy
+// of the block and ends with a D2H copy of `n_out` floats from `out` into h_loss -- both inside the graph.
 static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_batch *b, const rec_train_hparams *hp,
-                            float *out, Body body) {
-  if (!e->use_graph || e->timing || e->trace) {
-    int rc = upload_adam_scalars(e);
-    return rc ? rc : body(b);
-  }
+                            float *out, Body body, bool host = false, int n_out = 0) {
   rec_batch own = e->own;
   own.B = b->B;
   if (!b->r) { own.r = nullptr; own.s_next = nullptr; own.true_next_len = nullptr; own.is_end = nullptr; }
-  copy_batch_kernel<<<cdiv(b->B * (2 * e->cfg.state_size + 5), 256), 256, 0, e->stream>>>(*b, own, e->cfg.state_size);
-  REC_LAUNCH_CHECK(e);
+  if (host) {
+    const size_t B = (size_t)b->B, L = (size_t)e->cfg.state_size, mb = (size_t)e->cfg.max_batch;
+    int64_t *p64 = (int64_t *)e->h_own;
+    memcpy(p64, b->s, 8 * B * L);
+    memcpy(p64 + 2 * mb * L, b->a, 8 * B);
+    memcpy(p64 + 2 * mb * L + mb, b->true_len, 8 * B);
+    if (b->r) {
+      memcpy(p64 + mb * L, b->s_next, 8 * B * L);
+      memcpy(p64 + 2 * mb * L + 2 * mb, b->true_next_len, 8 * B);
+      float *pr = (float *)(p64 + mb * (2 * L + 3));
+      memcpy(pr, b->r, 4 * B);
+      memcpy((uint8_t *)(pr + mb), b->is_end, B);
+    }
+    kind |= 16;
+  }
+  auto run = [&](const rec_batch *bb) -> int {
+    int rc = upload_adam_scalars(e);
+    if (rc) return rc;
+    if (host) REC_CUDA(e, cudaMemcpyAsync(e->own_block, e->h_own, e->own_bytes, cudaMemcpyHostToDevice, e->stream));
+    if ((rc = body(bb))) return rc;
+    if (host) REC_CUDA(e, cudaMemcpyAsync(e->h_loss, out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, e->stream));
+    return REC_OK;
+  };
+  if (!e->use_graph || e->timing || e->trace) return run(host ? &own : b);
+  if (!host) {
+    copy_batch_kernel<<<cdiv(b->B * (2 * e->cfg.state_size + 5), 256), 256, 0, e->stream>>>(*b, own, e->cfg.state_size);
+    REC_LAUNCH_CHECK(e);
+  }
   uint64_t key = 1469598103934665603ull;
   key = fnv(key, &kind, sizeof(kind)); key = fnv(key, &main_net, sizeof(main_net)); key = fnv(key, &b->B, sizeof(int));
   key = fnv(key, hp, sizeof(*hp)); key = fnv(key, &out, sizeof(out));
@@ -351,8 +382,7 @@ static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_bat
   }
   if (!g->exec && g->seen < 1) {  // first sighting: run eagerly (also sets kernel attributes outside any capture)
     g->seen++;
-    int rc = upload_adam_scalars(e);
-    return rc ? rc : body(&own);
+    return run(&own);
   }
   if (!g->exec) {
     const int64_t l0 = e->launches;
@@ -361,8 +391,7 @@ static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_bat
     cudaStream_t user_stream = e->stream;
     REC_CUDA(e, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
     e->stream = e->cap_stream;
-    int rc = upload_adam_scalars(e);
-    if (!rc) rc = body(&own);
+    int rc = run(&own);
     cudaError_t st = cudaStreamEndCapture(e->cap_stream, &graph);
     e->stream = user_stream;
     if (rc || st != cudaSuccess || !graph) {
@@ -435,6 +464,30 @@ extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, cons
   return run_step_graphed(e, 0, 0, b, hp, loss_out, [&](const rec_batch *bb) {
     return supervised_body(e, bb, hp, loss_out, step_size, bc2_sqrt);
   });
+}
+
+static int finish_host_step(rec_engine *e, int rc, float *out, int n) {
+  if (rc) return rc;
+  REC_CUDA(e, cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n; ++i) out[i] = e->h_loss[i];
+  return REC_OK;
+}
+
+extern "C" int rec_train_step_supervised_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp, float *loss_host) {
+  int rc = check_net(e, 0, true);
+  if (rc) return rc;
+  if ((rc = check_batch(e, host_b, false))) return rc;
+  if (!hp || !loss_host) REC_FAIL(e, REC_EINVAL, "rec_train_step_supervised_host: null argument");
+  if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
+  float step_size, bc2_sqrt;
+  adam_scalars(e, 0, hp, &step_size, &bc2_sqrt);
+  float *out = e->loss_buf + 4;
+  rec_batch hb = *host_b;
+  hb.r = nullptr;  // supervised step: only s / a / true_len are read
+  rc = run_step_graphed(e, 0, 0, &hb, hp, out, [&](const rec_batch *bb) {
+    return supervised_body(e, bb, hp, out, step_size, bc2_sqrt);
+  }, true, 1);
+  return finish_host_step(e, rc, loss_host, 1);
 }
 
 // One fused SQN / SMORL step.  Branch structure (each branch is a stream; parallel branches under graph capture):
@@ -518,6 +571,32 @@ extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_tra
   return run_step_graphed(e, 1, main_net, b, hp, losses_out, [&](const rec_batch *bb) {
     return q_step_body(e, bb, hp, main_net, losses_out, step_size, bc2_sqrt);
   });
+}
+
+extern "C" int rec_train_step_q_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp, int main_net,
+                                     float *losses_host) {
+  if (!e) return REC_EINVAL;
+  if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q_host needs a twin-net engine with Q heads");
+  if (main_net != 0 && main_net != 1) REC_FAIL(e, REC_EINVAL, "main_net must be 0 or 1");
+  int rc = check_net(e, main_net, true);
+  if (rc) return rc;
+  if ((rc = check_net(e, 1 - main_net, false))) return rc;
+  if ((rc = check_batch(e, host_b, true))) return rc;
+  if (!hp || !losses_host) REC_FAIL(e, REC_EINVAL, "rec_train_step_q_host: null argument");
+  if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
+  const int n_q = e->cfg.n_heads - 1;
+  if (n_q == 3) {
+    if (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 || hp->div_dim < 1 ||
+        hp->topk_div > e->cfg.max_topk || hp->topk_nov > e->cfg.max_topk)
+      REC_FAIL(e, REC_EINVAL, "SMORL step needs div_emb, unpopular and 1 <= topk_div/topk_nov <= max_topk");
+  }
+  float step_size, bc2_sqrt;
+  adam_scalars(e, main_net, hp, &step_size, &bc2_sqrt);
+  float *out = e->loss_buf + 4;
+  rc = run_step_graphed(e, 1, main_net, host_b, hp, out, [&](const rec_batch *bb) {
+    return q_step_body(e, bb, hp, main_net, out, step_size, bc2_sqrt);
+  }, true, 2);
+  return finish_host_step(e, rc, losses_host, 2);
 }
 
 static int eval_kmax(const rec_eval_opts *o) {

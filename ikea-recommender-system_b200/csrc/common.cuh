@@ -79,7 +79,10 @@ struct rec_engine {
   cudaEvent_t ev_fork[2], ev_join[2], ev_mark[2];
   bool overlap;        // REC_NO_OVERLAP=1 serialises everything on the caller's stream
   bool side_dirty[2];  // work was issued on side[i] since its last join
-  rec_batch own;         // engine-owned copy of the caller's batch
+  rec_batch own;         // engine-owned copy of the caller's batch (pointers into own_block)
+  uint8_t *own_block, *h_own;  // device block and its pinned host mirror (host entry points)
+  size_t own_bytes;
+  float *h_loss;         // pinned: losses of the last host-entry step
   struct GraphEntry { uint64_t key; void *exec; int launches; int seen; } graphs[16];
   int n_graphs;
   long long *trace;      // optional device buffer for clock64 phase traces (debug)

@@ -52,6 +52,7 @@ class Engine:
                  n_heads, n_nets, use_packed_seq, frozen_pad_row, device, max_batch=256, max_topk=N.REC_MAX_TOPK,
                  vocab_lo=0, vocab_hi=None):
         self.lib = N.load_library()
+        self._host_losses = (C.c_float * 4)()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError(f"the B200 engine runs on CUDA devices only (got device={device!r}); "
@@ -175,6 +176,27 @@ class Engine:
                 self.lib.rec_train_step_q(self.handle, C.byref(batch), C.byref(hp), main_net, _ptr(losses_out)),
                 "rec_train_step_q")
 
+    # host entry points: the batch holds HOST pointers, losses come back as python floats (synchronous)
+    def train_step_supervised_host(self, batch: N.RecBatch, hp: N.RecTrainHparams) -> float:
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_step_supervised_host(self.handle, C.byref(batch), C.byref(hp), self._host_losses),
+                "rec_train_step_supervised_host")
+        return self._host_losses[0]
+
+    def train_step_q_host(self, batch: N.RecBatch, hp: N.RecTrainHparams, main_net: int):
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_step_q_host(self.handle, C.byref(batch), C.byref(hp), main_net, self._host_losses),
+                "rec_train_step_q_host")
+        return self._host_losses[0], self._host_losses[1]
+
+    @property
+    def host_batch_bytes(self) -> int:
+        """Bytes of the H2D copy a host-entry step makes (the engine's whole batch block)."""
+        mb, L = self.cfg["max_batch"], self.cfg["state_size"]
+        return mb * (2 * L + 3) * 8 + mb * 5
+
     def eval_batch(self, net_id, batch: N.RecBatch, opts: N.RecEvalOpts, acc: N.RecEvalAccum, topk_ids=None,
                    topk_scores=None):
         self.ensure_batch(batch.B)
@@ -217,6 +239,10 @@ class Engine:
 
     def set_tensor_cores(self, on: bool):
         self.lib.rec_set_tensor_cores(self.handle, int(on))
+
+    def set_cuda_graphs(self, on: bool):
+        """Replay the single-GPU train step as a CUDA graph (default on; REC_NO_GRAPH=1 disables)."""
+        self.lib.rec_set_cuda_graphs(self.handle, int(on))
 
     def launch_count(self):
         return int(self.lib.rec_launch_count(self.handle))

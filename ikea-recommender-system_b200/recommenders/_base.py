@@ -113,6 +113,17 @@ class NativeSessionNet(nn.Module):
     def _param_device(self):
         return self.embedding.weight.device
 
+    def _param_objects(self):
+        """The Parameter objects behind _net_tensors(), looked up once (module attribute access is slow)."""
+        g = self._trunk
+        sfx = ["", "_reverse"] if self._bidirectional else [""]
+        objs = [self.embedding.weight]
+        for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+            objs += [getattr(g, n + x) for x in sfx]
+        for h in self._head_modules():
+            objs += [h.weight, h.bias]
+        return objs
+
     def _attach(self, engine: Engine, net_id: int):
         self._engine, self._net_id = engine, net_id
 
@@ -295,7 +306,25 @@ class NativeTrainerBase:
             n.to(self.device)
         self._engine = None  # pointers changed
 
+    _FULL_CHECK_EVERY = 64
+
     def _ready(self, B) -> Engine:
+        # fast path (a few us): same storage behind every cached Parameter object as at the last full bind.
+        # A full re-derivation (module walk + rec_bind_params when anything moved) still runs every
+        # _FULL_CHECK_EVERY calls, so even replaced Parameter objects are picked up.
+        fast = getattr(self, "_fast_bind", None)
+        if fast is not None and self._engine is not None and B <= self._engine.cfg["max_batch"]:
+            objs, sig, opt_ids, calls = fast
+            if calls < self._FULL_CHECK_EVERY and opt_ids == tuple(id(n._opt_m) for n in self._nets) \
+                    and sig == tuple(p.data_ptr() for p in objs):
+                fast[3] = calls + 1
+                return self._engine
+        eng = self._ready_full(B)
+        objs = [p for n in self._nets for p in n._param_objects()]
+        self._fast_bind = [objs, tuple(p.data_ptr() for p in objs), tuple(id(n._opt_m) for n in self._nets), 0]
+        return eng
+
+    def _ready_full(self, B) -> Engine:
         dev = torch.device(self.device)
         if dev.type != "cuda":
             raise RuntimeError(f"device={self.device!r}: the native trainers run on a B200 only (no CPU fallback)")

@@ -3,7 +3,7 @@ trunk, concat(h_fwd, h_bwd) -> Dropout -> Linear(2H, V); supervised CE trainer."
 
 import torch
 
-from .._native_models import supervised_train_step
+from .._native_models import host_path, supervised_train_step, supervised_train_step_host
 from ..._base import NativeSessionNet, NativeTrainerBase
 
 
@@ -28,6 +28,8 @@ class BidirGRU4Rec_trainer(NativeTrainerBase):
         self._setup([self.gru_model], device, learning_rate)
 
     def train_step(self, s, a, true_len):
+        if host_path(self, s):
+            return supervised_train_step_host(self, s, a, true_len)
         return supervised_train_step(self, s, a, true_len).item()
 
     def train_step_async(self, s, a, true_len) -> torch.Tensor:

@@ -7,7 +7,7 @@ embedding_dim`), `state_dict()` keys (`embedding.weight`, `gru.*_l0`, `output.*`
 
 import torch
 
-from .._native_models import supervised_train_step
+from .._native_models import host_path, supervised_train_step, supervised_train_step_host
 from ..._base import NativeSessionNet, NativeTrainerBase
 
 
@@ -32,6 +32,8 @@ class GRU4Rec_trainer(NativeTrainerBase):
 
     def train_step(self, s, a, true_len):
         """One supervised step (reference :129-155); returns the batch-mean CE loss as a float."""
+        if host_path(self, s):
+            return supervised_train_step_host(self, s, a, true_len)
         return supervised_train_step(self, s, a, true_len).item()
 
     def train_step_async(self, s, a, true_len) -> torch.Tensor:

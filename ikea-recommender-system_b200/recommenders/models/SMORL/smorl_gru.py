@@ -8,7 +8,7 @@ oracle this class restores the novelty column (`topk_nov`, `nov_rew_sig`, commen
 import numpy as np
 import torch
 
-from .._native_models import q_train_step
+from .._native_models import host_path, q_train_step, q_train_step_host
 from ..._base import NativeSessionNet, NativeTrainerBase, make_hparams
 from ...evaluate.eval_protocol import _as_div_table, _unpopular_bitmap, _token_lut
 
@@ -76,6 +76,8 @@ class SMORL_trainer(NativeTrainerBase):
     def train_step(self, s, a, r_acc, s_next, true_len, true_next_len, is_end):
         """Scalarised double-Q step (reference :233-334, novelty column restored)."""
         self._ready(int(s.shape[0]))
+        if host_path(self, s):
+            return q_train_step_host(self, self._hp(), s, a, r_acc, s_next, true_len, true_next_len, is_end)
         out = q_train_step(self, self._hp(), s, a, r_acc, s_next, true_len, true_next_len, is_end).tolist()
         return out[0], out[1]
 

@@ -3,7 +3,7 @@ and a Q head, double-Q TD + cross-entropy, one Adam per net -- executed natively
 
 import torch
 
-from .._native_models import q_train_step
+from .._native_models import host_path, q_train_step, q_train_step_host
 from ..._base import NativeSessionNet, NativeTrainerBase, make_hparams
 
 
@@ -40,6 +40,8 @@ class SQN_trainer(NativeTrainerBase):
 
     def train_step(self, s, a, r, s_next, true_len, true_next_len, is_end):
         """Double-Q step (reference :183-254); returns (sup_loss, q_loss) as floats."""
+        if host_path(self, s):
+            return q_train_step_host(self, self._hp(), s, a, r, s_next, true_len, true_next_len, is_end)
         out = q_train_step(self, self._hp(), s, a, r, s_next, true_len, true_next_len, is_end).tolist()
         return out[0], out[1]
 

@@ -25,6 +25,45 @@ def supervised_train_step(trainer, s, a, true_len) -> torch.Tensor:
     return trainer._loss_dev[0]
 
 
+def _host(t, dtype):
+    """CPU tensor in the dtype/layout the C ABI reads (no copy in the common case)."""
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def host_path(trainer, s) -> bool:
+    """CPU tensors on an unsharded trainer go through the synchronous host entry points of the C ABI."""
+    return (not s.is_cuda) and trainer._shard is None
+
+
+def supervised_train_step_host(trainer, s, a, true_len) -> float:
+    """GRU4Rec_trainer / BidirGRU4Rec_trainer.train_step with CPU tensors: rec_train_step_supervised_host."""
+    net = trainer.gru_model
+    if net._family == "bidir" and net.training and net.dropout.p > 0:
+        raise NotImplementedError("BidirGRU4Rec dropout > 0 in training mode is not implemented natively yet")
+    B = int(s.shape[0])
+    eng = trainer._ready(B)
+    hs, ha, hl = _host(s, torch.int64), _host(a, torch.int64), _host(true_len, torch.int64)
+    trainer._stager.h2d_bytes = eng.host_batch_bytes
+    return eng.train_step_supervised_host(eng._batch(B, hs, ha, hl), make_hparams(trainer.learning_rate))
+
+
+def q_train_step_host(trainer, hp, s, a, r, s_next, true_len, true_next_len, is_end, main=None):
+    """SQN_trainer / SMORL_trainer.train_step with CPU tensors: rec_train_step_q_host -> (sup_loss, q_loss)."""
+    B = int(s.shape[0])
+    if main is None:
+        main = pick_main(trainer)
+    trainer.last_main = main + 1
+    eng = trainer._ready(B)
+    hs, ha, hl = _host(s, torch.int64), _host(a, torch.int64), _host(true_len, torch.int64)
+    hsn, hnl = _host(s_next, torch.int64), _host(true_next_len, torch.int64)
+    hr = _host(r, torch.float32).reshape(-1)  # (q6) rewards are cast to fp32
+    he = _host(is_end, torch.uint8)
+    trainer._stager.h2d_bytes = eng.host_batch_bytes
+    return eng.train_step_q_host(eng._batch(B, hs, ha, hl, hr, hsn, hnl, he), hp, main)
+
+
 def _sharded_step(trainer, hp, main, s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
     """Vocabulary-sharded step: ONE all-gather of the packed local batches, then phases A-D with their
     three collectives (records all-gather, Q all-reduce, dh all-reduce)."""

@@ -165,6 +165,14 @@ int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train
  * losses_out[0] = sup_loss, losses_out[1] = q_loss (device). */
 int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
                      float *losses_out);
+/* The same two steps called the way the reference's trainers are: every pointer of `host_b` is HOST memory
+ * (the CPU tensors a DataLoader yields; hp->div_emb / hp->unpopular stay device pointers) and the losses come
+ * back as host floats (the reference returns `loss.item()`).  Synchronous: the batch is packed into a pinned
+ * mirror, one H2D copy, the step and the D2H copy of the losses run as one CUDA graph, then the call waits. */
+int rec_train_step_supervised_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp,
+                                   float *loss_host);
+int rec_train_step_q_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp, int main_net,
+                          float *losses_host);
 
 /* Phase-split variant of the same step for vocabulary-sharded multi-GPU runs: every rank holds the full
  * (all-gathered) batch, replicas of embedding + GRU and rows [vocab_lo,vocab_hi) of every head; the caller

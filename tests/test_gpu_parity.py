@@ -531,3 +531,35 @@ def test_large_batch_chunked_tensor_core_backward(pkg, B):
         assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} loss")
     assert_state_close(t.gru_model.state_dict(), ref.gru_model.state_dict(), rtol=RTOL, atol=ATOL_P, outlier_frac=1e-3,
                        outlier_atol=0.02 * 0.01 * 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graphs", [True, False])
+def test_host_entry_and_device_entry_agree_bitwise(pkg, graphs):
+    """rec_train_step_q_host (CPU tensors in, floats out) and rec_train_step_q (device tensors) run the same
+    kernels in the same order: losses and every parameter must be identical, with and without graph replay."""
+    g = load_golden("sqn_64")
+    cfg, B, steps, packed, train_pad, layers = _meta(g)
+    batches = list(_batches(rows_from_golden(g), B, steps))
+
+    def run(device_inputs):
+        random.seed(7)
+        torch.manual_seed(7)
+        t = pkg.SQN_trainer(hidden_dim=cfg["hidden_dim"], embedding_dim=cfg["embedding_dim"], train_pad_embed=train_pad,
+                            use_packed_seq=packed, learning_rate=0.01, item_num=cfg["item_num"],
+                            state_size=cfg["state_size"], action_dim=cfg["action_dim"], gamma=0.5, gru_layers=layers,
+                            device=DEV)
+        t.send_to_device()
+        t._ready(B).set_cuda_graphs(graphs)
+        losses = []
+        for rep in range(3):                       # > 2 sightings of the same shape: eager, capture, replay
+            for b in batches:
+                bb = tuple(x.to(DEV) for x in b) if device_inputs else b
+                losses.append(tuple(t.train_step(*bb)))
+        return losses, {k: v.detach().cpu().clone() for k, v in t.DQN_1.state_dict().items()}
+
+    l_host, p_host = run(False)
+    l_dev, p_dev = run(True)
+    assert l_host == l_dev
+    for k in p_host:
+        assert torch.equal(p_host[k], p_dev[k]), k
