@@ -143,16 +143,24 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   }
   e->use_graph = getenv("REC_NO_GRAPH") == nullptr;
   e->overlap = getenv("REC_NO_OVERLAP") == nullptr;
-  for (int i = 0; i < 2; ++i) {
-    e->side_dirty[i] = false;
-    if (cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_mark[i], cudaEventDisableTiming) != cudaSuccess)
-      e->overlap = false;
-  }
+  e->tl_on = getenv("REC_TIMELINE") != nullptr;
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  {
+    // priorities (honoured between graph branches): main/capture stream > side 0/1 (supervised-head backward,
+    // embedding chain) > side 2 (HBM-bound Q-head sweep, which must not push critical-path CTAs off the SMs)
+    const int prio_mid = (prio_least + prio_greatest) / 2;
+    const int prio[3] = {prio_mid, prio_mid, prio_least};
+    for (int i = 0; i < 3; ++i) {
+      e->side_dirty[i] = false;
+      if (cudaStreamCreateWithPriority(&e->side[i], cudaStreamNonBlocking, prio[i]) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
+        e->overlap = false;
+    }
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventCreateWithFlags(&e->ev_mark[i], cudaEventDisableTiming) != cudaSuccess) e->overlap = false;
+  }
   // the capture stream (main branch of the graph) outranks the side branch: the one-CTA-per-SM tensor-core
   // kernels must get their SM slots before the streaming kernels fill the machine
   if (cudaStreamCreateWithPriority(&e->cap_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) e->use_graph = false;
@@ -201,12 +209,12 @@ extern "C" void rec_destroy(rec_engine *e) {
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->h_own) cudaFreeHost(e->h_own);
   if (e->h_loss) cudaFreeHost(e->h_loss);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     if (e->side[i]) { cudaStreamSynchronize(e->side[i]); cudaStreamDestroy(e->side[i]); }
     if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
-    if (e->ev_mark[i]) cudaEventDestroy(e->ev_mark[i]);
   }
+  for (int i = 0; i < 4; ++i) if (e->ev_mark[i]) cudaEventDestroy(e->ev_mark[i]);
   free(e);
 }
 
@@ -320,6 +328,34 @@ __global__ void copy_batch_kernel(rec_batch src, rec_batch dst, int L) {
   }
 }
 
+void rec_timeline_record(rec_engine *e, const char *file, int line) {
+  if (e->tl_n >= 96) return;
+  rec_engine::TlEntry &t = e->tl[e->tl_n++];
+  if (!t.ev) cudaEventCreate(&t.ev);
+  t.file = file; t.line = line;
+  t.stream = e->stream == e->side[0] ? 1 : e->stream == e->side[1] ? 2 : 0;
+  cudaEventRecord(t.ev, e->stream);
+}
+
+static void timeline_begin(rec_engine *e) {
+  if (!e->tl_on) return;
+  e->tl_n = 0;
+  rec_timeline_record(e, "step-start", 0);
+}
+
+static void timeline_dump(rec_engine *e) {
+  if (!e->tl_on) return;
+  cudaDeviceSynchronize();
+  if (++e->tl_steps % 50 != 0) return;
+  fprintf(stderr, "[timeline] step %d\n", e->tl_steps);
+  for (int i = 1; i < e->tl_n; ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->tl[0].ev, e->tl[i].ev);
+    const char *f = strrchr(e->tl[i].file, '/');
+    fprintf(stderr, "[timeline]   end %7.1f us  stream %d  %s:%d\n", ms * 1e3, e->tl[i].stream, f ? f + 1 : e->tl[i].file, e->tl[i].line);
+  }
+}
+
 static uint64_t fnv(uint64_t h, const void *p, size_t n) {
   const unsigned char *c = (const unsigned char *)p;
   for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
@@ -360,7 +396,12 @@ static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_bat
     if (host) REC_CUDA(e, cudaMemcpyAsync(e->h_loss, out, sizeof(float) * n_out, cudaMemcpyDeviceToHost, e->stream));
     return REC_OK;
   };
-  if (!e->use_graph || e->timing || e->trace) return run(host ? &own : b);
+  if (!e->use_graph || e->timing || e->trace || e->tl_on) {
+    timeline_begin(e);
+    int rc = run(host ? &own : b);
+    timeline_dump(e);
+    return rc;
+  }
   if (!host) {
     copy_batch_kernel<<<cdiv(b->B * (2 * e->cfg.state_size + 5), 256), 256, 0, e->stream>>>(*b, own, e->cfg.state_size);
     REC_LAUNCH_CHECK(e);
@@ -491,11 +532,13 @@ extern "C" int rec_train_step_supervised_host(rec_engine *e, const rec_batch *ho
 }
 
 // One fused SQN / SMORL step.  Branch structure (each branch is a stream; parallel branches under graph capture):
-//   main   : GRU fwd -> supervised stats -> [mark 0] -> greedy-action stats -> Q row dots -> TD / losses -> q_dh
-//            -> [mark 1] -> Q-head gradient rows + streaming Adam                                  (HBM-bound)
-//   side 0 : (after mark 0) supervised-head backward + Adam (tensor cores, latency-bound)
-//            -> (after mark 1) dh reduce -> GRU backward / weight update
-//   side 1 : token ordering (start of step), duplicate sums, embedding-table Adam               (see trunk_backward)
+//   main   : GRU fwd -> supervised stats -> [mark 0] -> greedy-action stats -> fused per-row Q kernel -> [mark 1]
+//            -> (after mark 2) dh reduce -> GRU backward / weight update            (critical path, top priority)
+//   side 0 : (after mark 0) supervised-head backward + Adam (tensor cores, latency-bound) -> [mark 2]
+//   side 1 : token ordering (start of step), duplicate sums, embedding-table Adam    (see trunk_backward)
+//   side 2 : (after mark 1) losses, Q-head gradient rows -> (after mark 2) streaming Adam sweep of the Q heads.
+//            The sweep saturates the HBM: it starts when the supervised-head kernel is done and shares the machine
+//            with the small GRU-backward kernels, at the lowest priority.
 static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out,
                        float step_size, float bc2_sqrt) {
   int rc;
@@ -529,24 +572,24 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
   {  // issued after the greedy-action statistics so that those get the SMs first
     SideScope side(e, 0, 0);
     if ((rc = launch_sup_head_bwd(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
+    side_mark(e, 2);  // supervised head done: dh slices final, HBM free for the Q-head sweep
   }
-  if ((rc = launch_head_merge(e, e->part, n_split, B, 0, false, true))) return rc;
-  // Q(s,a) on main, Q_boot(s',a*) on boot: row gather-dots
-  if ((rc = launch_row_dots(e, main_net, e->h_state[0], b->a, nullptr, B, 1, n_q, e->q_sa))) return rc;
-  if ((rc = launch_row_dots(e, boot, e->h_state[2], nullptr, e->astar, B, 1, n_q, e->q_boot))) return rc;
+  // a*, Q(s,a), Q_boot(s',a*), rewards, TD target, dq, Q-head dh slice: one launch
   const float alpha_eff = (n_q == 3) ? hp->alpha : 1.f;
-  if ((rc = launch_td(e, b, hp, n_q, alpha_eff, extra(e).q_loss_rows))) return rc;
-  if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
-  REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
-  if ((rc = launch_q_dh(e, main_net, b, B))) return rc;
-  side_mark(e, 1);  // every dh slice of the Q heads is written
+  if ((rc = launch_q_rows_fused(e, main_net, b, hp, n_split, alpha_eff, extra(e).q_loss_rows))) return rc;
+  side_mark(e, 1);
   {
-    SideScope side(e, 0, 1);
-    if ((rc = launch_dh_reduce(e, B))) return rc;
-    if ((rc = trunk_backward(e, main_net, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp, true))) return rc;
+    SideScope side(e, 2, 1);
+    if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
+    REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    static const int sweep_mark = getenv("REC_SWEEP_EARLY") ? -1 : 2;
+    if ((rc = launch_q_heads_update(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, sweep_mark))) return rc;
   }
-  if ((rc = launch_q_heads_update(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp))) return rc;
+  side_wait_mark(e, 2);
+  if ((rc = launch_dh_reduce(e, B))) return rc;
+  if ((rc = trunk_backward(e, main_net, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp, true))) return rc;
   side_join(e, 0);
+  side_join(e, 2);
   return REC_OK;
 }
 
@@ -667,8 +710,7 @@ extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_tr
   if (main_net < 0 || main_net >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "main_net out of range");
   int rc = check_net(e, main_net, true);
   if (rc) return rc;
-  side_join(e, 0);  // a previous step abandoned after phase C may still have its Q-head sweep in flight
-  side_join(e, 1);
+  for (int i = 0; i < 3; ++i) side_join(e, i);  // a step abandoned after phase C may still have side work in flight
   if ((rc = check_batch(e, b, n_q > 0))) return rc;
   if (n_q > 0 && e->cfg.n_nets != 2) REC_FAIL(e, REC_EINVAL, "Q heads need a twin-net engine");
   if (n_q == 3 && (!hp->div_emb || !hp->unpopular || hp->topk_div < 1 || hp->topk_nov < 1 ||

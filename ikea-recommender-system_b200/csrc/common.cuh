@@ -75,10 +75,13 @@ struct rec_engine {
   cudaStream_t cap_stream;  // private stream used only while capturing (the caller's stream may be the legacy default)
   // Independent branches of the step (Q-head Adam sweep next to the supervised-head kernel, embedding chain
   // next to the GRU weight update) run on a second stream; under graph capture they become parallel branches.
-  cudaStream_t side[2];
-  cudaEvent_t ev_fork[2], ev_join[2], ev_mark[2];
+  cudaStream_t side[3];
+  cudaEvent_t ev_fork[3], ev_join[3], ev_mark[4];
   bool overlap;        // REC_NO_OVERLAP=1 serialises everything on the caller's stream
-  bool side_dirty[2];  // work was issued on side[i] since its last join
+  bool tl_on;          // REC_TIMELINE=1
+  int tl_n, tl_steps;
+  struct TlEntry { cudaEvent_t ev; const char *file; int line; int stream; } tl[96];
+  bool side_dirty[3];  // work was issued on side[i] since its last join
   rec_batch own;         // engine-owned copy of the caller's batch (pointers into own_block)
   uint8_t *own_block, *h_own;  // device block and its pinned host mirror (host entry points)
   size_t own_bytes;
@@ -107,9 +110,13 @@ struct rec_engine {
     }                                                                                     \
   } while (0)
 
+// REC_TIMELINE=1 (debug, eager mode): an event after every launch; rec_timeline_dump prints when each kernel
+// finished relative to the start of the step and on which stream.
+void rec_timeline_record(rec_engine *e, const char *file, int line);
 #define REC_LAUNCH_CHECK(e)                                                               \
   do {                                                                                    \
     (e)->launches++;                                                                      \
+    if ((e)->tl_on) rec_timeline_record((e), __FILE__, __LINE__);                         \
     cudaError_t _st = cudaGetLastError();                                                 \
     if (_st != cudaSuccess) {                                                             \
       snprintf((e)->err, sizeof((e)->err), "kernel launch failed: %s (%s:%d)",            \
@@ -170,8 +177,9 @@ int launch_gru_transpose(rec_engine *e, int net_id);
 int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
                             float step_size, float bc2_sqrt, const rec_train_hparams *hp, int stages = 7);
 
+// wait_mark >= 0: the streaming sweep (not the gradient-row kernel) additionally waits for side_mark(e, wait_mark)
 int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
-                        float bc2_sqrt, const rec_train_hparams *hp);
+                        float bc2_sqrt, const rec_train_hparams *hp, int wait_mark = -1);
 
 // Launches issued while a SideScope is alive go to side stream `idx`, ordered after everything issued so far on
 // the current stream -- or, with `mark` >= 0, after the point remembered by side_mark(e, mark).  Scopes nest
@@ -195,6 +203,9 @@ struct SideScope {
   }
   ~SideScope() { e->stream = main; }
 };
+static inline void side_wait_mark(rec_engine *e, int k) {
+  if (side_enabled(e)) cudaStreamWaitEvent(e->stream, e->ev_mark[k], 0);
+}
 static inline void side_join(rec_engine *e, int idx) {
   if (!e->side_dirty[idx]) return;
   cudaEventRecord(e->ev_join[idx], e->side[idx]);
@@ -232,5 +243,7 @@ int launch_q_dh(rec_engine *e, int net_id, const rec_batch *b, int B);
 int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                         float bc2_sqrt, const rec_train_hparams *hp, float inv_B);
 int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
-                          float bc2_sqrt, const rec_train_hparams *hp);
+                          float bc2_sqrt, const rec_train_hparams *hp, int wait_mark = -1);
 int launch_dh_reduce(rec_engine *e, int B);
+int launch_q_rows_fused(rec_engine *e, int main_net, const rec_batch *b, const rec_train_hparams *hp, int n_split,
+                        float alpha_eff, float *q_loss_rows);

@@ -228,17 +228,25 @@ static int launch_adam_stream_set(rec_engine *e, const AdamStreamSet &ts, int n_
                                   const rec_train_hparams *hp, float step_size, float bc2_sqrt) {
   const int64_t n4 = rows * (D / 4);
   if (n4 >= (int64_t)1 << 31) REC_FAIL(e, REC_EINVAL, "adam_stream: tensor too large (%lld float4)", (long long)n4);
-  constexpr int UNROLL = 2;
+  // The sweep is persistent (grid-stride) with a SMALL resident footprint: `ctas` CTAs per SM keep enough bytes in
+  // flight to saturate the HBM (UNROLL x 48 B per thread) while leaving most warp slots and registers of every
+  // SM to the latency-bound kernels of the other graph branches, which would otherwise starve behind it.
+  static const int ctas = getenv("REC_SWEEP_CTAS") ? atoi(getenv("REC_SWEEP_CTAS")) : 2;
+  static const int unroll = getenv("REC_SWEEP_UNROLL") ? atoi(getenv("REC_SWEEP_UNROLL")) : 2;
   const int D4 = D / 4;
   int shift = -1;
   if ((D4 & (D4 - 1)) == 0) { shift = 0; while ((1 << shift) < D4) ++shift; }
-  int64_t want = cdiv64(n4, 256 * UNROLL);
-  int per = (e->sm_count * 16) / n_tensors;
+  int64_t want = cdiv64(n4, 256 * unroll);
+  int per = (e->sm_count * ctas) / n_tensors;
   int blocks = (int)(want < (int64_t)per ? want : (int64_t)per);
   if (blocks < 1) blocks = 1;
   dim3 grid(blocks, n_tensors);
-  adam_stream_kernel<UNROLL><<<grid, 256, 0, e->stream>>>(ts, slot_of_row, grad_stride / 4, (uint32_t)n4, D4, shift, hp->beta1,
-                                                          hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt, e->d_sc);
+  if (unroll == 4)
+    adam_stream_kernel<4><<<grid, 256, 0, e->stream>>>(ts, slot_of_row, grad_stride / 4, (uint32_t)n4, D4, shift, hp->beta1,
+                                                       hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt, e->d_sc);
+  else
+    adam_stream_kernel<2><<<grid, 256, 0, e->stream>>>(ts, slot_of_row, grad_stride / 4, (uint32_t)n4, D4, shift, hp->beta1,
+                                                       hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt, e->d_sc);
   REC_LAUNCH_CHECK(e);
   if (with_bias) {
     dim3 g2(cdiv((int)rows, 256), n_tensors);
@@ -328,12 +336,13 @@ __global__ void q_slot_reset_kernel(const int64_t *__restrict__ a, int B, int Vl
 
 // Adam on every Q head (heads 1..n_q) of net `net_id`: streaming sweep with row-sparse gradients.
 int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
-                        float bc2_sqrt, const rec_train_hparams *hp) {
+                        float bc2_sqrt, const rec_train_hparams *hp, int wait_mark) {
   const int n_q = e->cfg.n_heads - 1, D = e->D;
   const rec_net_params &p = e->nets[net_id].p;
   q_grad_rows_kernel<<<cdiv(B * n_q, 8), 256, 0, e->stream>>>(b->a, e->dq, h, B, D, n_q, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
                                                        e->q_bgrad, e->q_slot);
   REC_LAUNCH_CHECK(e);
+  if (wait_mark >= 0) side_wait_mark(e, wait_mark);
   {
     AdamStreamSet ts = {};
     for (int j = 0; j < n_q; ++j) {

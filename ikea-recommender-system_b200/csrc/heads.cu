@@ -11,6 +11,7 @@
 //                          dW/db tile + dh partial, and applies Adam to the tile in the same pass
 //                          (W, m, v are read once and written once per step: 24 B/param).
 #include "common.cuh"
+#include "rewards.cuh"
 
 #define TM 64   // batch rows per tile
 #define TN 64   // vocabulary rows per tile
@@ -382,6 +383,105 @@ __global__ void __launch_bounds__(256) row_dots_kernel(HeadPtrs hp, const float 
   if (lane == 0) out[(int64_t)b * out_stride + j] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Everything between the greedy-action statistics and the backward passes, for one row per warp:
+//   merge of the argmax records -> a*;  Q(s,a) on the main net, Q_boot(s',a*) on the bootstrap net;
+//   SMORL rewards;  TD target, dq, per-row Q loss;  dh contribution of the Q heads.
+// Same arithmetic, in the same order, as head_merge_kernel(has_arg) + row_dots_kernel x2 + td_kernel +
+// q_dh_kernel, which stay in use for the phase-split (vocabulary-sharded) step.  One launch instead of
+// five on the critical path of the single-GPU step.
+// ------------------------------------------------------------------------------------------------
+struct QRowArgs {
+  const float *part; int part_stride, n_split;
+  HeadPtrs main_heads, boot_heads;
+  const float *h_main, *h_boot;      // [B, D] final states main(s), boot(s')
+  const int64_t *a, *s, *div_lens;
+  const float *r_acc; const uint8_t *is_end;
+  const int32_t *row_ids;            // merged top-k ids of the supervised logits (SMORL rewards)
+  int B, D, L, N, Vloc, vocab_lo, n_q;
+  float alpha_eff;
+  float *row_stats; int32_t *astar;
+  float *q_sa, *q_boot, *dq, *q_loss_rows, *rewards, *dh_slice;
+};
+
+__global__ void __launch_bounds__(256) q_rows_fused_kernel(QRowArgs A, rec_train_hparams hp) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= A.B) return;
+  const int D = A.D, n_q = A.n_q;
+  // (1) greedy action: merge of the per-split argmax records
+  float bv = REC_NEG_INF;
+  int bi = 0x7fffffff;
+  for (int sp = lane; sp < A.n_split; sp += 32) {
+    const float *o = A.part + ((int64_t)sp * A.B + b) * A.part_stride;
+    float v = o[3];
+    int i = __float_as_int(o[4]);
+    if (better(v, i, bv, bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) {
+    float *rs = A.row_stats + (int64_t)b * ROW_STRIDE;
+    rs[2] = bv; rs[3] = __int_as_float(bi); A.astar[b] = bi;
+  }
+  // (2) Q(s,a) and Q_boot(s',a*)
+  const int64_t loc_a = A.a[b] - A.vocab_lo, loc_s = (int64_t)bi - A.vocab_lo;
+  float qsa[3] = {0.f, 0.f, 0.f}, qbt[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < n_q; ++j) {
+    if (loc_a >= 0 && loc_a < A.Vloc) {
+      const float *wr = A.main_heads.w[1 + j] + loc_a * D, *hr = A.h_main + (int64_t)b * D;
+      float acc = 0.f;
+      for (int k = lane; k < D; k += 32) acc = fmaf(hr[k], __ldg(wr + k), acc);
+      qsa[j] = warp_sum(acc) + __ldg(A.main_heads.b[1 + j] + loc_a);
+    }
+    if (loc_s >= 0 && loc_s < A.Vloc) {
+      const float *wr = A.boot_heads.w[1 + j] + loc_s * D, *hr = A.h_boot + (int64_t)b * D;
+      float acc = 0.f;
+      for (int k = lane; k < D; k += 32) acc = fmaf(hr[k], __ldg(wr + k), acc);
+      qbt[j] = warp_sum(acc) + __ldg(A.boot_heads.b[1 + j] + loc_s);
+    }
+  }
+  // (3) rewards
+  float r[3] = {A.r_acc[b], 0.f, 0.f};
+  if (n_q == 3) {
+    const int32_t *ids = A.row_ids + (int64_t)b * REC_MAX_TOPK;
+    int last = last_action_of(A.s, A.div_lens, b, A.L, A.N, hp.pad_pos_end);
+    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, A.N, lane);
+    float nov = 0.f;
+    for (int j = 0; j < hp.topk_nov; ++j) nov += hp.unpopular[ids[j]] ? hp.nov_reward : 0.f;
+    r[2] = nov / (float)hp.topk_nov;
+  }
+  // (4) TD target, dq, per-row loss (every lane computes the same scalars)
+  const bool end = A.is_end[b] != 0;
+  float loss = 0.f, dq[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < n_q; ++j) {
+    float boot = end ? 0.f : qbt[j];
+    float y = r[j] + hp.gamma * boot;
+    float diff = y - qsa[j];
+    float w = (n_q == 3) ? hp.q_weights[j] : 1.f;
+    loss += diff * diff * w;
+    dq[j] = A.alpha_eff * w * 2.f * (-diff) / (float)A.B;
+  }
+  if (lane == 0) {
+    for (int j = 0; j < n_q; ++j) {
+      A.q_sa[b * 3 + j] = qsa[j]; A.q_boot[b * 3 + j] = qbt[j];
+      A.dq[b * 3 + j] = dq[j]; A.rewards[b * 3 + j] = r[j];
+    }
+    A.q_loss_rows[b] = loss;
+  }
+  // (5) dh contribution of the Q heads (before Adam touches their weights)
+  for (int k = lane; k < D; k += 32) {
+    float acc = 0.f;
+    if (loc_a >= 0 && loc_a < A.Vloc)
+      for (int j = 0; j < n_q; ++j) acc = fmaf(dq[j], __ldg(A.main_heads.w[1 + j] + loc_a * D + k), acc);
+    A.dh_slice[(int64_t)b * D + k] = acc;
+  }
+}
+
 // dh_q[b, :] = sum_j dq[b, j] * W_{1+j}[a_b]  (Q heads only touch row a_b) -- runs BEFORE Adam.
 __global__ void __launch_bounds__(256) q_dh_kernel(HeadPtrs hp, const int64_t *__restrict__ a,
                                                    const float *__restrict__ dq, int B, int D, int Vloc, int vocab_lo,
@@ -664,6 +764,26 @@ int head_bwd_dense_slices(const rec_engine *e, int B) {
   return n_cta > n_tiles ? n_tiles : n_cta;
 }
 
+// Fused per-row Q path of the single-GPU step (see q_rows_fused_kernel).
+int launch_q_rows_fused(rec_engine *e, int main_net, const rec_batch *b, const rec_train_hparams *hp, int n_split,
+                        float alpha_eff, float *q_loss_rows) {
+  const int B = b->B;
+  QRowArgs A;
+  A.part = e->part; A.part_stride = e->part_stride; A.n_split = n_split;
+  A.main_heads = head_ptrs(e, main_net); A.boot_heads = head_ptrs(e, 1 - main_net);
+  A.h_main = e->h_state[0]; A.h_boot = e->h_state[2];
+  A.a = b->a; A.s = b->s; A.div_lens = b->true_next_len;  // (q2) the reference indexes s with true_next_len
+  A.r_acc = b->r; A.is_end = b->is_end; A.row_ids = e->row_ids;
+  A.B = B; A.D = e->D; A.L = e->cfg.state_size; A.N = e->cfg.item_num; A.Vloc = e->Vloc; A.vocab_lo = e->cfg.vocab_lo;
+  A.n_q = e->cfg.n_heads - 1; A.alpha_eff = alpha_eff;
+  A.row_stats = e->row_stats; A.astar = e->astar;
+  A.q_sa = e->q_sa; A.q_boot = e->q_boot; A.dq = e->dq; A.q_loss_rows = q_loss_rows; A.rewards = e->rewards;
+  A.dh_slice = e->dh_part + (int64_t)head_bwd_dense_slices(e, B) * B * e->D;
+  q_rows_fused_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(A, *hp);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
 // Q heads: dh contribution of rows a_b; must run before Adam touches the Q-head weights.
 int launch_q_dh(rec_engine *e, int net_id, const rec_batch *b, int B) {
   const int n_q = e->cfg.n_heads - 1;
@@ -709,10 +829,10 @@ int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_bat
 
 // Row-sparse gradients of the Q heads + dense Adam: pure HBM streaming (24 B/param).
 int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
-                          float bc2_sqrt, const rec_train_hparams *hp) {
+                          float bc2_sqrt, const rec_train_hparams *hp, int wait_mark) {
   if (e->cfg.n_heads < 2) return REC_OK;
   if (e->timing) cudaEventRecord(e->ev[6], e->stream);
-  int rc = launch_q_heads_adam(e, net_id, h, b, B, step_size, bc2_sqrt, hp);
+  int rc = launch_q_heads_adam(e, net_id, h, b, B, step_size, bc2_sqrt, hp, wait_mark);
   if (rc) return rc;
   if (e->timing) cudaEventRecord(e->ev[7], e->stream);
   return REC_OK;
