@@ -245,9 +245,18 @@ def run_native(args, wl):
     parts = {"q_heads_adam_stream (3 launches of adam_stream_kernel, row-sparse grads)": rl(ab["q_heads"], avg[3]),
              "head_bwd_adam_tc_kernel (supervised head: tcgen05 logits/dW/dh + fused Adam)": rl(ab["sup_head"], avg[0]),
              "adam_stream_kernel (embedding table)": rl(ab["emb_adam"], avg[2])}
+    # DRAM traffic per launch from the committed ncu --set full capture (cfg2 only; null elsewhere)
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    if wl["name"].startswith("cfg2") and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        tkeys = ["q_heads_adam_stream", "head_bwd_adam_tc_kernel", "adam_stream_kernel_embedding"]
+        for k, tk in zip(parts, tkeys):
+            parts[k]["traffic"] = tj[tk]["dram_bytes_read"] + tj[tk]["dram_bytes_write"]
     dom = max(parts, key=lambda k: parts[k]["kernel_ms"])
+    traffic = parts[dom].get("traffic")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": parts[dom]["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": parts[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": parts[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": parts[dom]["algorithmic_bytes_per_launch"],
                 "kernel_ms": parts[dom]["kernel_ms"], "kernel_share_of_step": parts[dom]["kernel_share_of_step"],
                 "kernels": parts,
