@@ -92,6 +92,7 @@ SYMBOLS = {
     "rec_eval_merge": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecEvalOpts), _P, C.c_int,
                                  C.POINTER(RecEvalAccum), _P, _P]),
     "rec_set_cuda_graphs": (C.c_int, [_P, C.c_int]),
+    "rec_set_stream": (C.c_int, [_P, _P]),
     "rec_set_tensor_cores": (C.c_int, [_P, C.c_int]),
     "rec_launch_count": (C.c_int64, [_P]),
     "rec_enable_kernel_timing": (C.c_int, [_P, C.c_int]),

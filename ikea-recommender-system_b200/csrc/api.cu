@@ -126,6 +126,8 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, extra(e).q_loss_rows, float, mb);
   ALLOC(e, e->summary, float, mb * e->part_stride);
   ALLOC(e, e->d_sc, float, 4);
+  ALLOC(e, e->d_step, long long, REC_MAX_NETS);
+  cudaMemsetAsync(e->d_step, 0, sizeof(long long) * REC_MAX_NETS, e->stream);
   if (cudaMallocHost((void **)&e->h_sc, 4 * sizeof(float)) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMallocHost failed"); rec_destroy(e); return REC_ENOMEM; }
   {
     // engine-owned batch: ONE block [int64 s | s_next | a | true_len | true_next_len][float r][uint8 is_end] so
@@ -196,7 +198,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_carry, e->emb_tmeta, e->d_sc, (void *)e->own_block};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
@@ -240,14 +242,30 @@ extern "C" int rec_bind_params(rec_engine *e, int net_id, const rec_net_params *
   return launch_gru_transpose(e, net_id);
 }
 
+__global__ void set_step_kernel(long long *d_step, long long v) { *d_step = v; }
+
 extern "C" int rec_set_adam_step(rec_engine *e, int net_id, int64_t step) {
   if (!e || net_id < 0 || net_id >= e->cfg.n_nets) return REC_EINVAL;
   e->nets[net_id].adam_step = step;
+  set_step_kernel<<<1, 1, 0, e->stream>>>(e->d_step + net_id, (long long)step);
+  REC_LAUNCH_CHECK(e);
   return REC_OK;
 }
 extern "C" int64_t rec_get_adam_step(const rec_engine *e, int net_id) {
   if (!e || net_id < 0 || net_id >= e->cfg.n_nets) return -1;
-  return e->nets[net_id].adam_step;
+  // the device counter is authoritative (steps replayed from a caller-captured graph never pass through the host)
+  long long t = 0;
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess ||
+      cudaMemcpy(&t, e->d_step + net_id, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  const_cast<rec_engine *>(e)->nets[net_id].adam_step = t;
+  return t;
+}
+
+extern "C" int rec_set_stream(rec_engine *e, void *stream) {
+  if (!e) return REC_EINVAL;
+  e->stream = (cudaStream_t)stream;
+  return REC_OK;
 }
 
 extern "C" int rec_set_cuda_graphs(rec_engine *e, int on) {
@@ -270,8 +288,11 @@ extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) { if (!e) return 
 extern "C" float rec_last_kernel_ms(rec_engine *e, int which) {
   if (!e || which < 0 || which > 3) return -1.f;
   float ms = -1.f;
-  if (cudaEventSynchronize(e->ev[2 * which + 1]) != cudaSuccess) return -1.f;
-  if (cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) return -1.f;
+  if (cudaEventSynchronize(e->ev[2 * which + 1]) != cudaSuccess ||
+      cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) {
+    cudaGetLastError();  // events never recorded (kernel did not run in timing mode): not an engine error
+    return -1.f;
+  }
   return ms;
 }
 
@@ -296,20 +317,30 @@ extern "C" int rec_head_logits(rec_engine *e, int net_id, int head, const float 
   return launch_head_logits(e, net_id, head, h, B, logits, ld);
 }
 
+// torch.optim.Adam (single-tensor/foreach, capturable=False) computes its bias corrections as python doubles:
+//   step_size = lr / (1 - beta1^t),  denom = sqrt(v) / sqrt(1 - beta2^t) + eps.
+// The step counter lives in DEVICE memory and the scalars are produced by a one-thread kernel that is the first
+// node of every step: a replayed graph stays valid across steps, and steps may be queued asynchronously without a
+// host buffer being overwritten before the GPU has read it.  The host mirrors the counter for rec_get_adam_step.
+__global__ void adam_step_kernel(long long *__restrict__ d_step, float lr, float beta1, float beta2, float *__restrict__ sc) {
+  const long long t = ++(*d_step);
+  const double bc1 = 1.0 - pow((double)beta1, (double)t);
+  const double bc2 = 1.0 - pow((double)beta2, (double)t);
+  sc[0] = (float)((double)lr / bc1);
+  sc[1] = __fdiv_rn(1.f, (float)sqrt(bc2));
+}
+
 static void adam_scalars(rec_engine *e, int net_id, const rec_train_hparams *hp, float *step_size, float *bc2_sqrt) {
-  // torch.optim.Adam (single-tensor/foreach, capturable=False): python-double scalars
-  int64_t t = ++e->nets[net_id].adam_step;
+  int64_t t = ++e->nets[net_id].adam_step;   // host mirror; same values as the kernel (by-value fallbacks only)
   double bc1 = 1.0 - pow((double)hp->beta1, (double)t);
   double bc2 = 1.0 - pow((double)hp->beta2, (double)t);
   *step_size = (float)((double)hp->lr / bc1);
   *bc2_sqrt = (float)sqrt(bc2);
-  // the kernels read the scalars from device memory (so that a captured CUDA graph stays valid across steps)
-  e->h_sc[0] = *step_size;
-  e->h_sc[1] = 1.f / *bc2_sqrt;
 }
 
-static int upload_adam_scalars(rec_engine *e) {
-  REC_CUDA(e, cudaMemcpyAsync(e->d_sc, e->h_sc, 2 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+static int upload_adam_scalars(rec_engine *e, int net_id, const rec_train_hparams *hp) {
+  adam_step_kernel<<<1, 1, 0, e->stream>>>(e->d_step + net_id, hp->lr, hp->beta1, hp->beta2, e->d_sc);
+  REC_LAUNCH_CHECK(e);
   return REC_OK;
 }
 
@@ -389,7 +420,7 @@ static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_bat
     kind |= 16;
   }
   auto run = [&](const rec_batch *bb) -> int {
-    int rc = upload_adam_scalars(e);
+    int rc = upload_adam_scalars(e, main_net, hp);
     if (rc) return rc;
     if (host) REC_CUDA(e, cudaMemcpyAsync(e->own_block, e->h_own, e->own_bytes, cudaMemcpyHostToDevice, e->stream));
     if ((rc = body(bb))) return rc;
@@ -771,7 +802,7 @@ extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, flo
   if ((rc = launch_loss_reduce(e, B, n_q > 0 ? extra(e).q_loss_rows : nullptr, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, (n_q > 0 ? 2 : 1) * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
   adam_scalars(e, main_net, hp, &e->cur_step_size, &e->cur_bc2_sqrt);
-  if ((rc = upload_adam_scalars(e))) return rc;
+  if ((rc = upload_adam_scalars(e, main_net, hp))) return rc;
   if ((rc = launch_head_backward_adam(e, main_net, e->h_state[0], b, B, e->cur_step_size, e->cur_bc2_sqrt, hp, 1.f / (float)B))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(dh_out, e->dh, sizeof(float) * (size_t)B * e->D, cudaMemcpyDeviceToDevice, e->stream));
   e->cur_phase = 3;
@@ -785,8 +816,9 @@ extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
   const rec_batch *b = &e->cur_batch;
   const int main_net = e->cur_main;
   e->cur_phase = 0;
-  int rc;
-  return trunk_backward(e, main_net, b->s, b->true_len, b->B, dh_reduced, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, false);
+  int rc = trunk_backward(e, main_net, b->s, b->true_len, b->B, dh_reduced, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, false);
+  for (int i = 0; i < 3; ++i) side_join(e, i);  // the Q-head sweep forked in phase C rejoins here
+  return rc;
 }
 
 // Sharded evaluation: per-shard record (max, sumexp, target logit, top-k candidates) per row ...

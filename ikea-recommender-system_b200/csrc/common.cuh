@@ -69,7 +69,8 @@ struct rec_engine {
   float *summary;        // [maxB][part_stride] per-row record of this shard
   float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;
-  float *h_sc, *d_sc;    // Adam scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)}: pinned host copy -> device (read by every Adam kernel)
+  float *h_sc, *d_sc;    // d_sc: Adam scalars {lr/(1-b1^t), 1/sqrt(1-b2^t)} written by adam_step_kernel, read by every Adam kernel
+  long long *d_step;     // [REC_MAX_NETS] device-side Adam step counters
   // CUDA-graph replay of the single-GPU train step (fixed engine-owned input buffers)
   bool use_graph;
   cudaStream_t cap_stream;  // private stream used only while capturing (the caller's stream may be the legacy default)

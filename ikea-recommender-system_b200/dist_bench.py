@@ -92,7 +92,7 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "global_batch": B * world,
                            "parallelism": f"vocab-sharded heads x{world} (embedding+GRU replicated), "
-                                          "4 collectives/step over NCCL",
+                                          "4 collectives/step over NCCL, whole step replayed as one CUDA graph",
                            "l2_policy": "distinct batch every step; twin nets alternate"},
                 "clocks": clk,
                 "e2e": {"value": B * world * K / e2e_s, "unit": "sessions/s",
@@ -106,4 +106,5 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
                 "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     dist.barrier()
+    trainer.release_graphs()
     dist.destroy_process_group()

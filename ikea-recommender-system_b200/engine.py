@@ -53,6 +53,8 @@ class Engine:
                  vocab_lo=0, vocab_hi=None):
         self.lib = N.load_library()
         self._host_losses = (C.c_float * 4)()
+        self._replayed_launches = 0
+        self.timing = False
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError(f"the B200 engine runs on CUDA devices only (got device={device!r}); "
@@ -244,10 +246,17 @@ class Engine:
         """Replay the single-GPU train step as a CUDA graph (default on; REC_NO_GRAPH=1 disables)."""
         self.lib.rec_set_cuda_graphs(self.handle, int(on))
 
+    def set_stream(self, cuda_stream: int):
+        """Launch on another stream from now on (used while the sharded step is captured into a torch CUDA graph)."""
+        self.lib.rec_set_stream(self.handle, C.c_void_p(cuda_stream))
+
     def launch_count(self):
-        return int(self.lib.rec_launch_count(self.handle))
+        """Kernels launched by this engine, including those replayed from caller-captured graphs."""
+        return int(self.lib.rec_launch_count(self.handle)) + self._replayed_launches
 
     def enable_kernel_timing(self, on=True):
+        """Per-kernel CUDA-event timing: steps run eagerly and serially (no graph replay, no branch overlap)."""
+        self.timing = bool(on)
         self.lib.rec_enable_kernel_timing(self.handle, int(on))
 
     def last_kernel_ms(self, which):

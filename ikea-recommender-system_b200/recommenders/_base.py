@@ -356,6 +356,12 @@ class NativeTrainerBase:
                 self._engine.bind(i, n._net_tensors())
         return self._engine
 
+    def release_graphs(self):
+        """Drop CUDA graphs that captured NCCL collectives (call before dist.destroy_process_group())."""
+        st = getattr(self, "_sharded_step", None)
+        if st is not None:
+            st.release_graphs()
+
     def shard_vocabulary(self, rank: int, world: int, group=None):
         """Vocabulary-shard every head of every net over `world` ranks (call before send_to_device)."""
         from ..sharded import shard_bounds

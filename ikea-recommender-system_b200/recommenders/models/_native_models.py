@@ -83,16 +83,7 @@ def _sharded_step(trainer, hp, main, s, a, true_len, r=None, s_next=None, true_n
         st = trainer._sharded_step = ShardedStep(eng, world, group, n0.hidden_dim * (2 if n0._bidirectional else 1))
         st.alloc_inputs(B, L, ds.device)
     local = eng._batch(B, ds, da, dln, dr, dsn, dnl, de)
-    N.check(eng.lib, eng.handle, eng.lib.rec_pack_batch(eng.handle, C.byref(local), C.c_void_p(st.packed.data_ptr())),
-            "rec_pack_batch")
-    dist.all_gather_into_tensor(st.gathered_in, st.packed, group=group)
-    gb = st.global_batch
-    N.check(eng.lib, eng.handle,
-            eng.lib.rec_unpack_batch(eng.handle, C.c_void_p(st.gathered_in.data_ptr()), world, B, C.byref(gb)),
-            "rec_unpack_batch")
-    if r is None:
-        gb = eng._batch(Bg, st.g_s, st.g_a, st.g_ln)
-    st.run(gb, hp, main, trainer._loss_dev, has_q=r is not None)
+    st.step(local, hp, main, trainer._loss_dev, has_q=r is not None)
     return trainer._loss_dev[:2]
 
 

@@ -15,8 +15,12 @@ Collectives per train step (all <= 1 MB, latency-bound):
 
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
+
+from . import _native as N
 
 
 def shard_bounds(V: int, rank: int, world: int):
@@ -70,6 +74,9 @@ class ShardedStep:
         self.rec = engine.record_floats()
         self.cap = 0
         self.B_local = -1
+        self._graphs = {}
+        self._cap_stream = None
+        self.use_graphs = True
 
     def alloc_inputs(self, B_local, L, dev):
         """Persistent buffers of the input all-gather (packed local batch, gathered bytes, global field arrays)."""
@@ -91,6 +98,61 @@ class ShardedStep:
         self.gathered = torch.empty(self.world, Bg, self.rec, dtype=torch.float32, device=dev)
         self.q = torch.zeros(2, Bg, 3, dtype=torch.float32, device=dev)
         self.dh = torch.empty(Bg, self.D, dtype=torch.float32, device=dev)
+
+    # ---- whole-step graph: input all-gather, unpack, phases A-D and their three collectives --------------
+    # The sequence has ~45 launches and 4 NCCL calls for ~0.4 ms of GPU work; issued eagerly it is bound by the
+    # host.  After `warm` eager executions of a (twin, kind, lr) key the sequence is captured ONCE into a torch
+    # CUDA graph (NCCL collectives are capturable) on a private stream, with the engine switched to that stream
+    # (rec_set_stream); every later step is: pack the local batch into the static buffer, replay.
+    # REC_NO_GRAPH=1 disables.  All ranks capture at the same step (same keys on every rank by construction).
+    def step(self, local_batch, hp, main_net, losses_out, has_q, warm=3):
+        import os
+        eng = self.eng
+        N.check(eng.lib, eng.handle,
+                eng.lib.rec_pack_batch(eng.handle, C.byref(local_batch), C.c_void_p(self.packed.data_ptr())), "rec_pack_batch")
+        key = (int(main_net), bool(has_q), float(hp.lr), id(losses_out))
+        ent = self._graphs.setdefault(key, {"seen": 0, "graph": None, "launches": 0})
+        if os.environ.get("REC_NO_GRAPH") or not self.use_graphs or eng.timing:
+            return self._sequence(hp, main_net, losses_out, has_q)
+        if ent["graph"] is None:
+            if ent["seen"] < warm:
+                ent["seen"] += 1
+                return self._sequence(hp, main_net, losses_out, has_q)
+            user_stream = torch.cuda.current_stream()
+            if self._cap_stream is None:
+                self._cap_stream = torch.cuda.Stream()
+            g = torch.cuda.CUDAGraph()
+            l0 = int(eng.lib.rec_launch_count(eng.handle))
+            try:
+                with torch.cuda.graph(g, stream=self._cap_stream):
+                    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+                    self._sequence(hp, main_net, losses_out, has_q)
+            finally:
+                eng.set_stream(user_stream.cuda_stream)
+            ent["graph"] = g
+            ent["launches"] = int(eng.lib.rec_launch_count(eng.handle)) - l0
+            eng._replayed_launches -= ent["launches"]  # nothing ran during the capture itself
+        ent["graph"].replay()
+        eng._replayed_launches += ent["launches"]
+
+    def release_graphs(self):
+        """Drop the captured graphs.  Must run before dist.destroy_process_group(): tearing down an NCCL
+        communicator that live CUDA graphs still reference hangs."""
+        import gc
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        gc.collect()
+
+    def _sequence(self, hp, main_net, losses_out, has_q):
+        eng = self.eng
+        dist.all_gather_into_tensor(self.gathered_in, self.packed, group=self.group)
+        gb = self.global_batch
+        N.check(eng.lib, eng.handle,
+                eng.lib.rec_unpack_batch(eng.handle, C.c_void_p(self.gathered_in.data_ptr()), self.world, self.B_local,
+                                         C.byref(gb)), "rec_unpack_batch")
+        if not has_q:
+            gb = eng._batch(self.B_local * self.world, self.g_s, self.g_a, self.g_ln)
+        self.run(gb, hp, main_net, losses_out, has_q)
 
     def run(self, batch, hp, main_net, losses_out, has_q):
         Bg = batch.B

@@ -219,6 +219,10 @@ int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, co
 /* 1 (default): rec_train_step_* replay a captured CUDA graph of the whole step from its second call on (inputs are
  * first copied into engine-owned buffers, Adam scalars live in device memory); 0: plain stream launches. */
 int rec_set_cuda_graphs(rec_engine *e, int on);
+/* Switches the stream every later call launches on (the engine is created on the caller's current stream).
+ * Needed when the caller captures the phase-split step, NCCL collectives included, into its own CUDA graph:
+ * the engine must launch on the capturing stream (sharded.py: ShardedStep). */
+int rec_set_stream(rec_engine *e, void *stream);
 /* Debug/A-B switch: 0 forces the generic CUDA-core head kernels even when the tcgen05 path applies (D == 64). */
 int rec_set_tensor_cores(rec_engine *e, int on);
 /* Number of kernels this engine launched since creation (bench.py's gpu_launches). */

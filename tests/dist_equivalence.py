@@ -17,6 +17,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("DIST_HANG_DUMP_S", "150")), exit=True)  # a hang prints where
     import b200pkg
     pkg = b200pkg.load()
     import oracle
@@ -28,7 +30,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    V, L, B, steps = 5000, 10, 64, 3
+    V, L, B, steps = 5000, 10, 64, int(os.environ.get("DIST_STEPS", "12"))  # > 2 x warm: both twins get captured + replayed
     kw = dict(hidden_dim=64, embedding_dim=64, padding_pos="end", train_pad_embed=True, use_packed_seq=True,
               learning_rate=0.01, item_num=V, state_size=L, action_dim=V, gamma=0.5, gru_layers=1,
               q_weights=torch.tensor([1.0, 0.5, 0.25]), alpha=1.0, topk_div=2, topk_nov=1, nov_rew_sig=1.0)
@@ -67,6 +69,7 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"dist_equivalence ok: world={world}")
+    t.release_graphs()
     dist.destroy_process_group()
 
 
