@@ -83,6 +83,13 @@ SYMBOLS = {
     "rec_train_phase_b": (C.c_int, [_P, _P, C.c_int, _P]),
     "rec_train_phase_c": (C.c_int, [_P, _P, _P, _P]),
     "rec_train_phase_d": (C.c_int, [_P, _P]),
+    "rec_dp_packed_bytes": (C.c_int64, [_P, C.c_int]),
+    "rec_dp_grad_floats": (C.c_int64, [_P]),
+    "rec_dp_forward": (C.c_int, [_P, C.POINTER(RecBatch), C.c_int, _P]),
+    "rec_dp_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(RecBatch)]),
+    "rec_train_phase_a_heads": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
+    "rec_dp_backward": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "rec_dp_apply": (C.c_int, [_P, _P, _P]),
     "rec_packed_batch_bytes": (C.c_int64, [_P, C.c_int]),
     "rec_pack_batch": (C.c_int, [_P, C.POINTER(RecBatch), _P]),
     "rec_unpack_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(RecBatch)]),

@@ -109,6 +109,9 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->emb_sorted, int32_t, mb * L);
   ALLOC(e, e->emb_seg, int32_t, mb * L + 2);
   cudaMemsetAsync(e->emb_seg, 0, sizeof(int32_t) * (mb * L + 2), e->stream);
+  e->emb_csort_n = (int)((mb * L + 4095) / 4096 * 4096);
+  ALLOC(e, e->emb_csort, int32_t, 2 * (int64_t)e->emb_csort_n);
+  ALLOC(e, e->emb_ccount, int32_t, 16);
   ALLOC(e, e->emb_carry, float, (mb * L / 32 + 1) * 64);
   ALLOC(e, e->emb_tmeta, int32_t, (mb * L / 32 + 1) * 2);
   e->part_stride = 72;
@@ -198,7 +201,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_csort, e->emb_ccount, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
@@ -733,8 +736,8 @@ static int shard_head_pass(rec_engine *e, int net_id, const float *h, const rec_
 
 extern "C" int rec_record_floats(const rec_engine *e) { return e ? e->part_stride : -1; }
 
-extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
-                                 float *records_out) {
+static int phase_a_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *records_out,
+                        bool skip_gru) {
   if (!e) return REC_EINVAL;
   if (!b || !hp || !records_out) REC_FAIL(e, REC_EINVAL, "rec_train_phase_a: null argument");
   const int n_q = e->cfg.n_heads - 1;
@@ -751,7 +754,9 @@ extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_tr
   e->cur_batch = *b; e->cur_hp = *hp; e->cur_main = main_net; e->cur_phase = 1;
   e->cur_topk = (n_q == 3) ? (hp->topk_div > hp->topk_nov ? hp->topk_div : hp->topk_nov) : 0;
   REC_CUDA(e, cudaMemsetAsync(records_out, 0, sizeof(float) * (size_t)B * e->part_stride, e->stream));
-  if (n_q > 0) {
+  if (skip_gru) {
+    if (n_q > 0 && (rc = check_net(e, boot, false))) return rc;  // final states came from rec_dp_unpack
+  } else if (n_q > 0) {
     if ((rc = check_net(e, boot, false))) return rc;
     const int nets[3] = {main_net, main_net, boot};
     const int64_t *ss[3] = {b->s, b->s_next, b->s_next};
@@ -764,6 +769,155 @@ extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_tr
   }
   float w[3] = {n_q == 3 ? hp->q_weights[0] : 1.f, hp->q_weights[1], hp->q_weights[2]};
   return shard_head_pass(e, main_net, e->h_state[0], b, 0, e->cur_topk, n_q, w, true, records_out);
+}
+
+extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
+                                 float *records_out) {
+  if (e) e->dp_active = false;
+  return phase_a_body(e, b, hp, main_net, records_out, false);
+}
+
+// ---- data-parallel trunk of the vocabulary-sharded step --------------------------------------------------
+// The heads are sharded by vocabulary and see the GLOBAL batch; embedding + GRU are replicated.  Running the
+// recurrent trunk on the global batch on every rank would make its cost grow with the number of GPUs, so each
+// rank runs it on its OWN sessions only:
+//   rec_dp_forward   local GRU passes -> packed record [batch fields | final states]      -> all-gather
+//   rec_dp_unpack    global batch fields + global final states
+//   rec_train_phase_a_heads / _b / _c   (unchanged head phases on the global batch)       -> all-reduce dL/dh
+//   rec_dp_backward  BPTT + weight gradients of the local sessions -> GRU gradient vector -> all-reduce
+//                    and the local dx rows                                                 -> all-gather
+//   rec_dp_apply     identical Adam update of the replicated GRU + embedding table on every rank
+__global__ void pack_h_kernel(const float *h0, const float *h1, const float *h2, int n_h, int n, float *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_h * n) return;
+  const int k = i / n, j = i - k * n;
+  out[i] = (k == 0 ? h0 : k == 1 ? h1 : h2)[j];
+}
+__global__ void unpack_h_kernel(const uint8_t *gathered, size_t stride, size_t h_off, int G, int n_h, int n, float *h0,
+                                float *h1, float *h2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * n_h * n) return;
+  const int g = i / (n_h * n), r = i - g * (n_h * n), k = r / n, j = r - k * n;
+  const float *src = reinterpret_cast<const float *>(gathered + (size_t)g * stride + h_off);
+  (k == 0 ? h0 : k == 1 ? h1 : h2)[(size_t)g * n + j] = src[r];
+}
+__global__ void sum_splits_kernel(const float *__restrict__ part, int splits, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int sidx = 0; sidx < splits; ++sidx) acc += part[(size_t)sidx * n + i];
+  out[i] = acc;
+}
+
+static int dp_n_h(const rec_engine *e) { return e->cfg.n_heads > 1 ? 3 : 1; }
+
+extern "C" int64_t rec_dp_packed_bytes(const rec_engine *e, int B_local) {
+  if (!e || B_local < 1) return -1;
+  return rec_packed_batch_bytes(e, B_local) + (int64_t)dp_n_h(e) * B_local * e->D * (int64_t)sizeof(float);
+}
+extern "C" int64_t rec_dp_grad_floats(const rec_engine *e) {
+  if (!e) return -1;
+  const int E = e->cfg.embedding_dim, H = e->cfg.hidden_dim;
+  return (int64_t)e->dirs * 2 * (3 * H) * ((E > H ? E : H) + 1);
+}
+
+extern "C" int rec_dp_forward(rec_engine *e, const rec_batch *local, int main_net, void *packed_out) {
+  if (!e) return REC_EINVAL;
+  const int n_q = e->cfg.n_heads - 1;
+  if (main_net < 0 || main_net >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "main_net out of range");
+  int rc = check_net(e, main_net, true);
+  if (rc) return rc;
+  if ((rc = check_batch(e, local, n_q > 0))) return rc;
+  if (!packed_out) REC_FAIL(e, REC_EINVAL, "rec_dp_forward: null argument");
+  for (int i = 0; i < 3; ++i) side_join(e, i);
+  const int B = local->B, boot = 1 - main_net;
+  rec_batch own = e->own;
+  own.B = B;
+  if (!local->r) { own.r = nullptr; own.s_next = nullptr; own.true_next_len = nullptr; own.is_end = nullptr; }
+  copy_batch_kernel<<<cdiv(B * (2 * e->cfg.state_size + 5), 256), 256, 0, e->stream>>>(*local, own, e->cfg.state_size);
+  REC_LAUNCH_CHECK(e);
+  e->dp_local = own;
+  if (n_q > 0) {
+    if ((rc = check_net(e, boot, false))) return rc;
+    const int nets[3] = {main_net, main_net, boot};
+    const int64_t *ss[3] = {own.s, own.s_next, own.s_next};
+    const int64_t *ll[3] = {own.true_len, own.true_next_len, own.true_len};
+    float *hh[3] = {e->h_state[0], e->h_state[1], e->h_state[2]};
+    const bool sv[3] = {true, false, false};
+    if ((rc = launch_gru_forward_multi(e, 3, nets, ss, ll, hh, sv, B))) return rc;
+  } else {
+    if ((rc = launch_gru_forward(e, main_net, own.s, own.true_len, B, e->h_state[0], true))) return rc;
+  }
+  if ((rc = launch_pack_batch(e, &own, (uint8_t *)packed_out))) return rc;
+  const int n = B * e->D, n_h = dp_n_h(e);
+  pack_h_kernel<<<cdiv(n_h * n, 256), 256, 0, e->stream>>>(e->h_state[0], e->h_state[1], e->h_state[2], n_h, n,
+                                                           (float *)((uint8_t *)packed_out + rec_packed_batch_bytes(e, B)));
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+extern "C" int rec_dp_unpack(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *out) {
+  if (!e) return REC_EINVAL;
+  if (!gathered || n_ranks < 1 || B_local < 1 || !out || !out->s || !out->s_next || !out->a || !out->true_len ||
+      !out->true_next_len || !out->r || !out->is_end)
+    REC_FAIL(e, REC_EINVAL, "rec_dp_unpack: bad argument");
+  if (n_ranks * B_local > e->cfg.max_batch) REC_FAIL(e, REC_EINVAL, "rec_dp_unpack: global batch exceeds max_batch");
+  const size_t stride = (size_t)rec_dp_packed_bytes(e, B_local);
+  int rc = launch_unpack_batch(e, (const uint8_t *)gathered, n_ranks, B_local, stride, out);
+  if (rc) return rc;
+  const int n = B_local * e->D, n_h = dp_n_h(e);
+  unpack_h_kernel<<<cdiv(n_ranks * n_h * n, 256), 256, 0, e->stream>>>((const uint8_t *)gathered, stride,
+                                                                      (size_t)rec_packed_batch_bytes(e, B_local), n_ranks, n_h,
+                                                                      n, e->h_state[0], e->h_state[1], e->h_state[2]);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+extern "C" int rec_train_phase_a_heads(rec_engine *e, const rec_batch *global_b, const rec_train_hparams *hp, int main_net,
+                                       float *records_out) {
+  if (e) e->dp_active = true;
+  return phase_a_body(e, global_b, hp, main_net, records_out, true);
+}
+
+extern "C" int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank, float *gru_grads_out, float *dx_out) {
+  if (!e) return REC_EINVAL;
+  if (e->cur_phase != 3 || !e->dp_active) REC_FAIL(e, REC_EINVAL, "rec_dp_backward called out of order");
+  if (!dh_reduced || !gru_grads_out || !dx_out || rank < 0) REC_FAIL(e, REC_EINVAL, "rec_dp_backward: bad argument");
+  const rec_batch &lb = e->dp_local;
+  const int B = lb.B, main_net = e->cur_main;
+  if ((rank + 1) * B > e->cur_batch.B) REC_FAIL(e, REC_EINVAL, "rec_dp_backward: rank %d outside the global batch", rank);
+  int rc = launch_gru_backward(e, main_net, lb.s, lb.true_len, B, dh_reduced + (size_t)rank * B * e->D, e->cur_step_size,
+                               e->cur_bc2_sqrt, &e->cur_hp, 1 | 2);
+  if (rc) return rc;
+  const int n = (int)rec_dp_grad_floats(e);
+  sum_splits_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(e->wgrad_part, e->wgrad_splits, n, gru_grads_out);
+  REC_LAUNCH_CHECK(e);
+  REC_CUDA(e, cudaMemcpyAsync(dx_out, e->dx, sizeof(float) * (size_t)B * e->cfg.state_size * e->dirs * e->cfg.embedding_dim,
+                              cudaMemcpyDeviceToDevice, e->stream));
+  e->cur_phase = 4;
+  return REC_OK;
+}
+
+extern "C" int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const float *dx_gathered) {
+  if (!e) return REC_EINVAL;
+  if (e->cur_phase != 4) REC_FAIL(e, REC_EINVAL, "rec_dp_apply called out of order");
+  if (!gru_grads_reduced || !dx_gathered) REC_FAIL(e, REC_EINVAL, "rec_dp_apply: null argument");
+  const rec_batch *gb = &e->cur_batch;
+  const int main_net = e->cur_main;
+  e->cur_phase = 0;
+  // the launchers read the engine's buffers: point them at the reduced / gathered data for this call
+  float *const own_part = e->wgrad_part, *const own_dx = e->dx;
+  const int own_splits = e->wgrad_splits;
+  e->wgrad_part = const_cast<float *>(gru_grads_reduced); e->wgrad_splits = 1; e->dx = const_cast<float *>(dx_gathered);
+  int rc;
+  {
+    SideScope side(e, 1);  // embedding chain over the GLOBAL positions next to the GRU Adam
+    rc = launch_embedding_update(e, main_net, gb->s, gb->true_len, gb->B, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, 7);
+  }
+  if (!rc) rc = launch_gru_backward(e, main_net, gb->s, gb->true_len, gb->B, nullptr, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, 4);
+  e->wgrad_part = own_part; e->wgrad_splits = own_splits; e->dx = own_dx;
+  for (int i = 0; i < 3; ++i) side_join(e, i);
+  return rc;
 }
 
 extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float *q_out) {

@@ -43,6 +43,9 @@ struct rec_engine {
   uint8_t *emb_leader;   // [maxB*L] chunk-leader flags (batches spanning several dedup chunks)
   int32_t *emb_sorted;   // [maxB*L] positions sorted by (row, position)  (sort-based dedup, E = 64)
   int32_t *emb_seg;      // [maxB*L + 2] row of each sorted entry; [cap] = valid entries, [cap+1] = finished-tile counter
+  int32_t *emb_csort;    // [2][emb_csort_n] per-chunk sorted (position | row) lists of batches beyond one chunk
+  int emb_csort_n;
+  int32_t *emb_ccount;   // [16] valid entries per chunk
   float *emb_carry;      // [maxB*L/32 + 1, 64] partial sums of runs continued from the previous tile
   int32_t *emb_tmeta;    // [maxB*L/32 + 1, 2] (tile starts inside a run, leader of the tile's last run)
   // head statistics partials: [n_split][maxB][PART_STRIDE]
@@ -59,6 +62,8 @@ struct rec_engine {
   int32_t *astar;        // [maxB]
   // saved call context for the phase-split API
   rec_batch cur_batch;
+  rec_batch dp_local;    // data-parallel trunk: this rank's own sessions (engine-owned copy)
+  bool dp_active;
   rec_train_hparams cur_hp;
   int cur_main, cur_topk, cur_phase;
   float cur_step_size, cur_bc2_sqrt;

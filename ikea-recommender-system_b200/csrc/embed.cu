@@ -274,52 +274,71 @@ __global__ void __launch_bounds__(256) q_grad_rows_kernel(const int64_t *__restr
                                                           const float *__restrict__ h, int B, int D, int n_q, int Vloc,
                                                           int vocab_lo, float *__restrict__ grad_rows,
                                                           float *__restrict__ bgrad, int32_t *__restrict__ slot_of_row) {
+  // the action ids of the whole batch are staged in shared memory: the two scans below are latency chains
+  // (load -> ballot -> next) and ran at L2 latency per iteration when they read global memory
+  extern __shared__ int32_t sa[];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) sa[i] = (int32_t)a[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per (batch row, Q head)
   if (w >= B * n_q) return;
   const int b = w / n_q, j = w - b * n_q;
-  const int64_t key = a[b];
-  const int64_t loc = key - vocab_lo;
+  const int key = sa[b];
+  const int loc = key - vocab_lo;
   if (loc < 0 || loc >= Vloc) return;
   for (int q0 = 0; q0 < b; q0 += 32) {
     int q = q0 + lane;
-    if (__ballot_sync(0xffffffffu, q < b && a[q] == key)) return;
+    if (__ballot_sync(0xffffffffu, q < b && sa[q] == key)) return;
   }
+  // Pass 1 of each column block only records the matching rows in a per-warp list (shared-memory reads and
+  // ballots, no global loads); flush() then fetches dq and the h rows of 16 list entries at a time -- independent
+  // loads -- and accumulates strictly in batch order.  A popular action has hundreds of duplicates: chasing them
+  // one 32-row window at a time cost two dependent global latencies per window.
+  constexpr int CAP = 128;
+  __shared__ int plist[8][CAP];
+  const int wid = threadIdx.x >> 5;
   for (int d0 = 0; d0 < D; d0 += 128) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float bsum = 0.f;
     const int col = d0 + lane * 4;
-    for (int q0 = b; q0 < B; q0 += 32) {
-      const int q = q0 + lane;
-      const bool hit = q < B && a[q] == key;
-      const float gl = hit ? dq[q * 3 + j] : 0.f;  // coalesced, then broadcast by shuffle
-      unsigned mm = __ballot_sync(0xffffffffu, hit);
-      while (mm) {
-        int idx[4];
-        float4 hv[4];
-        int n = 0;
+    int cnt = 0;
+    auto flush = [&]() {
+      for (int i0 = 0; i0 < cnt; i0 += 16) {
+        float4 hv[16];
+        float g[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          idx[u] = -1;
+        for (int u = 0; u < 16; ++u) {
+          g[u] = 0.f;
           hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (mm) {
-            idx[u] = __ffs(mm) - 1;
-            mm &= mm - 1;
-            if (col < D) hv[u] = *reinterpret_cast<const float4 *>(h + (int64_t)(q0 + idx[u]) * D + col);
-            n = u + 1;
+          if (i0 + u < cnt) {
+            const int q = plist[wid][i0 + u];
+            g[u] = dq[q * 3 + j];
+            if (col < D) hv[u] = *reinterpret_cast<const float4 *>(h + (int64_t)q * D + col);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (u < n) {
-            const float g = __shfl_sync(0xffffffffu, gl, idx[u]);
-            bsum += g;
-            acc.x = fmaf(g, hv[u].x, acc.x); acc.y = fmaf(g, hv[u].y, acc.y);
-            acc.z = fmaf(g, hv[u].z, acc.z); acc.w = fmaf(g, hv[u].w, acc.w);
+        for (int u = 0; u < 16; ++u) {
+          if (i0 + u < cnt) {
+            bsum += g[u];
+            acc.x = fmaf(g[u], hv[u].x, acc.x); acc.y = fmaf(g[u], hv[u].y, acc.y);
+            acc.z = fmaf(g[u], hv[u].z, acc.z); acc.w = fmaf(g[u], hv[u].w, acc.w);
           }
         }
       }
+      __syncwarp();
+      cnt = 0;
+    };
+    for (int q0 = b; q0 < B; q0 += 32) {
+      const int q = q0 + lane;
+      const bool hit = q < B && sa[q] == key;
+      const unsigned mm = __ballot_sync(0xffffffffu, hit);
+      if (!mm) continue;
+      if (hit) plist[wid][cnt + __popc(mm & ((1u << lane) - 1u))] = q;
+      cnt += __popc(mm);
+      __syncwarp();
+      if (cnt > CAP - 32) flush();
     }
+    flush();
     if (col < D) *reinterpret_cast<float4 *>(grad_rows + ((int64_t)b * n_q + j) * D + col) = acc;
     if (d0 == 0 && lane == 0) bgrad[b * n_q + j] = bsum;
   }
@@ -339,7 +358,8 @@ int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_bat
                         float bc2_sqrt, const rec_train_hparams *hp, int wait_mark) {
   const int n_q = e->cfg.n_heads - 1, D = e->D;
   const rec_net_params &p = e->nets[net_id].p;
-  q_grad_rows_kernel<<<cdiv(B * n_q, 8), 256, 0, e->stream>>>(b->a, e->dq, h, B, D, n_q, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
+  if ((size_t)B * sizeof(int32_t) > 48 * 1024) REC_FAIL(e, REC_EINVAL, "Q-head gradient rows: batch of %d sessions exceeds the 12288 supported", B);
+  q_grad_rows_kernel<<<cdiv(B * n_q, 8), 256, (size_t)B * sizeof(int32_t), e->stream>>>(b->a, e->dq, h, B, D, n_q, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
                                                        e->q_bgrad, e->q_slot);
   REC_LAUNCH_CHECK(e);
   if (wait_mark >= 0) side_wait_mark(e, wait_mark);
@@ -375,60 +395,42 @@ int launch_fill_i32(rec_engine *e, int32_t *p, int64_t n, int32_t v) {
 }
 
 
-// ---- sort-based duplicate combining (E = 64, one direction, P <= 8192) ------------------------------------
+// ---- sort-based duplicate combining (E = 64, one direction, P <= 32768) ------------------------------------
 // emb_rank_kernel orders the token positions by (row, position) (see below).
 // emb_tilesum64_kernel: one warp per tile of 32 sorted entries loads its 32 dx rows with independent loads and
 // walks them in sorted order; a row whose run continues from the previous tile leaves a carry that the last
 // warp to finish folds into the run's accumulator in tile order.  The summation order depends only on the
 // sorted order => deterministic, no float atomics.
-// Sorting by brute-force ranking: P <= 8192 keys means <= 67 M comparisons, spread over every SM, which beats
-// a single-CTA sorting network by far.  Every CTA recomputes the row of all positions into shared memory
+// Sorting by brute-force ranking: P <= 8192 keys means <= 67 M comparisons (1 G at the 32768 cap), spread over every SM, which beats
+// a single-CTA sorting network by far.  Every CTA stages the row keys of all positions in shared memory
 // (invalid positions get INT_MAX), 8 warps share 32 elements and count the entries ordered before each:
 // rank(i) = #{j : row_j < row_i} + #{j < i : row_j == row_i}.  Ranks are a permutation, so the scatter is
 // conflict-free.
-__global__ void __launch_bounds__(256) emb_rank_kernel(const int64_t *__restrict__ s, const int64_t *__restrict__ lens,
-                                                       int B, int L, int N, int packed, int frozen_row,
-                                                       int32_t *__restrict__ keys, int32_t *__restrict__ sorted_pos,
-                                                       int32_t *__restrict__ sorted_row, int cap) {
+// Batches beyond EMB_CHUNK positions are ranked chunk by chunk (quadratic work only inside a chunk) and the
+// sorted chunks are merged by emb_merge_rank_kernel.
+constexpr int EMB_CHUNK = 4096;
+
+__global__ void __launch_bounds__(256) emb_rank_kernel(const int32_t *__restrict__ keys, int P, int C,
+                                                       int32_t *__restrict__ out_pos, int32_t *__restrict__ out_row,
+                                                       int32_t *__restrict__ counts) {
   extern __shared__ int32_t srow[];
-  const int tid = threadIdx.x, P = B * L;
-  const int Ppad = (P + 15) & ~15;
+  const int tid = threadIdx.x;
+  const int c = (blockIdx.x * 32) / C;        // chunk of this CTA (C is a multiple of 32)
+  const int c0 = c * C;
+  const int Pc = min(C, P - c0);
+  const int Ppad = (Pc + 15) & ~15;
   int n_valid = 0;
-  for (int i0 = 0; i0 < Ppad; i0 += 4 * 256) {
-    int64_t itv[4], lv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {  // independent loads first: this phase is pure latency
-      const int i = i0 + u * 256 + tid;
-      itv[u] = 0;
-      lv[u] = L;
-      if (i < P) {
-        itv[u] = s[i];
-        if (packed) lv[u] = lens[i / L];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 256 + tid;
-      if (i >= Ppad) continue;
-      int row = 0x7fffffff;
-      if (i < P) {
-        const int t = i - (i / L) * L;
-        const int len = (int)(lv[u] < 1 ? 1 : (lv[u] > L ? L : lv[u]));
-        int64_t it = itv[u];
-        it = it < 0 ? 0 : (it > N ? N : it);
-        const bool ok = (t < len && (int)it != frozen_row);
-        if (ok) { row = (int)it; ++n_valid; }
-        if (blockIdx.x == 0) keys[i] = ok ? row : -1;
-      }
-      srow[i] = row;
-    }
+  for (int i = tid; i < Ppad; i += 256) {   // keys were computed once by emb_keys_kernel (-1 = no gradient)
+    const int k = i < Pc ? keys[c0 + i] : -1;
+    n_valid += k >= 0;
+    srow[i] = k >= 0 ? k : 0x7fffffff;
   }
-  if (blockIdx.x == 0) {
+  if (blockIdx.x * 32 == c0) {
     __shared__ int nv[8];
     for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
     if ((tid & 31) == 0) nv[tid >> 5] = n_valid;
     __syncthreads();
-    if (tid == 0) sorted_row[cap] = nv[0] + nv[1] + nv[2] + nv[3] + nv[4] + nv[5] + nv[6] + nv[7];
+    if (tid == 0) counts[c] = nv[0] + nv[1] + nv[2] + nv[3] + nv[4] + nv[5] + nv[6] + nv[7];
   } else {
     __syncthreads();
   }
@@ -436,8 +438,8 @@ __global__ void __launch_bounds__(256) emb_rank_kernel(const int64_t *__restrict
   // loop is branch-free (row_j is counted when it is below row_i + [j < i])
   __shared__ int part_cnt[8][32];
   const int lane = tid & 31, wid = tid >> 5;
-  const int i = blockIdx.x * 32 + lane;
-  const int ri = i < P ? srow[i] : 0x7ffffffe;
+  const int i = blockIdx.x * 32 + lane - c0;  // position inside the chunk
+  const int ri = i < Pc ? srow[i] : 0x7ffffffe;
   const int Q = Ppad >> 3;                  // entries per warp (multiple of 2)
   int cnt = 0;
   const int2 *src = reinterpret_cast<const int2 *>(srow + wid * Q);
@@ -451,13 +453,56 @@ __global__ void __launch_bounds__(256) emb_rank_kernel(const int64_t *__restrict
   }
   part_cnt[wid][lane] = cnt;
   __syncthreads();
-  if (wid == 0 && i < P && ri != 0x7fffffff) {
+  if (wid == 0 && i < Pc && ri != 0x7fffffff) {
     int rank = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) rank += part_cnt[w][lane];
-    sorted_pos[rank] = i;
-    sorted_row[rank] = ri;
+    out_pos[c0 + rank] = c0 + i;
+    out_row[c0 + rank] = ri;
   }
+}
+
+// Global rank of entry r of sorted chunk c = r + sum over the other chunks of the entries ordered before it:
+// chunks hold ascending position ranges, so an equal row of an EARLIER chunk comes first (upper bound) and of a
+// LATER chunk comes after (lower bound).  All chunk lists are staged in shared memory; the searches are binary.
+__global__ void __launch_bounds__(256) emb_merge_rank_kernel(const int32_t *__restrict__ c_pos, const int32_t *__restrict__ c_row,
+                                                             const int32_t *__restrict__ counts, int C, int n_chunks,
+                                                             int32_t *__restrict__ sorted_pos, int32_t *__restrict__ sorted_row,
+                                                             int cap) {
+  extern __shared__ int32_t srow[];
+  __shared__ int cnt[16];
+  const int tid = threadIdx.x;
+  if (tid < n_chunks) cnt[tid] = counts[tid];
+  __syncthreads();
+  for (int i = tid; i < n_chunks * C; i += 256) {
+    const int c = i / C, r = i - c * C;
+    srow[i] = r < cnt[c] ? c_row[i] : 0x7fffffff;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) {
+    int tot = 0;
+    for (int c = 0; c < n_chunks; ++c) tot += cnt[c];
+    sorted_row[cap] = tot;
+  }
+  const int e = blockIdx.x * 256 + tid;
+  if (e >= n_chunks * C) return;
+  const int c = e / C, r = e - c * C;
+  if (r >= cnt[c]) return;
+  const int row = srow[e];
+  int rank = r;
+  for (int o = 0; o < n_chunks; ++o) {
+    if (o == c) continue;
+    const int32_t *list = srow + o * C;
+    const int thr = row + (o < c ? 1 : 0);   // first index with list[idx] >= thr
+    int lo = 0, hi = cnt[o];
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (list[mid] < thr) lo = mid + 1; else hi = mid;
+    }
+    rank += lo;
+  }
+  sorted_pos[rank] = c_pos[e];
+  sorted_row[rank] = row;
 }
 
 __global__ void __launch_bounds__(256) emb_tilesum64_kernel(const int32_t *__restrict__ sorted_pos, int32_t *__restrict__ sorted_row,
@@ -553,14 +598,30 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
   const rec_config &c = e->cfg;
   const int L = c.state_size, E = c.embedding_dim, P = B * L;
   NetBind &nb = e->nets[net_id];
-  const bool sorted_path = (E == 64 && e->dirs == 1 && P <= 8192);
+  const bool sorted_path = (E == 64 && e->dirs == 1 && P <= 32768);
+  static bool rank_attr_set = false;
+  if (sorted_path && !rank_attr_set) {
+    REC_CUDA(e, cudaFuncSetAttribute(emb_merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * (int)sizeof(int32_t)));
+    rank_attr_set = true;
+  }
   if (stages & 1) {
+    emb_keys_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(s, lengths, B, L, c.item_num, c.use_packed_seq,
+                                                        c.frozen_pad_row, e->emb_keys);
     if (sorted_path) {
-      emb_rank_kernel<<<cdiv(P, 32), 256, ((P + 15) & ~15) * sizeof(int32_t), e->stream>>>(
-          s, lengths, B, L, c.item_num, c.use_packed_seq, c.frozen_pad_row, e->emb_keys, e->emb_sorted, e->emb_seg, c.max_batch * L);
-    } else {
-      emb_keys_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(s, lengths, B, L, c.item_num, c.use_packed_seq,
-                                                          c.frozen_pad_row, e->emb_keys);
+      REC_LAUNCH_CHECK(e);
+      const int cap = c.max_batch * L;
+      const int n_chunks = cdiv(P, EMB_CHUNK);
+      const int Cs = n_chunks > 1 ? EMB_CHUNK : ((P + 31) & ~31);
+      const size_t smem = (size_t)((Cs + 15) & ~15) * sizeof(int32_t);
+      if (n_chunks == 1) {
+        emb_rank_kernel<<<cdiv(P, 32), 256, smem, e->stream>>>(e->emb_keys, P, Cs, e->emb_sorted, e->emb_seg, e->emb_seg + cap);
+      } else {
+        emb_rank_kernel<<<cdiv(P, 32), 256, smem, e->stream>>>(e->emb_keys, P, Cs, e->emb_csort, e->emb_csort + e->emb_csort_n,
+                                                               e->emb_ccount);
+        REC_LAUNCH_CHECK(e);
+        emb_merge_rank_kernel<<<cdiv(n_chunks * EMB_CHUNK, 256), 256, (size_t)n_chunks * EMB_CHUNK * sizeof(int32_t), e->stream>>>(
+            e->emb_csort, e->emb_csort + e->emb_csort_n, e->emb_ccount, EMB_CHUNK, n_chunks, e->emb_sorted, e->emb_seg, cap);
+      }
     }
     REC_LAUNCH_CHECK(e);
   }

@@ -91,8 +91,10 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "global_batch": B * world,
-                           "parallelism": f"vocab-sharded heads x{world} (embedding+GRU replicated), "
-                                          "4 collectives/step over NCCL, whole step replayed as one CUDA graph",
+                           "parallelism": f"vocab-sharded heads x{world}, embedding+GRU replicated, trunk "
+                                          + ("data-parallel (6 collectives/step)" if trainer._sharded_step.dp_trunk
+                                             else "on the global batch (4 collectives/step)")
+                                          + " over NCCL, whole step replayed as one CUDA graph",
                            "l2_policy": "distinct batch every step; twin nets alternate"},
                 "clocks": clk,
                 "e2e": {"value": B * world * K / e2e_s, "unit": "sessions/s",

@@ -228,6 +228,35 @@ class Engine:
     def train_phase_d(self, dh_reduced):
         N.check(self.lib, self.handle, self.lib.rec_train_phase_d(self.handle, _ptr(dh_reduced)), "rec_train_phase_d")
 
+    # -- data-parallel trunk of the sharded step (see include/recsys_b200.h) ------------------------
+    def dp_packed_bytes(self, B_local):
+        return int(self.lib.rec_dp_packed_bytes(self.handle, B_local))
+
+    def dp_grad_floats(self):
+        return int(self.lib.rec_dp_grad_floats(self.handle))
+
+    def dp_forward(self, local_batch, main_net, packed_out):
+        N.check(self.lib, self.handle,
+                self.lib.rec_dp_forward(self.handle, C.byref(local_batch), main_net, _ptr(packed_out)), "rec_dp_forward")
+
+    def dp_unpack(self, gathered, world, B_local, global_batch):
+        N.check(self.lib, self.handle,
+                self.lib.rec_dp_unpack(self.handle, _ptr(gathered), world, B_local, C.byref(global_batch)), "rec_dp_unpack")
+
+    def train_phase_a_heads(self, batch, hp, main_net, records_out):
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_phase_a_heads(self.handle, C.byref(batch), C.byref(hp), main_net, _ptr(records_out)),
+                "rec_train_phase_a_heads")
+
+    def dp_backward(self, dh_reduced, rank, gru_grads_out, dx_out):
+        N.check(self.lib, self.handle,
+                self.lib.rec_dp_backward(self.handle, _ptr(dh_reduced), rank, _ptr(gru_grads_out), _ptr(dx_out)),
+                "rec_dp_backward")
+
+    def dp_apply(self, gru_grads_reduced, dx_gathered):
+        N.check(self.lib, self.handle, self.lib.rec_dp_apply(self.handle, _ptr(gru_grads_reduced), _ptr(dx_gathered)),
+                "rec_dp_apply")
+
     def eval_shard_candidates(self, net_id, batch, head_idx, kmax, records_out):
         self.ensure_batch(batch.B)
         N.check(self.lib, self.handle,

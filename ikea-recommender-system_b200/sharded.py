@@ -69,8 +69,21 @@ def all_gather_rows(local_rows, group=None):
 class ShardedStep:
     """Drives rec_train_phase_a..d of one engine with the three collectives in between."""
 
-    def __init__(self, engine, world, group, D):
+    def __init__(self, engine, world, group, D, rank=0, dp_trunk=None):
         self.eng, self.world, self.group, self.D = engine, world, group, D
+        # dp_trunk: embedding + GRU run on each rank's own sessions (two more, small, collectives) instead of on
+        # the all-gathered global batch on every rank.  Measured on B200 (cfg2, B = 256 per GPU): the replicated
+        # trunk wins at 2 GPUs (0.39 vs 0.45 ms), both tie at 4 (0.49), the data-parallel trunk wins at 8
+        # (0.61 vs 0.72 ms) -> default: world > 4.  REC_DP_TRUNK=1 / REC_NO_DP_TRUNK=1 force either.
+        import os
+        self.rank = rank
+        if dp_trunk is None:
+            dp_trunk = world > 4
+        if os.environ.get("REC_DP_TRUNK"):
+            dp_trunk = True
+        if os.environ.get("REC_NO_DP_TRUNK"):
+            dp_trunk = False
+        self.dp_trunk = bool(dp_trunk)
         self.rec = engine.record_floats()
         self.cap = 0
         self.B_local = -1
@@ -91,6 +104,23 @@ class ShardedStep:
         self.g_r = torch.zeros(Bg, dtype=torch.float32, device=dev)
         self.g_e = torch.zeros(Bg, dtype=torch.uint8, device=dev)
         self.global_batch = self.eng._batch(Bg, self.g_s, self.g_a, self.g_ln, self.g_r, self.g_sn, self.g_nl, self.g_e)
+        if self.dp_trunk:
+            self.local_packed = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self.l_s, self.l_sn = torch.zeros(B_local, L, **i64), torch.zeros(B_local, L, **i64)
+            self.l_a, self.l_ln, self.l_nl = torch.zeros(B_local, **i64), torch.zeros(B_local, **i64), torch.zeros(B_local, **i64)
+            self.l_r = torch.zeros(B_local, dtype=torch.float32, device=dev)
+            self.l_e = torch.zeros(B_local, dtype=torch.uint8, device=dev)
+            self.local_batch = self.eng._batch(B_local, self.l_s, self.l_a, self.l_ln, self.l_r, self.l_sn, self.l_nl, self.l_e)
+            self.eng.ensure_batch(Bg)
+            cfg = self.eng.cfg
+            nb = self.eng.dp_packed_bytes(B_local)
+            self.packed = torch.zeros(nb, dtype=torch.uint8, device=dev)
+            self.gathered_in = torch.zeros(self.world * nb, dtype=torch.uint8, device=dev)
+            f32 = dict(dtype=torch.float32, device=dev)
+            self.gru_grads = torch.zeros(self.eng.dp_grad_floats(), **f32)
+            n_dx = B_local * L * (2 if cfg["bidirectional"] else 1) * cfg["embedding_dim"]
+            self.dx_send = torch.zeros(n_dx, **f32)
+            self.dx_all = torch.zeros(self.world * n_dx, **f32)
 
     def _alloc(self, Bg, dev):
         self.cap = Bg
@@ -108,8 +138,15 @@ class ShardedStep:
     def step(self, local_batch, hp, main_net, losses_out, has_q, warm=3):
         import os
         eng = self.eng
-        N.check(eng.lib, eng.handle,
-                eng.lib.rec_pack_batch(eng.handle, C.byref(local_batch), C.c_void_p(self.packed.data_ptr())), "rec_pack_batch")
+        if self.dp_trunk:
+            # the local batch pointers vary from step to step: copy it into the static staging fields eagerly
+            # (one tiny kernel); everything after that, incl. the local GRU passes, is replayable
+            N.check(eng.lib, eng.handle,
+                    eng.lib.rec_pack_batch(eng.handle, C.byref(local_batch), C.c_void_p(self.local_packed.data_ptr())),
+                    "rec_pack_batch")
+        else:
+            N.check(eng.lib, eng.handle,
+                    eng.lib.rec_pack_batch(eng.handle, C.byref(local_batch), C.c_void_p(self.packed.data_ptr())), "rec_pack_batch")
         key = (int(main_net), bool(has_q), float(hp.lr), id(losses_out))
         ent = self._graphs.setdefault(key, {"seen": 0, "graph": None, "launches": 0})
         if os.environ.get("REC_NO_GRAPH") or not self.use_graphs or eng.timing:
@@ -144,6 +181,8 @@ class ShardedStep:
         gc.collect()
 
     def _sequence(self, hp, main_net, losses_out, has_q):
+        if self.dp_trunk:
+            return self._sequence_dp(hp, main_net, losses_out, has_q)
         eng = self.eng
         dist.all_gather_into_tensor(self.gathered_in, self.packed, group=self.group)
         gb = self.global_batch
@@ -153,6 +192,35 @@ class ShardedStep:
         if not has_q:
             gb = eng._batch(self.B_local * self.world, self.g_s, self.g_a, self.g_ln)
         self.run(gb, hp, main_net, losses_out, has_q)
+
+    def _sequence_dp(self, hp, main_net, losses_out, has_q):
+        """Data-parallel trunk: 6 collectives, all small; per-rank work independent of the number of GPUs
+        except for the (global-batch x local-vocabulary) head kernels."""
+        eng, world, B = self.eng, self.world, self.B_local
+        Bg = B * world
+        # static local fields <- the packed staging record (world = 1 unpack)
+        N.check(eng.lib, eng.handle,
+                eng.lib.rec_unpack_batch(eng.handle, C.c_void_p(self.local_packed.data_ptr()), 1, B, C.byref(self.local_batch)),
+                "rec_unpack_batch")
+        lb = self.local_batch if has_q else eng._batch(B, self.l_s, self.l_a, self.l_ln)
+        eng.dp_forward(lb, main_net, self.packed)
+        dist.all_gather_into_tensor(self.gathered_in, self.packed, group=self.group)
+        eng.dp_unpack(self.gathered_in, world, B, self.global_batch)
+        gb = self.global_batch if has_q else eng._batch(Bg, self.g_s, self.g_a, self.g_ln)
+        dev = losses_out.device
+        if Bg != self.cap:
+            self._alloc(Bg, dev)
+        eng.train_phase_a_heads(gb, hp, main_net, self.records)
+        dist.all_gather_into_tensor(self.gathered, self.records, group=self.group)
+        eng.train_phase_b(self.gathered, world, self.q)
+        if has_q:
+            dist.all_reduce(self.q, group=self.group)
+        eng.train_phase_c(self.q, losses_out, self.dh)
+        dist.all_reduce(self.dh, group=self.group)
+        eng.dp_backward(self.dh, self.rank, self.gru_grads, self.dx_send)
+        dist.all_reduce(self.gru_grads, group=self.group)
+        dist.all_gather_into_tensor(self.dx_all, self.dx_send, group=self.group)
+        eng.dp_apply(self.gru_grads, self.dx_all)
 
     def run(self, batch, hp, main_net, losses_out, has_q):
         Bg = batch.B

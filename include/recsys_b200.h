@@ -193,6 +193,24 @@ int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float 
 int rec_train_phase_c(rec_engine *e, const float *q_reduced, float *losses_out, float *dh_out);
 int rec_train_phase_d(rec_engine *e, const float *dh_reduced);
 
+/* Data-parallel trunk for the sharded step (the heads stay sharded by vocabulary and see the global batch; the
+ * replicated embedding + GRU run on each rank's OWN sessions only, so their cost does not grow with the number
+ * of GPUs).  Sequence per step, collectives by the caller:
+ *   rec_dp_forward(local batch)            -> packed_out[rec_dp_packed_bytes(B_local)]          all-gather
+ *   rec_dp_unpack(gathered, G, B_local)    -> global batch fields (+ final states inside the engine)
+ *   rec_train_phase_a_heads / _b / _c      (as rec_train_phase_a/b/c, without the GRU forward)  all-reduce dh
+ *   rec_dp_backward(dh_reduced, rank)      -> gru_grads_out[rec_dp_grad_floats()]               all-reduce
+ *                                          -> dx_out[B_local * L * dirs * E]                    all-gather
+ *   rec_dp_apply(gru_grads_reduced, dx_gathered)   identical Adam update of the replicas on every rank */
+int64_t rec_dp_packed_bytes(const rec_engine *e, int B_local);
+int64_t rec_dp_grad_floats(const rec_engine *e);
+int rec_dp_forward(rec_engine *e, const rec_batch *local_b, int main_net, void *packed_out);
+int rec_dp_unpack(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *global_out);
+int rec_train_phase_a_heads(rec_engine *e, const rec_batch *global_b, const rec_train_hparams *hp, int main_net,
+                            float *records_out);
+int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank, float *gru_grads_out, float *dx_out);
+int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const float *dx_gathered);
+
 /* Input plumbing of sharded runs: one rank's batch packed into ONE byte buffer (so a single all-gather moves
  * every field), and the inverse for the gathered [n_ranks][rec_packed_batch_bytes] buffer -> field arrays of
  * n_ranks*B_local rows (caller-owned; out->B is ignored). */

@@ -415,18 +415,32 @@ def test_vocab_sharded_phases_equal_unsharded_and_oracle(pkg):
             assert torch.equal(shards[0]._nets[net_i].state_dict()[k], shards[1]._nets[net_i].state_dict()[k])
 
 
-def test_multi_gpu_equals_oracle_when_two_gpus_present(pkg):
-    """Runs tests/dist_equivalence.py under torchrun over NCCL when the box has >= 2 GPUs."""
+def _run_dist_equivalence(nproc, port, env_extra):
     import os
     import subprocess
     import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs (covered by the virtual-rank test on one GPU)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29613", os.path.join(root, "tests", "dist_equivalence.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "dist_equivalence.py")]
+    env = dict(os.environ, **env_extra)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "dist_equivalence ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("trunk", ["replicated", "data_parallel"])
+def test_sharded_step_under_torchrun_world1(pkg, trunk):
+    """tests/dist_equivalence.py with ONE rank over NCCL: the whole sharded driver (packed all-gather, phases,
+    collectives, torch CUDA-graph capture + replay, and with `data_parallel` the rec_dp_* trunk entry points)
+    against the oracle, on a single GPU."""
+    _run_dist_equivalence(1, 29614, {"REC_DP_TRUNK": "1"} if trunk == "data_parallel" else {"REC_NO_DP_TRUNK": "1"})
+
+
+@pytest.mark.parametrize("trunk", ["replicated", "data_parallel"])
+def test_multi_gpu_equals_oracle_when_two_gpus_present(pkg, trunk):
+    """Runs tests/dist_equivalence.py under torchrun over NCCL when the box has >= 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (covered by the virtual-rank and world-1 tests on one GPU)")
+    _run_dist_equivalence(2, 29613, {"REC_DP_TRUNK": "1"} if trunk == "data_parallel" else {"REC_NO_DP_TRUNK": "1"})
 
 
 def test_tensor_core_heads_agree_with_cuda_core_heads(pkg):
