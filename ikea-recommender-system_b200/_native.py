@@ -47,7 +47,8 @@ class RecTrainHparams(C.Structure):
                 ("gamma", C.c_float), ("alpha", C.c_float), ("q_weights", C.c_float * 3),
                 ("div_emb", C.c_void_p), ("div_dim", C.c_int32), ("topk_div", C.c_int32),
                 ("topk_nov", C.c_int32), ("nov_reward", C.c_float), ("unpopular", C.c_void_p),
-                ("out_to_in", C.c_void_p), ("pad_pos_end", C.c_int32)]
+                ("out_to_in", C.c_void_p), ("pad_pos_end", C.c_int32), ("dropout_p", C.c_float),
+                ("dropout_seed", C.c_uint64), ("dropout_mask", C.c_void_p)]
 
 
 class RecEvalOpts(C.Structure):

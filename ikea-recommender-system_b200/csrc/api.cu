@@ -126,6 +126,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   ALLOC(e, e->rewards, float, mb * 3);
   ALLOC(e, e->loss_buf, float, 8);
   ALLOC(e, e->astar, int32_t, mb);
+  ALLOC(e, e->drop_mask, uint8_t, mb * D);
   ALLOC(e, extra(e).q_loss_rows, float, mb);
   ALLOC(e, e->summary, float, mb * e->part_stride);
   ALLOC(e, e->d_sc, float, 4);
@@ -200,7 +201,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   cudaStreamSynchronize(e->stream);
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
-                  e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar,
+                  e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar, e->drop_mask,
                   extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_csort, e->emb_ccount, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int n = 0; n < REC_MAX_NETS; ++n)
@@ -516,7 +517,9 @@ static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hp
                            float step_size, float bc2_sqrt) {
   int rc;
   const int B = b->B;
+  const bool drop = hp->dropout_p > 0.f;
   if ((rc = launch_gru_forward(e, 0, b->s, b->true_len, B, e->h_state[0], true))) return rc;
+  if (drop && (rc = launch_dropout(e, 0, e->h_state[0], nullptr, B, hp, false))) return rc;  // heads see the dropped state
   HeadStatsArgs a = {};
   a.net_id = 0; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
   int n_split = 0;
@@ -525,6 +528,7 @@ static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hp
   if ((rc = launch_loss_reduce(e, B, nullptr, e->loss_buf))) return rc;
   REC_CUDA(e, cudaMemcpyAsync(loss_out, e->loss_buf, sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
   if ((rc = launch_head_backward_adam(e, 0, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;
+  if (drop && (rc = launch_dropout(e, 0, nullptr, e->dh, B, hp, true))) return rc;           // dL/dh through the mask
   return trunk_backward(e, 0, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp, false);
 }
 
@@ -533,6 +537,7 @@ extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, cons
   if (rc) return rc;
   if ((rc = check_batch(e, b, false))) return rc;
   if (!hp || !loss_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_supervised: null argument");
+  if (hp->dropout_p < 0.f || hp->dropout_p >= 1.f) REC_FAIL(e, REC_EINVAL, "dropout_p must be in [0, 1)");
   if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
   float step_size, bc2_sqrt;
   adam_scalars(e, 0, hp, &step_size, &bc2_sqrt);
@@ -553,6 +558,7 @@ extern "C" int rec_train_step_supervised_host(rec_engine *e, const rec_batch *ho
   if (rc) return rc;
   if ((rc = check_batch(e, host_b, false))) return rc;
   if (!hp || !loss_host) REC_FAIL(e, REC_EINVAL, "rec_train_step_supervised_host: null argument");
+  if (hp->dropout_p < 0.f || hp->dropout_p >= 1.f) REC_FAIL(e, REC_EINVAL, "dropout_p must be in [0, 1)");
   if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "sharded engine: use the rec_train_phase_* entry points");
   float step_size, bc2_sqrt;
   adam_scalars(e, 0, hp, &step_size, &bc2_sqrt);

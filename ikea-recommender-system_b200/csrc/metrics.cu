@@ -67,6 +67,39 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const float *__restric
   if (threadIdx.x == 0) { out[0] = sh[0][0] / (float)B; out[1] = sh[1][0] / (float)B; }
 }
 
+// ---- dropout on the final GRU state (BidirGRU4Rec/model.py:60,93) ---------------------------------------
+// keep = injected mask, or a counter-based draw from (seed, Adam step of this net, element): no RNG state to
+// carry, the step counter lives in device memory so that a replayed graph draws a fresh mask every step.
+__device__ __forceinline__ float u01_hash(unsigned long long seed, unsigned long long t, unsigned long long i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (t * 0x100000001B3ull + i + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;   // splitmix64 finaliser
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+__global__ void dropout_fwd_kernel(float *__restrict__ h, int n, float p, unsigned long long seed,
+                                   const long long *__restrict__ d_step, const uint8_t *__restrict__ injected,
+                                   uint8_t *__restrict__ mask_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool keep = injected ? injected[i] != 0 : u01_hash(seed, (unsigned long long)*d_step, (unsigned long long)i) >= p;
+  mask_out[i] = keep ? 1 : 0;
+  h[i] = keep ? h[i] / (1.f - p) : 0.f;
+}
+__global__ void dropout_bwd_kernel(float *__restrict__ dh, int n, float p, const uint8_t *__restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dh[i] = mask[i] ? dh[i] / (1.f - p) : 0.f;
+}
+int launch_dropout(rec_engine *e, int net_id, float *h, float *dh, int B, const rec_train_hparams *hp, bool backward) {
+  const int n = B * e->D;
+  if (backward) dropout_bwd_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(dh, n, hp->dropout_p, e->drop_mask);
+  else dropout_fwd_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(h, n, hp->dropout_p, hp->dropout_seed, e->d_step + net_id,
+                                                              hp->dropout_mask, e->drop_mask);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
 // ---- evaluation metrics ----------------------------------------------------------------------------
 // One warp per row -> per-row metric record rowm[b][0..M): hits[n_k], ndcg[n_k], reps[n_k], div, nov, ce
 __global__ void __launch_bounds__(256) eval_rows_kernel(int B, int L, int N, int V, const int64_t *__restrict__ s,

@@ -173,7 +173,7 @@ class NativeSessionNet(nn.Module):
         s, lengths = self._dev_inputs(s, lengths)
         h = eng.forward_state(self._net_id, s, lengths)
         if self._family == "bidir" and self.training and self.dropout.p > 0:
-            raise NotImplementedError("BidirGRU4Rec dropout > 0 in training mode is not implemented natively yet")
+            h = self.dropout(h)  # API-compatibility path only (BidirGRU4Rec/model.py:93); training runs in train_step
         return [eng.head_logits(self._net_id, i, h) for i in range(len(self._HEADS[self._family]))]
 
     def forward(self, s, lengths):

@@ -21,6 +21,8 @@ class BidirGRU4Rec_trainer(NativeTrainerBase):
                  learning_rate, item_num, state_size, action_dim, device, padding_idx=None, torch_rand_seed=118,
                  python_rand_seed=999):
         self._seed(torch_rand_seed, python_rand_seed)
+        self._dropout_seed = int(torch_rand_seed)   # seed of the device-side dropout mask stream
+        self.dropout_mask_override = None           # optional uint8 [B, 2H] keep mask for the next steps (tests)
         self.gru_model = BidirGRU4Rec(hidden_size=hidden_dim, embedding_dim=embedding_dim,
                                       train_pad_embed=train_pad_embed, use_packed_seq=use_packed_seq,
                                       item_num=item_num, state_size=state_size, action_dim=action_dim,

@@ -9,13 +9,26 @@ import torch
 from .._base import make_hparams
 
 
+def _supervised_hparams(trainer):
+    """Adam hyper-parameters + the BidirGRU4Rec dropout of the supervised step (train mode only)."""
+    net = trainer.gru_model
+    hp = make_hparams(trainer.learning_rate)
+    if net._family == "bidir" and net.training and net.dropout.p > 0:
+        if trainer._shard is not None:
+            raise NotImplementedError("dropout > 0 is not implemented for the vocabulary-sharded step")
+        hp.dropout_p = float(net.dropout.p)
+        hp.dropout_seed = int(getattr(trainer, "_dropout_seed", 118))
+        mask = getattr(trainer, "dropout_mask_override", None)  # device uint8 [B, 2H], 1 = keep (parity tests)
+        if mask is not None:
+            trainer._dropout_mask_keepalive = mask = mask.to(device=net._param_device(), dtype=torch.uint8).contiguous()
+            hp.dropout_mask = mask.data_ptr()
+    return hp
+
+
 def supervised_train_step(trainer, s, a, true_len) -> torch.Tensor:
     """GRU4Rec_trainer / BidirGRU4Rec_trainer.train_step (GRU4Rec/model.py:129-155)."""
-    net = trainer.gru_model
-    if net._family == "bidir" and net.training and net.dropout.p > 0:
-        raise NotImplementedError("BidirGRU4Rec dropout > 0 in training mode is not implemented natively yet")
     B = int(s.shape[0])
-    hp = make_hparams(trainer.learning_rate)
+    hp = _supervised_hparams(trainer)
     if trainer._shard is not None:
         return _sharded_step(trainer, hp, 0, s, a, true_len)[0]
     eng = trainer._ready(B)
@@ -39,14 +52,11 @@ def host_path(trainer, s) -> bool:
 
 def supervised_train_step_host(trainer, s, a, true_len) -> float:
     """GRU4Rec_trainer / BidirGRU4Rec_trainer.train_step with CPU tensors: rec_train_step_supervised_host."""
-    net = trainer.gru_model
-    if net._family == "bidir" and net.training and net.dropout.p > 0:
-        raise NotImplementedError("BidirGRU4Rec dropout > 0 in training mode is not implemented natively yet")
     B = int(s.shape[0])
     eng = trainer._ready(B)
     hs, ha, hl = _host(s, torch.int64), _host(a, torch.int64), _host(true_len, torch.int64)
     trainer._stager.h2d_bytes = eng.host_batch_bytes
-    return eng.train_step_supervised_host(eng._batch(B, hs, ha, hl), make_hparams(trainer.learning_rate))
+    return eng.train_step_supervised_host(eng._batch(B, hs, ha, hl), _supervised_hparams(trainer))
 
 
 def q_train_step_host(trainer, hp, s, a, r, s_next, true_len, true_next_len, is_end, main=None):

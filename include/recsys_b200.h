@@ -104,6 +104,13 @@ typedef struct rec_train_hparams {
   const uint8_t *unpopular;    /* bitmap-as-bytes [V]: 1 if action id is in the unpopular set */
   const int64_t *out_to_in;    /* optional LUT [V]: output-token id -> input-token id (NULL = identity) */
   int32_t pad_pos_end;         /* 1: "end" padding (last action = s[len-1]); 0: "beg" (s[L-1]) */
+  /* BidirGRU4Rec: nn.Dropout(p) on concat(h_fwd, h_bwd) in train mode (BidirGRU4Rec/model.py:60,93), supervised
+   * step only.  The keep mask is drawn on the device from (dropout_seed, Adam step, element) unless
+   * dropout_mask (device uint8 [B, D], 1 = keep) injects one -- torch's Philox stream cannot be reproduced, so
+   * parity tests feed the same mask to the oracle.  dropout_p = 0 disables. */
+  float dropout_p;
+  uint64_t dropout_seed;
+  const uint8_t *dropout_mask;
 } rec_train_hparams;
 
 /* Options of one evaluation sweep: the keyword arguments of evaluate()/update_train_metrics()

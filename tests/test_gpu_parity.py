@@ -577,3 +577,62 @@ def test_host_entry_and_device_entry_agree_bitwise(pkg, graphs):
     assert l_host == l_dev
     for k in p_host:
         assert torch.equal(p_host[k], p_dev[k]), k
+
+
+class _FixedMaskDropout(torch.nn.Module):
+    """nn.Dropout with the keep mask supplied from outside (what the oracle needs to share a mask with the GPU)."""
+
+    def __init__(self, p):
+        super().__init__()
+        self.p, self.mask = p, None
+
+    def forward(self, x):
+        return x * self.mask.to(x.dtype) / (1.0 - self.p) if self.training else x
+
+
+@pytest.mark.gpu
+def test_bidir_dropout_train_step_matches_oracle_with_shared_mask(pkg):
+    """BidirGRU4Rec/model.py:60,93: dropout on concat(h_fwd, h_bwd) in train mode.  torch's Philox stream cannot be
+    reproduced on the device, so both sides get the same keep mask (A18 in SURVEY.md section 8a)."""
+    V, L, B, H, p, steps = 3000, 10, 96, 64, 0.3, 4
+    kw = dict(hidden_dim=H, embedding_dim=64, gru_layers=1, dropout=p, train_pad_embed=True, use_packed_seq=True,
+              learning_rate=0.01, item_num=V, state_size=L, action_dim=V)
+    t = pkg.BidirGRU4Rec_trainer(device=DEV, **kw)
+    ref = oracle.GRUTrainer(family="bidir", **kw)
+    ref.gru_model.dropout = _FixedMaskDropout(p)
+    assert_state_close(t.gru_model.state_dict(), ref.gru_model.state_dict(), rtol=0, atol=0)
+    t.send_to_device(); t.set_train(); ref.gru_model.train()
+    rows = _syn().make_replay_rows(steps * B, V, L, seed=11)
+    g = torch.Generator().manual_seed(5)
+    for i in range(steps):
+        s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+        mask = (torch.rand(B, 2 * H, generator=g) >= p).to(torch.uint8)
+        ref.gru_model.dropout.mask = mask
+        t.dropout_mask_override = mask
+        want = ref.train_step(s, a, ln)
+        got = t.train_step(s, a, ln)
+        assert_close([got], [want], rtol=RTOL, atol=1e-5, what=f"step {i} loss with dropout")
+    assert_state_close(t.gru_model.state_dict(), ref.gru_model.state_dict(), rtol=RTOL, atol=ATOL_P, **OUT)
+
+
+@pytest.mark.gpu
+def test_bidir_dropout_device_rng_is_deterministic_and_active(pkg):
+    """Without an injected mask the keep mask comes from (seed, Adam step, element): same seed -> same run,
+    dropout on != dropout off, eval mode ignores it."""
+    V, L, B, H = 2000, 10, 64, 64
+    kw = dict(hidden_dim=H, embedding_dim=64, gru_layers=1, train_pad_embed=True, use_packed_seq=True,
+              learning_rate=0.01, item_num=V, state_size=L, action_dim=V)
+    rows = _syn().make_replay_rows(4 * B, V, L, seed=12)
+
+    def run(p, seed):
+        t = pkg.BidirGRU4Rec_trainer(device=DEV, dropout=p, torch_rand_seed=seed, **kw)
+        t.send_to_device(); t.set_train()
+        out = []
+        for i in range(4):
+            s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+            out.append(t.train_step(s, a, ln))
+        return out
+
+    a1, a2, b0 = run(0.5, 118), run(0.5, 118), run(0.0, 118)
+    assert a1 == a2
+    assert all(abs(x - y) > 1e-6 for x, y in zip(a1[1:], b0[1:]))   # step 0 losses may coincide only by accident
