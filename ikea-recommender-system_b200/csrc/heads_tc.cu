@@ -17,6 +17,7 @@
 #include "tc.cuh"
 
 #define PART_TOPK_OFF 5
+#define LOG2E_F 1.4426950408889634f
 constexpr int BLK = 128 * 128;  // bytes of one [128 rows][64 bf16] operand block
 
 struct TcHeadPtrs {
@@ -73,253 +74,429 @@ __device__ __noinline__ void topk_insert_chunk(const float *lbuf, float *lv, int
   }
 }
 
-// NB = 128-session blocks per CTA (they share every converted W tile), NT = threads (256: two 64-column
-// halves per row, 512: four 32-column quarters per row).  TMEM: NB x 2 accumulator tiles of 128 columns.
-template <int NB, int NT>
-__global__ void __launch_bounds__(NT, 1) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
-                                                              int vocab_lo, int n_tiles, int do_stats, int first_head,
-                                                              int upg, float w0, float w1, float w2,
-                                                              const int64_t *__restrict__ target, int topk,
-                                                              float *__restrict__ part, int part_stride,
-                                                              long long *__restrict__ trace) {
+// NB = 128-session blocks per CTA (they share every converted W tile), NT = compute threads (256: two
+// 64-column halves per row, 512: four 32-column quarters per row) + ONE extra warp that only issues MMAs.
+// ARG = greedy-action mode: the `nh` Q heads are pre-combined while they are converted,
+//   sum_j w_j (h . W_j[a] + b_j[a]) = h . (sum_j w_j W_j[a]) + sum_j w_j b_j[a],
+// so a vocabulary tile costs ONE set of MMAs whatever the number of heads.
+// TMEM: 2 x NB accumulator tiles of 128 columns (double-buffered over units).
+//
+// Warp roles (no block-wide barrier inside the main loop -- tcgen05.mma issue blocks the issuing thread
+// for about as long as the tensor pipe needs, which used to stall every warp at the next __syncthreads):
+//   compute warps: store(u+1) [regs -> bf16 hi/lo smem stage], fetch(u+2) [global -> regs], arrive full[(u+1)&1],
+//                  wait done[u&1], epilogue(u) from TMEM[u&1]
+//   issuer warp  : wait full[u&1] (all compute warps stored unit u), issue MMAs(u) -> commit done[u&1]
+// Stage / TMEM buffer (u&1) is reused by unit u+2: every compute warp stores unit u+2 only after it has seen
+// done[u&1] (MMA(u) complete) and finished epilogue(u) in program order.
+// RING = the fp32 weight tiles arrive by TMA bulk copies into a ring of `n_slots` 32 KB shared-memory slots filled
+// by a LOADER warp (per-thread global loads of a whole tile ran into the SM's outstanding-request limit: ~6000
+// cycles per tile); the compute warps read their share of a slot, release it, and convert from registers.
+template <int NB, int NT, bool ARG, bool RING>
+__global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
+                                                                   int vocab_lo, int n_tiles, int do_stats, int first_head,
+                                                                   int nh, float w0, float w1, float w2,
+                                                                   const int64_t *__restrict__ target, int topk,
+                                                                   float *__restrict__ part, int part_stride,
+                                                                   long long *__restrict__ trace, int n_slots) {
   int tr_n = 0;
-#define STRACE(tag) do { if (trace && do_stats && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && tr_n < 120) { trace[2 * tr_n] = (tag); trace[2 * tr_n + 1] = clock64(); ++tr_n; } } while (0)
+#define STRACE(tag) do { if (trace && (ARG || do_stats) && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && tr_n < 120) { asm volatile("" ::: "memory"); trace[2 * tr_n] = (tag); trace[2 * tr_n + 1] = clock64(); ++tr_n; asm volatile("" ::: "memory"); } } while (0)
   constexpr int CS = NT / 128;   // column splits per row
   constexpr int CW = 128 / CS;   // columns per thread and tile
   constexpr int TASKS = 1024 / NT;  // 16-byte chunk pairs per thread when staging a [128 x 64] fp32 tile
+  constexpr int NH = (ARG && !RING) ? 3 : 1;   // head tiles a thread keeps in flight per unit (register-fetch path)
   extern __shared__ uint8_t raw[];
-  uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);  // 1024-aligned; offset arithmetic keeps the pointer provably shared (LDS/STS, not generic LD/ST)
+  constexpr int NST = RING ? 1 : 2;  // bf16 W stages (RING: the TMEM double buffer alone overlaps MMA(u+1) with epilogue(u))
   uint8_t *h_blk = sm;                                            // [NB][hi|lo] x BLK
   uint8_t *w_st = sm + NB * 2 * BLK;                              // stage s: hi at w_st + s*2*BLK, lo at + BLK
-  float *bias_g = reinterpret_cast<float *>(w_st + 4 * BLK);     // [3][128] (3-deep: a thread may run one barrier ahead)
-  float *xch = bias_g + 384;                                      // [NB][128][CS][5] end-of-kernel exchange
-  float *tv = xch + NB * 128 * CS * 5;                            // [NB][topk][NT]
+  float *bias_g = reinterpret_cast<float *>(w_st + NST * 2 * BLK);  // [4][128] (a warp may run up to 3 units ahead of another)
+  float *tv = bias_g + 512;                                       // [NB][topk][NT]
   int *ti = reinterpret_cast<int *>(tv + (size_t)NB * topk * NT); // [NB][topk][NT]
-  __shared__ uint64_t mbar[2];
+  float *stg = reinterpret_cast<float *>(ti + (size_t)NB * topk * NT);  // RING: [n_slots][128 x 64] fp32 (every region before it is a multiple of 128 B)
+  float *xch = stg;                                               // [NB][128][CS][5] end-of-kernel exchange (RING: reuses the slots)
+  __shared__ uint64_t mbar_done[2], mbar_full[2], slot_full[4], slot_free[4];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column split
+  const bool issuer = warp == NT / 32, loader = RING && warp == NT / 32 + 1;
+  const int q = warp & 3, cq = (warp >> 2) & (CS - 1);  // TMEM lane quarter, column split
   const int sp = blockIdx.x, n_split = gridDim.x, bg = blockIdx.y;
   const int b0 = bg * NB * 128;
   const int per = (n_tiles + n_split - 1) / n_split;
   const int t_lo = sp * per, t_hi = min(n_tiles, t_lo + per);
-  const int n_groups = max(0, t_hi - t_lo), n_units = n_groups * upg;
-  const bool argmode = !do_stats && topk == 0;
+  const int n_units = max(0, t_hi - t_lo);
 
   STRACE(19);
-  if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_barrier_init(); }
+  if (tid == 0) {
+    tc::mbar_init(&mbar_done[0], 1); tc::mbar_init(&mbar_done[1], 1);
+    tc::mbar_init(&mbar_full[0], NT / 32); tc::mbar_init(&mbar_full[1], NT / 32);
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&slot_full[i], 1); tc::mbar_init(&slot_free[i], NT / 32); }
+    tc::fence_barrier_init();
+  }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, NB * 256);
   // h blocks of this CTA -> bf16 hi/lo (zero rows beyond B)
-  for (int nb = 0; nb < NB; ++nb) {
-#pragma unroll
-    for (int i = 0; i < TASKS; ++i) {
-      const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if (b0 + nb * 128 + row < B) {
-        const float4 *p = reinterpret_cast<const float4 *>(h + (int64_t)(b0 + nb * 128 + row) * 64 + c8 * 8);
-        a = p[0];
-        b = p[1];
-      }
-      tc::store_split8(h_blk + nb * 2 * BLK, h_blk + nb * 2 * BLK + BLK, row, c8, a, b);
-    }
-  }
-
-  // unit u = (vocabulary tile g, head hh).  fetch(): global -> registers (in flight across a whole
-  // pipeline step); store(): registers -> bf16 hi/lo swizzled smem stage + bias tile.
-  float4 fa[TASKS], fb[TASKS];
-  float fbias = 0.f;
-  auto unit_scale = [&](int hh) { return (argmode && upg > 1) ? (hh == 0 ? w0 : (hh == 1 ? w1 : w2)) : 1.f; };
-  auto fetch = [&](int u) {
-    const int g = u / upg, hh = u - g * upg, head = first_head + hh, v0 = (t_lo + g) * 128;
-    const float *src = hp.w[head];
-#pragma unroll
-    for (int i = 0; i < TASKS; ++i) {
-      const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
-      fa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      fb[i] = fa[i];
-      if (v0 + row < Vloc) {
-        const float4 *p = reinterpret_cast<const float4 *>(src + (int64_t)(v0 + row) * 64 + c8 * 8);
-        fa[i] = p[0];
-        fb[i] = p[1];
-      }
-    }
-    fbias = (tid < 128 && v0 + tid < Vloc) ? __ldg(hp.b[head] + v0 + tid) : 0.f;
-  };
-  auto store = [&](int u) {
-    const int g = u / upg, hh = u - g * upg, s = u & 1;
-    const float scale = unit_scale(hh);
-    uint8_t *bh = w_st + s * 2 * BLK, *bl = bh + BLK;
-#pragma unroll
-    for (int i = 0; i < TASKS; ++i) {
-      const int c = tid + NT * i;
-      if (scale != 1.f) {
-        fa[i].x *= scale; fa[i].y *= scale; fa[i].z *= scale; fa[i].w *= scale;
-        fb[i].x *= scale; fb[i].y *= scale; fb[i].z *= scale; fb[i].w *= scale;
-      }
-      tc::store_split8(bh, bl, c >> 3, c & 7, fa[i], fb[i]);
-    }
-    if (tid < 128) {
-      float *dst = bias_g + (g % 3) * 128 + tid;
-      *dst = (hh == 0) ? fbias * scale : (*dst + fbias * scale);
-    }
-  };
-  const uint32_t id_l = tc::instr_desc(128, 128, 0, 0);
-  auto issue_unit = [&](int u) {  // one thread: NB logits tiles against the same W stage
-    const int g = u / upg, hh = u - g * upg, s = u & 1;
-    const uint64_t bh = tc::desc_kmajor(tc::smem_u32(w_st + s * 2 * BLK), 0), bl = tc::desc_kmajor(tc::smem_u32(w_st + s * 2 * BLK + BLK), 0);
-#pragma unroll
+  if (tid < NT) {
     for (int nb = 0; nb < NB; ++nb) {
-      const uint32_t d = tmem_base_s + (uint32_t)((g & 1) * NB + nb) * 128;
-      const uint64_t ah = tc::desc_kmajor(tc::smem_u32(h_blk + nb * 2 * BLK), 0), al = tc::desc_kmajor(tc::smem_u32(h_blk + nb * 2 * BLK + BLK), 0);
-      bool acc = hh > 0;
 #pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { tc::mma_bf16(d, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id_l, acc); acc = true; }
+      for (int i = 0; i < TASKS; ++i) {
+        const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (b0 + nb * 128 + row < B) {
+          const float4 *p = reinterpret_cast<const float4 *>(h + (int64_t)(b0 + nb * 128 + row) * 64 + c8 * 8);
+          a = p[0];
+          b = p[1];
+        }
+        tc::store_split8(h_blk + nb * 2 * BLK, h_blk + nb * 2 * BLK + BLK, row, c8, a, b);
       }
     }
-    tc::mma_commit(&mbar[s]);
-  };
-
-  // per-thread running state per block: row (b0 + nb*128 + q*32 + lane), tile columns [cq*CW, cq*CW + CW)
-  float m_run[NB], s_run[NB], tgt[NB], av[NB], tau[NB];
-  int ai[NB], cnt[NB], trow[NB];
-  float r_v0[NB], r_v1[NB];  // top-k <= 2 lives in registers (no warm-up cost when a CTA only sees a few tiles)
-  int r_i0[NB], r_i1[NB];
-  const bool smallk = topk > 0 && topk <= 2;
-#pragma unroll
-  for (int nb = 0; nb < NB; ++nb) {
-    m_run[nb] = REC_NEG_INF; s_run[nb] = 0.f; tgt[nb] = REC_NEG_INF; av[nb] = REC_NEG_INF; tau[nb] = REC_NEG_INF;
-    ai[nb] = 0x7fffffff; cnt[nb] = 0;
-    r_v0[nb] = REC_NEG_INF; r_v1[nb] = REC_NEG_INF; r_i0[nb] = 0x7fffffff; r_i1[nb] = 0x7fffffff;
-    const int row = b0 + nb * 128 + q * 32 + lane;
-    trow[nb] = (do_stats && target && row < B) ? (int)(target[row] - vocab_lo) : -1;
   }
-
-  STRACE(20);
-  if (n_units > 0) { fetch(0); store(0); }
-  if (n_units > 1) fetch(1);
-  STRACE(21);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  if (n_units > 0 && tid == 0) issue_unit(0);
+  const uint32_t tmem_base = tmem_base_s;
+  STRACE(20);
 
-  for (int u = 0; u < n_units; ++u) {
-    STRACE(1);
-    if (u + 1 < n_units) {
-      if (u >= 1) tc::mbar_wait(&mbar[(u + 1) & 1], ((u - 1) >> 1) & 1);  // MMA(u-1) done: its smem stage is free
-      STRACE(2);
-      store(u + 1);
-      STRACE(3);
-      if (u + 2 < n_units) fetch(u + 2);  // lands while this step's barrier / MMA wait / epilogue run
+  if (issuer) {
+    // ---- MMA issuer warp: NB logits tiles against the same W stage per unit ----
+    const uint32_t id_l = tc::instr_desc(128, 128, 0, 0);
+    // weight tiles -> L2 a few units ahead of the compute warps' register loads (units 0 and 1 are fetched directly)
+    constexpr int PD = 3;
+    auto l2_ahead = [&](int u) {
+      const int v0 = (t_lo + u) * 128;
+      const uint32_t bytes = (uint32_t)min(128, Vloc - v0) * 256u;
+      for (int hh = 0; hh < nh; ++hh) tc::l2_prefetch(hp.w[first_head + hh] + (int64_t)v0 * 64, bytes);
+    };
+    if (!RING && lane == 0)
+      for (int u = 2; u < min(n_units, 2 + PD); ++u) l2_ahead(u);
+    for (int u = 0; u < n_units; ++u) {
+      const int s = u & 1, ws = u & (NST - 1);
+      if (!RING && lane == 0 && u + 2 + PD < n_units) l2_ahead(u + 2 + PD);
+      tc::mbar_wait(&mbar_full[s], (u >> 1) & 1);
+      tc::tc_fence_after();
+      if (lane == 0) {
+        const uint64_t bh = tc::desc_kmajor(tc::smem_u32(w_st + ws * 2 * BLK), 0), bl = tc::desc_kmajor(tc::smem_u32(w_st + ws * 2 * BLK + BLK), 0);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const uint32_t d = tmem_base + (uint32_t)(s * NB + nb) * 128;
+          const uint64_t ah = tc::desc_kmajor(tc::smem_u32(h_blk + nb * 2 * BLK), 0), al = tc::desc_kmajor(tc::smem_u32(h_blk + nb * 2 * BLK + BLK), 0);
+          bool acc = false;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { tc::mma_bf16(d, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id_l, acc); acc = true; }
+          }
+        }
+        tc::mma_commit(&mbar_done[s]);
+      }
+      __syncwarp();
     }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    STRACE(4);
-    if (u + 1 < n_units && tid == 0) issue_unit(u + 1);
-    STRACE(5);
-    const int g = u / upg;
-    if (u - g * upg != upg - 1) continue;  // accumulate the remaining heads of this group first
-    tc::mbar_wait(&mbar[u & 1], (u >> 1) & 1);
-    tc::tc_fence_after();
-    STRACE(6);
-    // ---- epilogue of group g: NB blocks x CW columns in chunks of 32 ----
-    const int v0 = (t_lo + g) * 128;
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-#pragma unroll 1
-      for (int half = 0; half < CW / 32; ++half) {
-        const int c_lo = v0 + cq * CW + half * 32;
-        float l[32];
-        tc::tmem_ld32(tmem_base_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(((g & 1) * NB + nb) * 128 + cq * CW + half * 32), l);
-        const float *bgp = bias_g + (g % 3) * 128 + cq * CW + half * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 b4 = *reinterpret_cast<const float4 *>(bgp + j);
-          l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
-        }
-        if (c_lo + 32 > Vloc) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
-        }
-        if (do_stats) {
-          float tmax = REC_NEG_INF;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
-          const float nm = fmaxf(m_run[nb], tmax);
-          float ps = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) ps += __expf(l[j] - nm);
-          s_run[nb] = s_run[nb] * __expf(m_run[nb] - nm) + ps;
-          m_run[nb] = nm;
-          if (trow[nb] >= c_lo && trow[nb] < c_lo + 32) {
-            const int tj = trow[nb] - c_lo;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j == tj) tgt[nb] = l[j];
-          }
-        }
-        if (topk > 0) {
-          // fast path: nothing in this chunk beats the current k-th best (one compare against the chunk max);
-          // the insertion code exists once, out of line, and walks the chunk from local memory
-          float cmax = l[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, l[j]);
-          if (smallk) {
-            if (cmax > tau[nb]) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float v = l[j];
-                const int id = vocab_lo + c_lo + j;
-                const bool g0 = v > r_v0[nb], g1 = v > r_v1[nb];
-                r_v1[nb] = g0 ? r_v0[nb] : (g1 ? v : r_v1[nb]);
-                r_i1[nb] = g0 ? r_i0[nb] : (g1 ? id : r_i1[nb]);
-                r_v0[nb] = g0 ? v : r_v0[nb];
-                r_i0[nb] = g0 ? id : r_i0[nb];
-              }
-              tau[nb] = topk == 1 ? r_v0[nb] : r_v1[nb];
-            }
-          } else if (cmax > tau[nb]) {
-            float lbuf[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) lbuf[j] = l[j];
-            topk_insert_chunk(lbuf, tv + (size_t)nb * topk * NT + tid, ti + (size_t)nb * topk * NT + tid, NT, topk,
-                              vocab_lo + c_lo, cnt[nb], tau[nb]);
-          }
-        }
-        if (argmode) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (l[j] > av[nb]) { av[nb] = l[j]; ai[nb] = vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+  } else if (loader) {
+    // ---- TMA loader warp: (unit, head) tiles in order into the slot ring ----
+    if (lane == 0) {
+      int sl = 0;
+      uint32_t round = 0;
+      for (int u = 0; u < n_units; ++u) {
+        const int v0 = (t_lo + u) * 128;
+        const uint32_t bytes = (uint32_t)min(128, Vloc - v0) * 256u;
+        for (int hh = 0; hh < nh; ++hh) {
+          if (round > 0) tc::mbar_wait(&slot_free[sl], (round - 1) & 1);
+          tc::mbar_expect_tx(&slot_full[sl], bytes);
+          tc::bulk_g2s(stg + sl * 8192, hp.w[first_head + hh] + (int64_t)v0 * 64, bytes, &slot_full[sl]);
+          if (++sl == n_slots) { sl = 0; ++round; }
         }
       }
     }
-  }
-
-  STRACE(30);
-  // ---- combine the CS column splits of every row inside the CTA, then publish ONE record per row ----
+  } else {
+    // ---- compute warps ----
+    // unit u = vocabulary tile t_lo + u.  fetch(): global -> registers (in flight across a whole pipeline step);
+    // store(): registers -> (combined heads) -> bf16 hi/lo swizzled smem stage + bias tile.
+    float4 fa[NH][TASKS], fb[NH][TASKS];
+    float fbias[NH];
+    const float wsc[3] = {(ARG && nh > 1) ? w0 : 1.f, ARG ? w1 : 0.f, ARG ? w2 : 0.f};
+    auto fetch = [&](int u) {
+      const int v0 = (t_lo + u) * 128;
 #pragma unroll
-  for (int nb = 0; nb < NB; ++nb) {
-    float *x = xch + ((nb * 128 + q * 32 + lane) * CS + cq) * 5;
-    x[0] = m_run[nb]; x[1] = s_run[nb]; x[2] = tgt[nb]; x[3] = av[nb]; x[4] = __int_as_float(ai[nb]);
-    if (topk > 0) {  // pad the private list so that the merge below can read topk entries
-      float *lv = tv + (size_t)nb * topk * NT + tid;
-      int *li = ti + (size_t)nb * topk * NT + tid;
-      if (smallk) {
-        lv[0] = r_v0[nb]; li[0] = r_i0[nb];
-        if (topk > 1) { lv[NT] = r_v1[nb]; li[NT] = r_i1[nb]; }
+      for (int hh = 0; hh < NH; ++hh) {
+        fbias[hh] = 0.f;
+#pragma unroll
+        for (int i = 0; i < TASKS; ++i) { fa[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f); fb[hh][i] = fa[hh][i]; }
+        if (hh < nh) {
+          const float *src = hp.w[first_head + hh];
+#pragma unroll
+          for (int i = 0; i < TASKS; ++i) {
+            const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
+            if (v0 + row < Vloc) {
+              const float4 *p = reinterpret_cast<const float4 *>(src + (int64_t)(v0 + row) * 64 + c8 * 8);
+              fa[hh][i] = p[0];
+              fb[hh][i] = p[1];
+            }
+          }
+          if (tid < 128 && v0 + tid < Vloc) fbias[hh] = __ldg(hp.b[first_head + hh] + v0 + tid);
+        }
+      }
+    };
+    auto store = [&](int u) {
+      const int s = u & 1;
+      uint8_t *bh = w_st + s * 2 * BLK, *bl = bh + BLK;
+#pragma unroll
+      for (int i = 0; i < TASKS; ++i) {
+        const int c = tid + NT * i;
+        float4 a = fa[0][i], b = fb[0][i];
+        if (ARG) {
+          a.x *= wsc[0]; a.y *= wsc[0]; a.z *= wsc[0]; a.w *= wsc[0];
+          b.x *= wsc[0]; b.y *= wsc[0]; b.z *= wsc[0]; b.w *= wsc[0];
+#pragma unroll
+          for (int hh = 1; hh < NH; ++hh) {  // heads beyond nh were fetched as zeros
+            a.x = fmaf(wsc[hh], fa[hh][i].x, a.x); a.y = fmaf(wsc[hh], fa[hh][i].y, a.y);
+            a.z = fmaf(wsc[hh], fa[hh][i].z, a.z); a.w = fmaf(wsc[hh], fa[hh][i].w, a.w);
+            b.x = fmaf(wsc[hh], fb[hh][i].x, b.x); b.y = fmaf(wsc[hh], fb[hh][i].y, b.y);
+            b.z = fmaf(wsc[hh], fb[hh][i].z, b.z); b.w = fmaf(wsc[hh], fb[hh][i].w, b.w);
+          }
+        }
+        tc::store_split8(bh, bl, c >> 3, c & 7, a, b);
+      }
+      if (tid < 128) {
+        float bsum = fbias[0] * wsc[0];
+        if (ARG) {
+#pragma unroll
+          for (int hh = 1; hh < NH; ++hh) bsum = fmaf(wsc[hh], fbias[hh], bsum);
+        }
+        bias_g[(u & 3) * 128 + tid] = bsum;
+      }
+    };
+    // RING: this thread's chunk pairs of unit u from the slot ring (heads combined on the fly) -> bf16 stage.
+    // Bank-conflict-free slot reads: the 8 lanes of a row read alternating 16-byte halves of their 32-byte chunk.
+    int g_sl = 0;
+    uint32_t g_round = 0;
+    float4 ga[TASKS], gb[TASKS];
+    auto gather = [&](int u) {
+      const int v0 = (t_lo + u) * 128;
+      for (int hh = 0; hh < nh; ++hh) {
+        tc::mbar_wait(&slot_full[g_sl], g_round & 1);
+        STRACE(41);
+        const float *src = stg + g_sl * 8192;
+        const float w = wsc[hh];
+#pragma unroll
+        for (int i = 0; i < TASKS; ++i) {
+          const int c = tid + NT * i, row = c >> 3, c8 = c & 7, sw = (c8 >> 2) & 1;
+          float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+          if (v0 + row < Vloc) {
+            x0 = *reinterpret_cast<const float4 *>(src + row * 64 + c8 * 8 + 4 * sw);
+            x1 = *reinterpret_cast<const float4 *>(src + row * 64 + c8 * 8 + 4 * (sw ^ 1));
+          }
+          const float4 x = sw ? x1 : x0, y = sw ? x0 : x1;
+          if (hh == 0) {
+            ga[i] = make_float4(x.x * w, x.y * w, x.z * w, x.w * w);
+            gb[i] = make_float4(y.x * w, y.y * w, y.z * w, y.w * w);
+          } else {
+            ga[i].x = fmaf(w, x.x, ga[i].x); ga[i].y = fmaf(w, x.y, ga[i].y); ga[i].z = fmaf(w, x.z, ga[i].z); ga[i].w = fmaf(w, x.w, ga[i].w);
+            gb[i].x = fmaf(w, y.x, gb[i].x); gb[i].y = fmaf(w, y.y, gb[i].y); gb[i].z = fmaf(w, y.z, gb[i].z); gb[i].w = fmaf(w, y.w, gb[i].w);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&slot_free[g_sl]);  // the values are in registers: the loader may refill the slot
+        STRACE(42);
+        if (++g_sl == n_slots) { g_sl = 0; ++g_round; }
+      }
+    };
+    auto store_gathered = [&]() {  // registers -> the (single) bf16 stage; its last reader, MMA(u-1), must be complete
+#pragma unroll
+      for (int i = 0; i < TASKS; ++i) {
+        const int c = tid + NT * i;
+        tc::store_split8(w_st, w_st + BLK, c >> 3, c & 7, ga[i], gb[i]);
+      }
+    };
+    float rb[3] = {0.f, 0.f, 0.f};  // RING: bias values of the next unit (tid < 128), one per head
+    auto bias_fetch = [&](int u) {
+      const int v0 = (t_lo + u) * 128;
+      if (tid < 128) {
+#pragma unroll
+        for (int hh = 0; hh < 3; ++hh) rb[hh] = (hh < nh && v0 + tid < Vloc) ? __ldg(hp.b[first_head + hh] + v0 + tid) : 0.f;
+      }
+    };
+    auto bias_store = [&](int u) {
+      if (tid < 128) bias_g[(u & 3) * 128 + tid] = fmaf(wsc[2], rb[2], fmaf(wsc[1], rb[1], wsc[0] * rb[0]));
+    };
+    auto publish = [&](int u) {  // this warp's share of unit u is in shared memory
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&mbar_full[u & 1]);
+    };
+
+    // per-thread running state per block: row (b0 + nb*128 + q*32 + lane), tile columns [cq*CW, cq*CW + CW)
+    float m_run[NB], s_run[NB], tgt[NB], av[NB], tau[NB];
+    int ai[NB], cnt[NB], trow[NB];
+    float r_v0[NB], r_v1[NB];  // top-k <= 2 lives in registers (no warm-up cost when a CTA only sees a few tiles)
+    int r_i0[NB], r_i1[NB];
+    const bool smallk = topk > 0 && topk <= 2;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      m_run[nb] = REC_NEG_INF; s_run[nb] = 0.f; tgt[nb] = REC_NEG_INF; av[nb] = REC_NEG_INF; tau[nb] = REC_NEG_INF;
+      ai[nb] = 0x7fffffff; cnt[nb] = 0;
+      r_v0[nb] = REC_NEG_INF; r_v1[nb] = REC_NEG_INF; r_i0[nb] = 0x7fffffff; r_i1[nb] = 0x7fffffff;
+      const int row = b0 + nb * 128 + q * 32 + lane;
+      trow[nb] = (!ARG && do_stats && target && row < B) ? (int)(target[row] - vocab_lo) : -1;
+    }
+
+    if (RING) {
+      if (n_units > 0) { bias_fetch(0); gather(0); store_gathered(); bias_store(0); publish(0); }
+      if (n_units > 1) bias_fetch(1);
+    } else {
+      if (n_units > 0) { fetch(0); store(0); publish(0); }
+      if (n_units > 1) fetch(1);
+    }
+    STRACE(21);
+
+    for (int u = 0; u < n_units; ++u) {
+      STRACE(1);
+      if (RING) {
+        if (u + 1 < n_units) gather(u + 1);  // slot ring -> registers (heads combined)
+        STRACE(3);
+        tc::mbar_wait(&mbar_done[u & 1], (u >> 1) & 1);  // MMA(u) complete: logits(u) in TMEM, the bf16 stage is free
+        tc::tc_fence_after();
+        STRACE(5);
+        if (u + 1 < n_units) {
+          store_gathered();
+          bias_store(u + 1);
+          publish(u + 1);  // MMA(u+1) runs during epilogue(u)
+          if (u + 2 < n_units) bias_fetch(u + 2);
+        }
       } else {
-        for (int k = cnt[nb]; k < topk; ++k) { lv[k * NT] = REC_NEG_INF; li[k * NT] = 0x7fffffff; }
+        if (u + 1 < n_units) {
+          // stage (u+1)&1 was last read by MMA(u-1), whose completion this warp observed in iteration u-1
+          store(u + 1);
+          STRACE(3);
+          publish(u + 1);  // BEFORE the next fetch: the proxy fence would otherwise wait for those loads to land
+          if (u + 2 < n_units) fetch(u + 2);  // lands while this step's MMA wait / epilogue run
+        }
+        STRACE(5);
+        tc::mbar_wait(&mbar_done[u & 1], (u >> 1) & 1);
+        tc::tc_fence_after();
+      }
+      STRACE(6);
+      // ---- epilogue of unit u: NB blocks x CW columns in chunks of 32 ----
+      const int v0 = (t_lo + u) * 128;
+      if (ARG) {
+        // greedy action: chunk maximum first, the index search only when it beats the running maximum
+        constexpr int EC = RING ? 32 : 16;  // register-fetch path: the raw head tiles of unit u+2 are live in registers
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll 1
+          for (int ch = 0; ch < CW / EC; ++ch) {
+            const int c_lo = v0 + cq * CW + ch * EC;
+            float l[EC];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((u & 1) * NB + nb) * 128 + cq * CW + ch * EC);
+            if (EC == 32) tc::tmem_ld32(ta, l); else tc::tmem_ld16(ta, l);
+            const float *bgp = bias_g + (u & 3) * 128 + cq * CW + ch * EC;
+#pragma unroll
+            for (int j = 0; j < EC; j += 4) {
+              float4 b4 = *reinterpret_cast<const float4 *>(bgp + j);
+              l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
+            }
+            if (c_lo + EC > Vloc) {
+#pragma unroll
+              for (int j = 0; j < EC; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
+            }
+            float cm[4] = {l[0], l[1], l[2], l[3]};
+#pragma unroll
+            for (int j = 4; j < EC; ++j) cm[j & 3] = fmaxf(cm[j & 3], l[j]);
+            if (fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) > av[nb]) {  // rare once the running maximum has warmed up
+#pragma unroll
+              for (int j = 0; j < EC; ++j)
+                if (l[j] > av[nb]) { av[nb] = l[j]; ai[nb] = vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+            }
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll 1
+        for (int half = 0; half < CW / 32; ++half) {
+          const int c_lo = v0 + cq * CW + half * 32;
+          float l[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((u & 1) * NB + nb) * 128 + cq * CW + half * 32), l);
+          const float *bgp = bias_g + (u & 3) * 128 + cq * CW + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = *reinterpret_cast<const float4 *>(bgp + j);
+            l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
+          }
+          if (c_lo + 32 > Vloc) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (c_lo + j >= Vloc) l[j] = REC_NEG_INF;
+          }
+          float tmax = fmaxf(l[0], l[1]);  // chunk maximum (also the gate of the top-k fast path)
+#pragma unroll
+          for (int j = 2; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
+          if (!ARG && do_stats) {
+            // (REC_NEG_INF is the finite -FLT_MAX: the clamp keeps nm * log2e finite for an all-masked chunk)
+            const float nm = fmaxf(m_run[nb], tmax), nml = -fmaxf(nm, -1e30f) * LOG2E_F;
+            float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ps[j & 3] += tc::ex2_ftz(fmaf(l[j], LOG2E_F, nml));
+            s_run[nb] = fmaf(s_run[nb], tc::ex2_ftz((m_run[nb] - nm) * LOG2E_F), (ps[0] + ps[1]) + (ps[2] + ps[3]));
+            m_run[nb] = nm;
+            if (trow[nb] >= c_lo && trow[nb] < c_lo + 32) {
+              const int tj = trow[nb] - c_lo;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j == tj) tgt[nb] = l[j];
+            }
+          }
+          if (!ARG && topk > 0) {
+            // fast path: nothing in this chunk beats the current k-th best (one compare against the chunk max);
+            // the insertion code exists once, out of line, and walks the chunk from local memory
+            const float cmax = tmax;
+            if (smallk) {
+              if (cmax > tau[nb]) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float v = l[j];
+                  const int id = vocab_lo + c_lo + j;
+                  const bool g0 = v > r_v0[nb], g1 = v > r_v1[nb];
+                  r_v1[nb] = g0 ? r_v0[nb] : (g1 ? v : r_v1[nb]);
+                  r_i1[nb] = g0 ? r_i0[nb] : (g1 ? id : r_i1[nb]);
+                  r_v0[nb] = g0 ? v : r_v0[nb];
+                  r_i0[nb] = g0 ? id : r_i0[nb];
+                }
+                tau[nb] = topk == 1 ? r_v0[nb] : r_v1[nb];
+              }
+            } else if (cmax > tau[nb]) {
+              float lbuf[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) lbuf[j] = l[j];
+              topk_insert_chunk(lbuf, tv + (size_t)nb * topk * NT + tid, ti + (size_t)nb * topk * NT + tid, NT, topk,
+                                vocab_lo + c_lo, cnt[nb], tau[nb]);
+            }
+          }
+        }
+      }
+    }
+
+    STRACE(30);
+    if (RING) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // every compute warp is done with the slot ring
+    // ---- combine the CS column splits of every row inside the CTA, then publish ONE record per row ----
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      float *x = xch + ((nb * 128 + q * 32 + lane) * CS + cq) * 5;
+      x[0] = m_run[nb]; x[1] = s_run[nb]; x[2] = tgt[nb]; x[3] = av[nb]; x[4] = __int_as_float(ai[nb]);
+      if (!ARG && topk > 0) {  // pad the private list so that the merge below can read topk entries
+        float *lv = tv + (size_t)nb * topk * NT + tid;
+        int *li = ti + (size_t)nb * topk * NT + tid;
+        if (smallk) {
+          lv[0] = r_v0[nb]; li[0] = r_i0[nb];
+          if (topk > 1) { lv[NT] = r_v1[nb]; li[NT] = r_i1[nb]; }
+        } else {
+          for (int k = cnt[nb]; k < topk; ++k) { lv[k * NT] = REC_NEG_INF; li[k * NT] = 0x7fffffff; }
+        }
       }
     }
   }
   __syncthreads();
-  if (cq == 0) {
+  if (tid < NT && cq == 0) {
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       const int r = q * 32 + lane, row = b0 + nb * 128 + r;
@@ -340,7 +517,7 @@ __global__ void __launch_bounds__(NT, 1) head_stats_tc_kernel(TcHeadPtrs hp, con
       for (int c = 0; c < CS; ++c) if (x[c * 5 + 1] > 0.f) ssum += x[c * 5 + 1] * __expf(x[c * 5] - m);
       float *o = part + ((int64_t)sp * B + row) * part_stride;
       o[0] = m; o[1] = ssum; o[2] = tg; o[3] = bv; o[4] = __int_as_float(bi);
-      if (topk > 0) {
+      if (!ARG && topk > 0) {
         // CS-way merge of the sorted private lists (ids of different splits are disjoint)
         int pos[CS];
 #pragma unroll
@@ -368,7 +545,7 @@ __global__ void __launch_bounds__(NT, 1) head_stats_tc_kernel(TcHeadPtrs hp, con
   STRACE(31);
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base_s, NB * 256);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, NB * 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -389,8 +566,26 @@ static TcHeadPtrs tc_head_ptrs(const rec_engine *e, int net_id) {
 
 bool tc_heads_supported(const rec_engine *e) { return e->D == 64 && e->use_tc; }
 
-// Same contract as launch_head_stats (heads.cu); *n_split_out counts RECORDS per row (2 per CTA column).
-template <int NB, int NT>
+// Same contract as launch_head_stats (heads.cu); *n_split_out counts records per row (one per CTA column).
+template <int NB, int NT, bool ARG, bool RING>
+static int launch_stats_tc_kernel(rec_engine *e, const HeadStatsArgs &a, dim3 grid, size_t smem, int n_tiles, int topk, int n_slots) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    REC_CUDA(e, cudaFuncSetAttribute(head_stats_tc_kernel<NB, NT, ARG, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  head_stats_tc_kernel<NB, NT, ARG, RING><<<grid, NT + (RING ? 64 : 32), smem, e->stream>>>(
+      tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo, n_tiles, ARG ? 0 : a.do_stats, ARG ? 1 : a.stats_head,
+      ARG ? a.n_arg : 1, a.w[0], a.w[1], a.w[2], a.target, topk, e->part, e->part_stride, trace_sel() == (ARG ? 2 : 1) ? e->trace : nullptr,
+      n_slots);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+// Same contract as launch_head_stats (heads.cu); *n_split_out counts records per row (one per CTA column).
+// RING_OK: the 512-thread (training) variants stream the weights through the TMA slot ring when at least one
+// 32 KB slot fits next to the top-k lists; the evaluation variants keep the register-fetch path.
+template <int NB, int NT, bool ARG, bool RING_OK>
 static int launch_stats_tc_variant(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
   const int n_tiles = cdiv(e->Vloc, 128), ng = cdiv(a.B, 128 * NB);
   int n_split = e->sm_count / ng;  // one CTA per SM, a single wave
@@ -398,32 +593,33 @@ static int launch_stats_tc_variant(rec_engine *e, const HeadStatsArgs &a, int *n
   if (n_split < 1) n_split = 1;
   int per = cdiv(n_tiles, n_split);
   n_split = cdiv(n_tiles, per);
-  const bool arg = a.n_arg > 0;
-  const int topk = arg ? 0 : a.topk;
-  const size_t smem = 1024 + (size_t)(NB * 2 + 4) * BLK + 1536 + (size_t)NB * 128 * (NT / 128) * 5 * 4 + (size_t)NB * topk * NT * 8;
-  if (smem > 227 * 1024) REC_FAIL(e, REC_EINVAL, "head statistics kernel needs %zu B of shared memory (top-k %d)", smem, topk);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    REC_CUDA(e, cudaFuncSetAttribute(head_stats_tc_kernel<NB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  const int topk = ARG ? 0 : a.topk;
+  const size_t xch_bytes = (size_t)NB * 128 * (NT / 128) * 5 * 4, lists = (size_t)NB * topk * NT * 8;
+  const size_t base_ring = 1024 + (size_t)(NB * 2 + 2) * BLK + 2048 + lists + 128;  // single bf16 stage, xch inside the slots
+  const size_t smem_plain = 1024 + (size_t)(NB * 2 + 4) * BLK + 2048 + lists + 128 + xch_bytes;
+  if (smem_plain > 227 * 1024) REC_FAIL(e, REC_EINVAL, "head statistics kernel needs %zu B of shared memory (top-k %d)", smem_plain, topk);
+  static int no_ring = -1;
+  if (no_ring < 0) { const char *v = getenv("REC_NO_RING"); no_ring = v ? atoi(v) : 0; }
+  int n_slots = RING_OK && !no_ring ? (int)((227 * 1024 - base_ring) / 32768) : 0;
+  if (n_slots > 4) n_slots = 4;
   dim3 grid(n_split, ng);
-  head_stats_tc_kernel<NB, NT><<<grid, NT, smem, e->stream>>>(tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo,
-                                                             n_tiles, arg ? 0 : a.do_stats, arg ? 1 : a.stats_head,
-                                                             arg ? a.n_arg : 1, a.w[0], a.w[1], a.w[2], a.target, topk,
-                                                             e->part, e->part_stride, trace_sel() == 1 ? e->trace : nullptr);
-  REC_LAUNCH_CHECK(e);
   *n_split_out = n_split;
-  return REC_OK;
+  if (RING_OK && n_slots > 0)
+    return launch_stats_tc_kernel<NB, NT, ARG, RING_OK>(e, a, grid, base_ring + (size_t)n_slots * 32768, n_tiles, topk, n_slots);
+  return launch_stats_tc_kernel<NB, NT, ARG, false>(e, a, grid, smem_plain, n_tiles, topk, 0);
 }
 
 // Same contract as launch_head_stats (heads.cu); *n_split_out = records per row.
 int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
-  const int topk = a.n_arg > 0 ? 0 : a.topk;
-  if (a.B <= 128) return launch_stats_tc_variant<1, 512>(e, a, n_split_out);
-  if (topk <= 8) return launch_stats_tc_variant<2, 512>(e, a, n_split_out);   // training: 16 warps, 32 columns/thread
-  if (topk <= 20) return launch_stats_tc_variant<2, 256>(e, a, n_split_out);  // evaluation: top-k lists dominate smem
-  return launch_stats_tc_variant<1, 256>(e, a, n_split_out);
+  if (a.n_arg > 0) {
+    if (a.n_arg > 3) REC_FAIL(e, REC_EINVAL, "greedy-action pass supports at most 3 Q heads (got %d)", a.n_arg);
+    if (a.B <= 128) return launch_stats_tc_variant<1, 512, true, true>(e, a, n_split_out);
+    return launch_stats_tc_variant<2, 512, true, true>(e, a, n_split_out);
+  }
+  if (a.B <= 128) return launch_stats_tc_variant<1, 512, false, true>(e, a, n_split_out);
+  if (a.topk <= 8) return launch_stats_tc_variant<2, 512, false, true>(e, a, n_split_out);   // training: 16 warps, 32 columns/thread
+  if (a.topk <= 20) return launch_stats_tc_variant<2, 256, false, false>(e, a, n_split_out);  // evaluation: top-k lists dominate smem
+  return launch_stats_tc_variant<1, 256, false, false>(e, a, n_split_out);
 }
 
 // ================================================================================================
@@ -470,7 +666,7 @@ __global__ void __maxnreg__(104) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const u
                                                                           const float *__restrict__ sc) {
   if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
   extern __shared__ uint8_t raw[];
-  uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);  // 1024-aligned; offset arithmetic keeps the pointer provably shared (LDS/STS, not generic LD/ST)
   int tr_n = 0;
 #define TRACE(tag) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < 120) { trace[2 * tr_n] = (tag); trace[2 * tr_n + 1] = clock64(); ++tr_n; } } while (0)
   uint8_t *h_blk = sm;                 // chunk of 256 sessions: [bb][hi|lo] x BLK      (64 KB)
@@ -787,6 +983,344 @@ __global__ void __maxnreg__(104) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const u
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// ================================================================================================
+// head_bwd_adam_tc2_kernel -- the same computation for batches of at most 256 sessions (dh resident in TMEM),
+// warp-specialised: 16 compute warps + ONE warp that only issues tcgen05.mma / TMA / L2 prefetches.
+// tcgen05.mma issue blocks the issuing thread for about as long as the tensor pipe is busy (the gradient
+// GEMMs with N = 64 are shared-memory-bandwidth bound: ~48 cycles per MMA), so in the kernel above every warp
+// stalled behind thread 0 at the next block barrier.  Here compute warps and the issuer only meet at mbarriers:
+//   compute: wait W(t) staged -> convert to bf16 hi/lo -> arrive WREADY            issuer: logits(bb=0,1)
+//            wait L[bb] -> dlogits in registers -> (bb>0: wait G) -> smem -> arrive DL   issuer: dW,db,dh(bb) -> commit G
+//            wait G -> dW/db TMEM -> smem -> Adam (p, m, v hit L2: the issuer prefetched the tile's m, v at tile
+//            start and the TMA copy of W left p there)
+// ================================================================================================
+#define BWD2_THREADS 544
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTrainPtrs hp, const uint8_t *__restrict__ hpack,
+                                                                           const int64_t *__restrict__ target,
+                                                                           const float *__restrict__ row_stats, int B, int Vloc,
+                                                                           int vocab_lo, int n_tiles, float inv_B,
+                                                                           float *__restrict__ dh_part, float b1, float b2,
+                                                                           float eps, float step_size, float inv_bc2_sqrt,
+                                                                           long long *__restrict__ trace,
+                                                                           const float *__restrict__ sc) {
+  if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
+  extern __shared__ uint8_t raw[];
+  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);  // 1024-aligned; offset arithmetic keeps the pointer provably shared (LDS/STS, not generic LD/ST)
+  int tr_n = 0;
+  uint8_t *h_blk = sm;                 // 256 sessions: [bb][hi|lo] x BLK      (64 KB)
+  uint8_t *w_hi = sm + 4 * BLK, *w_lo = sm + 5 * BLK;            // (32 KB)
+  uint8_t *dl_hi = sm + 6 * BLK, *dl_lo = sm + 8 * BLK;          // each 2 blocks (v halves)  (64 KB)
+  float *w_stage = reinterpret_cast<float *>(sm + 10 * BLK);     // fp32 tile [128][64], TMA destination (32 KB)
+  uint8_t *ones = sm + 12 * BLK;                                  // 4 KB of bf16 1.0
+  float *bias_s = reinterpret_cast<float *>(ones + 4096);        // [128]
+  float *db_s = bias_s + 128;                                     // [128]
+  float *lse_s = db_s + 128;                                      // [256]
+  int *tgt_s = reinterpret_cast<int *>(lse_s + 256);             // [256] target column relative to vocab_lo
+  float *dws = reinterpret_cast<float *>(dl_hi);                 // alias: [128][68] fp32 after the MMAs of a tile
+  enum { MB_L0 = 0, MB_L1, MB_W, MB_H, MB_G, MB_WREADY, MB_DL, MB_N };
+  __shared__ uint64_t mbar[MB_N];
+  __shared__ uint32_t tmem_base_s;
+  constexpr uint32_t T_L = 0 /* 2 x 128 */, T_DW = 256, T_DB = 320, T_DH = 384 /* 2 x 64 */;
+  constexpr int NT = 512;  // compute threads
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp == NT / 32;
+  const int q = warp & 3, cq = (warp >> 2) & 3;  // TMEM lane quarter; column quarter (4 warps share a lane quarter)
+  const int nbb = (B + 127) / 128;
+  const float log2_inv_B = __log2f(inv_B);
+
+  if (tid == 0) {
+    for (int i = 0; i < MB_N; ++i) tc::mbar_init(&mbar[i], (i == MB_WREADY || i == MB_DL) ? NT / 32 : 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  for (int i = tid; i < 4096 / 4; i += BWD2_THREADS) reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;
+  if (tid < 256) {
+    lse_s[tid] = tid < B ? row_stats[(int64_t)tid * 8] : 0.f;
+    tgt_s[tid] = tid < B ? (int)(target[tid] - vocab_lo) : -1;
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (issuer) {
+    const uint32_t s_h = tc::smem_u32(h_blk), s_wh = tc::smem_u32(w_hi), s_wl = tc::smem_u32(w_lo);
+    const uint32_t s_dh = tc::smem_u32(dl_hi), s_dl = tc::smem_u32(dl_lo), s_one = tc::smem_u32(ones);
+    auto prefetch_w = [&](int t) {  // TMA bulk copy of the fp32 tile
+      const uint32_t bytes = (uint32_t)min(128, Vloc - t * 128) * 256u;
+      tc::mbar_expect_tx(&mbar[MB_W], bytes);
+      tc::bulk_g2s(w_stage, hp.w + (int64_t)t * 128 * 64, bytes, &mbar[MB_W]);
+    };
+    const uint64_t d_w_k_hi = tc::desc_kmajor(s_wh, 0), d_w_k_lo = tc::desc_kmajor(s_wl, 0);
+    const uint64_t d_dl_mn_hi = tc::desc_mnmajor(s_dh, 0, BLK), d_dl_mn_lo = tc::desc_mnmajor(s_dl, 0, BLK);
+    const uint64_t d_dl_k_hi = tc::desc_kmajor(s_dh, 0), d_dl_k_lo = tc::desc_kmajor(s_dl, 0);
+    const uint64_t d_w_mn_hi = tc::desc_mnmajor(s_wh, 0, BLK), d_w_mn_lo = tc::desc_mnmajor(s_wl, 0, BLK);
+    const uint64_t d_one = tc::desc_kmajor(s_one, 0);
+    auto issue_logits = [&](int bb) {
+      const uint32_t id = tc::instr_desc(128, 128, 0, 0);
+      const uint64_t d_h_hi = tc::desc_kmajor(s_h + bb * 2 * BLK, 0), d_h_lo = tc::desc_kmajor(s_h + bb * 2 * BLK + BLK, 0);
+      bool acc = false;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a = pass == 2 ? d_h_lo : d_h_hi, b = pass == 1 ? d_w_k_lo : d_w_k_hi;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { tc::mma_bf16(tmem + T_L + bb * 128, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id, acc); acc = true; }
+      }
+      tc::mma_commit(&mbar[MB_L0 + bb]);
+    };
+    auto issue_dW = [&](int bb, bool first_of_tile) {  // dW += dl^T . h[bb]  (A: dl MN-major, B: h MN-major, K = batch)
+      const uint32_t id = tc::instr_desc(128, 64, 1, 1);
+      const uint64_t d_h_hi = tc::desc_mnmajor(s_h + bb * 2 * BLK, 0, BLK), d_h_lo = tc::desc_mnmajor(s_h + bb * 2 * BLK + BLK, 0, BLK);
+      bool acc = !first_of_tile;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a = pass == 2 ? d_dl_mn_lo : d_dl_mn_hi, b = pass == 1 ? d_h_lo : d_h_hi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { tc::mma_bf16(tmem + T_DW, a + (uint64_t)(k * 128), b + (uint64_t)(k * 128), id, acc); acc = true; }
+      }
+    };
+    auto issue_db = [&](bool first_of_tile) {  // db += dl^T . 1  (B: 16 rows of ones, K-major, two K blocks of 2 KB)
+      const uint32_t id = tc::instr_desc(128, 16, 1, 0);
+      bool acc = !first_of_tile;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const uint64_t a = pass == 1 ? d_dl_mn_lo : d_dl_mn_hi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          tc::mma_bf16(tmem + T_DB, a + (uint64_t)(k * 128), d_one + (uint64_t)((k >> 2) * 128 + (k & 3) * 2), id, acc);
+          acc = true;
+        }
+      }
+    };
+    auto issue_dh = [&](int bb, bool acc_dh) {  // dh[bb] += dl . W  (A: dl K-major (K = v, 2 blocks), B: W MN-major)
+      const uint32_t id = tc::instr_desc(128, 64, 0, 1);
+      bool acc = acc_dh;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a = pass == 2 ? d_dl_k_lo : d_dl_k_hi, b = pass == 1 ? d_w_mn_lo : d_w_mn_hi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          tc::mma_bf16(tmem + T_DH + bb * 64, a + (uint64_t)((k >> 2) * (BLK >> 4) + (k & 3) * 2), b + (uint64_t)(k * 128), id, acc);
+          acc = true;
+        }
+      }
+    };
+    if ((int)blockIdx.x < n_tiles) {
+      if (lane == 0) {
+        prefetch_w(blockIdx.x);
+        tc::mbar_expect_tx(&mbar[MB_H], (uint32_t)nbb * 2 * BLK);
+        tc::bulk_g2s(h_blk, hpack, (uint32_t)nbb * 2 * BLK, &mbar[MB_H]);
+      }
+      tc::mbar_wait(&mbar[MB_H], 0);
+    }
+    uint32_t ph_dl = 0;
+    int k = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+      if (lane == 0) {  // Adam state of this tile -> L2 while the tile's GEMMs run
+        const uint32_t bytes = (uint32_t)min(128, Vloc - t * 128) * 256u;
+        tc::l2_prefetch(hp.wm + (int64_t)t * 128 * 64, bytes);
+        tc::l2_prefetch(hp.wv + (int64_t)t * 128 * 64, bytes);
+      }
+      tc::mbar_wait(&mbar[MB_WREADY], k & 1);
+      tc::tc_fence_after();
+      if (lane == 0) {
+        if (t + (int)gridDim.x < n_tiles) prefetch_w(t + gridDim.x);  // every compute warp has read the staging buffer
+        for (int bb = 0; bb < nbb; ++bb) issue_logits(bb);
+      }
+      __syncwarp();
+      for (int bb = 0; bb < nbb; ++bb) {
+        tc::mbar_wait(&mbar[MB_DL], ph_dl);
+        ph_dl ^= 1;
+        tc::tc_fence_after();
+        if (lane == 0) {
+          issue_dW(bb, bb == 0);
+          issue_db(bb == 0);
+          issue_dh(bb, k > 0);
+          tc::mma_commit(&mbar[MB_G]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+#define TRACE2(tag) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < 120) { asm volatile("" ::: "memory"); trace[2 * tr_n] = (tag); trace[2 * tr_n + 1] = clock64(); ++tr_n; asm volatile("" ::: "memory"); } } while (0)
+    auto publish = [&](int which) {
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&mbar[which]);
+    };
+    uint32_t phG = 0;
+    float bias_p = 0.f, bias_m = 0.f, bias_v = 0.f;
+    if (tid < 128 && (int)blockIdx.x < n_tiles && (int)blockIdx.x * 128 + tid < Vloc) {
+      const int i = blockIdx.x * 128 + tid;
+      bias_p = hp.b[i]; bias_m = hp.bm[i]; bias_v = hp.bv[i];
+    }
+    int k = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+      const int v0 = t * 128;
+      // ---- W tile: staged fp32 (TMA) -> bf16 hi/lo in smem ---------------------------------------------
+      TRACE2(1);
+      tc::mbar_wait(&mbar[MB_W], k & 1);
+      TRACE2(2);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (v0 + row < Vloc) {
+          const float4 *p = reinterpret_cast<const float4 *>(w_stage + row * 64 + c8 * 8);
+          a = p[0];
+          b = p[1];
+        }
+        tc::store_split8(w_hi, w_lo, row, c8, a, b);
+      }
+      if (tid < 128) bias_s[tid] = bias_p;
+      publish(MB_WREADY);
+      TRACE2(3);
+      for (int bb = 0; bb < nbb; ++bb) {
+        TRACE2(4);
+        tc::mbar_wait(&mbar[MB_L0 + bb], k & 1);
+        tc::tc_fence_after();
+        TRACE2(5);
+        // ---- epilogue 1: dlogits of (row, 32 columns), computed in registers first ------------------
+        const int r = q * 32 + lane, rl = bb * 128 + r;
+        float l[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + T_L + (uint32_t)(bb * 128 + cq * 32), l);
+        TRACE2(51);
+        {
+          // dl = exp(l + b - lse) / B as ONE ex2 of an fma: (l + b) log2e + (log2(1/B) - lse log2e); the one-hot
+          // target and the masking of columns/rows beyond the matrix are rare fix-ups outside the hot loop
+          const bool rv = rl < B;
+          const float cst = fmaf(-lse_s[rl], LOG2E_F, log2_inv_B);
+          const int tj = tgt_s[rl] - v0 - cq * 32;
+          const float4 *bg = reinterpret_cast<const float4 *>(bias_s + cq * 32);
+          const int nvalid = rv ? min(32, Vloc - v0 - cq * 32) : 0;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = bg[j4];
+            l[j4 * 4 + 0] = tc::ex2_ftz(fmaf(l[j4 * 4 + 0] + b4.x, LOG2E_F, cst));
+            l[j4 * 4 + 1] = tc::ex2_ftz(fmaf(l[j4 * 4 + 1] + b4.y, LOG2E_F, cst));
+            l[j4 * 4 + 2] = tc::ex2_ftz(fmaf(l[j4 * 4 + 2] + b4.z, LOG2E_F, cst));
+            l[j4 * 4 + 3] = tc::ex2_ftz(fmaf(l[j4 * 4 + 3] + b4.w, LOG2E_F, cst));
+          }
+          if (tj >= 0 && tj < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= inv_B;
+          }
+          if (nvalid < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j >= nvalid) l[j] = 0.f;
+          }
+        }
+        TRACE2(6);
+        if (bb > 0) {  // the dl buffer is still being read by the gradient MMAs of block bb-1
+          tc::mbar_wait(&mbar[MB_G], phG);
+          phG ^= 1;
+        }
+        TRACE2(7);
+        {
+          uint8_t *bh = dl_hi + (cq >> 1) * BLK, *bl = dl_lo + (cq >> 1) * BLK;
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            tc::store_split8(bh, bl, r, (cq & 1) * 4 + c8, make_float4(l[c8 * 8], l[c8 * 8 + 1], l[c8 * 8 + 2], l[c8 * 8 + 3]),
+                             make_float4(l[c8 * 8 + 4], l[c8 * 8 + 5], l[c8 * 8 + 6], l[c8 * 8 + 7]));
+        }
+        publish(MB_DL);
+        TRACE2(8);
+      }
+      // Adam operands of this thread's 4 x 4 elements, requested now: they land while the gradient MMAs run.
+      // Float4 index f = tid + 512 i: a warp instruction covers 512 contiguous bytes (full 32-byte sectors --
+      // 16-byte pieces at a 32-byte stride halved the store throughput: one sector request per cycle and SM).
+      float4 P[4], M[4], U[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = tid + NT * i, row = f >> 4;
+        const int64_t off = (int64_t)(v0 + min(row, Vloc - 1 - v0)) * 64 + (f & 15) * 4;
+        P[i] = *reinterpret_cast<const float4 *>(hp.w + off);
+        M[i] = *reinterpret_cast<const float4 *>(hp.wm + off);
+        U[i] = *reinterpret_cast<const float4 *>(hp.wv + off);
+      }
+      TRACE2(9);
+      tc::mbar_wait(&mbar[MB_G], phG);  // gradient MMAs of the last block: the tile is complete
+      phG ^= 1;
+      tc::tc_fence_after();
+      TRACE2(10);
+      // ---- epilogue 2: dW (TMEM) -> smem fp32 [128][68]; db -> smem -------------------------------
+      {
+        const int r = q * 32 + lane;
+        float g[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DW + (uint32_t)(cq * 16), g);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4 *>(dws + r * 68 + cq * 16 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+        if (cq == 0) {
+          float d16[16];
+          tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DB, d16);
+          db_s[r] = d16[0];
+        }
+      }
+      tc::tc_fence_before();
+      compute_bar();
+      TRACE2(11);
+      // ---- Adam on the tile (coalesced layout) ------------------------------------------------------
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = tid + NT * i, row = f >> 4;
+        const float4 g = *reinterpret_cast<const float4 *>(dws + row * 68 + (f & 15) * 4);
+        adam_f(P[i].x, M[i].x, U[i].x, g.x, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(P[i].y, M[i].y, U[i].y, g.y, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(P[i].z, M[i].z, U[i].z, g.z, b1, b2, eps, step_size, inv_bc2_sqrt);
+        adam_f(P[i].w, M[i].w, U[i].w, g.w, b1, b2, eps, step_size, inv_bc2_sqrt);
+      }
+      TRACE2(13);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = tid + NT * i, row = f >> 4;
+        if (v0 + row >= Vloc) continue;
+        const int64_t off = (int64_t)(v0 + row) * 64 + (f & 15) * 4;
+        *reinterpret_cast<float4 *>(hp.w + off) = P[i];
+        *reinterpret_cast<float4 *>(hp.wm + off) = M[i];
+        *reinterpret_cast<float4 *>(hp.wv + off) = U[i];
+      }
+      TRACE2(14);
+      if (tid < 128) {
+        if (v0 + tid < Vloc) {
+          adam_f(bias_p, bias_m, bias_v, db_s[tid], b1, b2, eps, step_size, inv_bc2_sqrt);
+          hp.b[v0 + tid] = bias_p; hp.bm[v0 + tid] = bias_m; hp.bv[v0 + tid] = bias_v;
+        }
+        const int nt = t + gridDim.x;  // bias of the next tile: in flight across the barrier and the W wait
+        bias_p = 0.f; bias_m = 0.f; bias_v = 0.f;
+        if (nt < n_tiles && nt * 128 + tid < Vloc) { bias_p = hp.b[nt * 128 + tid]; bias_m = hp.bm[nt * 128 + tid]; bias_v = hp.bv[nt * 128 + tid]; }
+      }
+      compute_bar();  // dws (aliases dl), bias_s and db_s are rewritten by the next tile
+      TRACE2(12);
+    }
+    // ---- resident dh of this CTA: TMEM -> its slice ---------------------------------------------------
+    float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
+    for (int bb = 0; bb < nbb; ++bb) {
+      const int row = bb * 128 + q * 32 + lane;
+      float g[16];
+      if (k > 0) {
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + cq * 16), g);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) g[j] = 0.f;
+      }
+      if (row < B) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 bool tc_bwd_supported(const rec_engine *e, int B) { (void)B; return tc_heads_supported(e); }
 
 int tc_bwd_slices(const rec_engine *e) {
@@ -811,6 +1345,22 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   }
   h_prepack_kernel<<<cdiv(B, 128), 256, 0, e->stream>>>(h, B, e->hpack);
   REC_LAUNCH_CHECK(e);
+  static int v1 = -1;
+  if (v1 < 0) { const char *v = getenv("REC_BWD_V1"); v1 = v ? atoi(v) : 0; }
+  if (B <= 256 && !v1) {  // warp-specialised variant: dh resident in TMEM
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr2_set = true;
+    }
+    head_bwd_adam_tc2_kernel<<<n_cta, BWD2_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo,
+                                                                      n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
+                                                                      step_size, 1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr,
+                                                                      e->d_sc);
+    REC_LAUNCH_CHECK(e);
+    *n_slices = n_cta;
+    return REC_OK;
+  }
   head_bwd_adam_tc_kernel<<<n_cta, BWD_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles,
                                                           inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size,
                                                           1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr, e->d_sc);

@@ -2,7 +2,7 @@ import sys, torch, ctypes
 sys.path.insert(0, '/root/repo')
 import b200pkg; pkg = b200pkg.load()
 import bench
-wl = bench.WORKLOADS['cfg2']
+wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else 'cfg2']
 batches, unpop, e_div = bench._make_data(wl, 8)
 dev = torch.device('cuda:0')
 t = pkg.SMORL_trainer(device=dev, **bench._trainer_kwargs(wl, e_div, unpop)); t.send_to_device()
