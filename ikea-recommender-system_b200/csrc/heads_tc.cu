@@ -985,17 +985,21 @@ __global__ void __maxnreg__(104) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const u
 
 // ================================================================================================
 // head_bwd_adam_tc2_kernel -- the same computation for batches of at most 256 sessions (dh resident in TMEM),
-// warp-specialised: 16 compute warps + ONE warp that only issues tcgen05.mma / TMA / L2 prefetches.
-// tcgen05.mma issue blocks the issuing thread for about as long as the tensor pipe is busy (the gradient
-// GEMMs with N = 64 are shared-memory-bandwidth bound: ~48 cycles per MMA), so in the kernel above every warp
-// stalled behind thread 0 at the next block barrier.  Here compute warps and the issuer only meet at mbarriers:
-//   compute: wait W(t) staged -> convert to bf16 hi/lo -> arrive WREADY            issuer: logits(bb=0,1)
-//            wait L[bb] -> dlogits in registers -> (bb>0: wait G) -> smem -> arrive DL   issuer: dW,db,dh(bb) -> commit G
-//            wait G -> dW/db TMEM -> smem -> Adam (p, m, v hit L2: the issuer prefetched the tile's m, v at tile
-//            start and the TMA copy of W left p there)
+// warp-specialised into four roles that only meet at mbarriers:
+//   16 compute warps : wait W(t) staged -> convert to bf16 hi/lo -> arrive WREADY
+//                      wait L[bb] -> dlogits in registers (ONE ex2 per logit) -> (bb>0: wait G) -> smem -> arrive DL
+//                      wait G (the W/dl operands are free again)
+//   1 issuer warp    : TMA prefetch of W(t+1), L2 prefetch of the tile's Adam state, logits(bb=0,1) MMAs,
+//                      dW,db,dh(bb) MMAs -> commit G (and GT after the tile's last block)
+//   8 Adam warps     : (TMEM lane quarter = 32 vocabulary rows) x (32 columns): wait GT -> dW/db TMEM -> registers /
+//                      per-warp smem transpose -> arrive DWFREE -> coalesced Adam on p, m, v (L2 hits).
+//                      They run one tile behind the others: the update of tile t overlaps the GEMMs of tile t+1.
+// Why: tcgen05.mma issue blocks the issuing thread for as long as the tensor pipe is busy (the gradient GEMMs with
+// N = 64 are shared-memory-bandwidth bound, ~48 cycles per MMA), and the Adam stores are bound by the SM's
+// store port (one 32-byte sector per cycle: 3072 cycles per tile) -- neither may sit on the critical path.
 // ================================================================================================
-#define BWD2_THREADS 544
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+#define BWD2_COMPUTE 512
+#define BWD2_THREADS (BWD2_COMPUTE + 32 + 256)
 
 __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTrainPtrs hp, const uint8_t *__restrict__ hpack,
                                                                            const int64_t *__restrict__ target,
@@ -1007,7 +1011,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
                                                                            const float *__restrict__ sc) {
   if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
   extern __shared__ uint8_t raw[];
-  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);  // 1024-aligned; offset arithmetic keeps the pointer provably shared (LDS/STS, not generic LD/ST)
+  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);  // 1024-aligned, provably shared
   int tr_n = 0;
   uint8_t *h_blk = sm;                 // 256 sessions: [bb][hi|lo] x BLK      (64 KB)
   uint8_t *w_hi = sm + 4 * BLK, *w_lo = sm + 5 * BLK;            // (32 KB)
@@ -1015,24 +1019,24 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
   float *w_stage = reinterpret_cast<float *>(sm + 10 * BLK);     // fp32 tile [128][64], TMA destination (32 KB)
   uint8_t *ones = sm + 12 * BLK;                                  // 4 KB of bf16 1.0
   float *bias_s = reinterpret_cast<float *>(ones + 4096);        // [128]
-  float *db_s = bias_s + 128;                                     // [128]
-  float *lse_s = db_s + 128;                                      // [256]
+  float *lse_s = bias_s + 128;                                    // [256]
   int *tgt_s = reinterpret_cast<int *>(lse_s + 256);             // [256] target column relative to vocab_lo
-  float *dws = reinterpret_cast<float *>(dl_hi);                 // alias: [128][68] fp32 after the MMAs of a tile
-  enum { MB_L0 = 0, MB_L1, MB_W, MB_H, MB_G, MB_WREADY, MB_DL, MB_N };
+  float *xpose = reinterpret_cast<float *>(tgt_s + 256);         // [8 warps][32 rows][20] Adam warps' transpose staging
+  enum { MB_L0 = 0, MB_L1, MB_W, MB_H, MB_G, MB_GT, MB_WREADY, MB_DL, MB_DWFREE, MB_N };
   __shared__ uint64_t mbar[MB_N];
   __shared__ uint32_t tmem_base_s;
   constexpr uint32_t T_L = 0 /* 2 x 128 */, T_DW = 256, T_DB = 320, T_DH = 384 /* 2 x 64 */;
-  constexpr int NT = 512;  // compute threads
+  constexpr int NT = BWD2_COMPUTE;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool issuer = warp == NT / 32;
+  const bool issuer = warp == NT / 32, adam = warp > NT / 32;
   const int q = warp & 3, cq = (warp >> 2) & 3;  // TMEM lane quarter; column quarter (4 warps share a lane quarter)
   const int nbb = (B + 127) / 128;
   const float log2_inv_B = __log2f(inv_B);
 
   if (tid == 0) {
-    for (int i = 0; i < MB_N; ++i) tc::mbar_init(&mbar[i], (i == MB_WREADY || i == MB_DL) ? NT / 32 : 1);
+    for (int i = 0; i < MB_N; ++i)
+      tc::mbar_init(&mbar[i], (i == MB_WREADY || i == MB_DL) ? NT / 32 : (i == MB_DWFREE ? 8 : 1));
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
@@ -1135,15 +1139,101 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
       for (int bb = 0; bb < nbb; ++bb) {
         tc::mbar_wait(&mbar[MB_DL], ph_dl);
         ph_dl ^= 1;
+        if (bb == 0 && k > 0) tc::mbar_wait(&mbar[MB_DWFREE], (k - 1) & 1);  // the Adam warps have read dW/db of the previous tile
         tc::tc_fence_after();
         if (lane == 0) {
           issue_dW(bb, bb == 0);
           issue_db(bb == 0);
           issue_dh(bb, k > 0);
           tc::mma_commit(&mbar[MB_G]);
+          if (bb == nbb - 1) tc::mma_commit(&mbar[MB_GT]);
         }
         __syncwarp();
       }
+    }
+  } else if (adam) {
+    // ---- Adam warps: warp (aq, ch) owns vocabulary rows [32 aq, 32 aq + 32) x columns [32 ch, 32 ch + 32) of every tile.
+    // Both 16-column halves leave TMEM right after the tile's gradients complete (the first half waits in registers,
+    // the second in the warp's smem staging), so the next tile's dW GEMM is never held up by the update.
+    const int aw = warp - (NT / 32 + 1);  // 0..7
+    const int aq = warp & 3;              // TMEM lane quarter this warp may read (hardware: warp index % 4)
+    const int c0 = (aw >> 2) * 32;
+    float *xp = xpose + aw * (32 * 20);
+    const int rsub = lane >> 2, csub = (lane & 3) * 4;  // staging read-out: 8 rows x 64 bytes per instruction
+    int k = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+      const int v0 = t * 128 + aq * 32;
+      const int nrows = min(32, Vloc - v0);  // may be <= 0 in the last tile
+      float bp = 0.f, bm = 0.f, bv = 0.f;
+      if (c0 == 0 && lane < nrows) { bp = hp.b[v0 + lane]; bm = hp.bm[v0 + lane]; bv = hp.bv[v0 + lane]; }
+      tc::mbar_wait(&mbar[MB_GT], k & 1);
+      tc::tc_fence_after();
+      float4 G[4];
+      {
+        float g[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(aq * 32) << 16) + T_DW + (uint32_t)c0, g);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(xp + lane * 20 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) G[i] = *reinterpret_cast<const float4 *>(xp + (i * 8 + rsub) * 20 + csub);
+      __syncwarp();
+      float dbias = 0.f;
+      {
+        float g[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(aq * 32) << 16) + T_DW + (uint32_t)(c0 + 16), g);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(xp + lane * 20 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+        if (c0 == 0) {
+          tc::tmem_ld16(tmem + ((uint32_t)(aq * 32) << 16) + T_DB, g);
+          dbias = g[0];
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&mbar[MB_DWFREE]);  // this warp's share of dW/db is out of TMEM
+#pragma unroll 1
+      for (int rd = 0; rd < 2; ++rd) {
+        if (rd == 1) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) G[i] = *reinterpret_cast<const float4 *>(xp + (i * 8 + rsub) * 20 + csub);
+        }
+#pragma unroll
+        for (int ip = 0; ip < 4; ip += 2) {  // two float4 per lane and array in flight (register budget: 72)
+          float4 P[2], M[2], U[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int row = (ip + i) * 8 + rsub;
+            const int64_t off = (int64_t)(v0 + max(0, min(row, nrows - 1))) * 64 + c0 + rd * 16 + csub;
+            if (nrows > 0) {
+              P[i] = *reinterpret_cast<const float4 *>(hp.w + off);
+              M[i] = *reinterpret_cast<const float4 *>(hp.wm + off);
+              U[i] = *reinterpret_cast<const float4 *>(hp.wv + off);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int row = (ip + i) * 8 + rsub;
+            const float4 g = G[ip + i];
+            adam_f(P[i].x, M[i].x, U[i].x, g.x, b1, b2, eps, step_size, inv_bc2_sqrt);
+            adam_f(P[i].y, M[i].y, U[i].y, g.y, b1, b2, eps, step_size, inv_bc2_sqrt);
+            adam_f(P[i].z, M[i].z, U[i].z, g.z, b1, b2, eps, step_size, inv_bc2_sqrt);
+            adam_f(P[i].w, M[i].w, U[i].w, g.w, b1, b2, eps, step_size, inv_bc2_sqrt);
+            if (row < nrows) {
+              const int64_t off = (int64_t)(v0 + row) * 64 + c0 + rd * 16 + csub;
+              *reinterpret_cast<float4 *>(hp.w + off) = P[i];
+              *reinterpret_cast<float4 *>(hp.wm + off) = M[i];
+              *reinterpret_cast<float4 *>(hp.wv + off) = U[i];
+            }
+          }
+        }
+      }
+      if (c0 == 0 && lane < nrows) {
+        adam_f(bp, bm, bv, dbias, b1, b2, eps, step_size, inv_bc2_sqrt);
+        hp.b[v0 + lane] = bp; hp.bm[v0 + lane] = bm; hp.bv[v0 + lane] = bv;
+      }
+      __syncwarp();  // xp is rewritten by the next tile
     }
   } else {
 #define TRACE2(tag) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < 120) { asm volatile("" ::: "memory"); trace[2 * tr_n] = (tag); trace[2 * tr_n + 1] = clock64(); ++tr_n; asm volatile("" ::: "memory"); } } while (0)
@@ -1154,11 +1244,8 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
       if (lane == 0) tc::mbar_arrive(&mbar[which]);
     };
     uint32_t phG = 0;
-    float bias_p = 0.f, bias_m = 0.f, bias_v = 0.f;
-    if (tid < 128 && (int)blockIdx.x < n_tiles && (int)blockIdx.x * 128 + tid < Vloc) {
-      const int i = blockIdx.x * 128 + tid;
-      bias_p = hp.b[i]; bias_m = hp.bm[i]; bias_v = hp.bv[i];
-    }
+    float bias_p = 0.f;
+    if (tid < 128 && (int)blockIdx.x < n_tiles && (int)blockIdx.x * 128 + tid < Vloc) bias_p = hp.b[blockIdx.x * 128 + tid];
     int k = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
       const int v0 = t * 128;
@@ -1179,6 +1266,10 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
       }
       if (tid < 128) bias_s[tid] = bias_p;
       publish(MB_WREADY);
+      if (tid < 128) {  // logits bias of the next tile (its Adam update belongs to a later tile: no hazard)
+        const int nt = t + gridDim.x;
+        bias_p = (nt < n_tiles && nt * 128 + tid < Vloc) ? hp.b[nt * 128 + tid] : 0.f;
+      }
       TRACE2(3);
       for (int bb = 0; bb < nbb; ++bb) {
         TRACE2(4);
@@ -1231,72 +1322,10 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
         publish(MB_DL);
         TRACE2(8);
       }
-      // Adam operands of this thread's 4 x 4 elements, requested now: they land while the gradient MMAs run.
-      // Float4 index f = tid + 512 i: a warp instruction covers 512 contiguous bytes (full 32-byte sectors --
-      // 16-byte pieces at a 32-byte stride halved the store throughput: one sector request per cycle and SM).
-      float4 P[4], M[4], U[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = tid + NT * i, row = f >> 4;
-        const int64_t off = (int64_t)(v0 + min(row, Vloc - 1 - v0)) * 64 + (f & 15) * 4;
-        P[i] = *reinterpret_cast<const float4 *>(hp.w + off);
-        M[i] = *reinterpret_cast<const float4 *>(hp.wm + off);
-        U[i] = *reinterpret_cast<const float4 *>(hp.wv + off);
-      }
-      TRACE2(9);
-      tc::mbar_wait(&mbar[MB_G], phG);  // gradient MMAs of the last block: the tile is complete
+      tc::mbar_wait(&mbar[MB_G], phG);  // gradient MMAs of the last block: W and dl operands may be overwritten
       phG ^= 1;
       tc::tc_fence_after();
       TRACE2(10);
-      // ---- epilogue 2: dW (TMEM) -> smem fp32 [128][68]; db -> smem -------------------------------
-      {
-        const int r = q * 32 + lane;
-        float g[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DW + (uint32_t)(cq * 16), g);
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4 *>(dws + r * 68 + cq * 16 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-        if (cq == 0) {
-          float d16[16];
-          tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DB, d16);
-          db_s[r] = d16[0];
-        }
-      }
-      tc::tc_fence_before();
-      compute_bar();
-      TRACE2(11);
-      // ---- Adam on the tile (coalesced layout) ------------------------------------------------------
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = tid + NT * i, row = f >> 4;
-        const float4 g = *reinterpret_cast<const float4 *>(dws + row * 68 + (f & 15) * 4);
-        adam_f(P[i].x, M[i].x, U[i].x, g.x, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(P[i].y, M[i].y, U[i].y, g.y, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(P[i].z, M[i].z, U[i].z, g.z, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(P[i].w, M[i].w, U[i].w, g.w, b1, b2, eps, step_size, inv_bc2_sqrt);
-      }
-      TRACE2(13);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = tid + NT * i, row = f >> 4;
-        if (v0 + row >= Vloc) continue;
-        const int64_t off = (int64_t)(v0 + row) * 64 + (f & 15) * 4;
-        *reinterpret_cast<float4 *>(hp.w + off) = P[i];
-        *reinterpret_cast<float4 *>(hp.wm + off) = M[i];
-        *reinterpret_cast<float4 *>(hp.wv + off) = U[i];
-      }
-      TRACE2(14);
-      if (tid < 128) {
-        if (v0 + tid < Vloc) {
-          adam_f(bias_p, bias_m, bias_v, db_s[tid], b1, b2, eps, step_size, inv_bc2_sqrt);
-          hp.b[v0 + tid] = bias_p; hp.bm[v0 + tid] = bias_m; hp.bv[v0 + tid] = bias_v;
-        }
-        const int nt = t + gridDim.x;  // bias of the next tile: in flight across the barrier and the W wait
-        bias_p = 0.f; bias_m = 0.f; bias_v = 0.f;
-        if (nt < n_tiles && nt * 128 + tid < Vloc) { bias_p = hp.b[nt * 128 + tid]; bias_m = hp.bm[nt * 128 + tid]; bias_v = hp.bv[nt * 128 + tid]; }
-      }
-      compute_bar();  // dws (aliases dl), bias_s and db_s are rewritten by the next tile
-      TRACE2(12);
     }
     // ---- resident dh of this CTA: TMEM -> its slice ---------------------------------------------------
     float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
@@ -1337,7 +1366,7 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   TcTrainPtrs t = {p.head_w[0], p.head_w_m[0], p.head_w_v[0], p.head_b[0], p.head_b_m[0], p.head_b_v[0]};
   const int n_tiles = cdiv(e->Vloc, 128);
   const int n_cta = tc_bwd_slices(e);
-  const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072;
+  const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072 + 8 * 32 * 20 * 4;  // (the transpose staging belongs to tc2 only)
   static bool attr_set = false;
   if (!attr_set) {
     REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

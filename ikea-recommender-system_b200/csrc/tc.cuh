@@ -171,15 +171,24 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// two fp32 -> packed bf16x2 hi and lo words (element `a` in the low half).  cvt.rn.bf16x2.f32 converts a pair
+// per instruction; the scalar F2F.BF16.F32 it replaces runs at conversion-unit rate (16 lanes/clk/SM).
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
 // 8 consecutive fp32 (one 16-byte bf16 chunk) -> hi/lo chunks at (row, col8*8) of two blocks
 __device__ __forceinline__ void store_split8(uint8_t *blk_hi, uint8_t *blk_lo, int row, int chunk, const float4 &a,
                                              const float4 &b) {
-  __nv_bfloat16 h[8], l[8];
-  split_bf16(a.x, h[0], l[0]); split_bf16(a.y, h[1], l[1]); split_bf16(a.z, h[2], l[2]); split_bf16(a.w, h[3], l[3]);
-  split_bf16(b.x, h[4], l[4]); split_bf16(b.y, h[5], l[5]); split_bf16(b.z, h[6], l[6]); split_bf16(b.w, h[7], l[7]);
+  uint4 h, l;
+  split_bf16x2(a.x, a.y, h.x, l.x);
+  split_bf16x2(a.z, a.w, h.y, l.y);
+  split_bf16x2(b.x, b.y, h.z, l.z);
+  split_bf16x2(b.z, b.w, h.w, l.w);
   uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
-  *reinterpret_cast<uint4 *>(blk_hi + off) = *reinterpret_cast<const uint4 *>(h);
-  *reinterpret_cast<uint4 *>(blk_lo + off) = *reinterpret_cast<const uint4 *>(l);
+  *reinterpret_cast<uint4 *>(blk_hi + off) = h;
+  *reinterpret_cast<uint4 *>(blk_lo + off) = l;
 }
 
 }  // namespace tc
