@@ -336,6 +336,104 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
   }
 }
 
+// Training-shaped merge (n_split <= 160 records per row, top-k <= 2): every lane requests ALL its records up front
+// (one memory round trip instead of one per reduction pass), then the same reductions run from registers.
+// Results are bit-identical to head_merge_kernel (same per-lane orders, same warp reductions).
+__global__ void __launch_bounds__(128) head_merge_small_kernel(const float *__restrict__ part, int part_stride, int n_split,
+                                                               int B, int topk, int has_stats, int has_arg,
+                                                               float *__restrict__ row_stats, int32_t *__restrict__ row_ids,
+                                                               float *__restrict__ row_topv, int32_t *__restrict__ astar,
+                                                               float *__restrict__ summary) {
+  constexpr int R = 5;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  float *rs = row_stats + (int64_t)row * ROW_STRIDE;
+  float *sm = summary ? summary + (int64_t)row * part_stride : nullptr;
+  float4 a[R];
+  float a4[R], tv[R][2];
+  int ti[R][2];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int sp = lane + 32 * r;
+    a[r] = make_float4(REC_NEG_INF, 0.f, REC_NEG_INF, REC_NEG_INF);
+    a4[r] = __int_as_float(0x7fffffff);
+    tv[r][0] = tv[r][1] = REC_NEG_INF;
+    ti[r][0] = ti[r][1] = 0x7fffffff;
+    if (sp < n_split) {
+      const float *o = part + ((int64_t)sp * B + row) * part_stride;
+      a[r] = *reinterpret_cast<const float4 *>(o);
+      a4[r] = o[4];
+      if (topk > 0) { tv[r][0] = o[PART_TOPK_OFF]; ti[r][0] = __float_as_int(o[PART_TOPK_OFF + REC_MAX_TOPK]); }
+      if (topk > 1) { tv[r][1] = o[PART_TOPK_OFF + 1]; ti[r][1] = __float_as_int(o[PART_TOPK_OFF + REC_MAX_TOPK + 1]); }
+    }
+  }
+  if (has_stats) {
+    float m = REC_NEG_INF, tg = REC_NEG_INF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { m = fmaxf(m, a[r].x); tg = fmaxf(tg, a[r].z); }
+    m = warp_max(m);
+    tg = warp_max(tg);
+    float ssum = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (lane + 32 * r < n_split && a[r].y > 0.f) ssum += a[r].y * __expf(a[r].x - m);
+    ssum = warp_sum(ssum);
+    if (lane == 0) {
+      float lse = m + logf(ssum);
+      rs[0] = lse; rs[1] = tg; rs[4] = lse - tg; rs[5] = m; rs[6] = ssum;
+      if (sm) { sm[0] = m; sm[1] = ssum; sm[2] = tg; }
+    }
+  }
+  if (has_arg) {
+    float bv = REC_NEG_INF;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float v = a[r].w;
+      const int i = __float_as_int(a4[r]);
+      if (lane + 32 * r < n_split && better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      rs[2] = bv; rs[3] = __int_as_float(bi); astar[row] = bi;
+      if (sm) { sm[3] = bv; sm[4] = __int_as_float(bi); }
+    }
+  }
+  if (topk > 0) {
+    float lastv = 3.402823466e+38f;
+    int lasti = -1;
+    for (int k = 0; k < topk; ++k) {
+      float bv = REC_NEG_INF;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float v = tv[r][j];
+          const int i = ti[r][j];
+          if (j < topk && i != 0x7fffffff && better(lastv, lasti, v, i) && better(v, i, bv, bi)) { bv = v; bi = i; }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv;
+        if (sm) { sm[PART_TOPK_OFF + k] = bv; sm[PART_TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(bi); }
+      }
+      lastv = bv; lasti = bi;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Plain logits (API compatibility with `model(s, lengths)`): logits[b, v] = h[b].W[v] + bias[v].
 // ------------------------------------------------------------------------------------------------
@@ -479,6 +577,140 @@ __global__ void __launch_bounds__(256) q_rows_fused_kernel(QRowArgs A, rec_train
     if (loc_a >= 0 && loc_a < A.Vloc)
       for (int j = 0; j < n_q; ++j) acc = fmaf(dq[j], __ldg(A.main_heads.w[1 + j] + loc_a * D + k), acc);
     A.dh_slice[(int64_t)b * D + k] = acc;
+  }
+}
+
+// Same computation with the memory round trips collapsed (D = 32 DPL <= 128, <= 160 records per row): the four
+// independent dependency chains (records -> a* -> bootstrap rows | a_b -> main rows | lengths -> s -> E_div row |
+// top-k ids) are requested side by side instead of one after the other, and the main-head rows loaded for Q(s,a)
+// are reused for the dh slice.  Arithmetic orders are those of q_rows_fused_kernel (bit-identical results).
+template <int DPL>
+__global__ void __launch_bounds__(128) q_rows_fused_small_kernel(QRowArgs A, rec_train_hparams hp) {
+  constexpr int R = 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= A.B) return;
+  const int D = A.D, n_q = A.n_q;
+  // round trip 1: records, a_b, lengths, reward inputs
+  float rv[R];
+  int ri[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int sp = lane + 32 * r;
+    rv[r] = REC_NEG_INF; ri[r] = 0x7fffffff;
+    if (sp < A.n_split) {
+      const float *o = A.part + ((int64_t)sp * A.B + b) * A.part_stride;
+      rv[r] = o[3]; ri[r] = __float_as_int(o[4]);
+    }
+  }
+  const int64_t loc_a = A.a[b] - A.vocab_lo;
+  const float r_acc = A.r_acc[b];
+  const bool end = A.is_end[b] != 0;
+  int64_t dlen = 1;
+  if (n_q == 3 && hp.pad_pos_end) dlen = A.div_lens[b];
+  const float *hm = A.h_main + (int64_t)b * D, *hb = A.h_boot + (int64_t)b * D;
+  float hmr[DPL], hbr[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) { hmr[i] = hm[lane + 32 * i]; hbr[i] = hb[lane + 32 * i]; }
+  // round trip 2 (a_b known): main-head rows; (lengths known): last item of s
+  const bool a_here = loc_a >= 0 && loc_a < A.Vloc;
+  float wm[3][DPL], bm_[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) wm[j][i] = (j < n_q && a_here) ? __ldg(A.main_heads.w[1 + j] + loc_a * D + lane + 32 * i) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) if (j < n_q && a_here) bm_[j] = __ldg(A.main_heads.b[1 + j] + loc_a);
+  int last = 0;
+  if (n_q == 3) {
+    int64_t it;
+    if (hp.pad_pos_end) {
+      int64_t l = dlen < 1 ? 1 : (dlen > A.L ? A.L : dlen);
+      it = A.s[(int64_t)b * A.L + (l - 1)];
+    } else {
+      it = A.s[(int64_t)b * A.L + (A.L - 1)];
+    }
+    last = (int)(it < 0 ? 0 : (it > A.N ? A.N : it));
+  }
+  // (1) greedy action
+  float bv = REC_NEG_INF;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (lane + 32 * r < A.n_split && better(rv[r], ri[r], bv, bi)) { bv = rv[r]; bi = ri[r]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  // round trip 3 (a* known): bootstrap rows
+  const int64_t loc_s = (int64_t)bi - A.vocab_lo;
+  const bool s_here = loc_s >= 0 && loc_s < A.Vloc;
+  float wb[3][DPL], bb_[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) wb[j][i] = (j < n_q && s_here) ? __ldg(A.boot_heads.w[1 + j] + loc_s * D + lane + 32 * i) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) if (j < n_q && s_here) bb_[j] = __ldg(A.boot_heads.b[1 + j] + loc_s);
+  // (3) rewards (their loads overlap the bootstrap rows in flight)
+  float r[3] = {r_acc, 0.f, 0.f};
+  if (n_q == 3) {
+    const int32_t *ids = A.row_ids + (int64_t)b * REC_MAX_TOPK;
+    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, A.N, lane);
+    float nov = 0.f;
+    for (int j = 0; j < hp.topk_nov; ++j) nov += hp.unpopular[ids[j]] ? hp.nov_reward : 0.f;
+    r[2] = nov / (float)hp.topk_nov;
+  }
+  // (2) Q(s,a) and Q_boot(s',a*)
+  float qsa[3] = {0.f, 0.f, 0.f}, qbt[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= n_q) continue;
+    if (a_here) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc = fmaf(hmr[i], wm[j][i], acc);
+      qsa[j] = warp_sum(acc) + bm_[j];
+    }
+    if (s_here) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc = fmaf(hbr[i], wb[j][i], acc);
+      qbt[j] = warp_sum(acc) + bb_[j];
+    }
+  }
+  // (4) TD target, dq, per-row loss (every lane computes the same scalars)
+  float loss = 0.f, dq[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j >= n_q) continue;
+    float boot = end ? 0.f : qbt[j];
+    float y = r[j] + hp.gamma * boot;
+    float diff = y - qsa[j];
+    float w = (n_q == 3) ? hp.q_weights[j] : 1.f;
+    loss += diff * diff * w;
+    dq[j] = A.alpha_eff * w * 2.f * (-diff) / (float)A.B;
+  }
+  if (lane == 0) {
+    float *rs = A.row_stats + (int64_t)b * ROW_STRIDE;
+    rs[2] = bv; rs[3] = __int_as_float(bi); A.astar[b] = bi;
+    for (int j = 0; j < n_q; ++j) {
+      A.q_sa[b * 3 + j] = qsa[j]; A.q_boot[b * 3 + j] = qbt[j];
+      A.dq[b * 3 + j] = dq[j]; A.rewards[b * 3 + j] = r[j];
+    }
+    A.q_loss_rows[b] = loss;
+  }
+  // (5) dh contribution of the Q heads (before Adam touches their weights): the rows are still in registers
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) {
+    float acc = 0.f;
+    if (a_here) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) if (j < n_q) acc = fmaf(dq[j], wm[j][i], acc);
+    }
+    A.dh_slice[(int64_t)b * D + lane + 32 * i] = acc;
   }
 }
 
@@ -729,9 +961,14 @@ int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
 
 int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats, bool has_arg,
                       float *summary) {
-  head_merge_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(part, e->part_stride, n_split, B, topk, has_stats ? 1 : 0,
-                                                      has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv, e->astar,
-                                                      summary);
+  if (n_split <= 160 && topk <= 2 && (e->part_stride & 3) == 0)
+    head_merge_small_kernel<<<cdiv(B, 4), 128, 0, e->stream>>>(part, e->part_stride, n_split, B, topk, has_stats ? 1 : 0,
+                                                              has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv,
+                                                              e->astar, summary);
+  else
+    head_merge_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(part, e->part_stride, n_split, B, topk, has_stats ? 1 : 0,
+                                                        has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv, e->astar,
+                                                        summary);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
 }
@@ -779,7 +1016,9 @@ int launch_q_rows_fused(rec_engine *e, int main_net, const rec_batch *b, const r
   A.row_stats = e->row_stats; A.astar = e->astar;
   A.q_sa = e->q_sa; A.q_boot = e->q_boot; A.dq = e->dq; A.q_loss_rows = q_loss_rows; A.rewards = e->rewards;
   A.dh_slice = e->dh_part + (int64_t)head_bwd_dense_slices(e, B) * B * e->D;
-  q_rows_fused_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(A, *hp);
+  if (n_split <= 160 && e->D == 64) q_rows_fused_small_kernel<2><<<cdiv(B, 4), 128, 0, e->stream>>>(A, *hp);
+  else if (n_split <= 160 && e->D == 128) q_rows_fused_small_kernel<4><<<cdiv(B, 4), 128, 0, e->stream>>>(A, *hp);
+  else q_rows_fused_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(A, *hp);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
 }

@@ -178,6 +178,17 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uin
   const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
 }
+// 8 consecutive fp32 -> one 16-byte bf16 hi chunk + one lo chunk (registers)
+__device__ __forceinline__ void split8(const float4 &a, const float4 &b, uint4 &h, uint4 &l) {
+  split_bf16x2(a.x, a.y, h.x, l.x);
+  split_bf16x2(a.z, a.w, h.y, l.y);
+  split_bf16x2(b.x, b.y, h.z, l.z);
+  split_bf16x2(b.z, b.w, h.w, l.w);
+}
+// one 16-byte chunk -> position (row, chunk) of a SWIZZLE_128B block
+__device__ __forceinline__ void store_chunk(uint8_t *blk, int row, int chunk, const uint4 &v) {
+  *reinterpret_cast<uint4 *>(blk + (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4))) = v;
+}
 // 8 consecutive fp32 (one 16-byte bf16 chunk) -> hi/lo chunks at (row, col8*8) of two blocks
 __device__ __forceinline__ void store_split8(uint8_t *blk_hi, uint8_t *blk_lo, int row, int chunk, const float4 &a,
                                              const float4 &b) {
