@@ -130,10 +130,26 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
   if (tid == 0) {
     tc::mbar_init(&mbar_done[0], 1); tc::mbar_init(&mbar_done[1], 1);
     tc::mbar_init(&mbar_full[0], NT / 32); tc::mbar_init(&mbar_full[1], NT / 32);
-    for (int i = 0; i < 4; ++i) { tc::mbar_init(&slot_full[i], 1); tc::mbar_init(&slot_free[i], NT / 32); }
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, NB * 256);
+  // The loader owns the slot barriers: it initialises them and requests the first n_slots tiles BEFORE the block-wide
+  // prologue barrier, so the cold DRAM latency of the first tile overlaps the staging of h.
+  int ld_sl = 0, ld_u = 0, ld_hh = 0;
+  uint32_t ld_round = 0;
+  auto loader_issue = [&]() {  // next (unit, head) tile -> slot ld_sl; one thread
+    const int v0 = (t_lo + ld_u) * 128;
+    const uint32_t bytes = (uint32_t)min(128, Vloc - v0) * 256u;
+    tc::mbar_expect_tx(&slot_full[ld_sl], bytes);
+    tc::bulk_g2s(stg + ld_sl * 8192, hp.w[first_head + ld_hh] + (int64_t)v0 * 64, bytes, &slot_full[ld_sl]);
+    if (++ld_sl == n_slots) { ld_sl = 0; ++ld_round; }
+    if (++ld_hh == nh) { ld_hh = 0; ++ld_u; }
+  };
+  if (loader && lane == 0) {
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&slot_full[i], 1); tc::mbar_init(&slot_free[i], NT / 32); }
+    tc::fence_barrier_init();
+    while (ld_round == 0 && ld_u < n_units) loader_issue();
+  }
   // h blocks of this CTA -> bf16 hi/lo (zero rows beyond B)
   if (tid < NT) {
     for (int nb = 0; nb < NB; ++nb) {
@@ -195,17 +211,9 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
   } else if (loader) {
     // ---- TMA loader warp: (unit, head) tiles in order into the slot ring ----
     if (lane == 0) {
-      int sl = 0;
-      uint32_t round = 0;
-      for (int u = 0; u < n_units; ++u) {
-        const int v0 = (t_lo + u) * 128;
-        const uint32_t bytes = (uint32_t)min(128, Vloc - v0) * 256u;
-        for (int hh = 0; hh < nh; ++hh) {
-          if (round > 0) tc::mbar_wait(&slot_free[sl], (round - 1) & 1);
-          tc::mbar_expect_tx(&slot_full[sl], bytes);
-          tc::bulk_g2s(stg + sl * 8192, hp.w[first_head + hh] + (int64_t)v0 * 64, bytes, &slot_full[sl]);
-          if (++sl == n_slots) { sl = 0; ++round; }
-        }
+      while (ld_u < n_units) {
+        tc::mbar_wait(&slot_free[ld_sl], (ld_round - 1) & 1);  // every compute warp has read the slot's previous tile
+        loader_issue();
       }
     }
   } else {
@@ -1034,10 +1042,17 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
   const int nbb = (B + 127) / 128;
   const float log2_inv_B = __log2f(inv_B);
 
-  if (tid == 0) {
+  if (issuer && lane == 0) {
     for (int i = 0; i < MB_N; ++i)
       tc::mbar_init(&mbar[i], (i == MB_WREADY || i == MB_DL) ? NT / 32 : (i == MB_DWFREE ? 8 : 1));
     tc::fence_barrier_init();
+    if ((int)blockIdx.x < n_tiles) {  // first weight tile + the packed h image: in flight during the prologue
+      const uint32_t bytes = (uint32_t)min(128, Vloc - (int)blockIdx.x * 128) * 256u;
+      tc::mbar_expect_tx(&mbar[MB_W], bytes);
+      tc::bulk_g2s(w_stage, hp.w + (int64_t)blockIdx.x * 128 * 64, bytes, &mbar[MB_W]);
+      tc::mbar_expect_tx(&mbar[MB_H], (uint32_t)nbb * 2 * BLK);
+      tc::bulk_g2s(h_blk, hpack, (uint32_t)nbb * 2 * BLK, &mbar[MB_H]);
+    }
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   for (int i = tid; i < 4096 / 4; i += BWD2_THREADS) reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;
@@ -1113,14 +1128,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
         }
       }
     };
-    if ((int)blockIdx.x < n_tiles) {
-      if (lane == 0) {
-        prefetch_w(blockIdx.x);
-        tc::mbar_expect_tx(&mbar[MB_H], (uint32_t)nbb * 2 * BLK);
-        tc::bulk_g2s(h_blk, hpack, (uint32_t)nbb * 2 * BLK, &mbar[MB_H]);
-      }
-      tc::mbar_wait(&mbar[MB_H], 0);
-    }
+    if ((int)blockIdx.x < n_tiles) tc::mbar_wait(&mbar[MB_H], 0);
     uint32_t ph_dl = 0;
     int k = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
