@@ -626,8 +626,16 @@ int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out
   }
   if (a.B <= 128) return launch_stats_tc_variant<1, 512, false, true>(e, a, n_split_out);
   if (a.topk <= 8) return launch_stats_tc_variant<2, 512, false, true>(e, a, n_split_out);   // training: 16 warps, 32 columns/thread
-  if (a.topk <= 20) return launch_stats_tc_variant<2, 256, false, false>(e, a, n_split_out);  // evaluation: top-k lists dominate smem
-  return launch_stats_tc_variant<1, 256, false, false>(e, a, n_split_out);
+  static int eval_wide = -1;
+  if (eval_wide < 0) { const char *v = getenv("REC_EVAL_WIDE"); eval_wide = v ? atoi(v) : 1; }
+  // evaluation (8 < k <= 20): the per-thread top-k lists dominate shared memory.  For moderate (batch x catalogue) sizes
+  // one 128-session block with 16 warps (32 logits per thread and tile) beats two blocks with 8 warps.
+  // (measured: 70 852 items / B = 2000: 0.83 vs 0.97 ms per batch; 1 M items / B = 5000: 8.3 vs 6.7 ms -- with many
+  // column groups the per-tile weight conversion, repeated by every group, outweighs the faster epilogue)
+  if (a.topk <= 20 && eval_wide && (int64_t)cdiv(a.B, 128) * cdiv(e->Vloc, 128) < 200000)
+    return launch_stats_tc_variant<1, 512, false, true>(e, a, n_split_out);
+  if (a.topk <= 20) return launch_stats_tc_variant<2, 256, false, true>(e, a, n_split_out);
+  return launch_stats_tc_variant<1, 256, false, true>(e, a, n_split_out);
 }
 
 // ================================================================================================
