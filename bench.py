@@ -134,7 +134,8 @@ def algorithmic_bytes(wl):
     V, N, E, H, D, Kh = wl["item_num"], wl["item_num"], wl["E"], wl["H"], wl["H"], 4
     P = (N + 1) * E + (3 * H * E + 3 * H * H + 6 * H) + Kh * (D * V + V)
     return dict(step=24 * P + 4 * (Kh + 1) * D * V, head_bwd_adam=24 * Kh * (D + 1) * V, emb_adam=24 * (N + 1) * E,
-                sup_head=24 * (D + 1) * V, q_heads=24 * (Kh - 1) * (D + 1) * V)
+                sup_head=24 * (D + 1) * V, q_heads=24 * (Kh - 1) * (D + 1) * V,
+                sup_stats=4 * (D + 1) * V, greedy_stats=4 * (Kh - 1) * (D + 1) * V)
 
 
 def cpu_reference_rate(wl, batches, unpop, e_div, steps, warmup, budget_s=25.0):
@@ -226,7 +227,7 @@ def run_native(args, wl):
 
     # ---- roofline: dominant kernels timed live with CUDA events on the engine's stream ------------
     eng.enable_kernel_timing(True)
-    kms = {0: [], 2: [], 3: []}
+    kms = {0: [], 2: [], 3: [], 4: [], 5: []}
     for i in range(min(K, 50)):
         trainer.train_step_async(*dev_batches[(W + i) % n_b])
         for which in kms:
@@ -242,15 +243,18 @@ def run_native(args, wl):
         return {"achieved": a, "frac": a / peak, "kernel_ms": kms_, "algorithmic_bytes_per_launch": nbytes,
                 "kernel_share_of_step": kms_ / step_ms}
 
-    parts = {"q_heads_adam_stream (3 launches of adam_stream_kernel, row-sparse grads)": rl(ab["q_heads"], avg[3]),
-             "head_bwd_adam_tc_kernel (supervised head: tcgen05 logits/dW/dh + fused Adam)": rl(ab["sup_head"], avg[0]),
-             "adam_stream_kernel (embedding table)": rl(ab["emb_adam"], avg[2])}
+    parts = {"q_heads_adam_stream (adam_stream_kernel over the 3 Q heads, row-sparse grads)": rl(ab["q_heads"], avg[3]),
+             "head_bwd_adam_tc2_kernel (supervised head: tcgen05 logits/dW/dh + fused Adam, warp-specialised)": rl(ab["sup_head"], avg[0]),
+             "adam_stream_kernel (embedding table)": rl(ab["emb_adam"], avg[2]),
+             "head_stats_tc_kernel (supervised head: logits + online softmax + top-k, weights streamed once)": rl(ab["sup_stats"], avg[4]),
+             "head_stats_tc_kernel (greedy action: 3 Q heads pre-combined, argmax)": rl(ab["greedy_stats"], avg[5])}
     # DRAM traffic per launch from the committed ncu --set full capture (cfg2 only; null elsewhere)
     traffic = None
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
     if wl["name"].startswith("cfg2") and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        tkeys = ["q_heads_adam_stream", "head_bwd_adam_tc_kernel", "adam_stream_kernel_embedding"]
+        tkeys = ["q_heads_adam_stream", "head_bwd_adam_tc_kernel", "adam_stream_kernel_embedding",
+                 "head_stats_tc_kernel_supervised", "head_stats_tc_kernel_greedy_action"]
         for k, tk in zip(parts, tkeys):
             parts[k]["traffic"] = tj[tk]["dram_bytes_read"] + tj[tk]["dram_bytes_write"]
     dom = max(parts, key=lambda k: parts[k]["kernel_ms"])

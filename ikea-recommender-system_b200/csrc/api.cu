@@ -181,7 +181,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
       ALLOC(e, e->nets[n].w_ihT[d], float, G * E);
       ALLOC(e, e->nets[n].w_hhT[d], float, G * H);
     }
-  for (int i = 0; i < 8; ++i) cudaEventCreate(&e->ev[i]);
+  for (int i = 0; i < 12; ++i) cudaEventCreate(&e->ev[i]);
   if (launch_fill_i32(e, e->emb_slot, (int64_t)c.item_num + 1, -1) != REC_OK ||
       launch_fill_i32(e, e->q_slot, e->Vloc, -1) != REC_OK) {
     snprintf(g_err, sizeof(g_err), "%s", e->err);
@@ -209,7 +209,7 @@ extern "C" void rec_destroy(rec_engine *e) {
       if (e->nets[n].w_ihT[d]) cudaFree(e->nets[n].w_ihT[d]);
       if (e->nets[n].w_hhT[d]) cudaFree(e->nets[n].w_hhT[d]);
     }
-  for (int i = 0; i < 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 12; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < e->n_graphs; ++i) if (e->graphs[i].exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graphs[i].exec);
   if (e->h_sc) cudaFreeHost(e->h_sc);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
@@ -290,7 +290,7 @@ extern "C" int rec_debug_set_trace(rec_engine *e, long long *dev_buf) {
 extern "C" int64_t rec_launch_count(const rec_engine *e) { return e ? e->launches : -1; }
 extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) { if (!e) return REC_EINVAL; e->timing = on != 0; return REC_OK; }
 extern "C" float rec_last_kernel_ms(rec_engine *e, int which) {
-  if (!e || which < 0 || which > 3) return -1.f;
+  if (!e || which < 0 || which > 5) return -1.f;
   float ms = -1.f;
   if (cudaEventSynchronize(e->ev[2 * which + 1]) != cudaSuccess ||
       cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) {
@@ -601,14 +601,18 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
   a.net_id = main_net; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
   a.topk = (n_q == 3) ? (hp->topk_div > hp->topk_nov ? hp->topk_div : hp->topk_nov) : 0;
   int n_split = 0;
+  if (e->timing) cudaEventRecord(e->ev[8], e->stream);
   if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
+  if (e->timing) cudaEventRecord(e->ev[9], e->stream);
   if ((rc = launch_head_merge(e, e->part, n_split, B, a.topk, true, false))) return rc;
   side_mark(e, 0);  // log-sum-exp of the supervised logits is final: its backward may start
   // greedy action a* = argmax_a sum_h w_h Q_h(s', a) on the main net
   HeadStatsArgs g = {};
   g.net_id = main_net; g.h = e->h_state[1]; g.B = B; g.n_arg = n_q;
   g.w[0] = n_q == 3 ? hp->q_weights[0] : 1.f; g.w[1] = hp->q_weights[1]; g.w[2] = hp->q_weights[2];
+  if (e->timing) cudaEventRecord(e->ev[10], e->stream);
   if ((rc = head_stats_dispatch(e, g, &n_split))) return rc;
+  if (e->timing) cudaEventRecord(e->ev[11], e->stream);
   {  // issued after the greedy-action statistics so that those get the SMs first
     SideScope side(e, 0, 0);
     if ((rc = launch_sup_head_bwd(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B))) return rc;

@@ -97,7 +97,7 @@ struct rec_engine {
   int n_graphs;
   long long *trace;      // optional device buffer for clock64 phase traces (debug)
   bool use_tc;           // tensor-core (tcgen05) head kernels when D == 64
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[12];
   float last_ms[3];
 };
 

@@ -255,9 +255,11 @@ int64_t rec_launch_count(const rec_engine *e);
 /* CUDA-event time (ms) of the most recent dominant-kernel launch when profiling is enabled. */
 int rec_enable_kernel_timing(rec_engine *e, int on);
 float rec_last_kernel_ms(rec_engine *e, int which); /* which: 0 supervised-head bwd+Adam, 1 eval head statistics,
-                                                        2 embedding Adam sweep, 3 Q-heads Adam sweep */
+                                                        2 embedding Adam sweep, 3 Q-heads Adam sweep,
+                                                        4 supervised-head statistics (train), 5 greedy-action pass */
 
-/* Debug: device buffer [240] int64 receiving (tag, clock64) pairs of CTA 0 of the tensor-core backward kernel. */
+/* Debug: device buffer [240] int64 receiving (tag, clock64) pairs of CTA 0 of the tensor-core backward kernel
+ * (REC_TRACE_SEL=1: the supervised statistics kernel, =2: the greedy-action kernel). */
 int rec_debug_set_trace(rec_engine *e, long long *dev_buf);
 /* Self-test of the tcgen05/TMEM plumbing (bf16x3 split GEMM of one 128-row tile; see csrc/tc_selftest.cu):
  * mode 0: C[128,128] = A[128,64].B[128,64]^T ; mode 1: C[128,64] = P[128,128]^T.Q[128,64] ;
