@@ -51,27 +51,23 @@ __device__ __forceinline__ void stage_rows64(uint8_t *blk_hi, uint8_t *blk_lo, c
   }
 }
 
-// Slow path of the running top-k: insert the elements of one 32-column chunk that beat the k-th best into
-// the thread-private sorted list (shared memory, stride `stride` between ranks).  Ascending column order +
-// strict comparisons keep equal scores ordered by ascending id.
-__device__ __noinline__ void topk_insert_chunk(const float *lbuf, float *lv, int *li, int stride, int topk, int id0,
-                                               int &cnt, float &tau) {
-#pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    const float v = lbuf[j];
-    if (v > tau) {
-      int p = cnt < topk ? cnt : topk - 1;
-      while (p > 0 && lv[(p - 1) * stride] < v) {
-        lv[p * stride] = lv[(p - 1) * stride];
-        li[p * stride] = li[(p - 1) * stride];
-        --p;
-      }
-      lv[p * stride] = v;
-      li[p * stride] = id0 + j;
-      if (cnt < topk) ++cnt;
-      tau = cnt == topk ? lv[(topk - 1) * stride] : REC_NEG_INF;
-    }
+// Slow path of the running top-k: insert ONE element that beats the k-th best into the thread-private sorted list
+// (shared memory, stride `stride` between ranks).  Callers walk a chunk in ascending column order; together with the
+// strict comparisons that keeps equal scores ordered by ascending id.  (A per-chunk routine that re-scanned all 32
+// columns from a local-memory copy cost ~350 instructions per call; with 32 independent rows per warp some lane
+// takes the slow path in most chunks -- k ln(n/k) insertions per row and thread -- so it doubled the evaluation
+// epilogue.)
+__device__ __noinline__ void topk_insert_one(float v, int id, float *lv, int *li, int stride, int topk, int &cnt, float &tau) {
+  int p = cnt < topk ? cnt : topk - 1;
+  while (p > 0 && lv[(p - 1) * stride] < v) {
+    lv[p * stride] = lv[(p - 1) * stride];
+    li[p * stride] = li[(p - 1) * stride];
+    --p;
   }
+  lv[p * stride] = v;
+  li[p * stride] = id;
+  if (cnt < topk) ++cnt;
+  tau = cnt == topk ? lv[(topk - 1) * stride] : REC_NEG_INF;
 }
 
 // NB = 128-session blocks per CTA (they share every converted W tile), NT = compute threads (256: two
@@ -92,7 +88,7 @@ __device__ __noinline__ void topk_insert_chunk(const float *lbuf, float *lv, int
 // by a LOADER warp (per-thread global loads of a whole tile ran into the SM's outstanding-request limit: ~6000
 // cycles per tile); the compute warps read their share of a slot, release it, and convert from registers.
 template <int NB, int NT, bool ARG, bool RING>
-__global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
+__global__ void __launch_bounds__(NT + (RING ? (ARG ? 64 : 128) : 32), 1) head_stats_tc_kernel(TcHeadPtrs hp, const float *__restrict__ h, int B, int Vloc,
                                                                    int vocab_lo, int n_tiles, int do_stats, int first_head,
                                                                    int nh, float w0, float w1, float w2,
                                                                    const int64_t *__restrict__ target, int topk,
@@ -114,11 +110,15 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
   int *ti = reinterpret_cast<int *>(tv + (size_t)NB * topk * NT); // [NB][topk][NT]
   float *stg = reinterpret_cast<float *>(ti + (size_t)NB * topk * NT);  // RING: [n_slots][128 x 64] fp32 (every region before it is a multiple of 128 B)
   float *xch = stg;                                               // [NB][128][CS][5] end-of-kernel exchange (RING: reuses the slots)
-  __shared__ uint64_t mbar_done[2], mbar_full[2], slot_full[4], slot_free[4];
+  __shared__ uint64_t mbar_done[2], mbar_full[2], mbar_tfree[2], slot_full[4], slot_free[4];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool issuer = warp == NT / 32, loader = RING && warp == NT / 32 + 1;
+  // CONV: two CONVERTER warps turn the ring's fp32 tiles into the bf16 hi/lo stage, so the compute warps run nothing
+  // but epilogues (statistics mode; in greedy-action mode the compute warps combine the heads themselves)
+  constexpr bool CONV = RING && !ARG;
+  constexpr int NPROD = CONV ? 2 : NT / 32;  // warps that fill the bf16 stage / read the ring slots
+  const bool issuer = warp == NT / 32, loader = RING && warp == NT / 32 + 1, conv = CONV && warp >= NT / 32 + 2;
   const int q = warp & 3, cq = (warp >> 2) & (CS - 1);  // TMEM lane quarter, column split
   const int sp = blockIdx.x, n_split = gridDim.x, bg = blockIdx.y;
   const int b0 = bg * NB * 128;
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
   STRACE(19);
   if (tid == 0) {
     tc::mbar_init(&mbar_done[0], 1); tc::mbar_init(&mbar_done[1], 1);
-    tc::mbar_init(&mbar_full[0], NT / 32); tc::mbar_init(&mbar_full[1], NT / 32);
+    tc::mbar_init(&mbar_full[0], NPROD); tc::mbar_init(&mbar_full[1], NPROD);
+    tc::mbar_init(&mbar_tfree[0], NT / 32); tc::mbar_init(&mbar_tfree[1], NT / 32);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, NB * 256);
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
     if (++ld_hh == nh) { ld_hh = 0; ++ld_u; }
   };
   if (loader && lane == 0) {
-    for (int i = 0; i < 4; ++i) { tc::mbar_init(&slot_full[i], 1); tc::mbar_init(&slot_free[i], NT / 32); }
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&slot_full[i], 1); tc::mbar_init(&slot_free[i], NPROD); }
     tc::fence_barrier_init();
     while (ld_round == 0 && ld_u < n_units) loader_issue();
   }
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
       const int s = u & 1, ws = u & (NST - 1);
       if (!RING && lane == 0 && u + 2 + PD < n_units) l2_ahead(u + 2 + PD);
       tc::mbar_wait(&mbar_full[s], (u >> 1) & 1);
+      if (CONV && u >= 2) tc::mbar_wait(&mbar_tfree[s], ((u - 2) >> 1) & 1);  // every compute warp has read logits(u-2)
       tc::tc_fence_after();
       if (lane == 0) {
         const uint64_t bh = tc::desc_kmajor(tc::smem_u32(w_st + ws * 2 * BLK), 0), bl = tc::desc_kmajor(tc::smem_u32(w_st + ws * 2 * BLK + BLK), 0);
@@ -215,6 +217,54 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
         tc::mbar_wait(&slot_free[ld_sl], (ld_round - 1) & 1);  // every compute warp has read the slot's previous tile
         loader_issue();
       }
+    }
+  } else if (conv) {
+    // ---- converter warps (64 threads): slot ring -> bf16 hi/lo stage + bias tile, one unit ahead of the MMAs ----
+    const int ctid = tid - (NT + 64);
+    const float *bsrc = hp.b[first_head];
+    int sl = 0;
+    uint32_t round = 0;
+    float bq[2] = {0.f, 0.f};
+    auto bias_fetch_c = [&](int u) {
+      const int v0 = (t_lo + u) * 128;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bq[j] = (v0 + ctid + 64 * j < Vloc) ? __ldg(bsrc + v0 + ctid + 64 * j) : 0.f;
+    };
+    if (n_units > 0) bias_fetch_c(0);
+    for (int u = 0; u < n_units; ++u) {
+      const int v0 = (t_lo + u) * 128;
+      tc::mbar_wait(&slot_full[sl], round & 1);
+      const float *src = stg + sl * 8192;
+#pragma unroll 1
+      for (int qd = 0; qd < 4; ++qd) {  // 32 rows per pass: 4 chunk pairs per thread in registers
+        float4 xa[4], xb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = ctid + 64 * (qd * 4 + i), row = c >> 3, c8 = c & 7, sw = (c8 >> 2) & 1;
+          float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+          if (v0 + row < Vloc) {
+            x0 = *reinterpret_cast<const float4 *>(src + row * 64 + c8 * 8 + 4 * sw);
+            x1 = *reinterpret_cast<const float4 *>(src + row * 64 + c8 * 8 + 4 * (sw ^ 1));
+          }
+          xa[i] = sw ? x1 : x0;
+          xb[i] = sw ? x0 : x1;
+        }
+        if (qd == 0 && u > 0) tc::mbar_wait(&mbar_done[(u - 1) & 1], ((u - 1) >> 1) & 1);  // MMA(u-1) complete: the stage is free
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = ctid + 64 * (qd * 4 + i);
+          tc::store_split8(w_st, w_st + BLK, c >> 3, c & 7, xa[i], xb[i]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&slot_free[sl]);
+      if (++sl == n_slots) { sl = 0; ++round; }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bias_g[(u & 3) * 128 + ctid + 64 * j] = bq[j];
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&mbar_full[u & 1]);
+      if (u + 1 < n_units) bias_fetch_c(u + 1);
     }
   } else {
     // ---- compute warps ----
@@ -349,7 +399,9 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
       trow[nb] = (!ARG && do_stats && target && row < B) ? (int)(target[row] - vocab_lo) : -1;
     }
 
-    if (RING) {
+    if (CONV) {
+      // nothing to stage: the converter warps fill the bf16 stage
+    } else if (RING) {
       if (n_units > 0) { bias_fetch(0); gather(0); store_gathered(); bias_store(0); publish(0); }
       if (n_units > 1) bias_fetch(1);
     } else {
@@ -360,7 +412,10 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
 
     for (int u = 0; u < n_units; ++u) {
       STRACE(1);
-      if (RING) {
+      if (CONV) {
+        tc::mbar_wait(&mbar_done[u & 1], (u >> 1) & 1);
+        tc::tc_fence_after();
+      } else if (RING) {
         if (u + 1 < n_units) gather(u + 1);  // slot ring -> registers (heads combined)
         STRACE(3);
         tc::mbar_wait(&mbar_done[u & 1], (u >> 1) & 1);  // MMA(u) complete: logits(u) in TMEM, the bf16 stage is free
@@ -473,14 +528,19 @@ __global__ void __launch_bounds__(NT + (RING ? 64 : 32), 1) head_stats_tc_kernel
                 tau[nb] = topk == 1 ? r_v0[nb] : r_v1[nb];
               }
             } else if (cmax > tau[nb]) {
-              float lbuf[32];
+              float *lv = tv + (size_t)nb * topk * NT + tid;
+              int *li = ti + (size_t)nb * topk * NT + tid;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) lbuf[j] = l[j];
-              topk_insert_chunk(lbuf, tv + (size_t)nb * topk * NT + tid, ti + (size_t)nb * topk * NT + tid, NT, topk,
-                                vocab_lo + c_lo, cnt[nb], tau[nb]);
+              for (int j = 0; j < 32; ++j)
+                if (l[j] > tau[nb]) topk_insert_one(l[j], vocab_lo + c_lo + j, lv, li, NT, topk, cnt[nb], tau[nb]);
             }
           }
         }
+      }
+      if (CONV) {  // logits(u) are consumed: the issuer may overwrite this TMEM buffer with unit u+2
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&mbar_tfree[u & 1]);
       }
     }
 
@@ -582,7 +642,7 @@ static int launch_stats_tc_kernel(rec_engine *e, const HeadStatsArgs &a, dim3 gr
     REC_CUDA(e, cudaFuncSetAttribute(head_stats_tc_kernel<NB, NT, ARG, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  head_stats_tc_kernel<NB, NT, ARG, RING><<<grid, NT + (RING ? 64 : 32), smem, e->stream>>>(
+  head_stats_tc_kernel<NB, NT, ARG, RING><<<grid, NT + (RING ? (ARG ? 64 : 128) : 32), smem, e->stream>>>(
       tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo, n_tiles, ARG ? 0 : a.do_stats, ARG ? 1 : a.stats_head,
       ARG ? a.n_arg : 1, a.w[0], a.w[1], a.w[2], a.target, topk, e->part, e->part_stride, trace_sel() == (ARG ? 2 : 1) ? e->trace : nullptr,
       n_slots);
