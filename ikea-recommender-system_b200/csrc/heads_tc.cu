@@ -515,17 +515,26 @@ __global__ void __launch_bounds__(NT + (RING ? (ARG ? 64 : 128) : 32), 1) head_s
             const float cmax = tmax;
             if (smallk) {
               if (cmax > tau[nb]) {
+                // 8-column groups behind their own maximum: with 32 independent rows per warp SOME lane enters here in
+                // most chunks (k ln(n/k) entries per row), but rarely more than one or two groups are live
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float v = l[j];
-                  const int id = vocab_lo + c_lo + j;
-                  const bool g0 = v > r_v0[nb], g1 = v > r_v1[nb];
-                  r_v1[nb] = g0 ? r_v0[nb] : (g1 ? v : r_v1[nb]);
-                  r_i1[nb] = g0 ? r_i0[nb] : (g1 ? id : r_i1[nb]);
-                  r_v0[nb] = g0 ? v : r_v0[nb];
-                  r_i0[nb] = g0 ? id : r_i0[nb];
+                for (int g8 = 0; g8 < 4; ++g8) {
+                  float gm = fmaxf(fmaxf(l[g8 * 8], l[g8 * 8 + 1]), fmaxf(l[g8 * 8 + 2], l[g8 * 8 + 3]));
+                  gm = fmaxf(gm, fmaxf(fmaxf(l[g8 * 8 + 4], l[g8 * 8 + 5]), fmaxf(l[g8 * 8 + 6], l[g8 * 8 + 7])));
+                  if (gm > tau[nb]) {
+#pragma unroll
+                    for (int j = g8 * 8; j < g8 * 8 + 8; ++j) {
+                      const float v = l[j];
+                      const int id = vocab_lo + c_lo + j;
+                      const bool g0 = v > r_v0[nb], g1 = v > r_v1[nb];
+                      r_v1[nb] = g0 ? r_v0[nb] : (g1 ? v : r_v1[nb]);
+                      r_i1[nb] = g0 ? r_i0[nb] : (g1 ? id : r_i1[nb]);
+                      r_v0[nb] = g0 ? v : r_v0[nb];
+                      r_i0[nb] = g0 ? id : r_i0[nb];
+                    }
+                    tau[nb] = topk == 1 ? r_v0[nb] : r_v1[nb];
+                  }
                 }
-                tau[nb] = topk == 1 ? r_v0[nb] : r_v1[nb];
               }
             } else if (cmax > tau[nb]) {
               float *lv = tv + (size_t)nb * topk * NT + tid;
@@ -692,7 +701,7 @@ int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out
   // one 128-session block with 16 warps (32 logits per thread and tile) beats two blocks with 8 warps.
   // (measured: 70 852 items / B = 2000: 0.83 vs 0.97 ms per batch; 1 M items / B = 5000: 8.3 vs 6.7 ms -- with many
   // column groups the per-tile weight conversion, repeated by every group, outweighs the faster epilogue)
-  if (a.topk <= 20 && eval_wide && (int64_t)cdiv(a.B, 128) * cdiv(e->Vloc, 128) < 200000)
+  if (a.topk <= 20 && (eval_wide == 2 || (eval_wide && (int64_t)cdiv(a.B, 128) * cdiv(e->Vloc, 128) < 200000)))
     return launch_stats_tc_variant<1, 512, false, true>(e, a, n_split_out);
   if (a.topk <= 20) return launch_stats_tc_variant<2, 256, false, true>(e, a, n_split_out);
   return launch_stats_tc_variant<1, 256, false, true>(e, a, n_split_out);
