@@ -1104,9 +1104,9 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
   float *w_stage = reinterpret_cast<float *>(sm + 10 * BLK);     // fp32 tile [128][64], TMA destination (32 KB)
   uint8_t *ones = sm + 12 * BLK;                                  // 4 KB of bf16 1.0
   float *bias_s = reinterpret_cast<float *>(ones + 4096);        // [128]
-  float *lse_s = bias_s + 128;                                    // [256]
-  int *tgt_s = reinterpret_cast<int *>(lse_s + 256);             // [256] target column relative to vocab_lo
-  float *xpose = reinterpret_cast<float *>(tgt_s + 256);         // [8 warps][32 rows][20] Adam warps' transpose staging
+  float *lse_s = bias_s + 128;                                    // [2][256] per-chunk log-sum-exp (double-buffered)
+  int *tgt_s = reinterpret_cast<int *>(lse_s + 512);             // [2][256] target column relative to vocab_lo
+  float *xpose = reinterpret_cast<float *>(tgt_s + 512);         // [8 warps][32 rows][20] Adam warps' transpose staging
   enum { MB_L0 = 0, MB_L1, MB_W, MB_H, MB_G, MB_GT, MB_WREADY, MB_DL, MB_DWFREE, MB_N };
   __shared__ uint64_t mbar[MB_N];
   __shared__ uint32_t tmem_base_s;
@@ -1116,7 +1116,11 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = warp == NT / 32, adam = warp > NT / 32;
   const int q = warp & 3, cq = (warp >> 2) & 3;  // TMEM lane quarter; column quarter (4 warps share a lane quarter)
-  const int nbb = (B + 127) / 128;
+  // batches beyond 256 sessions run in chunks of 256 per tile: the h chunk is re-read (TMA, from L2) per (tile, chunk),
+  // dW/db accumulate over the chunks in TMEM, dh leaves TMEM per (tile, chunk) into this CTA's slice
+  const int n_chunks = (B + 255) / 256;
+  const bool resident = n_chunks == 1;  // dh stays in TMEM across all tiles of the CTA
+  const int nbb0 = min(2, (B + 127) / 128);  // 128-session blocks of chunk 0
   const float log2_inv_B = __log2f(inv_B);
 
   if (issuer && lane == 0) {
@@ -1127,13 +1131,13 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
       const uint32_t bytes = (uint32_t)min(128, Vloc - (int)blockIdx.x * 128) * 256u;
       tc::mbar_expect_tx(&mbar[MB_W], bytes);
       tc::bulk_g2s(w_stage, hp.w + (int64_t)blockIdx.x * 128 * 64, bytes, &mbar[MB_W]);
-      tc::mbar_expect_tx(&mbar[MB_H], (uint32_t)nbb * 2 * BLK);
-      tc::bulk_g2s(h_blk, hpack, (uint32_t)nbb * 2 * BLK, &mbar[MB_H]);
+      tc::mbar_expect_tx(&mbar[MB_H], (uint32_t)nbb0 * 2 * BLK);
+      tc::bulk_g2s(h_blk, hpack, (uint32_t)nbb0 * 2 * BLK, &mbar[MB_H]);
     }
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   for (int i = tid; i < 4096 / 4; i += BWD2_THREADS) reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;
-  if (tid < 256) {
+  if (tid < 256 && resident) {
     lse_s[tid] = tid < B ? row_stats[(int64_t)tid * 8] : 0.f;
     tgt_s[tid] = tid < B ? (int)(target[tid] - vocab_lo) : -1;
   }
@@ -1205,8 +1209,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
         }
       }
     };
-    if ((int)blockIdx.x < n_tiles) tc::mbar_wait(&mbar[MB_H], 0);
-    uint32_t ph_dl = 0;
+    uint32_t ph_dl = 0, ph_ready = 0, ph_h = 0;
     int k = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
       if (lane == 0) {  // Adam state of this tile -> L2 while the tile's GEMMs run
@@ -1214,26 +1217,42 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
         tc::l2_prefetch(hp.wm + (int64_t)t * 128 * 64, bytes);
         tc::l2_prefetch(hp.wv + (int64_t)t * 128 * 64, bytes);
       }
-      tc::mbar_wait(&mbar[MB_WREADY], k & 1);
-      tc::tc_fence_after();
-      if (lane == 0) {
-        if (t + (int)gridDim.x < n_tiles) prefetch_w(t + gridDim.x);  // every compute warp has read the staging buffer
-        for (int bb = 0; bb < nbb; ++bb) issue_logits(bb);
-      }
-      __syncwarp();
-      for (int bb = 0; bb < nbb; ++bb) {
-        tc::mbar_wait(&mbar[MB_DL], ph_dl);
-        ph_dl ^= 1;
-        if (bb == 0 && k > 0) tc::mbar_wait(&mbar[MB_DWFREE], (k - 1) & 1);  // the Adam warps have read dW/db of the previous tile
+      for (int c = 0; c < n_chunks; ++c) {
+        const int nbb = min(2, (B - c * 256 + 127) / 128);
+        // every compute warp is done with the previous (tile, chunk): W converted (c == 0), lse/targets staged, dh read
+        tc::mbar_wait(&mbar[MB_WREADY], ph_ready);
+        ph_ready ^= 1;
+        if (k == 0 && c == 0) {
+          tc::mbar_wait(&mbar[MB_H], ph_h);  // requested before the prologue barrier
+          ph_h ^= 1;
+        } else if (!resident) {  // h chunk (all MMAs that read the previous one are complete)
+          if (lane == 0) {
+            tc::mbar_expect_tx(&mbar[MB_H], (uint32_t)nbb * 2 * BLK);
+            tc::bulk_g2s(h_blk, hpack + (size_t)c * 4 * BLK, (uint32_t)nbb * 2 * BLK, &mbar[MB_H]);
+          }
+          tc::mbar_wait(&mbar[MB_H], ph_h);
+          ph_h ^= 1;
+        }
         tc::tc_fence_after();
         if (lane == 0) {
-          issue_dW(bb, bb == 0);
-          issue_db(bb == 0);
-          issue_dh(bb, k > 0);
-          tc::mma_commit(&mbar[MB_G]);
-          if (bb == nbb - 1) tc::mma_commit(&mbar[MB_GT]);
+          if (c == 0 && t + (int)gridDim.x < n_tiles) prefetch_w(t + gridDim.x);  // every compute warp has read the staging buffer
+          for (int bb = 0; bb < nbb; ++bb) issue_logits(bb);
         }
         __syncwarp();
+        for (int bb = 0; bb < nbb; ++bb) {
+          tc::mbar_wait(&mbar[MB_DL], ph_dl);
+          ph_dl ^= 1;
+          if (c == 0 && bb == 0 && k > 0) tc::mbar_wait(&mbar[MB_DWFREE], (k - 1) & 1);  // the Adam warps have read dW/db of the previous tile
+          tc::tc_fence_after();
+          if (lane == 0) {
+            issue_dW(bb, c == 0 && bb == 0);
+            issue_db(c == 0 && bb == 0);
+            issue_dh(bb, resident && k > 0);
+            tc::mma_commit(&mbar[MB_G]);
+            if (c == n_chunks - 1 && bb == nbb - 1) tc::mma_commit(&mbar[MB_GT]);
+          }
+          __syncwarp();
+        }
       }
     }
   } else if (adam) {
@@ -1328,7 +1347,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&mbar[which]);
     };
-    uint32_t phG = 0;
+    uint32_t phG = 0, phL[2] = {0, 0};
     float bias_p = 0.f;
     if (tid < 128 && (int)blockIdx.x < n_tiles && (int)blockIdx.x * 128 + tid < Vloc) bias_p = hp.b[blockIdx.x * 128 + tid];
     int k = 0;
@@ -1351,71 +1370,100 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
         tc::store_split8(w_hi, w_lo, row, c8, a, b);
       }
       if (tid < 128) bias_s[tid] = bias_p;
-      publish(MB_WREADY);
-      if (tid < 128) {  // logits bias of the next tile (its Adam update belongs to a later tile: no hazard)
-        const int nt = t + gridDim.x;
-        bias_p = (nt < n_tiles && nt * 128 + tid < Vloc) ? hp.b[nt * 128 + tid] : 0.f;
-      }
-      TRACE2(3);
-      for (int bb = 0; bb < nbb; ++bb) {
-        TRACE2(4);
-        tc::mbar_wait(&mbar[MB_L0 + bb], k & 1);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int r0 = c * 256, nbb = min(2, (B - r0 + 127) / 128);
+        float *lse_c = lse_s + (resident ? 0 : (c & 1) * 256);
+        int *tgt_c = tgt_s + (resident ? 0 : (c & 1) * 256);
+        if (!resident && tid < 256) {  // this chunk's rows (the other buffer may still be read by a slower warp)
+          const int row = r0 + tid;
+          lse_c[tid] = row < B ? row_stats[(int64_t)row * 8] : 0.f;
+          tgt_c[tid] = row < B ? (int)(target[row] - vocab_lo) : -1;
+        }
+        publish(MB_WREADY);
+        if (c == 0 && tid < 128) {  // logits bias of the next tile (its Adam update belongs to a later tile: no hazard)
+          const int nt = t + gridDim.x;
+          bias_p = (nt < n_tiles && nt * 128 + tid < Vloc) ? hp.b[nt * 128 + tid] : 0.f;
+        }
+        TRACE2(3);
+        for (int bb = 0; bb < nbb; ++bb) {
+          TRACE2(4);
+          tc::mbar_wait(&mbar[MB_L0 + bb], phL[bb]);
+          phL[bb] ^= 1;
+          tc::tc_fence_after();
+          TRACE2(5);
+          // ---- epilogue 1: dlogits of (row, 32 columns), computed in registers first ------------------
+          const int r = q * 32 + lane, rl = bb * 128 + r;
+          float l[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + T_L + (uint32_t)(bb * 128 + cq * 32), l);
+          TRACE2(51);
+          {
+            // dl = exp(l + b - lse) / B as ONE ex2 of an fma: (l + b) log2e + (log2(1/B) - lse log2e); the one-hot
+            // target and the masking of columns/rows beyond the matrix are rare fix-ups outside the hot loop
+            const bool rv = r0 + rl < B;
+            const float cst = fmaf(-lse_c[rl], LOG2E_F, log2_inv_B);
+            const int tj = tgt_c[rl] - v0 - cq * 32;
+            const float4 *bg = reinterpret_cast<const float4 *>(bias_s + cq * 32);
+            const int nvalid = rv ? min(32, Vloc - v0 - cq * 32) : 0;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = bg[j4];
+              l[j4 * 4 + 0] = tc::ex2_ftz(fmaf(l[j4 * 4 + 0] + b4.x, LOG2E_F, cst));
+              l[j4 * 4 + 1] = tc::ex2_ftz(fmaf(l[j4 * 4 + 1] + b4.y, LOG2E_F, cst));
+              l[j4 * 4 + 2] = tc::ex2_ftz(fmaf(l[j4 * 4 + 2] + b4.z, LOG2E_F, cst));
+              l[j4 * 4 + 3] = tc::ex2_ftz(fmaf(l[j4 * 4 + 3] + b4.w, LOG2E_F, cst));
+            }
+            if (tj >= 0 && tj < 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= inv_B;
+            }
+            if (nvalid < 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j >= nvalid) l[j] = 0.f;
+            }
+          }
+          TRACE2(6);
+          if (bb > 0) {  // the dl buffer is still being read by the gradient MMAs of block bb-1
+            tc::mbar_wait(&mbar[MB_G], phG);
+            phG ^= 1;
+          }
+          TRACE2(7);
+          {
+            uint8_t *bh = dl_hi + (cq >> 1) * BLK, *bl = dl_lo + (cq >> 1) * BLK;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8)
+              tc::store_split8(bh, bl, r, (cq & 1) * 4 + c8, make_float4(l[c8 * 8], l[c8 * 8 + 1], l[c8 * 8 + 2], l[c8 * 8 + 3]),
+                               make_float4(l[c8 * 8 + 4], l[c8 * 8 + 5], l[c8 * 8 + 6], l[c8 * 8 + 7]));
+          }
+          publish(MB_DL);
+          TRACE2(8);
+        }
+        tc::mbar_wait(&mbar[MB_G], phG);  // gradient MMAs of the chunk's last block: W / dl / h operands may be overwritten
+        phG ^= 1;
         tc::tc_fence_after();
-        TRACE2(5);
-        // ---- epilogue 1: dlogits of (row, 32 columns), computed in registers first ------------------
-        const int r = q * 32 + lane, rl = bb * 128 + r;
-        float l[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + T_L + (uint32_t)(bb * 128 + cq * 32), l);
-        TRACE2(51);
-        {
-          // dl = exp(l + b - lse) / B as ONE ex2 of an fma: (l + b) log2e + (log2(1/B) - lse log2e); the one-hot
-          // target and the masking of columns/rows beyond the matrix are rare fix-ups outside the hot loop
-          const bool rv = rl < B;
-          const float cst = fmaf(-lse_s[rl], LOG2E_F, log2_inv_B);
-          const int tj = tgt_s[rl] - v0 - cq * 32;
-          const float4 *bg = reinterpret_cast<const float4 *>(bias_s + cq * 32);
-          const int nvalid = rv ? min(32, Vloc - v0 - cq * 32) : 0;
+        TRACE2(10);
+        if (!resident) {
+          // dh of this (tile, chunk): TMEM -> this CTA's slice (first tile stores, later tiles add)
+          float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
+          for (int bb = 0; bb < nbb; ++bb) {
+            const int row = r0 + bb * 128 + q * 32 + lane;
+            float g[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + cq * 16), g);
+            if (row < B) {
+              float4 *dst = reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = bg[j4];
-            l[j4 * 4 + 0] = tc::ex2_ftz(fmaf(l[j4 * 4 + 0] + b4.x, LOG2E_F, cst));
-            l[j4 * 4 + 1] = tc::ex2_ftz(fmaf(l[j4 * 4 + 1] + b4.y, LOG2E_F, cst));
-            l[j4 * 4 + 2] = tc::ex2_ftz(fmaf(l[j4 * 4 + 2] + b4.z, LOG2E_F, cst));
-            l[j4 * 4 + 3] = tc::ex2_ftz(fmaf(l[j4 * 4 + 3] + b4.w, LOG2E_F, cst));
-          }
-          if (tj >= 0 && tj < 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= inv_B;
-          }
-          if (nvalid < 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j >= nvalid) l[j] = 0.f;
+              for (int j = 0; j < 4; ++j) {
+                float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+                if (k > 0) { float4 p = dst[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                dst[j] = o;
+              }
+            }
           }
         }
-        TRACE2(6);
-        if (bb > 0) {  // the dl buffer is still being read by the gradient MMAs of block bb-1
-          tc::mbar_wait(&mbar[MB_G], phG);
-          phG ^= 1;
-        }
-        TRACE2(7);
-        {
-          uint8_t *bh = dl_hi + (cq >> 1) * BLK, *bl = dl_lo + (cq >> 1) * BLK;
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8)
-            tc::store_split8(bh, bl, r, (cq & 1) * 4 + c8, make_float4(l[c8 * 8], l[c8 * 8 + 1], l[c8 * 8 + 2], l[c8 * 8 + 3]),
-                             make_float4(l[c8 * 8 + 4], l[c8 * 8 + 5], l[c8 * 8 + 6], l[c8 * 8 + 7]));
-        }
-        publish(MB_DL);
-        TRACE2(8);
       }
-      tc::mbar_wait(&mbar[MB_G], phG);  // gradient MMAs of the last block: W and dl operands may be overwritten
-      phG ^= 1;
-      tc::tc_fence_after();
-      TRACE2(10);
     }
     // ---- resident dh of this CTA: TMEM -> its slice ---------------------------------------------------
     float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
-    for (int bb = 0; bb < nbb; ++bb) {
+    for (int bb = 0; resident && bb < nbb0; ++bb) {
       const int row = bb * 128 + q * 32 + lane;
       float g[16];
       if (k > 0) {
@@ -1452,7 +1500,7 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   TcTrainPtrs t = {p.head_w[0], p.head_w_m[0], p.head_w_v[0], p.head_b[0], p.head_b_m[0], p.head_b_v[0]};
   const int n_tiles = cdiv(e->Vloc, 128);
   const int n_cta = tc_bwd_slices(e);
-  const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072 + 8 * 32 * 20 * 4;  // (the transpose staging belongs to tc2 only)
+  const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072 + 2048 + 8 * 32 * 20 * 4;  // (double-buffered lse/targets and the transpose staging belong to tc2 only)
   static bool attr_set = false;
   if (!attr_set) {
     REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1462,7 +1510,7 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   REC_LAUNCH_CHECK(e);
   static int v1 = -1;
   if (v1 < 0) { const char *v = getenv("REC_BWD_V1"); v1 = v ? atoi(v) : 0; }
-  if (B <= 256 && !v1) {  // warp-specialised variant: dh resident in TMEM
+  if (!v1) {  // warp-specialised variant (dh resident in TMEM when B <= 256)
     static bool attr2_set = false;
     if (!attr2_set) {
       REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
