@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(192, 2) gru_fwd64_kernel(GruPasses ps, int B, 
   __shared__ float pre_h[FR][G];
   __shared__ int len_s[FR];
   __shared__ int tok_s[FR][64];  // L <= 64 on this path
+  __shared__ __align__(16) float xall[FR][16][E];  // L <= 16: every token row of the CTA's sessions (12 KB)
 
   float wi[E], wh[H];
   {
@@ -198,10 +199,28 @@ __global__ void __launch_bounds__(192, 2) gru_fwd64_kernel(GruPasses ps, int B, 
     }
     return v;
   };
-  if (tid < FR * 16) reinterpret_cast<float4 *>(&xs[xr][0])[xc] = load_x(0);
+  // L <= 16 (every headline config: L = 10): ALL token rows of the CTA's sessions are requested up front (one memory
+  // round trip, overlapped with the weight loads above) instead of one dependent gather per time step
+  const bool pre = L <= 16;
+  if (pre) {
+    for (int i = tid; i < FR * L * 16; i += 192) {
+      const int r = i / (L * 16), rem = i - r * L * 16, t = rem >> 4, c = rem & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < len_s[r]) v = __ldg(reinterpret_cast<const float4 *>(P.emb + (int64_t)tok_s[r][t] * E) + c);
+      reinterpret_cast<float4 *>(&xall[r][t][0])[c] = v;
+    }
+  } else if (tid < FR * 16) {
+    reinterpret_cast<float4 *>(&xs[xr][0])[xc] = load_x(0);
+  }
   __syncthreads();
   for (int i = 0; i < maxlen; ++i) {
-    float4 xnext = load_x(i + 1);  // prefetch, consumed after the gate phase
+    float4 xnext = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!pre) xnext = load_x(i + 1);  // prefetch, consumed after the gate phase
+    const float4 *xrow[FR];
+#pragma unroll
+    for (int r = 0; r < FR; ++r)
+      xrow[r] = pre ? reinterpret_cast<const float4 *>(&xall[r][dir ? max(len_s[r] - 1 - i, 0) : i][0])
+                    : reinterpret_cast<const float4 *>(&xs[r][0]);
     float ai[FR][2], ah[FR][2];
 #pragma unroll
     for (int r = 0; r < FR; ++r) { ai[r][0] = bij; ai[r][1] = 0.f; ah[r][0] = bhj; ah[r][1] = 0.f; }
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(192, 2) gru_fwd64_kernel(GruPasses ps, int B, 
     for (int k = 0; k < 16; ++k) {
 #pragma unroll
       for (int r = 0; r < FR; ++r) {
-        float4 x = reinterpret_cast<const float4 *>(&xs[r][0])[k];
+        float4 x = xrow[r][k];
         float4 hv = reinterpret_cast<const float4 *>(&hs[r][0])[k];
         ai[r][0] = fmaf(wi[4 * k], x.x, ai[r][0]); ai[r][1] = fmaf(wi[4 * k + 1], x.y, ai[r][1]);
         ai[r][0] = fmaf(wi[4 * k + 2], x.z, ai[r][0]); ai[r][1] = fmaf(wi[4 * k + 3], x.w, ai[r][1]);
@@ -238,7 +257,7 @@ __global__ void __launch_bounds__(192, 2) gru_fwd64_kernel(GruPasses ps, int B, 
         hs[r][u] = (1.f - zg) * ng + zg * hold;
       }
     }
-    if (tid < FR * 16) reinterpret_cast<float4 *>(&xs[xr][0])[xc] = xnext;
+    if (!pre && tid < FR * 16) reinterpret_cast<float4 *>(&xs[xr][0])[xc] = xnext;
     __syncthreads();
   }
   if (tid < FR * H) {
