@@ -9,6 +9,7 @@ Public surface (mirrors the reference `recommenders` package for the hot path):
     recommenders.models.SQN.sqn_gru          SQN_Network, SQN_trainer
     recommenders.models.SMORL.smorl_gru      SMORL_GRU_Net, SMORL_trainer
     recommenders.evaluate.eval_protocol      evaluate, update_train_metrics, get_preds
+    recommenders.data_utils.replay_buffer    DeviceReplayBuffer, DeviceEvaluationDataset (device-resident sampling)
 """
 
 from . import _native
@@ -21,6 +22,8 @@ from .recommenders.models.BidirGRU4Rec.model import BidirGRU4Rec, BidirGRU4Rec_t
 from .recommenders.models.SQN.sqn_gru import SQN_Network, SQN_trainer  # noqa: E402,F401
 from .recommenders.models.SMORL.smorl_gru import SMORL_GRU_Net, SMORL_trainer  # noqa: E402,F401
 from .recommenders.evaluate.eval_protocol import evaluate, update_train_metrics, get_preds  # noqa: E402,F401
+from .recommenders.data_utils.replay_buffer import DeviceReplayBuffer, DeviceEvaluationDataset  # noqa: E402,F401
 
 __all__ = ["Engine", "GRU4Rec", "GRU4Rec_trainer", "BidirGRU4Rec", "BidirGRU4Rec_trainer", "SQN_Network",
-           "SQN_trainer", "SMORL_GRU_Net", "SMORL_trainer", "evaluate", "update_train_metrics", "get_preds"]
+           "SQN_trainer", "SMORL_GRU_Net", "SMORL_trainer", "evaluate", "update_train_metrics", "get_preds",
+           "DeviceReplayBuffer", "DeviceEvaluationDataset"]

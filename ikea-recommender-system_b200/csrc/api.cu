@@ -13,6 +13,7 @@ int launch_eval_metrics(rec_engine *e, const rec_batch *b, const rec_eval_opts *
                         const rec_eval_accum *acc, double *rowm, int32_t *topk_ids, float *topk_scores);
 size_t head_bwd_smem_bytes(int D);
 int launch_pack_batch(rec_engine *e, const rec_batch *b, uint8_t *out);
+int launch_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B, const rec_batch *out);
 int launch_unpack_batch(rec_engine *e, const uint8_t *gathered, int G, int Bl, size_t stride, const rec_batch *out);
 
 static char g_err[512] = "";
@@ -1013,6 +1014,15 @@ extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_
 }
 
 // ---- packed batches for the input all-gather of sharded runs ----------------------------------------------
+extern "C" int rec_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B,
+                                const rec_batch *out) {
+  if (!e) return REC_EINVAL;
+  if (!columns || !idx || !out || n_rows < 1 || B < 1) REC_FAIL(e, REC_EINVAL, "rec_gather_batch: null argument or empty buffer");
+  if (!columns->s || !columns->a || !columns->true_len || !out->s || !out->a || !out->true_len)
+    REC_FAIL(e, REC_EINVAL, "rec_gather_batch: s, a and true_len are mandatory on both sides");
+  return launch_gather_batch(e, columns, n_rows, idx, B, out);
+}
+
 extern "C" int64_t rec_packed_batch_bytes(const rec_engine *e, int B) {
   if (!e || B < 1) return -1;
   int64_t n = (int64_t)B * (2 * e->cfg.state_size + 3) * 8 + (int64_t)B * 5;

@@ -268,6 +268,39 @@ __global__ void unpack_batch_kernel(const uint8_t *__restrict__ gathered, int G,
   }
 }
 
+// Replay-buffer sampling on the device (ikea/data_utils/replay_buffer.py:65-74 + the DataLoader's collate):
+// row idx[b] of every column of the device-resident buffer -> row b of the batch.  One thread per 8-byte element of
+// the state rows, the scalar columns ride along; indices are clamped into [0, n_rows).
+__global__ void gather_batch_kernel(rec_batch col, int64_t n_rows, const int64_t *__restrict__ idx, int B, int L,
+                                    int64_t *__restrict__ o_s, int64_t *__restrict__ o_sn, int64_t *__restrict__ o_a,
+                                    int64_t *__restrict__ o_len, int64_t *__restrict__ o_nlen, float *__restrict__ o_r,
+                                    uint8_t *__restrict__ o_end) {
+  const int n = B * L;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = i / L, t = i - b * L;
+    int64_t row = idx[b];
+    row = row < 0 ? 0 : (row >= n_rows ? n_rows - 1 : row);
+    o_s[i] = col.s[row * L + t];
+    if (col.s_next && o_sn) o_sn[i] = col.s_next[row * L + t];
+    if (t == 0) {
+      o_a[b] = col.a[row];
+      o_len[b] = col.true_len[row];
+      if (col.true_next_len && o_nlen) o_nlen[b] = col.true_next_len[row];
+      if (col.r && o_r) o_r[b] = col.r[row];
+      if (col.is_end && o_end) o_end[b] = col.is_end[row];
+    }
+  }
+}
+int launch_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B,
+                        const rec_batch *out) {
+  const int L = e->cfg.state_size, n = B * L;
+  gather_batch_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(*columns, n_rows, idx, B, L, (int64_t *)out->s, (int64_t *)out->s_next,
+                                                          (int64_t *)out->a, (int64_t *)out->true_len,
+                                                          (int64_t *)out->true_next_len, (float *)out->r, (uint8_t *)out->is_end);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
 int launch_pack_batch(rec_engine *e, const rec_batch *b, uint8_t *out) {
   const int n = b->B * (2 * e->cfg.state_size + 5);
   pack_batch_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(*b, e->cfg.state_size, out);

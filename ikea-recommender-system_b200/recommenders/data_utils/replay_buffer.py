@@ -1,0 +1,173 @@
+"""Device-resident replay buffer: the reference's `ReplayBuffer` / `EvaluationDataset`
+(ikea/data_utils/replay_buffer.py:26-127) + the `DataLoader(shuffle=True)` that feeds `train_step`
+(ikea/training/trainSQN.py), re-designed for the native path.
+
+The reference keeps the columns in numpy, indexes one row per `__getitem__`, collates 256 of them in python per step
+and ships the batch to the GPU: ~10^4-10^5 sessions/s.  Here the columns are uploaded ONCE, an epoch is one
+permutation (the same `torch.randperm(n, generator=g)` the DataLoader's RandomSampler draws, so a seeded epoch visits
+the rows in the reference's order), and every batch is one launch of `rec_gather_batch` (include/recsys_b200.h)
+that writes the tuple `(s, a, r, s_next, true_len, true_next_len, is_end)` straight into HBM -- no host work and no
+host->device copy per step.  Constructor keywords, `__len__` and `__getitem__` are the reference's.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ... import _native as N
+
+
+def _read_json_lines(path, names):
+    import pandas as pd
+    df = pd.read_json(path, orient="records", lines=True)
+    return {k: df[v] for k, v in names.items()}
+
+
+class DeviceReplayBuffer:
+    """Drop-in for `ReplayBuffer` (ikea/data_utils/replay_buffer.py:26-75) with device-side sampling."""
+
+    COLUMNS = ("states", "actions", "reward", "next_states", "true_state_len", "true_next_state_len", "is_end")
+
+    def __init__(self, dir=None, state_name="state", next_state_name="next_state", action_name="action",
+                 end_name="is_end", state_len_name="true_state_len", true_next_state_len_name="true_next_state_len",
+                 reward_name="r_act", arrays=None):
+        self.dir = dir
+        self.state_name, self.next_state_name = state_name, next_state_name
+        self.reward_name, self.action_name, self.end_name = reward_name, action_name, end_name
+        if arrays is None:
+            cols = _read_json_lines(dir, dict(states=state_name, next_states=next_state_name, actions=action_name,
+                                              reward=reward_name, true_state_len=state_len_name,
+                                              true_next_state_len=true_next_state_len_name, is_end=end_name))
+            arrays = dict(states=np.array(cols["states"].values.tolist()),
+                          next_states=np.array(cols["next_states"].values.tolist()),
+                          actions=cols["actions"].to_numpy(), reward=cols["reward"].to_numpy(),
+                          true_state_len=cols["true_state_len"].to_numpy(),
+                          true_next_state_len=cols["true_next_state_len"].to_numpy(), is_end=cols["is_end"].to_numpy())
+        missing = [c for c in self.COLUMNS if c not in arrays]
+        if missing:
+            raise ValueError(f"replay buffer columns missing: {missing}")
+        for c in self.COLUMNS:  # numpy, like the reference (host-side indexing keeps working)
+            setattr(self, c, np.asarray(arrays[c]))
+        n = len(self.actions)
+        if self.states.ndim != 2 or self.next_states.shape != self.states.shape or any(
+                len(getattr(self, c)) != n for c in self.COLUMNS):
+            raise ValueError("replay buffer columns disagree in length / shape")
+        self._dev = None
+        self._engine = None
+
+    @classmethod
+    def from_arrays(cls, states, actions, reward, next_states, true_state_len, true_next_state_len, is_end):
+        return cls(arrays=dict(states=states, actions=actions, reward=reward, next_states=next_states,
+                               true_state_len=true_state_len, true_next_state_len=true_next_state_len, is_end=is_end))
+
+    # ---- the reference's Dataset protocol ---------------------------------------------------------------
+    def __len__(self):
+        return len(self.actions)
+
+    def __getitem__(self, idx):
+        return (self.states[idx], self.actions[idx], self.reward[idx], self.next_states[idx], self.true_state_len[idx],
+                self.true_next_state_len[idx], self.is_end[idx])
+
+    # ---- device residency ----------------------------------------------------------------------------------
+    def to_device(self, device):
+        """Upload every column once: int64 ids / lengths, float32 rewards, uint8 is_end."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("DeviceReplayBuffer.to_device needs a CUDA device (there is no CPU path)")
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dtype=dt).to(device).contiguous()
+        self._dev = dict(s=t(self.states, torch.int64), a=t(self.actions, torch.int64), r=t(self.reward, torch.float32),
+                         sn=t(self.next_states, torch.int64), ln=t(self.true_state_len, torch.int64),
+                         nl=t(self.true_next_state_len, torch.int64), e=t(self.is_end.astype(np.uint8), torch.uint8))
+        return self
+
+    @property
+    def device(self):
+        return None if self._dev is None else self._dev["s"].device
+
+    def bytes_on_device(self):
+        return 0 if self._dev is None else sum(v.numel() * v.element_size() for v in self._dev.values())
+
+    @staticmethod
+    def epoch_permutation(n, shuffle=True, generator=None):
+        """Row order of one epoch: exactly what `iter(DataLoader(buffer, shuffle=shuffle, generator=generator))` visits.
+
+        A DataLoader iterator first draws its `_base_seed` from the generator (or the global RNG), then the
+        RandomSampler draws ONE `torch.randperm(n)` -- from `generator`, or, without one, from a fresh generator seeded
+        by another draw of the global RNG (torch/utils/data/dataloader.py, sampler.py).  Both draws are replayed here,
+        so `torch.manual_seed(seed)` + this method visits the rows in the reference loop's order."""
+        if not shuffle:
+            return torch.arange(n)
+        torch.empty((), dtype=torch.int64).random_(generator=generator)  # the iterator's _base_seed
+        if generator is None:
+            generator = torch.Generator()
+            generator.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+        return torch.randperm(n, generator=generator)
+
+    @staticmethod
+    def batch_bounds(n, batch_size, drop_last=False):
+        """[(lo, hi)) slices of the epoch order, like `BatchSampler`."""
+        stop = n - n % batch_size if drop_last else n
+        return [(lo, min(lo + batch_size, stop)) for lo in range(0, stop, batch_size)]
+
+    def batches(self, engine, batch_size, shuffle=True, generator=None, drop_last=False, slots=4):
+        """Yield `(s, a, r, s_next, true_len, true_next_len, is_end)` device tensors for one epoch.
+
+        `engine`: the trainer's native engine (`trainer._ready(batch_size)`); the gather runs on its stream, so a
+        `train_step_async(*batch)` issued next is ordered after it.  `slots` output buffers rotate: a yielded batch
+        stays valid until `slots - 1` later batches have been requested."""
+        if self._dev is None:
+            raise RuntimeError("call to_device(device) first")
+        d = self._dev
+        n, L, dev = len(self), int(self.states.shape[1]), d["s"].device
+        perm = self.epoch_permutation(n, shuffle, generator).to(dev)
+        cols = engine._batch(n, d["s"], d["a"], d["ln"], d["r"], d["sn"], d["nl"], d["e"])
+        ring = []
+        for _ in range(max(2, slots)):
+            i64 = dict(dtype=torch.int64, device=dev)
+            ring.append((torch.empty(batch_size, L, **i64), torch.empty(batch_size, **i64),
+                         torch.empty(batch_size, dtype=torch.float32, device=dev), torch.empty(batch_size, L, **i64),
+                         torch.empty(batch_size, **i64), torch.empty(batch_size, **i64),
+                         torch.empty(batch_size, dtype=torch.uint8, device=dev)))
+        for k, (lo, hi) in enumerate(self.batch_bounds(n, batch_size, drop_last)):
+            B = hi - lo
+            s, a, r, sn, ln, nl, e = (x[:B] for x in ring[k % len(ring)])
+            out = engine._batch(B, s, a, ln, r, sn, nl, e)
+            N.check(engine.lib, engine.handle,
+                    engine.lib.rec_gather_batch(engine.handle, C.byref(cols), n, C.c_void_p(perm[lo:hi].data_ptr()), B,
+                                                C.byref(out)), "rec_gather_batch")
+            yield s, a, r, sn, ln, nl, e
+
+
+class DeviceEvaluationDataset:
+    """Drop-in for `EvaluationDataset` (ikea/data_utils/replay_buffer.py:78-127): `(s, a, s_len)` only."""
+
+    def __init__(self, dir=None, state_name="state", action_name="action", state_len_name="true_state_len", arrays=None):
+        self.dir, self.state_name, self.action_name = dir, state_name, action_name
+        if arrays is None:
+            cols = _read_json_lines(dir, dict(states=state_name, actions=action_name, true_state_len=state_len_name))
+            arrays = dict(states=np.array(cols["states"].values.tolist()), actions=cols["actions"].to_numpy(),
+                          true_state_len=cols["true_state_len"].to_numpy())
+        self.states = np.asarray(arrays["states"])
+        self.actions = np.asarray(arrays["actions"])
+        self.true_state_len = np.asarray(arrays["true_state_len"])
+        self._dev = None
+
+    def __len__(self):
+        return len(self.actions)
+
+    def __getitem__(self, idx):
+        return (self.states[idx], self.actions[idx], self.true_state_len[idx])
+
+    def to_device(self, device):
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dtype=torch.int64).to(device).contiguous()
+        self._dev = (t(self.states), t(self.actions), t(self.true_state_len))
+        return self
+
+    def batches(self, batch_size):
+        """Sequential `(s, a, s_len)` device batches (views of the resident columns: evaluation never shuffles)."""
+        if self._dev is None:
+            raise RuntimeError("call to_device(device) first")
+        s, a, ln = self._dev
+        for lo in range(0, len(self), batch_size):
+            yield s[lo:lo + batch_size], a[lo:lo + batch_size], ln[lo:lo + batch_size]

@@ -222,6 +222,13 @@ int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const float *dx_
  * every field), and the inverse for the gathered [n_ranks][rec_packed_batch_bytes] buffer -> field arrays of
  * n_ranks*B_local rows (caller-owned; out->B is ignored). */
 int64_t rec_packed_batch_bytes(const rec_engine *e, int B);
+/* Device-resident replay buffer (replaces ReplayBuffer.__getitem__ + the DataLoader's default collate,
+ * ikea/data_utils/replay_buffer.py:65-74 and ikea/training/trainSQN.py's `for batch in train_loader`): `columns` holds
+ * the base pointers of the WHOLE buffer in HBM (n_rows rows; columns->B is ignored), `idx` [B] int64 device row
+ * numbers (one slice of the epoch's permutation).  Row idx[b] of every non-NULL column -> row b of `out`
+ * (device arrays of B rows, caller-owned).  Asynchronous on the engine's stream; indices are clamped to the buffer. */
+int rec_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B,
+                     const rec_batch *out);
 int rec_pack_batch(rec_engine *e, const rec_batch *b, void *packed_out);
 int rec_unpack_batch(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *out);
 

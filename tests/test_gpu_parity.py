@@ -636,3 +636,40 @@ def test_bidir_dropout_device_rng_is_deterministic_and_active(pkg):
     a1, a2, b0 = run(0.5, 118), run(0.5, 118), run(0.0, 118)
     assert a1 == a2
     assert all(abs(x - y) > 1e-6 for x, y in zip(a1[1:], b0[1:]))   # step 0 losses may coincide only by accident
+
+
+# ------------------------------------------------------------------------ device-resident replay buffer
+def test_device_replay_buffer_batches_equal_dataloader_and_train_identically(pkg):
+    """rec_gather_batch batches are bit-identical to DataLoader(shuffle=True) batches of the same
+    seeded epoch (ragged last batch included), and training from them reproduces the host-entry losses bit for bit."""
+    from torch.utils.data import DataLoader
+    V, L, B = 500, 10, 48
+    rows = _syn().make_replay_rows(5 * B + 7, V, L, seed=12)
+    arrays = dict(states=rows["state"], actions=rows["action"], reward=rows["r_act"], next_states=rows["next_state"],
+                  true_state_len=rows["true_state_len"], true_next_state_len=rows["true_next_state_len"],
+                  is_end=rows["is_end"])
+    buf = pkg.DeviceReplayBuffer.from_arrays(**arrays).to_device(DEV)
+    assert buf.bytes_on_device() > 0
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=V, state_size=L, action_dim=V, gamma=0.5, gru_layers=1)
+    t_dev = pkg.SQN_trainer(device=DEV, **kw)
+    t_host = pkg.SQN_trainer(device=DEV, **kw)
+    t_host.DQN_1.load_state_dict(t_dev.DQN_1.state_dict()); t_host.DQN_2.load_state_dict(t_dev.DQN_2.state_dict())
+    t_dev.send_to_device(); t_host.send_to_device()
+    eng = t_dev._ready(B)
+    loader = DataLoader(buf, batch_size=B, shuffle=True, generator=torch.Generator().manual_seed(5))
+    dev_iter = buf.batches(eng, B, shuffle=True, generator=torch.Generator().manual_seed(5))
+    rng = synced_random()
+    n_batches = 0
+    for host_b, dev_b in zip(loader, dev_iter):
+        s, a, r, sn, ln, nl, e = host_b
+        ds, da, dr, dsn, dln, dnl, de = dev_b
+        assert torch.equal(ds.cpu(), s) and torch.equal(dsn.cpu(), sn) and torch.equal(da.cpu(), a)
+        assert torch.equal(dln.cpu(), ln) and torch.equal(dnl.cpu(), nl)
+        assert torch.equal(dr.cpu(), r.to(torch.float32)) and torch.equal(de.cpu().bool(), e.bool())
+        rng.replay(); want = t_host.train_step(s, a, r, sn, ln, nl, e)
+        rng.replay(); got = t_dev.train_step_async(ds, da, dr, dsn, dln, dnl, de).cpu().tolist()
+        rng.advance()
+        assert list(want) == got
+        n_batches += 1
+    assert n_batches == 6  # 5 full batches + the ragged one

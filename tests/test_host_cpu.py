@@ -167,3 +167,54 @@ def test_synthetic_rows_follow_the_replay_buffer_contract(pkg):
     a1 = synthetic.make_replay_rows(50, 100, 6, seed=1)
     a2 = synthetic.make_replay_rows(50, 100, 6, seed=1)
     assert all(np.array_equal(a1[k], a2[k]) for k in a1)
+
+
+def _replay_arrays(n=37, L=6, N=50, seed=4):
+    from ikea_recommender_system_b200 import synthetic
+    rows = synthetic.make_replay_rows(n, N, L, seed=seed)
+    return dict(states=rows["state"], actions=rows["action"], reward=rows["r_act"], next_states=rows["next_state"],
+                true_state_len=rows["true_state_len"], true_next_state_len=rows["true_next_state_len"],
+                is_end=rows["is_end"]), rows
+
+
+def test_device_replay_buffer_follows_the_reference_dataset_protocol(pkg, tmp_path):
+    """Host side of SURVEY 8f N2: same tuple order as ReplayBuffer.__getitem__ (ikea/data_utils/replay_buffer.py:65-74),
+    same JSON-lines reader, and an epoch order identical to DataLoader(shuffle=True) with the same generator."""
+    import pandas as pd
+    from torch.utils.data import DataLoader
+    arrays, rows = _replay_arrays()
+    buf = pkg.DeviceReplayBuffer.from_arrays(**arrays)
+    n = len(buf)
+    assert n == len(rows["action"])
+    item = buf[5]
+    assert len(item) == 7
+    for got, key in zip(item, ("state", "action", "r_act", "next_state", "true_state_len", "true_next_state_len", "is_end")):
+        assert np.array_equal(np.asarray(got), np.asarray(rows[key][5]))
+    # JSON-lines file in the reference's format
+    df = pd.DataFrame({k: (list(map(list, v)) if np.asarray(v).ndim == 2 else list(np.asarray(v).tolist())) for k, v in rows.items()})
+    path = tmp_path / "replay.jsonl"
+    df.to_json(path, orient="records", lines=True)
+    buf2 = pkg.DeviceReplayBuffer(str(path))
+    for c in pkg.DeviceReplayBuffer.COLUMNS:
+        assert np.array_equal(np.asarray(getattr(buf2, c)).astype(np.float32), np.asarray(getattr(buf, c)).astype(np.float32)), c
+    # epoch order == RandomSampler's; batch slices == BatchSampler's
+    g1, g2 = torch.Generator().manual_seed(11), torch.Generator().manual_seed(11)
+    perm = pkg.DeviceReplayBuffer.epoch_permutation(n, True, g1)
+    loader = DataLoader(buf, batch_size=8, shuffle=True, generator=g2)
+    seen = torch.cat([b[1] for b in loader])  # actions in visiting order
+    assert torch.equal(seen, torch.as_tensor(arrays["actions"])[perm])
+    torch.manual_seed(77)  # the reference's scripts pass no generator: global RNG
+    perm_g = pkg.DeviceReplayBuffer.epoch_permutation(n, True)
+    torch.manual_seed(77)
+    seen_g = torch.cat([b[1] for b in DataLoader(buf, batch_size=8, shuffle=True)])
+    assert torch.equal(seen_g, torch.as_tensor(arrays["actions"])[perm_g])
+    assert pkg.DeviceReplayBuffer.batch_bounds(n, 8) == [(lo, min(lo + 8, n)) for lo in range(0, n, 8)]
+    assert pkg.DeviceReplayBuffer.batch_bounds(n, 8, drop_last=True)[-1] == (24, 32)
+    assert torch.equal(pkg.DeviceReplayBuffer.epoch_permutation(5, False), torch.arange(5))
+    with pytest.raises(RuntimeError):
+        buf.to_device("cpu")
+    with pytest.raises(RuntimeError):
+        next(buf.batches(None, 8))
+    ev = pkg.DeviceEvaluationDataset(arrays=dict(states=arrays["states"], actions=arrays["actions"],
+                                                 true_state_len=arrays["true_state_len"]))
+    assert len(ev) == n and len(ev[3]) == 3
