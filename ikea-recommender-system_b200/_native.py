@@ -93,6 +93,7 @@ SYMBOLS = {
     "rec_dp_apply": (C.c_int, [_P, _P, _P]),
     "rec_packed_batch_bytes": (C.c_int64, [_P, C.c_int]),
     "rec_gather_batch": (C.c_int, [_P, C.POINTER(RecBatch), C.c_int64, _P, C.c_int, C.POINTER(RecBatch)]),
+    "rec_build_replay_rows": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(RecBatch)]),
     "rec_pack_batch": (C.c_int, [_P, C.POINTER(RecBatch), _P]),
     "rec_unpack_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(RecBatch)]),
     "rec_eval_batch": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.POINTER(RecEvalOpts),

@@ -14,6 +14,8 @@ int launch_eval_metrics(rec_engine *e, const rec_batch *b, const rec_eval_opts *
 size_t head_bwd_smem_bytes(int D);
 int launch_pack_batch(rec_engine *e, const rec_batch *b, uint8_t *out);
 int launch_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B, const rec_batch *out);
+int launch_build_rows(rec_engine *e, const int64_t *off, int64_t n_sessions, const int64_t *items, const float *rewards,
+                      int64_t n, int64_t pad_id, int pad_end, const rec_batch *out);
 int launch_unpack_batch(rec_engine *e, const uint8_t *gathered, int G, int Bl, size_t stride, const rec_batch *out);
 
 static char g_err[512] = "";
@@ -1014,6 +1016,17 @@ extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_
 }
 
 // ---- packed batches for the input all-gather of sharded runs ----------------------------------------------
+extern "C" int rec_build_replay_rows(rec_engine *e, const int64_t *session_offsets, int64_t n_sessions, const int64_t *items,
+                                     const float *rewards, int64_t n_events, int64_t pad_id, int pad_pos_end,
+                                     const rec_batch *out) {
+  if (!e) return REC_EINVAL;
+  if (!session_offsets || !items || !out || n_sessions < 1 || n_events < 1)
+    REC_FAIL(e, REC_EINVAL, "rec_build_replay_rows: null argument or empty log");
+  if (!out->s || !out->s_next || !out->a || !out->true_len || !out->true_next_len || !out->is_end)
+    REC_FAIL(e, REC_EINVAL, "rec_build_replay_rows: every output column except r is mandatory");
+  return launch_build_rows(e, session_offsets, n_sessions, items, rewards, n_events, pad_id, pad_pos_end ? 1 : 0, out);
+}
+
 extern "C" int rec_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B,
                                 const rec_batch *out) {
   if (!e) return REC_EINVAL;

@@ -301,6 +301,60 @@ int launch_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows,
   return REC_OK;
 }
 
+// Replay-buffer construction from a raw event log (recommenders/data_utils/preprocessing.py:5-29,143-170,199-268):
+// one row per event; thread (row, t) finds the row's session by binary search in the CSR offsets and writes element t
+// of the padded sliding windows `state` (the <= L items before the event) and `next_state` (... including it).
+__global__ void build_rows_kernel(const int64_t *__restrict__ off, int64_t n_sessions, const int64_t *__restrict__ items,
+                                  const float *__restrict__ rewards, int64_t n, int L, int64_t pad_id, int pad_end,
+                                  int64_t *__restrict__ o_s, int64_t *__restrict__ o_sn, int64_t *__restrict__ o_a,
+                                  int64_t *__restrict__ o_len, int64_t *__restrict__ o_nlen, float *__restrict__ o_r,
+                                  uint8_t *__restrict__ o_end) {
+  const int64_t total = n * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / L;
+    const int t = (int)(i - row * L);
+    int64_t lo = 0, hi = n_sessions;  // off[lo] <= row < off[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (off[mid] <= row) lo = mid; else hi = mid;
+    }
+    const int64_t start = off[lo], stop = off[lo + 1];
+    const int64_t nb = row - start;  // n_items_bef
+    {
+      const int64_t cnt = nb < L ? nb : L, first = start + nb - cnt, padn = L - cnt;
+      int64_t v = pad_id;
+      if (pad_end) { if (t < cnt) v = items[first + t]; }
+      else if (t >= padn) v = items[first + t - padn];
+      o_s[i] = v;
+    }
+    {
+      const int64_t cnt = nb + 1 < L ? nb + 1 : L, first = start + nb + 1 - cnt, padn = L - cnt;
+      int64_t v = pad_id;
+      if (pad_end) { if (t < cnt) v = items[first + t]; }
+      else if (t >= padn) v = items[first + t - padn];
+      o_sn[i] = v;
+    }
+    if (t == 0) {
+      o_a[row] = items[row];
+      o_len[row] = nb < 1 ? 1 : (nb > L ? L : nb);
+      o_nlen[row] = nb + 1 > L ? L : nb + 1;
+      o_end[row] = row == stop - 1 ? 1 : 0;
+      if (o_r) o_r[row] = rewards ? rewards[row] : 0.f;
+    }
+  }
+}
+int launch_build_rows(rec_engine *e, const int64_t *off, int64_t n_sessions, const int64_t *items, const float *rewards,
+                      int64_t n, int64_t pad_id, int pad_end, const rec_batch *out) {
+  const int L = e->cfg.state_size;
+  const int64_t total = n * L;
+  const int blocks = (int)(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+  build_rows_kernel<<<blocks, 256, 0, e->stream>>>(off, n_sessions, items, rewards, n, L, pad_id, pad_end, (int64_t *)out->s,
+                                                  (int64_t *)out->s_next, (int64_t *)out->a, (int64_t *)out->true_len,
+                                                  (int64_t *)out->true_next_len, (float *)out->r, (uint8_t *)out->is_end);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
 int launch_pack_batch(rec_engine *e, const rec_batch *b, uint8_t *out) {
   const int n = b->B * (2 * e->cfg.state_size + 5);
   pack_batch_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(*b, e->cfg.state_size, out);

@@ -55,15 +55,63 @@ class DeviceReplayBuffer:
             raise ValueError("replay buffer columns disagree in length / shape")
         self._dev = None
         self._engine = None
+        self._n, self._L = n, int(self.states.shape[1])
 
     @classmethod
     def from_arrays(cls, states, actions, reward, next_states, true_state_len, true_next_state_len, is_end):
         return cls(arrays=dict(states=states, actions=actions, reward=reward, next_states=next_states,
                                true_state_len=true_state_len, true_next_state_len=true_next_state_len, is_end=is_end))
 
+    @classmethod
+    def from_event_log(cls, engine, session_ids, item_ids, pad_id, pad_pos="end", rewards=None):
+        """Build the buffer ON THE DEVICE from a raw event log sorted by session: what
+        `preprocess_train_data_incl_act_rew` (recommenders/data_utils/preprocessing.py:199-268) computes with a pandas
+        groupby-apply per session, as one launch of `rec_build_replay_rows`.  `engine` supplies state_size, the device
+        and the stream.  The host only derives the CSR session offsets (one vectorised numpy pass)."""
+        sid = np.asarray(session_ids)
+        n = len(sid)
+        if n == 0:
+            raise ValueError("empty event log")
+        starts = np.flatnonzero(np.concatenate(([True], sid[1:] != sid[:-1])))
+        off = np.concatenate((starts, [n])).astype(np.int64)
+        dev, L = engine.device, int(engine.cfg["state_size"])
+        d_off = torch.from_numpy(off).to(dev)
+        d_items = torch.as_tensor(np.ascontiguousarray(item_ids)).to(torch.int64).to(dev)
+        d_rew = None if rewards is None else torch.as_tensor(np.ascontiguousarray(rewards)).to(torch.float32).to(dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        cols = dict(s=torch.empty(n, L, **i64), a=torch.empty(n, **i64), r=torch.zeros(n, dtype=torch.float32, device=dev),
+                    sn=torch.empty(n, L, **i64), ln=torch.empty(n, **i64), nl=torch.empty(n, **i64),
+                    e=torch.empty(n, dtype=torch.uint8, device=dev))
+        out = engine._batch(n, cols["s"], cols["a"], cols["ln"], cols["r"], cols["sn"], cols["nl"], cols["e"])
+        N.check(engine.lib, engine.handle,
+                engine.lib.rec_build_replay_rows(engine.handle, C.c_void_p(d_off.data_ptr()), len(off) - 1,
+                                                 C.c_void_p(d_items.data_ptr()),
+                                                 C.c_void_p(d_rew.data_ptr() if d_rew is not None else 0), n, int(pad_id),
+                                                 1 if pad_pos == "end" else 0, C.byref(out)), "rec_build_replay_rows")
+        torch.cuda.synchronize(dev)
+        self = cls.__new__(cls)
+        self.dir = None
+        self._dev, self._engine = cols, engine
+        self._n, self._L = n, L
+        return self
+
+    def _host(self, name):
+        """Host mirror of a column of a device-built buffer (lazy; the training path never needs it)."""
+        key = dict(states="s", actions="a", reward="r", next_states="sn", true_state_len="ln",
+                   true_next_state_len="nl", is_end="e")[name]
+        v = self._dev[key].cpu().numpy()
+        return v.astype(bool) if name == "is_end" else v
+
+    def __getattr__(self, name):
+        if name in DeviceReplayBuffer.COLUMNS and "_dev" in self.__dict__ and self.__dict__["_dev"] is not None:
+            v = self._host(name)
+            self.__dict__[name] = v
+            return v
+        raise AttributeError(name)
+
     # ---- the reference's Dataset protocol ---------------------------------------------------------------
     def __len__(self):
-        return len(self.actions)
+        return self._n
 
     def __getitem__(self, idx):
         return (self.states[idx], self.actions[idx], self.reward[idx], self.next_states[idx], self.true_state_len[idx],
@@ -119,7 +167,7 @@ class DeviceReplayBuffer:
         if self._dev is None:
             raise RuntimeError("call to_device(device) first")
         d = self._dev
-        n, L, dev = len(self), int(self.states.shape[1]), d["s"].device
+        n, L, dev = self._n, self._L, d["s"].device
         perm = self.epoch_permutation(n, shuffle, generator).to(dev)
         cols = engine._batch(n, d["s"], d["a"], d["ln"], d["r"], d["sn"], d["nl"], d["e"])
         ring = []

@@ -229,6 +229,15 @@ int64_t rec_packed_batch_bytes(const rec_engine *e, int B);
  * (device arrays of B rows, caller-owned).  Asynchronous on the engine's stream; indices are clamped to the buffer. */
 int rec_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B,
                      const rec_batch *out);
+/* Replay-buffer construction on the device (replaces the pandas groupby-apply of
+ * recommenders/data_utils/preprocessing.py:199-268 with its helpers get_state :5-29 and get_next_state :143-170, shared
+ * by ikea/data_utils/preprocessing.py:385-489): an event log sorted by session, given as CSR `session_offsets`
+ * [n_sessions+1] (int64, device) over `items` [n_events] (+ optional per-event `rewards`), becomes one replay row per
+ * event in `out` (n_events rows, device, caller-owned): state / next_state padded to cfg.state_size with `pad_id` at the
+ * end (pad_pos_end != 0) or the beginning, action, true_len = clip(n_before, 1, L), true_next_len = min(n_before+1, L),
+ * is_end = last event of its session, r = rewards (0 when NULL; out->r may be NULL). */
+int rec_build_replay_rows(rec_engine *e, const int64_t *session_offsets, int64_t n_sessions, const int64_t *items,
+                          const float *rewards, int64_t n_events, int64_t pad_id, int pad_pos_end, const rec_batch *out);
 int rec_pack_batch(rec_engine *e, const rec_batch *b, void *packed_out);
 int rec_unpack_batch(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *out);
 

@@ -673,3 +673,36 @@ def test_device_replay_buffer_batches_equal_dataloader_and_train_identically(pkg
         assert list(want) == got
         n_batches += 1
     assert n_batches == 6  # 5 full batches + the ragged one
+
+
+@pytest.mark.parametrize("pad_pos", ["end", "beg"])
+def test_replay_rows_built_on_device_equal_the_reference_preprocessing(pkg, pad_pos):
+    """rec_build_replay_rows vs (a) the golden output of the real preprocess_train_data_incl_act_rew and
+    (b) the oracle on a larger seeded log (sessions of length 1 .. 3 L); integer work: bit-exact."""
+    import os
+    from oracle.preprocess import build_replay_rows
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_rr.npz"))
+    L, pad = int(g["state_len"]), int(g["pad_id"])
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=pad, state_size=L, action_dim=pad, gamma=0.5, gru_layers=1)
+    t = pkg.SQN_trainer(device=DEV, **kw); t.send_to_device()
+    eng = t._ready(32)
+    buf = pkg.DeviceReplayBuffer.from_event_log(eng, g["session_id"], g["item_id"], pad, pad_pos)
+    for col, key in (("states", "state"), ("next_states", "next_state"), ("actions", "action"),
+                     ("true_state_len", "true_state_len"), ("true_next_state_len", "true_next_state_len"), ("is_end", "is_end")):
+        assert np.array_equal(getattr(buf, col), g[f"{pad_pos}_{key}"]), col
+    rng = np.random.default_rng(9)
+    lens = rng.integers(1, 3 * L + 1, size=500)
+    sid = np.repeat(np.arange(500), lens)
+    items = rng.integers(0, pad, size=int(lens.sum()))
+    rew = rng.random(len(items)).astype(np.float32)
+    want = build_replay_rows(sid, items, L, pad, pad_pos, rewards=rew)
+    buf = pkg.DeviceReplayBuffer.from_event_log(eng, sid, items, pad, pad_pos, rewards=rew)
+    assert len(buf) == len(items)
+    for col, key in (("states", "state"), ("next_states", "next_state"), ("actions", "action"), ("reward", "r_act"),
+                     ("true_state_len", "true_state_len"), ("true_next_state_len", "true_next_state_len"), ("is_end", "is_end")):
+        assert np.array_equal(getattr(buf, col), want[key]), col
+    # and it feeds the trainer directly
+    b = next(buf.batches(eng, 32, shuffle=True, generator=torch.Generator().manual_seed(1)))
+    losses = t.train_step_async(*b).cpu()
+    assert torch.isfinite(losses).all()

@@ -179,3 +179,27 @@ def test_stable_topk_lowest_id_first():
     big = torch.zeros(2, 5000)
     big[0, 4000] = 1.0
     assert oracle.stable_topk(big, 4).tolist() == [[4000, 0, 1, 2], [0, 1, 2, 3]]
+
+
+def test_replay_row_construction_oracle_matches_reference_golden():
+    """oracle.preprocess.build_replay_rows vs the output of the real `preprocess_train_data_incl_act_rew`
+    (recommenders/data_utils/preprocessing.py:199-320) stored by oracle/make_golden_preprocess.py; plus the edge cases
+    of get_state / get_next_state (:5-29, :143-170): singleton sessions, sessions longer than state_len, both paddings."""
+    import os
+    from oracle.preprocess import build_replay_rows, session_offsets
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_rr.npz"))
+    L, pad = int(g["state_len"]), int(g["pad_id"])
+    for pos in ("end", "beg"):
+        mine = build_replay_rows(g["session_id"], g["item_id"], L, pad, pos)
+        for k in ("state", "next_state", "action", "true_state_len", "true_next_state_len", "is_end"):
+            assert np.array_equal(mine[k], g[f"{pos}_{k}"]), (pos, k)
+    off = session_offsets([7, 7, 7, 3, 9, 9])
+    assert off.tolist() == [0, 3, 4, 6]
+    r = build_replay_rows([1, 1, 1, 1, 2], [10, 11, 12, 13, 14], 2, 99, "end")
+    assert r["state"].tolist() == [[99, 99], [10, 99], [10, 11], [11, 12], [99, 99]]
+    assert r["next_state"].tolist() == [[10, 99], [10, 11], [11, 12], [12, 13], [14, 99]]
+    assert r["true_state_len"].tolist() == [1, 1, 2, 2, 1] and r["true_next_state_len"].tolist() == [1, 2, 2, 2, 1]
+    assert r["is_end"].tolist() == [False, False, False, True, True]
+    rb = build_replay_rows([1, 1, 1], [10, 11, 12], 3, 99, "beg")
+    assert rb["state"].tolist() == [[99, 99, 99], [99, 99, 10], [99, 10, 11]]
+    assert rb["next_state"].tolist() == [[99, 99, 10], [99, 10, 11], [10, 11, 12]]
