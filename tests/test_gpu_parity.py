@@ -2,6 +2,7 @@
 drop-in classes, against (a) the CPU oracle on the same seeded inputs and (b) the golden fixtures
 produced from the real reference.  Tolerances: indices / top-k ids exact; loss, Q-values, parameters
 after Adam within 1e-3 relative (north_star), atol 2e-5 for near-zero parameters."""
+import os
 import random
 
 import numpy as np
@@ -706,3 +707,74 @@ def test_replay_rows_built_on_device_equal_the_reference_preprocessing(pkg, pad_
     b = next(buf.batches(eng, 32, shuffle=True, generator=torch.Generator().manual_seed(1)))
     losses = t.train_step_async(*b).cpu()
     assert torch.isfinite(losses).all()
+
+
+def test_native_training_loop_matches_reference_style_loop(pkg, tmp_path):
+    """train_native (device buffer, device-side metric accumulation, evaluation points, best-model
+    checkpoint) against the reference-style loop of trainSQN.py:168-428 written with the drop-in pieces
+    (DataLoader -> train_step -> update_train_metrics -> evaluate): same losses, metrics and coverage."""
+    from torch.utils.data import DataLoader
+    from ikea_recommender_system_b200.recommenders.ikea.training.native_loop import eval_points
+    V, L, B, VB = 300, 8, 32, 64
+    rows = _syn().make_replay_rows(5 * B + 9, V, L, seed=21)
+    vrows = _syn().make_replay_rows(150, V, L, seed=22)
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    torch.manual_seed(4)
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16), freeze=True)
+    arrays = dict(states=rows["state"], actions=rows["action"], reward=rows["r_act"], next_states=rows["next_state"],
+                  true_state_len=rows["true_state_len"], true_next_state_len=rows["true_next_state_len"],
+                  is_end=rows["is_end"])
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=V, state_size=L, action_dim=V, gamma=0.5, gru_layers=1)
+    mk = dict(padding_pos="end", diversity_embedding=e_div, unpopular_actions_set=unpop)
+    ks = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1, topk_to_consider_nov=1,
+              topk_to_consider_cov=[1, 5, 10], novelty_rew_signal=1)
+    t_nat = pkg.SQN_trainer(device=DEV, **kw)
+    t_ref = pkg.SQN_trainer(device=DEV, **kw)
+    t_ref.DQN_1.load_state_dict(t_nat.DQN_1.state_dict()); t_ref.DQN_2.load_state_dict(t_nat.DQN_2.state_dict())
+    buf = pkg.DeviceReplayBuffer.from_arrays(**arrays).to_device(DEV)
+    val = pkg.DeviceEvaluationDataset(arrays=dict(states=vrows["state"], actions=vrows["action"],
+                                                  true_state_len=vrows["true_state_len"])).to_device(DEV)
+    eval_at = (0.5, 1.0)
+    rng = synced_random()
+    rng.replay()
+    hist = pkg.train_native(t_nat, buf, val, epochs=1, batch_size=B, val_batch_size=VB, eval_at=eval_at,
+                            generator=torch.Generator().manual_seed(3), out_dir=str(tmp_path), **mk)
+    # reference-style loop with the drop-in pieces
+    rng.replay()
+    t_ref.send_to_device()
+    loader = DataLoader(buf, batch_size=B, shuffle=True, generator=torch.Generator().manual_seed(3))
+    points = eval_points(len(loader), eval_at)
+    val_loader = [(torch.from_numpy(vrows["state"][lo:lo + VB]), torch.from_numpy(vrows["action"][lo:lo + VB]),
+                   torch.from_numpy(vrows["true_state_len"][lo:lo + VB])) for lo in range(0, 150, VB)]
+    tot = np.zeros(2); hr = np.zeros(3); nd = np.zeros(3); reps = np.zeros(3); n = 0; div = 0.0; nov = 0.0
+    cov = {k: set() for k in (1, 5, 10)}
+    want = []
+    for i, (s, a, r, sn, ln, nl, e) in enumerate(loader):
+        t_ref.set_train()
+        sup, q = t_ref.train_step(s, a, r, sn, ln, nl, e)
+        tot += (sup, q)
+        h, d, cov, dv, nv, rp = pkg.update_train_metrics(s=s, a=a, s_len=ln, model=t_ref.DQN_1, device=DEV,
+                                                         actions_covered_topk_dict=cov, **mk, **ks)
+        hr += h; nd += d; reps += rp; n += len(a); div += float(dv); nov += float(nv)
+        if i + 1 in points:
+            v1 = pkg.evaluate(val_loader, t_ref.DQN_1, DEV, t_ref.cross_entropy_loss, **mk, **ks)
+            v2 = pkg.evaluate(val_loader, t_ref.DQN_2, DEV, t_ref.cross_entropy_loss, **mk, **ks)
+            want.append(dict(sup=tot[0] / (i + 1), q=tot[1] / (i + 1), hr=hr / n, ndcg=nd / n, reps=reps / n, div=div / n,
+                             nov=nov / n, cov={k: len(c) / V for k, c in cov.items()}, v1=v1, v2=v2))
+    assert len(hist) == len(want) == 2
+    for got, w in zip(hist, want):
+        assert_close([got["train_sup_loss"], got["train_q_loss"]], [w["sup"], w["q"]], rtol=1e-6, atol=1e-7, what="train losses")
+        assert np.allclose(got["train_hr"], w["hr"]) and np.allclose(got["train_ndcg"], w["ndcg"])
+        assert np.allclose(got["train_reps"], w["reps"])
+        assert abs(got["train_div_rew"] - w["div"]) < 1e-5 and abs(got["train_nov_rew"] - w["nov"]) < 1e-6
+        for k in (1, 5, 10):
+            assert abs(got["train_cov"][k][1] - w["cov"][k]) < 1e-12
+        for sfx, v in (("", w["v1"]), ("_2", w["v2"])):
+            assert abs(got[f"val_loss{sfx}"] - float(v[0])) < 1e-6
+            assert np.array_equal(got[f"val_hr{sfx}"], v[1]) and np.array_equal(got[f"val_ndcg{sfx}"], v[2])
+            assert got[f"val_cov{sfx}"] == v[3]
+    ck = torch.load(os.path.join(str(tmp_path), "best_model.pt"))
+    assert set(ck) == {"epoch", "model_idx", "hidden_dim", "item_num", "action_dim", "state_size", "embedding_dim",
+                       "model_state_dict"}
+    assert "embedding.weight" in ck["model_state_dict"]
