@@ -521,6 +521,7 @@ static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hp
   int rc;
   const int B = b->B;
   const bool drop = hp->dropout_p > 0.f;
+  e->hpack_ready = false;
   if ((rc = launch_gru_forward(e, 0, b->s, b->true_len, B, e->h_state[0], true))) return rc;
   if (drop && (rc = launch_dropout(e, 0, e->h_state[0], nullptr, B, hp, false))) return rc;  // heads see the dropped state
   HeadStatsArgs a = {};
@@ -586,6 +587,7 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
                        float step_size, float bc2_sqrt) {
   int rc;
   const int B = b->B, boot = 1 - main_net, n_q = e->cfg.n_heads - 1;
+  e->hpack_ready = false;
   {  // ordering of the token positions for the embedding backward: needs only the batch
     SideScope side(e, 1);
     if ((rc = launch_embedding_update(e, main_net, b->s, b->true_len, B, step_size, bc2_sqrt, hp, 1))) return rc;
@@ -598,6 +600,10 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
     float *hh[3] = {e->h_state[0], e->h_state[1], e->h_state[2]};
     const bool sv[3] = {true, false, false};
     if ((rc = launch_gru_forward_multi(e, 3, nets, ss, ll, hh, sv, B))) return rc;
+  }
+  if (tc_bwd_supported(e, B)) {  // operand image of the supervised-head backward: only needs the forward pass
+    SideScope side(e, 0);
+    if ((rc = launch_h_prepack_early(e, e->h_state[0], B))) return rc;
   }
   // supervised head statistics (+ top-k of the supervised logits for the SMORL rewards)
   HeadStatsArgs a = {};

@@ -72,6 +72,7 @@ struct rec_engine {
   float *q_bgrad;        // [maxB][n_q]
   int32_t *q_slot;       // [Vloc] leader batch row of each action or -1
   uint8_t *hpack;        // [ceil(maxB/128)][hi|lo][16 KB] packed bf16 image of h for the tensor-core backward
+  bool hpack_ready;      // the packed image of the current supervised states was already produced (early, off the critical path)
   float *summary;        // [maxB][part_stride] per-row record of this shard
   float *qpack;          // [2][maxB][3] Q(s,a) | Q_boot(s',a*) contributions of this shard
   bool timing;
@@ -237,6 +238,7 @@ int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out
 bool tc_bwd_supported(const rec_engine *e, int B);
 int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                             float bc2_sqrt, const rec_train_hparams *hp, float inv_B, int *n_slices);
+int launch_h_prepack_early(rec_engine *e, const float *h, int B);
 int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats,
                       bool has_argmax, float *summary = nullptr);
 int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld);

@@ -1486,6 +1486,16 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
 
 bool tc_bwd_supported(const rec_engine *e, int B) { (void)B; return tc_heads_supported(e); }
 
+// The packed bf16 hi/lo image of the supervised states only needs the GRU forward: the Q step produces it on a side
+// stream right after the forward pass instead of in front of the backward kernel (which sits on the critical path).
+int launch_h_prepack_early(rec_engine *e, const float *h, int B) {
+  if (!tc_heads_supported(e)) return REC_OK;
+  h_prepack_kernel<<<cdiv(B, 128), 256, 0, e->stream>>>(h, B, e->hpack);
+  REC_LAUNCH_CHECK(e);
+  e->hpack_ready = true;
+  return REC_OK;
+}
+
 int tc_bwd_slices(const rec_engine *e) {
   const int n_tiles = cdiv(e->Vloc, 128);
   int n_cta = e->sm_count < n_tiles ? e->sm_count : n_tiles;
@@ -1506,8 +1516,11 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
     REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  h_prepack_kernel<<<cdiv(B, 128), 256, 0, e->stream>>>(h, B, e->hpack);
-  REC_LAUNCH_CHECK(e);
+  if (!e->hpack_ready) {
+    h_prepack_kernel<<<cdiv(B, 128), 256, 0, e->stream>>>(h, B, e->hpack);
+    REC_LAUNCH_CHECK(e);
+  }
+  e->hpack_ready = false;
   static int v1 = -1;
   if (v1 < 0) { const char *v = getenv("REC_BWD_V1"); v1 = v ? atoi(v) : 0; }
   if (!v1) {  // warp-specialised variant (dh resident in TMEM when B <= 256)
