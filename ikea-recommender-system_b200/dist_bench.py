@@ -101,7 +101,7 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
                         "h2d_bytes_per_step": int(trainer._stager.h2d_bytes), "d2h_bytes_per_step": 8,
                         "ms_per_step": 1e3 * e2e_s / K},
                 "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "head_bwd_adam_tc_kernel (supervised head, this rank's vocabulary shard)",
+                "roofline": {"bound": "hbm", "kernel": "head_bwd_adam_tc2_kernel (supervised head, this rank's vocabulary shard, global batch in chunks of 256)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": shard_bytes,
                              "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / K)},

@@ -153,12 +153,23 @@ class DeviceReplayBuffer:
         return torch.randperm(n, generator=generator)
 
     @staticmethod
-    def batch_bounds(n, batch_size, drop_last=False):
-        """[(lo, hi)) slices of the epoch order, like `BatchSampler`."""
-        stop = n - n % batch_size if drop_last else n
-        return [(lo, min(lo + batch_size, stop)) for lo in range(0, stop, batch_size)]
+    def batch_bounds(n, batch_size, drop_last=False, rank=0, world=1):
+        """[(lo, hi)) slices of the epoch order, like `BatchSampler`.
 
-    def batches(self, engine, batch_size, shuffle=True, generator=None, drop_last=False, slots=4):
+        world > 1 (vocabulary-sharded multi-GPU runs: every rank contributes `batch_size` local sessions to a global
+        batch of `world * batch_size`): rank r gets the r-th `batch_size` slice of every GLOBAL batch, so that the
+        concatenation over ranks is exactly the single-process batch of size `world * batch_size` -- the G-GPU run
+        trains on the same global batches, in the same order, as a 1-GPU run with the global batch size.  Ragged
+        global batches are dropped (every rank must take the same number of steps with the same local size)."""
+        if world == 1:
+            stop = n - n % batch_size if drop_last else n
+            return [(lo, min(lo + batch_size, stop)) for lo in range(0, stop, batch_size)]
+        if not 0 <= rank < world:
+            raise ValueError(f"rank {rank} outside world {world}")
+        g = batch_size * world
+        return [(lo + rank * batch_size, lo + (rank + 1) * batch_size) for lo in range(0, n - n % g, g)]
+
+    def batches(self, engine, batch_size, shuffle=True, generator=None, drop_last=False, slots=4, rank=0, world=1):
         """Yield `(s, a, r, s_next, true_len, true_next_len, is_end)` device tensors for one epoch.
 
         `engine`: the trainer's native engine (`trainer._ready(batch_size)`); the gather runs on its stream, so a
@@ -177,7 +188,8 @@ class DeviceReplayBuffer:
                          torch.empty(batch_size, dtype=torch.float32, device=dev), torch.empty(batch_size, L, **i64),
                          torch.empty(batch_size, **i64), torch.empty(batch_size, **i64),
                          torch.empty(batch_size, dtype=torch.uint8, device=dev)))
-        for k, (lo, hi) in enumerate(self.batch_bounds(n, batch_size, drop_last)):
+        # (world > 1: every rank must pass a generator with the same seed -- the permutation is replicated, not sent)
+        for k, (lo, hi) in enumerate(self.batch_bounds(n, batch_size, drop_last, rank, world)):
             B = hi - lo
             s, a, r, sn, ln, nl, e = (x[:B] for x in ring[k % len(ring)])
             out = engine._batch(B, s, a, ln, r, sn, nl, e)

@@ -211,6 +211,16 @@ def test_device_replay_buffer_follows_the_reference_dataset_protocol(pkg, tmp_pa
     assert pkg.DeviceReplayBuffer.batch_bounds(n, 8) == [(lo, min(lo + 8, n)) for lo in range(0, n, 8)]
     assert pkg.DeviceReplayBuffer.batch_bounds(n, 8, drop_last=True)[-1] == (24, 32)
     assert torch.equal(pkg.DeviceReplayBuffer.epoch_permutation(5, False), torch.arange(5))
+    # multi-GPU slicing: the ranks' local batches concatenate to the single-process global batches (ragged tail dropped)
+    G, Bl = 3, 4
+    per_rank = [pkg.DeviceReplayBuffer.batch_bounds(n, Bl, rank=r, world=G) for r in range(G)]
+    assert len({len(b) for b in per_rank}) == 1 and len(per_rank[0]) == n // (G * Bl)
+    glob = pkg.DeviceReplayBuffer.batch_bounds(n, G * Bl, drop_last=True)
+    for step, (lo, hi) in enumerate(glob):
+        cat = [i for r in range(G) for i in range(*per_rank[r][step])]
+        assert cat == list(range(lo, hi))
+    with pytest.raises(ValueError):
+        pkg.DeviceReplayBuffer.batch_bounds(n, Bl, rank=3, world=3)
     with pytest.raises(RuntimeError):
         buf.to_device("cpu")
     with pytest.raises(RuntimeError):
