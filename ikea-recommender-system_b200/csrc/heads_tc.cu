@@ -708,17 +708,15 @@ int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out
 }
 
 // ================================================================================================
-// head_bwd_adam_tc_kernel -- backward + Adam of the supervised head on the tensor cores (D = 64, B <= 256).
-// One persistent CTA per SM walks vocabulary tiles of 128 rows.  Per tile, with W, m, v read ONCE:
-//   for each 128-session block bb:
-//     L   = h[bb] . W^T                      tcgen05.mma  K-major x K-major            -> TMEM[0,128)
+// Supervised head backward + Adam on the tensor cores (D = 64).  Per 128-row vocabulary tile, with W, m, v read ONCE:
+//   for each 128-session block bb (batches beyond 256 sessions: chunks of two blocks):
+//     L   = h[bb] . W^T                      tcgen05.mma  K-major x K-major            -> TMEM[0,128) / [128,256)
 //     dl  = (exp(L + b - lse) - onehot)/B    epilogue: TMEM -> regs -> bf16 hi/lo -> smem (swizzled)
-//     dW += dl^T . h[bb]                     tcgen05.mma  MN-major x MN-major          -> TMEM[128,192)
-//     db += dl^T . 1                         tcgen05.mma  MN-major x K-major (ones)    -> TMEM[192,208)
-//     dh[bb] += dl . W                       tcgen05.mma  K-major x MN-major           -> TMEM[256+64bb, ...)
-//   dW, db: TMEM -> smem (fp32) -> Adam in the coalesced layout the weights were loaded in (the fp32
-//   weights of the tile never left registers) -> W, m, v written once.
-// dh stays in TMEM across ALL tiles of the CTA and is written once at the end (one slice per CTA).
+//     dW += dl^T . h[bb]                     tcgen05.mma  MN-major x MN-major          -> TMEM[256,320)
+//     db += dl^T . 1                         tcgen05.mma  MN-major x K-major (ones)    -> TMEM[320,336)
+//     dh[bb] += dl . W                       tcgen05.mma  K-major x MN-major           -> TMEM[384+64bb, ...)
+//   dW, db: TMEM -> registers / per-warp smem transpose -> Adam in coalesced 64-byte pieces -> W, m, v written once.
+// For B <= 256 dh stays in TMEM across ALL tiles of the CTA and is written once at the end (one slice per CTA).
 // The three operand roles of h, W and dl use the SAME shared-memory bytes (see tc.cuh).
 // ================================================================================================
 struct TcTrainPtrs {
@@ -738,339 +736,9 @@ __global__ void __launch_bounds__(256) h_prepack_kernel(const float *__restrict_
   stage_rows64(hi, lo, h, bb * 128, B, 1.f, tid);
 }
 
-#define BWD_THREADS 512
-// 104 registers x 512 threads leaves room for one 256-thread CTA of the streaming Adam kernel (48 registers)
-// on the same SM (__maxnreg__ cannot be combined with __launch_bounds__).
-__global__ void __maxnreg__(104) head_bwd_adam_tc_kernel(TcTrainPtrs hp, const uint8_t *__restrict__ hpack,
-                                                                          const int64_t *__restrict__ target,
-                                                                          const float *__restrict__ row_stats, int B, int Vloc,
-                                                                          int vocab_lo, int n_tiles, float inv_B,
-                                                                          float *__restrict__ dh_part, float b1, float b2,
-                                                                          float eps, float step_size, float inv_bc2_sqrt,
-                                                                          long long *__restrict__ trace,
-                                                                          const float *__restrict__ sc) {
-  if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
-  extern __shared__ uint8_t raw[];
-  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);  // 1024-aligned; offset arithmetic keeps the pointer provably shared (LDS/STS, not generic LD/ST)
-  int tr_n = 0;
-#define TRACE(tag) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_n < 120) { trace[2 * tr_n] = (tag); trace[2 * tr_n + 1] = clock64(); ++tr_n; } } while (0)
-  uint8_t *h_blk = sm;                 // chunk of 256 sessions: [bb][hi|lo] x BLK      (64 KB)
-  uint8_t *w_hi = sm + 4 * BLK, *w_lo = sm + 5 * BLK;            // (32 KB)
-  uint8_t *dl_hi = sm + 6 * BLK, *dl_lo = sm + 8 * BLK;          // each 2 blocks (v halves)  (64 KB)
-  float *w_stage = reinterpret_cast<float *>(sm + 10 * BLK);     // fp32 tile [128][64], TMA destination (32 KB)
-  uint8_t *ones = sm + 12 * BLK;                                  // 4 KB of bf16 1.0
-  float *bias_s = reinterpret_cast<float *>(ones + 4096);        // [128]
-  float *db_s = bias_s + 128;                                     // [128]
-  float *lse_s = db_s + 128;                                      // [256]
-  int *tgt_s = reinterpret_cast<int *>(lse_s + 256);             // [256] target column relative to vocab_lo
-  float *dws = reinterpret_cast<float *>(dl_hi);                 // alias: [128][68] fp32 after the MMAs of a tile
-  __shared__ uint64_t mbar[5];  // 0,1: logits(bb) ready, 2: W tile landed, 3: h chunk landed, 4: gradient MMAs done
-  __shared__ uint32_t tmem_base_s;
-  constexpr uint32_t T_L = 0 /* 2 x 128 */, T_DW = 256, T_DB = 320, T_DH = 384 /* 2 x 64 */;
-  constexpr int NT = BWD_THREADS;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter; column quarter (4 warps share a lane quarter)
-  const int n_chunks = (B + 255) / 256;
-  const bool resident = n_chunks == 1;  // dh stays in TMEM across all tiles of the CTA
-
-  if (tid == 0) {
-    for (int i = 0; i < 5; ++i) tc::mbar_init(&mbar[i], 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
-  for (int i = tid; i < 4096 / 4; i += NT) reinterpret_cast<uint32_t *>(ones)[i] = 0x3F803F80u;
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t s_h = tc::smem_u32(h_blk), s_wh = tc::smem_u32(w_hi), s_wl = tc::smem_u32(w_lo);
-  const uint32_t s_dh = tc::smem_u32(dl_hi), s_dl = tc::smem_u32(dl_lo), s_one = tc::smem_u32(ones);
-  uint32_t phL[2] = {0, 0}, phW = 0, phH = 0, phG = 0;
-  bool first_tile = true;
-
-  auto prefetch_w = [&](int t) {  // one thread: TMA bulk copy of the fp32 tile
-    const uint32_t bytes = (uint32_t)min(128, Vloc - t * 128) * 256u;
-    tc::mbar_expect_tx(&mbar[2], bytes);
-    tc::bulk_g2s(w_stage, hp.w + (int64_t)t * 128 * 64, bytes, &mbar[2]);
-  };
-  auto load_chunk = [&](int c) {  // one thread: packed h chunk (1 or 2 blocks of 32 KB)
-    const int nb = min(2, (B - c * 256 + 127) / 128);
-    tc::mbar_expect_tx(&mbar[3], (uint32_t)nb * 2 * BLK);
-    tc::bulk_g2s(h_blk, hpack + (size_t)c * 4 * BLK, (uint32_t)nb * 2 * BLK, &mbar[3]);
-  };
-  const uint64_t d_w_k_hi = tc::desc_kmajor(s_wh, 0), d_w_k_lo = tc::desc_kmajor(s_wl, 0);
-  auto issue_logits = [&](int bb) {
-    const uint32_t id = tc::instr_desc(128, 128, 0, 0);
-    const uint64_t d_h_hi = tc::desc_kmajor(s_h + bb * 2 * BLK, 0), d_h_lo = tc::desc_kmajor(s_h + bb * 2 * BLK + BLK, 0);
-    bool acc = false;
-#pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint64_t a = pass == 2 ? d_h_lo : d_h_hi, b = pass == 1 ? d_w_k_lo : d_w_k_hi;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tmem + T_L + bb * 128, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id, acc); acc = true; }
-    }
-    tc::mma_commit(&mbar[bb]);
-  };
-  // Gradient MMAs of one 128-session block.  The three accumulators are independent chains, so three
-  // different threads (lane 0 of warps 0, 1, 2) issue them concurrently; each commits to mbar[4] (count 3).
-  // Descriptors are built once; per MMA only the 14-bit start-address field advances.
-  const uint64_t d_dl_mn_hi = tc::desc_mnmajor(s_dh, 0, BLK), d_dl_mn_lo = tc::desc_mnmajor(s_dl, 0, BLK);
-  const uint64_t d_dl_k_hi = tc::desc_kmajor(s_dh, 0), d_dl_k_lo = tc::desc_kmajor(s_dl, 0);
-  const uint64_t d_w_mn_hi = tc::desc_mnmajor(s_wh, 0, BLK), d_w_mn_lo = tc::desc_mnmajor(s_wl, 0, BLK);
-  const uint64_t d_one = tc::desc_kmajor(s_one, 0);
-  auto issue_dW = [&](int bb, bool first_of_tile) {  // dW += dl^T . h[bb]  (A: dl MN-major, B: h MN-major, K = batch)
-    const uint32_t id = tc::instr_desc(128, 64, 1, 1);
-    const uint64_t d_h_hi = tc::desc_mnmajor(s_h + bb * 2 * BLK, 0, BLK), d_h_lo = tc::desc_mnmajor(s_h + bb * 2 * BLK + BLK, 0, BLK);
-    bool acc = !first_of_tile;
-#pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint64_t a = pass == 2 ? d_dl_mn_lo : d_dl_mn_hi, b = pass == 1 ? d_h_lo : d_h_hi;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { tc::mma_bf16(tmem + T_DW, a + (uint64_t)(k * 128), b + (uint64_t)(k * 128), id, acc); acc = true; }
-    }
-  };
-  auto issue_db = [&](bool first_of_tile) {  // db += dl^T . 1  (B: 16 rows of ones, K-major, two K blocks of 2 KB)
-    const uint32_t id = tc::instr_desc(128, 16, 1, 0);
-    bool acc = !first_of_tile;
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const uint64_t a = pass == 1 ? d_dl_mn_lo : d_dl_mn_hi;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        tc::mma_bf16(tmem + T_DB, a + (uint64_t)(k * 128), d_one + (uint64_t)((k >> 2) * 128 + (k & 3) * 2), id, acc);
-        acc = true;
-      }
-    }
-  };
-  auto issue_dh = [&](int bb, bool acc_dh) {  // dh[bb] += dl . W  (A: dl K-major (K = v, 2 blocks), B: W MN-major)
-    const uint32_t id = tc::instr_desc(128, 64, 0, 1);
-    bool acc = acc_dh;
-#pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint64_t a = pass == 2 ? d_dl_k_lo : d_dl_k_hi, b = pass == 1 ? d_w_mn_lo : d_w_mn_hi;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        tc::mma_bf16(tmem + T_DH + bb * 64, a + (uint64_t)((k >> 2) * (BLK >> 4) + (k & 3) * 2), b + (uint64_t)(k * 128), id, acc);
-        acc = true;
-      }
-    }
-  };
-
-  if (blockIdx.x < n_tiles && tid == 0) {
-    prefetch_w(blockIdx.x);
-    load_chunk(0);
-  }
-  int chunk_loaded = 0;
-
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int v0 = t * 128;
-    // ---- W tile: staged fp32 (TMA) -> registers (kept for Adam) -> bf16 hi/lo in smem ---------------
-    TRACE(1);
-    tc::mbar_wait(&mbar[2], phW);
-    phW ^= 1;
-    TRACE(2);
-    float4 pa[2], pb[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int c = tid + NT * i, row = c >> 3, c8 = c & 7;
-      pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      pb[i] = pa[i];
-      if (v0 + row < Vloc) {
-        const float4 *p = reinterpret_cast<const float4 *>(w_stage + row * 64 + c8 * 8);
-        pa[i] = p[0];
-        pb[i] = p[1];
-      }
-      tc::store_split8(w_hi, w_lo, row, c8, pa[i], pb[i]);
-    }
-    float bias_p = 0.f, bias_m = 0.f, bias_v = 0.f;
-    if (tid < 128 && v0 + tid < Vloc) { bias_p = hp.b[v0 + tid]; bias_m = hp.bm[v0 + tid]; bias_v = hp.bv[v0 + tid]; }
-    if (tid < 128) bias_s[tid] = bias_p;
-
-    for (int c = 0; c < n_chunks; ++c) {
-      const int r0 = c * 256, nbb = min(2, (B - r0 + 127) / 128);
-      if (chunk_loaded != c) {  // only when the batch spans several chunks (previous chunk's MMAs are complete)
-        if (tid == 0) load_chunk(c);
-        chunk_loaded = c;
-        tc::mbar_wait(&mbar[3], phH);
-        phH ^= 1;
-      } else if (first_tile && c == 0) {
-        tc::mbar_wait(&mbar[3], phH);
-        phH ^= 1;
-      }
-      if (tid < 256 && (!resident || first_tile)) {
-        const int row = r0 + tid;
-        lse_s[tid] = row < B ? row_stats[(int64_t)row * 8] : 0.f;
-        tgt_s[tid] = row < B ? (int)(target[row] - vocab_lo) : -1;
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();  // W operands (and staging reads), lse/tgt visible
-      tc::tc_fence_after();
-      TRACE(3);
-      if (tid == 0) {
-        if (c == 0 && t + (int)gridDim.x < n_tiles) prefetch_w(t + gridDim.x);  // staging is free: lands during this tile
-        for (int bb = 0; bb < nbb; ++bb) issue_logits(bb);  // both blocks' logits up front (separate TMEM tiles)
-      }
-      float4 m0[2], m1[2], u0[2], u1[2];
-      for (int bb = 0; bb < nbb; ++bb) {
-        TRACE(4);
-        tc::mbar_wait(&mbar[bb], phL[bb]);
-        phL[bb] ^= 1;
-        tc::tc_fence_after();
-        TRACE(5);
-        // ---- epilogue 1: dlogits of (row, 32 columns), computed in registers first ------------------
-        const int r = q * 32 + lane, rl = bb * 128 + r;
-        float l[32];
-        tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + T_L + (uint32_t)(bb * 128 + cq * 32), l);
-        tc::tmem_ld_wait();
-        {
-          const bool rv = r0 + rl < B;
-          const float lse = lse_s[rl];
-          const int tj = tgt_s[rl] - v0 - cq * 32;
-          const float *bg = bias_s + cq * 32;
-          const int nvalid = rv ? min(32, Vloc - v0 - cq * 32) : 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float d = (__expf(l[j] + bg[j] - lse) - (j == tj ? 1.f : 0.f)) * inv_B;
-            l[j] = j < nvalid ? d : 0.f;
-          }
-        }
-        TRACE(6);
-        if (bb > 0) {  // the dl buffer is still being read by the gradient MMAs of block bb-1
-          tc::mbar_wait(&mbar[4], phG);
-          phG ^= 1;
-        }
-        TRACE(7);
-        {
-          uint8_t *bh = dl_hi + (cq >> 1) * BLK, *bl = dl_lo + (cq >> 1) * BLK;
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8)
-            tc::store_split8(bh, bl, r, (cq & 1) * 4 + c8, make_float4(l[c8 * 8], l[c8 * 8 + 1], l[c8 * 8 + 2], l[c8 * 8 + 3]),
-                             make_float4(l[c8 * 8 + 4], l[c8 * 8 + 5], l[c8 * 8 + 6], l[c8 * 8 + 7]));
-        }
-        tc::fence_async_smem();
-        tc::tc_fence_before();
-        __syncthreads();
-        tc::tc_fence_after();
-        TRACE(8);
-        if (tid == 0) {
-          issue_dW(bb, c == 0 && bb == 0);
-          issue_db(c == 0 && bb == 0);
-          issue_dh(bb, resident && !first_tile);
-          tc::mma_commit(&mbar[4]);
-        }
-        TRACE(9);
-      }
-      tc::mbar_wait(&mbar[4], phG);  // gradient MMAs of the last block: the chunk is complete
-      phG ^= 1;
-      tc::tc_fence_after();
-      TRACE(10);
-      const bool last_chunk = c + 1 == n_chunks;
-      if (!resident) {
-        // dh of this (tile, chunk): TMEM -> this CTA's slice (first tile stores, later tiles add)
-        float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
-        for (int bb = 0; bb < nbb; ++bb) {
-          const int row = r0 + bb * 128 + q * 32 + lane;
-          float g[16];
-          tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + cq * 16), g);
-          tc::tmem_ld_wait();
-          if (row < B) {
-            float4 *dst = reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-              if (!first_tile) { float4 p = dst[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-              dst[j] = o;
-            }
-          }
-        }
-        tc::tc_fence_before();
-        __syncthreads();  // TMEM dh region, h chunk and lse/tgt smem are reused by the next chunk
-        tc::tc_fence_after();
-      }
-      if (!last_chunk) continue;
-      // ---- epilogue 2: dW (TMEM) -> smem fp32 [128][68]; db -> smem -------------------------------
-      {
-        const int r = q * 32 + lane;
-        float g[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DW + (uint32_t)(cq * 16), g);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4 *>(dws + r * 68 + cq * 16 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-        if (cq == 0) {
-          float d16[16];
-          tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DB, d16);
-          tc::tmem_ld_wait();
-          db_s[r] = d16[0];
-        }
-      }
-      tc::tc_fence_before();
-      __syncthreads();
-      tc::tc_fence_after();
-      TRACE(11);
-      // ---- Adam on the tile, in the layout the weights were loaded in -----------------------------
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int cc = tid + NT * i, row = cc >> 3, c8 = cc & 7;
-        if (v0 + row >= Vloc) continue;
-        const int64_t off = (int64_t)(v0 + row) * 64 + c8 * 8;
-        m0[i] = *reinterpret_cast<const float4 *>(hp.wm + off); m1[i] = *reinterpret_cast<const float4 *>(hp.wm + off + 4);
-        u0[i] = *reinterpret_cast<const float4 *>(hp.wv + off); u1[i] = *reinterpret_cast<const float4 *>(hp.wv + off + 4);
-        const float4 g0 = *reinterpret_cast<const float4 *>(dws + row * 68 + c8 * 8);
-        const float4 g1 = *reinterpret_cast<const float4 *>(dws + row * 68 + c8 * 8 + 4);
-        adam_f(pa[i].x, m0[i].x, u0[i].x, g0.x, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(pa[i].y, m0[i].y, u0[i].y, g0.y, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(pa[i].z, m0[i].z, u0[i].z, g0.z, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(pa[i].w, m0[i].w, u0[i].w, g0.w, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(pb[i].x, m1[i].x, u1[i].x, g1.x, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(pb[i].y, m1[i].y, u1[i].y, g1.y, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(pb[i].z, m1[i].z, u1[i].z, g1.z, b1, b2, eps, step_size, inv_bc2_sqrt);
-        adam_f(pb[i].w, m1[i].w, u1[i].w, g1.w, b1, b2, eps, step_size, inv_bc2_sqrt);
-        *reinterpret_cast<float4 *>(hp.w + off) = pa[i];     *reinterpret_cast<float4 *>(hp.w + off + 4) = pb[i];
-        *reinterpret_cast<float4 *>(hp.wm + off) = m0[i];    *reinterpret_cast<float4 *>(hp.wm + off + 4) = m1[i];
-        *reinterpret_cast<float4 *>(hp.wv + off) = u0[i];    *reinterpret_cast<float4 *>(hp.wv + off + 4) = u1[i];
-      }
-      if (tid < 128 && v0 + tid < Vloc) {
-        adam_f(bias_p, bias_m, bias_v, db_s[tid], b1, b2, eps, step_size, inv_bc2_sqrt);
-        hp.b[v0 + tid] = bias_p; hp.bm[v0 + tid] = bias_m; hp.bv[v0 + tid] = bias_v;
-      }
-      __syncthreads();  // dws (aliases dl), w smem and bias_s are rewritten by the next tile
-      TRACE(12);
-    }
-    first_tile = false;
-  }
-  // ---- resident dh of this CTA: TMEM -> its slice ---------------------------------------------------
-  if (resident) {
-    float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
-    const int nbb = (B + 127) / 128;
-    for (int bb = 0; bb < nbb; ++bb) {
-      const int row = bb * 128 + q * 32 + lane;
-      float g[16];
-      if (!first_tile) {
-        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + cq * 16), g);
-        tc::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) g[j] = 0.f;
-      }
-      if (row < B) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
 // ================================================================================================
-// head_bwd_adam_tc2_kernel -- the same computation for batches of at most 256 sessions (dh resident in TMEM),
-// warp-specialised into four roles that only meet at mbarriers:
+// head_bwd_adam_tc2_kernel -- warp-specialised into four roles that only meet at mbarriers (the first, single-role version
+// of this kernel -- every warp did every phase behind block barriers -- ran at 31 % of the HBM roofline at 1 M items):
 //   16 compute warps : wait W(t) staged -> convert to bf16 hi/lo -> arrive WREADY
 //                      wait L[bb] -> dlogits in registers (ONE ex2 per logit) -> (bb>0: wait G) -> smem -> arrive DL
 //                      wait G (the W/dl operands are free again)
@@ -1510,10 +1178,11 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   TcTrainPtrs t = {p.head_w[0], p.head_w_m[0], p.head_w_v[0], p.head_b[0], p.head_b_m[0], p.head_b_v[0]};
   const int n_tiles = cdiv(e->Vloc, 128);
   const int n_cta = tc_bwd_slices(e);
-  const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072 + 2048 + 8 * 32 * 20 * 4;  // (double-buffered lse/targets and the transpose staging belong to tc2 only)
+  // operands 12 x 16 KB, ones 4 KB, bias / double-buffered lse / targets 5 KB, Adam warps' transpose staging 20 KB
+  const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072 + 2048 + 8 * 32 * 20 * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   if (!e->hpack_ready) {
@@ -1521,25 +1190,10 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
     REC_LAUNCH_CHECK(e);
   }
   e->hpack_ready = false;
-  static int v1 = -1;
-  if (v1 < 0) { const char *v = getenv("REC_BWD_V1"); v1 = v ? atoi(v) : 0; }
-  if (!v1) {  // warp-specialised variant (dh resident in TMEM when B <= 256)
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr2_set = true;
-    }
-    head_bwd_adam_tc2_kernel<<<n_cta, BWD2_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo,
-                                                                      n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
-                                                                      step_size, 1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr,
-                                                                      e->d_sc);
-    REC_LAUNCH_CHECK(e);
-    *n_slices = n_cta;
-    return REC_OK;
-  }
-  head_bwd_adam_tc_kernel<<<n_cta, BWD_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles,
-                                                          inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size,
-                                                          1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr, e->d_sc);
+  head_bwd_adam_tc2_kernel<<<n_cta, BWD2_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo,
+                                                                    n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
+                                                                    step_size, 1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr,
+                                                                    e->d_sc);
   REC_LAUNCH_CHECK(e);
   *n_slices = n_cta;
   return REC_OK;
