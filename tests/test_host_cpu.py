@@ -228,3 +228,22 @@ def test_device_replay_buffer_follows_the_reference_dataset_protocol(pkg, tmp_pa
     ev = pkg.DeviceEvaluationDataset(arrays=dict(states=arrays["states"], actions=arrays["actions"],
                                                  true_state_len=arrays["true_state_len"]))
     assert len(ev) == n and len(ev[3]) == 3
+
+
+def test_native_loop_host_pieces(pkg, tmp_path):
+    """Host logic of train_native: evaluation points follow trainSQN.py:160-161 and the checkpoint has
+    SaveBestModel's keys (utils/save_best_model.py:29-41)."""
+    from ikea_recommender_system_b200.recommenders.ikea.training import native_loop as NL
+    assert NL.eval_points(100, (0.25, 0.5, 0.75, 1.0)) == [25, 50, 75, 100]
+    assert NL.eval_points(7, (0.5, 1.0)) == [3, 7]
+    net = pkg.SQN_Network(hidden_dim=8, item_num=20, state_size=4, action_dim=20, gamma=0.5, gru_layers=1, embedding_dim=8,
+                          train_pad_embed=True, use_packed_seq=True)
+    path = tmp_path / "best_model.pt"
+    NL.save_best_checkpoint(str(path), epoch=3, model=net, model_idx=2)
+    ck = torch.load(str(path))
+    assert set(ck) == {"epoch", "model_idx", "hidden_dim", "item_num", "action_dim", "state_size", "embedding_dim",
+                       "model_state_dict"}
+    assert ck["epoch"] == 3 and ck["model_idx"] == 2 and ck["item_num"] == 20
+    assert set(ck["model_state_dict"]) == set(net.state_dict())
+    with pytest.raises(TypeError):
+        NL._twins(object())
