@@ -528,10 +528,12 @@ def test_head_gradient_wrt_state_matches_autograd(pkg):
     assert_close(losses[:2], [ce, float(loss.detach()) - ce], rtol=RTOL, atol=1e-5)
 
 
-@pytest.mark.parametrize("B", [300, 600])
-def test_large_batch_chunked_tensor_core_backward(pkg, B):
-    """B > 256 exercises the chunked (non TMEM-resident dh) path of the tcgen05 backward kernel."""
-    V, L = 3000, 10
+@pytest.mark.parametrize("B,V", [(300, 3000), (600, 3000), (300, 40000)])
+def test_large_batch_chunked_tensor_core_backward(pkg, B, V):
+    """B > 256 exercises the chunked (non TMEM-resident dh) path of the tcgen05 backward kernel: a ragged second chunk
+    (300), an odd number of chunks (600), and several tiles per CTA (40 000 items = 313 tiles on 148 SMs: the dh slices
+    are accumulated across tiles in HBM)."""
+    L = 10
     kw = dict(hidden_dim=64, embedding_dim=64, gru_layers=1, train_pad_embed=True, use_packed_seq=True,
               learning_rate=0.01, item_num=V, state_size=L, action_dim=V)
     ref = oracle.GRUTrainer(**kw)
