@@ -34,6 +34,38 @@ def save_best_checkpoint(path, epoch, model, model_idx):
                 "model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}}, path)
 
 
+def logging_dict_train(train_sup_loss, train_q_loss, val_loss, topk_hr_ndcg, train_hr, train_ndcg, val_hr, val_ndcg,
+                       train_coverage_res, val_coverage_res, topk_cov, train_nov_rew, train_div_rew, val_nov_rew,
+                       val_div_rew, train_reps, val_reps, q_included=True, prefix=""):
+    """The wandb / tensorboard record of one evaluation point with the reference's key names
+    (`get_logging_dict_train`, utils/logging_SMORL.py:1-71); with a prefix (second twin) only the validation keys stay."""
+    res = {"Supervised Train Loss": train_sup_loss}
+    if q_included:
+        res["Q-Modification-Signal"] = train_q_loss
+    res[f"{prefix + ' '}Supervised Val Loss"] = val_loss
+    for i, k in enumerate(topk_hr_ndcg):
+        res[f"Train_HR@{k}"] = float(train_hr[i])
+        res[f"Train_NDCG@{k}"] = float(train_ndcg[i])
+        res[f"{prefix}Val_HR@{k}"] = float(val_hr[i])
+        res[f"{prefix}Val_NDCG@{k}"] = float(val_ndcg[i])
+        res[f"{prefix}Train_R@{k}"] = float(train_reps[i])
+        res[f"{prefix}Val_R@{k}"] = float(val_reps[i])
+    for k in topk_cov:
+        res[f"Train_NOV_CV@{k}"] = float(train_coverage_res[k][0])
+        res[f"Train_DIV_CV@{k}"] = float(train_coverage_res[k][1])
+        res[f"{prefix}Val_NOV_CV@{k}"] = float(val_coverage_res[k][0])
+        res[f"{prefix}Val_DIV_CV@{k}"] = float(val_coverage_res[k][1])
+    res["Train_Nov_Reward"] = float(train_nov_rew)
+    res["Train_Div_Reward"] = float(train_div_rew)
+    res[f"{prefix}Val_Nov_Reward"] = float(val_nov_rew)
+    res[f"{prefix}Val_Div_Reward"] = float(val_div_rew)
+    if prefix != "":
+        for key in list(res.keys()):
+            if "Val" not in key:
+                res.pop(key)
+    return res
+
+
 def eval_points(n_batches, eval_at):
     """Batch counts (1-based) after which the reference evaluates (trainSQN.py:160-161, :262)."""
     return sorted({int(n_batches * p) for p in eval_at})
@@ -42,11 +74,15 @@ def eval_points(n_batches, eval_at):
 def train_native(trainer, train_buffer, val_set, epochs, batch_size, val_batch_size, padding_pos, diversity_embedding,
                  unpopular_actions_set, eval_at=(0.5, 1.0), head_idx=0, topk_hr_ndcg=(5, 10, 20), topk_cov=(1, 5, 10),
                  topk_div=1, topk_nov=1, nov_rew_sig=1, input_tokenizer=None, output_tokenizer=None, generator=None,
-                 out_dir=None, best_model_metric="val_hr", drop_last=False, log=None):
-    """Returns the history: one dict per evaluation point with the reference's quantities
-    (train_sup_loss, train_q_loss, train_hr/ndcg/reps, train_div_rew, train_nov_rew, train_cov and, per twin,
-    val_loss/hr/ndcg/cov/r_div/r_nov/reps).  `train_buffer`: DeviceReplayBuffer on the trainer's device; `val_set`:
-    DeviceEvaluationDataset on it (or any iterable of `(s, a, s_len)` batches)."""
+                 out_dir=None, best_model_metric=None, drop_last=False, log=None):
+    """Returns the history: one dict per evaluation point with the reference's quantities -- raw (`train_sup_loss`,
+    `train_q_loss`, `train_hr/ndcg/reps`, `train_div_rew`, `train_nov_rew`, `train_cov`, and per twin `val_loss/hr/ndcg/
+    cov/r_div/r_nov/reps[_2]`) and as `logs`, the merged wandb records of both twins with the reference's key names
+    (`{**epoch_log_res, **epoch_log_res_sec}`, trainSQN.py:337-402).  Like the reference, the train-side sums restart
+    after every evaluation point (trainSQN.py:417-428), the better twin on `best_model_metric` (a logging key, default
+    `Val_HR@<largest k>`) is offered to the best-model saver with `epoch = log_counter` (:382-400).
+    `train_buffer`: DeviceReplayBuffer on the trainer's device; `val_set`: DeviceEvaluationDataset on it (or any
+    re-iterable of `(s, a, s_len)` batches); `log`: optional callable receiving each `logs` dict (e.g. `wandb.log`)."""
     nets = _twins(trainer)
     m1 = nets[0]
     trainer.send_to_device()
@@ -56,11 +92,13 @@ def train_native(trainer, train_buffer, val_set, epochs, batch_size, val_batch_s
     n_batches = len(bounds)
     points = set(eval_points(n_batches, eval_at))
     topk_hr_ndcg, topk_cov = list(topk_hr_ndcg), list(topk_cov)
+    if best_model_metric is None:
+        best_model_metric = f"Val_HR@{max(topk_hr_ndcg)}"
     opts, kmax, keep = EP._opts(m1, dev, head_idx, topk_hr_ndcg, topk_div, topk_nov, topk_cov, nov_rew_sig, padding_pos,
                                 diversity_embedding, unpopular_actions_set, input_tokenizer, output_tokenizer)
     unpop_np = keep[1].cpu().numpy()
     nk = len(topk_hr_ndcg)
-    history, best = [], 0.0
+    history, best, log_counter = [], 0.0, 0
 
     def val_batches():
         return val_set.batches(val_batch_size) if hasattr(val_set, "batches") else val_set
@@ -84,13 +122,14 @@ def train_native(trainer, train_buffer, val_set, epochs, batch_size, val_batch_s
                 continue
             rd = acc.read()
             ls = loss_sum.cpu().numpy()
-            rec = dict(epoch=epoch, batch=n_batch + 1,
+            rec = dict(epoch=epoch, batch=n_batch + 1, log_counter=log_counter,
                        train_sup_loss=float(ls[0] / batch_counter), train_q_loss=float(ls[1] / batch_counter),
                        train_hr=rd["hits"][:nk] / n_samples, train_ndcg=rd["ndcg"][:nk] / n_samples,
                        train_reps=rd["reps"][:nk] / n_samples, train_div_rew=float(rd["div_sum"] / n_samples),
                        train_nov_rew=float(rd["nov_sum"] / n_samples),
                        train_cov=EP._coverage(rd["cov_bits"], topk_cov, unpop_np, m1.action_dim,
                                               len(unpopular_actions_set)))
+            logs = {}
             for idx, net in enumerate(nets, start=1):
                 v = EP.evaluate(val_batches(), net, dev, trainer.cross_entropy_loss, padding_pos, diversity_embedding,
                                 unpopular_actions_set, head_idx=head_idx, topk_hr_ndcg=topk_hr_ndcg,
@@ -101,15 +140,29 @@ def train_native(trainer, train_buffer, val_set, epochs, batch_size, val_batch_s
                 rec.update({f"val_loss{sfx}": float(v[0]), f"val_hr{sfx}": v[1], f"val_ndcg{sfx}": v[2],
                             f"val_cov{sfx}": v[3], f"val_r_div{sfx}": float(v[4]), f"val_r_nov{sfx}": float(v[5]),
                             f"val_reps{sfx}": v[6]})
-                if out_dir is not None:
-                    score = rec[f"{best_model_metric}{sfx}"]
-                    score = float(np.asarray(score).reshape(-1)[-1])  # the largest k, like the reference's metric pick
-                    if score > best:
-                        best = score
-                        os.makedirs(out_dir, exist_ok=True)
-                        save_best_checkpoint(os.path.join(out_dir, "best_model.pt"), epoch, net, idx)
-            trainer.set_train()
+                logs.update(logging_dict_train(rec["train_sup_loss"], rec["train_q_loss"], float(v[0]), topk_hr_ndcg,
+                                               rec["train_hr"], rec["train_ndcg"], v[1], v[2], rec["train_cov"], v[3],
+                                               topk_cov, rec["train_nov_rew"], rec["train_div_rew"], v[5], v[4],
+                                               rec["train_reps"], v[6], q_included=True,
+                                               prefix="" if idx == 1 else "Sec_"))
+            if best_model_metric not in logs:
+                raise KeyError(f"best_model_metric {best_model_metric!r} is not a logging key: {sorted(logs)}")
+            first, second = logs[best_model_metric], logs["Sec_" + best_model_metric]
+            best_idx = 2 if first < second else 1                      # trainSQN.py:382-392
+            to_check = second if best_idx == 2 else first
+            rec["best_model_idx"] = best_idx
+            if out_dir is not None and to_check > best:                 # SaveBestModel.__call__ (maximisation)
+                best = to_check
+                os.makedirs(out_dir, exist_ok=True)
+                save_best_checkpoint(os.path.join(out_dir, "best_model.pt"), log_counter, nets[best_idx - 1], best_idx)
+            rec["logs"] = logs
             history.append(rec)
             if log is not None:
-                log(rec)
+                log(logs)
+            log_counter += 1
+            # the reference restarts every train-side sum after an evaluation point (trainSQN.py:417-428)
+            trainer.set_train()
+            acc = EvalAccumulators(dev, m1.action_dim)
+            loss_sum.zero_()
+            n_samples = batch_counter = 0
     return history

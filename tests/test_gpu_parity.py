@@ -749,7 +749,7 @@ def test_native_training_loop_matches_reference_style_loop(pkg, tmp_path):
     points = eval_points(len(loader), eval_at)
     val_loader = [(torch.from_numpy(vrows["state"][lo:lo + VB]), torch.from_numpy(vrows["action"][lo:lo + VB]),
                    torch.from_numpy(vrows["true_state_len"][lo:lo + VB])) for lo in range(0, 150, VB)]
-    tot = np.zeros(2); hr = np.zeros(3); nd = np.zeros(3); reps = np.zeros(3); n = 0; div = 0.0; nov = 0.0
+    tot = np.zeros(2); hr = np.zeros(3); nd = np.zeros(3); reps = np.zeros(3); n = 0; div = 0.0; nov = 0.0; nb = 0
     cov = {k: set() for k in (1, 5, 10)}
     want = []
     for i, (s, a, r, sn, ln, nl, e) in enumerate(loader):
@@ -759,11 +759,15 @@ def test_native_training_loop_matches_reference_style_loop(pkg, tmp_path):
         h, d, cov, dv, nv, rp = pkg.update_train_metrics(s=s, a=a, s_len=ln, model=t_ref.DQN_1, device=DEV,
                                                          actions_covered_topk_dict=cov, **mk, **ks)
         hr += h; nd += d; reps += rp; n += len(a); div += float(dv); nov += float(nv)
+        nb += 1
         if i + 1 in points:
             v1 = pkg.evaluate(val_loader, t_ref.DQN_1, DEV, t_ref.cross_entropy_loss, **mk, **ks)
             v2 = pkg.evaluate(val_loader, t_ref.DQN_2, DEV, t_ref.cross_entropy_loss, **mk, **ks)
-            want.append(dict(sup=tot[0] / (i + 1), q=tot[1] / (i + 1), hr=hr / n, ndcg=nd / n, reps=reps / n, div=div / n,
+            want.append(dict(sup=tot[0] / nb, q=tot[1] / nb, hr=hr / n, ndcg=nd / n, reps=reps / n, div=div / n,
                              nov=nov / n, cov={k: len(c) / V for k, c in cov.items()}, v1=v1, v2=v2))
+            # the reference restarts every train-side sum after an evaluation point (trainSQN.py:417-428)
+            tot = np.zeros(2); hr = np.zeros(3); nd = np.zeros(3); reps = np.zeros(3); n = 0; div = 0.0; nov = 0.0; nb = 0
+            cov = {k: set() for k in (1, 5, 10)}
     assert len(hist) == len(want) == 2
     for got, w in zip(hist, want):
         assert_close([got["train_sup_loss"], got["train_q_loss"]], [w["sup"], w["q"]], rtol=1e-6, atol=1e-7, what="train losses")
@@ -776,7 +780,17 @@ def test_native_training_loop_matches_reference_style_loop(pkg, tmp_path):
             assert abs(got[f"val_loss{sfx}"] - float(v[0])) < 1e-6
             assert np.array_equal(got[f"val_hr{sfx}"], v[1]) and np.array_equal(got[f"val_ndcg{sfx}"], v[2])
             assert got[f"val_cov{sfx}"] == v[3]
-    ck = torch.load(os.path.join(str(tmp_path), "best_model.pt"))
-    assert set(ck) == {"epoch", "model_idx", "hidden_dim", "item_num", "action_dim", "state_size", "embedding_dim",
-                       "model_state_dict"}
-    assert "embedding.weight" in ck["model_state_dict"]
+        logs = got["logs"]
+        assert logs["Val_HR@20"] == float(w["v1"][1][2]) and logs["Sec_Val_HR@20"] == float(w["v2"][1][2])
+        assert logs["Supervised Train Loss"] == got["train_sup_loss"] and "Q-Modification-Signal" in logs
+        assert got["best_model_idx"] == (2 if logs["Val_HR@20"] < logs["Sec_Val_HR@20"] else 1)
+    assert [h["log_counter"] for h in hist] == [0, 1]
+    best_seen = max(max(h["logs"]["Val_HR@20"], h["logs"]["Sec_Val_HR@20"]) for h in hist)
+    path = os.path.join(str(tmp_path), "best_model.pt")
+    if best_seen > 0:  # SaveBestModel only saves improvements over its initial 0
+        ck = torch.load(path)
+        assert set(ck) == {"epoch", "model_idx", "hidden_dim", "item_num", "action_dim", "state_size", "embedding_dim",
+                           "model_state_dict"}
+        assert "embedding.weight" in ck["model_state_dict"] and ck["epoch"] in (0, 1) and ck["model_idx"] in (1, 2)
+    else:
+        assert not os.path.exists(path)

@@ -247,3 +247,12 @@ def test_native_loop_host_pieces(pkg, tmp_path):
     assert set(ck["model_state_dict"]) == set(net.state_dict())
     with pytest.raises(TypeError):
         NL._twins(object())
+    # logging keys == the reference's get_logging_dict_train (golden written by oracle/make_golden_logging.py)
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "logging_train.json")))
+    kw = dict(g["inputs"])
+    for c in ("train_coverage_res", "val_coverage_res"):
+        kw[c] = {int(k): v for k, v in kw[c].items()}
+    assert NL.logging_dict_train(**kw, q_included=True, prefix="") == g["first"]
+    assert NL.logging_dict_train(**kw, q_included=True, prefix="Sec_") == g["second"]
+    assert "Val_HR@20" in g["first"] and "Sec_Val_HR@20" in g["second"] and "Train_HR@20" not in g["second"]
