@@ -256,3 +256,20 @@ def test_native_loop_host_pieces(pkg, tmp_path):
     assert NL.logging_dict_train(**kw, q_included=True, prefix="") == g["first"]
     assert NL.logging_dict_train(**kw, q_included=True, prefix="Sec_") == g["second"]
     assert "Val_HR@20" in g["first"] and "Sec_Val_HR@20" in g["second"] and "Train_HR@20" not in g["second"]
+
+
+def test_bench_algorithmic_bytes_follow_survey_8d():
+    """bench.py's roofline numerators: bytes/step = 24 P + 4 (K_h + 1) D V with P = (N+1)E + 3HE + 3H^2 + 6H + K_h (DV + V)
+    (SURVEY 8d); per-kernel figures are the Adam traffic (24 B/param) resp. one weight stream (4 B/param)."""
+    import bench
+    wl = bench.WORKLOADS["cfg2"]
+    V, E, H, Kh = wl["item_num"], wl["E"], wl["H"], 4
+    P = (V + 1) * E + (3 * H * E + 3 * H * H + 6 * H) + Kh * (H * V + V)
+    ab = bench.algorithmic_bytes(wl)
+    assert ab["step"] == 24 * P + 4 * (Kh + 1) * H * V
+    assert round(ab["step"] / 1e6) == 642  # DESIGN.md section 4
+    assert ab["sup_head"] == 24 * (H + 1) * V and ab["q_heads"] == 3 * ab["sup_head"]
+    assert ab["emb_adam"] == 24 * (V + 1) * E
+    assert ab["sup_stats"] == 4 * (H + 1) * V and ab["greedy_stats"] == 3 * ab["sup_stats"]
+    big = bench.algorithmic_bytes(bench.WORKLOADS["cfg4"])
+    assert 9.0e9 < big["step"] < 9.1e9  # 9.06 GB at 1 M items (SURVEY 8d)
