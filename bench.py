@@ -1,18 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark: SMORL-SQN-GRU4Rec train step, sessions/s (BASELINE.json cfg2).
+"""bench.py -- headline benchmark: SMORL-SQN-GRU4Rec train step, sessions/s, on the 1 M-item catalogue
+(BASELINE.json configs[3], the north-star target config; it fits one B200), plus top-k evaluation sessions/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload cfg2|cfg4|eval]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--workload cfg4|cfg2|eval|eval70k] [--no-secondary] [--no-cpu-baseline]
 
-Prints ONE JSON line (rank 0).  `value` = device-timed throughput with the batches already resident in
-HBM; `e2e` = the same metric through the public trainer API with HOST tensors (pinned staging + one H2D
-copy + a D2H read of the losses every step); `roofline` = algorithmic bytes of the dominant kernel /
-its CUDA-event duration against the measured HBM peak; `cpu_baseline` = the CPU oracle (a torch-CPU
-restatement pinned bit-exact to the reference) timed on this box's host cores.
-`--impl reference` times that CPU implementation alone.
+Prints ONE JSON line (rank 0).
+  value     device-timed throughput, batches already resident in HBM (CUDA events on the engine's stream)
+  e2e       the same metric through the public trainer API with HOST tensors (pinned staging + one H2D copy + a D2H
+            read of the losses every step)
+  roofline  whole train step: algorithmic bytes (24 P + 4 (K_h + 1) D V) / step time against the measured
+            HBM peak; `kernels` lists every timed kernel (exactly ONE launch between its two CUDA events) with its own
+            algorithmic bytes and fraction, `dominant` is the slowest of them
+  cpu_baseline  the CPU oracle (torch-CPU restatement pinned bit-exact to the reference) on this box's host cores
+  secondary the other two measurements of BASELINE.json's metric in the same line: "cfg2" (configs[1]: 70 852 items,
+            the reference's own catalogue size) and "eval" (configs[4]: full-catalogue top-k evaluation sweep over
+            1 M items), each with its own value / e2e / roofline.
+`--impl reference` times the CPU oracle alone (the reference is pure Python/PyTorch; no GPU code is imported).
+Under torchrun (N > 1): vocabulary-sharded step, see ikea-recommender-system_b200/dist_bench.py.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -25,14 +35,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: SQN-GRU4Rec + SMORL rewards, 70k items, batch 256, 1 B200
+    # BASELINE.json configs[3] on one GPU / sharded over N: 1M-item catalogue  (default: the north-star target config)
+    "cfg4": dict(name="cfg4: SMORL-SQN-GRU4Rec train_step, V=N=1000000, B=256 per GPU, L=10, E=H=64, 3 Q-heads + sup head",
+                 item_num=1_000_000, batch=256, L=10, E=64, H=64),
+    # configs[1]: SQN-GRU4Rec + SMORL rewards, 70k items, batch 256, 1 B200
     "cfg2": dict(name="cfg2: SMORL-SQN-GRU4Rec train_step, V=N=70852, B=256, L=10, E=H=64, 3 Q-heads + sup head",
                  item_num=70852, batch=256, L=10, E=64, H=64),
-    # configs[3]: 1M-item catalogue
-    "cfg4": dict(name="cfg4: SMORL-SQN-GRU4Rec train_step, V=N=1000000, B=256, L=10, E=H=64",
-                 item_num=1_000_000, batch=256, L=10, E=64, H=64),
 }
 METRIC = "SMORL-SQN-GRU4Rec train sessions/s"
+EVAL_METRIC = "full-catalogue top-k evaluation sessions/s"
 EVAL_WORKLOADS = {
     # BASELINE.json configs[4]: full-catalogue evaluation sweep over 1M items (HR/NDCG@{5,10,20} + coverage/div/nov)
     "eval": dict(name="cfg5: evaluate() sweep, V=N=1000000, val batch 5000, HR/NDCG@{5,10,20}, cov@{1,5,10,20}, div, nov",
@@ -40,6 +51,21 @@ EVAL_WORKLOADS = {
     "eval70k": dict(name="evaluate() sweep, V=N=70852, val batch 2000 (SMORL_paper.yaml), HR/NDCG@{5,10,20}, cov@{1,5,10,20}",
                     item_num=70852, batch=2000, L=10, E=64, H=64),
 }
+EVAL_KW = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1, topk_to_consider_nov=1,
+               topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+
+
+def synthetic_module():
+    """The synthetic-session generator, loaded by path: pure numpy, and the reference arm must not import (dlopen)
+    anything of the native package."""
+    name = "_bench_synthetic"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "ikea-recommender-system_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _peaks():
@@ -47,10 +73,10 @@ def _peaks():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
 
 
 class ClockSampler:
@@ -107,9 +133,8 @@ class ClockSampler:
 
 
 def _make_data(wl, n_batches, seed=0):
-    import numpy as np
     import torch
-    from ikea_recommender_system_b200 import synthetic
+    synthetic = synthetic_module()
     B = wl["batch"]
     rows = synthetic.make_replay_rows_fast(n_batches * B, wl["item_num"], wl["L"], seed=seed)
     unpop = synthetic.unpopular_set_from_actions(rows["action"])
@@ -129,13 +154,24 @@ def _trainer_kwargs(wl, e_div, unpop):
 
 
 def algorithmic_bytes(wl):
-    """bytes/step = 24*P + 4*(K_h+1)*D*V ; dominant kernel (head backward + Adam of
-    all K_h heads) = 24*K_h*(D+1)*V."""
+    """bytes/step = 24*P + 4*(K_h+1)*D*V; per kernel: dense Adam = 24 B/param (read + write p, m, v),
+    a forward statistics pass = 4 B per weight + bias it streams."""
     V, N, E, H, D, Kh = wl["item_num"], wl["item_num"], wl["E"], wl["H"], wl["H"], 4
     P = (N + 1) * E + (3 * H * E + 3 * H * H + 6 * H) + Kh * (D * V + V)
     return dict(step=24 * P + 4 * (Kh + 1) * D * V, head_bwd_adam=24 * Kh * (D + 1) * V, emb_adam=24 * (N + 1) * E,
-                sup_head=24 * (D + 1) * V, q_heads=24 * (Kh - 1) * (D + 1) * V,
+                sup_head=24 * (D + 1) * V, q_heads=24 * (Kh - 1) * D * V,
                 sup_stats=4 * (D + 1) * V, greedy_stats=4 * (Kh - 1) * (D + 1) * V)
+
+
+def _traffic(workload_key):
+    """DRAM bytes per launch from the committed `ncu --set full` capture of this round (profiles/r02_traffic.json,
+    stamped with the commit it was captured at); None when there is no capture for this workload."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        tj = json.load(open(path))
+        return tj.get(workload_key), {"file": "profiles/r02_traffic.json", "captured_at_commit": tj.get("commit")}
+    except Exception:
+        return None, None
 
 
 def cpu_reference_rate(wl, batches, unpop, e_div, steps, warmup, budget_s=25.0):
@@ -143,10 +179,7 @@ def cpu_reference_rate(wl, batches, unpop, e_div, steps, warmup, budget_s=25.0):
     import torch
     import oracle
     torch.set_num_threads(os.cpu_count() or 1)
-    kw = _trainer_kwargs(wl, e_div, unpop)
-    kw["topk_nov"] = 1
-    kw["nov_rew_sig"] = 1.0
-    t = oracle.SMORLTrainer(**kw)
+    t = oracle.SMORLTrainer(**_trainer_kwargs(wl, e_div, unpop))
     n = len(batches)
     t0 = time.perf_counter()
     t.train_step(*batches[0])
@@ -162,14 +195,50 @@ def cpu_reference_rate(wl, batches, unpop, e_div, steps, warmup, budget_s=25.0):
     return wl["batch"] * steps / dt, steps, dt, torch.get_num_threads()
 
 
-def run_reference(args, wl):
+def cpu_eval_rate(wl, n_sessions=512, bs=256):
+    """oracle.evaluate over a bounded sample of the evaluation workload on the host cores."""
+    import torch
+    import oracle
+    synthetic = synthetic_module()
+    torch.set_num_threads(os.cpu_count() or 1)
+    N, L = wl["item_num"], wl["L"]
+    rows = synthetic.make_replay_rows_fast(n_sessions, N, L, seed=7)
+    unpop = synthetic.unpopular_set_from_actions(rows["action"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(N + 1, 64, generator=torch.Generator().manual_seed(1)), freeze=True)
+    torch.manual_seed(118)
+    net = oracle.make_sqn(hidden_dim=wl["H"], embedding_dim=wl["E"], item_num=N, state_size=L, action_dim=N, gru_layers=1,
+                          use_packed_seq=True)
+    loader = []
+    for lo in range(0, n_sessions, bs):
+        s_, a_, _, _, ln_, _, _ = synthetic.as_torch_batch(rows, lo, min(lo + bs, n_sessions))
+        loader.append((s_, a_, ln_))
+    ce = torch.nn.CrossEntropyLoss()
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in EVAL_KW.items()}
+    oracle.evaluate(loader[:1], net, ce, "end", e_div, unpop, **kw)
+    t0 = time.perf_counter()
+    oracle.evaluate(loader, net, ce, "end", e_div, unpop, **kw)
+    dt = time.perf_counter() - t0
+    return n_sessions / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args, wl, eval_wl=None):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batches, unpop, e_div = _make_data(wl, min(args.steps + args.warmup, 64))
+    if eval_wl is not None:
+        rate, dt, cores = cpu_eval_rate(eval_wl, n_sessions=1024 if eval_wl["item_num"] > 500_000 else 8192)
+        sample = f"oracle.evaluate over a bounded sample, {dt:.1f} s on {cores} host threads (val batch 256)"
+        line = {"impl": "reference", "metric": EVAL_METRIC, "value": rate, "unit": "sessions/s", "n_gpus": args.gpus,
+                "steps": 1, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": eval_wl["name"]},
+                "cpu_baseline": {"value": rate, "unit": "sessions/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": rate, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    batches, unpop, e_div = _make_data(wl, min(args.steps + args.warmup, 16))
     # keep the whole run within a few minutes: bound the number of timed steps by a time budget
-    rate, steps, dt, cores = cpu_reference_rate(wl, batches, unpop, e_div, args.steps, max(1, min(args.warmup, 3)),
-                                                budget_s=150.0)
+    rate, steps, dt, cores = cpu_reference_rate(wl, batches, unpop, e_div, args.steps, max(1, min(args.warmup, 2)),
+                                                budget_s=120.0)
     sample = f"{steps} train_step calls at B={wl['batch']} (full batch, full catalogue) on {cores} host threads"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "sessions/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
@@ -180,20 +249,23 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def run_native(args, wl):
+KERNEL_SLOTS = {  # rec_last_kernel_ms(which): (label, key into algorithmic_bytes)
+    0: ("head_bwd_adam_tc2_kernel (supervised head: tcgen05 logits/dW/dh + fused Adam, warp-specialised)", "sup_head"),
+    3: ("adam_stream_kernel (3 Q heads, row-sparse grads; weights only, biases in adam_bias_kernel)", "q_heads"),
+    2: ("adam_stream_kernel (embedding table)", "emb_adam"),
+    4: ("head_stats_tc_kernel (supervised head: logits + online softmax + top-k, weights streamed once)", "sup_stats"),
+    5: ("head_stats_tc_kernel (greedy action: 3 Q heads pre-combined, argmax)", "greedy_stats"),
+}
+
+
+def train_bench(args, wl, wl_key, K, W, local, with_cpu):
+    """One single-GPU train-step measurement -> dict (the JSON line without the secondary objects)."""
     import torch
     import b200pkg
     pkg = b200pkg.load()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        from ikea_recommender_system_b200 import dist_bench
-        return dist_bench.run(args, wl, METRIC, _make_data, _trainer_kwargs, algorithmic_bytes, _peaks, ClockSampler)
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    K, W, B = args.steps, args.warmup, wl["batch"]
-    n_b = min(K + W, 256)
+    B = wl["batch"]
+    n_b = min(K + W, 64 if wl["item_num"] > 500_000 else 256)
     batches, unpop, e_div = _make_data(wl, n_b)
     trainer = pkg.SMORL_trainer(device=dev, **_trainer_kwargs(wl, e_div, unpop))
     trainer.send_to_device()
@@ -224,48 +296,35 @@ def run_native(args, wl):
     m1 = clocks.mark()
     clk = clocks.stop(m0, max(m1, m0 + 1))
     value = B * K / (ms / 1e3)
+    step_ms = ms / K
 
-    # ---- roofline: dominant kernels timed live with CUDA events on the engine's stream ------------
-    eng.enable_kernel_timing(True)
-    kms = {0: [], 2: [], 3: [], 4: [], 5: []}
+    # ---- roofline: every timed kernel = ONE launch between two CUDA events on the engine's stream ------------
+    eng.enable_kernel_timing(True)   # steps run eagerly and serially in this mode
+    kms = {k: [] for k in KERNEL_SLOTS}
     for i in range(min(K, 50)):
         trainer.train_step_async(*dev_batches[(W + i) % n_b])
         for which in kms:
             kms[which].append(eng.last_kernel_ms(which))
     eng.enable_kernel_timing(False)
     ab = algorithmic_bytes(wl)
-    peak, peak_src = _peaks()
-    avg = {k: sum(v) / len(v) for k, v in kms.items()}
-    step_ms = ms / K
-
-    def rl(nbytes, kms_):
-        a = nbytes / (kms_ / 1e3) / 1e9
-        return {"achieved": a, "frac": a / peak, "kernel_ms": kms_, "algorithmic_bytes_per_launch": nbytes,
-                "kernel_share_of_step": kms_ / step_ms}
-
-    parts = {"q_heads_adam_stream (adam_stream_kernel over the 3 Q heads, row-sparse grads)": rl(ab["q_heads"], avg[3]),
-             "head_bwd_adam_tc2_kernel (supervised head: tcgen05 logits/dW/dh + fused Adam, warp-specialised)": rl(ab["sup_head"], avg[0]),
-             "adam_stream_kernel (embedding table)": rl(ab["emb_adam"], avg[2]),
-             "head_stats_tc_kernel (supervised head: logits + online softmax + top-k, weights streamed once)": rl(ab["sup_stats"], avg[4]),
-             "head_stats_tc_kernel (greedy action: 3 Q heads pre-combined, argmax)": rl(ab["greedy_stats"], avg[5])}
-    # DRAM traffic per launch from the committed ncu --set full capture (cfg2 only; null elsewhere)
-    traffic = None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
-    if wl["name"].startswith("cfg2") and os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        tkeys = ["q_heads_adam_stream", "head_bwd_adam_tc_kernel", "adam_stream_kernel_embedding",
-                 "head_stats_tc_kernel_supervised", "head_stats_tc_kernel_greedy_action"]
-        for k, tk in zip(parts, tkeys):
-            parts[k]["traffic"] = tj[tk]["dram_bytes_read"] + tj[tk]["dram_bytes_write"]
-    dom = max(parts, key=lambda k: parts[k]["kernel_ms"])
-    traffic = parts[dom].get("traffic")
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": parts[dom]["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": parts[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": parts[dom]["algorithmic_bytes_per_launch"],
-                "kernel_ms": parts[dom]["kernel_ms"], "kernel_share_of_step": parts[dom]["kernel_share_of_step"],
-                "kernels": parts,
-                "step": {"algorithmic_bytes": ab["step"], "achieved": ab["step"] / (step_ms / 1e3) / 1e9,
-                         "frac": ab["step"] / (step_ms / 1e3) / 1e9 / peak}}
+    peak, peak_src, _ = _peaks()
+    traffic, traffic_src = _traffic(wl_key)
+    kernels = {}
+    for which, (label, key) in KERNEL_SLOTS.items():
+        t_ms = sum(kms[which]) / len(kms[which])
+        a = ab[key] / (t_ms / 1e3) / 1e9
+        kernels[label] = {"achieved": a, "frac": a / peak, "kernel_ms": t_ms, "algorithmic_bytes_per_launch": ab[key],
+                          "kernel_share_of_step": t_ms / step_ms,
+                          "traffic": (traffic or {}).get("kernels", {}).get(key)}
+    dom = max(kernels, key=lambda k: kernels[k]["kernel_ms"])
+    step_achieved = ab["step"] / (step_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"whole train step ({launches // K} kernel launches, CUDA-graph replay with parallel branches)",
+                "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+                "traffic": (traffic or {}).get("step"), "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab["step"], "kernel_ms": step_ms,
+                "dominant": dict(kernel=dom, **kernels[dom]), "kernels": kernels,
+                "note": "per-kernel times are taken in kernel-timing mode (branches serialised), so their shares add "
+                        "up to more than the overlapped step"}
 
     # ---- e2e: public API, host tensors in, python floats out ------------------------------------
     for i in range(max(W, 16)):  # both twins must have been captured (first sighting eager, second captures)
@@ -278,31 +337,32 @@ def run_native(args, wl):
     e2e_s = time.perf_counter() - t0
     e2e = {"value": B * K / e2e_s, "unit": "sessions/s", "h2d_bytes_per_step": int(trainer._stager.h2d_bytes),
            "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * e2e_s / K}
+    del trainer, dev_batches, eng
+    torch.cuda.empty_cache()
 
     # ---- CPU baseline (bounded sample) ------------------------------------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
-        rate, steps, dt, cores = cpu_reference_rate(wl, batches, unpop, e_div, 40, 2, budget_s=20.0)
+    if with_cpu:
+        rate, steps, dt, cores = cpu_reference_rate(wl, batches, unpop, e_div, 40, 1, budget_s=20.0)
         cpu = {"value": rate, "unit": "sessions/s", "cores": cores, "kind": "port",
                "sample": f"{steps} oracle train_step calls at B={B}, full catalogue, {dt:.1f} s"}
-
-    line = {"metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": 1, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+    return {"metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "l2_policy": "working set (p,m,v of the trained net: "
                        f"{ab['step'] / 1e6:.0f} MB/step, twins alternate) exceeds the 126 MB L2; distinct batch every step",
-                       "parallelism": "1 GPU"},
+                       "parallelism": "1 GPU", "numerics": "fp32 master weights + fp32 accumulate; head GEMMs as bf16 hi/lo "
+                       "pairs (3 tensor passes); top-k / argmax candidates re-scored in fp32"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
 
 
-def run_eval(args, wl):
-    """Secondary metric of BASELINE.json: full-catalogue top-k evaluation sessions/s (1 GPU)."""
+def eval_bench(args, wl, local, with_cpu):
+    """Full-catalogue top-k evaluation sessions/s on one GPU -> dict."""
     import torch
     import b200pkg
     pkg = b200pkg.load()
-    from ikea_recommender_system_b200 import synthetic
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    synthetic = synthetic_module()
+    dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     N, B, L = wl["item_num"], wl["batch"], wl["L"]
     n_batches = max(2, min(args.steps, 8))
@@ -318,17 +378,15 @@ def run_eval(args, wl):
     for i in range(n_batches):
         s_, a_, _, _, ln_, _, _ = synthetic.as_torch_batch(rows, i * B, (i + 1) * B)
         loader.append((s_, a_, ln_))
-    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1, topk_to_consider_nov=1,
-              topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
     ce = torch.nn.CrossEntropyLoss()
     for _ in range(max(1, args.warmup // 3)):
-        pkg.evaluate(loader[:2], net, dev, ce, "end", e_div, unpop, **kw)
+        pkg.evaluate(loader[:2], net, dev, ce, "end", e_div, unpop, **EVAL_KW)
     torch.cuda.synchronize()
     # e2e: the public evaluate() with host batches (H2D of s, a, len per batch; accumulators read back at the end)
     reps = max(1, args.steps // n_batches)
     t0 = time.perf_counter()
     for _ in range(reps):
-        out = pkg.evaluate(loader, net, dev, ce, "end", e_div, unpop, **kw)
+        out = pkg.evaluate(loader, net, dev, ce, "end", e_div, unpop, **EVAL_KW)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     sessions = reps * n_batches * B
@@ -342,9 +400,15 @@ def run_eval(args, wl):
         ds, dl = net._dev_inputs(s_, ln_)
         dev_b.append((ds, a_.to(dev), dl))
     acc = EvalAccumulators(dev, N)
+    clocks = ClockSampler(local)
+    clocks.start()
+    while clocks.proc is not None and len(clocks.rows) == 0 and clocks.proc.poll() is None:
+        eng.eval_batch(net._net_id, eng._batch(B, *dev_b[0]), o, acc.struct)
+        torch.cuda.synchronize()
     eng.enable_kernel_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.launch_count()
+    m0 = clocks.mark()
     torch.cuda.synchronize()
     ev0.record()
     for _ in range(reps):
@@ -353,28 +417,67 @@ def run_eval(args, wl):
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop(m0, max(clocks.mark(), m0 + 1))
     launches = eng.launch_count() - l0
     head_ms = eng.last_kernel_ms(1)
+    eng.enable_kernel_timing(False)
     value = sessions / (ms / 1e3)
-    flops = 2.0 * 64 * N * B * 3  # bf16x3: three tensor passes per logit
-    line = {"metric": "full-catalogue top-k evaluation sessions/s", "value": value, "unit": "sessions/s", "n_gpus": 1,
+    flops_alg = 2.0 * wl["H"] * N * B           # 2*D*V per session
+    _, _, pk = _peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", 1391.5)
+    line = {"metric": EVAL_METRIC, "value": value, "unit": "sessions/s", "n_gpus": 1,
             "steps": reps * n_batches, "warmup": args.warmup, "ms_per_step": ms / (reps * n_batches),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32 accumulate)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32 accumulate, fp32 re-score of the top-k candidates)",
             "data": "synthetic", "config": {"workload": wl["name"], "l2_policy": "head weights (256 MB at 1M items) exceed L2"},
+            "clocks": clk,
             "e2e": {"value": sessions / e2e_s, "unit": "sessions/s", "h2d_bytes_per_step": B * (L + 2) * 8,
                     "d2h_bytes_per_step": 8 * 27 + 4 * 8 * ((N + 31) // 32) // max(1, n_batches)},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "head_stats_tc_kernel (logits + online softmax + top-20)",
-                         "achieved": flops / (head_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+            "roofline": {"bound": "tensor", "kernel": "head_stats_tc_kernel (logits + online softmax + running top-k per tile)",
+                         "achieved": flops_alg / (head_ms / 1e3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": flops_alg / (head_ms / 1e3) / 1e12 / peak_tf,
                          "traffic": None, "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / (reps * n_batches)),
-                         "note": "executed bf16 FLOPs (3 passes); algorithmic 2*D*V per session"},
-            "metrics_sample": {"hr": [float(x) for x in out[1]], "ndcg": [float(x) for x in out[2]]}}
-    try:
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        line["roofline"]["peak"] = pk["bf16_tflops_sustained"]
-        line["roofline"]["frac"] = line["roofline"]["achieved"] / pk["bf16_tflops_sustained"]
-    except Exception:
-        pass
+                         "algorithmic_flops_per_launch": flops_alg,
+                         "note": "algorithmic 2*D*V FLOP per session (executed: 3 bf16 passes); the epilogue (one ex2 + "
+                                 "top-k compare per logit on the CUDA cores) is co-limiting at D = 64"},
+            "metrics_sample": {"hr": [float(x) for x in out[1]], "ndcg": [float(x) for x in out[2]]},
+            "cpu_baseline": None}
+    del net, eng
+    torch.cuda.empty_cache()
+    if with_cpu:
+        rate, dt, cores = cpu_eval_rate(wl, n_sessions=512 if N > 500_000 else 4096)
+        line["cpu_baseline"] = {"value": rate, "unit": "sessions/s", "cores": cores, "kind": "port",
+                                "sample": f"oracle.evaluate over a bounded sample of the same workload (val batch 256), {dt:.1f} s"}
+    return line
+
+
+def run_native(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import b200pkg
+        b200pkg.load()
+        from ikea_recommender_system_b200 import dist_bench
+        wl_key = args.workload if args.workload in WORKLOADS else "cfg4"
+        return dist_bench.run(args, WORKLOADS[wl_key], METRIC, _make_data, _trainer_kwargs, algorithmic_bytes,
+                              lambda: _peaks()[:2], ClockSampler,
+                              eval_wl=None if args.no_secondary else EVAL_WORKLOADS["eval"], eval_kw=EVAL_KW,
+                              eval_metric=EVAL_METRIC, synthetic=synthetic_module())
+    torch.cuda.set_device(local)
+    with_cpu = not args.no_cpu_baseline
+    if args.workload in EVAL_WORKLOADS:
+        line = eval_bench(args, EVAL_WORKLOADS[args.workload], local, with_cpu)
+        print(json.dumps(line), flush=True)
+        return
+    wl = WORKLOADS[args.workload]
+    line = train_bench(args, wl, args.workload, args.steps, args.warmup, local, with_cpu)
+    if not args.no_secondary:
+        sec = {}
+        other = "cfg2" if args.workload == "cfg4" else "cfg4"
+        sec[other] = train_bench(args, WORKLOADS[other], other, args.steps, args.warmup, local, False)
+        sec["eval"] = eval_bench(args, EVAL_WORKLOADS["eval"], local, with_cpu)
+        line["secondary"] = sec
     print(json.dumps(line), flush=True)
 
 
@@ -384,17 +487,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + sorted(EVAL_WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + sorted(EVAL_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="only the primary workload (no cfg2 / eval objects)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.workload in EVAL_WORKLOADS:
-        return run_eval(args, EVAL_WORKLOADS[args.workload])
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
-    else:
-        run_native(args, wl)
+        if args.workload in EVAL_WORKLOADS:
+            return run_reference(args, None, EVAL_WORKLOADS[args.workload])
+        return run_reference(args, WORKLOADS[args.workload])
+    run_native(args)
 
 
 if __name__ == "__main__":

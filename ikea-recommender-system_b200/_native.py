@@ -107,6 +107,7 @@ SYMBOLS = {
     "rec_launch_count": (C.c_int64, [_P]),
     "rec_enable_kernel_timing": (C.c_int, [_P, C.c_int]),
     "rec_last_kernel_ms": (C.c_float, [_P, C.c_int]),
+    "rec_debug_copy_astar": (C.c_int, [_P, _P, C.c_int]),
     "rec_debug_set_trace": (C.c_int, [_P, _P]),
     "rec_debug_tc_gemm": (C.c_int, [C.c_int, _P, _P, _P, _P]),
 }

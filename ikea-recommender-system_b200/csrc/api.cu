@@ -43,7 +43,8 @@ static EngineExtra &extra(rec_engine *e) { return *reinterpret_cast<EngineExtra 
 
 extern "C" int rec_abi_version(void) { return REC_ABI_VERSION; }
 
-extern "C" const char *rec_last_error(const rec_engine *e) { return e ? e->err : g_err; }
+extern "C" const char *rec_last_error(const rec_engine *e) {
+  DevGuard dev_guard(e); return e ? e->err : g_err; }
 
 extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out) {
   if (!cfg || !out) { snprintf(g_err, sizeof(g_err), "rec_create: null argument"); return REC_EINVAL; }
@@ -68,6 +69,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
              c.embedding_dim, c.hidden_dim);
     return REC_EINVAL;
   }
+  if (dev >= REC_MAX_DEVICES) { snprintf(g_err, sizeof(g_err), "rec_create: device ordinal %d not supported", dev); return REC_EINVAL; }
   if (c.n_heads < 1 || c.n_heads > REC_MAX_HEADS || c.n_heads == 3 || c.n_nets < 1 || c.n_nets > REC_MAX_NETS ||
       c.max_batch < 1 || c.state_size < 1 || c.item_num < 1 || c.action_dim < 1 || c.vocab_lo < 0 ||
       c.vocab_hi > c.action_dim || c.vocab_lo >= c.vocab_hi || c.max_topk < 1 || c.max_topk > REC_MAX_TOPK) {
@@ -79,6 +81,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   rec_engine *e = new (mem) rec_engine;
   memset((void *)e, 0, sizeof(rec_engine) + sizeof(EngineExtra));
   e->cfg = c;
+  e->dev = dev;
   e->stream = (cudaStream_t)stream;
   e->dirs = c.bidirectional ? 2 : 1;
   e->D = c.hidden_dim * e->dirs;
@@ -200,6 +203,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
 }
 
 extern "C" void rec_destroy(rec_engine *e) {
+  DevGuard dev_guard(e);
   if (!e) return;
   cudaStreamSynchronize(e->stream);
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
@@ -236,6 +240,7 @@ static int check_net(rec_engine *e, int net_id, bool need_opt) {
 }
 
 extern "C" int rec_bind_params(rec_engine *e, int net_id, const rec_net_params *p) {
+  DevGuard dev_guard(e);
   if (!e || !p) return REC_EINVAL;
   if (net_id < 0 || net_id >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "net_id %d out of range", net_id);
   if (!p->emb) REC_FAIL(e, REC_EINVAL, "rec_bind_params: emb is null");
@@ -252,6 +257,7 @@ extern "C" int rec_bind_params(rec_engine *e, int net_id, const rec_net_params *
 __global__ void set_step_kernel(long long *d_step, long long v) { *d_step = v; }
 
 extern "C" int rec_set_adam_step(rec_engine *e, int net_id, int64_t step) {
+  DevGuard dev_guard(e);
   if (!e || net_id < 0 || net_id >= e->cfg.n_nets) return REC_EINVAL;
   e->nets[net_id].adam_step = step;
   set_step_kernel<<<1, 1, 0, e->stream>>>(e->d_step + net_id, (long long)step);
@@ -259,6 +265,7 @@ extern "C" int rec_set_adam_step(rec_engine *e, int net_id, int64_t step) {
   return REC_OK;
 }
 extern "C" int64_t rec_get_adam_step(const rec_engine *e, int net_id) {
+  DevGuard dev_guard(e);
   if (!e || net_id < 0 || net_id >= e->cfg.n_nets) return -1;
   // the device counter is authoritative (steps replayed from a caller-captured graph never pass through the host)
   long long t = 0;
@@ -270,29 +277,42 @@ extern "C" int64_t rec_get_adam_step(const rec_engine *e, int net_id) {
 }
 
 extern "C" int rec_set_stream(rec_engine *e, void *stream) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   e->stream = (cudaStream_t)stream;
   return REC_OK;
 }
 
 extern "C" int rec_set_cuda_graphs(rec_engine *e, int on) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   e->use_graph = on != 0;
   return REC_OK;
 }
 extern "C" int rec_set_tensor_cores(rec_engine *e, int on) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   e->use_tc = on != 0;
   return REC_OK;
 }
 extern "C" int rec_debug_set_trace(rec_engine *e, long long *dev_buf) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   e->trace = dev_buf;
   return REC_OK;
 }
-extern "C" int64_t rec_launch_count(const rec_engine *e) { return e ? e->launches : -1; }
-extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) { if (!e) return REC_EINVAL; e->timing = on != 0; return REC_OK; }
+extern "C" int rec_debug_copy_astar(rec_engine *e, int32_t *out, int B) {
+  DevGuard dev_guard(e);
+  if (!e || !out || B < 1 || B > e->cfg.max_batch) return REC_EINVAL;
+  REC_CUDA(e, cudaMemcpyAsync(out, e->astar, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, e->stream));
+  return REC_OK;
+}
+extern "C" int64_t rec_launch_count(const rec_engine *e) {
+  DevGuard dev_guard(e); return e ? e->launches : -1; }
+extern "C" int rec_enable_kernel_timing(rec_engine *e, int on) {
+  DevGuard dev_guard(e); if (!e) return REC_EINVAL; e->timing = on != 0; return REC_OK; }
 extern "C" float rec_last_kernel_ms(rec_engine *e, int which) {
+  DevGuard dev_guard(e);
   if (!e || which < 0 || which > 5) return -1.f;
   float ms = -1.f;
   if (cudaEventSynchronize(e->ev[2 * which + 1]) != cudaSuccess ||
@@ -311,6 +331,7 @@ static int check_batch(rec_engine *e, const rec_batch *b, bool q) {
 }
 
 extern "C" int rec_forward_state(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B, float *h_out) {
+  DevGuard dev_guard(e);
   int rc = check_net(e, net_id, false);
   if (rc) return rc;
   if (!s || !lengths || !h_out || B < 1) REC_FAIL(e, REC_EINVAL, "rec_forward_state: bad argument");
@@ -318,6 +339,7 @@ extern "C" int rec_forward_state(rec_engine *e, int net_id, const int64_t *s, co
 }
 
 extern "C" int rec_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld) {
+  DevGuard dev_guard(e);
   int rc = check_net(e, net_id, false);
   if (rc) return rc;
   if (head < 0 || head >= e->cfg.n_heads || !h || !logits || ld < e->Vloc) REC_FAIL(e, REC_EINVAL, "rec_head_logits: bad argument");
@@ -446,7 +468,14 @@ static int run_step_graphed(rec_engine *e, int kind, int main_net, const rec_bat
   }
   uint64_t key = 1469598103934665603ull;
   key = fnv(key, &kind, sizeof(kind)); key = fnv(key, &main_net, sizeof(main_net)); key = fnv(key, &b->B, sizeof(int));
-  key = fnv(key, hp, sizeof(*hp)); key = fnv(key, &out, sizeof(out));
+  {  // field by field: the struct's padding bytes are indeterminate in a caller's stack object
+    const float f[] = {hp->lr, hp->beta1, hp->beta2, hp->eps, hp->gamma, hp->alpha, hp->q_weights[0], hp->q_weights[1],
+                       hp->q_weights[2], hp->nov_reward, hp->dropout_p};
+    const int32_t i[] = {hp->div_dim, hp->topk_div, hp->topk_nov, hp->pad_pos_end, e->use_tc ? 1 : 0, e->overlap ? 1 : 0};
+    const void *ptrs[] = {hp->div_emb, hp->unpopular, hp->out_to_in, hp->dropout_mask, out};
+    key = fnv(key, f, sizeof(f)); key = fnv(key, i, sizeof(i)); key = fnv(key, ptrs, sizeof(ptrs));
+    key = fnv(key, &hp->dropout_seed, sizeof(hp->dropout_seed));
+  }
   for (int n = 0; n < e->cfg.n_nets; ++n) key = fnv(key, &e->nets[n].p, sizeof(rec_net_params));
   rec_engine::GraphEntry *g = nullptr;
   for (int i = 0; i < e->n_graphs; ++i) if (e->graphs[i].key == key) g = &e->graphs[i];
@@ -537,6 +566,7 @@ static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hp
 }
 
 extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out) {
+  DevGuard dev_guard(e);
   int rc = check_net(e, 0, true);
   if (rc) return rc;
   if ((rc = check_batch(e, b, false))) return rc;
@@ -558,6 +588,7 @@ static int finish_host_step(rec_engine *e, int rc, float *out, int n) {
 }
 
 extern "C" int rec_train_step_supervised_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp, float *loss_host) {
+  DevGuard dev_guard(e);
   int rc = check_net(e, 0, true);
   if (rc) return rc;
   if ((rc = check_batch(e, host_b, false))) return rc;
@@ -613,7 +644,7 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
   if (e->timing) cudaEventRecord(e->ev[8], e->stream);
   if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
   if (e->timing) cudaEventRecord(e->ev[9], e->stream);
-  if ((rc = launch_head_merge(e, e->part, n_split, B, a.topk, true, false))) return rc;
+  if ((rc = launch_head_merge(e, e->part, n_split, B, a.topk, true, false, nullptr, &a))) return rc;
   side_mark(e, 0);  // log-sum-exp of the supervised logits is final: its backward may start
   // greedy action a* = argmax_a sum_h w_h Q_h(s', a) on the main net
   HeadStatsArgs g = {};
@@ -629,7 +660,7 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
   }
   // a*, Q(s,a), Q_boot(s',a*), rewards, TD target, dq, Q-head dh slice: one launch
   const float alpha_eff = (n_q == 3) ? hp->alpha : 1.f;
-  if ((rc = launch_q_rows_fused(e, main_net, b, hp, n_split, alpha_eff, extra(e).q_loss_rows))) return rc;
+  if ((rc = launch_q_rows_fused(e, main_net, b, hp, n_split, alpha_eff, extra(e).q_loss_rows, &g))) return rc;
   side_mark(e, 1);
   {
     SideScope side(e, 2, 1);
@@ -647,6 +678,7 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
 }
 
 extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q needs a twin-net engine with Q heads");
   if (main_net != 0 && main_net != 1) REC_FAIL(e, REC_EINVAL, "main_net must be 0 or 1");
@@ -671,6 +703,7 @@ extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_tra
 
 extern "C" int rec_train_step_q_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp, int main_net,
                                      float *losses_host) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q_host needs a twin-net engine with Q heads");
   if (main_net != 0 && main_net != 1) REC_FAIL(e, REC_EINVAL, "main_net must be 0 or 1");
@@ -706,6 +739,7 @@ static int eval_kmax(const rec_eval_opts *o) {
 
 extern "C" int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, const rec_eval_opts *o,
                               const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores) {
+  DevGuard dev_guard(e);
   int rc = check_net(e, net_id, false);
   if (rc) return rc;
   if ((rc = check_batch(e, b, false))) return rc;
@@ -724,7 +758,7 @@ extern "C" int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, con
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
   if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
   if (e->timing) cudaEventRecord(e->ev[3], e->stream);
-  if ((rc = launch_head_merge(e, e->part, n_split, B, kmax, true, false))) return rc;
+  if ((rc = launch_head_merge(e, e->part, n_split, B, kmax, true, false, nullptr, &a))) return rc;
   return launch_eval_metrics(e, b, o, kmax, acc, extra(e).rowm, topk_ids, topk_scores);
 }
 
@@ -741,19 +775,20 @@ static int shard_head_pass(rec_engine *e, int net_id, const float *h, const rec_
     a.net_id = net_id; a.h = h; a.B = b->B; a.do_stats = want_stats ? 1 : 0; a.stats_head = stats_head; a.target = b->a;
     a.topk = topk;
     if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
-    if ((rc = launch_head_merge(e, e->part, n_split, b->B, topk, want_stats, false, summary))) return rc;
+    if ((rc = launch_head_merge(e, e->part, n_split, b->B, topk, want_stats, false, summary, &a))) return rc;
   }
   if (n_q > 0) {
     HeadStatsArgs g = {};
     g.net_id = net_id; g.h = e->h_state[1]; g.B = b->B; g.n_arg = n_q;
     g.w[0] = w[0]; g.w[1] = w[1]; g.w[2] = w[2];
     if ((rc = head_stats_dispatch(e, g, &n_split))) return rc;
-    if ((rc = launch_head_merge(e, e->part, n_split, b->B, 0, false, true, summary))) return rc;
+    if ((rc = launch_head_merge(e, e->part, n_split, b->B, 0, false, true, summary, &g))) return rc;
   }
   return REC_OK;
 }
 
-extern "C" int rec_record_floats(const rec_engine *e) { return e ? e->part_stride : -1; }
+extern "C" int rec_record_floats(const rec_engine *e) {
+  DevGuard dev_guard(e); return e ? e->part_stride : -1; }
 
 static int phase_a_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *records_out,
                         bool skip_gru) {
@@ -792,6 +827,7 @@ static int phase_a_body(rec_engine *e, const rec_batch *b, const rec_train_hpara
 
 extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
                                  float *records_out) {
+  DevGuard dev_guard(e);
   if (e) e->dp_active = false;
   return phase_a_body(e, b, hp, main_net, records_out, false);
 }
@@ -831,16 +867,19 @@ __global__ void sum_splits_kernel(const float *__restrict__ part, int splits, in
 static int dp_n_h(const rec_engine *e) { return e->cfg.n_heads > 1 ? 3 : 1; }
 
 extern "C" int64_t rec_dp_packed_bytes(const rec_engine *e, int B_local) {
+  DevGuard dev_guard(e);
   if (!e || B_local < 1) return -1;
   return rec_packed_batch_bytes(e, B_local) + (int64_t)dp_n_h(e) * B_local * e->D * (int64_t)sizeof(float);
 }
 extern "C" int64_t rec_dp_grad_floats(const rec_engine *e) {
+  DevGuard dev_guard(e);
   if (!e) return -1;
   const int E = e->cfg.embedding_dim, H = e->cfg.hidden_dim;
   return (int64_t)e->dirs * 2 * (3 * H) * ((E > H ? E : H) + 1);
 }
 
 extern "C" int rec_dp_forward(rec_engine *e, const rec_batch *local, int main_net, void *packed_out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   const int n_q = e->cfg.n_heads - 1;
   if (main_net < 0 || main_net >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "main_net out of range");
@@ -876,6 +915,7 @@ extern "C" int rec_dp_forward(rec_engine *e, const rec_batch *local, int main_ne
 }
 
 extern "C" int rec_dp_unpack(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (!gathered || n_ranks < 1 || B_local < 1 || !out || !out->s || !out->s_next || !out->a || !out->true_len ||
       !out->true_next_len || !out->r || !out->is_end)
@@ -894,11 +934,13 @@ extern "C" int rec_dp_unpack(rec_engine *e, const void *gathered, int n_ranks, i
 
 extern "C" int rec_train_phase_a_heads(rec_engine *e, const rec_batch *global_b, const rec_train_hparams *hp, int main_net,
                                        float *records_out) {
+  DevGuard dev_guard(e);
   if (e) e->dp_active = true;
   return phase_a_body(e, global_b, hp, main_net, records_out, true);
 }
 
 extern "C" int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank, float *gru_grads_out, float *dx_out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 3 || !e->dp_active) REC_FAIL(e, REC_EINVAL, "rec_dp_backward called out of order");
   if (!dh_reduced || !gru_grads_out || !dx_out || rank < 0) REC_FAIL(e, REC_EINVAL, "rec_dp_backward: bad argument");
@@ -918,6 +960,7 @@ extern "C" int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank,
 }
 
 extern "C" int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const float *dx_gathered) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 4) REC_FAIL(e, REC_EINVAL, "rec_dp_apply called out of order");
   if (!gru_grads_reduced || !dx_gathered) REC_FAIL(e, REC_EINVAL, "rec_dp_apply: null argument");
@@ -940,6 +983,7 @@ extern "C" int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const
 }
 
 extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float *q_out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 1) REC_FAIL(e, REC_EINVAL, "rec_train_phase_b called out of order");
   if (!gathered || n_shards < 1 || (!q_out && e->cfg.n_heads > 1)) REC_FAIL(e, REC_EINVAL, "rec_train_phase_b: bad argument");
@@ -957,6 +1001,7 @@ extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_sha
 }
 
 extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, float *losses_out, float *dh_out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 2) REC_FAIL(e, REC_EINVAL, "rec_train_phase_c called out of order");
   if (!losses_out || !dh_out) REC_FAIL(e, REC_EINVAL, "rec_train_phase_c: null argument");
@@ -983,6 +1028,7 @@ extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, flo
 }
 
 extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 3) REC_FAIL(e, REC_EINVAL, "rec_train_phase_d called out of order");
   if (!dh_reduced) REC_FAIL(e, REC_EINVAL, "rec_train_phase_d: null argument");
@@ -997,6 +1043,7 @@ extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
 // Sharded evaluation: per-shard record (max, sumexp, target logit, top-k candidates) per row ...
 extern "C" int rec_eval_shard_candidates(rec_engine *e, int net_id, const rec_batch *b, int head_idx, int kmax,
                                          float *records_out) {
+  DevGuard dev_guard(e);
   int rc = check_net(e, net_id, false);
   if (rc) return rc;
   if ((rc = check_batch(e, b, false))) return rc;
@@ -1011,6 +1058,7 @@ extern "C" int rec_eval_shard_candidates(rec_engine *e, int net_id, const rec_ba
 // ... and the merge of the all-gathered records of all shards + metric accumulation (replicated).
 extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_opts *o, const float *gathered,
                               int n_shards, const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   int rc = check_batch(e, b, false);
   if (rc) return rc;
@@ -1025,6 +1073,7 @@ extern "C" int rec_eval_merge(rec_engine *e, const rec_batch *b, const rec_eval_
 extern "C" int rec_build_replay_rows(rec_engine *e, const int64_t *session_offsets, int64_t n_sessions, const int64_t *items,
                                      const float *rewards, int64_t n_events, int64_t pad_id, int pad_pos_end,
                                      const rec_batch *out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (!session_offsets || !items || !out || n_sessions < 1 || n_events < 1)
     REC_FAIL(e, REC_EINVAL, "rec_build_replay_rows: null argument or empty log");
@@ -1035,6 +1084,7 @@ extern "C" int rec_build_replay_rows(rec_engine *e, const int64_t *session_offse
 
 extern "C" int rec_gather_batch(rec_engine *e, const rec_batch *columns, int64_t n_rows, const int64_t *idx, int B,
                                 const rec_batch *out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (!columns || !idx || !out || n_rows < 1 || B < 1) REC_FAIL(e, REC_EINVAL, "rec_gather_batch: null argument or empty buffer");
   if (!columns->s || !columns->a || !columns->true_len || !out->s || !out->a || !out->true_len)
@@ -1043,16 +1093,19 @@ extern "C" int rec_gather_batch(rec_engine *e, const rec_batch *columns, int64_t
 }
 
 extern "C" int64_t rec_packed_batch_bytes(const rec_engine *e, int B) {
+  DevGuard dev_guard(e);
   if (!e || B < 1) return -1;
   int64_t n = (int64_t)B * (2 * e->cfg.state_size + 3) * 8 + (int64_t)B * 5;
   return (n + 15) / 16 * 16;
 }
 extern "C" int rec_pack_batch(rec_engine *e, const rec_batch *b, void *packed_out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (!b || !packed_out || !b->s || !b->a || !b->true_len || b->B < 1) REC_FAIL(e, REC_EINVAL, "rec_pack_batch: bad argument");
   return launch_pack_batch(e, b, (uint8_t *)packed_out);
 }
 extern "C" int rec_unpack_batch(rec_engine *e, const void *gathered, int n_ranks, int B_local, const rec_batch *out) {
+  DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (!gathered || n_ranks < 1 || B_local < 1 || !out || !out->s || !out->s_next || !out->a || !out->true_len ||
       !out->true_next_len || !out->r || !out->is_end)

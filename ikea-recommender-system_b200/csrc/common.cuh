@@ -7,6 +7,7 @@
 #include "../../include/recsys_b200.h"
 
 #define REC_NEG_INF (-3.402823466e+38f)
+#define REC_MAX_DEVICES 64
 
 struct NetBind {
   rec_net_params p;
@@ -19,6 +20,7 @@ struct NetBind {
 // Per-pass GRU buffers: which (net, sequence, lengths) produced which final state.
 struct rec_engine {
   rec_config cfg;
+  int dev;               // CUDA device the engine lives on (every entry point switches to it: DevGuard)
   cudaStream_t stream;
   char err[512];
   NetBind nets[REC_MAX_NETS];
@@ -98,6 +100,10 @@ struct rec_engine {
   int n_graphs;
   long long *trace;      // optional device buffer for clock64 phase traces (debug)
   bool use_tc;           // tensor-core (tcgen05) head kernels when D == 64
+  // what the most recent head-statistics launch published per (split,row) record (consumed by the merge that follows)
+  int st_kpub;           // top-k candidates per record (>= topk when the scores are approximate: see rec_kpub)
+  int st_apub;           // greedy-action candidates per record in the top-k slots (0: only the (value,id) pair at [3],[4])
+  bool st_approx;        // scores are bf16x3 tensor-core products: the merge re-scores its candidates in fp32
   cudaEvent_t ev[12];
   float last_ms[3];
 };
@@ -165,6 +171,34 @@ __device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g,
 __device__ __forceinline__ bool better(float v, int i, float w, int j) {
   return (v > w) || (v == w && i < j);
 }
+
+// Candidate margins of the fp32 re-score (SURVEY 7 hard part 1): the tensor-core statistics kernels rank by bf16x3
+// scores (~1e-5 relative), so every stage keeps MORE candidates than the k it is asked for, and the merge that
+// ends the chain re-scores its top-(k + margin) candidates with a fixed-order fp32 FFMA dot product and orders them
+// by (exact score desc, id asc) -- torch.topk / argmax on fp32 logits (eval_protocol.py:75, sqn_gru.py:229,
+// tensor_operations.py:73-84).  `cs` = threads that share a row inside the CTA (each keeps a private top-k list).
+__host__ __device__ inline int rec_kpub(int topk, int cs) {
+  int k = topk + (topk <= 2 ? 2 : 8);
+  if (k > cs * topk) k = cs * topk;
+  return k > REC_MAX_TOPK ? REC_MAX_TOPK : k;
+}
+__host__ __device__ inline int rec_kt(int topk) {  // candidates the merge re-scores
+  const int k = topk + (topk <= 2 ? 3 : 8);
+  return k > REC_MAX_TOPK ? REC_MAX_TOPK : k;
+}
+#define REC_ARG_CAND 4   // greedy-action candidates the merge re-scores
+
+// Every ABI entry point runs with the engine's device current and restores the caller's device afterwards
+// (an engine on cuda:1 called while cuda:0 is current would otherwise launch on a stream of another device).
+struct DevGuard {
+  int prev;
+  explicit DevGuard(const rec_engine *e) : prev(-1) {
+    if (!e) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != e->dev) { prev = cur; cudaSetDevice(e->dev); }
+  }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -239,8 +273,10 @@ bool tc_bwd_supported(const rec_engine *e, int B);
 int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                             float bc2_sqrt, const rec_train_hparams *hp, float inv_B, int *n_slices);
 int launch_h_prepack_early(rec_engine *e, const float *h, int B);
+// `src`: the statistics launch that produced `part` (its records may hold approximate scores and extra candidates:
+// e->st_*); nullptr: `part` holds exact per-shard summaries written by a previous merge (cross-GPU merge).
 int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats,
-                      bool has_argmax, float *summary = nullptr);
+                      bool has_argmax, float *summary = nullptr, const HeadStatsArgs *src = nullptr);
 int launch_head_logits(rec_engine *e, int net_id, int head, const float *h, int B, float *logits, int64_t ld);
 int launch_row_dots(rec_engine *e, int net_id, const float *h, const int64_t *ids, const int32_t *ids32,
                     int B, int first_head, int n, float *out);
@@ -256,4 +292,4 @@ int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_b
 int launch_dh_reduce(rec_engine *e, int B);
 int launch_dropout(rec_engine *e, int net_id, float *h, float *dh, int B, const rec_train_hparams *hp, bool backward);
 int launch_q_rows_fused(rec_engine *e, int main_net, const rec_batch *b, const rec_train_hparams *hp, int n_split,
-                        float alpha_eff, float *q_loss_rows);
+                        float alpha_eff, float *q_loss_rows, const HeadStatsArgs *src);

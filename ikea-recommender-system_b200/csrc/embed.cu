@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(256) adam_bias_kernel(AdamStreamSet ts, const 
 
 static int launch_adam_stream_set(rec_engine *e, const AdamStreamSet &ts, int n_tensors, bool with_bias, int64_t rows, int D,
                                   const int32_t *slot_of_row, int grad_stride, int bgrad_stride,
-                                  const rec_train_hparams *hp, float step_size, float bc2_sqrt) {
+                                  const rec_train_hparams *hp, float step_size, float bc2_sqrt, int time_slot = -1) {
+  // time_slot >= 0 (kernel-timing mode): CUDA events around the ONE adam_stream_kernel launch (rec_last_kernel_ms)
   const int64_t n4 = rows * (D / 4);
   if (n4 >= (int64_t)1 << 31) REC_FAIL(e, REC_EINVAL, "adam_stream: tensor too large (%lld float4)", (long long)n4);
   // The sweep is persistent (grid-stride) with a SMALL resident footprint: `ctas` CTAs per SM keep enough bytes in
@@ -241,12 +242,14 @@ static int launch_adam_stream_set(rec_engine *e, const AdamStreamSet &ts, int n_
   int blocks = (int)(want < (int64_t)per ? want : (int64_t)per);
   if (blocks < 1) blocks = 1;
   dim3 grid(blocks, n_tensors);
+  if (e->timing && time_slot >= 0) cudaEventRecord(e->ev[2 * time_slot], e->stream);
   if (unroll == 4)
     adam_stream_kernel<4><<<grid, 256, 0, e->stream>>>(ts, slot_of_row, grad_stride / 4, (uint32_t)n4, D4, shift, hp->beta1,
                                                        hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt, e->d_sc);
   else
     adam_stream_kernel<2><<<grid, 256, 0, e->stream>>>(ts, slot_of_row, grad_stride / 4, (uint32_t)n4, D4, shift, hp->beta1,
                                                        hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt, e->d_sc);
+  if (e->timing && time_slot >= 0) cudaEventRecord(e->ev[2 * time_slot + 1], e->stream);
   REC_LAUNCH_CHECK(e);
   if (with_bias) {
     dim3 g2(cdiv((int)rows, 256), n_tensors);
@@ -371,7 +374,7 @@ int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_bat
       ts.bp[j] = p.head_b[1 + j]; ts.bm[j] = p.head_b_m[1 + j]; ts.bv[j] = p.head_b_v[1 + j];
       ts.bgrad[j] = e->q_bgrad + j;
     }
-    int rc = launch_adam_stream_set(e, ts, n_q, true, e->Vloc, D, e->q_slot, n_q * D, n_q, hp, step_size, bc2_sqrt);
+    int rc = launch_adam_stream_set(e, ts, n_q, true, e->Vloc, D, e->q_slot, n_q * D, n_q, hp, step_size, bc2_sqrt, 3);
     if (rc) return rc;
   }
   q_slot_reset_kernel<<<cdiv(B, 256), 256, 0, e->stream>>>(b->a, B, e->Vloc, e->cfg.vocab_lo, e->q_slot);
@@ -599,10 +602,10 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
   const int L = c.state_size, E = c.embedding_dim, P = B * L;
   NetBind &nb = e->nets[net_id];
   const bool sorted_path = (E == 64 && e->dirs == 1 && P <= 32768);
-  static bool rank_attr_set = false;
-  if (sorted_path && !rank_attr_set) {
+  static bool rank_attr_set[REC_MAX_DEVICES] = {};
+  if (sorted_path && !rank_attr_set[e->dev]) {
     REC_CUDA(e, cudaFuncSetAttribute(emb_merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * (int)sizeof(int32_t)));
-    rank_attr_set = true;
+    rank_attr_set[e->dev] = true;
   }
   if (stages & 1) {
     emb_keys_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(s, lengths, B, L, c.item_num, c.use_packed_seq,
@@ -637,10 +640,10 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
     const int span = n_chunks > 1 ? chunk : P;
     int use_smem = 1;
     size_t smem = (size_t)span * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[REC_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
+    if (!attr_set[e->dev]) {
       REC_CUDA(e, cudaFuncSetAttribute(emb_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
+      attr_set[e->dev] = true;
     }
     uint8_t *flags = n_chunks > 1 ? e->emb_leader : nullptr;
     if (flags) REC_CUDA(e, cudaMemsetAsync(flags, 0, (size_t)P, e->stream));

@@ -664,10 +664,10 @@ int launch_gru_forward(rec_engine *e, int net_id, const int64_t *s, const int64_
   }
   const int E = c.embedding_dim, H = c.hidden_dim, L = c.state_size;
   size_t smem = (size_t)GRU_R * (E + H + 6 * H) * sizeof(float) + (size_t)GRU_R * (1 + L) * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
+  static bool attr_set[REC_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
+  if (!attr_set[e->dev] && smem > 48 * 1024) {
     REC_CUDA(e, cudaFuncSetAttribute(gru_fwd_kernel<GRU_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set[e->dev] = true;
   }
   if (smem > 200 * 1024) REC_FAIL(e, REC_EINVAL, "GRU forward needs %zu B of shared memory (E=%d,H=%d)", smem, E, H);
   dim3 grid(cdiv(B, GRU_R), e->dirs);
@@ -683,10 +683,10 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
   const rec_config &c = e->cfg;
   const int E = c.embedding_dim, H = c.hidden_dim, L = c.state_size, G = 3 * H;
   size_t smem = (size_t)GRU_R * (2 * H + 2 * G) * sizeof(float) + GRU_R * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
+  static bool attr_set[REC_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
+  if (!attr_set[e->dev] && smem > 48 * 1024) {
     REC_CUDA(e, cudaFuncSetAttribute(gru_bwd_kernel<GRU_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set[e->dev] = true;
   }
   if (stages & 1) {
     if (gru_fast_path(e)) {

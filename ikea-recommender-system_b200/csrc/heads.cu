@@ -252,11 +252,120 @@ __global__ void __launch_bounds__(256) head_stats_kernel(HeadPtrs hp, const floa
 // row_stats[b] = {lse, target_logit, argmax_val, argmax_id(bits), ce_row, max, sumexp, -}
 // ------------------------------------------------------------------------------------------------
 #define ROW_STRIDE 8
+
+// ---- fp32 re-score of candidates (one warp per session row, lane c owns candidate c) -----------------------
+// exact[c] = sum_k h[k] * W[id_c][k] in ascending k with ONE fp32 accumulator, + bias -- the arithmetic of nn.Linear
+// in fp32 up to summation order.  h[k] is broadcast from the lane that loaded it; every lane runs the loop (lanes
+// without a candidate compute on row 0 and are ignored by the caller).
+struct RescoreSrc {
+  const float *w[3], *b[3];   // heads scored: [0] for top-k, [0..n_arg) for the greedy action
+  const float *h;             // [B, D] states the candidates were scored on
+  int n_arg;                  // >0: greedy-action candidates (sum_j wq[j] * Q_j), else top-k of head w[0]
+  float wq[3];
+  int approx;                 // 1: records hold approximate (tensor-core) scores -> re-score
+  int kpub, apub;             // candidates per record: top-k slots / greedy-action slots
+};
+
+__device__ __forceinline__ float exact_row_dot(const float *__restrict__ W, const float *__restrict__ bias, int64_t loc,
+                                               const float *__restrict__ hrow, int D, int lane) {
+  const float *wr = W + loc * D;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < D; k0 += 32) {
+    const float hv = (k0 + lane < D) ? hrow[k0 + lane] : 0.f;
+    const int n = min(32, D - k0);
+    for (int kk = 0; kk < n; kk += 4) {  // D is a multiple of 4
+      const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wr + k0 + kk));
+      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk), w4.x, acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk + 1), w4.y, acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk + 2), w4.z, acc);
+      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk + 3), w4.w, acc);
+    }
+  }
+  return acc + __ldg(bias + loc);
+}
+
+// greedy-action score of candidate `id` in the oracle's order: ((q0*w0 + q1*w1) + q2*w2), plain q0 for one head
+__device__ __forceinline__ float exact_arg_score(const RescoreSrc &R, int id, int vocab_lo, int Vloc, const float *hrow,
+                                                 int D, int lane) {
+  int64_t loc = (int64_t)id - vocab_lo;
+  const bool ok = loc >= 0 && loc < Vloc;
+  if (!ok) loc = 0;
+  float sc = 0.f;
+  for (int j = 0; j < R.n_arg; ++j) {
+    float q = exact_row_dot(R.w[j], R.b[j], loc, hrow, D, lane);
+    if (R.n_arg > 1) q *= R.wq[j];
+    sc = (j == 0) ? q : sc + q;
+  }
+  return ok ? sc : REC_NEG_INF;
+}
+
+// Greedy action from `n_split` records of one row: best REC_ARG_CAND candidates by approximate score, re-scored in
+// fp32, best by (score desc, id asc).  All lanes return the winner.
+__device__ __forceinline__ void merge_arg_rescored(const float *__restrict__ part, int part_stride, int n_split, int B,
+                                                   int row, const RescoreSrc &R, int vocab_lo, int Vloc, int D, int lane,
+                                                   float &out_v, int &out_i) {
+  const int n = n_split * R.apub;
+  float lastv = 3.402823466e+38f, cv = REC_NEG_INF;
+  int lasti = -1, ci = 0x7fffffff;
+  for (int k = 0; k < REC_ARG_CAND; ++k) {
+    float bv = REC_NEG_INF;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < n; c += 32) {
+      const int sp = c / R.apub, j = c - sp * R.apub;
+      const float *o = part + ((int64_t)sp * B + row) * part_stride + PART_TOPK_OFF;
+      const float v = o[j];
+      const int i = __float_as_int(o[REC_MAX_TOPK + j]);
+      if (i != 0x7fffffff && better(lastv, lasti, v, i) && better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == k) { cv = bv; ci = bi; }
+    lastv = bv; lasti = bi;
+  }
+  const float ex = exact_arg_score(R, ci == 0x7fffffff ? vocab_lo : ci, vocab_lo, Vloc, R.h + (int64_t)row * D, D, lane);
+  float bv = (lane < REC_ARG_CAND && ci != 0x7fffffff) ? ex : REC_NEG_INF;
+  int bi = (lane < REC_ARG_CAND) ? ci : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  out_v = bv; out_i = bi;
+}
+
+// Orders the (<= 32) re-scored candidates of a row, one per lane, by (score desc, id asc) and writes the best
+// `topk` of them; slots without a candidate get (-FLT_MAX, 0x7fffffff) like an exhausted selection round.
+__device__ __forceinline__ void write_ranked(float v, int i, bool valid, int topk, int lane, int64_t row,
+                                             int32_t *__restrict__ row_ids, float *__restrict__ row_topv, float *sm) {
+  if (!valid) { v = REC_NEG_INF; i = 0x7fffffff; }
+  int rank = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float ov = __shfl_sync(0xffffffffu, v, j);
+    const int oi = __shfl_sync(0xffffffffu, i, j);
+    rank += better(ov, oi, v, i) ? 1 : 0;
+  }
+  const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+  int slot = -1;
+  if (valid && rank < topk) slot = rank;
+  else if (!valid && lane >= n_valid && lane < topk) slot = lane;
+  if (slot >= 0) {
+    row_ids[row * REC_MAX_TOPK + slot] = i; row_topv[row * REC_MAX_TOPK + slot] = v;
+    if (sm) { sm[PART_TOPK_OFF + slot] = v; sm[PART_TOPK_OFF + REC_MAX_TOPK + slot] = __int_as_float(i); }
+  }
+}
+
 __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict__ part, int part_stride, int n_split,
                                                          int B, int topk, int has_stats, int has_arg,
                                                          float *__restrict__ row_stats, int32_t *__restrict__ row_ids,
                                                          float *__restrict__ row_topv, int32_t *__restrict__ astar,
-                                                         float *__restrict__ summary) {
+                                                         float *__restrict__ summary, RescoreSrc R, int D, int vocab_lo,
+                                                         int Vloc) {
   // `summary` (optional): the merged result re-packed as ONE record per row in the partial-record
   // format, so that a second merge over the all-gathered summaries of all vocabulary shards
   // (n_split = number of shards) finishes the reduction across GPUs with this same kernel.
@@ -289,17 +398,21 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
   if (has_arg) {
     float bv = REC_NEG_INF;
     int bi = 0x7fffffff;
-    for (int sp = lane; sp < n_split; sp += 32) {
-      const float *o = part + ((int64_t)sp * B + row) * part_stride;
-      float v = o[3];
-      int i = __float_as_int(o[4]);
-      if (better(v, i, bv, bi)) { bv = v; bi = i; }
-    }
+    if (R.approx && R.apub > 0) {
+      merge_arg_rescored(part, part_stride, n_split, B, row, R, vocab_lo, Vloc, D, lane, bv, bi);
+    } else {
+      for (int sp = lane; sp < n_split; sp += 32) {
+        const float *o = part + ((int64_t)sp * B + row) * part_stride;
+        float v = o[3];
+        int i = __float_as_int(o[4]);
+        if (better(v, i, bv, bi)) { bv = v; bi = i; }
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
     }
     if (lane == 0) {
       rs[2] = bv; rs[3] = __int_as_float(bi); astar[row] = bi;
@@ -307,15 +420,17 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
     }
   }
   if (topk > 0) {
-    // K selection rounds over n_split*topk candidates; "taken" = not after the last pick in the order
-    float lastv = 3.402823466e+38f;
-    int lasti = -1;
-    const int n = n_split * topk;
-    for (int k = 0; k < topk; ++k) {
+    // selection rounds over n_split*kpub candidates; "taken" = not after the last pick in the order.
+    // Approximate scores: rec_kt(topk) rounds, lane k keeps the k-th pick for the fp32 re-score.
+    float lastv = 3.402823466e+38f, cv = REC_NEG_INF;
+    int lasti = -1, ci = 0x7fffffff;
+    const int kpub = R.kpub, n = n_split * kpub;
+    const int kt = R.approx ? rec_kt(topk) : topk;
+    for (int k = 0; k < kt; ++k) {
       float bv = REC_NEG_INF;
       int bi = 0x7fffffff;
       for (int c = lane; c < n; c += 32) {
-        int sp = c / topk, j = c - sp * topk;
+        int sp = c / kpub, j = c - sp * kpub;
         const float *o = part + ((int64_t)sp * B + row) * part_stride + PART_TOPK_OFF;
         float v = o[j];
         int i = __float_as_int(o[REC_MAX_TOPK + j]);
@@ -327,11 +442,18 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
         int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
       }
-      if (lane == 0) {
+      if (R.approx) {
+        if (lane == k) { cv = bv; ci = bi; }
+      } else if (lane == 0) {
         row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv;
         if (sm) { sm[PART_TOPK_OFF + k] = bv; sm[PART_TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(bi); }
       }
       lastv = bv; lasti = bi;
+    }
+    if (R.approx) {
+      const bool valid = lane < kt && ci != 0x7fffffff;
+      const float ex = exact_row_dot(R.w[0], R.b[0], valid ? (int64_t)ci - vocab_lo : 0, R.h + (int64_t)row * D, D, lane);
+      write_ranked(ex, ci, valid, topk, lane, row, row_ids, row_topv, sm);
     }
   }
 }
@@ -343,40 +465,62 @@ __global__ void __launch_bounds__(128) head_merge_small_kernel(const float *__re
                                                                int B, int topk, int has_stats, int has_arg,
                                                                float *__restrict__ row_stats, int32_t *__restrict__ row_ids,
                                                                float *__restrict__ row_topv, int32_t *__restrict__ astar,
-                                                               float *__restrict__ summary) {
-  constexpr int R = 5;
+                                                               float *__restrict__ summary, RescoreSrc R, int D,
+                                                               int vocab_lo, int Vloc) {
+  constexpr int R5 = 5, KP4 = 4;  // records per lane, candidate slots per record held in registers
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   float *rs = row_stats + (int64_t)row * ROW_STRIDE;
   float *sm = summary ? summary + (int64_t)row * part_stride : nullptr;
-  float4 a[R];
-  float a4[R], tv[R][2];
-  int ti[R][2];
+  const bool arg_cand = has_arg && R.approx && R.apub > 0;
+  const int np = arg_cand ? R.apub : (topk > 0 ? R.kpub : 0);  // <= KP4 (checked by the launcher)
+  float4 a[R5];
+  float a4[R5], tv[R5][KP4];
+  int ti[R5][KP4];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
+  for (int r = 0; r < R5; ++r) {
     const int sp = lane + 32 * r;
     a[r] = make_float4(REC_NEG_INF, 0.f, REC_NEG_INF, REC_NEG_INF);
     a4[r] = __int_as_float(0x7fffffff);
-    tv[r][0] = tv[r][1] = REC_NEG_INF;
-    ti[r][0] = ti[r][1] = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < KP4; ++j) { tv[r][j] = REC_NEG_INF; ti[r][j] = 0x7fffffff; }
     if (sp < n_split) {
       const float *o = part + ((int64_t)sp * B + row) * part_stride;
       a[r] = *reinterpret_cast<const float4 *>(o);
       a4[r] = o[4];
-      if (topk > 0) { tv[r][0] = o[PART_TOPK_OFF]; ti[r][0] = __float_as_int(o[PART_TOPK_OFF + REC_MAX_TOPK]); }
-      if (topk > 1) { tv[r][1] = o[PART_TOPK_OFF + 1]; ti[r][1] = __float_as_int(o[PART_TOPK_OFF + REC_MAX_TOPK + 1]); }
+#pragma unroll
+      for (int j = 0; j < KP4; ++j)
+        if (j < np) { tv[r][j] = o[PART_TOPK_OFF + j]; ti[r][j] = __float_as_int(o[PART_TOPK_OFF + REC_MAX_TOPK + j]); }
     }
   }
+  // one selection round over the register-held candidates: best entry strictly after (lastv, lasti) in the order
+  auto select_next = [&](float lastv, int lasti, float &bv, int &bi) {
+    bv = REC_NEG_INF; bi = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < R5; ++r)
+#pragma unroll
+      for (int j = 0; j < KP4; ++j) {
+        const float v = tv[r][j];
+        const int i = ti[r][j];
+        if (i != 0x7fffffff && better(lastv, lasti, v, i) && better(v, i, bv, bi)) { bv = v; bi = i; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+  };
   if (has_stats) {
     float m = REC_NEG_INF, tg = REC_NEG_INF;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { m = fmaxf(m, a[r].x); tg = fmaxf(tg, a[r].z); }
+    for (int r = 0; r < R5; ++r) { m = fmaxf(m, a[r].x); tg = fmaxf(tg, a[r].z); }
     m = warp_max(m);
     tg = warp_max(tg);
     float ssum = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int r = 0; r < R5; ++r)
       if (lane + 32 * r < n_split && a[r].y > 0.f) ssum += a[r].y * __expf(a[r].x - m);
     ssum = warp_sum(ssum);
     if (lane == 0) {
@@ -388,11 +532,25 @@ __global__ void __launch_bounds__(128) head_merge_small_kernel(const float *__re
   if (has_arg) {
     float bv = REC_NEG_INF;
     int bi = 0x7fffffff;
+    if (arg_cand) {
+      float lastv = 3.402823466e+38f, cv = REC_NEG_INF;
+      int lasti = -1, ci = 0x7fffffff;
+      for (int k = 0; k < REC_ARG_CAND; ++k) {
+        float sv; int si;
+        select_next(lastv, lasti, sv, si);
+        if (lane == k) { cv = sv; ci = si; }
+        lastv = sv; lasti = si;
+      }
+      const float ex = exact_arg_score(R, ci == 0x7fffffff ? vocab_lo : ci, vocab_lo, Vloc, R.h + (int64_t)row * D, D, lane);
+      bv = (lane < REC_ARG_CAND && ci != 0x7fffffff) ? ex : REC_NEG_INF;
+      bi = (lane < REC_ARG_CAND) ? ci : 0x7fffffff;
+    } else {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float v = a[r].w;
-      const int i = __float_as_int(a4[r]);
-      if (lane + 32 * r < n_split && better(v, i, bv, bi)) { bv = v; bi = i; }
+      for (int r = 0; r < R5; ++r) {
+        const float v = a[r].w;
+        const int i = __float_as_int(a4[r]);
+        if (lane + 32 * r < n_split && better(v, i, bv, bi)) { bv = v; bi = i; }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -405,31 +563,25 @@ __global__ void __launch_bounds__(128) head_merge_small_kernel(const float *__re
       if (sm) { sm[3] = bv; sm[4] = __int_as_float(bi); }
     }
   }
-  if (topk > 0) {
-    float lastv = 3.402823466e+38f;
-    int lasti = -1;
-    for (int k = 0; k < topk; ++k) {
-      float bv = REC_NEG_INF;
-      int bi = 0x7fffffff;
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float v = tv[r][j];
-          const int i = ti[r][j];
-          if (j < topk && i != 0x7fffffff && better(lastv, lasti, v, i) && better(v, i, bv, bi)) { bv = v; bi = i; }
-        }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == 0) {
+  if (topk > 0 && !arg_cand) {
+    float lastv = 3.402823466e+38f, cv = REC_NEG_INF;
+    int lasti = -1, ci = 0x7fffffff;
+    const int kt = R.approx ? rec_kt(topk) : topk;
+    for (int k = 0; k < kt; ++k) {
+      float bv; int bi;
+      select_next(lastv, lasti, bv, bi);
+      if (R.approx) {
+        if (lane == k) { cv = bv; ci = bi; }
+      } else if (lane == 0) {
         row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv;
         if (sm) { sm[PART_TOPK_OFF + k] = bv; sm[PART_TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(bi); }
       }
       lastv = bv; lasti = bi;
+    }
+    if (R.approx) {
+      const bool valid = lane < kt && ci != 0x7fffffff;
+      const float ex = exact_row_dot(R.w[0], R.b[0], valid ? (int64_t)ci - vocab_lo : 0, R.h + (int64_t)row * D, D, lane);
+      write_ranked(ex, ci, valid, topk, lane, row, row_ids, row_topv, sm);
     }
   }
 }
@@ -496,10 +648,11 @@ struct QRowArgs {
   const int64_t *a, *s, *div_lens;
   const float *r_acc; const uint8_t *is_end;
   const int32_t *row_ids;            // merged top-k ids of the supervised logits (SMORL rewards)
-  int B, D, L, N, Vloc, vocab_lo, n_q;
+  int B, D, L, N, V, Vloc, vocab_lo, n_q;
   float alpha_eff;
   float *row_stats; int32_t *astar;
   float *q_sa, *q_boot, *dq, *q_loss_rows, *rewards, *dh_slice;
+  RescoreSrc R;                      // greedy-action candidates: fp32 re-score on main(s') when R.approx
 };
 
 __global__ void __launch_bounds__(256) q_rows_fused_kernel(QRowArgs A, rec_train_hparams hp) {
@@ -507,20 +660,24 @@ __global__ void __launch_bounds__(256) q_rows_fused_kernel(QRowArgs A, rec_train
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= A.B) return;
   const int D = A.D, n_q = A.n_q;
-  // (1) greedy action: merge of the per-split argmax records
+  // (1) greedy action: merge of the per-split argmax records (approximate scores: fp32 re-score of the best few)
   float bv = REC_NEG_INF;
   int bi = 0x7fffffff;
-  for (int sp = lane; sp < A.n_split; sp += 32) {
-    const float *o = A.part + ((int64_t)sp * A.B + b) * A.part_stride;
-    float v = o[3];
-    int i = __float_as_int(o[4]);
-    if (better(v, i, bv, bi)) { bv = v; bi = i; }
-  }
+  if (A.R.approx && A.R.apub > 0) {
+    merge_arg_rescored(A.part, A.part_stride, A.n_split, A.B, b, A.R, A.vocab_lo, A.Vloc, D, lane, bv, bi);
+  } else {
+    for (int sp = lane; sp < A.n_split; sp += 32) {
+      const float *o = A.part + ((int64_t)sp * A.B + b) * A.part_stride;
+      float v = o[3];
+      int i = __float_as_int(o[4]);
+      if (better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
   }
   if (lane == 0) {
     float *rs = A.row_stats + (int64_t)b * ROW_STRIDE;
@@ -548,9 +705,9 @@ __global__ void __launch_bounds__(256) q_rows_fused_kernel(QRowArgs A, rec_train
   if (n_q == 3) {
     const int32_t *ids = A.row_ids + (int64_t)b * REC_MAX_TOPK;
     int last = last_action_of(A.s, A.div_lens, b, A.L, A.N, hp.pad_pos_end);
-    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, A.N, lane);
+    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, A.N, lane, A.V);
     float nov = 0.f;
-    for (int j = 0; j < hp.topk_nov; ++j) nov += hp.unpopular[ids[j]] ? hp.nov_reward : 0.f;
+    for (int j = 0; j < hp.topk_nov; ++j) nov += ((unsigned)ids[j] < (unsigned)A.V && hp.unpopular[ids[j]]) ? hp.nov_reward : 0.f;
     r[2] = nov / (float)hp.topk_nov;
   }
   // (4) TD target, dq, per-row loss (every lane computes the same scalars)
@@ -592,15 +749,17 @@ __global__ void __launch_bounds__(128) q_rows_fused_small_kernel(QRowArgs A, rec
   if (b >= A.B) return;
   const int D = A.D, n_q = A.n_q;
   // round trip 1: records, a_b, lengths, reward inputs
-  float rv[R];
-  int ri[R];
+  const bool cand = A.R.approx && A.R.apub > 0;  // records carry two approximate candidates each (tensor-core pass)
+  float rv[R], rv2[R];
+  int ri[R], ri2[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int sp = lane + 32 * r;
-    rv[r] = REC_NEG_INF; ri[r] = 0x7fffffff;
+    rv[r] = REC_NEG_INF; ri[r] = 0x7fffffff; rv2[r] = REC_NEG_INF; ri2[r] = 0x7fffffff;
     if (sp < A.n_split) {
       const float *o = A.part + ((int64_t)sp * A.B + b) * A.part_stride;
       rv[r] = o[3]; ri[r] = __float_as_int(o[4]);
+      if (cand) { rv2[r] = o[PART_TOPK_OFF + 1]; ri2[r] = __float_as_int(o[PART_TOPK_OFF + REC_MAX_TOPK + 1]); }
     }
   }
   const int64_t loc_a = A.a[b] - A.vocab_lo;
@@ -635,9 +794,35 @@ __global__ void __launch_bounds__(128) q_rows_fused_small_kernel(QRowArgs A, rec
   // (1) greedy action
   float bv = REC_NEG_INF;
   int bi = 0x7fffffff;
+  if (cand) {
+    // best REC_ARG_CAND candidates by approximate score -> exact fp32 score on main(s') -> (score desc, id asc)
+    float lastv = 3.402823466e+38f, cv = REC_NEG_INF;
+    int lasti = -1, ci = 0x7fffffff;
+    for (int k = 0; k < REC_ARG_CAND; ++k) {
+      float sv = REC_NEG_INF;
+      int si = 0x7fffffff;
 #pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (lane + 32 * r < A.n_split && better(rv[r], ri[r], bv, bi)) { bv = rv[r]; bi = ri[r]; }
+      for (int r = 0; r < R; ++r) {
+        if (ri[r] != 0x7fffffff && better(lastv, lasti, rv[r], ri[r]) && better(rv[r], ri[r], sv, si)) { sv = rv[r]; si = ri[r]; }
+        if (ri2[r] != 0x7fffffff && better(lastv, lasti, rv2[r], ri2[r]) && better(rv2[r], ri2[r], sv, si)) { sv = rv2[r]; si = ri2[r]; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, sv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, si, o);
+        if (better(ov, oi, sv, si)) { sv = ov; si = oi; }
+      }
+      if (lane == k) { cv = sv; ci = si; }
+      lastv = sv; lasti = si;
+    }
+    const float ex = exact_arg_score(A.R, ci == 0x7fffffff ? A.vocab_lo : ci, A.vocab_lo, A.Vloc, A.R.h + (int64_t)b * D, D, lane);
+    bv = (lane < REC_ARG_CAND && ci != 0x7fffffff) ? ex : REC_NEG_INF;
+    bi = (lane < REC_ARG_CAND) ? ci : 0x7fffffff;
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (lane + 32 * r < A.n_split && better(rv[r], ri[r], bv, bi)) { bv = rv[r]; bi = ri[r]; }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -658,9 +843,9 @@ __global__ void __launch_bounds__(128) q_rows_fused_small_kernel(QRowArgs A, rec
   float r[3] = {r_acc, 0.f, 0.f};
   if (n_q == 3) {
     const int32_t *ids = A.row_ids + (int64_t)b * REC_MAX_TOPK;
-    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, A.N, lane);
+    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, A.N, lane, A.V);
     float nov = 0.f;
-    for (int j = 0; j < hp.topk_nov; ++j) nov += hp.unpopular[ids[j]] ? hp.nov_reward : 0.f;
+    for (int j = 0; j < hp.topk_nov; ++j) nov += ((unsigned)ids[j] < (unsigned)A.V && hp.unpopular[ids[j]]) ? hp.nov_reward : 0.f;
     r[2] = nov / (float)hp.topk_nov;
   }
   // (2) Q(s,a) and Q_boot(s',a*)
@@ -956,19 +1141,42 @@ int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
                                                 a.w[2], e->part, e->part_stride);
   REC_LAUNCH_CHECK(e);
   *n_split_out = n_split;
+  e->st_approx = false;  // fp32 FFMA scores: ranked as they are
+  e->st_kpub = a.topk;
+  e->st_apub = 0;
   return REC_OK;
 }
 
+static RescoreSrc rescore_src(const rec_engine *e, const HeadStatsArgs *src, int topk) {
+  RescoreSrc R = {};
+  R.kpub = topk;
+  if (!src) return R;  // exact per-shard summaries (cross-GPU merge)
+  const rec_net_params &p = e->nets[src->net_id].p;
+  R.h = src->h;
+  R.n_arg = src->n_arg;
+  if (src->n_arg > 0) {
+    for (int j = 0; j < src->n_arg && j < 3; ++j) { R.w[j] = p.head_w[1 + j]; R.b[j] = p.head_b[1 + j]; R.wq[j] = src->w[j]; }
+  } else {
+    R.w[0] = p.head_w[src->stats_head]; R.b[0] = p.head_b[src->stats_head];
+  }
+  R.approx = e->st_approx ? 1 : 0;
+  R.kpub = topk > 0 ? e->st_kpub : 0;
+  R.apub = e->st_apub;
+  return R;
+}
+
 int launch_head_merge(rec_engine *e, const float *part, int n_split, int B, int topk, bool has_stats, bool has_arg,
-                      float *summary) {
-  if (n_split <= 160 && topk <= 2 && (e->part_stride & 3) == 0)
+                      float *summary, const HeadStatsArgs *src) {
+  const RescoreSrc R = rescore_src(e, src, topk);
+  if (R.approx && has_arg && topk > 0) REC_FAIL(e, REC_EINVAL, "head merge: a record holds either top-k or greedy-action candidates");
+  if (n_split <= 160 && topk <= 2 && (e->part_stride & 3) == 0 && R.kpub <= 4 && R.apub <= 4)
     head_merge_small_kernel<<<cdiv(B, 4), 128, 0, e->stream>>>(part, e->part_stride, n_split, B, topk, has_stats ? 1 : 0,
                                                               has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv,
-                                                              e->astar, summary);
+                                                              e->astar, summary, R, e->D, e->cfg.vocab_lo, e->Vloc);
   else
     head_merge_kernel<<<cdiv(B, 8), 256, 0, e->stream>>>(part, e->part_stride, n_split, B, topk, has_stats ? 1 : 0,
                                                         has_arg ? 1 : 0, e->row_stats, e->row_ids, e->row_topv, e->astar,
-                                                        summary);
+                                                        summary, R, e->D, e->cfg.vocab_lo, e->Vloc);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
 }
@@ -1003,15 +1211,16 @@ int head_bwd_dense_slices(const rec_engine *e, int B) {
 
 // Fused per-row Q path of the single-GPU step (see q_rows_fused_kernel).
 int launch_q_rows_fused(rec_engine *e, int main_net, const rec_batch *b, const rec_train_hparams *hp, int n_split,
-                        float alpha_eff, float *q_loss_rows) {
+                        float alpha_eff, float *q_loss_rows, const HeadStatsArgs *src) {
   const int B = b->B;
   QRowArgs A;
+  A.R = rescore_src(e, src, 0);
   A.part = e->part; A.part_stride = e->part_stride; A.n_split = n_split;
   A.main_heads = head_ptrs(e, main_net); A.boot_heads = head_ptrs(e, 1 - main_net);
   A.h_main = e->h_state[0]; A.h_boot = e->h_state[2];
   A.a = b->a; A.s = b->s; A.div_lens = b->true_next_len;  // (q2) the reference indexes s with true_next_len
   A.r_acc = b->r; A.is_end = b->is_end; A.row_ids = e->row_ids;
-  A.B = B; A.D = e->D; A.L = e->cfg.state_size; A.N = e->cfg.item_num; A.Vloc = e->Vloc; A.vocab_lo = e->cfg.vocab_lo;
+  A.B = B; A.D = e->D; A.L = e->cfg.state_size; A.N = e->cfg.item_num; A.V = e->cfg.action_dim; A.Vloc = e->Vloc; A.vocab_lo = e->cfg.vocab_lo;
   A.n_q = e->cfg.n_heads - 1; A.alpha_eff = alpha_eff;
   A.row_stats = e->row_stats; A.astar = e->astar;
   A.q_sa = e->q_sa; A.q_boot = e->q_boot; A.dq = e->dq; A.q_loss_rows = q_loss_rows; A.rewards = e->rewards;
@@ -1051,10 +1260,10 @@ int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_bat
     const int n_tiles = cdiv(e->Vloc, TN);
     size_t smem = head_bwd_smem_bytes(e->D);
     if (smem > 220 * 1024) REC_FAIL(e, REC_EINVAL, "head backward needs %zu B of shared memory (D=%d too large)", smem, e->D);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[REC_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
+    if (!attr_set[e->dev]) {
       REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set = true;
+      attr_set[e->dev] = true;
     }
     dim3 grid(head_bwd_dense_slices(e, B), 1);
     head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
@@ -1070,11 +1279,8 @@ int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_bat
 int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                           float bc2_sqrt, const rec_train_hparams *hp, int wait_mark) {
   if (e->cfg.n_heads < 2) return REC_OK;
-  if (e->timing) cudaEventRecord(e->ev[6], e->stream);
-  int rc = launch_q_heads_adam(e, net_id, h, b, B, step_size, bc2_sqrt, hp, wait_mark);
-  if (rc) return rc;
-  if (e->timing) cudaEventRecord(e->ev[7], e->stream);
-  return REC_OK;
+  // kernel-timing mode: the events of slot 3 bracket the adam_stream_kernel launch alone (embed.cu)
+  return launch_q_heads_adam(e, net_id, h, b, B, step_size, bc2_sqrt, hp, wait_mark);
 }
 
 int launch_dh_reduce(rec_engine *e, int B) {

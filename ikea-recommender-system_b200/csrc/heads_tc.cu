@@ -579,27 +579,36 @@ __global__ void __launch_bounds__(NT + (RING ? (ARG ? 64 : 128) : 32), 1) head_s
       const int r = q * 32 + lane, row = b0 + nb * 128 + r;
       if (row >= B) continue;
       const float *x = xch + ((nb * 128 + r) * CS) * 5;
-      float m = REC_NEG_INF, tg = REC_NEG_INF, bv = REC_NEG_INF;
-      int bi = 0x7fffffff;
+      float m = REC_NEG_INF, tg = REC_NEG_INF, bv = REC_NEG_INF, bv2 = REC_NEG_INF;
+      int bi = 0x7fffffff, bi2 = 0x7fffffff;
 #pragma unroll
       for (int c = 0; c < CS; ++c) {
         m = fmaxf(m, x[c * 5]);
         tg = fmaxf(tg, x[c * 5 + 2]);
         const float v = x[c * 5 + 3];
         const int i = __float_as_int(x[c * 5 + 4]);
-        if (better(v, i, bv, bi)) { bv = v; bi = i; }
+        if (better(v, i, bv, bi)) { bv2 = bv; bi2 = bi; bv = v; bi = i; }
+        else if (better(v, i, bv2, bi2)) { bv2 = v; bi2 = i; }
       }
       float ssum = 0.f;
 #pragma unroll
       for (int c = 0; c < CS; ++c) if (x[c * 5 + 1] > 0.f) ssum += x[c * 5 + 1] * __expf(x[c * 5] - m);
       float *o = part + ((int64_t)sp * B + row) * part_stride;
       o[0] = m; o[1] = ssum; o[2] = tg; o[3] = bv; o[4] = __int_as_float(bi);
+      if (ARG) {
+        // greedy action: the scores are bf16x3 products -- publish the two best of the CS per-thread maxima as
+        // candidates; the merge re-scores the best REC_ARG_CAND of all records in fp32 (common.cuh: rec_kpub)
+        o[PART_TOPK_OFF] = bv; o[PART_TOPK_OFF + REC_MAX_TOPK] = __int_as_float(bi);
+        o[PART_TOPK_OFF + 1] = bv2; o[PART_TOPK_OFF + REC_MAX_TOPK + 1] = __int_as_float(bi2);
+      }
       if (!ARG && topk > 0) {
-        // CS-way merge of the sorted private lists (ids of different splits are disjoint)
+        // CS-way merge of the sorted private lists (ids of different splits are disjoint); rec_kpub(topk, CS) >= topk
+        // entries leave the CTA so that the fp32 re-score of the final merge has a margin of candidates
+        const int kpub = rec_kpub(topk, CS);
         int pos[CS];
 #pragma unroll
         for (int c = 0; c < CS; ++c) pos[c] = 0;
-        for (int k = 0; k < topk; ++k) {
+        for (int k = 0; k < kpub; ++k) {
           float cv = REC_NEG_INF;
           int ci = 0x7fffffff, cc = 0;
 #pragma unroll
@@ -646,10 +655,10 @@ bool tc_heads_supported(const rec_engine *e) { return e->D == 64 && e->use_tc; }
 // Same contract as launch_head_stats (heads.cu); *n_split_out counts records per row (one per CTA column).
 template <int NB, int NT, bool ARG, bool RING>
 static int launch_stats_tc_kernel(rec_engine *e, const HeadStatsArgs &a, dim3 grid, size_t smem, int n_tiles, int topk, int n_slots) {
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  static size_t attr_smem[REC_MAX_DEVICES] = {};
+  if (smem > attr_smem[e->dev]) {
     REC_CUDA(e, cudaFuncSetAttribute(head_stats_tc_kernel<NB, NT, ARG, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+    attr_smem[e->dev] = smem;
   }
   head_stats_tc_kernel<NB, NT, ARG, RING><<<grid, NT + (RING ? (ARG ? 64 : 128) : 32), smem, e->stream>>>(
       tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo, n_tiles, ARG ? 0 : a.do_stats, ARG ? 1 : a.stats_head,
@@ -681,6 +690,9 @@ static int launch_stats_tc_variant(rec_engine *e, const HeadStatsArgs &a, int *n
   if (n_slots > 4) n_slots = 4;
   dim3 grid(n_split, ng);
   *n_split_out = n_split;
+  e->st_approx = true;
+  e->st_kpub = topk > 0 ? rec_kpub(topk, NT / 128) : 0;
+  e->st_apub = ARG ? 2 : 0;
   if (RING_OK && n_slots > 0)
     return launch_stats_tc_kernel<NB, NT, ARG, RING_OK>(e, a, grid, base_ring + (size_t)n_slots * 32768, n_tiles, topk, n_slots);
   return launch_stats_tc_kernel<NB, NT, ARG, false>(e, a, grid, smem_plain, n_tiles, topk, 0);
@@ -1180,10 +1192,10 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   const int n_cta = tc_bwd_slices(e);
   // operands 12 x 16 KB, ones 4 KB, bias / double-buffered lse / targets 5 KB, Adam warps' transpose staging 20 KB
   const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072 + 2048 + 8 * 32 * 20 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[REC_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
+  if (!attr_set[e->dev]) {
     REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[e->dev] = true;
   }
   if (!e->hpack_ready) {
     h_prepack_kernel<<<cdiv(B, 128), 256, 0, e->stream>>>(h, B, e->hpack);

@@ -13,7 +13,7 @@
 
 // ---- training-time rewards + TD target + Q loss gradient ------------------------------------------
 // One warp per row.  rewards r = [r_acc, r_div, r_nov] (SMORL, n_q = 3) or [r] (SQN, n_q = 1).
-__global__ void __launch_bounds__(256) td_kernel(int B, int L, int N, int n_q, const float *__restrict__ r_acc,
+__global__ void __launch_bounds__(256) td_kernel(int B, int L, int N, int V, int n_q, const float *__restrict__ r_acc,
                                                  const uint8_t *__restrict__ is_end,
                                                  const float *__restrict__ q_sa, const float *__restrict__ q_boot,
                                                  const int64_t *__restrict__ s, const int64_t *__restrict__ div_lens,
@@ -27,9 +27,9 @@ __global__ void __launch_bounds__(256) td_kernel(int B, int L, int N, int n_q, c
   if (n_q == 3) {
     const int32_t *ids = row_ids + (int64_t)b * REC_MAX_TOPK;
     int last = last_action_of(s, div_lens, b, L, N, hp.pad_pos_end);
-    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, N, lane);
+    r[1] = diversity_reward_warp(hp.div_emb, hp.div_dim, last, ids, hp.topk_div, hp.out_to_in, N, lane, V);
     float nov = 0.f;
-    for (int j = 0; j < hp.topk_nov; ++j) nov += hp.unpopular[ids[j]] ? hp.nov_reward : 0.f;
+    for (int j = 0; j < hp.topk_nov; ++j) nov += ((unsigned)ids[j] < (unsigned)V && hp.unpopular[ids[j]]) ? hp.nov_reward : 0.f;
     r[2] = nov / (float)hp.topk_nov;
   }
   if (lane == 0) {
@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(256) eval_rows_kernel(int B, int L, int N, int
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int32_t *ids = row_ids + (int64_t)b * REC_MAX_TOPK;
-  const int my = lane < kmax ? ids[lane] : -1;
+  int my = lane < kmax ? ids[lane] : -1;
+  if (my >= V) my = -1;  // exhausted top-k slot (fewer than kmax actions exist)
   double *out = rowm + (int64_t)b * M;
   // HR / NDCG: rank of the true action inside the top-k list
   const int64_t truth = a[b];
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) eval_rows_kernel(int B, int L, int N, int
   float div = 0.f;
   if (o.div_emb) {
     int last = last_action_of(s, lens, b, L, N, o.pad_pos_end);
-    div = diversity_reward_warp(o.div_emb, o.div_dim, last, ids, o.topk_div, o.out_to_in, N, lane);
+    div = diversity_reward_warp(o.div_emb, o.div_dim, last, ids, o.topk_div, o.out_to_in, N, lane, V);
   }
   if (lane == 0) {
     for (int i = 0; i < o.n_k; ++i) {
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256) eval_rows_kernel(int B, int L, int N, int
     double nov = 0.0;
     if (o.unpopular) {
       int cnt = 0;
-      for (int j = 0; j < o.topk_nov; ++j) cnt += o.unpopular[ids[j]] ? 1 : 0;
+      for (int j = 0; j < o.topk_nov; ++j) cnt += (ids[j] >= 0 && ids[j] < V && o.unpopular[ids[j]]) ? 1 : 0;
       nov = (double)cnt * (double)o.nov_reward / (double)o.topk_nov;
     }
     out[3 * o.n_k] = (double)div;
@@ -196,7 +197,7 @@ __global__ void copy_topk_kernel(const int32_t *__restrict__ row_ids, const floa
 // ------------------------------------------------------------------------------------------------
 int launch_td(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int n_q, float alpha_eff,
               float *q_loss_rows) {
-  td_kernel<<<cdiv(b->B, 8), 256, 0, e->stream>>>(b->B, e->cfg.state_size, e->cfg.item_num, n_q, b->r, b->is_end, e->q_sa,
+  td_kernel<<<cdiv(b->B, 8), 256, 0, e->stream>>>(b->B, e->cfg.state_size, e->cfg.item_num, e->cfg.action_dim, n_q, b->r, b->is_end, e->q_sa,
                                                  e->q_boot, b->s, b->true_next_len, e->row_ids, *hp, alpha_eff, e->dq,
                                                  q_loss_rows, e->rewards);
   REC_LAUNCH_CHECK(e);

@@ -19,7 +19,7 @@ __device__ __forceinline__ int last_action_of(const int64_t *s, const int64_t *l
 // 1 - mean_j cos(E[last], E[map(id_j)]), j < k   (CosineSimilarity(dim=2, eps=1e-6)); warp-cooperative
 __device__ __forceinline__ float diversity_reward_warp(const float *__restrict__ E, int dim, int last,
                                                        const int32_t *ids, int k, const int64_t *out_to_in,
-                                                       int N, int lane) {
+                                                       int N, int lane, int V = 0x7fffffff) {
   const float eps = 1e-6f;
   const float *x = E + (int64_t)last * dim;
   float nx = 0.f;
@@ -28,6 +28,7 @@ __device__ __forceinline__ float diversity_reward_warp(const float *__restrict__
   float sim_sum = 0.f;
   for (int j = 0; j < k; ++j) {
     int64_t id = ids[j];
+    if (id < 0 || id >= V) continue;  // exhausted top-k slot (k > V): contributes cos = 0
     if (out_to_in) id = out_to_in[id];
     id = id < 0 ? 0 : (id > N ? N : id);
     const float *y = E + id * dim;

@@ -69,6 +69,8 @@ class Engine:
         self._nets: Dict[int, NetTensors] = {}
         self._adam_steps: Dict[int, int] = {}
         self._keep = []  # keeps ctypes structs / tensors of the last call alive
+        self.generation = 0  # bumped whenever the native handle (and with it every workspace pointer) is re-created
+        self._tc_on, self._graphs_on = True, None
         self._create()
 
     # -- lifetime ----------------------------------------------------------------------------
@@ -82,6 +84,22 @@ class Engine:
             raise RuntimeError(f"rec_create failed (rc={rc}): {N.last_error(self.lib, None)}")
         self.handle = h
         self._stream = stream
+        self.generation += 1
+        # settings that live in the native handle survive a re-create
+        if not self._tc_on:
+            self.lib.rec_set_tensor_cores(h, 0)
+        if self._graphs_on is not None:
+            self.lib.rec_set_cuda_graphs(h, int(self._graphs_on))
+        if self.timing:
+            self.lib.rec_enable_kernel_timing(h, 1)
+
+    def follow_stream(self):
+        """Launch on torch's CURRENT stream of the engine's device (called at the top of every compute call: work
+        issued under `with torch.cuda.stream(s)` must not race with torch's own copies / reads on `s`)."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if stream != self._stream:
+            self.lib.rec_set_stream(self.handle, C.c_void_p(stream))
+            self._stream = stream
 
     def close(self):
         if self.handle is not None:
@@ -99,6 +117,9 @@ class Engine:
         return self.cfg["max_batch"]
 
     def ensure_batch(self, B: int):
+        """Grows the workspace by re-creating the native handle (`generation` changes: anything that cached engine
+        pointers -- CUDA graphs captured by ShardedStep -- must be rebuilt; see ShardedStep.step)."""
+        self.follow_stream()
         if B <= self.cfg["max_batch"]:
             return
         steps = {i: int(self.lib.rec_get_adam_step(self.handle, i)) for i in self._nets}
@@ -159,6 +180,7 @@ class Engine:
         return h
 
     def head_logits(self, net_id, head, h):
+        self.follow_stream()
         B = h.shape[0]
         V = self.cfg["vocab_hi"] - self.cfg["vocab_lo"]
         out = torch.empty(B, V, device=self.device, dtype=torch.float32)
@@ -217,15 +239,18 @@ class Engine:
                 "rec_train_phase_a")
 
     def train_phase_b(self, gathered, n_shards, q_out):
+        self.follow_stream()
         N.check(self.lib, self.handle, self.lib.rec_train_phase_b(self.handle, _ptr(gathered), n_shards, _ptr(q_out)),
                 "rec_train_phase_b")
 
     def train_phase_c(self, q_reduced, losses_out, dh_out):
+        self.follow_stream()
         N.check(self.lib, self.handle,
                 self.lib.rec_train_phase_c(self.handle, _ptr(q_reduced), _ptr(losses_out), _ptr(dh_out)),
                 "rec_train_phase_c")
 
     def train_phase_d(self, dh_reduced):
+        self.follow_stream()
         N.check(self.lib, self.handle, self.lib.rec_train_phase_d(self.handle, _ptr(dh_reduced)), "rec_train_phase_d")
 
     # -- data-parallel trunk of the sharded step (see include/recsys_b200.h) ------------------------
@@ -236,24 +261,29 @@ class Engine:
         return int(self.lib.rec_dp_grad_floats(self.handle))
 
     def dp_forward(self, local_batch, main_net, packed_out):
+        self.follow_stream()
         N.check(self.lib, self.handle,
                 self.lib.rec_dp_forward(self.handle, C.byref(local_batch), main_net, _ptr(packed_out)), "rec_dp_forward")
 
     def dp_unpack(self, gathered, world, B_local, global_batch):
+        self.follow_stream()
         N.check(self.lib, self.handle,
                 self.lib.rec_dp_unpack(self.handle, _ptr(gathered), world, B_local, C.byref(global_batch)), "rec_dp_unpack")
 
     def train_phase_a_heads(self, batch, hp, main_net, records_out):
+        self.follow_stream()
         N.check(self.lib, self.handle,
                 self.lib.rec_train_phase_a_heads(self.handle, C.byref(batch), C.byref(hp), main_net, _ptr(records_out)),
                 "rec_train_phase_a_heads")
 
     def dp_backward(self, dh_reduced, rank, gru_grads_out, dx_out):
+        self.follow_stream()
         N.check(self.lib, self.handle,
                 self.lib.rec_dp_backward(self.handle, _ptr(dh_reduced), rank, _ptr(gru_grads_out), _ptr(dx_out)),
                 "rec_dp_backward")
 
     def dp_apply(self, gru_grads_reduced, dx_gathered):
+        self.follow_stream()
         N.check(self.lib, self.handle, self.lib.rec_dp_apply(self.handle, _ptr(gru_grads_reduced), _ptr(dx_gathered)),
                 "rec_dp_apply")
 
@@ -264,20 +294,24 @@ class Engine:
                                                    _ptr(records_out)), "rec_eval_shard_candidates")
 
     def eval_merge(self, batch, opts, gathered, n_shards, acc, topk_ids=None, topk_scores=None):
+        self.follow_stream()
         N.check(self.lib, self.handle,
                 self.lib.rec_eval_merge(self.handle, C.byref(batch), C.byref(opts), _ptr(gathered), n_shards,
                                         C.byref(acc), _ptr(topk_ids), _ptr(topk_scores)), "rec_eval_merge")
 
     def set_tensor_cores(self, on: bool):
+        self._tc_on = bool(on)
         self.lib.rec_set_tensor_cores(self.handle, int(on))
 
     def set_cuda_graphs(self, on: bool):
         """Replay the single-GPU train step as a CUDA graph (default on; REC_NO_GRAPH=1 disables)."""
+        self._graphs_on = bool(on)
         self.lib.rec_set_cuda_graphs(self.handle, int(on))
 
     def set_stream(self, cuda_stream: int):
         """Launch on another stream from now on (used while the sharded step is captured into a torch CUDA graph)."""
         self.lib.rec_set_stream(self.handle, C.c_void_p(cuda_stream))
+        self._stream = cuda_stream
 
     def launch_count(self):
         """Kernels launched by this engine, including those replayed from caller-captured graphs."""

@@ -295,16 +295,32 @@ class NativeTrainerBase:
         self._loss_dev = None
         self._pending_steps = [0 for _ in nets]
         self._shard = None
+        self._fast_bind = None
 
     @staticmethod
     def _seed(torch_rand_seed, python_rand_seed):
         torch.manual_seed(torch_rand_seed)
         random.seed(python_rand_seed)
 
+    def _drop_engine(self):
+        """Forget the native engine (parameter storage moved / was re-sharded).  The Adam step counters live in
+        the engine: read them back first, or the next engine would restart bias correction at t = 1 on warm
+        moments (and repeat the step-keyed dropout masks)."""
+        if self._engine is not None and self._engine.handle is not None:
+            for i in range(len(self._nets)):
+                self._pending_steps[i] = self._engine.adam_step(i)
+        self._engine = None
+        self._fast_bind = None
+
     def send_to_device(self):
+        dev = torch.device(self.device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if all(p.device == dev for n in self._nets for p in n._param_objects()):
+            return  # already resident: the engine, its bound pointers and the optimizer state stay valid
+        self._drop_engine()
         for n in self._nets:
             n.to(self.device)
-        self._engine = None  # pointers changed
 
     _FULL_CHECK_EVERY = 64
 
@@ -331,9 +347,9 @@ class NativeTrainerBase:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         if self._nets[0]._param_device() != dev:
+            self._drop_engine()
             for n in self._nets:
                 n.to(dev)
-            self._engine = None
         if self._engine is None:
             n0 = self._nets[0]
             self._engine = Engine(item_num=n0.item_num, action_dim=n0.action_dim, embedding_dim=n0.embedding_dim,
@@ -367,10 +383,10 @@ class NativeTrainerBase:
         from ..sharded import shard_bounds
         V = self._nets[0].action_dim
         lo, hi = shard_bounds(V, rank, world)
+        self._drop_engine()
         for n in self._nets:
             n.shard_vocabulary(lo, hi, group)
         self._shard = (rank, world, group)
-        self._engine = None
 
     def _set_mode(self, train: bool):
         for n in self._nets:

@@ -15,13 +15,26 @@ import torch
 from ... import _native as N
 from ...engine import EvalAccumulators
 
-_cache = {}
+class _LRU(dict):
+    """Small bounded cache of device-side lookup tables (diversity table, unpopular bitmap, token LUT)."""
+
+    MAX = 16
+
+    def __setitem__(self, k, v):
+        if len(self) >= self.MAX and k not in self:
+            self.pop(next(iter(self)))
+        super().__setitem__(k, v)
+
+
+_cache = _LRU()
 
 
 def _as_div_table(diversity_embedding, device):
     """Frozen nn.Embedding (or tensor) -> contiguous fp32 table on `device` (cached by storage)."""
     w = diversity_embedding.weight if hasattr(diversity_embedding, "weight") else diversity_embedding
-    key = ("div", w.data_ptr(), str(device))
+    if w.is_cuda and w.device == torch.device(device) and w.dtype == torch.float32 and w.is_contiguous():
+        return w.detach()  # used in place: no copy to go stale
+    key = ("div", w.data_ptr(), int(getattr(w, "_version", 0)), tuple(w.shape), str(device))
     if key not in _cache:
         _cache[key] = (w, w.detach().to(device=device, dtype=torch.float32).contiguous())
     return _cache[key][1]
@@ -96,6 +109,29 @@ def _coverage(cov_bits, topk_cov, unpop_bitmap_np, num_actions, n_unpop):
     return res
 
 
+def _eval_one_batch(model, eng, batch, o, acc, kmax, topk_ids=None, virtual_gather=None):
+    """One fused evaluation batch.  On a vocabulary-sharded model (SURVEY 8e "collectives for eval", BASELINE
+    configs[4]): every rank scores the batch against its vocabulary slice and publishes ONE record per row
+    (max, sum-exp, target logit, its fp32-exact top-k candidates) -> one all-gather of the records -> every rank
+    merges them ((score desc, id asc), log-sum-exp combine) and accumulates the metrics.  Inputs and therefore the
+    merged results are replicated, so the coverage bitmaps / accumulators need no further reduction."""
+    if not model.is_sharded:
+        eng.eval_batch(model._net_id, batch, o, acc.struct, topk_ids=topk_ids)
+        return
+    import torch.distributed as dist
+    B, rec = int(batch.B), eng.record_floats()
+    dev = model._param_device()
+    records = torch.empty(B, rec, dtype=torch.float32, device=dev)
+    eng.eval_shard_candidates(model._net_id, batch, o.head_idx, kmax, records)
+    if virtual_gather is not None:  # tests: several shards living on one GPU
+        gathered = virtual_gather(records)
+    else:
+        world = dist.get_world_size(model._group)
+        gathered = torch.empty(world, B, rec, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, records, group=model._group)
+    eng.eval_merge(batch, o, gathered, int(gathered.shape[0]), acc.struct, topk_ids=topk_ids)
+
+
 def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, diversity_embedding,
              unpopular_actions_set, head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1,
              topk_to_consider_nov=1, topk_to_consider_cov=[1, 5, 10], novelty_rew_signal=1, input_tokenizer=None,
@@ -117,7 +153,7 @@ def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, 
         ds, dl = model._dev_inputs(s, s_len)
         da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         eng = model._ready(B)
-        eng.eval_batch(model._net_id, eng._batch(B, ds, da, dl), o, acc.struct)
+        _eval_one_batch(model, eng, eng._batch(B, ds, da, dl), o, acc, kmax)
         n_total += B
         n_batches += 1
     r = acc.read()
@@ -150,7 +186,7 @@ def update_train_metrics(s, a, s_len, model, device, padding_pos, diversity_embe
     ds, dl = model._dev_inputs(s, s_len)
     da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
     ids = torch.empty(B, kmax, dtype=torch.int32, device=dev)
-    eng.eval_batch(model._net_id, eng._batch(B, ds, da, dl), o, acc.struct, topk_ids=ids)
+    _eval_one_batch(model, eng, eng._batch(B, ds, da, dl), o, acc, kmax, topk_ids=ids)
     r = acc.read()
     nk = len(topk_hr_ndcg)
     ids_h = ids.cpu().numpy()

@@ -7,7 +7,7 @@ data-parallel at the input: each rank contributes its local batch, the (tiny) ba
 and every rank multiplies the full batch by its vocabulary slice.
 
 Collectives per train step (all <= 1 MB, latency-bound):
-    1. all_gather  packed int64 batch rows                     [G*B, 2L+4]
+    1. all_gather  packed local batches (rec_pack_batch: one byte buffer per rank)
     2. all_gather  per-shard head records (max, sum-exp, target logit, argmax, top-k candidates)
     3. all_reduce  Q(s,a) / Q_boot(s',a*) contributions         [2, G*B, 3]
     4. all_reduce  dL/dh partials                                [G*B, D]
@@ -26,44 +26,6 @@ from . import _native as N
 def shard_bounds(V: int, rank: int, world: int):
     """Balanced contiguous split of [0, V) (the same on every rank, no communication)."""
     return V * rank // world, V * (rank + 1) // world
-
-
-# ---- packed batch rows: one int64 row per session ------------------------------------------------
-def pack_rows(s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
-    """[B, 2L+4] int64: s | s_next | a | len | next_len | (r bits | is_end << 32)."""
-    B, L = s.shape
-    out = torch.zeros(B, 2 * L + 4, dtype=torch.int64, device=s.device)
-    out[:, :L] = s
-    out[:, 2 * L] = a
-    out[:, 2 * L + 1] = true_len
-    if r is not None:
-        out[:, L:2 * L] = s_next
-        out[:, 2 * L + 2] = true_next_len
-        rbits = r.to(torch.float32).contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
-        out[:, 2 * L + 3] = rbits | (is_end.to(torch.int64) << 32)
-    return out
-
-
-def unpack_rows(rows, L, with_q=True):
-    s = rows[:, :L].contiguous()
-    a = rows[:, 2 * L].contiguous()
-    ln = rows[:, 2 * L + 1].contiguous()
-    if not with_q:
-        return s, a, ln, None, None, None, None
-    sn = rows[:, L:2 * L].contiguous()
-    nl = rows[:, 2 * L + 2].contiguous()
-    last = rows[:, 2 * L + 3]
-    r = (last & 0xFFFFFFFF).to(torch.int32).view(torch.float32).contiguous()
-    e = ((last >> 32) & 1).to(torch.uint8).contiguous()
-    return s, a, ln, r, sn, nl, e
-
-
-def all_gather_rows(local_rows, group=None):
-    world = dist.get_world_size(group)
-    out = torch.empty(world * local_rows.shape[0], local_rows.shape[1], dtype=local_rows.dtype,
-                      device=local_rows.device)
-    dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
-    return out
 
 
 class ShardedStep:
@@ -147,6 +109,11 @@ class ShardedStep:
         else:
             N.check(eng.lib, eng.handle,
                     eng.lib.rec_pack_batch(eng.handle, C.byref(local_batch), C.c_void_p(self.packed.data_ptr())), "rec_pack_batch")
+        if eng.generation != getattr(self, "_eng_generation", None):
+            # the engine re-created its native handle (a larger batch arrived): graphs captured before that replay
+            # kernels on freed workspace pointers
+            self._graphs.clear()
+            self._eng_generation = eng.generation
         key = (int(main_net), bool(has_q), float(hp.lr), id(losses_out))
         ent = self._graphs.setdefault(key, {"seen": 0, "graph": None, "launches": 0})
         if os.environ.get("REC_NO_GRAPH") or not self.use_graphs or eng.timing:

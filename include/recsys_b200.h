@@ -274,6 +274,9 @@ float rec_last_kernel_ms(rec_engine *e, int which); /* which: 0 supervised-head 
                                                         2 embedding Adam sweep, 3 Q-heads Adam sweep,
                                                         4 supervised-head statistics (train), 5 greedy-action pass */
 
+/* Debug / tests: copies the greedy actions a*[B] (int32, global action ids) of the most recent Q step into the caller's
+ * device buffer (asynchronous on the engine's stream).  argmax of sqn_gru.py:229 / tensor_operations.py:73-84. */
+int rec_debug_copy_astar(rec_engine *e, int32_t *out, int B);
 /* Debug: device buffer [240] int64 receiving (tag, clock64) pairs of CTA 0 of the tensor-core backward kernel
  * (REC_TRACE_SEL=1: the supervised statistics kernel, =2: the greedy-action kernel). */
 int rec_debug_set_trace(rec_engine *e, long long *dev_buf);

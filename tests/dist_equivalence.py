@@ -52,6 +52,14 @@ def main():
         state = random.getstate()
         assert t.last_main == ref.last_main
         assert_close(got, want, rtol=1e-3, atol=1e-5, what=f"rank {rank} step {i} losses")
+        if os.environ.get("DIST_REGROW") and i == 8:
+            # a batch beyond the engine's max_batch re-creates the native handle: the step graphs captured so far
+            # point at freed workspace and must be dropped; training continues bit-for-bit afterwards
+            big = synthetic.make_replay_rows(B * world * 3, V, L, seed=99)
+            sb, _, _, _, lb, _, _ = synthetic.as_torch_batch(big, 0, B * world * 3)
+            gen0 = t._engine.generation
+            _ = t.SMORL_1.final_state(sb, lb)
+            assert t._engine.generation > gen0
     lo, hi = shard_bounds(V, rank, world)
     for mine, full in ((t.SMORL_1, ref.SMORL_1), (t.SMORL_2, ref.SMORL_2)):
         sd, fsd = mine.state_dict(), full.state_dict()
@@ -66,6 +74,38 @@ def main():
     ref_emb = emb.clone()
     dist.broadcast(ref_emb, src=0)
     assert torch.equal(emb, ref_emb)
+    # sharded evaluation through the public evaluate(): candidates per shard -> all-gather -> merge (replicated result)
+    vrows = synthetic.make_replay_rows(300, V, L, seed=17)
+    loader = []
+    for lo_ in (0, 150):
+        s_, a_, _, _, ln_, _, _ = synthetic.as_torch_batch(vrows, lo_, lo_ + 150)
+        loader.append((s_, a_, ln_))
+    ekw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=2, topk_to_consider_nov=1,
+               topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+    got_e = pkg.evaluate(loader, t.SMORL_1, dev, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **ekw)
+    # the oracle net with THIS run's trained parameters (gathered from all shards)
+    import copy
+    onet = copy.deepcopy(ref.SMORL_1)
+    assert V % world == 0
+    sd = {}
+    for k, v in t.SMORL_1.state_dict().items():
+        if "head" in k:
+            parts = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(parts, v.contiguous())
+            sd[k] = torch.cat(parts).cpu()
+        else:
+            sd[k] = v.cpu()
+    onet.load_state_dict(sd)
+    want_e = oracle.evaluate(loader, onet, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **ekw)
+    import numpy as np
+    from helpers import topk_margin, double_copy, MARGIN_MIN
+    with torch.no_grad():
+        o64 = double_copy(onet)
+        assert min(topk_margin(o64(s_, ln_)[0], 20) for s_, a_, ln_ in loader) > MARGIN_MIN  # ids are well-posed
+    assert abs(float(got_e[0]) - float(want_e[0])) <= 1e-4 * abs(float(want_e[0])), (got_e[0], want_e[0])
+    assert np.array_equal(got_e[1], want_e[1]) and np.allclose(got_e[2], want_e[2], rtol=1e-12), (got_e[1], want_e[1])
+    assert got_e[3] == want_e[3] and np.array_equal(got_e[6], want_e[6])
+    assert abs(float(got_e[4]) - float(want_e[4])) <= 1e-4 and np.isclose(got_e[5], want_e[5])
     dist.barrier()
     if rank == 0:
         print(f"dist_equivalence ok: world={world}")

@@ -13,6 +13,46 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+# ---- host-side mirror of the packed-batch all-gather (the product packs on the device: rec_pack_batch) ----------
+def pack_rows(s, a, true_len, r=None, s_next=None, true_next_len=None, is_end=None):
+    """[B, 2L+4] int64: s | s_next | a | len | next_len | (r bits | is_end << 32)."""
+    B, L = s.shape
+    out = torch.zeros(B, 2 * L + 4, dtype=torch.int64, device=s.device)
+    out[:, :L] = s
+    out[:, 2 * L] = a
+    out[:, 2 * L + 1] = true_len
+    if r is not None:
+        out[:, L:2 * L] = s_next
+        out[:, 2 * L + 2] = true_next_len
+        rbits = r.to(torch.float32).contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        out[:, 2 * L + 3] = rbits | (is_end.to(torch.int64) << 32)
+    return out
+
+
+def unpack_rows(rows, L, with_q=True):
+    s = rows[:, :L].contiguous()
+    a = rows[:, 2 * L].contiguous()
+    ln = rows[:, 2 * L + 1].contiguous()
+    if not with_q:
+        return s, a, ln, None, None, None, None
+    sn = rows[:, L:2 * L].contiguous()
+    nl = rows[:, 2 * L + 2].contiguous()
+    last = rows[:, 2 * L + 3]
+    r = (last & 0xFFFFFFFF).to(torch.int32).view(torch.float32).contiguous()
+    e = ((last >> 32) & 1).to(torch.uint8).contiguous()
+    return s, a, ln, r, sn, nl, e
+
+
+def all_gather_rows(local_rows, group=None):
+    world = dist.get_world_size(group)
+    out = torch.empty(world * local_rows.shape[0], local_rows.shape[1], dtype=local_rows.dtype,
+                      device=local_rows.device)
+    dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
+    return out
+
+
+
+
 def _merge_records(stats, topv, topi, argv, argi, K):
     """Python mirror of head_merge_kernel over the shard axis (axis 0)."""
     m = stats[:, :, 0].max(0).values
@@ -46,7 +86,7 @@ def _worker(rank, world, port, out):
         b200pkg.load()
         import oracle
         from ikea_recommender_system_b200 import synthetic
-        from ikea_recommender_system_b200.sharded import shard_bounds, pack_rows, unpack_rows, all_gather_rows
+        from ikea_recommender_system_b200.sharded import shard_bounds
         V, L, B, K = 301, 6, 10, 7
         lo, hi = shard_bounds(V, rank, world)
         bounds = [shard_bounds(V, g, world) for g in range(world)]

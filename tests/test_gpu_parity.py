@@ -347,7 +347,6 @@ def test_eval_properties_at_1m_items(pkg):
 def _virtual_rank_step(trainers, hp_fn, batch, main, has_q=True):
     """Drive rec_train_phase_a..d for G 'virtual ranks' living on ONE GPU: the collectives become
     torch.stack / sum.  (Kernels of different ranks never wait on one another.)"""
-    from ikea_recommender_system_b200.sharded import pack_rows, unpack_rows
     G = len(trainers)
     s, a, r, sn, ln, nl, e = [t.to(DEV) for t in batch]
     Bg, L = s.shape

@@ -1,0 +1,538 @@
+"""GPU parity tests, round 2: the benchmarked configurations themselves and the rows VERDICT r01 listed as untested.
+
+  * SMORL train step at BASELINE cfg2 (V = 70 852, B = 256) and cfg4 (V = 1 M) against the live oracle,
+  * top-k / greedy-action ids at DEFAULT-INITIALISED (unscaled) weights at V = 70 852 and 1 M -- the regime where
+    neighbouring logits are ~1e-6 apart and the bf16x3 tensor-core scores alone mis-rank; the fp32 candidate
+    re-score (csrc/heads.cu: exact_row_dot / write_ranked) is what makes these pass,
+  * tokenizer LUT (`out_to_in`) with action_dim != item_num (IKEA shape 10 107 / 127 421), "beg" padding and
+    `use_packed_seq=False` in evaluate and in the SMORL rewards,
+  * the native training loop against a loop built from the ORACLE's pieces,
+  * sharded evaluation (virtual ranks on one GPU) against the unsharded path and the oracle,
+  * the engine-lifetime bugs of ADVICE r01 (Adam step counters across send_to_device, non-default streams).
+
+Exact-id comparisons assert first that the comparison is well-posed (helpers.topk_margin on the oracle's float64
+logits): ids are compared bit-exactly wherever fp32 arithmetic itself separates the candidates."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import (assert_close, assert_state_close, synced_random, topk_margin, double_copy, MARGIN_MIN, RTOL,
+                     report)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ATOL_P = 2e-5
+
+
+def _syn():
+    from ikea_recommender_system_b200 import synthetic
+    return synthetic
+
+
+def _smorl_kw(V, N=None, topk=1, **over):
+    kw = dict(hidden_dim=64, embedding_dim=64, padding_pos="end", train_pad_embed=True, use_packed_seq=True,
+              learning_rate=0.01, item_num=V if N is None else N, state_size=10, action_dim=V, gamma=0.5, gru_layers=1,
+              q_weights=torch.tensor([1.0, 1.0, 1.0]), alpha=1.0, topk_div=topk, topk_nov=topk, nov_rew_sig=1.0)
+    kw.update(over)
+    return kw
+
+
+def _peek_main(ref, rng):
+    """Which twin the next train_step will train (consumes nothing: the RNG state is restored by the caller)."""
+    rng.replay()
+    return ref.net_1 if random.uniform(0, 1) <= 0.5 else ref.net_2
+
+
+def _assert_step_well_posed(ref, rng, batch, topk, w):
+    """The ids this step depends on -- top-k of the supervised logits (rewards) and the greedy action -- are
+    separated by more than fp32 rounding in the oracle's own float64 logits."""
+    m64 = double_copy(_peek_main(ref, rng))
+    with torch.no_grad():
+        sup, _ = m64(batch[0], batch[4])
+        _, qn = m64(batch[3], batch[5])
+        sc = (qn * w.double().view(1, -1, 1)).sum(1)
+    m_sup, m_arg = topk_margin(sup, topk), topk_margin(sc, 1)
+    assert m_sup > MARGIN_MIN and m_arg > MARGIN_MIN, (m_sup, m_arg)
+    return m_sup, m_arg
+
+
+def _compare_big_state(mine, ref_sd, steps, what, lr=0.01, chunk=1 << 24):
+    """assert_state_close for tensors of up to 64 M elements without float64 copies of the whole tensor."""
+    worst = {}
+    for k, want in ref_sd.items():
+        got = mine[k].detach().cpu().reshape(-1)
+        want = want.detach().reshape(-1)
+        assert got.shape == want.shape, k
+        n_bad, max_err, max_rel = 0, 0.0, 0.0
+        for lo in range(0, want.numel(), chunk):
+            a, b = got[lo:lo + chunk].double(), want[lo:lo + chunk].double()
+            err = (a - b).abs()
+            n_bad += int((err > ATOL_P + RTOL * b.abs()).sum())
+            max_err = max(max_err, float(err.max()))
+            max_rel = max(max_rel, float((err / (b.abs() + 1e-3)).max()))
+        worst[k] = dict(n_bad=n_bad, n=want.numel(), max_abs_err=max_err, max_rel_err_at_1e3_floor=max_rel)
+        assert n_bad <= max(1, int(1e-3 * want.numel())), f"{what} {k}: {n_bad}/{want.numel()} beyond rtol={RTOL}"
+        assert max_err <= 0.02 * lr * steps, f"{what} {k}: max abs err {max_err:.3e}"
+    report(what, worst)
+
+
+# ------------------------------------------------------------------------------------ (a) cfg2: the benchmarked step
+def test_smorl_cfg2_shapes_against_live_oracle(pkg):
+    """bench.py's secondary workload, verbatim: SMORL, V = N = 70 852, B = 256, q_weights (1,1,1), alpha 1,
+    topk_div = topk_nov = 1, default init.  Two steps (one per twin ordering of the seeded python RNG)."""
+    V, B = 70852, 256
+    rows = _syn().make_replay_rows_fast(2 * B, V, 10, seed=0)
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16, generator=torch.Generator().manual_seed(1)),
+                                               freeze=True)
+    kw = _smorl_kw(V)
+    ref = oracle.SMORLTrainer(div_embedding=e_div, unpopular_actions_set=unpop, **kw)
+    t = pkg.SMORL_trainer(div_embedding=e_div, unpopular_actions_set=unpop, device=DEV, **kw)
+    assert_state_close(t.SMORL_1.state_dict(), ref.SMORL_1.state_dict(), rtol=0, atol=0)
+    t.send_to_device()
+    rng = synced_random()
+    margins = []
+    for i in range(2):
+        b = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+        margins.append(_assert_step_well_posed(ref, rng, b, 1, kw["q_weights"]))
+        rng.replay(); want = ref.train_step(*b)
+        rng.replay(); got = t.train_step(*b)
+        rng.advance()
+        assert t.last_main == ref.last_main
+        assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} (sup, q) losses")
+        report(f"smorl_cfg2 step {i}", dict(got=list(got), want=list(want), margins=margins[-1]))
+    _compare_big_state(t.SMORL_1.state_dict(), ref.SMORL_1.state_dict(), 2, "smorl_cfg2 net1")
+    _compare_big_state(t.SMORL_2.state_dict(), ref.SMORL_2.state_dict(), 2, "smorl_cfg2 net2")
+
+
+# ------------------------------------------------------------------------------------ (b) cfg4: 1 M items
+def test_smorl_step_at_1m_items_against_live_oracle(pkg):
+    """BASELINE configs[3] on one GPU (bench.py's default workload): ONE SMORL step at V = N = 1 000 000, B = 256,
+    against the oracle (about 10 s of CPU time), default init."""
+    V, B = 1_000_000, 256
+    rows = _syn().make_replay_rows_fast(B, V, 10, seed=0)
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16, generator=torch.Generator().manual_seed(1)),
+                                               freeze=True)
+    kw = _smorl_kw(V)
+    ref = oracle.SMORLTrainer(div_embedding=e_div, unpopular_actions_set=unpop, **kw)
+    t = pkg.SMORL_trainer(div_embedding=e_div, unpopular_actions_set=unpop, device=DEV, **kw)
+    for n_mine, n_ref in ((t.SMORL_1, ref.SMORL_1), (t.SMORL_2, ref.SMORL_2)):
+        n_mine.load_state_dict(n_ref.state_dict())  # same seeded init either way; avoids a second 1 M-row comparison
+    t.send_to_device()
+    rng = synced_random()
+    b = _syn().as_torch_batch(rows, 0, B)
+    margins = _assert_step_well_posed(ref, rng, b, 1, kw["q_weights"])
+    rng.replay(); want = ref.train_step(*b)
+    rng.replay(); got = t.train_step(*b)
+    assert t.last_main == ref.last_main
+    assert_close(got, want, rtol=RTOL, atol=1e-5, what="(sup, q) losses at 1M items")
+    report("smorl_1m step", dict(got=list(got), want=list(want), margins=margins))
+    main_i = ref.last_main
+    mine = (t.SMORL_1 if main_i == 1 else t.SMORL_2).state_dict()
+    want_sd = (ref.SMORL_1 if main_i == 1 else ref.SMORL_2).state_dict()
+    _compare_big_state(mine, want_sd, 1, "smorl_1m trained net")
+    other = (t.SMORL_2 if main_i == 1 else t.SMORL_1).state_dict()
+    want_other = (ref.SMORL_2 if main_i == 1 else ref.SMORL_1).state_dict()
+    for k in ("embedding.weight", "q_head_div.weight", "sup_head_output.bias"):
+        assert torch.equal(other[k].cpu(), want_other[k]), f"bootstrap net must be untouched: {k}"
+
+
+# ------------------------------------------------------------------------------------ (c)/(f) unscaled top-k
+@pytest.mark.parametrize("V,B", [(70852, 300), (1_000_000, 64)])
+def test_evaluate_default_init_unscaled_against_live_oracle(pkg, V, B):
+    """top-20 ids at default init (no weight scaling): neighbouring logits are ~1e-6 apart, i.e. below the ~3e-6
+    absolute error of the bf16x3 tensor-core scores -- the fp32 candidate re-score decides the order.  Everything
+    `evaluate` returns is compared, and the ids / scores row by row."""
+    torch.manual_seed(3)
+    onet = oracle.make_gru4rec(hidden_dim=64, embedding_dim=64, item_num=V, state_size=10, action_dim=V, gru_layers=1,
+                               use_packed_seq=True)
+    net = pkg.GRU4Rec(hidden_size=64, embedding_dim=64, item_num=V, state_size=10, action_dim=V)
+    net.load_state_dict(onet.state_dict())
+    net.to(DEV)
+    rows = _syn().make_replay_rows_fast(B, V, 10, seed=0)
+    s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
+    with torch.no_grad():
+        margin = topk_margin(double_copy(onet)(s, ln), 20)
+        logits = onet(s, ln)
+    assert margin > MARGIN_MIN, margin
+    want_ids = oracle.stable_topk(logits, 20)
+    loader = [(s, a, ln)]
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16, generator=torch.Generator().manual_seed(1)),
+                                               freeze=True)
+    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=2, topk_to_consider_nov=3,
+              topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+    want = oracle.evaluate(loader, onet, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **kw)
+    got = pkg.evaluate(loader, net, DEV, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **kw)
+    # ids + scores through update_train_metrics' id output path (rec_eval_batch topk_ids / topk_scores)
+    from ikea_recommender_system_b200 import _native as N_
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    eng = net._ready(B)
+    o = N_.RecEvalOpts()
+    o.head_idx, o.n_k, o.n_cov = 0, 1, 0
+    o.ks[0] = 20
+    acc = EvalAccumulators(torch.device(DEV), V)
+    ids = torch.empty(B, 20, dtype=torch.int32, device=DEV)
+    sc = torch.empty(B, 20, dtype=torch.float32, device=DEV)
+    ds, dl = net._dev_inputs(s, ln)
+    eng.eval_batch(0, eng._batch(B, ds, a.to(DEV), dl), o, acc.struct, topk_ids=ids, topk_scores=sc)
+    n_rows_off = int((ids.cpu().long() != want_ids).any(1).sum())
+    report(f"eval default init V={V}", dict(margin=margin, rows_with_any_id_off=n_rows_off, rows=B))
+    assert torch.equal(ids.cpu().long(), want_ids)
+    assert_close(sc.cpu(), logits.gather(1, want_ids), rtol=2e-6, atol=2e-7, what="re-scored top-k scores (fp32)")
+    assert_close(got[0], want[0], rtol=1e-4)
+    assert np.array_equal(got[1], want[1]) and np.allclose(got[2], want[2], rtol=1e-12) and np.array_equal(got[6], want[6])
+    assert got[3] == want[3]
+    assert_close(got[4], want[4], rtol=1e-4)
+    assert np.isclose(got[5], want[5])
+
+
+def test_sqn_greedy_action_default_init_exact(pkg):
+    """argmax_a Q(s', a) at default init, V = 70 852 (SQN: one Q head; SMORL's weighted sum is covered by the
+    train-step tests): the a* the fused step used must be the oracle's fp32 argmax for every row."""
+    V, B = 70852, 256
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=V, state_size=10, action_dim=V, gamma=0.5, gru_layers=1)
+    ref = oracle.SQNTrainer(**kw)
+    t = pkg.SQN_trainer(device=DEV, **kw)
+    t.send_to_device()
+    rows = _syn().make_replay_rows_fast(B, V, 10, seed=0)
+    b = _syn().as_torch_batch(rows, 0, B)
+    rng = synced_random()
+    main = _peek_main(ref, rng)
+    with torch.no_grad():
+        _, q64 = double_copy(main)(b[3], b[5])
+        _, q32 = main(b[3], b[5])
+    assert topk_margin(q64, 1) > MARGIN_MIN
+    want_astar = oracle.stable_topk(q32, 1)[:, 0]
+    rng.replay(); t.train_step(*b)
+    eng = t._engine
+    import ctypes as C
+    astar = torch.zeros(B, dtype=torch.int32, device=DEV)
+    eng.lib.rec_debug_copy_astar(eng.handle, C.c_void_p(astar.data_ptr()), B)
+    torch.cuda.synchronize()
+    assert torch.equal(astar.cpu().long(), want_astar)
+
+
+# ------------------------------------------------------------------------------------ (d) tokenizer LUT, V != N, "beg"
+class _Tok:
+    """Minimal stand-in for recommenders/utils/tokenizer.py:4-130 (only stoi / itos are used by the metrics)."""
+
+    def __init__(self, words):
+        self.words = list(words)
+        self.index = {w: i for i, w in enumerate(self.words)}
+
+    def stoi(self, w):
+        return self.index[w]
+
+    def itos(self, i):
+        return self.words[int(i)]
+
+
+def _ikea_like(V, N, seed):
+    """Output vocabulary of V actions, each the string name of a distinct input token out of N."""
+    rng = np.random.default_rng(seed)
+    out_to_in = rng.permutation(N)[:V].astype(np.int64)
+    in_tok = _Tok([f"item{i}" for i in range(N + 1)])
+    out_tok = _Tok([f"item{int(i)}" for i in out_to_in])
+    return in_tok, out_tok, out_to_in
+
+
+def _rows_v_ne_n(n_rows, V, N, L, seed, pad_pos="end"):
+    """States over the INPUT vocabulary [0, N) (pad id N), actions over the OUTPUT vocabulary [0, V)."""
+    rows = _syn().make_replay_rows(n_rows, N, L, seed=seed, pad_pos=pad_pos)
+    rng = np.random.default_rng(seed + 100)
+    rows["action"] = rng.integers(0, V, size=n_rows).astype(np.int64)
+    return rows
+
+
+# data seeds picked (on the CPU oracle) so that the top-21 logits of every row are > MARGIN_MIN apart
+@pytest.mark.parametrize("pad_pos,packed,seed", [("end", True, 10), ("beg", False, 5), ("end", False, 3)])
+def test_evaluate_with_token_lut_and_v_ne_n(pkg, pad_pos, packed, seed):
+    """A12 + "beg" padding: IKEA shape (V = 10 107 outputs, N + 1 = 127 421 input tokens).  Diversity and repetitions
+    go through out_to_in (diversity.py:55-60, repetitiveness.py:42-46); coverage / novelty / HR use output ids."""
+    V, N, L, B = 10107, 127420, 10, 257
+    in_tok, out_tok, lut = _ikea_like(V, N, 0)
+    torch.manual_seed(5)
+    onet = oracle.make_sqn(hidden_dim=64, embedding_dim=64, item_num=N, state_size=L, action_dim=V, gru_layers=1,
+                           use_packed_seq=packed)
+    with torch.no_grad():
+        onet.embedding.weight.mul_(30.0)
+    net = pkg.SQN_Network(hidden_dim=64, item_num=N, state_size=L, action_dim=V, gamma=0.5, gru_layers=1,
+                          embedding_dim=64, use_packed_seq=packed)
+    net.load_state_dict(onet.state_dict())
+    net.to(DEV)
+    rows = _rows_v_ne_n(2 * B, V, N, L, seed, pad_pos)
+    # make repetitions non-trivial: plant the remapped version of a likely prediction into some states
+    loader = []
+    for lo in (0, B):
+        s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, lo, lo + B)
+        loader.append((s, a, ln))
+    with torch.no_grad():
+        for s, a, ln in loader:
+            top = oracle.stable_topk(onet(s, ln)[0], 3)
+            for b_i in range(0, B, 3):
+                pos = 0 if pad_pos == "end" else L - 1
+                s[b_i, pos] = int(lut[int(top[b_i, b_i % 3])])
+        margin = min(topk_margin(double_copy(onet)(s, ln)[0], 20) for s, a, ln in loader)
+    assert margin > MARGIN_MIN, margin
+    unpop = set(int(i) for i in np.random.default_rng(1).choice(V, size=V // 3, replace=False))
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(N + 1, 16, generator=torch.Generator().manual_seed(2)),
+                                               freeze=True)
+    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=3, topk_to_consider_nov=2,
+              topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+    want = oracle.evaluate(loader, onet, torch.nn.CrossEntropyLoss(), pad_pos, e_div, unpop, out_to_in=lut, **kw)
+    got = pkg.evaluate(loader, net, DEV, torch.nn.CrossEntropyLoss(), pad_pos, e_div, unpop, input_tokenizer=in_tok,
+                       output_tokenizer=out_tok, **kw)
+    assert float(want[6].sum()) > 0  # the planted repetitions are seen
+    assert_close(got[0], want[0], rtol=1e-4)
+    assert np.array_equal(got[1], want[1]) and np.allclose(got[2], want[2], rtol=1e-12)
+    assert np.array_equal(got[6], want[6]), (got[6], want[6])
+    assert got[3] == want[3]
+    assert_close(got[4], want[4], rtol=1e-4)
+    assert np.isclose(got[5], want[5])
+    # without the LUT the remapped metrics differ: the LUT is really applied
+    got_no = pkg.evaluate(loader, net, DEV, torch.nn.CrossEntropyLoss(), pad_pos, e_div, unpop, **kw)
+    assert not np.array_equal(got_no[6], got[6]) or abs(float(got_no[4]) - float(got[4])) > 1e-6
+
+
+@pytest.mark.parametrize("pad_pos,packed", [("end", True), ("beg", False)])
+def test_smorl_step_with_token_lut_and_v_ne_n(pkg, pad_pos, packed):
+    """SMORL rewards with action_dim != item_num: the diversity reward maps top-k OUTPUT ids through out_to_in before
+    the E_div lookup (smorl_gru.py:298-308 -> diversity.py:55-60); "beg" padding takes s[:, -1] as the last action."""
+    V, N, L, B = 10107, 127420, 10, 96
+    in_tok, out_tok, lut = _ikea_like(V, N, 1)
+    rows = _rows_v_ne_n(3 * B, V, N, L, 4, pad_pos)
+    unpop = set(int(i) for i in np.random.default_rng(2).choice(V, size=V // 4, replace=False))
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(N + 1, 16, generator=torch.Generator().manual_seed(3)),
+                                               freeze=True)
+    kw = _smorl_kw(V, N=N, topk=2, padding_pos=pad_pos, use_packed_seq=packed, q_weights=torch.tensor([1.0, 0.7, 0.4]),
+                   alpha=0.8)
+    ref = oracle.SMORLTrainer(div_embedding=e_div, unpopular_actions_set=unpop, out_to_in=lut, **kw)
+    t = pkg.SMORL_trainer(div_embedding=e_div, unpopular_actions_set=unpop, device=DEV, input_tokenizer=in_tok,
+                          output_tokenizer=out_tok, **kw)
+    assert_state_close(t.SMORL_1.state_dict(), ref.SMORL_1.state_dict(), rtol=0, atol=0)
+    t.send_to_device()
+    rng = synced_random()
+    for i in range(3):
+        b = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+        _assert_step_well_posed(ref, rng, b, 2, kw["q_weights"])
+        rng.replay(); want = ref.train_step(*b)
+        rng.replay(); got = t.train_step(*b)
+        rng.advance()
+        assert t.last_main == ref.last_main
+        assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} losses ({pad_pos}, packed={packed})")
+    out = dict(outlier_frac=1e-3, outlier_atol=0.02 * 0.01 * 3)
+    assert_state_close(t.SMORL_1.state_dict(), ref.SMORL_1.state_dict(), rtol=RTOL, atol=ATOL_P, **out)
+    assert_state_close(t.SMORL_2.state_dict(), ref.SMORL_2.state_dict(), rtol=RTOL, atol=ATOL_P, **out)
+
+
+# ------------------------------------------------------------------------------------ (e) N1 against the ORACLE's loop
+def test_native_training_loop_matches_oracle_loop(pkg, tmp_path):
+    """train_native against the loop of trainSQN.py:168-428 built from the ORACLE's pieces
+    (oracle.SQNTrainer.train_step -> oracle.update_train_metrics(DQN_1) every batch -> oracle.evaluate of both twins
+    at the evaluation points), fed by the same seeded DataLoader order."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from ikea_recommender_system_b200.recommenders.ikea.training.native_loop import eval_points
+    V, L, B, VB = 300, 8, 32, 64
+    rows = _syn().make_replay_rows(5 * B + 9, V, L, seed=21)
+    vrows = _syn().make_replay_rows(150, V, L, seed=22)
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    torch.manual_seed(4)
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16), freeze=True)
+    arrays = dict(states=rows["state"], actions=rows["action"], reward=rows["r_act"], next_states=rows["next_state"],
+                  true_state_len=rows["true_state_len"], true_next_state_len=rows["true_next_state_len"],
+                  is_end=rows["is_end"])
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=V, state_size=L, action_dim=V, gamma=0.5, gru_layers=1)
+    mk = dict(padding_pos="end", diversity_embedding=e_div, unpopular_actions_set=unpop)
+    ks = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1, topk_to_consider_nov=1,
+              topk_to_consider_cov=[1, 5, 10], novelty_rew_signal=1)
+    t_nat = pkg.SQN_trainer(device=DEV, **kw)
+    ref = oracle.SQNTrainer(**kw)
+    assert_state_close(t_nat.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=0, atol=0)
+    buf = pkg.DeviceReplayBuffer.from_arrays(**arrays).to_device(DEV)
+    val = pkg.DeviceEvaluationDataset(arrays=dict(states=vrows["state"], actions=vrows["action"],
+                                                  true_state_len=vrows["true_state_len"])).to_device(DEV)
+    eval_at = (0.5, 1.0)
+    rng = synced_random()
+    rng.replay()
+    hist = pkg.train_native(t_nat, buf, val, epochs=1, batch_size=B, val_batch_size=VB, eval_at=eval_at,
+                            generator=torch.Generator().manual_seed(3), out_dir=str(tmp_path), **mk)
+    rng.replay()
+    loader = DataLoader(buf, batch_size=B, shuffle=True, generator=torch.Generator().manual_seed(3))
+    points = eval_points(len(loader), eval_at)
+    val_loader = [(torch.from_numpy(vrows["state"][lo:lo + VB]), torch.from_numpy(vrows["action"][lo:lo + VB]),
+                   torch.from_numpy(vrows["true_state_len"][lo:lo + VB])) for lo in range(0, 150, VB)]
+    ce = torch.nn.CrossEntropyLoss()
+    tot = np.zeros(2); hr = np.zeros(3); nd = np.zeros(3); reps = np.zeros(3); n = 0; div = 0.0; nov = 0.0; nb = 0
+    cov = {k: set() for k in (1, 5, 10)}
+    want = []
+    for i, (s, a, r, sn, ln, nl, e) in enumerate(loader):
+        ref.net_1.train(); ref.net_2.train()
+        sup, q = ref.train_step(s, a, r.to(torch.float32), sn, ln, nl, e.bool())
+        tot += (sup, q)
+        h, d, cov, dv, nv, rp = oracle.update_train_metrics(s, a, ln, ref.DQN_1, "end", e_div, unpop, cov, **ks)
+        hr += h; nd += d; reps += rp; n += len(a); div += float(dv); nov += float(nv)
+        nb += 1
+        if i + 1 in points:
+            v1 = oracle.evaluate(val_loader, ref.DQN_1, ce, "end", e_div, unpop, **ks)
+            v2 = oracle.evaluate(val_loader, ref.DQN_2, ce, "end", e_div, unpop, **ks)
+            want.append(dict(sup=tot[0] / nb, q=tot[1] / nb, hr=hr / n, ndcg=nd / n, reps=reps / n, div=div / n,
+                             nov=nov / n, cov={k: len(c) / V for k, c in cov.items()}, v1=v1, v2=v2))
+            tot = np.zeros(2); hr = np.zeros(3); nd = np.zeros(3); reps = np.zeros(3); n = 0; div = 0.0; nov = 0.0; nb = 0
+            cov = {k: set() for k in (1, 5, 10)}
+    assert len(hist) == len(want) == 2
+    for got, w in zip(hist, want):
+        assert_close([got["train_sup_loss"], got["train_q_loss"]], [w["sup"], w["q"]], rtol=RTOL, atol=1e-5, what="train losses")
+        # ids are exact while the parameters agree to 1e-3: with V = 300 and trained-for-a-few-steps weights the top-20
+        # of a session can contain near-ties, so HR / NDCG / coverage are compared with one session of slack
+        assert np.allclose(got["train_hr"], w["hr"], atol=2.0 / (5 * B)) and np.allclose(got["train_ndcg"], w["ndcg"], atol=2.0 / (5 * B))
+        assert np.allclose(got["train_reps"], w["reps"], atol=4.0 / (5 * B))
+        assert abs(got["train_div_rew"] - w["div"]) < 2e-3 and abs(got["train_nov_rew"] - w["nov"]) < 2.0 / (5 * B)
+        for k in (1, 5, 10):
+            assert abs(got["train_cov"][k][1] - w["cov"][k]) <= 2.0 / V
+        for sfx, v in (("", w["v1"]), ("_2", w["v2"])):
+            assert abs(got[f"val_loss{sfx}"] - float(v[0])) < 1e-3 * max(1.0, abs(float(v[0])))
+            assert np.allclose(got[f"val_hr{sfx}"], v[1], atol=2.0 / 150) and np.allclose(got[f"val_ndcg{sfx}"], v[2], atol=2.0 / 150)
+    report("native loop vs oracle loop", dict(
+        train_hr_diff=[float(np.abs(g["train_hr"] - w["hr"]).max()) for g, w in zip(hist, want)],
+        val_hr_diff=[float(np.abs(g["val_hr"] - w["v1"][1]).max()) for g, w in zip(hist, want)]))
+
+
+# ------------------------------------------------------------------------------------ sharded evaluation (E2)
+def test_sharded_evaluation_virtual_ranks_equals_unsharded_and_oracle(pkg):
+    """BASELINE configs[4] protocol on one GPU: G engines hold vocabulary slices of the same net;
+    rec_eval_shard_candidates per shard -> stacked records (the all-gather) -> rec_eval_merge on every shard.
+    Default-init weights (unscaled): ids exact vs the oracle, metrics equal to the unsharded rec_eval_batch."""
+    from ikea_recommender_system_b200.sharded import shard_bounds
+    from ikea_recommender_system_b200.recommenders.evaluate import eval_protocol as EP
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    G, V, B = 3, 70852, 300
+    torch.manual_seed(3)
+    onet = oracle.make_sqn(hidden_dim=64, embedding_dim=64, item_num=V, state_size=10, action_dim=V, gru_layers=1,
+                           use_packed_seq=True)
+    rows = _syn().make_replay_rows_fast(B, V, 10, seed=0)
+    s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
+    with torch.no_grad():
+        assert topk_margin(double_copy(onet)(s, ln)[0], 20) > MARGIN_MIN
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16, generator=torch.Generator().manual_seed(1)),
+                                               freeze=True)
+    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=2, topk_to_consider_nov=1,
+              topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
+    want = oracle.evaluate([(s, a, ln)], onet, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **kw)
+
+    def mk():
+        n = pkg.SQN_Network(hidden_dim=64, item_num=V, state_size=10, action_dim=V, gamma=0.5, gru_layers=1,
+                            embedding_dim=64, use_packed_seq=True)
+        n.load_state_dict(onet.state_dict())
+        return n
+
+    full = mk().to(DEV)
+    got_full = pkg.evaluate([(s, a, ln)], full, DEV, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **kw)
+    shards = []
+    for g in range(G):
+        n = mk()
+        n.shard_vocabulary(*shard_bounds(V, g, G))
+        shards.append(n.to(DEV))
+    dev = torch.device(DEV)
+    o, kmax, keep = EP._opts(full, dev, 0, [5, 10, 20], 2, 1, [1, 5, 10, 20], 1, "end", e_div, unpop, None, None)
+    engs = [n._ready(B) for n in shards]
+    rec = engs[0].record_floats()
+    ds, dl = full._dev_inputs(s, ln)
+    da = a.to(DEV)
+    records = [torch.empty(B, rec, device=DEV) for _ in range(G)]
+    for g in range(G):
+        engs[g].eval_shard_candidates(0, engs[g]._batch(B, ds, da, dl), 0, kmax, records[g])
+    gathered = torch.stack(records).contiguous()
+    outs = []
+    for g in range(G):
+        acc = EvalAccumulators(dev, V)
+        ids = torch.empty(B, kmax, dtype=torch.int32, device=DEV)
+        engs[g].eval_merge(engs[g]._batch(B, ds, da, dl), o, gathered, G, acc.struct, topk_ids=ids)
+        outs.append((ids.cpu(), acc.read()))
+    with torch.no_grad():
+        want_ids = oracle.stable_topk(onet(s, ln)[0], kmax)
+    for ids, r in outs:
+        assert torch.equal(ids.long(), want_ids)
+        assert np.array_equal(r["hits"][:3] / B, got_full[1]) and np.allclose(r["ndcg"][:3] / B, got_full[2], rtol=1e-12)
+        assert np.array_equal(r["cov_bits"], outs[0][1]["cov_bits"])
+        assert abs(r["loss_sum"] - float(got_full[0])) <= 1e-5 * abs(float(got_full[0]))
+    assert np.array_equal(got_full[1], want[1]) and got_full[3] == want[3]
+    # and through the public evaluate() on a sharded module (virtual all-gather hook)
+    for g in range(G):
+        acc = EvalAccumulators(dev, V)
+        EP._eval_one_batch(shards[g], engs[g], engs[g]._batch(B, ds, da, dl), o, acc, kmax,
+                           virtual_gather=lambda rec_g: gathered)
+        assert np.array_equal(acc.read()["hits"], outs[0][1]["hits"])
+
+
+# ------------------------------------------------------------------------------------ engine lifetime
+def test_adam_step_counter_survives_send_to_device_and_engine_rebuild(pkg):
+    """send_to_device() / a dropped engine must not restart Adam's bias correction at t = 1 on warm
+    moments.  3 steps, send_to_device(), force an engine rebuild, 2 more steps -> parity with 5 oracle steps."""
+    V, B = 1000, 64
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=V, state_size=10, action_dim=V, gamma=0.5, gru_layers=1)
+    ref = oracle.SQNTrainer(**kw)
+    t = pkg.SQN_trainer(device=DEV, **kw)
+    t.send_to_device()
+    rows = _syn().make_replay_rows(5 * B, V, 10, seed=13)
+    rng = synced_random()
+    for i in range(5):
+        if i == 3:
+            t.send_to_device()       # no-op now: parameters are already resident
+            steps_before = [t._engine.adam_step(0), t._engine.adam_step(1)]
+            t._drop_engine()         # what a real move / re-shard does
+            assert t._pending_steps == steps_before and sum(steps_before) == 3
+        b = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+        rng.replay(); want = ref.train_step(*b)
+        rng.replay(); got = t.train_step(*b)
+        rng.advance()
+        assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} losses")
+    assert t._engine.adam_step(0) + t._engine.adam_step(1) == 5
+    out = dict(outlier_frac=1e-3, outlier_atol=0.02 * 0.01 * 5)
+    assert_state_close(t.DQN_1.state_dict(), ref.DQN_1.state_dict(), rtol=RTOL, atol=ATOL_P, **out)
+    assert_state_close(t.DQN_2.state_dict(), ref.DQN_2.state_dict(), rtol=RTOL, atol=ATOL_P, **out)
+
+
+def test_train_step_under_a_non_default_torch_stream(pkg):
+    """kernels follow torch's CURRENT stream, so staging copies / loss reads issued under
+    `with torch.cuda.stream(s)` are ordered with them: identical losses to the default-stream run."""
+    V, B = 1000, 64
+    kw = dict(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+              item_num=V, state_size=10, action_dim=V, gamma=0.5, gru_layers=1)
+    rows = _syn().make_replay_rows(6 * B, V, 10, seed=14)
+
+    def run(stream):
+        random.seed(5)
+        t = pkg.SQN_trainer(device=DEV, **kw)
+        t.send_to_device()
+        out = []
+        for i in range(6):
+            b = tuple(x.to(DEV) for x in _syn().as_torch_batch(rows, i * B, (i + 1) * B))
+            if stream is None:
+                out.append(tuple(t.train_step(*b)))
+            else:
+                stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(stream):
+                    out.append(tuple(t.train_step(*b)))
+        torch.cuda.synchronize()
+        return out
+
+    assert run(None) == run(torch.cuda.Stream())
+
+
+def test_sharded_step_graphs_survive_engine_regrowth(pkg):
+    """a larger batch re-creates the native handle (workspace pointers change); ShardedStep must drop
+    the CUDA graphs it captured on the old pointers.  World-1 NCCL run of tests/dist_equivalence.py with a
+    mid-run evaluation batch larger than the engine's max_batch."""
+    from test_gpu_parity import _run_dist_equivalence
+    _run_dist_equivalence(1, 29617, {"REC_NO_DP_TRUNK": "1", "DIST_REGROW": "1"})
