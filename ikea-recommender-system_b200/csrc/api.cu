@@ -21,7 +21,9 @@ int launch_unpack_batch(rec_engine *e, const uint8_t *gathered, int G, int Bl, s
 static char g_err[512] = "";
 
 static int head_stats_dispatch(rec_engine *e, const HeadStatsArgs &a, int *n_split) {
-  return tc_heads_supported(e) ? launch_head_stats_tc(e, a, n_split) : launch_head_stats(e, a, n_split);
+  if (tc_heads_supported(e)) return launch_head_stats_tc(e, a, n_split);
+  if (tck_heads_supported(e) && a.topk == 0) return launch_head_stats_tck(e, a, n_split);  // top-k (evaluation) at D > 64: CUDA-core path
+  return launch_head_stats(e, a, n_split);
 }
 
 struct EngineExtra {
@@ -88,6 +90,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   e->Vloc = c.vocab_hi - c.vocab_lo;
   e->sm_count = prop.multiProcessorCount;
   e->use_tc = true;
+  e->k_sup_net = -1; e->k_sup_head = -1;
   if (head_bwd_smem_bytes(e->D) > 220 * 1024) {
     snprintf(g_err, sizeof(g_err), "rec_create: head width D=%d exceeds the shared-memory budget of the backward kernel", e->D);
     free(mem);
@@ -211,6 +214,7 @@ extern "C" void rec_destroy(rec_engine *e) {
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar, e->drop_mask,
                   extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_csort, e->emb_ccount, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block};
   for (void *p : ptrs) if (p) cudaFree(p);
+  tck_free(e);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
       if (e->nets[n].w_ihT[d]) cudaFree(e->nets[n].w_ihT[d]);

@@ -106,6 +106,14 @@ struct rec_engine {
   bool st_approx;        // scores are bf16x3 tensor-core products: the merge re-scores its candidates in fp32
   cudaEvent_t ev[12];
   float last_ms[3];
+  // operand images of the K-loop tensor-core head kernels for D >= 128 (heads_tck.cu); allocated at first use
+  uint8_t *k_wimg[2];    // [0] statistics / backward head, [1] greedy-action heads (pre-combined)
+  uint8_t *k_himg[2];    // states scored by [0] / [1]
+  uint8_t *k_hT;         // h^T image (dW GEMM)
+  uint8_t *k_dlT;        // dlogits^T image [V, B]
+  float *k_db;           // bias-gradient partials [session blocks][V]
+  float *k_bias;         // combined bias of the greedy-action heads
+  int k_sup_net, k_sup_head;  // which (net, head) k_wimg[0] / k_himg[0] currently hold (-1: none)
 };
 
 #define REC_FAIL(e, code, ...)                          \
@@ -270,6 +278,13 @@ int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 bool tc_heads_supported(const rec_engine *e);
 int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 bool tc_bwd_supported(const rec_engine *e, int B);
+// heads_tck.cu: D = 128, 256, ... (K-loop pipelines over packed operand images)
+bool tck_heads_supported(const rec_engine *e);
+int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
+int tck_bwd_slices(const rec_engine *e);
+int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                             float bc2_sqrt, const rec_train_hparams *hp, float inv_B);
+void tck_free(rec_engine *e);
 int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                             float bc2_sqrt, const rec_train_hparams *hp, float inv_B, int *n_slices);
 int launch_h_prepack_early(rec_engine *e, const float *h, int B);

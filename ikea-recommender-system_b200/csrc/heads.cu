@@ -266,35 +266,88 @@ struct RescoreSrc {
   int kpub, apub;             // candidates per record: top-k slots / greedy-action slots
 };
 
-__device__ __forceinline__ float exact_row_dot(const float *__restrict__ W, const float *__restrict__ bias, int64_t loc,
-                                               const float *__restrict__ hrow, int D, int lane) {
-  const float *wr = W + loc * D;
-  float acc = 0.f;
-  for (int k0 = 0; k0 < D; k0 += 32) {
-    const float hv = (k0 + lane < D) ? hrow[k0 + lane] : 0.f;
-    const int n = min(32, D - k0);
-    for (int kk = 0; kk < n; kk += 4) {  // D is a multiple of 4
-      const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wr + k0 + kk));
-      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk), w4.x, acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk + 1), w4.y, acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk + 2), w4.z, acc);
-      acc = fmaf(__shfl_sync(0xffffffffu, hv, kk + 3), w4.w, acc);
+// Warp-cooperative: the warp walks the candidates four at a time; for each one every lane loads ONE float4 of the
+// candidate's weight row per 128 columns (coalesced, all loads of a group independent -> one memory round trip per
+// group instead of a chain of dependent per-lane loads), multiplies it with its float4 of h and the partial sums are
+// combined by the fixed butterfly of warp_sum -- a deterministic fp32 evaluation of h.W[id] whose rounding error
+// (~1e-7 relative) is that of any fp32 dot product.  `n_cand` is warp-uniform; lane c < n_cand passes its candidate's
+// local row `loc` (any valid row for the other lanes) and receives its candidate's score.
+template <int NH>
+struct RowSrc { const float *p[NH]; };
+template <int NH>
+__device__ __forceinline__ void exact_rows_coop(const RowSrc<NH> W, int64_t loc, int n_cand,
+                                                const float *__restrict__ hrow, int D, int lane, float *out) {
+#pragma unroll
+  for (int j = 0; j < NH; ++j) out[j] = 0.f;
+  for (int c0 = 0; c0 < n_cand; c0 += 4) {
+    float part[NH][4];
+#pragma unroll
+    for (int j = 0; j < NH; ++j)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) part[j][cc] = 0.f;
+    int64_t locs[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) locs[cc] = __shfl_sync(0xffffffffu, loc, (c0 + cc) & 31);
+    for (int k0 = lane * 4; k0 < D; k0 += 128) {
+      const float4 hv = *reinterpret_cast<const float4 *>(hrow + k0);
+      float4 w4[NH][4];
+#pragma unroll
+      for (int j = 0; j < NH; ++j)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          w4[j][cc] = (c0 + cc < n_cand) ? __ldg(reinterpret_cast<const float4 *>(W.p[j] + locs[cc] * D + k0))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NH; ++j)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float a = part[j][cc];
+          a = fmaf(hv.x, w4[j][cc].x, a); a = fmaf(hv.y, w4[j][cc].y, a);
+          a = fmaf(hv.z, w4[j][cc].z, a); a = fmaf(hv.w, w4[j][cc].w, a);
+          part[j][cc] = a;
+        }
     }
+#pragma unroll
+    for (int j = 0; j < NH; ++j)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float sfull = warp_sum(part[j][cc]);
+        if (lane == c0 + cc) out[j] = sfull;
+      }
   }
-  return acc + __ldg(bias + loc);
+}
+
+// exact score of head (W, bias) for the candidate this lane owns (lanes >= n_cand: unspecified)
+__device__ __forceinline__ float exact_row_dot(const float *__restrict__ W, const float *__restrict__ bias, int64_t loc,
+                                               int n_cand, const float *__restrict__ hrow, int D, int lane) {
+  RowSrc<1> Ws; Ws.p[0] = W;
+  float o[1];
+  exact_rows_coop<1>(Ws, loc, n_cand, hrow, D, lane, o);
+  return o[0] + __ldg(bias + loc);
 }
 
 // greedy-action score of candidate `id` in the oracle's order: ((q0*w0 + q1*w1) + q2*w2), plain q0 for one head
-__device__ __forceinline__ float exact_arg_score(const RescoreSrc &R, int id, int vocab_lo, int Vloc, const float *hrow,
-                                                 int D, int lane) {
+__device__ __forceinline__ float exact_arg_score(const RescoreSrc &R, int id, int n_cand, int vocab_lo, int Vloc,
+                                                 const float *hrow, int D, int lane) {
   int64_t loc = (int64_t)id - vocab_lo;
   const bool ok = loc >= 0 && loc < Vloc;
   if (!ok) loc = 0;
   float sc = 0.f;
-  for (int j = 0; j < R.n_arg; ++j) {
-    float q = exact_row_dot(R.w[j], R.b[j], loc, hrow, D, lane);
-    if (R.n_arg > 1) q *= R.wq[j];
-    sc = (j == 0) ? q : sc + q;
+  if (R.n_arg == 3) {
+    RowSrc<3> Ws; Ws.p[0] = R.w[0]; Ws.p[1] = R.w[1]; Ws.p[2] = R.w[2];
+    float q[3];
+    exact_rows_coop<3>(Ws, loc, n_cand, hrow, D, lane, q);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float qj = (q[j] + __ldg(R.b[j] + loc)) * R.wq[j];
+      sc = (j == 0) ? qj : sc + qj;
+    }
+  } else {
+    for (int j = 0; j < R.n_arg; ++j) {
+      float q = exact_row_dot(R.w[j], R.b[j], loc, n_cand, hrow, D, lane);
+      if (R.n_arg > 1) q *= R.wq[j];
+      sc = (j == 0) ? q : sc + q;
+    }
   }
   return ok ? sc : REC_NEG_INF;
 }
@@ -326,7 +379,7 @@ __device__ __forceinline__ void merge_arg_rescored(const float *__restrict__ par
     if (lane == k) { cv = bv; ci = bi; }
     lastv = bv; lasti = bi;
   }
-  const float ex = exact_arg_score(R, ci == 0x7fffffff ? vocab_lo : ci, vocab_lo, Vloc, R.h + (int64_t)row * D, D, lane);
+  const float ex = exact_arg_score(R, ci == 0x7fffffff ? vocab_lo : ci, REC_ARG_CAND, vocab_lo, Vloc, R.h + (int64_t)row * D, D, lane);
   float bv = (lane < REC_ARG_CAND && ci != 0x7fffffff) ? ex : REC_NEG_INF;
   int bi = (lane < REC_ARG_CAND) ? ci : 0x7fffffff;
 #pragma unroll
@@ -452,7 +505,7 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float *__restrict
     }
     if (R.approx) {
       const bool valid = lane < kt && ci != 0x7fffffff;
-      const float ex = exact_row_dot(R.w[0], R.b[0], valid ? (int64_t)ci - vocab_lo : 0, R.h + (int64_t)row * D, D, lane);
+      const float ex = exact_row_dot(R.w[0], R.b[0], valid ? (int64_t)ci - vocab_lo : 0, kt, R.h + (int64_t)row * D, D, lane);
       write_ranked(ex, ci, valid, topk, lane, row, row_ids, row_topv, sm);
     }
   }
@@ -541,7 +594,7 @@ __global__ void __launch_bounds__(128) head_merge_small_kernel(const float *__re
         if (lane == k) { cv = sv; ci = si; }
         lastv = sv; lasti = si;
       }
-      const float ex = exact_arg_score(R, ci == 0x7fffffff ? vocab_lo : ci, vocab_lo, Vloc, R.h + (int64_t)row * D, D, lane);
+      const float ex = exact_arg_score(R, ci == 0x7fffffff ? vocab_lo : ci, REC_ARG_CAND, vocab_lo, Vloc, R.h + (int64_t)row * D, D, lane);
       bv = (lane < REC_ARG_CAND && ci != 0x7fffffff) ? ex : REC_NEG_INF;
       bi = (lane < REC_ARG_CAND) ? ci : 0x7fffffff;
     } else {
@@ -580,7 +633,7 @@ __global__ void __launch_bounds__(128) head_merge_small_kernel(const float *__re
     }
     if (R.approx) {
       const bool valid = lane < kt && ci != 0x7fffffff;
-      const float ex = exact_row_dot(R.w[0], R.b[0], valid ? (int64_t)ci - vocab_lo : 0, R.h + (int64_t)row * D, D, lane);
+      const float ex = exact_row_dot(R.w[0], R.b[0], valid ? (int64_t)ci - vocab_lo : 0, kt, R.h + (int64_t)row * D, D, lane);
       write_ranked(ex, ci, valid, topk, lane, row, row_ids, row_topv, sm);
     }
   }
@@ -815,7 +868,7 @@ __global__ void __launch_bounds__(128) q_rows_fused_small_kernel(QRowArgs A, rec
       if (lane == k) { cv = sv; ci = si; }
       lastv = sv; lasti = si;
     }
-    const float ex = exact_arg_score(A.R, ci == 0x7fffffff ? A.vocab_lo : ci, A.vocab_lo, A.Vloc, A.R.h + (int64_t)b * D, D, lane);
+    const float ex = exact_arg_score(A.R, ci == 0x7fffffff ? A.vocab_lo : ci, REC_ARG_CAND, A.vocab_lo, A.Vloc, A.R.h + (int64_t)b * D, D, lane);
     bv = (lane < REC_ARG_CAND && ci != 0x7fffffff) ? ex : REC_NEG_INF;
     bi = (lane < REC_ARG_CAND) ? ci : 0x7fffffff;
   } else {
@@ -1204,6 +1257,7 @@ size_t head_bwd_smem_bytes(int D) {
 // Number of per-CTA dh slices the supervised-head kernel writes; the Q heads' slice follows them.
 int head_bwd_dense_slices(const rec_engine *e, int B) {
   if (tc_bwd_supported(e, B)) return tc_bwd_slices(e);
+  if (tck_heads_supported(e)) return tck_bwd_slices(e);
   const int n_tiles = cdiv(e->Vloc, TN);
   int n_cta = e->n_dh_part - 1;
   return n_cta > n_tiles ? n_tiles : n_cta;
@@ -1249,6 +1303,9 @@ int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_bat
   if (tc_bwd_supported(e, B)) {
     int n_slices = 0;
     int rc = launch_head_bwd_adam_tc(e, net_id, h, b, B, step_size, bc2_sqrt, hp, inv_B, &n_slices);
+    if (rc) return rc;
+  } else if (tck_heads_supported(e)) {
+    int rc = launch_head_bwd_adam_tck(e, net_id, h, b, B, step_size, bc2_sqrt, hp, inv_B);
     if (rc) return rc;
   } else {
     const rec_net_params &p = e->nets[net_id].p;

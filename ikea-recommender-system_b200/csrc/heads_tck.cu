@@ -1,0 +1,754 @@
+// Full-vocabulary heads for wide states (D = 128, 256, 384, 512, ...: BidirGRU4Rec-SQN, BASELINE cfg3 has D = 512) on
+// the 5th-generation tensor cores.  With D > 64 neither the states (h[256 x 512] as bf16 hi/lo = 512 KB) nor a weight
+// tile fit in shared memory next to each other, so every GEMM here is a K-LOOP pipeline over PACKED OPERAND IMAGES:
+//
+//   image of a matrix X[R, C] (C % 64 == 0): blocks [ceil(R/128)][C/64], block = bf16 hi [128 rows][64] (16 KB) | bf16
+//   lo (16 KB), 128-byte swizzle -- exactly the bytes tcgen05.mma wants in shared memory, so a pipeline stage is filled
+//   by plain TMA bulk copies.  The same bytes serve as a K-major operand (MN = rows, K = the 64 columns) or as an
+//   MN-major operand (MN = the 64 columns, K = rows): logits, dW and dh all read the SAME images.
+//
+//   pack_img_kernel          fp32 master weights -> image (once per step and head; the Q heads of the greedy-action
+//                            pass are pre-combined  sum_j w_j W_j  while they are packed), h -> image, h^T -> image
+//   tck_kernel<HeadFwd<M>>   logits tile [128 sessions x 128 items] = h . W^T, K-loop over D, accumulators in TMEM
+//                            (double-buffered over vocabulary tiles); epilogue M = STATS: online (max, sum-exp) +
+//                            target logit | ARG: running argmax (greedy action) | DL: dlogits = (softmax - onehot)/B
+//                            written as the image dl^T[V, B] (+ bias-gradient partials)
+//   tck_kernel<HeadDh>       dh[128 sessions x 256] += dl . W   (both operands MN-major views), split-K over the catalogue
+//   tck_kernel<HeadDwAdam>   dW tile [128 items x 256] = dl^T . h (K = batch) -> fused Adam on W, m, v (+ bias)
+//
+// One kernel skeleton (tck_kernel): 8 epilogue warps + 1 MMA-issuer warp + 1 TMA-loader warp that meet only at
+// mbarriers (stage full / stage empty / accumulator full / accumulator empty).  The products are evaluated as
+// hi*hi + hi*lo + lo*hi with fp32 accumulation ("bf16x3", ~1e-5 relative) exactly like the D = 64 kernels.
+// Reference semantics: nn.Linear heads + CrossEntropyLoss + Adam of models/SQN/sqn_gru.py:78-112,183-254 and
+// models/BidirGRU4Rec/model.py:51-99 (cfg3 = SQN heads on the concatenated bidirectional state).
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tck {
+
+constexpr int BLK = 16384;      // one [128][64] bf16 operand block
+constexpr int BLK2 = 2 * BLK;   // hi + lo
+constexpr int HALF = 8192;      // 64 rows of a block
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_THREADS + 64;  // + issuer warp + loader warp
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int ROW_STRIDE_ = 8;  // row_stats stride (heads.cu)
+constexpr int TOPK_OFF = 5;     // part record layout (heads.cu / heads_tc.cu)
+
+// ------------------------------------------------------------------------------------------------------------
+// Packing
+// ------------------------------------------------------------------------------------------------------------
+struct PackSrc {
+  const float *p[3];
+  float w[3];
+  int n;
+};
+
+// fp32 row-major [R, C] (leading dimension ld) -> image; rows in [R, 128 * ceil(R/128)) are written as zeros.
+__global__ void __launch_bounds__(256) pack_img_kernel(PackSrc s, int R, int C, int64_t ld, uint8_t *__restrict__ img) {
+  const int c8n = C >> 3, KB = C >> 6;
+  const int64_t n_chunks = (int64_t)((R + 127) / 128) * 128 * c8n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / c8n;
+    const int c8 = (int)(i - row * c8n);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (row < R) {
+      const float4 *p0 = reinterpret_cast<const float4 *>(s.p[0] + row * ld + c8 * 8);
+      a = p0[0]; b = p0[1];
+      if (s.n > 1 || s.w[0] != 1.f) {
+        const float w0 = s.w[0];
+        a.x *= w0; a.y *= w0; a.z *= w0; a.w *= w0; b.x *= w0; b.y *= w0; b.z *= w0; b.w *= w0;
+        for (int j = 1; j < s.n; ++j) {
+          const float4 *pj = reinterpret_cast<const float4 *>(s.p[j] + row * ld + c8 * 8);
+          const float4 x = pj[0], y = pj[1];
+          const float w = s.w[j];
+          a.x = fmaf(w, x.x, a.x); a.y = fmaf(w, x.y, a.y); a.z = fmaf(w, x.z, a.z); a.w = fmaf(w, x.w, a.w);
+          b.x = fmaf(w, y.x, b.x); b.y = fmaf(w, y.y, b.y); b.z = fmaf(w, y.z, b.z); b.w = fmaf(w, y.w, b.w);
+        }
+      }
+    }
+    uint8_t *blk = img + ((row >> 7) * KB + (c8 >> 3)) * (int64_t)BLK2;
+    tc::store_split8(blk, blk + BLK, (int)(row & 127), c8 & 7, a, b);
+  }
+}
+
+// h [B, D] -> image of h^T: rows = state dimension d (D % 128 == 0), columns = sessions (KBS = ceil(B/64) blocks,
+// sessions beyond B are zeros).  The matrix is tiny (<= 512 KB): strided reads are fine.
+__global__ void __launch_bounds__(256) pack_img_T_kernel(const float *__restrict__ h, int B, int D, int KBS,
+                                                        uint8_t *__restrict__ img) {
+  const int c8n = KBS * 8;
+  const int n_chunks = D * c8n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += gridDim.x * blockDim.x) {
+    const int c8 = i / D, row = i - c8 * D;  // consecutive threads: consecutive d -> coalesced reads of h rows
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = c8 * 8 + j;
+      v[j] = b < B ? h[(int64_t)b * D + row] : 0.f;
+    }
+    uint8_t *blk = img + ((int64_t)(row >> 7) * KBS + (c8 >> 3)) * BLK2;
+    tc::store_split8(blk, blk + BLK, row & 127, c8 & 7, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
+__global__ void bias_combine_kernel(PackSrc s, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = s.w[0] * s.p[0][i];
+  for (int j = 1; j < s.n; ++j) acc = fmaf(s.w[j], s.p[j][i], acc);
+  out[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel skeleton
+// ------------------------------------------------------------------------------------------------------------
+// OP supplies:  STAGES, STAGE_BYTES, ACC_COLS (TMEM columns of one accumulator), TMEM_COLS (allocation, power of 2),
+//   units(p, lo, hi)            this CTA's range of output units (an accumulator's worth of output each)
+//   k_steps(p, u)               pipeline stages consumed by unit u
+//   load(p, u, ks, stage, bar)  ONE thread: expect_tx + TMA bulk copies of stage (u, ks)
+//   mma(p, u, ks, saddr, tacc, first)  ONE thread: the tcgen05.mma's of stage (u, ks) into accumulator tacc
+//   Epi                         per-thread epilogue object: tile(p, u, i, tacc) per unit, finish(p) at the end
+template <class OP>
+__global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Params p) {
+  extern __shared__ uint8_t raw[];
+  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int u_lo = 0, u_hi = 0;
+  OP::units(p, u_lo, u_hi);
+  if (tid == 0) {
+    for (int s = 0; s < OP::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, OP::TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  uint8_t *extra = sm + OP::STAGES * OP::STAGE_BYTES;
+
+  if (warp == EPI_WARPS + 1) {
+    // ---- TMA loader ----
+    if (lane == 0) {
+      int s = 0;
+      uint32_t round = 0;
+      for (int u = u_lo; u < u_hi; ++u) {
+        const int nk = OP::k_steps(p, u);
+        for (int ks = 0; ks < nk; ++ks) {
+          if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage are complete
+          OP::load(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+          if (++s == OP::STAGES) { s = 0; ++round; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    // ---- MMA issuer ----
+    int s = 0, i = 0;
+    uint32_t round = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++i) {
+      const int b = i & 1;
+      if (i >= 2) tc::mbar_wait(&tempty[b], ((i - 2) >> 1) & 1);  // the epilogue has read this accumulator
+      tc::tc_fence_after();
+      const int nk = OP::k_steps(p, u);
+      for (int ks = 0; ks < nk; ++ks) {
+        tc::mbar_wait(&full[s], round & 1);
+        tc::tc_fence_after();
+        if (lane == 0) {
+          OP::mma(p, u, ks, tc::smem_u32(sm + s * OP::STAGE_BYTES), tmem + (uint32_t)(b * OP::ACC_COLS), ks == 0);
+          tc::mma_commit(&empty[s]);
+        }
+        __syncwarp();
+        if (++s == OP::STAGES) { s = 0; ++round; }
+      }
+      if (lane == 0) tc::mma_commit(&tfull[b]);
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue warps ----
+    typename OP::Epi epi(p, extra, tid);
+    int i = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++i) {
+      const int b = i & 1;
+      tc::mbar_wait(&tfull[b], (i >> 1) & 1);
+      tc::tc_fence_after();
+      epi.tile(p, u, i, tmem + (uint32_t)(b * OP::ACC_COLS));
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[b]);
+    }
+    epi.finish(p);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, OP::TMEM_COLS);
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// Forward: logits[128 sessions x 128 items] per unit, K-loop over D
+// ------------------------------------------------------------------------------------------------------------
+struct FwdParams {
+  const uint8_t *himg, *wimg;  // [n_sb][KB], [n_tiles][KB]
+  int KB, B, Vloc, vocab_lo, n_tiles;
+  const float *bias;           // [Vloc] (combined for the greedy-action pass)
+  const int64_t *target;       // [B] or null
+  float *part;                 // STATS / ARG: records [n_split][B][part_stride]
+  int part_stride;
+  const float *row_stats;      // DL: merged statistics (lse at [row * 8])
+  float inv_B;
+  uint8_t *dlT;                // DL: image [n_tiles][dl_cb]
+  int dl_cb;
+  float *db_part;              // DL: [n_sb][n_tiles * 128]
+};
+
+enum { M_STATS = 0, M_ARG = 1, M_DL = 2 };
+
+template <int MODE>
+struct HeadFwd {
+  using Params = FwdParams;
+  static constexpr int STAGES = 3, STAGE_BYTES = 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
+  static constexpr int EXTRA_BYTES = 8192;
+
+  __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) {
+    const int per = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    lo = blockIdx.x * per;
+    hi = min(p.n_tiles, lo + per);
+    if (hi < lo) hi = lo;
+  }
+  __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KB; }
+  __device__ static __forceinline__ void load(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+    tc::mbar_expect_tx(bar, 2 * BLK2);
+    tc::bulk_g2s(stage, p.himg + ((int64_t)blockIdx.y * p.KB + ks) * BLK2, BLK2, bar);
+    tc::bulk_g2s(stage + BLK2, p.wimg + ((int64_t)u * p.KB + ks) * BLK2, BLK2, bar);
+  }
+  __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
+    const uint32_t id = tc::instr_desc(128, 128, 0, 0);
+    const uint64_t ah = tc::desc_kmajor(st, 0), al = tc::desc_kmajor(st + BLK, 0);
+    const uint64_t bh = tc::desc_kmajor(st + BLK2, 0), bl = tc::desc_kmajor(st + BLK2 + BLK, 0);
+    bool acc = !first;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tacc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id, acc); acc = true; }
+    }
+  }
+
+  struct Epi {
+    float *xs;  // extra shared memory
+    int q, cq, lane, row, trow;
+    float m_run, s_run, tgt, av, cst;
+    int ai;
+    bool rv;
+    __device__ __forceinline__ Epi(const Params &p, uint8_t *extra, int tid) {
+      xs = reinterpret_cast<float *>(extra);
+      const int warp = tid >> 5;
+      lane = tid & 31; q = warp & 3; cq = warp >> 2;
+      row = blockIdx.y * 128 + q * 32 + lane;
+      rv = row < p.B;
+      m_run = REC_NEG_INF; s_run = 0.f; tgt = REC_NEG_INF; av = REC_NEG_INF; ai = 0x7fffffff;
+      trow = (MODE != M_ARG && p.target && rv) ? (int)(p.target[row] - p.vocab_lo) : -1;
+      cst = 0.f;
+      if (MODE == M_DL) cst = fmaf(-(rv ? p.row_stats[(int64_t)row * ROW_STRIDE_] : 0.f), LOG2E, __log2f(p.inv_B));
+    }
+    __device__ __forceinline__ void tile(const Params &p, int u, int i, uint32_t tacc) {
+      const int v0 = u * 128;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int c_lo = v0 + cq * 64 + half * 32;
+        float l[32];
+        tc::tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64 + half * 32), l);
+        if (c_lo + 32 <= p.Vloc) {
+          const float4 *bg = reinterpret_cast<const float4 *>(p.bias + c_lo);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(bg + (j >> 2));
+            l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) l[j] = (c_lo + j < p.Vloc) ? l[j] + __ldg(p.bias + c_lo + j) : REC_NEG_INF;
+        }
+        if (MODE == M_STATS) {
+          float tmax = fmaxf(l[0], l[1]);
+#pragma unroll
+          for (int j = 2; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
+          const float nm = fmaxf(m_run, tmax), nml = -fmaxf(nm, -1e30f) * LOG2E;
+          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ps[j & 3] += tc::ex2_ftz(fmaf(l[j], LOG2E, nml));
+          s_run = fmaf(s_run, tc::ex2_ftz((m_run - nm) * LOG2E), (ps[0] + ps[1]) + (ps[2] + ps[3]));
+          m_run = nm;
+          if (trow >= c_lo && trow < c_lo + 32) {
+            const int tj = trow - c_lo;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j == tj) tgt = l[j];
+          }
+        } else if (MODE == M_ARG) {
+          float cm[4] = {l[0], l[1], l[2], l[3]};
+#pragma unroll
+          for (int j = 4; j < 32; ++j) cm[j & 3] = fmaxf(cm[j & 3], l[j]);
+          if (fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) > av) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (l[j] > av) { av = l[j]; ai = p.vocab_lo + c_lo + j; }  // ascending ids: strict > keeps the lowest id
+          }
+        } else {
+          // dlogits = exp(l - lse) / B  (- 1/B at the target); zero outside the matrix
+          const int tj = trow - c_lo;
+          const int nvalid = rv ? min(32, p.Vloc - c_lo) : 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) l[j] = tc::ex2_ftz(fmaf(l[j], LOG2E, cst));
+          if (tj >= 0 && tj < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= p.inv_B;
+          }
+          if (nvalid < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j >= nvalid) l[j] = 0.f;
+          }
+          // dl^T image: row = item (tile u, row r), column = session
+          const int sl = q * 32 + lane;
+          uint8_t *blk = p.dlT + ((int64_t)u * p.dl_cb + 2 * blockIdx.y + (sl >> 6)) * BLK2;
+          const int c = sl & 63;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            uint32_t hi, lo;
+            tc::split_bf16x2(l[j], l[j + 1], hi, lo);
+            const int r = cq * 64 + half * 32 + j;
+            const uint32_t o0 = tc::sw128_off(r, c), o1 = tc::sw128_off(r + 1, c);
+            *reinterpret_cast<uint16_t *>(blk + o0) = (uint16_t)(hi & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(blk + o1) = (uint16_t)(hi >> 16);
+            *reinterpret_cast<uint16_t *>(blk + BLK + o0) = (uint16_t)(lo & 0xFFFFu);
+            *reinterpret_cast<uint16_t *>(blk + BLK + o1) = (uint16_t)(lo >> 16);
+          }
+          // bias gradient: column sums over the warp's 32 sessions (transpose-reduce: lane j ends with column j)
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < o; ++k) {
+              const bool up = (lane & o) != 0;
+              const float send = up ? l[k] : l[k + o];
+              const float keep = up ? l[k + o] : l[k];
+              l[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          xs[(i & 1) * 512 + q * 128 + cq * 64 + half * 32 + lane] = l[0];
+        }
+      }
+      if (MODE == M_DL) {
+        epi_bar();
+        const int t = threadIdx.x;
+        if (t < 128) {
+          const float *d = xs + (i & 1) * 512 + t;
+          p.db_part[((int64_t)blockIdx.y * p.n_tiles + u) * 128 + t] = (d[0] + d[128]) + (d[256] + d[384]);
+        }
+      }
+    }
+    __device__ __forceinline__ void finish(const Params &p) {
+      if (MODE == M_DL) return;
+      // combine the two column halves of every row, publish ONE record per (split, row)
+      float *x = xs + ((q * 32 + lane) * 2 + cq) * 5;
+      x[0] = m_run; x[1] = s_run; x[2] = tgt; x[3] = av; x[4] = __int_as_float(ai);
+      epi_bar();
+      if (cq == 0 && rv) {
+        const float *y = xs + ((q * 32 + lane) * 2) * 5;
+        const float m = fmaxf(y[0], y[5]), tg = fmaxf(y[2], y[7]);
+        float ssum = 0.f;
+        if (y[1] > 0.f) ssum += y[1] * __expf(y[0] - m);
+        if (y[6] > 0.f) ssum += y[6] * __expf(y[5] - m);
+        float v0 = y[3], v1 = y[8];
+        int i0 = __float_as_int(y[4]), i1 = __float_as_int(y[9]);
+        if (better(v1, i1, v0, i0)) { float tv = v0; v0 = v1; v1 = tv; int ti = i0; i0 = i1; i1 = ti; }
+        float *o = p.part + ((int64_t)blockIdx.x * p.B + row) * p.part_stride;
+        o[0] = m; o[1] = ssum; o[2] = tg; o[3] = v0; o[4] = __int_as_float(i0);
+        if (MODE == M_ARG) {  // two approximate candidates per record: the merge re-scores the best few in fp32
+          o[TOPK_OFF] = v0; o[TOPK_OFF + REC_MAX_TOPK] = __int_as_float(i0);
+          o[TOPK_OFF + 1] = v1; o[TOPK_OFF + REC_MAX_TOPK + 1] = __int_as_float(i1);
+        }
+      }
+    }
+  };
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// dh[128 sessions x (64 NCB)] = sum over this CTA's vocabulary range of dl . W   (A, B: MN-major views)
+// ------------------------------------------------------------------------------------------------------------
+struct DhParams {
+  const uint8_t *dlT, *wimg;
+  int KB, NCB, dl_cb, n_tiles, B, D;
+  float *dh_part;  // [n_split][B][D]
+};
+
+struct HeadDh {
+  using Params = DhParams;
+  static constexpr int STAGES = 2, STAGE_BYTES = 12 * HALF, ACC_COLS = 256, TMEM_COLS = 256;
+  static constexpr int EXTRA_BYTES = 0;
+  __device__ static __forceinline__ void range(const Params &p, int &t_lo, int &t_hi) {
+    const int per = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    t_lo = blockIdx.x * per;
+    t_hi = min(p.n_tiles, t_lo + per);
+  }
+  __device__ static __forceinline__ void units(const Params &, int &lo, int &hi) { lo = 0; hi = 1; }
+  __device__ static __forceinline__ int k_steps(const Params &p, int) {
+    int t_lo, t_hi;
+    range(p, t_lo, t_hi);
+    return max(0, t_hi - t_lo) * 2;
+  }
+  __device__ static __forceinline__ void load(const Params &p, int, int ks, uint8_t *stage, uint64_t *bar) {
+    int t_lo, t_hi;
+    range(p, t_lo, t_hi);
+    const int t = t_lo + (ks >> 1), rh = ks & 1;
+    tc::mbar_expect_tx(bar, (uint32_t)(4 + 2 * p.NCB) * HALF);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint8_t *blk = p.dlT + ((int64_t)t * p.dl_cb + 2 * blockIdx.z + c) * BLK2 + rh * HALF;
+      tc::bulk_g2s(stage + c * HALF, blk, HALF, bar);
+      tc::bulk_g2s(stage + 2 * HALF + c * HALF, blk + BLK, HALF, bar);
+    }
+    for (int c = 0; c < p.NCB; ++c) {
+      const uint8_t *blk = p.wimg + ((int64_t)t * p.KB + blockIdx.y * p.NCB + c) * BLK2 + rh * HALF;
+      tc::bulk_g2s(stage + 4 * HALF + c * HALF, blk, HALF, bar);
+      tc::bulk_g2s(stage + 8 * HALF + c * HALF, blk + BLK, HALF, bar);
+    }
+  }
+  __device__ static __forceinline__ void mma(const Params &p, int, int, uint32_t st, uint32_t tacc, bool first) {
+    const uint32_t id = tc::instr_desc(128, 64 * p.NCB, 1, 1);
+    const uint64_t ah = tc::desc_mnmajor(st, 0, HALF), al = tc::desc_mnmajor(st + 2 * HALF, 0, HALF);
+    const uint64_t bh = tc::desc_mnmajor(st + 4 * HALF, 0, HALF), bl = tc::desc_mnmajor(st + 8 * HALF, 0, HALF);
+    bool acc = !first;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tacc, a + (uint64_t)(k * 128), b + (uint64_t)(k * 128), id, acc); acc = true; }
+    }
+  }
+  struct Epi {
+    int q, cq, lane;
+    __device__ __forceinline__ Epi(const Params &, uint8_t *, int tid) {
+      const int warp = tid >> 5;
+      lane = tid & 31; q = warp & 3; cq = warp >> 2;
+    }
+    __device__ __forceinline__ void tile(const Params &p, int, int, uint32_t tacc) {
+      const int row = blockIdx.z * 128 + q * 32 + lane;
+      const int N = 64 * p.NCB, nch = N / 64;  // 32-column chunks per column half
+      float *dst = p.dh_part + ((int64_t)blockIdx.x * p.B + row) * p.D + blockIdx.y * N;
+      for (int ch = 0; ch < nch; ++ch) {
+        const int c0 = cq * (N / 2) + ch * 32;
+        float g[32];
+        tc::tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, g);
+        if (row < p.B) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4 *>(dst + c0 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+        }
+      }
+    }
+    __device__ __forceinline__ void finish(const Params &) {}
+  };
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// dW tile [128 items x (128 NRB)] = dl^T . h  (K = batch) -> Adam on W, m, v (+ bias when the tile starts at column 0)
+// ------------------------------------------------------------------------------------------------------------
+struct DwParams {
+  const uint8_t *dlT, *hT;  // [n_tiles][KBS], [D/128][KBS]
+  int KBS, NRB, n_dchunks, n_tiles, Vloc, D, n_sb;
+  float *w, *wm, *wv, *b, *bm, *bv;
+  const float *db_part;     // [n_sb][n_tiles * 128]
+  float b1, b2, eps, step_size, inv_bc2_sqrt;
+  const float *sc;
+};
+
+struct HeadDwAdam {
+  using Params = DwParams;
+  static constexpr int STAGES = 2, STAGE_BYTES = 3 * BLK2, ACC_COLS = 256, TMEM_COLS = 512;
+  static constexpr int EXTRA_BYTES = EPI_WARPS * 32 * 20 * 4;
+  __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) {
+    const int total = p.n_tiles * p.n_dchunks;
+    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    lo = blockIdx.x * per;
+    hi = min(total, lo + per);
+    if (hi < lo) hi = lo;
+  }
+  __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KBS; }
+  __device__ static __forceinline__ void load(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+    const int t = u / p.n_dchunks, dc = u - t * p.n_dchunks;
+    tc::mbar_expect_tx(bar, (uint32_t)(1 + p.NRB) * BLK2);
+    tc::bulk_g2s(stage, p.dlT + ((int64_t)t * p.KBS + ks) * BLK2, BLK2, bar);
+    for (int i = 0; i < p.NRB; ++i) {
+      const uint8_t *blk = p.hT + ((int64_t)(dc * p.NRB + i) * p.KBS + ks) * BLK2;
+      tc::bulk_g2s(stage + BLK2 + i * BLK, blk, BLK, bar);
+      tc::bulk_g2s(stage + BLK2 + p.NRB * BLK + i * BLK, blk + BLK, BLK, bar);
+    }
+  }
+  __device__ static __forceinline__ void mma(const Params &p, int, int, uint32_t st, uint32_t tacc, bool first) {
+    const uint32_t id = tc::instr_desc(128, 128 * p.NRB, 0, 0);
+    const uint64_t ah = tc::desc_kmajor(st, 0), al = tc::desc_kmajor(st + BLK, 0);
+    const uint64_t bh = tc::desc_kmajor(st + BLK2, 0), bl = tc::desc_kmajor(st + BLK2 + p.NRB * BLK, 0);
+    bool acc = !first;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tacc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id, acc); acc = true; }
+    }
+  }
+  struct Epi {
+    float *xp;
+    int q, cq, lane, rsub, csub;
+    float step_size, inv_bc2_sqrt;
+    __device__ __forceinline__ Epi(const Params &p, uint8_t *extra, int tid) {
+      const int warp = tid >> 5;
+      lane = tid & 31; q = warp & 3; cq = warp >> 2;
+      xp = reinterpret_cast<float *>(extra) + warp * (32 * 20);
+      rsub = lane >> 2; csub = (lane & 3) * 4;
+      step_size = p.sc ? p.sc[0] : p.step_size;
+      inv_bc2_sqrt = p.sc ? p.sc[1] : p.inv_bc2_sqrt;
+    }
+    __device__ __forceinline__ void tile(const Params &p, int u, int, uint32_t tacc) {
+      const int t = u / p.n_dchunks, dc = u - t * p.n_dchunks;
+      const int N = 128 * p.NRB;
+      const int v0 = t * 128 + q * 32;
+      const int nrows = min(32, p.Vloc - v0);  // may be <= 0 in the last tile
+      const int col0 = dc * N + cq * (N / 2);
+      for (int pc = 0; pc < N / 32; ++pc) {     // 16-column pieces of this warp's column half
+        float g[16];
+        tc::tmem_ld16(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * (N / 2) + pc * 16), g);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(xp + lane * 20 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
+        __syncwarp();
+        float4 G[4], P[4], M[4], U[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) G[i] = *reinterpret_cast<const float4 *>(xp + (i * 8 + rsub) * 20 + csub);
+        __syncwarp();
+        if (nrows > 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = min(i * 8 + rsub, nrows - 1);
+            const int64_t off = (int64_t)(v0 + r) * p.D + col0 + pc * 16 + csub;
+            P[i] = *reinterpret_cast<const float4 *>(p.w + off);
+            M[i] = *reinterpret_cast<const float4 *>(p.wm + off);
+            U[i] = *reinterpret_cast<const float4 *>(p.wv + off);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + rsub;
+            adam_elem(P[i].x, M[i].x, U[i].x, G[i].x, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
+            adam_elem(P[i].y, M[i].y, U[i].y, G[i].y, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
+            adam_elem(P[i].z, M[i].z, U[i].z, G[i].z, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
+            adam_elem(P[i].w, M[i].w, U[i].w, G[i].w, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
+            if (r < nrows) {
+              const int64_t off = (int64_t)(v0 + r) * p.D + col0 + pc * 16 + csub;
+              *reinterpret_cast<float4 *>(p.w + off) = P[i];
+              *reinterpret_cast<float4 *>(p.wm + off) = M[i];
+              *reinterpret_cast<float4 *>(p.wv + off) = U[i];
+            }
+          }
+        }
+      }
+      if (dc == 0 && cq == 0 && lane < nrows) {  // bias of this tile's rows: gradient = sum of the per-session-block partials
+        float g = 0.f;
+        for (int sb = 0; sb < p.n_sb; ++sb) g += p.db_part[((int64_t)sb * p.n_tiles + t) * 128 + q * 32 + lane];
+        float bp = p.b[v0 + lane], m = p.bm[v0 + lane], v = p.bv[v0 + lane];
+        adam_elem(bp, m, v, g, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
+        p.b[v0 + lane] = bp; p.bm[v0 + lane] = m; p.bv[v0 + lane] = v;
+      }
+    }
+    __device__ __forceinline__ void finish(const Params &) {}
+  };
+};
+
+template <class OP>
+static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
+  const size_t smem = 1024 + (size_t)OP::STAGES * OP::STAGE_BYTES + OP::EXTRA_BYTES;
+  static bool attr_set[REC_MAX_DEVICES] = {};
+  if (!attr_set[e->dev]) {
+    REC_CUDA(e, cudaFuncSetAttribute(tck_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[e->dev] = true;
+  }
+  tck_kernel<OP><<<grid, THREADS, smem, e->stream>>>(p);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+}  // namespace tck
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------------
+bool tck_heads_supported(const rec_engine *e) { return e->use_tc && e->D >= 128 && e->D % 128 == 0 && e->D <= 1024; }
+
+static int tck_alloc(rec_engine *e, void **ptr, size_t bytes) {
+  if (*ptr) return REC_OK;
+  cudaError_t st = cudaMalloc(ptr, bytes);
+  if (st != cudaSuccess) REC_FAIL(e, REC_ENOMEM, "cudaMalloc(%zu B) for the tensor-core head images failed: %s", bytes, cudaGetErrorString(st));
+  return REC_OK;
+}
+
+// Operand images are sized by max_batch / Vloc / D at first use and live as long as the engine.
+static int tck_ensure(rec_engine *e) {
+  const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(e->cfg.max_batch, 128);
+  int rc;
+  const size_t wbytes = (size_t)n_tiles * KB * tck::BLK2;
+  for (int i = 0; i < 2; ++i) if ((rc = tck_alloc(e, (void **)&e->k_wimg[i], wbytes))) return rc;
+  for (int i = 0; i < 2; ++i) if ((rc = tck_alloc(e, (void **)&e->k_himg[i], (size_t)n_sb * KB * tck::BLK2))) return rc;
+  if ((rc = tck_alloc(e, (void **)&e->k_hT, (size_t)(e->D / 128) * (2 * n_sb) * tck::BLK2))) return rc;
+  if ((rc = tck_alloc(e, (void **)&e->k_dlT, (size_t)n_tiles * (2 * n_sb) * tck::BLK2))) return rc;
+  if ((rc = tck_alloc(e, (void **)&e->k_db, sizeof(float) * (size_t)n_sb * n_tiles * 128))) return rc;
+  if ((rc = tck_alloc(e, (void **)&e->k_bias, sizeof(float) * (size_t)n_tiles * 128))) return rc;
+  return REC_OK;
+}
+
+void tck_free(rec_engine *e) {
+  void *ptrs[] = {e->k_wimg[0], e->k_wimg[1], e->k_himg[0], e->k_himg[1], e->k_hT, e->k_dlT, e->k_db, e->k_bias};
+  for (void *p : ptrs) if (p) cudaFree(p);
+}
+
+static int tck_pack(rec_engine *e, const tck::PackSrc &s, int R, int C, uint8_t *img) {
+  const int64_t n_chunks = (int64_t)cdiv(R, 128) * 128 * (C / 8);
+  int64_t blocks = cdiv64(n_chunks, 256);
+  const int64_t cap = (int64_t)e->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  tck::pack_img_kernel<<<(int)blocks, 256, 0, e->stream>>>(s, R, C, C, img);
+  REC_LAUNCH_CHECK(e);
+  return REC_OK;
+}
+
+// Same contract as launch_head_stats (heads.cu) for statistics (no top-k) and the greedy-action pass.
+int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
+  int rc = tck_ensure(e);
+  if (rc) return rc;
+  const rec_net_params &np = e->nets[a.net_id].p;
+  const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(a.B, 128);
+  const bool arg = a.n_arg > 0;
+  if (arg && a.n_arg > 3) REC_FAIL(e, REC_EINVAL, "greedy-action pass supports at most 3 Q heads (got %d)", a.n_arg);
+  // weight image of the scored head(s)
+  tck::PackSrc ws = {};
+  uint8_t *wimg = e->k_wimg[arg ? 1 : 0];
+  const float *bias;
+  if (arg) {
+    ws.n = a.n_arg;
+    for (int j = 0; j < a.n_arg; ++j) { ws.p[j] = np.head_w[1 + j]; ws.w[j] = a.n_arg > 1 ? a.w[j] : 1.f; }
+    if (a.n_arg > 1) {
+      tck::PackSrc bs = ws;
+      for (int j = 0; j < a.n_arg; ++j) bs.p[j] = np.head_b[1 + j];
+      tck::bias_combine_kernel<<<cdiv(e->Vloc, 256), 256, 0, e->stream>>>(bs, e->Vloc, e->k_bias);
+      REC_LAUNCH_CHECK(e);
+      bias = e->k_bias;
+    } else {
+      bias = np.head_b[1];
+    }
+  } else {
+    ws.n = 1; ws.p[0] = np.head_w[a.stats_head]; ws.w[0] = 1.f;
+    bias = np.head_b[a.stats_head];
+  }
+  if ((rc = tck_pack(e, ws, e->Vloc, e->D, wimg))) return rc;
+  if (!arg) { e->k_sup_net = a.net_id; e->k_sup_head = a.stats_head; }
+  // state image
+  tck::PackSrc hs = {};
+  hs.n = 1; hs.p[0] = a.h; hs.w[0] = 1.f;
+  uint8_t *himg = e->k_himg[arg ? 1 : 0];
+  if ((rc = tck_pack(e, hs, a.B, e->D, himg))) return rc;
+
+  int n_split = e->sm_count / n_sb;
+  if (n_split > n_tiles) n_split = n_tiles;
+  if (n_split < 1) n_split = 1;
+  const int per = cdiv(n_tiles, n_split);
+  n_split = cdiv(n_tiles, per);
+  tck::FwdParams p = {};
+  p.himg = himg; p.wimg = wimg; p.KB = KB; p.B = a.B; p.Vloc = e->Vloc; p.vocab_lo = e->cfg.vocab_lo; p.n_tiles = n_tiles;
+  p.bias = bias; p.target = arg ? nullptr : a.target; p.part = e->part; p.part_stride = e->part_stride;
+  dim3 grid(n_split, n_sb);
+  rc = arg ? tck::launch_tck<tck::HeadFwd<tck::M_ARG>>(e, grid, p) : tck::launch_tck<tck::HeadFwd<tck::M_STATS>>(e, grid, p);
+  if (rc) return rc;
+  *n_split_out = n_split;
+  e->st_approx = true;
+  e->st_kpub = 0;
+  e->st_apub = arg ? 2 : 0;
+  return REC_OK;
+}
+
+int tck_bwd_slices(const rec_engine *e) {
+  const int n_tiles = cdiv(e->Vloc, 128), KB = e->D / 64;
+  const int NCB = KB % 4 == 0 ? 4 : 2, n_dchunks = KB / NCB;
+  const int n_sb_max = cdiv(e->cfg.max_batch, 128);
+  int n_split = e->sm_count / (n_dchunks * (n_sb_max < 2 ? n_sb_max : 2));
+  if (n_split > n_tiles) n_split = n_tiles;
+  if (n_split > e->n_dh_part - 1) n_split = e->n_dh_part - 1;
+  if (n_split < 1) n_split = 1;
+  const int per = cdiv(n_tiles, n_split);
+  return cdiv(n_tiles, per);
+}
+
+// Supervised head backward + Adam for D >= 128: dlogits image -> (dh partial slices || dW + Adam).
+// Writes tck_bwd_slices(e) slices of dh_part (every slice fully).
+int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                             float bc2_sqrt, const rec_train_hparams *hp, float inv_B) {
+  int rc = tck_ensure(e);
+  if (rc) return rc;
+  const rec_net_params &np = e->nets[net_id].p;
+  const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(B, 128);
+  uint8_t *wimg = e->k_wimg[0];
+  if (e->k_sup_net != net_id || e->k_sup_head != 0) {  // the statistics pass of this step packed another head
+    tck::PackSrc ws = {};
+    ws.n = 1; ws.p[0] = np.head_w[0]; ws.w[0] = 1.f;
+    if ((rc = tck_pack(e, ws, e->Vloc, e->D, wimg))) return rc;
+    tck::PackSrc hs = {};
+    hs.n = 1; hs.p[0] = h; hs.w[0] = 1.f;
+    if ((rc = tck_pack(e, hs, B, e->D, e->k_himg[0]))) return rc;
+  }
+  e->k_sup_net = -1;
+  const int KBS = 2 * n_sb;
+  tck::pack_img_T_kernel<<<cdiv(e->D * KBS * 8, 256), 256, 0, e->stream>>>(h, B, e->D, KBS, e->k_hT);
+  REC_LAUNCH_CHECK(e);
+  // (1) dlogits image + bias-gradient partials
+  {
+    int n_split = e->sm_count / n_sb;
+    if (n_split > n_tiles) n_split = n_tiles;
+    if (n_split < 1) n_split = 1;
+    const int per = cdiv(n_tiles, n_split);
+    n_split = cdiv(n_tiles, per);
+    tck::FwdParams p = {};
+    p.himg = e->k_himg[0]; p.wimg = wimg; p.KB = KB; p.B = B; p.Vloc = e->Vloc; p.vocab_lo = e->cfg.vocab_lo; p.n_tiles = n_tiles;
+    p.bias = np.head_b[0]; p.target = b->a; p.row_stats = e->row_stats; p.inv_B = inv_B;
+    p.dlT = e->k_dlT; p.dl_cb = KBS; p.db_part = e->k_db;
+    if ((rc = tck::launch_tck<tck::HeadFwd<tck::M_DL>>(e, dim3(n_split, n_sb), p))) return rc;
+  }
+  // (2) dh partial slices (reads the weight IMAGE: independent of the Adam update below)
+  {
+    const int NCB = KB % 4 == 0 ? 4 : 2, n_dchunks = KB / NCB;
+    int n_split = e->sm_count / (n_dchunks * n_sb);
+    if (n_split > n_tiles) n_split = n_tiles;
+    const int n_slices = tck_bwd_slices(e);
+    if (n_split > n_slices) n_split = n_slices;
+    if (n_split < 1) n_split = 1;
+    const int per = cdiv(n_tiles, n_split);
+    n_split = cdiv(n_tiles, per);
+    tck::DhParams p = {};
+    p.dlT = e->k_dlT; p.wimg = wimg; p.KB = KB; p.NCB = NCB; p.dl_cb = KBS; p.n_tiles = n_tiles; p.B = B; p.D = e->D;
+    p.dh_part = e->dh_part;
+    if (n_split < n_slices)  // slices the split does not reach must still read as zero
+      REC_CUDA(e, cudaMemsetAsync(e->dh_part + (int64_t)n_split * B * e->D, 0, sizeof(float) * (size_t)(n_slices - n_split) * B * e->D, e->stream));
+    if ((rc = tck::launch_tck<tck::HeadDh>(e, dim3(n_split, n_dchunks, n_sb), p))) return rc;
+  }
+  // (3) dW + Adam
+  {
+    const int NRB = e->D % 256 == 0 ? 2 : 1, n_dchunks = e->D / (128 * NRB);
+    const int total = n_tiles * n_dchunks;
+    int n_cta = e->sm_count < total ? e->sm_count : total;
+    tck::DwParams p = {};
+    p.dlT = e->k_dlT; p.hT = e->k_hT; p.KBS = KBS; p.NRB = NRB; p.n_dchunks = n_dchunks; p.n_tiles = n_tiles; p.Vloc = e->Vloc;
+    p.D = e->D; p.n_sb = n_sb;
+    p.w = np.head_w[0]; p.wm = np.head_w_m[0]; p.wv = np.head_w_v[0]; p.b = np.head_b[0]; p.bm = np.head_b_m[0]; p.bv = np.head_b_v[0];
+    p.db_part = e->k_db; p.b1 = hp->beta1; p.b2 = hp->beta2; p.eps = hp->eps; p.step_size = step_size; p.inv_bc2_sqrt = 1.f / bc2_sqrt;
+    p.sc = e->d_sc;
+    if ((rc = tck::launch_tck<tck::HeadDwAdam>(e, dim3(n_cta), p))) return rc;
+  }
+  return REC_OK;
+}

@@ -1,5 +1,5 @@
 """cfg3 (BidirGRU4Rec SQN, V=N=250000, L=50, E=H=256, B=256): device-timed train step (generic CUDA-core kernels)."""
-import sys, torch, time
+import os, sys, torch, time
 sys.path.insert(0, '/root/repo')
 import b200pkg; pkg = b200pkg.load()
 from ikea_recommender_system_b200 import synthetic
@@ -14,7 +14,7 @@ for i in range(4): t.train_step_async(*bs[i])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-n = 10
+n = int(os.environ.get('N_STEPS', '10'))
 for i in range(n): t.train_step_async(*bs[i % 8])
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n

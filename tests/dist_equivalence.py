@@ -55,8 +55,9 @@ def main():
         if os.environ.get("DIST_REGROW") and i == 8:
             # a batch beyond the engine's max_batch re-creates the native handle: the step graphs captured so far
             # point at freed workspace and must be dropped; training continues bit-for-bit afterwards
-            big = synthetic.make_replay_rows(B * world * 3, V, L, seed=99)
-            sb, _, _, _, lb, _, _ = synthetic.as_torch_batch(big, 0, B * world * 3)
+            nbig = t._engine.max_batch + 64
+            big = synthetic.make_replay_rows(nbig, V, L, seed=99)
+            sb, _, _, _, lb, _, _ = synthetic.as_torch_batch(big, 0, nbig)
             gen0 = t._engine.generation
             _ = t.SMORL_1.final_state(sb, lb)
             assert t._engine.generation > gen0
