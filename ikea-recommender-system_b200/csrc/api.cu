@@ -109,6 +109,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   e->n_dh_part = (n_tiles < 2 * e->sm_count ? n_tiles : 2 * e->sm_count) + 1;
   ALLOC(e, e->dh_part, float, (int64_t)e->n_dh_part * mb * D);
   e->wgrad_splits = 64;
+  e->wgrad_used = 64;
   const int64_t KS = (E > H ? E : H) + 1;
   ALLOC(e, e->wgrad_part, float, (int64_t)e->wgrad_splits * dirs * 2 * G * KS);
   ALLOC(e, e->emb_keys, int32_t, mb * L);
@@ -215,6 +216,7 @@ extern "C" void rec_destroy(rec_engine *e) {
                   extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_csort, e->emb_ccount, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block};
   for (void *p : ptrs) if (p) cudaFree(p);
   tck_free(e);
+  gtc_free(e);
   for (int n = 0; n < REC_MAX_NETS; ++n)
     for (int d = 0; d < 2; ++d) {
       if (e->nets[n].w_ihT[d]) cudaFree(e->nets[n].w_ihT[d]);
@@ -393,7 +395,7 @@ __global__ void copy_batch_kernel(rec_batch src, rec_batch dst, int L) {
 }
 
 void rec_timeline_record(rec_engine *e, const char *file, int line) {
-  if (e->tl_n >= 96) return;
+  if (e->tl_n >= 400) return;
   rec_engine::TlEntry &t = e->tl[e->tl_n++];
   if (!t.ev) cudaEventCreate(&t.ev);
   t.file = file; t.line = line;
@@ -955,7 +957,7 @@ extern "C" int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank,
                                e->cur_bc2_sqrt, &e->cur_hp, 1 | 2);
   if (rc) return rc;
   const int n = (int)rec_dp_grad_floats(e);
-  sum_splits_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(e->wgrad_part, e->wgrad_splits, n, gru_grads_out);
+  sum_splits_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(e->wgrad_part, e->wgrad_used, n, gru_grads_out);
   REC_LAUNCH_CHECK(e);
   REC_CUDA(e, cudaMemcpyAsync(dx_out, e->dx, sizeof(float) * (size_t)B * e->cfg.state_size * e->dirs * e->cfg.embedding_dim,
                               cudaMemcpyDeviceToDevice, e->stream));
@@ -973,15 +975,15 @@ extern "C" int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const
   e->cur_phase = 0;
   // the launchers read the engine's buffers: point them at the reduced / gathered data for this call
   float *const own_part = e->wgrad_part, *const own_dx = e->dx;
-  const int own_splits = e->wgrad_splits;
-  e->wgrad_part = const_cast<float *>(gru_grads_reduced); e->wgrad_splits = 1; e->dx = const_cast<float *>(dx_gathered);
+  const int own_splits = e->wgrad_splits, own_used = e->wgrad_used;
+  e->wgrad_part = const_cast<float *>(gru_grads_reduced); e->wgrad_splits = 1; e->wgrad_used = 1; e->dx = const_cast<float *>(dx_gathered);
   int rc;
   {
     SideScope side(e, 1);  // embedding chain over the GLOBAL positions next to the GRU Adam
     rc = launch_embedding_update(e, main_net, gb->s, gb->true_len, gb->B, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, 7);
   }
   if (!rc) rc = launch_gru_backward(e, main_net, gb->s, gb->true_len, gb->B, nullptr, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, 4);
-  e->wgrad_part = own_part; e->wgrad_splits = own_splits; e->dx = own_dx;
+  e->wgrad_part = own_part; e->wgrad_splits = own_splits; e->wgrad_used = own_used; e->dx = own_dx;
   for (int i = 0; i < 3; ++i) side_join(e, i);
   return rc;
 }

@@ -39,6 +39,7 @@ struct rec_engine {
   int n_dh_part;
   float *wgrad_part;     // [splits][dirs][3H][E+H+2]
   int wgrad_splits;
+  int wgrad_used;        // split-K slices the most recent weight-gradient launch wrote (<= wgrad_splits)
   int32_t *emb_keys;     // [maxB*L] row id or -1
   int32_t *emb_slot;     // [N+1] slot of the leader position or -1
   float *emb_grad_rows;  // [maxB*L, E]
@@ -90,7 +91,7 @@ struct rec_engine {
   bool overlap;        // REC_NO_OVERLAP=1 serialises everything on the caller's stream
   bool tl_on;          // REC_TIMELINE=1
   int tl_n, tl_steps;
-  struct TlEntry { cudaEvent_t ev; const char *file; int line; int stream; } tl[96];
+  struct TlEntry { cudaEvent_t ev; const char *file; int line; int stream; } tl[400];
   bool side_dirty[3];  // work was issued on side[i] since its last join
   rec_batch own;         // engine-owned copy of the caller's batch (pointers into own_block)
   uint8_t *own_block, *h_own;  // device block and its pinned host mirror (host entry points)
@@ -114,6 +115,15 @@ struct rec_engine {
   float *k_db;           // bias-gradient partials [session blocks][V]
   float *k_bias;         // combined bias of the greedy-action heads
   int k_sup_net, k_sup_head;  // which (net, head) k_wimg[0] / k_himg[0] currently hold (-1: none)
+  // tensor-core GRU trunk for E, H >= 128 (gru_tc.cu); allocated at first use
+  uint8_t *g_wimg;       // [net][dir][W_ih | W_hh | W_hh regrouped] weight images
+  uint8_t *g_ximg[2], *g_ximg2;  // gathered embedding rows of s / s' (main table) / s' (bootstrap table)
+  float *g_gi[3];        // [B L, dirs, 3H] input projections per pass
+  uint8_t *g_himg[2];    // ping/pong bf16 images of h_t: [pass][dir][session block][H/64]
+  uint8_t *g_hprev_img;  // [dir][B L][H] image of h_{t-1} per position (dW_hh GEMM)
+  uint8_t *g_dstep[2];   // ping/pong images of the gate gradients of one step: [dir][session block][3H/64]
+  uint8_t *g_dgi_img, *g_dgh_img;  // [dir][B L][3H] images of the gate gradients (dx / weight-gradient GEMMs)
+  float *g_dhw;          // [B, D] running dL/dh of the BPTT
 };
 
 #define REC_FAIL(e, code, ...)                          \
@@ -285,6 +295,13 @@ int tck_bwd_slices(const rec_engine *e);
 int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                              float bc2_sqrt, const rec_train_hparams *hp, float inv_B);
 void tck_free(rec_engine *e);
+// gru_tc.cu: GRU trunk for E, H multiples of 128
+bool gru_tc_supported(const rec_engine *e);
+int launch_gru_forward_tc(rec_engine *e, int n_pass, const int *net_ids, const int64_t *const *s,
+                          const int64_t *const *lengths, float *const *h_out, const bool *save, int B);
+int launch_gru_backward_tc(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B, const float *dh,
+                           int stages);
+void gtc_free(rec_engine *e);
 int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                             float bc2_sqrt, const rec_train_hparams *hp, float inv_B, int *n_slices);
 int launch_h_prepack_early(rec_engine *e, const float *h, int B);

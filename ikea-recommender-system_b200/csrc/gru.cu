@@ -647,6 +647,7 @@ int launch_gru_forward_multi(rec_engine *e, int n_pass, const int *net_ids, cons
     REC_LAUNCH_CHECK(e);
     return REC_OK;
   }
+  if (gru_tc_supported(e)) return launch_gru_forward_tc(e, n_pass, net_ids, s, lengths, h_out, save, B);
   for (int i = 0; i < n_pass; ++i) {
     int rc = launch_gru_forward(e, net_ids[i], s[i], lengths[i], B, h_out[i], save[i]);
     if (rc) return rc;
@@ -657,7 +658,7 @@ int launch_gru_forward_multi(rec_engine *e, int n_pass, const int *net_ids, cons
 int launch_gru_forward(rec_engine *e, int net_id, const int64_t *s, const int64_t *lengths, int B,
                        float *h_out, bool save) {
   const rec_config &c = e->cfg;
-  if (gru_fast_path(e)) {
+  if (gru_fast_path(e) || gru_tc_supported(e)) {
     const int64_t *sa[1] = {s}, *la[1] = {lengths};
     float *ha[1] = {h_out};
     return launch_gru_forward_multi(e, 1, &net_id, sa, la, ha, &save, B);
@@ -688,6 +689,13 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
     REC_CUDA(e, cudaFuncSetAttribute(gru_bwd_kernel<GRU_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[e->dev] = true;
   }
+  if (!gru_fast_path(e) && gru_tc_supported(e)) {
+    if (stages & 3) {
+      int rc = launch_gru_backward_tc(e, net_id, s, lengths, B, dh, stages & 3);
+      if (rc) return rc;
+    }
+    stages &= 4;
+  }
   if (stages & 1) {
     if (gru_fast_path(e)) {
       dim3 grid(cdiv(B, BR), e->dirs);
@@ -703,6 +711,7 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
   }
   // weight gradients (split over token positions) + Adam on the GRU parameters
   const int KS = (E > H ? E : H) + 1;
+  if (stages & 2) e->wgrad_used = e->wgrad_splits;
   const int splits = e->wgrad_splits;
   if (stages & 2) {
     dim3 g2(cdiv(G, 64), cdiv(E > H ? E : H, 64), e->dirs * 2 * splits);
@@ -722,7 +731,7 @@ int launch_gru_backward(rec_engine *e, int net_id, const int64_t *s, const int64
     q.wiT[d] = nb.w_ihT[d]; q.whT[d] = nb.w_hhT[d];
   }
   int total = (G * E + G * H + 2 * G) * e->dirs;
-  gru_adam_kernel<<<cdiv(total, 64), 256, 0, e->stream>>>(q, e->wgrad_part, splits, e->dirs, E, H, KS, hp->beta1,
+  gru_adam_kernel<<<cdiv(total, 64), 256, 0, e->stream>>>(q, e->wgrad_part, e->wgrad_used, e->dirs, E, H, KS, hp->beta1,
                                                           hp->beta2, hp->eps, step_size, bc2_sqrt, e->d_sc);
   REC_LAUNCH_CHECK(e);
   return REC_OK;

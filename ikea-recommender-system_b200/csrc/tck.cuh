@@ -1,0 +1,188 @@
+// Skeleton of the K-loop tcgen05 GEMM pipelines over packed bf16 hi/lo operand images (see heads_tck.cu for the image
+// format): packing kernels, the warp-specialised kernel template and its launcher.  Included by heads_tck.cu (wide
+// heads) and gru_tc.cu (GRU trunk for E, H >= 128).
+#pragma once
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tck {
+
+constexpr int BLK = 16384;      // one [128][64] bf16 operand block
+constexpr int BLK2 = 2 * BLK;   // hi + lo
+constexpr int HALF = 8192;      // 64 rows of a block
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_THREADS + 64;  // + issuer warp + loader warp
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int ROW_STRIDE_ = 8;  // row_stats stride (heads.cu)
+constexpr int TOPK_OFF = 5;     // part record layout (heads.cu / heads_tc.cu)
+
+// ------------------------------------------------------------------------------------------------------------
+// Packing
+// ------------------------------------------------------------------------------------------------------------
+struct PackSrc {
+  const float *p[3];
+  float w[3];
+  int n;
+};
+
+// fp32 row-major [R, C] (leading dimension ld) -> image; rows in [R, 128 * ceil(R/128)) are written as zeros.
+static __global__ void __launch_bounds__(256) pack_img_kernel(PackSrc s, int R, int C, int64_t ld, uint8_t *__restrict__ img) {
+  const int c8n = C >> 3, KB = C >> 6;
+  const int64_t n_chunks = (int64_t)((R + 127) / 128) * 128 * c8n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / c8n;
+    const int c8 = (int)(i - row * c8n);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (row < R) {
+      const float4 *p0 = reinterpret_cast<const float4 *>(s.p[0] + row * ld + c8 * 8);
+      a = p0[0]; b = p0[1];
+      if (s.n > 1 || s.w[0] != 1.f) {
+        const float w0 = s.w[0];
+        a.x *= w0; a.y *= w0; a.z *= w0; a.w *= w0; b.x *= w0; b.y *= w0; b.z *= w0; b.w *= w0;
+        for (int j = 1; j < s.n; ++j) {
+          const float4 *pj = reinterpret_cast<const float4 *>(s.p[j] + row * ld + c8 * 8);
+          const float4 x = pj[0], y = pj[1];
+          const float w = s.w[j];
+          a.x = fmaf(w, x.x, a.x); a.y = fmaf(w, x.y, a.y); a.z = fmaf(w, x.z, a.z); a.w = fmaf(w, x.w, a.w);
+          b.x = fmaf(w, y.x, b.x); b.y = fmaf(w, y.y, b.y); b.z = fmaf(w, y.z, b.z); b.w = fmaf(w, y.w, b.w);
+        }
+      }
+    }
+    uint8_t *blk = img + ((row >> 7) * KB + (c8 >> 3)) * (int64_t)BLK2;
+    tc::store_split8(blk, blk + BLK, (int)(row & 127), c8 & 7, a, b);
+  }
+}
+
+// h [B, D] -> image of h^T: rows = state dimension d (D % 128 == 0), columns = sessions (KBS = ceil(B/64) blocks,
+// sessions beyond B are zeros).  The matrix is tiny (<= 512 KB): strided reads are fine.
+static __global__ void __launch_bounds__(256) pack_img_T_kernel(const float *__restrict__ h, int B, int D, int KBS,
+                                                        uint8_t *__restrict__ img) {
+  const int c8n = KBS * 8;
+  const int n_chunks = D * c8n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += gridDim.x * blockDim.x) {
+    const int c8 = i / D, row = i - c8 * D;  // consecutive threads: consecutive d -> coalesced reads of h rows
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = c8 * 8 + j;
+      v[j] = b < B ? h[(int64_t)b * D + row] : 0.f;
+    }
+    uint8_t *blk = img + ((int64_t)(row >> 7) * KBS + (c8 >> 3)) * BLK2;
+    tc::store_split8(blk, blk + BLK, row & 127, c8 & 7, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
+static __global__ void bias_combine_kernel(PackSrc s, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = s.w[0] * s.p[0][i];
+  for (int j = 1; j < s.n; ++j) acc = fmaf(s.w[j], s.p[j][i], acc);
+  out[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Kernel skeleton
+// ------------------------------------------------------------------------------------------------------------
+// OP supplies:  STAGES, STAGE_BYTES, ACC_COLS (TMEM columns of one accumulator), TMEM_COLS (allocation, power of 2),
+//   units(p, lo, hi)            this CTA's range of output units (an accumulator's worth of output each)
+//   k_steps(p, u)               pipeline stages consumed by unit u
+//   load(p, u, ks, stage, bar)  ONE thread: expect_tx + TMA bulk copies of stage (u, ks)
+//   mma(p, u, ks, saddr, tacc, first)  ONE thread: the tcgen05.mma's of stage (u, ks) into accumulator tacc
+//   Epi                         per-thread epilogue object: tile(p, u, i, tacc) per unit, finish(p) at the end
+template <class OP>
+__global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Params p) {
+  extern __shared__ uint8_t raw[];
+  uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int u_lo = 0, u_hi = 0;
+  OP::units(p, u_lo, u_hi);
+  if (tid == 0) {
+    for (int s = 0; s < OP::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, OP::TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  uint8_t *extra = sm + OP::STAGES * OP::STAGE_BYTES;
+
+  if (warp == EPI_WARPS + 1) {
+    // ---- TMA loader ----
+    if (lane == 0) {
+      int s = 0;
+      uint32_t round = 0;
+      for (int u = u_lo; u < u_hi; ++u) {
+        const int nk = OP::k_steps(p, u);
+        for (int ks = 0; ks < nk; ++ks) {
+          if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage are complete
+          OP::load(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+          if (++s == OP::STAGES) { s = 0; ++round; }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    // ---- MMA issuer ----
+    int s = 0, i = 0;
+    uint32_t round = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++i) {
+      const int b = i & 1;
+      if (i >= 2) tc::mbar_wait(&tempty[b], ((i - 2) >> 1) & 1);  // the epilogue has read this accumulator
+      tc::tc_fence_after();
+      const int nk = OP::k_steps(p, u);
+      for (int ks = 0; ks < nk; ++ks) {
+        tc::mbar_wait(&full[s], round & 1);
+        tc::tc_fence_after();
+        if (lane == 0) {
+          OP::mma(p, u, ks, tc::smem_u32(sm + s * OP::STAGE_BYTES), tmem + (uint32_t)(b * OP::ACC_COLS), ks == 0);
+          tc::mma_commit(&empty[s]);
+        }
+        __syncwarp();
+        if (++s == OP::STAGES) { s = 0; ++round; }
+      }
+      if (lane == 0) tc::mma_commit(&tfull[b]);
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue warps ----
+    typename OP::Epi epi(p, extra, tid);
+    int i = 0;
+    for (int u = u_lo; u < u_hi; ++u, ++i) {
+      const int b = i & 1;
+      tc::mbar_wait(&tfull[b], (i >> 1) & 1);
+      tc::tc_fence_after();
+      epi.tile(p, u, i, tmem + (uint32_t)(b * OP::ACC_COLS));
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[b]);
+    }
+    epi.finish(p);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, OP::TMEM_COLS);
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+template <class OP>
+static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
+  const size_t smem = 1024 + (size_t)OP::STAGES * OP::STAGE_BYTES + OP::EXTRA_BYTES;
+  static bool attr_set[REC_MAX_DEVICES] = {};
+  if (!attr_set[e->dev]) {
+    REC_CUDA(e, cudaFuncSetAttribute(tck_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[e->dev] = true;
+  }
+  tck_kernel<OP><<<grid, THREADS, smem, e->stream>>>(p);
+  e->launches++;
+  if (e->tl_on) rec_timeline_record(e, OP::NAME, 0);
+  cudaError_t st = cudaGetLastError();
+  if (st != cudaSuccess) REC_FAIL(e, REC_ECUDA, "kernel launch failed: %s (%s)", cudaGetErrorString(st), OP::NAME);
+  return REC_OK;
+}
+
+}  // namespace tck
