@@ -122,7 +122,7 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   e->emb_csort_n = (int)((mb * L + 4095) / 4096 * 4096);
   ALLOC(e, e->emb_csort, int32_t, 2 * (int64_t)e->emb_csort_n);
   ALLOC(e, e->emb_ccount, int32_t, 16);
-  ALLOC(e, e->emb_carry, float, (mb * L / 32 + 1) * 64);
+  ALLOC(e, e->emb_carry, float, (mb * L / 32 + 1) * (int64_t)(E > 64 ? E : 64));
   ALLOC(e, e->emb_tmeta, int32_t, (mb * L / 32 + 1) * 2);
   e->part_stride = 72;
   e->n_split_max = 2 * e->sm_count;
@@ -557,7 +557,12 @@ static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hp
   const int B = b->B;
   const bool drop = hp->dropout_p > 0.f;
   e->hpack_ready = false;
+  if (tck_heads_supported(e)) {  // weight image of the head: packed next to the GRU forward
+    SideScope side(e, 0);
+    if ((rc = tck_prepack_heads(e, 0, 0, nullptr))) return rc;
+  }
   if ((rc = launch_gru_forward(e, 0, b->s, b->true_len, B, e->h_state[0], true))) return rc;
+  if (tck_heads_supported(e)) side_join(e, 0);
   if (drop && (rc = launch_dropout(e, 0, e->h_state[0], nullptr, B, hp, false))) return rc;  // heads see the dropped state
   HeadStatsArgs a = {};
   a.net_id = 0; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
@@ -629,6 +634,11 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
     SideScope side(e, 1);
     if ((rc = launch_embedding_update(e, main_net, b->s, b->true_len, B, step_size, bc2_sqrt, hp, 1))) return rc;
   }
+  if (tck_heads_supported(e)) {  // weight images of the heads (D >= 128): packed next to the GRU forward
+    SideScope side(e, 0);
+    const float wq[3] = {n_q == 3 ? hp->q_weights[0] : 1.f, hp->q_weights[1], hp->q_weights[2]};
+    if ((rc = tck_prepack_heads(e, main_net, n_q, wq))) return rc;
+  }
   // three GRU passes: main(s, len) [saved], main(s', len'), boot(s', len)  -- (q1) boot sees true_len
   {
     const int nets[3] = {main_net, main_net, boot};
@@ -638,6 +648,7 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
     const bool sv[3] = {true, false, false};
     if ((rc = launch_gru_forward_multi(e, 3, nets, ss, ll, hh, sv, B))) return rc;
   }
+  if (tck_heads_supported(e)) side_join(e, 0);
   if (tc_bwd_supported(e, B)) {  // operand image of the supervised-head backward: only needs the forward pass
     SideScope side(e, 0);
     if ((rc = launch_h_prepack_early(e, e->h_state[0], B))) return rc;
@@ -673,9 +684,12 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
     if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
     REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
     static const int sweep_mark = getenv("REC_SWEEP_EARLY") ? -1 : 2;
-    if ((rc = launch_q_heads_update(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp, sweep_mark))) return rc;
+    // wide heads (D >= 128): mark 3 = dh slices final; the sweep then shares the HBM with the supervised head's dW + Adam
+    // kernel while the latency-bound GRU backward runs on the SMs that kernel leaves free
+    if ((rc = launch_q_heads_update(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp,
+                                    tck_heads_supported(e) && sweep_mark >= 0 ? 3 : sweep_mark))) return rc;
   }
-  side_wait_mark(e, 2);
+  side_wait_mark(e, tck_heads_supported(e) ? 3 : 2);
   if ((rc = launch_dh_reduce(e, B))) return rc;
   if ((rc = trunk_backward(e, main_net, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp, true))) return rc;
   side_join(e, 0);

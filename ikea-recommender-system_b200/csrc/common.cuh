@@ -115,6 +115,7 @@ struct rec_engine {
   float *k_db;           // bias-gradient partials [session blocks][V]
   float *k_bias;         // combined bias of the greedy-action heads
   int k_sup_net, k_sup_head;  // which (net, head) k_wimg[0] / k_himg[0] currently hold (-1: none)
+  bool k_fresh[2];       // k_wimg[i] was packed ahead of its consumer in this step (tck_prepack_heads)
   // tensor-core GRU trunk for E, H >= 128 (gru_tc.cu); allocated at first use
   uint8_t *g_wimg;       // [net][dir][W_ih | W_hh | W_hh regrouped] weight images
   uint8_t *g_ximg[2], *g_ximg2;  // gathered embedding rows of s / s' (main table) / s' (bootstrap table)
@@ -295,6 +296,7 @@ int tck_bwd_slices(const rec_engine *e);
 int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                              float bc2_sqrt, const rec_train_hparams *hp, float inv_B);
 void tck_free(rec_engine *e);
+int tck_prepack_heads(rec_engine *e, int net_id, int n_arg, const float *w);
 // gru_tc.cu: GRU trunk for E, H multiples of 128
 bool gru_tc_supported(const rec_engine *e);
 int launch_gru_forward_tc(rec_engine *e, int n_pass, const int *net_ids, const int64_t *const *s,

@@ -511,8 +511,11 @@ __global__ void __launch_bounds__(256) emb_merge_rank_kernel(const int32_t *__re
 __global__ void __launch_bounds__(256) emb_tilesum64_kernel(const int32_t *__restrict__ sorted_pos, int32_t *__restrict__ sorted_row,
                                                             int cap, const float *__restrict__ dx, float *__restrict__ grad_rows,
                                                             int32_t *__restrict__ slot_of_row, float *__restrict__ carry,
-                                                            int32_t *__restrict__ tile_meta) {
+                                                            int32_t *__restrict__ tile_meta, int E, int dirs) {
+  // blockIdx.y = 64-column chunk of the embedding row (E = 64: one chunk); dx rows are [position][direction][E] and
+  // the directions of a position are added first (direction order), then the positions in sorted order
   const int lane = threadIdx.x & 31;
+  const int col = blockIdx.y * 64 + 2 * lane;
   const int T = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int n_valid = sorted_row[cap];
   const int n_tiles = (n_valid + 31) >> 5;
@@ -531,13 +534,19 @@ __global__ void __launch_bounds__(256) emb_tilesum64_kernel(const int32_t *__res
   for (int u = 0; u < 32; ++u) {
     const int pp = __shfl_sync(0xffffffffu, pos, u);
     v[u] = make_float2(0.f, 0.f);
-    if (pp >= 0) v[u] = *reinterpret_cast<const float2 *>(dx + (int64_t)pp * 64 + 2 * lane);
+    if (pp >= 0) {
+      v[u] = *reinterpret_cast<const float2 *>(dx + (int64_t)pp * dirs * E + col);
+      if (dirs == 2) {
+        const float2 w = *reinterpret_cast<const float2 *>(dx + ((int64_t)pp * 2 + 1) * E + col);
+        v[u].x += w.x; v[u].y += w.y;
+      }
+    }
   }
   float2 acc = make_float2(0.f, 0.f);
   int cur = -1;  // leader position of the open run; -1 = run continued from the previous tile (-> carry)
   auto flush = [&]() {
-    float *dst = cur < 0 ? carry + (int64_t)T * 64 : grad_rows + (int64_t)cur * 64;
-    *reinterpret_cast<float2 *>(dst + 2 * lane) = acc;
+    float *dst = cur < 0 ? carry + (int64_t)T * E : grad_rows + (int64_t)cur * E;
+    *reinterpret_cast<float2 *>(dst + col) = acc;
   };
 #pragma unroll
   for (int u = 0; u < 32; ++u) {
@@ -562,15 +571,16 @@ __global__ void __launch_bounds__(256) emb_tilesum64_kernel(const int32_t *__res
 // carries of the following tiles to the run's accumulator in tile order.
 __global__ void __launch_bounds__(256) emb_carry_kernel(const int32_t *__restrict__ sorted_row, int cap,
                                                         float *__restrict__ grad_rows, const float *__restrict__ carry,
-                                                        const int32_t *__restrict__ tile_meta) {
+                                                        const int32_t *__restrict__ tile_meta, int E) {
   const int lane = threadIdx.x & 31;
+  const int col = blockIdx.y * 64 + 2 * lane;
   const int T = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int n_tiles = (sorted_row[cap] + 31) >> 5;
   if (T < 1 || T >= n_tiles) return;
   if (!tile_meta[2 * T]) return;                 // tile starts with a run head
   const int leader = tile_meta[2 * (T - 1) + 1];
   if (leader < 0) return;                        // previous tile is itself a continuation: not the first one
-  float2 *dst = reinterpret_cast<float2 *>(grad_rows + (int64_t)leader * 64 + 2 * lane);
+  float2 *dst = reinterpret_cast<float2 *>(grad_rows + (int64_t)leader * E + col);
   float2 acc = *dst;
   for (int T0 = T; T0 < n_tiles; T0 += 32) {
     // tiles T0.. belong to the run while they start inside it; the run ends in the first tile that has a head
@@ -584,7 +594,7 @@ __global__ void __launch_bounds__(256) emb_carry_kernel(const int32_t *__restric
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
       v[u] = make_float2(0.f, 0.f);
-      if (u < n) v[u] = *reinterpret_cast<const float2 *>(carry + (int64_t)(T0 + u) * 64 + 2 * lane);
+      if (u < n) v[u] = *reinterpret_cast<const float2 *>(carry + (int64_t)(T0 + u) * E + col);
     }
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
@@ -601,7 +611,7 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
   const rec_config &c = e->cfg;
   const int L = c.state_size, E = c.embedding_dim, P = B * L;
   NetBind &nb = e->nets[net_id];
-  const bool sorted_path = (E == 64 && e->dirs == 1 && P <= 32768);
+  const bool sorted_path = (E % 64 == 0 && e->dirs <= 2 && P <= 32768);
   static bool rank_attr_set[REC_MAX_DEVICES] = {};
   if (sorted_path && !rank_attr_set[e->dev]) {
     REC_CUDA(e, cudaFuncSetAttribute(emb_merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * (int)sizeof(int32_t)));
@@ -629,10 +639,11 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
     REC_LAUNCH_CHECK(e);
   }
   if ((stages & 2) && sorted_path) {
-    emb_tilesum64_kernel<<<cdiv(cdiv(P, 32), 8), 256, 0, e->stream>>>(e->emb_sorted, e->emb_seg, c.max_batch * L, e->dx,
-                                                                     e->emb_grad_rows, e->emb_slot, e->emb_carry, e->emb_tmeta);
+    const dim3 tg(cdiv(cdiv(P, 32), 8), E / 64);
+    emb_tilesum64_kernel<<<tg, 256, 0, e->stream>>>(e->emb_sorted, e->emb_seg, c.max_batch * L, e->dx, e->emb_grad_rows, e->emb_slot,
+                                                   e->emb_carry, e->emb_tmeta, E, e->dirs);
     REC_LAUNCH_CHECK(e);
-    emb_carry_kernel<<<cdiv(cdiv(P, 32), 8), 256, 0, e->stream>>>(e->emb_seg, c.max_batch * L, e->emb_grad_rows, e->emb_carry, e->emb_tmeta);
+    emb_carry_kernel<<<tg, 256, 0, e->stream>>>(e->emb_seg, c.max_batch * L, e->emb_grad_rows, e->emb_carry, e->emb_tmeta, E);
     REC_LAUNCH_CHECK(e);
   } else if (stages & 2) {
     const int chunk = 4096;

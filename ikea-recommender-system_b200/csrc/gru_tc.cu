@@ -22,6 +22,8 @@ using tck::BLK2;
 using tck::HALF;
 using tck::EPI_THREADS;
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ int eff_len(const int64_t *lens, int b, int L, int packed) {
   if (!packed) return L;
   const int64_t l = lens[b];
@@ -87,12 +89,15 @@ struct GemmParams {
   int m_tiles, n_tiles;    // tiles of 128 rows / NT columns
   int NT;                  // 128 or 256
   int k_total, n_split;    // K / 64; split-K
-  int M;                   // rows >= M are not written
+  int M;                   // C rows >= M are not written
+  int c_trans;             // 1: the tile is computed transposed -- accumulator row m, column n is C[n * ldc + m] (M <-> N
+                           //    swapped so that a warp's 32 lanes, = 32 consecutive m, store 128 contiguous bytes)
   int64_t ldc, c_split_stride;
 };
 
 struct Gemm {
   using Params = GemmParams;
+  static constexpr bool CLUSTERED = false;
   static constexpr const char *NAME = "tck:gemm";
   static constexpr int STAGES = 2, STAGE_BYTES = 3 * BLK2, ACC_COLS = 256, TMEM_COLS = 512;
   static constexpr int EXTRA_BYTES = 0;
@@ -177,9 +182,30 @@ struct Gemm {
       decode(p, u, mt, nt, k_lo, k_hi, sp);
       const int z = blockIdx.z;
       const int row = mt * 128 + q * 32 + lane;
+      const int half = p.NT >> 1;
+      if (p.c_trans) {
+        // accumulator row = C column: lanes store consecutive floats of one C row
+        float *dst = p.C[z] + (int64_t)sp * p.c_split_stride + row;
+        const float bv = p.bias[z] ? __ldg(p.bias[z] + row) : 0.f;
+        for (int ch = 0; ch < half / 32; ++ch) {
+          const int c0 = nt * p.NT + cq * half + ch * 32;
+          if (c0 >= p.M) break;  // warp-uniform
+          float g[32];
+          if (k_hi > k_lo) {
+            tc::tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * half + ch * 32), g);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[j] = 0.f;
+          }
+          const int nv = min(32, p.M - c0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) dst[(int64_t)(c0 + j) * p.ldc] = g[j] + bv;
+        }
+        return;
+      }
       float *dst = p.C[z] + (int64_t)sp * p.c_split_stride + (int64_t)row * p.ldc + nt * p.NT;
       const float *bias = p.bias[z] ? p.bias[z] + nt * p.NT : nullptr;
-      const int half = p.NT >> 1;
       const bool vec = (p.ldc & 3) == 0 && (p.c_split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C[z]) & 15) == 0;
       for (int ch = 0; ch < half / 32; ++ch) {
         const int c0 = cq * half + ch * 32;
@@ -198,7 +224,7 @@ struct Gemm {
           if (vec) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + c0 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-          } else {  // odd row pitch (the split-K partial layout of the GRU weight gradients)
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[c0 + j] = g[j];
           }
@@ -219,26 +245,29 @@ struct StepPass {
 };
 struct StepParams {
   StepPass pass[6];  // z = pass * dirs + dir
-  const uint8_t *himg_in;
-  uint8_t *himg_out;  // [z][n_sb][KBh]
+  uint8_t *himg[2];  // ping/pong images of h_t: step t reads [t & 1], writes [(t + 1) & 1]; each [z][n_sb][KBh]
   float *gates_save, *hprev_save;
   uint8_t *hprev_img;  // [dir][Prb][KBh]
-  int KBh, B, L, H, dirs, step, packed, n_sb, Prb;
+  int KBh, B, L, H, dirs, packed, n_sb, Prb;
 };
 
 struct GruStep {
   using Params = StepParams;
   static constexpr int WB = 2 * 192 * 128;  // one (unit, k-block) of the regrouped W_hh image: hi 24 KB | lo 24 KB
-  static constexpr const char *NAME = "tck:gru_step";
+  // one launch = all L time steps: unit u = step u; the H/64 CTAs of a cluster own 64 hidden units each of the same
+  // (pass, direction, session block) and exchange h_t through the ping/pong image in global memory
+  static constexpr bool CLUSTERED = true;
+  static constexpr const char *NAME = "tck:gru_steps";
   static constexpr int STAGES = 2, STAGE_BYTES = BLK2 + WB, ACC_COLS = 256, TMEM_COLS = 256;
   static constexpr int EXTRA_BYTES = 0;
-  __device__ static __forceinline__ void units(const Params &, int &lo, int &hi) { lo = 0; hi = 1; }
+  __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) { lo = 0; hi = p.L; }
   __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KBh; }
-  __device__ static __forceinline__ void load(const Params &p, int, int ks, uint8_t *stage, uint64_t *bar) {
-    const int z = blockIdx.z;
+  __device__ static __forceinline__ void load_b(const Params &p, int, int ks, uint8_t *stage, uint64_t *bar) {
     tc::mbar_expect_tx(bar, BLK2 + WB);
-    tc::bulk_g2s(stage, p.himg_in + (((int64_t)z * p.n_sb + blockIdx.y) * p.KBh + ks) * BLK2, BLK2, bar);
-    tc::bulk_g2s(stage + BLK2, p.pass[z].whh_perm + ((int64_t)blockIdx.x * p.KBh + ks) * WB, WB, bar);
+    tc::bulk_g2s(stage + BLK2, p.pass[blockIdx.z].whh_perm + ((int64_t)blockIdx.x * p.KBh + ks) * WB, WB, bar);
+  }
+  __device__ static __forceinline__ void load_a(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+    tc::bulk_g2s(stage, p.himg[u & 1] + (((int64_t)blockIdx.z * p.n_sb + blockIdx.y) * p.KBh + ks) * BLK2, BLK2, bar);
   }
   __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
     const uint32_t id = tc::instr_desc(128, 192, 0, 0);
@@ -258,24 +287,29 @@ struct GruStep {
       const int warp = tid >> 5;
       lane = tid & 31; q = warp & 3; cq = warp >> 2;
     }
-    __device__ __forceinline__ void tile(const Params &p, int, int, uint32_t tacc) {
+    __device__ __forceinline__ void tile(const Params &p, int step, int, uint32_t tacc) {
       const int z = blockIdx.z, j = blockIdx.x, sb = blockIdx.y;
       const StepPass &P = p.pass[z];
       const int dir = z % p.dirs, H = p.H, G = 3 * H;
       const int rl = q * 32 + lane, row = sb * 128 + rl;
       const bool valid = row < p.B;
       const int len = valid ? eff_len(P.lens, row, p.L, p.packed) : 0;
-      const bool active = valid && p.step < len;
-      const int tok = active ? (dir ? len - 1 - p.step : p.step) : 0;
+      const bool active = valid && step < len;
+      const int tok = active ? (dir ? len - 1 - step : step) : 0;
       const int u0 = j * 64 + cq * 32;
       const int64_t pos = (int64_t)row * p.L + tok;
       const float *gi = P.gi + (pos * p.dirs + dir) * G + u0;
       float *hs = P.h_state + (int64_t)row * (p.dirs * H) + dir * H + u0;
       float *gs = p.gates_save + (pos * p.dirs + dir) * 4 * H + u0;
       float *hp = p.hprev_save + (pos * p.dirs + dir) * H + u0;
-      uint8_t *oblk = p.himg_out + (((int64_t)z * p.n_sb + sb) * p.KBh + j) * BLK2;
+      uint8_t *oblk = p.himg[(step + 1) & 1] + (((int64_t)z * p.n_sb + sb) * p.KBh + j) * BLK2;
       uint8_t *pblk = p.hprev_img + (((int64_t)dir * p.Prb + (pos >> 7)) * p.KBh + j) * BLK2;
       const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32);
+      if (valid && step + 1 < len) {  // the next step's input projections (HBM-resident) -> L2 while this step computes
+        const int tok1 = dir ? len - 2 - step : step + 1;
+        const float *g1 = P.gi + (((int64_t)row * p.L + tok1) * p.dirs + dir) * G + u0;
+        prefetch_l2(g1); prefetch_l2(g1 + H); prefetch_l2(g1 + 2 * H);
+      }
 #pragma unroll 1
       for (int c8 = 0; c8 < 4; ++c8) {  // 8 hidden units per round
         float ar[8], az[8], an[8];
@@ -301,7 +335,7 @@ struct GruStep {
         const int uo = c8 * 8;
 #pragma unroll
         for (int k = 0; k < 8; ++k) hold[k] = 0.f;
-        if (valid && p.step > 0) {
+        if (valid && step > 0) {
           const float4 a = *reinterpret_cast<const float4 *>(hs + uo), b = *reinterpret_cast<const float4 *>(hs + uo + 4);
           hold[0] = a.x; hold[1] = a.y; hold[2] = a.z; hold[3] = a.w; hold[4] = b.x; hold[5] = b.y; hold[6] = b.z; hold[7] = b.w;
         }
@@ -344,7 +378,7 @@ struct GruStep {
         } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k) hnew[k] = hold[k];
-          if (valid && p.step == 0) {  // (cannot happen: len >= 1) keep the state defined
+          if (valid && step == 0) {  // (cannot happen: len >= 1) keep the state defined
             *reinterpret_cast<float4 *>(hs + uo) = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(hs + uo + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -360,29 +394,32 @@ struct GruStep {
 // ---- one BPTT time step --------------------------------------------------------------------------------------------
 struct BpttParams {
   const uint8_t *whh_img[2];  // per direction, natural [3H/128][H/64]
-  const uint8_t *dgh_in;
-  uint8_t *dgh_out;           // step images [dir][n_sb][KG]
+  uint8_t *dstep[2];          // ping/pong step images [dir][n_sb][KG]: step t reads [(t + 1) & 1], writes [t & 1]
   float *dhw;                 // [B, dirs * H] running dL/dh ("direct" part between the steps)
   const float *gates_save, *hprev_save;
   const int64_t *lens;
   uint8_t *dgi_img, *dgh_img;  // [dir][Prb][KG]
-  int Prb, KG, KBh, B, L, H, dirs, step, packed, n_sb;
+  int Prb, KG, KBh, B, L, H, dirs, packed, n_sb;
 };
 
 struct GruBptt {
   using Params = BpttParams;
+  // one launch = all L steps in reverse: unit u = step L - 1 - u; the H/64 CTAs of a cluster own 64 state columns each
+  static constexpr bool CLUSTERED = true;
   static constexpr const char *NAME = "tck:gru_bptt";
   static constexpr int STAGES = 4, STAGE_BYTES = BLK2 + 2 * HALF, ACC_COLS = 64, TMEM_COLS = 64;
   static constexpr int EXTRA_BYTES = 0;
-  __device__ static __forceinline__ void units(const Params &, int &lo, int &hi) { lo = 0; hi = 1; }
+  __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) { lo = 0; hi = p.L; }
   __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KG; }
-  __device__ static __forceinline__ void load(const Params &p, int, int ks, uint8_t *stage, uint64_t *bar) {
-    const int dir = blockIdx.z;
+  __device__ static __forceinline__ void load_b(const Params &p, int, int ks, uint8_t *stage, uint64_t *bar) {
     tc::mbar_expect_tx(bar, BLK2 + 2 * HALF);
-    tc::bulk_g2s(stage, p.dgh_in + (((int64_t)dir * p.n_sb + blockIdx.y) * p.KG + ks) * BLK2, BLK2, bar);
-    const uint8_t *blk = p.whh_img[dir] + ((int64_t)(ks >> 1) * p.KBh + blockIdx.x) * BLK2 + (ks & 1) * HALF;
+    const uint8_t *blk = p.whh_img[blockIdx.z] + ((int64_t)(ks >> 1) * p.KBh + blockIdx.x) * BLK2 + (ks & 1) * HALF;
     tc::bulk_g2s(stage + BLK2, blk, HALF, bar);
     tc::bulk_g2s(stage + BLK2 + HALF, blk + BLK, HALF, bar);
+  }
+  __device__ static __forceinline__ void load_a(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+    const int t = p.L - 1 - u;
+    tc::bulk_g2s(stage, p.dstep[(t + 1) & 1] + (((int64_t)blockIdx.z * p.n_sb + blockIdx.y) * p.KG + ks) * BLK2, BLK2, bar);
   }
   __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
     const uint32_t id = tc::instr_desc(128, 64, 0, 1);
@@ -402,14 +439,15 @@ struct GruBptt {
       const int warp = tid >> 5;
       lane = tid & 31; q = warp & 3; cq = warp >> 2;
     }
-    __device__ __forceinline__ void tile(const Params &p, int, int, uint32_t tacc) {
+    __device__ __forceinline__ void tile(const Params &p, int u, int, uint32_t tacc) {
+      const int step = p.L - 1 - u;
       const int dir = blockIdx.z, cb = blockIdx.x, sb = blockIdx.y;
       const int H = p.H;
       const int rl = q * 32 + lane, row = sb * 128 + rl;
       const bool valid = row < p.B;
       const int len = valid ? eff_len(p.lens, row, p.L, p.packed) : 0;
-      const bool active = valid && p.step < len;
-      const int tok = active ? (dir ? len - 1 - p.step : p.step) : 0;
+      const bool active = valid && step < len;
+      const int tok = active ? (dir ? len - 1 - step : step) : 0;
       const int c0 = cb * 64 + cq * 32;
       const int64_t pos = (int64_t)row * p.L + tok;
       float acc[32];
@@ -417,10 +455,17 @@ struct GruBptt {
       float *dh = p.dhw + (int64_t)row * (p.dirs * H) + dir * H + c0;
       const float *g = p.gates_save + (pos * p.dirs + dir) * 4 * H + c0;
       const float *hpv = p.hprev_save + (pos * p.dirs + dir) * H + c0;
-      uint8_t *sblk = p.dgh_out + (((int64_t)dir * p.n_sb + sb) * p.KG) * BLK2;          // + kb * BLK2
+      uint8_t *sblk = p.dstep[step & 1] + (((int64_t)dir * p.n_sb + sb) * p.KG) * BLK2;          // + kb * BLK2
       uint8_t *ib = p.dgi_img + (((int64_t)dir * p.Prb + (pos >> 7)) * p.KG) * BLK2;
       uint8_t *hb = p.dgh_img + (((int64_t)dir * p.Prb + (pos >> 7)) * p.KG) * BLK2;
       const int pr = (int)(pos & 127);
+      if (valid && step >= 1 && step - 1 < len) {  // the saved activations of the next (earlier) step -> L2
+        const int tok1 = dir ? len - step : step - 1;
+        const int64_t pos1 = (int64_t)row * p.L + tok1;
+        const float *g1 = p.gates_save + (pos1 * p.dirs + dir) * 4 * H + c0;
+        prefetch_l2(g1); prefetch_l2(g1 + H); prefetch_l2(g1 + 2 * H); prefetch_l2(g1 + 3 * H);
+        prefetch_l2(p.hprev_save + (pos1 * p.dirs + dir) * H + c0);
+      }
 #pragma unroll 1
       for (int c8 = 0; c8 < 4; ++c8) {
         const int uo = c8 * 8;
@@ -498,26 +543,31 @@ struct GruBptt {
 
 // Bias gradients: column sums of the dgi / dgh images over this split's position range -> bias column (KS - 1) of the
 // split-K partial layout part[split][dir][which][3H][KS] that gru_adam_kernel reduces.
+// grid (splits, 3H/64 column blocks, dirs * 2); a warp reads whole 128-byte image rows (lane = two columns).
 __global__ void __launch_bounds__(256) gru_bias_colsum_kernel(const uint8_t *__restrict__ dgi_img, const uint8_t *__restrict__ dgh_img,
                                                              int Prb, int KG, int G, int dirs, int n_split, int KS,
                                                              float *__restrict__ part) {
-  const int split = blockIdx.x, which = blockIdx.y & 1, dir = blockIdx.y >> 1;
+  __shared__ float red[8][64];
+  const int split = blockIdx.x, cb = blockIdx.y, which = blockIdx.z & 1, dir = blockIdx.z >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_total = Prb * 2, per = (k_total + n_split - 1) / n_split;
   const int k_lo = split * per, k_hi = min(k_total, k_lo + per);
   const uint8_t *img = (which ? dgh_img : dgi_img) + (int64_t)dir * Prb * KG * BLK2;
-  for (int j = threadIdx.x; j < G; j += blockDim.x) {
+  float a0 = 0.f, a1 = 0.f;
+  for (int r = k_lo * 64 + warp; r < k_hi * 64; r += 8) {  // global position row
+    const uint8_t *blk = img + ((int64_t)(r >> 7) * KG + cb) * BLK2;
+    const uint32_t off = tc::sw128_off(r & 127, 2 * lane);
+    const uint32_t hi = *reinterpret_cast<const uint32_t *>(blk + off), lo = *reinterpret_cast<const uint32_t *>(blk + BLK + off);
+    a0 += __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+    a1 += __uint_as_float(hi & 0xFFFF0000u) + __uint_as_float(lo & 0xFFFF0000u);
+  }
+  red[warp][2 * lane] = a0; red[warp][2 * lane + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
     float acc = 0.f;
-    for (int kk = k_lo; kk < k_hi; ++kk) {
-      const uint8_t *blk = img + ((int64_t)(kk >> 1) * KG + (j >> 6)) * BLK2;
-      const int r0 = (kk & 1) * 64;
-      for (int r = r0; r < r0 + 64; ++r) {
-        const uint32_t off = tc::sw128_off(r, j & 63);
-        const float hi = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t *>(blk + off) << 16);
-        const float lo = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t *>(blk + BLK + off) << 16);
-        acc += hi + lo;
-      }
-    }
-    part[((((int64_t)split * dirs + dir) * 2 + which) * G + j) * KS + KS - 1] = acc;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += red[w][threadIdx.x];
+    part[((((int64_t)split * dirs + dir) * 2 + which) * G + cb * 64 + threadIdx.x) * KS + KS - 1] = acc;
   }
 }
 
@@ -528,7 +578,7 @@ __global__ void __launch_bounds__(256) gru_bias_colsum_kernel(const uint8_t *__r
 // ------------------------------------------------------------------------------------------------------------
 bool gru_tc_supported(const rec_engine *e) {
   const rec_config &c = e->cfg;
-  return e->use_tc && c.embedding_dim % 128 == 0 && c.hidden_dim % 128 == 0 && c.embedding_dim <= 512 && c.hidden_dim <= 512;
+  return e->use_tc && c.embedding_dim % 128 == 0 && c.hidden_dim % 128 == 0 && c.embedding_dim <= 512 && c.hidden_dim <= 512;  // H / 64 <= 8 CTAs per cluster
 }
 
 static int gtc_alloc(rec_engine *e, void **ptr, size_t bytes) {
@@ -659,14 +709,15 @@ int launch_gru_forward_tc(rec_engine *e, int n_pass, const int *net_ids, const i
     for (int i = 0; i < n_pass; ++i)
       for (int dir = 0; dir < d.dirs; ++dir) {
         const int z = i * d.dirs + dir;
-        g.A[z] = ximg(ximg_of[i]);
-        g.B[z] = gtc_wslot(e, d, net_ids[i], dir);
+        g.A[z] = gtc_wslot(e, d, net_ids[i], dir);
+        g.B[z] = ximg(ximg_of[i]);
         g.C[z] = e->g_gi[i] + (int64_t)dir * d.G;
         g.bias[z] = e->nets[net_ids[i]].p.b_ih[dir];
       }
-    g.a_mn = 0; g.b_mn = 0; g.a_cbs = d.KBe; g.b_cbs = d.KBe;
-    g.NT = d.G % 256 == 0 ? 256 : 128;
-    g.m_tiles = d.Prb; g.n_tiles = d.G / g.NT; g.k_total = d.KBe; g.n_split = 1;
+    // computed transposed (accumulator rows = gate index): coalesced 128-byte stores into gi[p, dir, :]
+    g.a_mn = 0; g.b_mn = 0; g.a_cbs = d.KBe; g.b_cbs = d.KBe; g.c_trans = 1;
+    g.NT = d.Prb % 2 == 0 ? 256 : 128;
+    g.m_tiles = d.G / 128; g.n_tiles = (d.Prb * 128) / g.NT; g.k_total = d.KBe; g.n_split = 1;
     g.M = d.Prb * 128;  // the gi buffer is padded to whole row blocks
     g.ldc = (int64_t)d.dirs * d.G; g.c_split_stride = 0;
     const int total = g.m_tiles * g.n_tiles;
@@ -687,13 +738,8 @@ int launch_gru_forward_tc(rec_engine *e, int n_pass, const int *net_ids, const i
     }
   sp.gates_save = e->gates_save; sp.hprev_save = e->hprev_save; sp.hprev_img = e->g_hprev_img;
   sp.KBh = d.KBh; sp.B = B; sp.L = d.L; sp.H = d.H; sp.dirs = d.dirs; sp.packed = c.use_packed_seq; sp.n_sb = d.n_sb; sp.Prb = d.Prb;
-  for (int t = 0; t < d.L; ++t) {
-    sp.step = t;
-    sp.himg_in = e->g_himg[t & 1];
-    sp.himg_out = e->g_himg[(t + 1) & 1];
-    if ((rc = tck::launch_tck<gtc::GruStep>(e, dim3(d.KBh, d.n_sb, n_pass * d.dirs), sp))) return rc;
-  }
-  return REC_OK;
+  sp.himg[0] = e->g_himg[0]; sp.himg[1] = e->g_himg[1];
+  return tck::launch_tck<gtc::GruStep>(e, dim3(d.KBh, d.n_sb, n_pass * d.dirs), sp);
 }
 
 // stages as launch_gru_backward: 1 = BPTT (+ dx), 2 = weight gradients (split-K partials in e->wgrad_part)
@@ -723,23 +769,20 @@ int launch_gru_backward_tc(rec_engine *e, int net_id, const int64_t *s, const in
     bp.dgi_img = e->g_dgi_img; bp.dgh_img = e->g_dgh_img;
     bp.Prb = d.Prb; bp.KG = d.KG; bp.KBh = d.KBh; bp.B = B; bp.L = d.L; bp.H = d.H; bp.dirs = d.dirs; bp.packed = c.use_packed_seq;
     bp.n_sb = d.n_sb;
-    for (int t = d.L - 1; t >= 0; --t) {
-      bp.step = t;
-      bp.dgh_in = e->g_dstep[(t + 1) & 1];   // gate gradients of step t + 1 (zeros for the last step)
-      bp.dgh_out = e->g_dstep[t & 1];
-      if ((rc = tck::launch_tck<gtc::GruBptt>(e, dim3(d.KBh, d.n_sb, d.dirs), bp))) return rc;
-    }
+    bp.dstep[0] = e->g_dstep[0]; bp.dstep[1] = e->g_dstep[1];  // step L - 1 reads the zeroed image [L & 1]
+    if ((rc = tck::launch_tck<gtc::GruBptt>(e, dim3(d.KBh, d.n_sb, d.dirs), bp))) return rc;
     // dx[p, dir, :] = dgi[p, :] . W_ih
     gtc::GemmParams g = {};
     for (int dir = 0; dir < d.dirs; ++dir) {
-      g.A[dir] = e->g_dgi_img + dir * used_big;
-      g.B[dir] = gtc_wslot(e, d, net_id, dir);
+      g.A[dir] = gtc_wslot(e, d, net_id, dir);
+      g.B[dir] = e->g_dgi_img + dir * used_big;
       g.C[dir] = e->dx + (int64_t)dir * d.E;
       g.bias[dir] = nullptr;
     }
-    g.a_mn = 0; g.b_mn = 1; g.a_cbs = d.KG; g.b_cbs = d.KBe;
-    g.NT = d.E % 256 == 0 ? 256 : 128;
-    g.m_tiles = d.Prb; g.n_tiles = d.E / g.NT; g.k_total = d.KG; g.n_split = 1;
+    // transposed: accumulator rows = embedding column (A = MN-major view of the W_ih image), columns = positions
+    g.a_mn = 1; g.b_mn = 0; g.a_cbs = d.KBe; g.b_cbs = d.KG; g.c_trans = 1;
+    g.NT = d.Prb % 2 == 0 ? 256 : 128;
+    g.m_tiles = d.E / 128; g.n_tiles = (d.Prb * 128) / g.NT; g.k_total = d.KG; g.n_split = 1;
     g.M = (int)d.P; g.ldc = (int64_t)d.dirs * d.E; g.c_split_stride = 0;
     const int total = g.m_tiles * g.n_tiles;
     int n_cta = e->sm_count / d.dirs;
@@ -748,28 +791,29 @@ int launch_gru_backward_tc(rec_engine *e, int net_id, const int64_t *s, const in
   }
   if (stages & 2) {
     const int KS = (d.E > d.H ? d.E : d.H) + 1;
-    int splits = 2 * d.Prb < 16 ? 2 * d.Prb : 16;   // split-K slices actually written (gru_adam_kernel sums e->wgrad_used)
+    int splits = 2 * d.Prb < 12 ? 2 * d.Prb : 12;   // split-K slices actually written (gru_adam_kernel sums e->wgrad_used)
     if (splits > e->wgrad_splits) splits = e->wgrad_splits;
     e->wgrad_used = splits;
     for (int which = 0; which < 2; ++which) {
       gtc::GemmParams g = {};
       const int N = which ? d.H : d.E;
       for (int dir = 0; dir < d.dirs; ++dir) {
-        g.A[dir] = (which ? e->g_dgh_img : e->g_dgi_img) + dir * used_big;
-        g.B[dir] = which ? e->g_hprev_img + (size_t)dir * d.Prb * d.KBh * tck::BLK2 : e->g_ximg[0];
+        g.A[dir] = which ? e->g_hprev_img + (size_t)dir * d.Prb * d.KBh * tck::BLK2 : e->g_ximg[0];
+        g.B[dir] = (which ? e->g_dgh_img : e->g_dgi_img) + dir * used_big;
         g.C[dir] = e->wgrad_part + ((int64_t)dir * 2 + which) * d.G * KS;
         g.bias[dir] = nullptr;
       }
-      g.a_mn = 1; g.b_mn = 1; g.a_cbs = d.KG; g.b_cbs = N / 64;
-      g.NT = N % 256 == 0 ? 256 : 128;
-      g.m_tiles = d.G / 128; g.n_tiles = N / g.NT; g.k_total = d.Prb * 2; g.n_split = splits;
+      // transposed: accumulator rows = input feature k, columns = gate row j -> part[j * KS + k], coalesced along k
+      g.a_mn = 1; g.b_mn = 1; g.a_cbs = N / 64; g.b_cbs = d.KG; g.c_trans = 1;
+      g.NT = d.G % 256 == 0 ? 256 : 128;
+      g.m_tiles = N / 128; g.n_tiles = d.G / g.NT; g.k_total = d.Prb * 2; g.n_split = splits;
       g.M = d.G; g.ldc = KS; g.c_split_stride = (int64_t)d.dirs * 2 * d.G * KS;
       const int total = g.m_tiles * g.n_tiles * splits;
       int n_cta = e->sm_count / d.dirs;
       if (n_cta > total) n_cta = total;
       if ((rc = tck::launch_tck<gtc::Gemm>(e, dim3(n_cta, 1, d.dirs), g))) return rc;
     }
-    gtc::gru_bias_colsum_kernel<<<dim3(splits, 2 * d.dirs), 256, 0, e->stream>>>(e->g_dgi_img, e->g_dgh_img, d.Prb, d.KG, d.G, d.dirs,
+    gtc::gru_bias_colsum_kernel<<<dim3(splits, d.KG, 2 * d.dirs), 256, 0, e->stream>>>(e->g_dgi_img, e->g_dgh_img, d.Prb, d.KG, d.G, d.dirs,
                                                                                   splits, KS, e->wgrad_part);
     REC_LAUNCH_CHECK(e);
   }

@@ -47,6 +47,7 @@ enum { M_STATS = 0, M_ARG = 1, M_DL = 2 };
 template <int MODE>
 struct HeadFwd {
   using Params = FwdParams;
+  static constexpr bool CLUSTERED = false;
   static constexpr const char *NAME = MODE == M_STATS ? "tck:head_stats" : MODE == M_ARG ? "tck:head_greedy" : "tck:head_dlogits";
   static constexpr int STAGES = 3, STAGE_BYTES = 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
   static constexpr int EXTRA_BYTES = 8192;
@@ -224,6 +225,7 @@ struct DhParams {
 
 struct HeadDh {
   using Params = DhParams;
+  static constexpr bool CLUSTERED = false;
   static constexpr const char *NAME = "tck:head_dh";
   static constexpr int STAGES = 2, STAGE_BYTES = 12 * HALF, ACC_COLS = 256, TMEM_COLS = 256;
   static constexpr int EXTRA_BYTES = 0;
@@ -293,11 +295,14 @@ struct HeadDh {
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// dW tile [128 items x (128 NRB)] = dl^T . h  (K = batch) -> Adam on W, m, v (+ bias when the tile starts at column 0)
+// dW^T tile [128 state columns x 256 items] = h^T . dl (K = batch) -> Adam on W, m, v (+ bias for the first column tile).
+// The tile is computed TRANSPOSED (TMEM lane = state column d, TMEM column = item row v): a warp's global accesses to
+// W[v, d0 .. d0 + 32) are then 128 contiguous bytes per instruction with no shared-memory transpose, and the four
+// lane-quarter warps cover 512 contiguous bytes of every weight row.
 // ------------------------------------------------------------------------------------------------------------
 struct DwParams {
   const uint8_t *dlT, *hT;  // [n_tiles][KBS], [D/128][KBS]
-  int KBS, NRB, n_dchunks, n_tiles, Vloc, D, n_sb;
+  int KBS, n_vt, n_dt, n_tiles, Vloc, D, n_sb;
   float *w, *wm, *wv, *b, *bm, *bv;
   const float *db_part;     // [n_sb][n_tiles * 128]
   float b1, b2, eps, step_size, inv_bc2_sqrt;
@@ -306,11 +311,12 @@ struct DwParams {
 
 struct HeadDwAdam {
   using Params = DwParams;
+  static constexpr bool CLUSTERED = false;
   static constexpr const char *NAME = "tck:head_dw_adam";
   static constexpr int STAGES = 2, STAGE_BYTES = 3 * BLK2, ACC_COLS = 256, TMEM_COLS = 512;
-  static constexpr int EXTRA_BYTES = EPI_WARPS * 32 * 20 * 4;
+  static constexpr int EXTRA_BYTES = 0;
   __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) {
-    const int total = p.n_tiles * p.n_dchunks;
+    const int total = p.n_vt * p.n_dt;
     const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
     lo = blockIdx.x * per;
     hi = min(total, lo + per);
@@ -318,19 +324,21 @@ struct HeadDwAdam {
   }
   __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KBS; }
   __device__ static __forceinline__ void load(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
-    const int t = u / p.n_dchunks, dc = u - t * p.n_dchunks;
-    tc::mbar_expect_tx(bar, (uint32_t)(1 + p.NRB) * BLK2);
-    tc::bulk_g2s(stage, p.dlT + ((int64_t)t * p.KBS + ks) * BLK2, BLK2, bar);
-    for (int i = 0; i < p.NRB; ++i) {
-      const uint8_t *blk = p.hT + ((int64_t)(dc * p.NRB + i) * p.KBS + ks) * BLK2;
+    const int vt = u / p.n_dt, dt = u - vt * p.n_dt;
+    tc::mbar_expect_tx(bar, 3 * BLK2);
+    tc::bulk_g2s(stage, p.hT + ((int64_t)dt * p.KBS + ks) * BLK2, BLK2, bar);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int t = min(2 * vt + i, p.n_tiles - 1);  // an odd tile count: the duplicate's rows lie beyond Vloc
+      const uint8_t *blk = p.dlT + ((int64_t)t * p.KBS + ks) * BLK2;
       tc::bulk_g2s(stage + BLK2 + i * BLK, blk, BLK, bar);
-      tc::bulk_g2s(stage + BLK2 + p.NRB * BLK + i * BLK, blk + BLK, BLK, bar);
+      tc::bulk_g2s(stage + BLK2 + 2 * BLK + i * BLK, blk + BLK, BLK, bar);
     }
   }
-  __device__ static __forceinline__ void mma(const Params &p, int, int, uint32_t st, uint32_t tacc, bool first) {
-    const uint32_t id = tc::instr_desc(128, 128 * p.NRB, 0, 0);
+  __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
+    const uint32_t id = tc::instr_desc(128, 256, 0, 0);
     const uint64_t ah = tc::desc_kmajor(st, 0), al = tc::desc_kmajor(st + BLK, 0);
-    const uint64_t bh = tc::desc_kmajor(st + BLK2, 0), bl = tc::desc_kmajor(st + BLK2 + p.NRB * BLK, 0);
+    const uint64_t bh = tc::desc_kmajor(st + BLK2, 0), bl = tc::desc_kmajor(st + BLK2 + 2 * BLK, 0);
     bool acc = !first;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
@@ -340,64 +348,51 @@ struct HeadDwAdam {
     }
   }
   struct Epi {
-    float *xp;
-    int q, cq, lane, rsub, csub;
+    int q, cq, lane;
     float step_size, inv_bc2_sqrt;
-    __device__ __forceinline__ Epi(const Params &p, uint8_t *extra, int tid) {
+    __device__ __forceinline__ Epi(const Params &p, uint8_t *, int tid) {
       const int warp = tid >> 5;
       lane = tid & 31; q = warp & 3; cq = warp >> 2;
-      xp = reinterpret_cast<float *>(extra) + warp * (32 * 20);
-      rsub = lane >> 2; csub = (lane & 3) * 4;
       step_size = p.sc ? p.sc[0] : p.step_size;
       inv_bc2_sqrt = p.sc ? p.sc[1] : p.inv_bc2_sqrt;
     }
     __device__ __forceinline__ void tile(const Params &p, int u, int, uint32_t tacc) {
-      const int t = u / p.n_dchunks, dc = u - t * p.n_dchunks;
-      const int N = 128 * p.NRB;
-      const int v0 = t * 128 + q * 32;
-      const int nrows = min(32, p.Vloc - v0);  // may be <= 0 in the last tile
-      const int col0 = dc * N + cq * (N / 2);
-      for (int pc = 0; pc < N / 32; ++pc) {     // 16-column pieces of this warp's column half
-        float g[16];
-        tc::tmem_ld16(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * (N / 2) + pc * 16), g);
+      const int vt = u / p.n_dt, dt = u - vt * p.n_dt;
+      const int d = dt * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int v0 = vt * 256 + cq * 128 + ch * 32;
+        if (v0 >= p.Vloc) break;  // warp-uniform
+        float g[32];
+        tc::tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 128 + ch * 32), g);
+        const int nrows = min(32, p.Vloc - v0);
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(xp + lane * 20 + j) = make_float4(g[j], g[j + 1], g[j + 2], g[j + 3]);
-        __syncwarp();
-        float4 G[4], P[4], M[4], U[4];
+        for (int hf = 0; hf < 2; ++hf) {
+          float P[16], M[16], U[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) G[i] = *reinterpret_cast<const float4 *>(xp + (i * 8 + rsub) * 20 + csub);
-        __syncwarp();
-        if (nrows > 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = min(i * 8 + rsub, nrows - 1);
-            const int64_t off = (int64_t)(v0 + r) * p.D + col0 + pc * 16 + csub;
-            P[i] = *reinterpret_cast<const float4 *>(p.w + off);
-            M[i] = *reinterpret_cast<const float4 *>(p.wm + off);
-            U[i] = *reinterpret_cast<const float4 *>(p.wv + off);
+          for (int j = 0; j < 16; ++j) {
+            const int64_t off = (int64_t)(v0 + min(hf * 16 + j, nrows - 1)) * p.D + d;
+            P[j] = p.w[off]; M[j] = p.wm[off]; U[j] = p.wv[off];
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + rsub;
-            adam_elem(P[i].x, M[i].x, U[i].x, G[i].x, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
-            adam_elem(P[i].y, M[i].y, U[i].y, G[i].y, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
-            adam_elem(P[i].z, M[i].z, U[i].z, G[i].z, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
-            adam_elem(P[i].w, M[i].w, U[i].w, G[i].w, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
-            if (r < nrows) {
-              const int64_t off = (int64_t)(v0 + r) * p.D + col0 + pc * 16 + csub;
-              *reinterpret_cast<float4 *>(p.w + off) = P[i];
-              *reinterpret_cast<float4 *>(p.wm + off) = M[i];
-              *reinterpret_cast<float4 *>(p.wv + off) = U[i];
+          for (int j = 0; j < 16; ++j) {
+            adam_elem(P[j], M[j], U[j], g[hf * 16 + j], p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
+            if (hf * 16 + j < nrows) {
+              const int64_t off = (int64_t)(v0 + hf * 16 + j) * p.D + d;
+              p.w[off] = P[j]; p.wm[off] = M[j]; p.wv[off] = U[j];
             }
           }
         }
       }
-      if (dc == 0 && cq == 0 && lane < nrows) {  // bias of this tile's rows: gradient = sum of the per-session-block partials
-        float g = 0.f;
-        for (int sb = 0; sb < p.n_sb; ++sb) g += p.db_part[((int64_t)sb * p.n_tiles + t) * 128 + q * 32 + lane];
-        float bp = p.b[v0 + lane], m = p.bm[v0 + lane], v = p.bv[v0 + lane];
-        adam_elem(bp, m, v, g, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
-        p.b[v0 + lane] = bp; p.bm[v0 + lane] = m; p.bv[v0 + lane] = v;
+      if (dt == 0) {  // bias of this unit's 256 rows: gradient = sum of the per-session-block partials
+        const int v = vt * 256 + cq * 128 + q * 32 + lane;
+        if (v < p.Vloc) {
+          float g = 0.f;
+          for (int sb = 0; sb < p.n_sb; ++sb) g += p.db_part[((int64_t)sb * p.n_tiles + (v >> 7)) * 128 + (v & 127)];
+          float bp = p.b[v], m = p.bm[v], vv = p.bv[v];
+          adam_elem(bp, m, vv, g, p.b1, p.b2, p.eps, step_size, inv_bc2_sqrt);
+          p.b[v] = bp; p.bm[v] = m; p.bv[v] = vv;
+        }
       }
     }
     __device__ __forceinline__ void finish(const Params &) {}
@@ -448,6 +443,44 @@ static int tck_pack(rec_engine *e, const tck::PackSrc &s, int R, int C, uint8_t 
   return REC_OK;
 }
 
+// Weight image of one head (head >= 0 -> k_wimg[0]) or of the pre-combined greedy-action heads sum_j w_j Q_j
+// (head < 0 -> k_wimg[1], + combined bias).
+static int tck_pack_head_image(rec_engine *e, int net_id, int head, int n_arg, const float *w) {
+  const rec_net_params &np = e->nets[net_id].p;
+  tck::PackSrc ws = {};
+  if (head < 0) {
+    ws.n = n_arg;
+    for (int j = 0; j < n_arg; ++j) { ws.p[j] = np.head_w[1 + j]; ws.w[j] = n_arg > 1 ? w[j] : 1.f; }
+    if (n_arg > 1) {
+      tck::PackSrc bs = ws;
+      for (int j = 0; j < n_arg; ++j) bs.p[j] = np.head_b[1 + j];
+      tck::bias_combine_kernel<<<cdiv(e->Vloc, 256), 256, 0, e->stream>>>(bs, e->Vloc, e->k_bias);
+      REC_LAUNCH_CHECK(e);
+    }
+    return tck_pack(e, ws, e->Vloc, e->D, e->k_wimg[1]);
+  }
+  ws.n = 1; ws.p[0] = np.head_w[head]; ws.w[0] = 1.f;
+  int rc = tck_pack(e, ws, e->Vloc, e->D, e->k_wimg[0]);
+  if (rc) return rc;
+  e->k_sup_net = net_id; e->k_sup_head = head;
+  return REC_OK;
+}
+
+// The weight images only depend on the parameters: the fused train steps produce them on a side stream while the
+// GRU forward runs (HBM-bound packing next to the latency-bound recurrence).
+int tck_prepack_heads(rec_engine *e, int net_id, int n_arg, const float *w) {
+  if (!tck_heads_supported(e)) return REC_OK;
+  int rc = tck_ensure(e);
+  if (rc) return rc;
+  if ((rc = tck_pack_head_image(e, net_id, 0, 0, w))) return rc;
+  e->k_fresh[0] = true;
+  if (n_arg > 0) {
+    if ((rc = tck_pack_head_image(e, net_id, -1, n_arg, w))) return rc;
+    e->k_fresh[1] = true;
+  }
+  return REC_OK;
+}
+
 // Same contract as launch_head_stats (heads.cu) for statistics (no top-k) and the greedy-action pass.
 int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
   int rc = tck_ensure(e);
@@ -456,28 +489,12 @@ int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_ou
   const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(a.B, 128);
   const bool arg = a.n_arg > 0;
   if (arg && a.n_arg > 3) REC_FAIL(e, REC_EINVAL, "greedy-action pass supports at most 3 Q heads (got %d)", a.n_arg);
-  // weight image of the scored head(s)
-  tck::PackSrc ws = {};
+  // weight image of the scored head(s) -- unless tck_prepack_heads() already produced it on a side stream
   uint8_t *wimg = e->k_wimg[arg ? 1 : 0];
-  const float *bias;
-  if (arg) {
-    ws.n = a.n_arg;
-    for (int j = 0; j < a.n_arg; ++j) { ws.p[j] = np.head_w[1 + j]; ws.w[j] = a.n_arg > 1 ? a.w[j] : 1.f; }
-    if (a.n_arg > 1) {
-      tck::PackSrc bs = ws;
-      for (int j = 0; j < a.n_arg; ++j) bs.p[j] = np.head_b[1 + j];
-      tck::bias_combine_kernel<<<cdiv(e->Vloc, 256), 256, 0, e->stream>>>(bs, e->Vloc, e->k_bias);
-      REC_LAUNCH_CHECK(e);
-      bias = e->k_bias;
-    } else {
-      bias = np.head_b[1];
-    }
-  } else {
-    ws.n = 1; ws.p[0] = np.head_w[a.stats_head]; ws.w[0] = 1.f;
-    bias = np.head_b[a.stats_head];
-  }
-  if ((rc = tck_pack(e, ws, e->Vloc, e->D, wimg))) return rc;
-  if (!arg) { e->k_sup_net = a.net_id; e->k_sup_head = a.stats_head; }
+  const float *bias = arg ? (a.n_arg > 1 ? e->k_bias : np.head_b[1]) : np.head_b[a.stats_head];
+  const bool fresh = arg ? e->k_fresh[1] : (e->k_fresh[0] && e->k_sup_net == a.net_id && e->k_sup_head == a.stats_head);
+  e->k_fresh[arg ? 1 : 0] = false;
+  if (!fresh && (rc = tck_pack_head_image(e, a.net_id, arg ? -1 : a.stats_head, a.n_arg, a.w))) return rc;
   // state image
   tck::PackSrc hs = {};
   hs.n = 1; hs.p[0] = a.h; hs.w[0] = 1.f;
@@ -565,17 +582,21 @@ int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const re
       REC_CUDA(e, cudaMemsetAsync(e->dh_part + (int64_t)n_split * B * e->D, 0, sizeof(float) * (size_t)(n_slices - n_split) * B * e->D, e->stream));
     if ((rc = tck::launch_tck<tck::HeadDh>(e, dim3(n_split, n_dchunks, n_sb), p))) return rc;
   }
+  side_mark(e, 3);  // the dh slices are final: the GRU backward need not wait for the (HBM-bound) weight update below
   // (3) dW + Adam
   {
-    const int NRB = e->D % 256 == 0 ? 2 : 1, n_dchunks = e->D / (128 * NRB);
-    const int total = n_tiles * n_dchunks;
-    int n_cta = e->sm_count < total ? e->sm_count : total;
     tck::DwParams p = {};
-    p.dlT = e->k_dlT; p.hT = e->k_hT; p.KBS = KBS; p.NRB = NRB; p.n_dchunks = n_dchunks; p.n_tiles = n_tiles; p.Vloc = e->Vloc;
+    p.dlT = e->k_dlT; p.hT = e->k_hT; p.KBS = KBS; p.n_vt = cdiv(n_tiles, 2); p.n_dt = e->D / 128; p.n_tiles = n_tiles; p.Vloc = e->Vloc;
     p.D = e->D; p.n_sb = n_sb;
     p.w = np.head_w[0]; p.wm = np.head_w_m[0]; p.wv = np.head_w_v[0]; p.b = np.head_b[0]; p.bm = np.head_b_m[0]; p.bv = np.head_b_v[0];
     p.db_part = e->k_db; p.b1 = hp->beta1; p.b2 = hp->beta2; p.eps = hp->eps; p.step_size = step_size; p.inv_bc2_sqrt = 1.f / bc2_sqrt;
     p.sc = e->d_sc;
+    const int total = p.n_vt * p.n_dt;
+    // with branch overlap on, this kernel runs NEXT TO the GRU backward (a few latency-bound CTAs per step that need
+    // most of an SM's shared memory each): leave SMs free for them instead of queueing behind one full persistent wave
+    int n_cta = side_enabled(e) ? e->sm_count - 24 : e->sm_count;
+    if (n_cta > total) n_cta = total;
+    if (n_cta < 1) n_cta = 1;
     if ((rc = tck::launch_tck<tck::HeadDwAdam>(e, dim3(n_cta), p))) return rc;
   }
   return REC_OK;

@@ -81,6 +81,37 @@ static __global__ void bias_combine_kernel(PackSrc s, int n, float *__restrict__
   out[i] = acc;
 }
 
+// ---- thread-block-cluster helpers (time-step loops: the CTAs of a cluster exchange a step's result through global
+// memory and signal each other through mbarriers in distributed shared memory) ---------------------------------------
+__device__ __forceinline__ uint32_t cluster_size_x() { uint32_t v; asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(v)); return v; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(tc::smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    if (spins > (1u << 24)) __trap();
+  }
+}
+// generic-proxy writes (of other CTAs, made visible by an acquire) -> async-proxy (TMA) reads of this thread
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------
 // Kernel skeleton
 // ------------------------------------------------------------------------------------------------------------
@@ -90,38 +121,70 @@ static __global__ void bias_combine_kernel(PackSrc s, int n, float *__restrict__
 //   load(p, u, ks, stage, bar)  ONE thread: expect_tx + TMA bulk copies of stage (u, ks)
 //   mma(p, u, ks, saddr, tacc, first)  ONE thread: the tcgen05.mma's of stage (u, ks) into accumulator tacc
 //   Epi                         per-thread epilogue object: tile(p, u, i, tacc) per unit, finish(p) at the end
+//   CLUSTERED                   true: the grid's x extent is ONE thread-block cluster and units are TIME STEPS: unit u + 1
+//                               of every CTA reads (load_a) what the epilogues of ALL CTAs of the cluster wrote to global
+//                               memory in unit u.  load() is split into load_b (independent of the previous unit, issued
+//                               early) and load_a (after the cluster-wide "step done" barrier).
 template <class OP>
 __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Params p) {
   extern __shared__ uint8_t raw[];
   uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
-  __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2];
+  __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2], stepbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int u_lo = 0, u_hi = 0;
   OP::units(p, u_lo, u_hi);
+  const uint32_t csize = OP::CLUSTERED ? cluster_size_x() : 1u;
   if (tid == 0) {
     for (int s = 0; s < OP::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
+    tc::mbar_init(&stepbar, csize * EPI_WARPS);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, OP::TMEM_COLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  if (OP::CLUSTERED) cluster_sync_all();  // every CTA's barriers are initialised before a peer may arrive on them
   const uint32_t tmem = tmem_base_s;
   uint8_t *extra = sm + OP::STAGES * OP::STAGE_BYTES;
 
   if (warp == EPI_WARPS + 1) {
     // ---- TMA loader ----
     if (lane == 0) {
-      int s = 0;
+      int s = 0, i = 0;
       uint32_t round = 0;
-      for (int u = u_lo; u < u_hi; ++u) {
+      for (int u = u_lo; u < u_hi; ++u, ++i) {
         const int nk = OP::k_steps(p, u);
-        for (int ks = 0; ks < nk; ++ks) {
-          if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage are complete
-          OP::load(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
-          if (++s == OP::STAGES) { s = 0; ++round; }
+        if constexpr (OP::CLUSTERED) {
+          // operands that do not depend on the previous step go out first; the step's own operand follows the
+          // cluster-wide "previous step written" barrier
+          const int npre = nk < OP::STAGES ? nk : OP::STAGES;
+          const int s0 = s;
+          const uint32_t round0 = round;
+          for (int ks = 0; ks < npre; ++ks) {
+            if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);
+            OP::load_b(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+            if (++s == OP::STAGES) { s = 0; ++round; }
+          }
+          if (i > 0) { mbar_wait_cluster(&stepbar, (uint32_t)(i - 1) & 1u); fence_proxy_async_all(); }
+          s = s0; round = round0;
+          for (int ks = 0; ks < npre; ++ks) {
+            OP::load_a(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+            if (++s == OP::STAGES) { s = 0; ++round; }
+          }
+          for (int ks = npre; ks < nk; ++ks) {
+            if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);
+            OP::load_b(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+            OP::load_a(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+            if (++s == OP::STAGES) { s = 0; ++round; }
+          }
+        } else {
+          for (int ks = 0; ks < nk; ++ks) {
+            if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage are complete
+            OP::load(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+            if (++s == OP::STAGES) { s = 0; ++round; }
+          }
         }
       }
     }
@@ -157,11 +220,17 @@ __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Para
       tc::tc_fence_after();
       epi.tile(p, u, i, tmem + (uint32_t)(b * OP::ACC_COLS));
       tc::tc_fence_before();
+      if (OP::CLUSTERED) __threadfence();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty[b]);
+      if (lane == 0) {
+        tc::mbar_arrive(&tempty[b]);
+        if (OP::CLUSTERED)  // this warp's share of the step is in global memory: tell every CTA of the cluster
+          for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(&stepbar, r);
+      }
     }
     epi.finish(p);
   }
+  if (OP::CLUSTERED) cluster_sync_all();  // no CTA leaves (its barriers vanish) while a peer may still arrive on them
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, OP::TMEM_COLS);
@@ -177,7 +246,17 @@ static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
     REC_CUDA(e, cudaFuncSetAttribute(tck_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[e->dev] = true;
   }
-  tck_kernel<OP><<<grid, THREADS, smem, e->stream>>>(p);
+  if (OP::CLUSTERED) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = grid.x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    REC_CUDA(e, cudaLaunchKernelEx(&cfg, tck_kernel<OP>, p));
+  } else {
+    tck_kernel<OP><<<grid, THREADS, smem, e->stream>>>(p);
+  }
   e->launches++;
   if (e->tl_on) rec_timeline_record(e, OP::NAME, 0);
   cudaError_t st = cudaGetLastError();

