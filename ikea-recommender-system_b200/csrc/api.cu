@@ -684,10 +684,11 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
     if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
     REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
     static const int sweep_mark = getenv("REC_SWEEP_EARLY") ? -1 : 2;
-    // wide heads (D >= 128): mark 3 = dh slices final; the sweep then shares the HBM with the supervised head's dW + Adam
-    // kernel while the latency-bound GRU backward runs on the SMs that kernel leaves free
+    // (wide heads, D >= 128: the sweep also waits for the supervised head's dW + Adam kernel -- started together, the two
+    // HBM-bound kernels fill every SM's register file and the GRU backward, which needs most of an SM per CTA, queues
+    // behind both: 4.6 vs 3.8 ms per step at cfg3)
     if ((rc = launch_q_heads_update(e, main_net, e->h_state[0], b, B, step_size, bc2_sqrt, hp,
-                                    tck_heads_supported(e) && sweep_mark >= 0 ? 3 : sweep_mark))) return rc;
+                                    tck_heads_supported(e) && sweep_mark >= 0 && getenv("REC_SWEEP_WITH_DW") ? 3 : sweep_mark))) return rc;
   }
   side_wait_mark(e, tck_heads_supported(e) ? 3 : 2);
   if ((rc = launch_dh_reduce(e, B))) return rc;

@@ -14,6 +14,7 @@
 // The time loop is a chain of small launches captured in the step's CUDA graph: no grid-wide barrier, no cluster.
 // Semantics: torch.nn.GRU + pack_padded_sequence exactly as gru.cu (models/BidirGRU4Rec/model.py:51-99,
 // models/SQN/sqn_gru.py:69-104): per-row length mask, reverse direction walks len-1..0, layer 0 only.
+#include <stdlib.h>
 #include "tck.cuh"
 
 namespace gtc {
@@ -22,6 +23,7 @@ using tck::BLK2;
 using tck::HALF;
 using tck::EPI_THREADS;
 
+#define GTC_STAMP(p, u, k) do { if ((p).trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) (p).trace[(u) * 8 + (k)] = clock64(); } while (0)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int eff_len(const int64_t *lens, int b, int L, int packed) {
@@ -51,9 +53,10 @@ __global__ void __launch_bounds__(256) gather_pack_kernel(const float *__restric
   }
 }
 
-// GRU weights of up to 2 nets x 2 directions -> images.  which 0: W_ih [3H, E] natural, 1: W_hh [3H, H] natural,
-// 2: W_hh with the rows regrouped per 64 hidden units: unit j = rows {r_j (64) | z_j (64) | n_j (64)}, stored as
-// [H/64 units][H/64 k-blocks][hi 192 x 128 B | lo 192 x 128 B].
+// GRU weights of up to 2 nets x 2 directions -> images.  which 0: W_ih [3H, E] natural; 1: W_hh^T [H, 3H] (rows =
+// state column, K = gate row: the B operand of the BPTT step, any 32-row slice of it is contiguous per k-block);
+// 2: W_hh with the rows regrouped per 32 hidden units: unit j = rows {r_j (32) | z_j (32) | n_j (32)}, stored as
+// [H/32 units][H/64 k-blocks][hi 96 x 128 B | lo 96 x 128 B] (the B operand of the forward step).
 struct WPackArgs {
   const float *wih[4], *whh[4];
   uint8_t *wih_img[4], *whh_img[4], *whh_perm[4];
@@ -61,20 +64,34 @@ struct WPackArgs {
 };
 __global__ void __launch_bounds__(256) gru_pack_weights_kernel(WPackArgs a) {
   const int slot = blockIdx.z, which = blockIdx.y;
-  const int G = 3 * a.H, C = which == 0 ? a.E : a.H, c8n = C >> 3, KB = C >> 6;
+  const int G = 3 * a.H;
+  if (which == 1) {  // transposed: image row c (state column), image column j (gate row)
+    const int c8n = G >> 3, KB = G >> 6, n_chunks = a.H * c8n;
+    const float *src = a.whh[slot];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += gridDim.x * blockDim.x) {
+      const int c8 = i / a.H, row = i - c8 * a.H;  // consecutive threads: consecutive c -> coalesced reads of W_hh rows
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = src[(int64_t)(c8 * 8 + k) * a.H + row];
+      uint8_t *blk = a.whh_img[slot] + ((int64_t)(row >> 7) * KB + (c8 >> 3)) * BLK2;
+      tc::store_split8(blk, blk + BLK, row & 127, c8 & 7, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+    }
+    return;
+  }
+  const int C = which == 0 ? a.E : a.H, c8n = C >> 3, KB = C >> 6;
   const float *src = which == 0 ? a.wih[slot] : a.whh[slot];
   const int n_chunks = G * c8n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += gridDim.x * blockDim.x) {
     const int row = i / c8n, c8 = i - row * c8n;
     const float4 *p0 = reinterpret_cast<const float4 *>(src + (int64_t)row * C + c8 * 8);
     const float4 x = p0[0], y = p0[1];
-    if (which < 2) {
-      uint8_t *blk = (which == 0 ? a.wih_img[slot] : a.whh_img[slot]) + ((int64_t)(row >> 7) * KB + (c8 >> 3)) * BLK2;
+    if (which == 0) {
+      uint8_t *blk = a.wih_img[slot] + ((int64_t)(row >> 7) * KB + (c8 >> 3)) * BLK2;
       tc::store_split8(blk, blk + BLK, row & 127, c8 & 7, x, y);
     } else {
-      const int g = row / a.H, u = row - g * a.H, j = u >> 6, r = g * 64 + (u & 63);
-      uint8_t *blk = a.whh_perm[slot] + ((int64_t)j * KB + (c8 >> 3)) * (2 * 192 * 128);
-      tc::store_split8(blk, blk + 192 * 128, r, c8 & 7, x, y);
+      const int gt = row / a.H, u = row - gt * a.H, j = u >> 5, r = gt * 32 + (u & 31);
+      uint8_t *blk = a.whh_perm[slot] + ((int64_t)j * KB + (c8 >> 3)) * (2 * 96 * 128);
+      tc::store_split8(blk, blk + 96 * 128, r, c8 & 7, x, y);
     }
   }
 }
@@ -98,6 +115,7 @@ struct GemmParams {
 struct Gemm {
   using Params = GemmParams;
   static constexpr bool CLUSTERED = false;
+  static constexpr int RESIDENT_BYTES = 0;
   static constexpr const char *NAME = "tck:gemm";
   static constexpr int STAGES = 2, STAGE_BYTES = 3 * BLK2, ACC_COLS = 256, TMEM_COLS = 512;
   static constexpr int EXTRA_BYTES = 0;
@@ -249,30 +267,39 @@ struct StepParams {
   float *gates_save, *hprev_save;
   uint8_t *hprev_img;  // [dir][Prb][KBh]
   int KBh, B, L, H, dirs, packed, n_sb, Prb;
+  long long *trace;  // debug (REC_TRACE_SEL=3): clock64 stamps of CTA (0,0,0): [step][8] = loader in/out, issuer in/out, epilogue in/out
 };
 
 struct GruStep {
   using Params = StepParams;
-  static constexpr int WB = 2 * 192 * 128;  // one (unit, k-block) of the regrouped W_hh image: hi 24 KB | lo 24 KB
-  // one launch = all L time steps: unit u = step u; the H/64 CTAs of a cluster own 64 hidden units each of the same
-  // (pass, direction, session block) and exchange h_t through the ping/pong image in global memory
+  // one launch = all L time steps: unit u = step u.  The H/32 CTAs of a cluster own 32 hidden units each of the same
+  // (pass, direction, session block); their slice of W_hh (r|z|n rows of the 32 units, all k-blocks) stays RESIDENT in
+  // shared memory, only the image of h_{t-1} streams in (all four k-blocks in flight at once), and h_t travels to the
+  // other CTAs through the ping/pong image in global memory + the cluster-wide step barrier.
   static constexpr bool CLUSTERED = true;
   static constexpr const char *NAME = "tck:gru_steps";
-  static constexpr int STAGES = 2, STAGE_BYTES = BLK2 + WB, ACC_COLS = 256, TMEM_COLS = 256;
+  static constexpr int WB = 2 * 96 * 128;  // one (unit, k-block) of the regrouped W_hh image: hi 12 KB | lo 12 KB
+  static constexpr int STAGES = 4, STAGE_BYTES = BLK2, ACC_COLS = 128, TMEM_COLS = 256;
+  static constexpr int RESIDENT_BYTES = 4 * WB;  // H <= 256
   static constexpr int EXTRA_BYTES = 0;
   __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) { lo = 0; hi = p.L; }
   __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KBh; }
-  __device__ static __forceinline__ void load_b(const Params &p, int, int ks, uint8_t *stage, uint64_t *bar) {
-    tc::mbar_expect_tx(bar, BLK2 + WB);
-    tc::bulk_g2s(stage + BLK2, p.pass[blockIdx.z].whh_perm + ((int64_t)blockIdx.x * p.KBh + ks) * WB, WB, bar);
+  __device__ static __forceinline__ void load_resident(const Params &p, uint8_t *res, uint64_t *bar) {
+    tc::mbar_expect_tx(bar, (uint32_t)p.KBh * WB);
+    tc::bulk_g2s(res, p.pass[blockIdx.z].whh_perm + (int64_t)blockIdx.x * p.KBh * WB, (uint32_t)p.KBh * WB, bar);
   }
-  __device__ static __forceinline__ void load_a(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+  __device__ static __forceinline__ void load(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+    if (ks == 0) GTC_STAMP(p, u, 0);
+    tc::mbar_expect_tx(bar, BLK2);
     tc::bulk_g2s(stage, p.himg[u & 1] + (((int64_t)blockIdx.z * p.n_sb + blockIdx.y) * p.KBh + ks) * BLK2, BLK2, bar);
+    if (ks == p.KBh - 1) GTC_STAMP(p, u, 1);
   }
-  __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
-    const uint32_t id = tc::instr_desc(128, 192, 0, 0);
+  __device__ static __forceinline__ void mma(const Params &p, int u, int ks, uint32_t st, uint32_t res, uint32_t tacc, bool first) {
+    if (ks == 0) GTC_STAMP(p, u, 2);
+    if (ks == p.KBh - 1) GTC_STAMP(p, u, 3);
+    const uint32_t id = tc::instr_desc(128, 96, 0, 0);
     const uint64_t ah = tc::desc_kmajor(st, 0), al = tc::desc_kmajor(st + BLK, 0);
-    const uint64_t bh = tc::desc_kmajor(st + BLK2, 0), bl = tc::desc_kmajor(st + BLK2 + 192 * 128, 0);
+    const uint64_t bh = tc::desc_kmajor(res + ks * WB, 0), bl = tc::desc_kmajor(res + ks * WB + 96 * 128, 0);
     bool acc = !first;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
@@ -288,6 +315,7 @@ struct GruStep {
       lane = tid & 31; q = warp & 3; cq = warp >> 2;
     }
     __device__ __forceinline__ void tile(const Params &p, int step, int, uint32_t tacc) {
+      if (threadIdx.x == 0) GTC_STAMP(p, step, 4);
       const int z = blockIdx.z, j = blockIdx.x, sb = blockIdx.y;
       const StepPass &P = p.pass[z];
       const int dir = z % p.dirs, H = p.H, G = 3 * H;
@@ -296,22 +324,23 @@ struct GruStep {
       const int len = valid ? eff_len(P.lens, row, p.L, p.packed) : 0;
       const bool active = valid && step < len;
       const int tok = active ? (dir ? len - 1 - step : step) : 0;
-      const int u0 = j * 64 + cq * 32;
+      const int u0 = j * 32 + cq * 16;
       const int64_t pos = (int64_t)row * p.L + tok;
       const float *gi = P.gi + (pos * p.dirs + dir) * G + u0;
       float *hs = P.h_state + (int64_t)row * (p.dirs * H) + dir * H + u0;
       float *gs = p.gates_save + (pos * p.dirs + dir) * 4 * H + u0;
       float *hp = p.hprev_save + (pos * p.dirs + dir) * H + u0;
-      uint8_t *oblk = p.himg[(step + 1) & 1] + (((int64_t)z * p.n_sb + sb) * p.KBh + j) * BLK2;
-      uint8_t *pblk = p.hprev_img + (((int64_t)dir * p.Prb + (pos >> 7)) * p.KBh + j) * BLK2;
-      const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32);
+      uint8_t *oblk = p.himg[(step + 1) & 1] + (((int64_t)z * p.n_sb + sb) * p.KBh + (j >> 1)) * BLK2;
+      uint8_t *pblk = p.hprev_img + (((int64_t)dir * p.Prb + (pos >> 7)) * p.KBh + (j >> 1)) * BLK2;
+      const int ch0 = (j & 1) * 4 + cq * 2;  // first 16-byte chunk of this thread's 16 hidden units inside their 64-column block
+      const uint32_t tbase = tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 16);
       if (valid && step + 1 < len) {  // the next step's input projections (HBM-resident) -> L2 while this step computes
         const int tok1 = dir ? len - 2 - step : step + 1;
         const float *g1 = P.gi + (((int64_t)row * p.L + tok1) * p.dirs + dir) * G + u0;
         prefetch_l2(g1); prefetch_l2(g1 + H); prefetch_l2(g1 + 2 * H);
       }
 #pragma unroll 1
-      for (int c8 = 0; c8 < 4; ++c8) {  // 8 hidden units per round
+      for (int c8 = 0; c8 < 2; ++c8) {  // 8 hidden units per round
         float ar[8], az[8], an[8];
         float hold[8], hnew[8];
         {
@@ -327,7 +356,7 @@ struct GruStep {
               : "=r"(r8[0]), "=r"(r8[1]), "=r"(r8[2]), "=r"(r8[3]), "=r"(r8[4]), "=r"(r8[5]), "=r"(r8[6]), "=r"(r8[7]),
                 "=r"(z8[0]), "=r"(z8[1]), "=r"(z8[2]), "=r"(z8[3]), "=r"(z8[4]), "=r"(z8[5]), "=r"(z8[6]), "=r"(z8[7]),
                 "=r"(n8[0]), "=r"(n8[1]), "=r"(n8[2]), "=r"(n8[3]), "=r"(n8[4]), "=r"(n8[5]), "=r"(n8[6]), "=r"(n8[7])
-              : "r"(tbase + (uint32_t)(c8 * 8)), "r"(tbase + (uint32_t)(64 + c8 * 8)), "r"(tbase + (uint32_t)(128 + c8 * 8))
+              : "r"(tbase + (uint32_t)(c8 * 8)), "r"(tbase + (uint32_t)(32 + c8 * 8)), "r"(tbase + (uint32_t)(64 + c8 * 8))
               : "memory");
 #pragma unroll
           for (int k = 0; k < 8; ++k) { ar[k] = __uint_as_float(r8[k]); az[k] = __uint_as_float(z8[k]); an[k] = __uint_as_float(n8[k]); }
@@ -372,7 +401,7 @@ struct GruStep {
             *reinterpret_cast<float4 *>(gs + 3 * H + uo + 4) = make_float4(phn[4], phn[5], phn[6], phn[7]);
             *reinterpret_cast<float4 *>(hp + uo) = make_float4(hold[0], hold[1], hold[2], hold[3]);
             *reinterpret_cast<float4 *>(hp + uo + 4) = make_float4(hold[4], hold[5], hold[6], hold[7]);
-            tc::store_split8(pblk, pblk + BLK, (int)(pos & 127), cq * 4 + c8, make_float4(hold[0], hold[1], hold[2], hold[3]),
+            tc::store_split8(pblk, pblk + BLK, (int)(pos & 127), ch0 + c8, make_float4(hold[0], hold[1], hold[2], hold[3]),
                              make_float4(hold[4], hold[5], hold[6], hold[7]));
           }
         } else {
@@ -383,9 +412,10 @@ struct GruStep {
             *reinterpret_cast<float4 *>(hs + uo + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        tc::store_split8(oblk, oblk + BLK, rl, cq * 4 + c8, make_float4(hnew[0], hnew[1], hnew[2], hnew[3]),
+        tc::store_split8(oblk, oblk + BLK, rl, ch0 + c8, make_float4(hnew[0], hnew[1], hnew[2], hnew[3]),
                          make_float4(hnew[4], hnew[5], hnew[6], hnew[7]));
       }
+      if (threadIdx.x == 0) GTC_STAMP(p, step, 5);
     }
     __device__ __forceinline__ void finish(const Params &) {}
   };
@@ -393,7 +423,7 @@ struct GruStep {
 
 // ---- one BPTT time step --------------------------------------------------------------------------------------------
 struct BpttParams {
-  const uint8_t *whh_img[2];  // per direction, natural [3H/128][H/64]
+  const uint8_t *whh_img[2];  // per direction: image of W_hh^T [H/128][3H/64]
   uint8_t *dstep[2];          // ping/pong step images [dir][n_sb][KG]: step t reads [(t + 1) & 1], writes [t & 1]
   float *dhw;                 // [B, dirs * H] running dL/dh ("direct" part between the steps)
   const float *gates_save, *hprev_save;
@@ -404,33 +434,40 @@ struct BpttParams {
 
 struct GruBptt {
   using Params = BpttParams;
-  // one launch = all L steps in reverse: unit u = step L - 1 - u; the H/64 CTAs of a cluster own 64 state columns each
+  // one launch = all L steps in reverse: unit u = step L - 1 - u.  The H/32 CTAs of a cluster own 32 state columns each;
+  // their rows of W_hh^T (all 3H/64 k-blocks) stay RESIDENT in shared memory, the step image of the gate gradients
+  // streams in through 4 stages.
   static constexpr bool CLUSTERED = true;
   static constexpr const char *NAME = "tck:gru_bptt";
-  static constexpr int STAGES = 4, STAGE_BYTES = BLK2 + 2 * HALF, ACC_COLS = 64, TMEM_COLS = 64;
+  static constexpr int STAGES = 4, STAGE_BYTES = BLK2, ACC_COLS = 32, TMEM_COLS = 64;
+  static constexpr int RESIDENT_BYTES = 12 * 8192;  // 3H/64 k-blocks x (32 rows hi 4 KB | lo 4 KB), H <= 256
   static constexpr int EXTRA_BYTES = 0;
   __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) { lo = 0; hi = p.L; }
   __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KG; }
-  __device__ static __forceinline__ void load_b(const Params &p, int, int ks, uint8_t *stage, uint64_t *bar) {
-    tc::mbar_expect_tx(bar, BLK2 + 2 * HALF);
-    const uint8_t *blk = p.whh_img[blockIdx.z] + ((int64_t)(ks >> 1) * p.KBh + blockIdx.x) * BLK2 + (ks & 1) * HALF;
-    tc::bulk_g2s(stage + BLK2, blk, HALF, bar);
-    tc::bulk_g2s(stage + BLK2 + HALF, blk + BLK, HALF, bar);
+  __device__ static __forceinline__ void load_resident(const Params &p, uint8_t *res, uint64_t *bar) {
+    tc::mbar_expect_tx(bar, (uint32_t)p.KG * 8192);
+    const int r0 = blockIdx.x * 32;  // first state column of this CTA = row of the W_hh^T image
+    const uint8_t *src = p.whh_img[blockIdx.z] + (int64_t)(r0 >> 7) * p.KG * BLK2 + (r0 & 127) * 128;
+    for (int kb = 0; kb < p.KG; ++kb) {
+      tc::bulk_g2s(res + kb * 8192, src + (int64_t)kb * BLK2, 4096, bar);
+      tc::bulk_g2s(res + kb * 8192 + 4096, src + (int64_t)kb * BLK2 + BLK, 4096, bar);
+    }
   }
-  __device__ static __forceinline__ void load_a(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+  __device__ static __forceinline__ void load(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
     const int t = p.L - 1 - u;
+    tc::mbar_expect_tx(bar, BLK2);
     tc::bulk_g2s(stage, p.dstep[(t + 1) & 1] + (((int64_t)blockIdx.z * p.n_sb + blockIdx.y) * p.KG + ks) * BLK2, BLK2, bar);
   }
-  __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
-    const uint32_t id = tc::instr_desc(128, 64, 0, 1);
+  __device__ static __forceinline__ void mma(const Params &, int, int ks, uint32_t st, uint32_t res, uint32_t tacc, bool first) {
+    const uint32_t id = tc::instr_desc(128, 32, 0, 0);
     const uint64_t ah = tc::desc_kmajor(st, 0), al = tc::desc_kmajor(st + BLK, 0);
-    const uint64_t bh = tc::desc_mnmajor(st + BLK2, 0, HALF), bl = tc::desc_mnmajor(st + BLK2 + HALF, 0, HALF);
+    const uint64_t bh = tc::desc_kmajor(res + ks * 8192, 0), bl = tc::desc_kmajor(res + ks * 8192 + 4096, 0);
     bool acc = !first;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
       const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tacc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 128), id, acc); acc = true; }
+      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tacc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id, acc); acc = true; }
     }
   }
   struct Epi {
@@ -448,10 +485,10 @@ struct GruBptt {
       const int len = valid ? eff_len(p.lens, row, p.L, p.packed) : 0;
       const bool active = valid && step < len;
       const int tok = active ? (dir ? len - 1 - step : step) : 0;
-      const int c0 = cb * 64 + cq * 32;
+      const int c0 = cb * 32 + cq * 16;
       const int64_t pos = (int64_t)row * p.L + tok;
-      float acc[32];
-      tc::tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32), acc);
+      float acc[16];
+      tc::tmem_ld16(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 16), acc);
       float *dh = p.dhw + (int64_t)row * (p.dirs * H) + dir * H + c0;
       const float *g = p.gates_save + (pos * p.dirs + dir) * 4 * H + c0;
       const float *hpv = p.hprev_save + (pos * p.dirs + dir) * H + c0;
@@ -467,7 +504,7 @@ struct GruBptt {
         prefetch_l2(p.hprev_save + (pos1 * p.dirs + dir) * H + c0);
       }
 #pragma unroll 1
-      for (int c8 = 0; c8 < 4; ++c8) {
+      for (int c8 = 0; c8 < 2; ++c8) {
         const int uo = c8 * 8;
         float dhv[8], a_r[8], a_z[8], a_n[8], h_n[8], direct[8];
         if (valid) {
@@ -517,17 +554,17 @@ struct GruBptt {
         const float4 z0 = make_float4(a_z[0], a_z[1], a_z[2], a_z[3]), z1 = make_float4(a_z[4], a_z[5], a_z[6], a_z[7]);
         const float4 n0 = make_float4(a_n[0], a_n[1], a_n[2], a_n[3]), n1 = make_float4(a_n[4], a_n[5], a_n[6], a_n[7]);
         const float4 m0 = make_float4(h_n[0], h_n[1], h_n[2], h_n[3]), m1 = make_float4(h_n[4], h_n[5], h_n[6], h_n[7]);
-        const int ch = cq * 4 + c8;
+        const int ch = (cb & 1) * 4 + cq * 2 + c8;  // 16-byte chunk inside the 64-column block (cb >> 1) of each gate
         // step image of dgh (r | z | n-through-r blocks): every row is written (zeros for rows that are not active)
         {
-          uint8_t *b0 = sblk + (int64_t)(0 * p.KBh + cb) * BLK2, *b1 = sblk + (int64_t)(1 * p.KBh + cb) * BLK2, *b2 = sblk + (int64_t)(2 * p.KBh + cb) * BLK2;
+          uint8_t *b0 = sblk + (int64_t)(0 * p.KBh + (cb >> 1)) * BLK2, *b1 = sblk + (int64_t)(1 * p.KBh + (cb >> 1)) * BLK2, *b2 = sblk + (int64_t)(2 * p.KBh + (cb >> 1)) * BLK2;
           tc::store_split8(b0, b0 + BLK, rl, ch, r0, r1);
           tc::store_split8(b1, b1 + BLK, rl, ch, z0, z1);
           tc::store_split8(b2, b2 + BLK, rl, ch, m0, m1);
         }
         if (active) {
-          uint8_t *i0 = ib + (int64_t)(0 * p.KBh + cb) * BLK2, *i1 = ib + (int64_t)(1 * p.KBh + cb) * BLK2, *i2 = ib + (int64_t)(2 * p.KBh + cb) * BLK2;
-          uint8_t *h0 = hb + (int64_t)(0 * p.KBh + cb) * BLK2, *h1 = hb + (int64_t)(1 * p.KBh + cb) * BLK2, *h2 = hb + (int64_t)(2 * p.KBh + cb) * BLK2;
+          uint8_t *i0 = ib + (int64_t)(0 * p.KBh + (cb >> 1)) * BLK2, *i1 = ib + (int64_t)(1 * p.KBh + (cb >> 1)) * BLK2, *i2 = ib + (int64_t)(2 * p.KBh + (cb >> 1)) * BLK2;
+          uint8_t *h0 = hb + (int64_t)(0 * p.KBh + (cb >> 1)) * BLK2, *h1 = hb + (int64_t)(1 * p.KBh + (cb >> 1)) * BLK2, *h2 = hb + (int64_t)(2 * p.KBh + (cb >> 1)) * BLK2;
           tc::store_split8(i0, i0 + BLK, pr, ch, r0, r1);
           tc::store_split8(i1, i1 + BLK, pr, ch, z0, z1);
           tc::store_split8(i2, i2 + BLK, pr, ch, n0, n1);
@@ -578,7 +615,7 @@ __global__ void __launch_bounds__(256) gru_bias_colsum_kernel(const uint8_t *__r
 // ------------------------------------------------------------------------------------------------------------
 bool gru_tc_supported(const rec_engine *e) {
   const rec_config &c = e->cfg;
-  return e->use_tc && c.embedding_dim % 128 == 0 && c.hidden_dim % 128 == 0 && c.embedding_dim <= 512 && c.hidden_dim <= 512;  // H / 64 <= 8 CTAs per cluster
+  return e->use_tc && c.embedding_dim % 128 == 0 && c.hidden_dim % 128 == 0 && c.embedding_dim <= 512 && c.hidden_dim <= 256;  // H / 32 <= 8 CTAs per cluster, resident W_hh slices sized for H <= 256
 }
 
 static int gtc_alloc(rec_engine *e, void **ptr, size_t bytes) {
@@ -739,7 +776,11 @@ int launch_gru_forward_tc(rec_engine *e, int n_pass, const int *net_ids, const i
   sp.gates_save = e->gates_save; sp.hprev_save = e->hprev_save; sp.hprev_img = e->g_hprev_img;
   sp.KBh = d.KBh; sp.B = B; sp.L = d.L; sp.H = d.H; sp.dirs = d.dirs; sp.packed = c.use_packed_seq; sp.n_sb = d.n_sb; sp.Prb = d.Prb;
   sp.himg[0] = e->g_himg[0]; sp.himg[1] = e->g_himg[1];
-  return tck::launch_tck<gtc::GruStep>(e, dim3(d.KBh, d.n_sb, n_pass * d.dirs), sp);
+  {
+    static const int sel = getenv("REC_TRACE_SEL") ? atoi(getenv("REC_TRACE_SEL")) : 0;
+    sp.trace = sel == 3 ? e->trace : nullptr;
+  }
+  return tck::launch_tck<gtc::GruStep>(e, dim3(d.H / 32, d.n_sb, n_pass * d.dirs), sp);
 }
 
 // stages as launch_gru_backward: 1 = BPTT (+ dx), 2 = weight gradients (split-K partials in e->wgrad_part)
@@ -770,7 +811,7 @@ int launch_gru_backward_tc(rec_engine *e, int net_id, const int64_t *s, const in
     bp.Prb = d.Prb; bp.KG = d.KG; bp.KBh = d.KBh; bp.B = B; bp.L = d.L; bp.H = d.H; bp.dirs = d.dirs; bp.packed = c.use_packed_seq;
     bp.n_sb = d.n_sb;
     bp.dstep[0] = e->g_dstep[0]; bp.dstep[1] = e->g_dstep[1];  // step L - 1 reads the zeroed image [L & 1]
-    if ((rc = tck::launch_tck<gtc::GruBptt>(e, dim3(d.KBh, d.n_sb, d.dirs), bp))) return rc;
+    if ((rc = tck::launch_tck<gtc::GruBptt>(e, dim3(d.H / 32, d.n_sb, d.dirs), bp))) return rc;
     // dx[p, dir, :] = dgi[p, :] . W_ih
     gtc::GemmParams g = {};
     for (int dir = 0; dir < d.dirs; ++dir) {

@@ -21,6 +21,7 @@
 // hi*hi + hi*lo + lo*hi with fp32 accumulation ("bf16x3", ~1e-5 relative) exactly like the D = 64 kernels.
 // Reference semantics: nn.Linear heads + CrossEntropyLoss + Adam of models/SQN/sqn_gru.py:78-112,183-254 and
 // models/BidirGRU4Rec/model.py:51-99 (cfg3 = SQN heads on the concatenated bidirectional state).
+#include <stdlib.h>
 #include "tck.cuh"
 
 namespace tck {
@@ -48,6 +49,7 @@ template <int MODE>
 struct HeadFwd {
   using Params = FwdParams;
   static constexpr bool CLUSTERED = false;
+  static constexpr int RESIDENT_BYTES = 0;
   static constexpr const char *NAME = MODE == M_STATS ? "tck:head_stats" : MODE == M_ARG ? "tck:head_greedy" : "tck:head_dlogits";
   static constexpr int STAGES = 3, STAGE_BYTES = 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
   static constexpr int EXTRA_BYTES = 8192;
@@ -226,6 +228,7 @@ struct DhParams {
 struct HeadDh {
   using Params = DhParams;
   static constexpr bool CLUSTERED = false;
+  static constexpr int RESIDENT_BYTES = 0;
   static constexpr const char *NAME = "tck:head_dh";
   static constexpr int STAGES = 2, STAGE_BYTES = 12 * HALF, ACC_COLS = 256, TMEM_COLS = 256;
   static constexpr int EXTRA_BYTES = 0;
@@ -312,6 +315,7 @@ struct DwParams {
 struct HeadDwAdam {
   using Params = DwParams;
   static constexpr bool CLUSTERED = false;
+  static constexpr int RESIDENT_BYTES = 0;
   static constexpr const char *NAME = "tck:head_dw_adam";
   static constexpr int STAGES = 2, STAGE_BYTES = 3 * BLK2, ACC_COLS = 256, TMEM_COLS = 512;
   static constexpr int EXTRA_BYTES = 0;
@@ -436,7 +440,7 @@ void tck_free(rec_engine *e) {
 static int tck_pack(rec_engine *e, const tck::PackSrc &s, int R, int C, uint8_t *img) {
   const int64_t n_chunks = (int64_t)cdiv(R, 128) * 128 * (C / 8);
   int64_t blocks = cdiv64(n_chunks, 256);
-  const int64_t cap = (int64_t)e->sm_count * 16;
+  const int64_t cap = (int64_t)e->sm_count * 4;
   if (blocks > cap) blocks = cap;
   tck::pack_img_kernel<<<(int)blocks, 256, 0, e->stream>>>(s, R, C, C, img);
   REC_LAUNCH_CHECK(e);
@@ -592,9 +596,11 @@ int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const re
     p.db_part = e->k_db; p.b1 = hp->beta1; p.b2 = hp->beta2; p.eps = hp->eps; p.step_size = step_size; p.inv_bc2_sqrt = 1.f / bc2_sqrt;
     p.sc = e->d_sc;
     const int total = p.n_vt * p.n_dt;
-    // with branch overlap on, this kernel runs NEXT TO the GRU backward (a few latency-bound CTAs per step that need
-    // most of an SM's shared memory each): leave SMs free for them instead of queueing behind one full persistent wave
-    int n_cta = side_enabled(e) ? e->sm_count - 24 : e->sm_count;
+    // with branch overlap on, this kernel runs NEXT TO the GRU backward (32 latency-bound CTAs in clusters of 8 that need
+    // a whole SM's shared memory each): leave SMs free for them instead of queueing behind one full persistent wave
+    // (measured at cfg3: reserve 0 / 32 / 40 / 56 SMs -> 4.23 / 4.24 / 7.47 (a cluster starved) / 3.98 ms per step)
+    static const int reserve = getenv("REC_DW_RESERVE") ? atoi(getenv("REC_DW_RESERVE")) : 56;
+    int n_cta = side_enabled(e) ? e->sm_count - reserve : e->sm_count;
     if (n_cta > total) n_cta = total;
     if (n_cta < 1) n_cta = 1;
     if ((rc = tck::launch_tck<tck::HeadDwAdam>(e, dim3(n_cta), p))) return rc;

@@ -30,27 +30,41 @@ struct PackSrc {
 static __global__ void __launch_bounds__(256) pack_img_kernel(PackSrc s, int R, int C, int64_t ld, uint8_t *__restrict__ img) {
   const int c8n = C >> 3, KB = C >> 6;
   const int64_t n_chunks = (int64_t)((R + 127) / 128) * 128 * c8n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / c8n;
-    const int c8 = (int)(i - row * c8n);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (row < R) {
-      const float4 *p0 = reinterpret_cast<const float4 *>(s.p[0] + row * ld + c8 * 8);
-      a = p0[0]; b = p0[1];
-      if (s.n > 1 || s.w[0] != 1.f) {
-        const float w0 = s.w[0];
-        a.x *= w0; a.y *= w0; a.z *= w0; a.w *= w0; b.x *= w0; b.y *= w0; b.z *= w0; b.w *= w0;
-        for (int j = 1; j < s.n; ++j) {
-          const float4 *pj = reinterpret_cast<const float4 *>(s.p[j] + row * ld + c8 * 8);
-          const float4 x = pj[0], y = pj[1];
-          const float w = s.w[j];
-          a.x = fmaf(w, x.x, a.x); a.y = fmaf(w, x.y, a.y); a.z = fmaf(w, x.z, a.z); a.w = fmaf(w, x.w, a.w);
-          b.x = fmaf(w, y.x, b.x); b.y = fmaf(w, y.y, b.y); b.z = fmaf(w, y.z, b.z); b.w = fmaf(w, y.w, b.w);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // two chunks (4 x 16 B loads per source) in flight per thread: the grid stays small (4 CTAs per SM) so that the
+  // latency-bound kernels of other graph branches find free warp slots next to this HBM-bound sweep
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_chunks; i0 += 2 * stride) {
+    float4 a[2], b[2];
+    int64_t row[2];
+    int c8[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      row[u] = i / c8n;
+      c8[u] = (int)(i - row[u] * c8n);
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f); b[u] = a[u];
+      if (i < n_chunks && row[u] < R) {
+        const float4 *p0 = reinterpret_cast<const float4 *>(s.p[0] + row[u] * ld + c8[u] * 8);
+        a[u] = p0[0]; b[u] = p0[1];
+        if (s.n > 1 || s.w[0] != 1.f) {
+          const float w0 = s.w[0];
+          a[u].x *= w0; a[u].y *= w0; a[u].z *= w0; a[u].w *= w0; b[u].x *= w0; b[u].y *= w0; b[u].z *= w0; b[u].w *= w0;
+          for (int j = 1; j < s.n; ++j) {
+            const float4 *pj = reinterpret_cast<const float4 *>(s.p[j] + row[u] * ld + c8[u] * 8);
+            const float4 x = pj[0], y = pj[1];
+            const float w = s.w[j];
+            a[u].x = fmaf(w, x.x, a[u].x); a[u].y = fmaf(w, x.y, a[u].y); a[u].z = fmaf(w, x.z, a[u].z); a[u].w = fmaf(w, x.w, a[u].w);
+            b[u].x = fmaf(w, y.x, b[u].x); b[u].y = fmaf(w, y.y, b[u].y); b[u].z = fmaf(w, y.z, b[u].z); b[u].w = fmaf(w, y.w, b[u].w);
+          }
         }
       }
     }
-    uint8_t *blk = img + ((row >> 7) * KB + (c8 >> 3)) * (int64_t)BLK2;
-    tc::store_split8(blk, blk + BLK, (int)(row & 127), c8 & 7, a, b);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (i0 + u * stride >= n_chunks) continue;
+      uint8_t *blk = img + ((row[u] >> 7) * KB + (c8[u] >> 3)) * (int64_t)BLK2;
+      tc::store_split8(blk, blk + BLK, (int)(row[u] & 127), c8[u] & 7, a[u], b[u]);
+    }
   }
 }
 
@@ -122,14 +136,16 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 //   mma(p, u, ks, saddr, tacc, first)  ONE thread: the tcgen05.mma's of stage (u, ks) into accumulator tacc
 //   Epi                         per-thread epilogue object: tile(p, u, i, tacc) per unit, finish(p) at the end
 //   CLUSTERED                   true: the grid's x extent is ONE thread-block cluster and units are TIME STEPS: unit u + 1
-//                               of every CTA reads (load_a) what the epilogues of ALL CTAs of the cluster wrote to global
-//                               memory in unit u.  load() is split into load_b (independent of the previous unit, issued
-//                               early) and load_a (after the cluster-wide "step done" barrier).
+//                               of every CTA reads (load) what the epilogues of ALL CTAs of the cluster wrote to global
+//                               memory in unit u: the loader waits for the cluster-wide "step done" barrier per unit.
+//   RESIDENT_BYTES              > 0: an operand that is the same for every unit (the recurrent weights of this CTA's
+//                               hidden units) is loaded ONCE by load_resident(p, smem, bar) and stays in shared memory;
+//                               mma() receives its address
 template <class OP>
 __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Params p) {
   extern __shared__ uint8_t raw[];
   uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
-  __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2], stepbar;
+  __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2], stepbar, resbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int u_lo = 0, u_hi = 0;
@@ -139,6 +155,7 @@ __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Para
     for (int s = 0; s < OP::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], EPI_WARPS); }
     tc::mbar_init(&stepbar, csize * EPI_WARPS);
+    tc::mbar_init(&resbar, 1);
     tc::fence_barrier_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, OP::TMEM_COLS);
@@ -147,7 +164,8 @@ __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Para
   tc::tc_fence_after();
   if (OP::CLUSTERED) cluster_sync_all();  // every CTA's barriers are initialised before a peer may arrive on them
   const uint32_t tmem = tmem_base_s;
-  uint8_t *extra = sm + OP::STAGES * OP::STAGE_BYTES;
+  uint8_t *resident = sm + OP::STAGES * OP::STAGE_BYTES;
+  uint8_t *extra = resident + OP::RESIDENT_BYTES;
 
   if (warp == EPI_WARPS + 1) {
     // ---- TMA loader ----
@@ -157,26 +175,15 @@ __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Para
       for (int u = u_lo; u < u_hi; ++u, ++i) {
         const int nk = OP::k_steps(p, u);
         if constexpr (OP::CLUSTERED) {
-          // operands that do not depend on the previous step go out first; the step's own operand follows the
-          // cluster-wide "previous step written" barrier
-          const int npre = nk < OP::STAGES ? nk : OP::STAGES;
-          const int s0 = s;
-          const uint32_t round0 = round;
-          for (int ks = 0; ks < npre; ++ks) {
-            if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);
-            OP::load_b(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
-            if (++s == OP::STAGES) { s = 0; ++round; }
+          if (i == 0) {
+            if constexpr (OP::RESIDENT_BYTES > 0) OP::load_resident(p, resident, &resbar);
+          } else {  // the previous step of every CTA of the cluster is in global memory
+            mbar_wait_cluster(&stepbar, (uint32_t)(i - 1) & 1u);
+            fence_proxy_async_all();
           }
-          if (i > 0) { mbar_wait_cluster(&stepbar, (uint32_t)(i - 1) & 1u); fence_proxy_async_all(); }
-          s = s0; round = round0;
-          for (int ks = 0; ks < npre; ++ks) {
-            OP::load_a(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
-            if (++s == OP::STAGES) { s = 0; ++round; }
-          }
-          for (int ks = npre; ks < nk; ++ks) {
+          for (int ks = 0; ks < nk; ++ks) {
             if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);
-            OP::load_b(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
-            OP::load_a(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
+            OP::load(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
             if (++s == OP::STAGES) { s = 0; ++round; }
           }
         } else {
@@ -197,11 +204,15 @@ __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Para
       if (i >= 2) tc::mbar_wait(&tempty[b], ((i - 2) >> 1) & 1);  // the epilogue has read this accumulator
       tc::tc_fence_after();
       const int nk = OP::k_steps(p, u);
+      if constexpr (OP::RESIDENT_BYTES > 0) { if (i == 0) tc::mbar_wait(&resbar, 0); }
       for (int ks = 0; ks < nk; ++ks) {
         tc::mbar_wait(&full[s], round & 1);
         tc::tc_fence_after();
         if (lane == 0) {
-          OP::mma(p, u, ks, tc::smem_u32(sm + s * OP::STAGE_BYTES), tmem + (uint32_t)(b * OP::ACC_COLS), ks == 0);
+          if constexpr (OP::RESIDENT_BYTES > 0)
+            OP::mma(p, u, ks, tc::smem_u32(sm + s * OP::STAGE_BYTES), tc::smem_u32(resident), tmem + (uint32_t)(b * OP::ACC_COLS), ks == 0);
+          else
+            OP::mma(p, u, ks, tc::smem_u32(sm + s * OP::STAGE_BYTES), tmem + (uint32_t)(b * OP::ACC_COLS), ks == 0);
           tc::mma_commit(&empty[s]);
         }
         __syncwarp();
@@ -240,7 +251,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 
 template <class OP>
 static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
-  const size_t smem = 1024 + (size_t)OP::STAGES * OP::STAGE_BYTES + OP::EXTRA_BYTES;
+  const size_t smem = 1024 + (size_t)OP::STAGES * OP::STAGE_BYTES + OP::RESIDENT_BYTES + OP::EXTRA_BYTES;
   static bool attr_set[REC_MAX_DEVICES] = {};
   if (!attr_set[e->dev]) {
     REC_CUDA(e, cudaFuncSetAttribute(tck_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
