@@ -13,9 +13,10 @@ Prints ONE JSON line (rank 0).
             HBM peak; `kernels` lists every timed kernel (exactly ONE launch between its two CUDA events) with its own
             algorithmic bytes and fraction, `dominant` is the slowest of them
   cpu_baseline  the CPU oracle (torch-CPU restatement pinned bit-exact to the reference) on this box's host cores
-  secondary the other two measurements of BASELINE.json's metric in the same line: "cfg2" (configs[1]: 70 852 items,
-            the reference's own catalogue size) and "eval" (configs[4]: full-catalogue top-k evaluation sweep over
-            1 M items), each with its own value / e2e / roofline.
+  secondary the other measurements of BASELINE.json's metric in the same line: "cfg2" (configs[1]: 70 852 items,
+            the reference's own catalogue size), "cfg3" (configs[2]: BidirGRU4Rec-SQN, 250 k items, L = 50, H = 256) and
+            "eval" (configs[4]: full-catalogue top-k evaluation sweep over 1 M items), each with its own value / e2e /
+            roofline.
 `--impl reference` times the CPU oracle alone (the reference is pure Python/PyTorch; no GPU code is imported).
 Under torchrun (N > 1): vocabulary-sharded step, see ikea-recommender-system_b200/dist_bench.py.
 """
@@ -41,6 +42,10 @@ WORKLOADS = {
     # configs[1]: SQN-GRU4Rec + SMORL rewards, 70k items, batch 256, 1 B200
     "cfg2": dict(name="cfg2: SMORL-SQN-GRU4Rec train_step, V=N=70852, B=256, L=10, E=H=64, 3 Q-heads + sup head",
                  item_num=70852, batch=256, L=10, E=64, H=64),
+    # configs[2]: BidirGRU4Rec SQN at IKEA-scale synthetic catalogue (250k items, seq len 50, hidden 256); the reference
+    # has no such class: SQN heads on the concatenated bidirectional state, D = 512
+    "cfg3": dict(name="cfg3: BidirGRU4Rec-SQN train_step, V=N=250000, B=256, L=50, E=H=256 (D=512), sup head + 1 Q head",
+                 item_num=250_000, batch=256, L=50, E=256, H=256, family="bidir_sqn"),
 }
 METRIC = "SMORL-SQN-GRU4Rec train sessions/s"
 EVAL_METRIC = "full-catalogue top-k evaluation sessions/s"
@@ -144,6 +149,24 @@ def _make_data(wl, n_batches, seed=0):
     return batches, unpop, e_div
 
 
+def _sqn_kwargs(wl):
+    return dict(hidden_dim=wl["H"], embedding_dim=wl["E"], train_pad_embed=True, use_packed_seq=True, learning_rate=0.005,
+                item_num=wl["item_num"], state_size=wl["L"], action_dim=wl["item_num"], gamma=0.5, gru_layers=1)
+
+
+def _make_trainer(pkg, wl, dev, e_div, unpop):
+    if wl.get("family") == "bidir_sqn":
+        return pkg.SQN_trainer(device=dev, bidirectional=True, **_sqn_kwargs(wl))
+    return pkg.SMORL_trainer(device=dev, **_trainer_kwargs(wl, e_div, unpop))
+
+
+def _make_oracle_trainer(wl, e_div, unpop):
+    import oracle
+    if wl.get("family") == "bidir_sqn":
+        return oracle.SQNTrainer(family="bidir_sqn", **_sqn_kwargs(wl))
+    return oracle.SMORLTrainer(**_trainer_kwargs(wl, e_div, unpop))
+
+
 def _trainer_kwargs(wl, e_div, unpop):
     import torch
     return dict(hidden_dim=wl["H"], embedding_dim=wl["E"], padding_pos="end", train_pad_embed=True,
@@ -156,8 +179,10 @@ def _trainer_kwargs(wl, e_div, unpop):
 def algorithmic_bytes(wl):
     """bytes/step = 24*P + 4*(K_h+1)*D*V; per kernel: dense Adam = 24 B/param (read + write p, m, v),
     a forward statistics pass = 4 B per weight + bias it streams."""
-    V, N, E, H, D, Kh = wl["item_num"], wl["item_num"], wl["E"], wl["H"], wl["H"], 4
-    P = (N + 1) * E + (3 * H * E + 3 * H * H + 6 * H) + Kh * (D * V + V)
+    bidir = wl.get("family") == "bidir_sqn"
+    dirs = 2 if bidir else 1
+    V, N, E, H, D, Kh = wl["item_num"], wl["item_num"], wl["E"], wl["H"], wl["H"] * dirs, (2 if bidir else 4)
+    P = (N + 1) * E + dirs * (3 * H * E + 3 * H * H + 6 * H) + Kh * (D * V + V)
     return dict(step=24 * P + 4 * (Kh + 1) * D * V, head_bwd_adam=24 * Kh * (D + 1) * V, emb_adam=24 * (N + 1) * E,
                 sup_head=24 * (D + 1) * V, q_heads=24 * (Kh - 1) * D * V,
                 sup_stats=4 * (D + 1) * V, greedy_stats=4 * (Kh - 1) * (D + 1) * V)
@@ -179,7 +204,7 @@ def cpu_reference_rate(wl, batches, unpop, e_div, steps, warmup, budget_s=25.0):
     import torch
     import oracle
     torch.set_num_threads(os.cpu_count() or 1)
-    t = oracle.SMORLTrainer(**_trainer_kwargs(wl, e_div, unpop))
+    t = _make_oracle_trainer(wl, e_div, unpop)
     n = len(batches)
     t0 = time.perf_counter()
     t.train_step(*batches[0])
@@ -258,6 +283,15 @@ KERNEL_SLOTS = {  # rec_last_kernel_ms(which): (label, key into algorithmic_byte
 }
 
 
+KERNEL_SLOTS_WIDE = {  # D >= 128 (cfg3): the K-loop tcgen05 kernels over packed operand images (csrc/heads_tck.cu)
+    0: ("tck_kernel<HeadDwAdam> (supervised head: dW^T tile GEMM over the dlogits / h^T images + fused Adam)", "sup_head"),
+    3: ("adam_stream_kernel (Q head, row-sparse grads; weights only, bias in adam_bias_kernel)", "q_heads"),
+    2: ("adam_stream_kernel (embedding table)", "emb_adam"),
+    4: ("tck_kernel<HeadFwd<STATS>> (supervised head: logits K-loop + online softmax, weight image streamed once)", "sup_stats"),
+    5: ("tck_kernel<HeadFwd<ARG>> (greedy action: Q-head logits K-loop + running argmax)", "greedy_stats"),
+}
+
+
 def train_bench(args, wl, wl_key, K, W, local, with_cpu):
     """One single-GPU train-step measurement -> dict (the JSON line without the secondary objects)."""
     import torch
@@ -267,7 +301,7 @@ def train_bench(args, wl, wl_key, K, W, local, with_cpu):
     B = wl["batch"]
     n_b = min(K + W, 64 if wl["item_num"] > 500_000 else 256)
     batches, unpop, e_div = _make_data(wl, n_b)
-    trainer = pkg.SMORL_trainer(device=dev, **_trainer_kwargs(wl, e_div, unpop))
+    trainer = _make_trainer(pkg, wl, dev, e_div, unpop)
     trainer.send_to_device()
     trainer.set_train()
     dev_batches = [tuple(t.to(dev) for t in b) for b in batches]
@@ -300,7 +334,8 @@ def train_bench(args, wl, wl_key, K, W, local, with_cpu):
 
     # ---- roofline: every timed kernel = ONE launch between two CUDA events on the engine's stream ------------
     eng.enable_kernel_timing(True)   # steps run eagerly and serially in this mode
-    kms = {k: [] for k in KERNEL_SLOTS}
+    slots = KERNEL_SLOTS_WIDE if wl.get("family") == "bidir_sqn" else KERNEL_SLOTS
+    kms = {k: [] for k in slots}
     for i in range(min(K, 50)):
         trainer.train_step_async(*dev_batches[(W + i) % n_b])
         for which in kms:
@@ -310,7 +345,7 @@ def train_bench(args, wl, wl_key, K, W, local, with_cpu):
     peak, peak_src, _ = _peaks()
     traffic, traffic_src = _traffic(wl_key)
     kernels = {}
-    for which, (label, key) in KERNEL_SLOTS.items():
+    for which, (label, key) in slots.items():
         t_ms = sum(kms[which]) / len(kms[which])
         a = ab[key] / (t_ms / 1e3) / 1e9
         kernels[label] = {"achieved": a, "frac": a / peak, "kernel_ms": t_ms, "algorithmic_bytes_per_launch": ab[key],
@@ -346,13 +381,16 @@ def train_bench(args, wl, wl_key, K, W, local, with_cpu):
         rate, steps, dt, cores = cpu_reference_rate(wl, batches, unpop, e_div, 40, 1, budget_s=20.0)
         cpu = {"value": rate, "unit": "sessions/s", "cores": cores, "kind": "port",
                "sample": f"{steps} oracle train_step calls at B={B}, full catalogue, {dt:.1f} s"}
-    return {"metric": METRIC, "value": value, "unit": "sessions/s", "n_gpus": 1, "steps": K, "warmup": W,
+    return {"metric": METRIC if wl.get("family") != "bidir_sqn" else "BidirGRU4Rec-SQN train sessions/s",
+            "value": value, "unit": "sessions/s", "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "l2_policy": "working set (p,m,v of the trained net: "
                        f"{ab['step'] / 1e6:.0f} MB/step, twins alternate) exceeds the 126 MB L2; distinct batch every step",
                        "parallelism": "1 GPU", "numerics": "fp32 master weights + fp32 accumulate; head GEMMs as bf16 hi/lo "
-                       "pairs (3 tensor passes); top-k / argmax candidates re-scored in fp32"},
+                       "pairs (3 tensor passes); top-k / argmax candidates re-scored in fp32"
+                       + ("; GRU input projection / recurrence / BPTT / weight gradients as bf16 hi/lo tcgen05 GEMMs"
+                          if wl.get("family") == "bidir_sqn" else "")},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
 
 
@@ -476,6 +514,8 @@ def run_native(args):
         sec = {}
         other = "cfg2" if args.workload == "cfg4" else "cfg4"
         sec[other] = train_bench(args, WORKLOADS[other], other, args.steps, args.warmup, local, False)
+        if args.workload != "cfg3":
+            sec["cfg3"] = train_bench(args, WORKLOADS["cfg3"], "cfg3", min(args.steps, 100), args.warmup, local, with_cpu)
         sec["eval"] = eval_bench(args, EVAL_WORKLOADS["eval"], local, with_cpu)
         line["secondary"] = sec
     print(json.dumps(line), flush=True)

@@ -116,6 +116,7 @@ struct Gemm {
   using Params = GemmParams;
   static constexpr bool CLUSTERED = false;
   static constexpr int RESIDENT_BYTES = 0;
+  static constexpr int EPI_WARPS = 8;
   static constexpr const char *NAME = "tck:gemm";
   static constexpr int STAGES = 2, STAGE_BYTES = 3 * BLK2, ACC_COLS = 256, TMEM_COLS = 512;
   static constexpr int EXTRA_BYTES = 0;
@@ -277,6 +278,7 @@ struct GruStep {
   // shared memory, only the image of h_{t-1} streams in (all four k-blocks in flight at once), and h_t travels to the
   // other CTAs through the ping/pong image in global memory + the cluster-wide step barrier.
   static constexpr bool CLUSTERED = true;
+  static constexpr int EPI_WARPS = 8;
   static constexpr const char *NAME = "tck:gru_steps";
   static constexpr int WB = 2 * 96 * 128;  // one (unit, k-block) of the regrouped W_hh image: hi 12 KB | lo 12 KB
   static constexpr int STAGES = 4, STAGE_BYTES = BLK2, ACC_COLS = 128, TMEM_COLS = 256;
@@ -438,6 +440,7 @@ struct GruBptt {
   // their rows of W_hh^T (all 3H/64 k-blocks) stay RESIDENT in shared memory, the step image of the gate gradients
   // streams in through 4 stages.
   static constexpr bool CLUSTERED = true;
+  static constexpr int EPI_WARPS = 8;
   static constexpr const char *NAME = "tck:gru_bptt";
   static constexpr int STAGES = 4, STAGE_BYTES = BLK2, ACC_COLS = 32, TMEM_COLS = 64;
   static constexpr int RESIDENT_BYTES = 12 * 8192;  // 3H/64 k-blocks x (32 rows hi 4 KB | lo 4 KB), H <= 256

@@ -50,6 +50,7 @@ struct HeadFwd {
   using Params = FwdParams;
   static constexpr bool CLUSTERED = false;
   static constexpr int RESIDENT_BYTES = 0;
+  static constexpr int EPI_WARPS = 8;
   static constexpr const char *NAME = MODE == M_STATS ? "tck:head_stats" : MODE == M_ARG ? "tck:head_greedy" : "tck:head_dlogits";
   static constexpr int STAGES = 3, STAGE_BYTES = 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
   static constexpr int EXTRA_BYTES = 8192;
@@ -229,6 +230,7 @@ struct HeadDh {
   using Params = DhParams;
   static constexpr bool CLUSTERED = false;
   static constexpr int RESIDENT_BYTES = 0;
+  static constexpr int EPI_WARPS = 8;
   static constexpr const char *NAME = "tck:head_dh";
   static constexpr int STAGES = 2, STAGE_BYTES = 12 * HALF, ACC_COLS = 256, TMEM_COLS = 256;
   static constexpr int EXTRA_BYTES = 0;
@@ -316,6 +318,7 @@ struct HeadDwAdam {
   using Params = DwParams;
   static constexpr bool CLUSTERED = false;
   static constexpr int RESIDENT_BYTES = 0;
+  static constexpr int EPI_WARPS = 8;
   static constexpr const char *NAME = "tck:head_dw_adam";
   static constexpr int STAGES = 2, STAGE_BYTES = 3 * BLK2, ACC_COLS = 256, TMEM_COLS = 512;
   static constexpr int EXTRA_BYTES = 0;
@@ -514,6 +517,9 @@ int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_ou
   p.himg = himg; p.wimg = wimg; p.KB = KB; p.B = a.B; p.Vloc = e->Vloc; p.vocab_lo = e->cfg.vocab_lo; p.n_tiles = n_tiles;
   p.bias = bias; p.target = arg ? nullptr : a.target; p.part = e->part; p.part_stride = e->part_stride;
   dim3 grid(n_split, n_sb);
+  // kernel-timing mode: the caller's start event (slot 4 statistics / slot 5 greedy action) is re-recorded here so that
+  // it brackets exactly this ONE launch, not the packing kernels above
+  if (e->timing) cudaEventRecord(e->ev[arg ? 10 : 8], e->stream);
   rc = arg ? tck::launch_tck<tck::HeadFwd<tck::M_ARG>>(e, grid, p) : tck::launch_tck<tck::HeadFwd<tck::M_STATS>>(e, grid, p);
   if (rc) return rc;
   *n_split_out = n_split;
@@ -603,6 +609,7 @@ int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const re
     int n_cta = side_enabled(e) ? e->sm_count - reserve : e->sm_count;
     if (n_cta > total) n_cta = total;
     if (n_cta < 1) n_cta = 1;
+    if (e->timing) cudaEventRecord(e->ev[0], e->stream);  // slot 0 brackets this ONE launch (the caller records the end)
     if ((rc = tck::launch_tck<tck::HeadDwAdam>(e, dim3(n_cta), p))) return rc;
   }
   return REC_OK;

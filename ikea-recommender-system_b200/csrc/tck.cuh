@@ -142,7 +142,8 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 //                               hidden units) is loaded ONCE by load_resident(p, smem, bar) and stays in shared memory;
 //                               mma() receives its address
 template <class OP>
-__global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Params p) {
+__global__ void __launch_bounds__(OP::EPI_WARPS * 32 + 64, 1) tck_kernel(const typename OP::Params p) {
+  constexpr int EPI_WARPS = OP::EPI_WARPS;  // 8 (default) or 16 epilogue warps + issuer warp + loader warp
   extern __shared__ uint8_t raw[];
   uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
   __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2], stepbar, resbar;
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Para
     if (lane == 0) {
       int s = 0, i = 0;
       uint32_t round = 0;
+      if constexpr (!OP::CLUSTERED && OP::RESIDENT_BYTES > 0) OP::load_resident(p, resident, &resbar);
       for (int u = u_lo; u < u_hi; ++u, ++i) {
         const int nk = OP::k_steps(p, u);
         if constexpr (OP::CLUSTERED) {
@@ -247,7 +249,8 @@ __global__ void __launch_bounds__(THREADS, 1) tck_kernel(const typename OP::Para
   if (warp == 0) tc::tmem_dealloc(tmem, OP::TMEM_COLS);
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+template <int NTHREADS = EPI_THREADS>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 template <class OP>
 static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
@@ -259,14 +262,14 @@ static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
   }
   if (OP::CLUSTERED) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+    cfg.gridDim = grid; cfg.blockDim = dim3(OP::EPI_WARPS * 32 + 64); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = grid.x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     REC_CUDA(e, cudaLaunchKernelEx(&cfg, tck_kernel<OP>, p));
   } else {
-    tck_kernel<OP><<<grid, THREADS, smem, e->stream>>>(p);
+    tck_kernel<OP><<<grid, OP::EPI_WARPS * 32 + 64, smem, e->stream>>>(p);
   }
   e->launches++;
   if (e->tl_on) rec_timeline_record(e, OP::NAME, 0);
