@@ -21,8 +21,9 @@ int launch_unpack_batch(rec_engine *e, const uint8_t *gathered, int G, int Bl, s
 static char g_err[512] = "";
 
 static int head_stats_dispatch(rec_engine *e, const HeadStatsArgs &a, int *n_split) {
+  if (tck_topk_supported(e, a)) return launch_head_stats_tck(e, a, n_split);  // evaluation-shaped top-k (any D % 64 == 0)
   if (tc_heads_supported(e)) return launch_head_stats_tc(e, a, n_split);
-  if (tck_heads_supported(e) && a.topk == 0) return launch_head_stats_tck(e, a, n_split);  // top-k (evaluation) at D > 64: CUDA-core path
+  if (tck_heads_supported(e) && a.topk == 0) return launch_head_stats_tck(e, a, n_split);
   return launch_head_stats(e, a, n_split);
 }
 

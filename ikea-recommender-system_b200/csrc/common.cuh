@@ -291,6 +291,7 @@ int launch_head_stats_tc(rec_engine *e, const HeadStatsArgs &a, int *n_split_out
 bool tc_bwd_supported(const rec_engine *e, int B);
 // heads_tck.cu: D = 128, 256, ... (K-loop pipelines over packed operand images)
 bool tck_heads_supported(const rec_engine *e);
+bool tck_topk_supported(const rec_engine *e, const HeadStatsArgs &a);
 int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 int tck_bwd_slices(const rec_engine *e);
 int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,

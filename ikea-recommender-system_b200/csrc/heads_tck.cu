@@ -41,6 +41,7 @@ struct FwdParams {
   uint8_t *dlT;                // DL: image [n_tiles][dl_cb]
   int dl_cb;
   float *db_part;              // DL: [n_sb][n_tiles * 128]
+  int topk;                    // HeadTopk: k of the running top-k (<= 20)
 };
 
 enum { M_STATS = 0, M_ARG = 1, M_DL = 2 };
@@ -212,6 +213,176 @@ struct HeadFwd {
           o[TOPK_OFF] = v0; o[TOPK_OFF + REC_MAX_TOPK] = __int_as_float(i0);
           o[TOPK_OFF + 1] = v1; o[TOPK_OFF + REC_MAX_TOPK + 1] = __int_as_float(i1);
         }
+      }
+    }
+  };
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Evaluation-shaped forward: statistics + running top-k (k <= 20; score desc, id asc) of every row, 16 epilogue warps
+// (four 32-column quarters per row and tile).  ARES: D = 64 -- the 128-session state block stays resident in shared
+// memory and only the weight image streams (3 stages); D > 64: state and weight k-blocks stream together (2 stages).
+// Against head_stats_tc_kernel (heads_tc.cu) at evaluation shapes: no fp32 staging ring and no converter warps (the
+// image is packed once per batch: 85 us at 1 M items against ~4 ms of scoring), twice the epilogue warps per logit.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void topk_insert(float v, int id, float *lv, int *li, int stride, int topk, int &cnt, float &tau) {
+  int p = cnt < topk ? cnt : topk - 1;
+  while (p > 0 && lv[(p - 1) * stride] < v) {
+    lv[p * stride] = lv[(p - 1) * stride];
+    li[p * stride] = li[(p - 1) * stride];
+    --p;
+  }
+  lv[p * stride] = v;
+  li[p * stride] = id;
+  if (cnt < topk) ++cnt;
+  tau = cnt == topk ? lv[(topk - 1) * stride] : REC_NEG_INF;
+}
+
+template <bool ARES>
+struct HeadTopk {
+  using Params = FwdParams;
+  static constexpr bool CLUSTERED = false;
+  static constexpr int EPI_WARPS = 16, NT = 512, CS = 4, KMAX = 20;
+  static constexpr int RESIDENT_BYTES = ARES ? BLK2 : 0;
+  static constexpr const char *NAME = ARES ? "tck:head_topk64" : "tck:head_topk";
+  static constexpr int STAGES = ARES ? 3 : 2, STAGE_BYTES = ARES ? BLK2 : 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
+  static constexpr int LIST_BYTES = KMAX * NT * 8, XCH_BYTES = 128 * CS * 5 * 4;
+  static constexpr int EXTRA_BYTES = LIST_BYTES + XCH_BYTES;
+
+  __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) {
+    const int per = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    lo = blockIdx.x * per;
+    hi = min(p.n_tiles, lo + per);
+    if (hi < lo) hi = lo;
+  }
+  __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KB; }
+  __device__ static __forceinline__ void load_resident(const Params &p, uint8_t *res, uint64_t *bar) {
+    tc::mbar_expect_tx(bar, BLK2);
+    tc::bulk_g2s(res, p.himg + (int64_t)blockIdx.y * p.KB * BLK2, BLK2, bar);
+  }
+  __device__ static __forceinline__ void load(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+    if (ARES) {
+      tc::mbar_expect_tx(bar, BLK2);
+      tc::bulk_g2s(stage, p.wimg + ((int64_t)u * p.KB + ks) * BLK2, BLK2, bar);
+    } else {
+      tc::mbar_expect_tx(bar, 2 * BLK2);
+      tc::bulk_g2s(stage, p.himg + ((int64_t)blockIdx.y * p.KB + ks) * BLK2, BLK2, bar);
+      tc::bulk_g2s(stage + BLK2, p.wimg + ((int64_t)u * p.KB + ks) * BLK2, BLK2, bar);
+    }
+  }
+  __device__ static __forceinline__ void mma_ab(uint32_t a0, uint32_t b0, uint32_t tacc, bool first) {
+    const uint32_t id = tc::instr_desc(128, 128, 0, 0);
+    const uint64_t ah = tc::desc_kmajor(a0, 0), al = tc::desc_kmajor(a0 + BLK, 0);
+    const uint64_t bh = tc::desc_kmajor(b0, 0), bl = tc::desc_kmajor(b0 + BLK, 0);
+    bool acc = !first;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint64_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { tc::mma_bf16(tacc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), id, acc); acc = true; }
+    }
+  }
+  __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t res, uint32_t tacc, bool first) {
+    mma_ab(res, st, tacc, first);
+  }
+  __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
+    mma_ab(st, st + BLK2, tacc, first);
+  }
+
+  struct Epi {
+    float *lv, *xs;
+    int *li;
+    int q, cq, lane, row, trow, cnt, tid_;
+    float m_run, s_run, tgt, tau;
+    bool rv;
+    __device__ __forceinline__ Epi(const Params &p, uint8_t *extra, int tid) {
+      tid_ = tid;
+      lv = reinterpret_cast<float *>(extra) + tid;
+      li = reinterpret_cast<int *>(extra + KMAX * NT * 4) + tid;
+      xs = reinterpret_cast<float *>(extra + LIST_BYTES);
+      const int warp = tid >> 5;
+      lane = tid & 31; q = warp & 3; cq = warp >> 2;
+      row = blockIdx.y * 128 + q * 32 + lane;
+      rv = row < p.B;
+      m_run = REC_NEG_INF; s_run = 0.f; tgt = REC_NEG_INF; tau = REC_NEG_INF; cnt = 0;
+      trow = (p.target && rv) ? (int)(p.target[row] - p.vocab_lo) : -1;
+    }
+    __device__ __forceinline__ void tile(const Params &p, int u, int, uint32_t tacc) {
+      const int c_lo = u * 128 + cq * 32;
+      float l[32];
+      tc::tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32), l);
+      if (c_lo + 32 <= p.Vloc) {
+        const float4 *bg = reinterpret_cast<const float4 *>(p.bias + c_lo);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(bg + (j >> 2));
+          l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) l[j] = (c_lo + j < p.Vloc) ? l[j] + __ldg(p.bias + c_lo + j) : REC_NEG_INF;
+      }
+      float tmax = fmaxf(l[0], l[1]);
+#pragma unroll
+      for (int j = 2; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
+      {
+        const float nm = fmaxf(m_run, tmax), nml = -fmaxf(nm, -1e30f) * LOG2E;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ps[j & 3] += tc::ex2_ftz(fmaf(l[j], LOG2E, nml));
+        s_run = fmaf(s_run, tc::ex2_ftz((m_run - nm) * LOG2E), (ps[0] + ps[1]) + (ps[2] + ps[3]));
+        m_run = nm;
+      }
+      if (trow >= c_lo && trow < c_lo + 32) {
+        const int tj = trow - c_lo;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j == tj) tgt = l[j];
+      }
+      if (tmax > tau) {  // rare once the list has warmed up: walk the chunk in ascending column order (ties: lowest id first)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (l[j] > tau) topk_insert(l[j], p.vocab_lo + c_lo + j, lv, li, NT, p.topk, cnt, tau);
+      }
+    }
+    __device__ __forceinline__ void finish(const Params &p) {
+      float *x = xs + ((q * 32 + lane) * CS + cq) * 5;
+      x[0] = m_run; x[1] = s_run; x[2] = tgt;
+      for (int k = cnt; k < p.topk; ++k) { lv[k * NT] = REC_NEG_INF; li[k * NT] = 0x7fffffff; }
+      epi_bar<NT>();
+      if (cq != 0 || !rv) return;
+      const float *y = xs + ((q * 32 + lane) * CS) * 5;
+      float m = REC_NEG_INF, tg = REC_NEG_INF;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) { m = fmaxf(m, y[c * 5]); tg = fmaxf(tg, y[c * 5 + 2]); }
+      float ssum = 0.f;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) if (y[c * 5 + 1] > 0.f) ssum += y[c * 5 + 1] * __expf(y[c * 5] - m);
+      float *o = p.part + ((int64_t)blockIdx.x * p.B + row) * p.part_stride;
+      o[0] = m; o[1] = ssum; o[2] = tg; o[3] = REC_NEG_INF; o[4] = __int_as_float(0x7fffffff);
+      // CS-way merge of the sorted private lists (ids of different quarters are disjoint); rec_kpub(topk, CS) >= topk
+      // entries leave the CTA so that the fp32 re-score of the final merge has a margin of candidates
+      const float *tvb = reinterpret_cast<const float *>(lv - tid_);
+      const int *tib = reinterpret_cast<const int *>(li - tid_);
+      const int kpub = rec_kpub(p.topk, CS);
+      int pos[CS];
+#pragma unroll
+      for (int c = 0; c < CS; ++c) pos[c] = 0;
+      for (int k = 0; k < kpub; ++k) {
+        float cv = REC_NEG_INF;
+        int ci = 0x7fffffff, cc = 0;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) {
+          if (pos[c] < p.topk) {
+            const int t2 = (c * 4 + q) * 32 + lane;  // thread id of (q, cq = c, lane)
+            const float v = tvb[pos[c] * NT + t2];
+            const int i = tib[pos[c] * NT + t2];
+            if (better(v, i, cv, ci)) { cv = v; ci = i; cc = c; }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CS; ++c) if (c == cc) ++pos[c];
+        o[TOPK_OFF + k] = cv;
+        o[TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(ci);
       }
     }
   };
@@ -412,6 +583,14 @@ struct HeadDwAdam {
 // Host side
 // ------------------------------------------------------------------------------------------------------------
 bool tck_heads_supported(const rec_engine *e) { return e->use_tc && e->D >= 128 && e->D % 128 == 0 && e->D <= 1024; }
+// statistics + running top-k over operand images: any D % 64 == 0 (D = 64: evaluation-shaped k only -- the training
+// steps' k <= 2 stay with head_stats_tc_kernel, which keeps them in registers)
+bool tck_topk_supported(const rec_engine *e, const HeadStatsArgs &a) {
+  static const int off = getenv("REC_NO_TCK_TOPK") ? 1 : 0;
+  if (off || !e->use_tc || a.n_arg > 0 || a.topk < 1 || a.topk > tck::HeadTopk<true>::KMAX) return false;
+  if (e->D == 64) return a.topk > 8;
+  return e->D % 128 == 0 && e->D <= 1024;
+}
 
 static int tck_alloc(rec_engine *e, void **ptr, size_t bytes) {
   if (*ptr) return REC_OK;
@@ -422,16 +601,25 @@ static int tck_alloc(rec_engine *e, void **ptr, size_t bytes) {
 }
 
 // Operand images are sized by max_batch / Vloc / D at first use and live as long as the engine.
-static int tck_ensure(rec_engine *e) {
+// what: 1 = forward (weight image 0, state image 0), 2 = greedy-action pass (image 1), 4 = backward (dl^T, h^T, db)
+static int tck_ensure(rec_engine *e, int what) {
   const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(e->cfg.max_batch, 128);
   int rc;
-  const size_t wbytes = (size_t)n_tiles * KB * tck::BLK2;
-  for (int i = 0; i < 2; ++i) if ((rc = tck_alloc(e, (void **)&e->k_wimg[i], wbytes))) return rc;
-  for (int i = 0; i < 2; ++i) if ((rc = tck_alloc(e, (void **)&e->k_himg[i], (size_t)n_sb * KB * tck::BLK2))) return rc;
-  if ((rc = tck_alloc(e, (void **)&e->k_hT, (size_t)(e->D / 128) * (2 * n_sb) * tck::BLK2))) return rc;
-  if ((rc = tck_alloc(e, (void **)&e->k_dlT, (size_t)n_tiles * (2 * n_sb) * tck::BLK2))) return rc;
-  if ((rc = tck_alloc(e, (void **)&e->k_db, sizeof(float) * (size_t)n_sb * n_tiles * 128))) return rc;
-  if ((rc = tck_alloc(e, (void **)&e->k_bias, sizeof(float) * (size_t)n_tiles * 128))) return rc;
+  const size_t wbytes = (size_t)n_tiles * KB * tck::BLK2, hbytes = (size_t)n_sb * KB * tck::BLK2;
+  if (what & 1) {
+    if ((rc = tck_alloc(e, (void **)&e->k_wimg[0], wbytes))) return rc;
+    if ((rc = tck_alloc(e, (void **)&e->k_himg[0], hbytes))) return rc;
+  }
+  if (what & 2) {
+    if ((rc = tck_alloc(e, (void **)&e->k_wimg[1], wbytes))) return rc;
+    if ((rc = tck_alloc(e, (void **)&e->k_himg[1], hbytes))) return rc;
+    if ((rc = tck_alloc(e, (void **)&e->k_bias, sizeof(float) * (size_t)n_tiles * 128))) return rc;
+  }
+  if (what & 4) {
+    if ((rc = tck_alloc(e, (void **)&e->k_hT, (size_t)(e->D / 128) * (2 * n_sb) * tck::BLK2))) return rc;
+    if ((rc = tck_alloc(e, (void **)&e->k_dlT, (size_t)n_tiles * (2 * n_sb) * tck::BLK2))) return rc;
+    if ((rc = tck_alloc(e, (void **)&e->k_db, sizeof(float) * (size_t)n_sb * n_tiles * 128))) return rc;
+  }
   return REC_OK;
 }
 
@@ -477,7 +665,7 @@ static int tck_pack_head_image(rec_engine *e, int net_id, int head, int n_arg, c
 // GRU forward runs (HBM-bound packing next to the latency-bound recurrence).
 int tck_prepack_heads(rec_engine *e, int net_id, int n_arg, const float *w) {
   if (!tck_heads_supported(e)) return REC_OK;
-  int rc = tck_ensure(e);
+  int rc = tck_ensure(e, n_arg > 0 ? 3 : 1);
   if (rc) return rc;
   if ((rc = tck_pack_head_image(e, net_id, 0, 0, w))) return rc;
   e->k_fresh[0] = true;
@@ -490,8 +678,10 @@ int tck_prepack_heads(rec_engine *e, int net_id, int n_arg, const float *w) {
 
 // Same contract as launch_head_stats (heads.cu) for statistics (no top-k) and the greedy-action pass.
 int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
-  int rc = tck_ensure(e);
+  int rc = tck_ensure(e, a.n_arg > 0 ? 2 : 1);
   if (rc) return rc;
+  if (a.topk > tck::HeadTopk<true>::KMAX || (a.topk > 0 && a.n_arg > 0))
+    REC_FAIL(e, REC_EINVAL, "tensor-core statistics over operand images: top-k <= %d, not combined with a greedy-action pass", tck::HeadTopk<true>::KMAX);
   const rec_net_params &np = e->nets[a.net_id].p;
   const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(a.B, 128);
   const bool arg = a.n_arg > 0;
@@ -520,11 +710,13 @@ int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_ou
   // kernel-timing mode: the caller's start event (slot 4 statistics / slot 5 greedy action) is re-recorded here so that
   // it brackets exactly this ONE launch, not the packing kernels above
   if (e->timing) cudaEventRecord(e->ev[arg ? 10 : 8], e->stream);
-  rc = arg ? tck::launch_tck<tck::HeadFwd<tck::M_ARG>>(e, grid, p) : tck::launch_tck<tck::HeadFwd<tck::M_STATS>>(e, grid, p);
+  p.topk = a.topk;
+  if (a.topk > 0) rc = KB == 1 ? tck::launch_tck<tck::HeadTopk<true>>(e, grid, p) : tck::launch_tck<tck::HeadTopk<false>>(e, grid, p);
+  else rc = arg ? tck::launch_tck<tck::HeadFwd<tck::M_ARG>>(e, grid, p) : tck::launch_tck<tck::HeadFwd<tck::M_STATS>>(e, grid, p);
   if (rc) return rc;
   *n_split_out = n_split;
   e->st_approx = true;
-  e->st_kpub = 0;
+  e->st_kpub = a.topk > 0 ? rec_kpub(a.topk, tck::HeadTopk<true>::CS) : 0;
   e->st_apub = arg ? 2 : 0;
   return REC_OK;
 }
@@ -545,7 +737,7 @@ int tck_bwd_slices(const rec_engine *e) {
 // Writes tck_bwd_slices(e) slices of dh_part (every slice fully).
 int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                              float bc2_sqrt, const rec_train_hparams *hp, float inv_B) {
-  int rc = tck_ensure(e);
+  int rc = tck_ensure(e, 1 | 4);
   if (rc) return rc;
   const rec_net_params &np = e->nets[net_id].p;
   const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(B, 128);
