@@ -777,6 +777,12 @@ extern "C" int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, con
   HeadStatsArgs a = {};
   a.net_id = net_id; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = o->head_idx; a.target = b->a; a.topk = kmax;
   int n_split = 0;
+  if (tck_chunk_topk_supported(e, a)) {
+    // large batch x large catalogue: chunk maxima on the tensor cores, exact top-k from the best chunks (heads_tck.cu)
+    if ((rc = launch_head_topk_chunks(e, a, &n_split, nullptr))) return rc;
+    if ((rc = launch_head_merge(e, e->part, n_split, B, 0, true, false, nullptr, &a))) return rc;
+    return launch_eval_metrics(e, b, o, kmax, acc, extra(e).rowm, topk_ids, topk_scores);
+  }
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
   if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
   if (e->timing) cudaEventRecord(e->ev[3], e->stream);
@@ -796,8 +802,13 @@ static int shard_head_pass(rec_engine *e, int net_id, const float *h, const rec_
     HeadStatsArgs a = {};
     a.net_id = net_id; a.h = h; a.B = b->B; a.do_stats = want_stats ? 1 : 0; a.stats_head = stats_head; a.target = b->a;
     a.topk = topk;
-    if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
-    if ((rc = launch_head_merge(e, e->part, n_split, b->B, topk, want_stats, false, summary, &a))) return rc;
+    if (want_stats && n_q == 0 && tck_chunk_topk_supported(e, a)) {
+      if ((rc = launch_head_topk_chunks(e, a, &n_split, summary))) return rc;
+      if ((rc = launch_head_merge(e, e->part, n_split, b->B, 0, true, false, summary, &a))) return rc;
+    } else {
+      if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
+      if ((rc = launch_head_merge(e, e->part, n_split, b->B, topk, want_stats, false, summary, &a))) return rc;
+    }
   }
   if (n_q > 0) {
     HeadStatsArgs g = {};

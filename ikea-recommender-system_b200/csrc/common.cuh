@@ -115,6 +115,8 @@ struct rec_engine {
   float *k_db;           // bias-gradient partials [session blocks][V]
   float *k_bias;         // combined bias of the greedy-action heads
   int k_sup_net, k_sup_head;  // which (net, head) k_wimg[0] / k_himg[0] currently hold (-1: none)
+  float *k_cmax;         // chunk maxima [B][V/32] of the evaluation top-k (HeadTopk<.., CM>)
+  int *k_chosen;         // [B][KC] the chunks with the largest maxima per row
   bool k_fresh[2];       // k_wimg[i] was packed ahead of its consumer in this step (tck_prepack_heads)
   // tensor-core GRU trunk for E, H >= 128 (gru_tc.cu); allocated at first use
   uint8_t *g_wimg;       // [net][dir][W_ih | W_hh | W_hh regrouped] weight images
@@ -292,6 +294,8 @@ bool tc_bwd_supported(const rec_engine *e, int B);
 // heads_tck.cu: D = 128, 256, ... (K-loop pipelines over packed operand images)
 bool tck_heads_supported(const rec_engine *e);
 bool tck_topk_supported(const rec_engine *e, const HeadStatsArgs &a);
+bool tck_chunk_topk_supported(const rec_engine *e, const HeadStatsArgs &a);
+int launch_head_topk_chunks(rec_engine *e, const HeadStatsArgs &a, int *n_split_out, float *summary);
 int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 int tck_bwd_slices(const rec_engine *e);
 int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,

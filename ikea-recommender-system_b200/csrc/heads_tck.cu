@@ -42,6 +42,9 @@ struct FwdParams {
   int dl_cb;
   float *db_part;              // DL: [n_sb][n_tiles * 128]
   int topk;                    // HeadTopk: k of the running top-k (<= 20)
+  float *cmax;                 // HeadTopk<.., CM>: chunk maxima [B][cmax_ld >= n_tiles * 4]
+  int64_t cmax_ld;
+  int n_sb, per;               // HeadCmaxFlat: session blocks, units per CTA of the flattened (session block, tile) space
 };
 
 enum { M_STATS = 0, M_ARG = 1, M_DL = 2 };
@@ -238,15 +241,19 @@ __device__ __noinline__ void topk_insert(float v, int id, float *lv, int *li, in
   tau = cnt == topk ? lv[(topk - 1) * stride] : REC_NEG_INF;
 }
 
-template <bool ARES>
+// CM (chunk maxima, large evaluation batches): no lists at all in this pass -- every thread writes the maximum of its
+// 32-column chunk to cmax[chunk][row]; chunk_select_kernel + chunk_rescore_kernel (below) then find the k + margin chunks
+// with the largest maxima per row (every top-k element lies in one of the k chunks with the largest maxima) and score
+// those chunks exactly in fp32.  The tensor-core pass becomes a divergence-free streaming epilogue.
+template <bool ARES, bool CM = false>
 struct HeadTopk {
   using Params = FwdParams;
   static constexpr bool CLUSTERED = false;
   static constexpr int EPI_WARPS = 16, NT = 512, CS = 4, KMAX = 20;
   static constexpr int RESIDENT_BYTES = ARES ? BLK2 : 0;
-  static constexpr const char *NAME = ARES ? "tck:head_topk64" : "tck:head_topk";
-  static constexpr int STAGES = ARES ? 3 : 2, STAGE_BYTES = ARES ? BLK2 : 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
-  static constexpr int LIST_BYTES = KMAX * NT * 8, XCH_BYTES = 128 * CS * 5 * 4;
+  static constexpr const char *NAME = CM ? (ARES ? "tck:head_cmax64" : "tck:head_cmax") : (ARES ? "tck:head_topk64" : "tck:head_topk");
+  static constexpr int STAGES = ARES ? (CM ? 4 : 3) : (CM ? 3 : 2), STAGE_BYTES = ARES ? BLK2 : 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
+  static constexpr int LIST_BYTES = CM ? 0 : KMAX * NT * 8, XCH_BYTES = 128 * CS * 5 * 4;
   static constexpr int EXTRA_BYTES = LIST_BYTES + XCH_BYTES;
 
   __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) {
@@ -298,7 +305,7 @@ struct HeadTopk {
     __device__ __forceinline__ Epi(const Params &p, uint8_t *extra, int tid) {
       tid_ = tid;
       lv = reinterpret_cast<float *>(extra) + tid;
-      li = reinterpret_cast<int *>(extra + KMAX * NT * 4) + tid;
+      li = reinterpret_cast<int *>(extra + (CM ? 0 : KMAX * NT * 4)) + tid;
       xs = reinterpret_cast<float *>(extra + LIST_BYTES);
       const int warp = tid >> 5;
       lane = tid & 31; q = warp & 3; cq = warp >> 2;
@@ -338,7 +345,9 @@ struct HeadTopk {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j == tj) tgt = l[j];
       }
-      if (tmax > tau) {  // rare once the list has warmed up: walk the chunk in ascending column order (ties: lowest id first)
+      if (CM) {
+        if (rv) p.cmax[(int64_t)row * p.cmax_ld + (u * CS + cq)] = tmax;
+      } else if (tmax > tau) {  // rare once the list has warmed up: walk the chunk in ascending column order (ties: lowest id first)
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (l[j] > tau) topk_insert(l[j], p.vocab_lo + c_lo + j, lv, li, NT, p.topk, cnt, tau);
@@ -347,7 +356,7 @@ struct HeadTopk {
     __device__ __forceinline__ void finish(const Params &p) {
       float *x = xs + ((q * 32 + lane) * CS + cq) * 5;
       x[0] = m_run; x[1] = s_run; x[2] = tgt;
-      for (int k = cnt; k < p.topk; ++k) { lv[k * NT] = REC_NEG_INF; li[k * NT] = 0x7fffffff; }
+      if (!CM) for (int k = cnt; k < p.topk; ++k) { lv[k * NT] = REC_NEG_INF; li[k * NT] = 0x7fffffff; }
       epi_bar<NT>();
       if (cq != 0 || !rv) return;
       const float *y = xs + ((q * 32 + lane) * CS) * 5;
@@ -359,6 +368,7 @@ struct HeadTopk {
       for (int c = 0; c < CS; ++c) if (y[c * 5 + 1] > 0.f) ssum += y[c * 5 + 1] * __expf(y[c * 5] - m);
       float *o = p.part + ((int64_t)blockIdx.x * p.B + row) * p.part_stride;
       o[0] = m; o[1] = ssum; o[2] = tg; o[3] = REC_NEG_INF; o[4] = __int_as_float(0x7fffffff);
+      if (CM) return;
       // CS-way merge of the sorted private lists (ids of different quarters are disjoint); rec_kpub(topk, CS) >= topk
       // entries leave the CTA so that the fp32 re-score of the final merge has a margin of candidates
       const float *tvb = reinterpret_cast<const float *>(lv - tid_);
@@ -387,6 +397,285 @@ struct HeadTopk {
     }
   };
 };
+
+// The chunk-maxima pass over the FLATTENED unit space (session block, tile): every CTA gets the same number of units
+// whatever the ratio of session blocks to SMs (a [splits x session blocks] grid leaves 28 of 148 SMs idle at 40 session
+// blocks).  A CTA may cross session-block boundaries: it publishes one statistics record per block it touched, in slot
+// (CTA index - first CTA of that block); untouched slots hold neutral records (fill_neutral_records_kernel).
+__global__ void fill_neutral_records_kernel(float *__restrict__ part, int64_t n, int stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float *o = part + i * stride;
+  o[0] = REC_NEG_INF; o[1] = 0.f; o[2] = REC_NEG_INF; o[3] = REC_NEG_INF; o[4] = __int_as_float(0x7fffffff);
+}
+
+struct HeadCmaxFlat {
+  using Params = FwdParams;
+  static constexpr bool CLUSTERED = false;
+  static constexpr int EPI_WARPS = 16, NT = 512, CS = 4;
+  static constexpr int RESIDENT_BYTES = 0;
+  static constexpr const char *NAME = "tck:head_cmax_flat";
+  static constexpr int STAGES = 3, STAGE_BYTES = 2 * BLK2, ACC_COLS = 128, TMEM_COLS = 256;
+  static constexpr int EXTRA_BYTES = 128 * CS * 5 * 4;
+  __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) {
+    const int total = p.n_sb * p.n_tiles;
+    lo = blockIdx.x * p.per;
+    hi = min(total, lo + p.per);
+    if (hi < lo) hi = lo;
+  }
+  __device__ static __forceinline__ int k_steps(const Params &p, int) { return p.KB; }
+  __device__ static __forceinline__ void load(const Params &p, int u, int ks, uint8_t *stage, uint64_t *bar) {
+    const int sb = u / p.n_tiles, t = u - sb * p.n_tiles;
+    tc::mbar_expect_tx(bar, 2 * BLK2);
+    tc::bulk_g2s(stage, p.himg + ((int64_t)sb * p.KB + ks) * BLK2, BLK2, bar);
+    tc::bulk_g2s(stage + BLK2, p.wimg + ((int64_t)t * p.KB + ks) * BLK2, BLK2, bar);
+  }
+  __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
+    HeadTopk<false, true>::mma_ab(st, st + BLK2, tacc, first);
+  }
+  struct Epi {
+    float *xs;
+    int q, cq, lane, row, trow, cur_sb;
+    float m_run, s_run, tgt;
+    bool rv;
+    __device__ __forceinline__ Epi(const Params &, uint8_t *extra, int tid) {
+      xs = reinterpret_cast<float *>(extra);
+      const int warp = tid >> 5;
+      lane = tid & 31; q = warp & 3; cq = warp >> 2;
+      cur_sb = -1; row = 0; trow = -1; rv = false;
+      m_run = REC_NEG_INF; s_run = 0.f; tgt = REC_NEG_INF;
+    }
+    __device__ __forceinline__ void flush(const Params &p) {
+      float *x = xs + ((q * 32 + lane) * CS + cq) * 5;
+      x[0] = m_run; x[1] = s_run; x[2] = tgt;
+      epi_bar<NT>();
+      if (cq == 0 && rv) {
+        const float *y = xs + ((q * 32 + lane) * CS) * 5;
+        float m = REC_NEG_INF, tg = REC_NEG_INF;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) { m = fmaxf(m, y[c * 5]); tg = fmaxf(tg, y[c * 5 + 2]); }
+        float ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) if (y[c * 5 + 1] > 0.f) ssum += y[c * 5 + 1] * __expf(y[c * 5] - m);
+        const int slot = (int)blockIdx.x - (cur_sb * p.n_tiles) / p.per;
+        float *o = p.part + ((int64_t)slot * p.B + row) * p.part_stride;
+        o[0] = m; o[1] = ssum; o[2] = tg;
+      }
+      epi_bar<NT>();  // xs is rewritten by the next flush
+    }
+    __device__ __forceinline__ void tile(const Params &p, int u, int, uint32_t tacc) {
+      const int sb = u / p.n_tiles, t = u - sb * p.n_tiles;
+      if (sb != cur_sb) {  // uniform across the CTA: every epilogue thread walks the same unit sequence
+        if (cur_sb >= 0) flush(p);
+        cur_sb = sb;
+        row = sb * 128 + q * 32 + lane;
+        rv = row < p.B;
+        trow = (p.target && rv) ? (int)(p.target[row] - p.vocab_lo) : -1;
+        m_run = REC_NEG_INF; s_run = 0.f; tgt = REC_NEG_INF;
+      }
+      const int c_lo = t * 128 + cq * 32;
+      float l[32];
+      tc::tmem_ld32(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32), l);
+      if (c_lo + 32 <= p.Vloc) {
+        const float4 *bg = reinterpret_cast<const float4 *>(p.bias + c_lo);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(bg + (j >> 2));
+          l[j] += b4.x; l[j + 1] += b4.y; l[j + 2] += b4.z; l[j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) l[j] = (c_lo + j < p.Vloc) ? l[j] + __ldg(p.bias + c_lo + j) : REC_NEG_INF;
+      }
+      float tmax = fmaxf(l[0], l[1]);
+#pragma unroll
+      for (int j = 2; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
+      const float nm = fmaxf(m_run, tmax), nml = -fmaxf(nm, -1e30f) * LOG2E;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ps[j & 3] += tc::ex2_ftz(fmaf(l[j], LOG2E, nml));
+      s_run = fmaf(s_run, tc::ex2_ftz((m_run - nm) * LOG2E), (ps[0] + ps[1]) + (ps[2] + ps[3]));
+      m_run = nm;
+      if (trow >= c_lo && trow < c_lo + 32) {
+        const int tj = trow - c_lo;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j == tj) tgt = l[j];
+      }
+      if (rv) p.cmax[(int64_t)row * p.cmax_ld + (t * CS + cq)] = tmax;
+    }
+    __device__ __forceinline__ void finish(const Params &p) {
+      if (cur_sb >= 0) flush(p);
+    }
+  };
+};
+
+// ---- exact top-k from chunk maxima ------------------------------------------------------------------------------------
+constexpr int KC = 24;      // chunks kept per row: k <= 20 plus a margin for the ~1e-5 relative error of the bf16x3 maxima
+constexpr int CCAP = 512;   // candidate list of the threshold pass (expected ~50 entries)
+
+// warp = row, two kernels (selection: few registers, many warps; scoring: register-heavy, 16 loads in flight per lane).
+//  (1) lane-strided pass over the row's chunk maxima: lane maximum; t0 = KC-th largest of the 32 lane maxima -- at least
+//      KC chunks reach t0, so the KC best chunks all do;
+//  (2) second pass (L2 hits): chunks >= t0 are appended to a shared-memory list (ballot + prefix); KC rounds of a warp
+//      argmax pick the KC best by (maximum desc, chunk asc); a list overflow (a row of massive ties) falls back to KC
+//      full passes;
+//  (3) the 32 columns of every kept chunk are scored EXACTLY in fp32 (lane = column: h . W[v] in ascending k with one
+//      accumulator, + bias -- nn.Linear up to summation order), and the top-k of the KC x 32 exact scores by
+//      (score desc, id asc) is torch.topk on fp32 logits (eval_protocol.py:75).
+// Writes row_ids / row_topv like head_merge_kernel, and the candidate slots of `summary` when this shard's result
+// travels on to a cross-shard merge.
+// Selection kernel (few registers: 64 warps per SM hide the latency of streaming the maxima).
+__global__ void __launch_bounds__(256) chunk_select_kernel(const float *__restrict__ cmax, int64_t ld, int n_chunks, int B,
+                                                          int *__restrict__ chosen) {
+  __shared__ float lv_all[8 * CCAP];
+  __shared__ int lc_all[8 * CCAP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + wid;
+  if (row >= B) return;
+  float *lv = lv_all + wid * CCAP;
+  int *lc = lc_all + wid * CCAP;
+  const float *cm = cmax + (int64_t)row * ld;
+  // (1) lane maxima -> t0  (8 independent 128-byte loads per warp and iteration)
+  float lm = REC_NEG_INF;
+  for (int c = lane; c < n_chunks; c += 32 * 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c + 32 * j < n_chunks ? __ldg(cm + c + 32 * j) : REC_NEG_INF;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lm = fmaxf(lm, v[j]);
+  }
+  int rank = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float o = __shfl_sync(0xffffffffu, lm, j);
+    rank += (o > lm || (o == lm && j < lane)) ? 1 : 0;
+  }
+  const int src = __ffs(__ballot_sync(0xffffffffu, rank == KC - 1)) - 1;
+  const float t0 = __shfl_sync(0xffffffffu, lm, src);
+  // (2) candidates >= t0
+  int n_list = 0;
+  bool overflow = false;
+  for (int c0 = 0; c0 < n_chunks && !overflow; c0 += 32 * 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c0 + 32 * j + lane < n_chunks ? __ldg(cm + c0 + 32 * j + lane) : REC_NEG_INF;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + 32 * j + lane;
+      const bool take = c < n_chunks && v[j] >= t0;
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m) {
+        const int pos = n_list + __popc(m & ((1u << lane) - 1u));
+        if (take && pos < CCAP) { lv[pos] = v[j]; lc[pos] = c; }
+        n_list += __popc(m);
+        if (n_list > CCAP) overflow = true;
+      }
+    }
+  }
+  __syncwarp();
+  float lastv = 3.402823466e+38f;
+  int lastc = -1;
+  for (int r = 0; r < KC; ++r) {
+    float bv = REC_NEG_INF;
+    int bc = 0x7fffffff;
+    if (!overflow) {
+      for (int e = lane; e < n_list; e += 32) {
+        const float v = lv[e];
+        const int c = lc[e];
+        if (better(lastv, lastc, v, c) && better(v, c, bv, bc)) { bv = v; bc = c; }
+      }
+    } else {
+      for (int c = lane; c < n_chunks; c += 32) {
+        const float v = __ldg(cm + c);
+        if (better(lastv, lastc, v, c) && better(v, c, bv, bc)) { bv = v; bc = c; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (better(ov, oc, bv, bc)) { bv = ov; bc = oc; }
+    }
+    if (lane == 0) chosen[(int64_t)row * KC + r] = bc;
+    lastv = bv; lastc = bc;
+  }
+}
+
+template <int D4>  // D / 4 when the state row fits in registers (D = 64), else 0 (row in shared memory)
+__global__ void __launch_bounds__(256) chunk_score_kernel(const int *__restrict__ chosen,
+                                                         const float *__restrict__ W, const float *__restrict__ bias,
+                                                         const float *__restrict__ h, int B, int D, int Vloc, int vocab_lo,
+                                                         int topk, int32_t *__restrict__ row_ids, float *__restrict__ row_topv,
+                                                         float *__restrict__ summary, int part_stride) {
+  extern __shared__ float smem_f[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + wid;
+  if (row >= B) return;
+  float *hs = smem_f + wid * D;               // state row (D4 == 0)
+  const int mine = lane < KC ? chosen[(int64_t)row * KC + lane] : 0x7fffffff;  // lane r holds the r-th best chunk
+  // (3) exact scores of the 32 columns of every kept chunk (lane = column)
+  float4 hr[D4 > 0 ? D4 : 1];
+  if (D4 > 0) {
+#pragma unroll
+    for (int k4 = 0; k4 < D4; ++k4) hr[k4] = __ldg(reinterpret_cast<const float4 *>(h + (int64_t)row * D) + k4);
+  } else {
+    for (int k = lane; k < D; k += 32) hs[k] = h[(int64_t)row * D + k];
+    __syncwarp();
+  }
+  float sc[KC];
+  int ids[KC];
+#pragma unroll
+  for (int r = 0; r < KC; ++r) {
+    const int c = __shfl_sync(0xffffffffu, mine, r);
+    const int v = c == 0x7fffffff ? Vloc : c * 32 + lane;
+    float acc = REC_NEG_INF;
+    ids[r] = 0x7fffffff;
+    if (v < Vloc) {
+      const float4 *wr = reinterpret_cast<const float4 *>(W + (int64_t)v * D);
+      acc = 0.f;
+      if (D4 > 0) {
+        float4 w4[D4 > 0 ? D4 : 1];
+#pragma unroll
+        for (int k4 = 0; k4 < D4; ++k4) w4[k4] = __ldg(wr + k4);
+#pragma unroll
+        for (int k4 = 0; k4 < D4; ++k4) {
+          acc = fmaf(hr[k4].x, w4[k4].x, acc); acc = fmaf(hr[k4].y, w4[k4].y, acc);
+          acc = fmaf(hr[k4].z, w4[k4].z, acc); acc = fmaf(hr[k4].w, w4[k4].w, acc);
+        }
+      } else {
+        for (int k4 = 0; k4 < (D >> 2); ++k4) {
+          const float4 w4 = __ldg(wr + k4);
+          const float4 h4 = *reinterpret_cast<const float4 *>(hs + 4 * k4);
+          acc = fmaf(h4.x, w4.x, acc); acc = fmaf(h4.y, w4.y, acc); acc = fmaf(h4.z, w4.z, acc); acc = fmaf(h4.w, w4.w, acc);
+        }
+      }
+      acc += __ldg(bias + v);
+      ids[r] = vocab_lo + v;
+    }
+    sc[r] = acc;
+  }
+  float pv = 3.402823466e+38f;
+  int pi = -1;
+  float *sm = summary ? summary + (int64_t)row * part_stride : nullptr;
+  for (int k = 0; k < topk; ++k) {
+    float bv = REC_NEG_INF;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < KC; ++r)
+      if (ids[r] != 0x7fffffff && better(pv, pi, sc[r], ids[r]) && better(sc[r], ids[r], bv, bi)) { bv = sc[r]; bi = ids[r]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv;
+      if (sm) { sm[TOPK_OFF + k] = bv; sm[TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(bi); }
+    }
+    pv = bv; pi = bi;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // dh[128 sessions x (64 NCB)] = sum over this CTA's vocabulary range of dl . W   (A, B: MN-major views)
@@ -624,7 +913,7 @@ static int tck_ensure(rec_engine *e, int what) {
 }
 
 void tck_free(rec_engine *e) {
-  void *ptrs[] = {e->k_wimg[0], e->k_wimg[1], e->k_himg[0], e->k_himg[1], e->k_hT, e->k_dlT, e->k_db, e->k_bias};
+  void *ptrs[] = {e->k_wimg[0], e->k_wimg[1], e->k_himg[0], e->k_himg[1], e->k_hT, e->k_dlT, e->k_db, e->k_bias, e->k_cmax, e->k_chosen};
   for (void *p : ptrs) if (p) cudaFree(p);
 }
 
@@ -673,6 +962,64 @@ int tck_prepack_heads(rec_engine *e, int net_id, int n_arg, const float *w) {
     if ((rc = tck_pack_head_image(e, net_id, -1, n_arg, w))) return rc;
     e->k_fresh[1] = true;
   }
+  return REC_OK;
+}
+
+// Evaluation-shaped batches over a large catalogue: statistics + chunk maxima on the tensor cores, then the exact top-k
+// from the best chunks (see HeadTopk<.., CM>).  Writes the per-(split, row) statistics records (merged by the caller with
+// launch_head_merge(topk = 0)) and row_ids / row_topv (+ the candidate slots of `summary`).
+bool tck_chunk_topk_supported(const rec_engine *e, const HeadStatsArgs &a) {
+  static const int off = getenv("REC_NO_CHUNK_TOPK") ? 1 : 0;
+  return !off && tck_topk_supported(e, a) && a.B >= 1024 && e->Vloc >= 32768;
+}
+
+int launch_head_topk_chunks(rec_engine *e, const HeadStatsArgs &a, int *n_split_out, float *summary) {
+  int rc = tck_ensure(e, 1);
+  if (rc) return rc;
+  const rec_net_params &np = e->nets[a.net_id].p;
+  const int KB = e->D / 64, n_tiles = cdiv(e->Vloc, 128), n_sb = cdiv(a.B, 128), n_chunks = n_tiles * 4;
+  const int64_t mb = e->cfg.max_batch;
+  const int64_t cld = (n_chunks + 31) / 32 * 32;  // row pitch of the chunk maxima: whole 128-byte lines
+  if ((rc = tck_alloc(e, (void **)&e->k_cmax, sizeof(float) * (size_t)cld * mb))) return rc;
+  if ((rc = tck_pack_head_image(e, a.net_id, a.stats_head, 0, a.w))) return rc;
+  tck::PackSrc hs = {};
+  hs.n = 1; hs.p[0] = a.h; hs.w[0] = 1.f;
+  if ((rc = tck_pack(e, hs, a.B, e->D, e->k_himg[0]))) return rc;
+  // flattened (session block, tile) unit space: one persistent CTA per SM, equal shares
+  const int total = n_sb * n_tiles;
+  int n_cta = e->sm_count < total ? e->sm_count : total;
+  const int per = cdiv(total, n_cta);
+  n_cta = cdiv(total, per);
+  int n_split = cdiv(n_tiles, per) + 1;  // records per row: the CTAs that can touch one session block
+  if (n_split > n_cta) n_split = n_cta;
+  tck::FwdParams p = {};
+  p.himg = e->k_himg[0]; p.wimg = e->k_wimg[0]; p.KB = KB; p.B = a.B; p.Vloc = e->Vloc; p.vocab_lo = e->cfg.vocab_lo; p.n_tiles = n_tiles;
+  p.bias = np.head_b[a.stats_head]; p.target = a.target; p.part = e->part; p.part_stride = e->part_stride;
+  p.topk = a.topk; p.cmax = e->k_cmax; p.cmax_ld = cld; p.n_sb = n_sb; p.per = per;
+  if ((int64_t)n_split * a.B > ((int64_t)e->sm_count * 4 * 128 + 4 * (int64_t)e->cfg.max_batch))
+    REC_FAIL(e, REC_EINVAL, "chunk-maxima pass: %d records per row exceed the statistics workspace", n_split);
+  tck::fill_neutral_records_kernel<<<(int)cdiv64((int64_t)n_split * a.B, 256), 256, 0, e->stream>>>(e->part, (int64_t)n_split * a.B, e->part_stride);
+  REC_LAUNCH_CHECK(e);
+  if (e->timing) cudaEventRecord(e->ev[2], e->stream);  // slot 1 (evaluation head kernel): this ONE launch
+  if ((rc = tck::launch_tck<tck::HeadCmaxFlat>(e, dim3(n_cta), p))) return rc;
+  if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+  if ((rc = tck_alloc(e, (void **)&e->k_chosen, sizeof(int) * (size_t)mb * tck::KC))) return rc;
+  tck::chunk_select_kernel<<<cdiv(a.B, 8), 256, 0, e->stream>>>(e->k_cmax, cld, n_chunks, a.B, e->k_chosen);
+  REC_LAUNCH_CHECK(e);
+  const size_t smem = 8 * (size_t)e->D * sizeof(float);
+  if (e->D == 64)
+    tck::chunk_score_kernel<16><<<cdiv(a.B, 8), 256, smem, e->stream>>>(e->k_chosen, np.head_w[a.stats_head], np.head_b[a.stats_head], a.h, a.B,
+                                                                       e->D, e->Vloc, e->cfg.vocab_lo, a.topk, e->row_ids, e->row_topv,
+                                                                       summary, e->part_stride);
+  else
+    tck::chunk_score_kernel<0><<<cdiv(a.B, 8), 256, smem, e->stream>>>(e->k_chosen, np.head_w[a.stats_head], np.head_b[a.stats_head], a.h, a.B,
+                                                                      e->D, e->Vloc, e->cfg.vocab_lo, a.topk, e->row_ids, e->row_topv,
+                                                                      summary, e->part_stride);
+  REC_LAUNCH_CHECK(e);
+  *n_split_out = n_split;
+  e->st_approx = false;  // the ids / scores in row_ids / row_topv are exact
+  e->st_kpub = 0;
+  e->st_apub = 0;
   return REC_OK;
 }
 

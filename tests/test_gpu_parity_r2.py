@@ -144,7 +144,7 @@ def test_smorl_step_at_1m_items_against_live_oracle(pkg):
 
 
 # ------------------------------------------------------------------------------------ (c)/(f) unscaled top-k
-@pytest.mark.parametrize("V,B", [(70852, 300), (1_000_000, 64)])
+@pytest.mark.parametrize("V,B", [(70852, 300), (1_000_000, 64), (70852, 1100), (250_000, 1040)])  # B >= 1024: chunk-maxima path
 def test_evaluate_default_init_unscaled_against_live_oracle(pkg, V, B):
     """top-20 ids at default init (no weight scaling): neighbouring logits are ~1e-6 apart, i.e. below the ~3e-6
     absolute error of the bf16x3 tensor-core scores -- the fp32 candidate re-score decides the order.  Everything
@@ -158,9 +158,16 @@ def test_evaluate_default_init_unscaled_against_live_oracle(pkg, V, B):
     rows = _syn().make_replay_rows_fast(B, V, 10, seed=0)
     s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
     with torch.no_grad():
-        margin = topk_margin(double_copy(onet)(s, ln), 20)
+        l64 = double_copy(onet)(s, ln)
         logits = onet(s, ln)
-    assert margin > MARGIN_MIN, margin
+    # rows whose 21 best float64 logits are separated by more than a few fp32 ulp: only there is the order defined for
+    # EVERY correct fp32 implementation (helpers.topk_margin); with > 1000 rows a handful of near-ties is expected
+    top = torch.topk(l64, 21, dim=1).values
+    ok_rows = (top[:, :-1] - top[:, 1:]).min(1).values > MARGIN_MIN
+    margin = float((top[:, :-1] - top[:, 1:]).min(1).values[ok_rows].min())
+    assert int(ok_rows.sum()) >= B - max(2, B // 50), int(ok_rows.sum())
+    if B <= 512:
+        assert bool(ok_rows.all()), "seed no longer well-posed"
     want_ids = oracle.stable_topk(logits, 20)
     loader = [(s, a, ln)]
     unpop = _syn().unpopular_set_from_actions(rows["action"])
@@ -182,10 +189,13 @@ def test_evaluate_default_init_unscaled_against_live_oracle(pkg, V, B):
     sc = torch.empty(B, 20, dtype=torch.float32, device=DEV)
     ds, dl = net._dev_inputs(s, ln)
     eng.eval_batch(0, eng._batch(B, ds, a.to(DEV), dl), o, acc.struct, topk_ids=ids, topk_scores=sc)
-    n_rows_off = int((ids.cpu().long() != want_ids).any(1).sum())
-    report(f"eval default init V={V}", dict(margin=margin, rows_with_any_id_off=n_rows_off, rows=B))
-    assert torch.equal(ids.cpu().long(), want_ids)
-    assert_close(sc.cpu(), logits.gather(1, want_ids), rtol=2e-6, atol=2e-7, what="re-scored top-k scores (fp32)")
+    n_rows_off = int((ids.cpu().long() != want_ids)[ok_rows].any(1).sum())
+    report(f"eval default init V={V} B={B}", dict(margin=margin, rows_with_any_id_off=n_rows_off, rows=B,
+                                                  rows_compared=int(ok_rows.sum())))
+    assert torch.equal(ids.cpu().long()[ok_rows], want_ids[ok_rows])
+    assert_close(sc.cpu()[ok_rows], logits.gather(1, want_ids)[ok_rows], rtol=2e-6, atol=2e-7, what="re-scored top-k scores (fp32)")
+    if not bool(ok_rows.all()):
+        return  # the aggregate metrics below include the rows with undefined order
     assert_close(got[0], want[0], rtol=1e-4)
     assert np.array_equal(got[1], want[1]) and np.allclose(got[2], want[2], rtol=1e-12) and np.array_equal(got[6], want[6])
     assert got[3] == want[3]
