@@ -8,6 +8,7 @@ Public surface (mirrors the reference `recommenders` package for the hot path):
     recommenders.models.BidirGRU4Rec.model   BidirGRU4Rec, BidirGRU4Rec_trainer
     recommenders.models.SQN.sqn_gru          SQN_Network, SQN_trainer
     recommenders.models.SMORL.smorl_gru      SMORL_GRU_Net, SMORL_trainer
+    recommenders.models.SARM.sarm            MultiObjectiveQNetwork, SARM_trainer
     recommenders.evaluate.eval_protocol      evaluate, update_train_metrics, get_preds
     recommenders.data_utils.replay_buffer    DeviceReplayBuffer, DeviceEvaluationDataset (device-resident sampling)
     recommenders.ikea.training.native_loop   train_native (the train_SQN / train_SMORL loop without per-batch host trips)
@@ -22,10 +23,11 @@ from .recommenders.models.GRU4Rec.model import GRU4Rec, GRU4Rec_trainer  # noqa:
 from .recommenders.models.BidirGRU4Rec.model import BidirGRU4Rec, BidirGRU4Rec_trainer  # noqa: E402,F401
 from .recommenders.models.SQN.sqn_gru import SQN_Network, SQN_trainer  # noqa: E402,F401
 from .recommenders.models.SMORL.smorl_gru import SMORL_GRU_Net, SMORL_trainer  # noqa: E402,F401
+from .recommenders.models.SARM.sarm import MultiObjectiveQNetwork, SARM_trainer  # noqa: E402,F401
 from .recommenders.evaluate.eval_protocol import evaluate, update_train_metrics, get_preds  # noqa: E402,F401
 from .recommenders.data_utils.replay_buffer import DeviceReplayBuffer, DeviceEvaluationDataset  # noqa: E402,F401
 from .recommenders.ikea.training.native_loop import train_native  # noqa: E402,F401
 
 __all__ = ["Engine", "GRU4Rec", "GRU4Rec_trainer", "BidirGRU4Rec", "BidirGRU4Rec_trainer", "SQN_Network",
-           "SQN_trainer", "SMORL_GRU_Net", "SMORL_trainer", "evaluate", "update_train_metrics", "get_preds",
+           "SQN_trainer", "SMORL_GRU_Net", "SMORL_trainer", "MultiObjectiveQNetwork", "SARM_trainer", "evaluate", "update_train_metrics", "get_preds",
            "DeviceReplayBuffer", "DeviceEvaluationDataset", "train_native"]

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librecsys_b200.so")
 
-REC_MAX_HEADS = 4
+REC_MAX_HEADS = 5
 REC_MAX_NETS = 2
 REC_MAX_TOPK = 32
 REC_MAX_KLIST = 8
@@ -77,6 +77,7 @@ SYMBOLS = {
     "rec_head_logits": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int64]),
     "rec_train_step_supervised": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), _P]),
     "rec_train_step_q": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
+    "rec_train_step_sarm": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), _P]),
     "rec_train_step_supervised_host": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), _P]),
     "rec_train_step_q_host": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
     "rec_record_floats": (C.c_int, [_P]),

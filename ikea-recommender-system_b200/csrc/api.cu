@@ -182,8 +182,13 @@ extern "C" int rec_create(const rec_config *cfg, void *stream, rec_engine **out)
   // kernels must get their SM slots before the streaming kernels fill the machine
   if (cudaStreamCreateWithPriority(&e->cap_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) e->use_graph = false;
   ALLOC(e, e->hpack, uint8_t, (size_t)((mb + 255) / 256) * 4 * 16384);
-  ALLOC(e, e->q_grad_rows, float, mb * 3 * D);
-  ALLOC(e, e->q_bgrad, float, mb * 3);
+  ALLOC(e, e->q_grad_rows, float, mb * 4 * D);  // up to 4 row-sparse heads (SARM: heads 1..4)
+  ALLOC(e, e->q_bgrad, float, mb * 4);
+  if (c.n_heads == 5) {
+    ALLOC(e, e->sarm_qmax, float, 5 * mb);
+    ALLOC(e, e->sarm_dq, float, mb * 5);
+    ALLOC(e, e->sarm_extra, float, mb);
+  }
   ALLOC(e, e->q_slot, int32_t, e->Vloc);
   ALLOC(e, e->qpack, float, 2 * mb * 3);
   ALLOC(e, extra(e).rowm, double, mb * (3 * REC_MAX_KLIST + 3));
@@ -214,7 +219,7 @@ extern "C" void rec_destroy(rec_engine *e) {
   void *ptrs[] = {e->h_state[0], e->h_state[1], e->h_state[2], e->gates_save, e->hprev_save, e->dgi, e->dgh, e->dx,
                   e->dh, e->dh_part, e->wgrad_part, e->emb_keys, e->emb_slot, e->emb_grad_rows, e->part, e->row_stats,
                   e->row_ids, e->row_topv, e->q_sa, e->q_boot, e->dq, e->rewards, e->loss_buf, e->astar, e->drop_mask,
-                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_csort, e->emb_ccount, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block};
+                  extra(e).q_loss_rows, extra(e).rowm, e->summary, e->qpack, e->q_grad_rows, e->q_bgrad, e->q_slot, e->hpack, e->emb_leader, e->emb_sorted, e->emb_seg, e->emb_csort, e->emb_ccount, e->emb_carry, e->emb_tmeta, e->d_sc, e->d_step, (void *)e->own_block, e->sarm_qmax, e->sarm_dq, e->sarm_extra};
   for (void *p : ptrs) if (p) cudaFree(p);
   tck_free(e);
   gtc_free(e);
@@ -748,6 +753,136 @@ extern "C" int rec_train_step_q_host(rec_engine *e, const rec_batch *host_b, con
     return q_step_body(e, bb, hp, main_net, out, step_size, bc2_sqrt);
   }, true, 2);
   return finish_host_step(e, rc, losses_host, 2);
+}
+
+// ---- SARM (models/SARM/sarm.py:117-149): one net, five Q heads, head 0 doubles as the supervised head ----------------
+__global__ void copy_stat_kernel(const float *__restrict__ row_stats, int col, int B, float *__restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = row_stats[(int64_t)b * 8 + col];
+}
+
+// One warp per session: Q_i(s, a) for the five heads (fp32 row dots), TD targets y_i = r + gamma * max_a Q_i(s', a)
+// (the reference masks nothing with is_end here: sarm.py:133-135), per-row loss sum_i (y_i - Q_i)^2 / 5, the gradients
+// dQ_i = (2/5) (Q_i - y_i) / B, and the dh contribution of heads 1..4 (head 0's travels through its dense backward:
+// `extra`).  Runs before any Adam kernel touches the head weights.
+struct SarmPtrs { const float *w[5], *b[5]; };
+__global__ void __launch_bounds__(256) sarm_rows_entry(SarmPtrs P, const float *__restrict__ h, const int64_t *__restrict__ a,
+                                                       const float *__restrict__ r, const float *__restrict__ qmax, int qmax_ld,
+                                                       int B, int D, int Vloc, int vocab_lo, float gamma, float *__restrict__ dq,
+                                                       float *__restrict__ extra, float *__restrict__ q_loss_rows,
+                                                       float *__restrict__ dh_slice);
+
+static int sarm_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *losses_out, float step_size,
+                          float bc2_sqrt) {
+  int rc;
+  const int B = b->B;
+  e->hpack_ready = false;
+  {  // token ordering of the embedding backward: needs only the batch
+    SideScope side(e, 1);
+    if ((rc = launch_embedding_update(e, 0, b->s, b->true_len, B, step_size, bc2_sqrt, hp, 1))) return rc;
+  }
+  {  // two passes of the same net: s (saved for the backward) and s' (values only)
+    const int nets[2] = {0, 0};
+    const int64_t *ss[2] = {b->s, b->s_next};
+    const int64_t *ll[2] = {b->true_len, b->true_next_len};
+    float *hh[2] = {e->h_state[0], e->h_state[1]};
+    const bool sv[2] = {true, false};
+    if ((rc = launch_gru_forward_multi(e, 2, nets, ss, ll, hh, sv, B))) return rc;
+  }
+  int n_split = 0;
+  // max_a Q_i(s', a) for the five heads: greedy-action pass per head, merge with the fp32 re-score -> exact maxima
+  for (int i = 0; i < 5; ++i) {
+    HeadStatsArgs g = {};
+    g.net_id = 0; g.h = e->h_state[1]; g.B = B; g.n_arg = 1; g.w[0] = 1.f; g.arg_shift = i - 1;
+    if ((rc = head_stats_dispatch(e, g, &n_split))) return rc;
+    if ((rc = launch_head_merge(e, e->part, n_split, B, 0, false, true, nullptr, &g))) return rc;
+    copy_stat_kernel<<<cdiv(B, 256), 256, 0, e->stream>>>(e->row_stats, 2, B, e->sarm_qmax + (int64_t)i * e->cfg.max_batch);
+    REC_LAUNCH_CHECK(e);
+  }
+  // cross-entropy statistics of head 0 on s
+  HeadStatsArgs a = {};
+  a.net_id = 0; a.h = e->h_state[0]; a.B = B; a.do_stats = 1; a.stats_head = 0; a.target = b->a;
+  if ((rc = head_stats_dispatch(e, a, &n_split))) return rc;
+  if ((rc = launch_head_merge(e, e->part, n_split, B, 0, true, false, nullptr, &a))) return rc;
+  // per-row Q terms
+  {
+    const rec_net_params &p = e->nets[0].p;
+    SarmPtrs P;
+    for (int i = 0; i < 5; ++i) { P.w[i] = p.head_w[i]; P.b[i] = p.head_b[i]; }
+    float *q_slice = e->dh_part + (int64_t)head_bwd_dense_slices(e, B) * B * e->D;
+    sarm_rows_entry<<<cdiv(B, 8), 256, 0, e->stream>>>(P, e->h_state[0], b->a, b->r, e->sarm_qmax, e->cfg.max_batch, B, e->D, e->Vloc,
+                                                       e->cfg.vocab_lo, hp->gamma, e->sarm_dq, e->sarm_extra, extra(e).q_loss_rows, q_slice);
+    REC_LAUNCH_CHECK(e);
+  }
+  if ((rc = launch_loss_reduce(e, B, extra(e).q_loss_rows, e->loss_buf))) return rc;
+  REC_CUDA(e, cudaMemcpyAsync(losses_out, e->loss_buf, 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  // head 0: dense backward + Adam with its Q gradient added at the target column; heads 1..4: row-sparse sweep
+  e->bwd_extra = e->sarm_extra;
+  rc = launch_sup_head_bwd(e, 0, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1.f / (float)B);
+  e->bwd_extra = nullptr;
+  if (rc) return rc;
+  if ((rc = launch_q_heads_adam_ex(e, 0, e->h_state[0], b, B, step_size, bc2_sqrt, hp, 1, 4, e->sarm_dq + 1, 5))) return rc;
+  if ((rc = launch_dh_reduce(e, B))) return rc;
+  return trunk_backward(e, 0, b->s, b->true_len, B, e->dh, step_size, bc2_sqrt, hp, true);
+}
+
+__global__ void __launch_bounds__(256) sarm_rows_entry(SarmPtrs P, const float *__restrict__ h, const int64_t *__restrict__ a,
+                                                       const float *__restrict__ r, const float *__restrict__ qmax, int qmax_ld,
+                                                       int B, int D, int Vloc, int vocab_lo, float gamma, float *__restrict__ dq,
+                                                       float *__restrict__ extra, float *__restrict__ q_loss_rows,
+                                                       float *__restrict__ dh_slice) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int64_t loc = a[b] - vocab_lo;
+  const bool here = loc >= 0 && loc < Vloc;
+  const float *hr = h + (int64_t)b * D;
+  float g[5];
+  float loss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    float q = 0.f;
+    if (here) {
+      const float *wr = P.w[i] + loc * D;
+      float acc = 0.f;
+      for (int k = lane; k < D; k += 32) acc = fmaf(hr[k], __ldg(wr + k), acc);
+      q = warp_sum(acc) + __ldg(P.b[i] + loc);
+    }
+    const float y = r[b] + gamma * qmax[(int64_t)i * qmax_ld + b];
+    const float diff = y - q;
+    loss += diff * diff;
+    g[i] = here ? 0.2f * 2.f * (-diff) / (float)B : 0.f;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dq[b * 5 + i] = g[i];
+    extra[b] = g[0];
+    q_loss_rows[b] = 0.2f * loss;
+  }
+  for (int k = lane; k < D; k += 32) {
+    float acc = 0.f;
+    if (here) {
+#pragma unroll
+      for (int i = 1; i < 5; ++i) acc = fmaf(g[i], __ldg(P.w[i] + loc * D + k), acc);
+    }
+    dh_slice[(int64_t)b * D + k] = acc;
+  }
+}
+
+extern "C" int rec_train_step_sarm(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *losses_out) {
+  DevGuard dev_guard(e);
+  if (!e) return REC_EINVAL;
+  if (e->cfg.n_heads != 5 || e->cfg.n_nets != 1) REC_FAIL(e, REC_EINVAL, "rec_train_step_sarm needs a single-net engine with 5 heads");
+  int rc = check_net(e, 0, true);
+  if (rc) return rc;
+  if ((rc = check_batch(e, b, true))) return rc;
+  if (!hp || !losses_out) REC_FAIL(e, REC_EINVAL, "rec_train_step_sarm: null argument");
+  if (e->Vloc != e->cfg.action_dim) REC_FAIL(e, REC_EINVAL, "rec_train_step_sarm: vocabulary-sharded engines are not supported");
+  float step_size, bc2_sqrt;
+  adam_scalars(e, 0, hp, &step_size, &bc2_sqrt);
+  return run_step_graphed(e, 2, 0, b, hp, losses_out, [&](const rec_batch *bb) {
+    return sarm_step_body(e, bb, hp, losses_out, step_size, bc2_sqrt);
+  });
 }
 
 static int eval_kmax(const rec_eval_opts *o) {

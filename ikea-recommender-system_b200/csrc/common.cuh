@@ -117,6 +117,11 @@ struct rec_engine {
   int k_sup_net, k_sup_head;  // which (net, head) k_wimg[0] / k_himg[0] currently hold (-1: none)
   float *k_cmax;         // chunk maxima [B][V/32] of the evaluation top-k (HeadTopk<.., CM>)
   int *k_chosen;         // [B][KC] the chunks with the largest maxima per row
+  // SARM (5 Q heads, rec_train_step_sarm)
+  float *sarm_qmax;      // [5][maxB] max_a Q_i(s', a), exact (re-scored)
+  float *sarm_dq;        // [maxB][5] dL/dQ_i(s_b, a_b)
+  float *sarm_extra;     // [maxB] head 0's Q gradient, added to its dlogits at the target column
+  const float *bwd_extra;  // non-null while a supervised-head backward must add a per-row gradient at the target column
   bool k_fresh[2];       // k_wimg[i] was packed ahead of its consumer in this step (tck_prepack_heads)
   // tensor-core GRU trunk for E, H >= 128 (gru_tc.cu); allocated at first use
   uint8_t *g_wimg;       // [net][dir][W_ih | W_hh | W_hh regrouped] weight images
@@ -243,6 +248,10 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
 // wait_mark >= 0: the streaming sweep (not the gradient-row kernel) additionally waits for side_mark(e, wait_mark)
 int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                         float bc2_sqrt, const rec_train_hparams *hp, int wait_mark = -1);
+// generalised: heads first_head .. first_head + n - 1 with dq[b * dq_stride + j] (SARM: heads 1..4, stride 5)
+int launch_q_heads_adam_ex(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                           float bc2_sqrt, const rec_train_hparams *hp, int first_head, int n, const float *dq,
+                           int dq_stride, int wait_mark = -1);
 
 // Launches issued while a SideScope is alive go to side stream `idx`, ordered after everything issued so far on
 // the current stream -- or, with `mark` >= 0, after the point remembered by side_mark(e, mark).  Scopes nest
@@ -284,8 +293,9 @@ struct HeadStatsArgs {
   int stats_head;         // head whose logits feed stats / top-k
   const int64_t *target;  // [B] global action ids (target logit)
   int topk;               // >0: running top-k of `stats_head` (score desc, id asc)
-  int n_arg;              // >0: argmax over sum_j w[j] * Q_{1+j}, j < n_arg
+  int n_arg;              // >0: argmax over sum_j w[j] * Q_{1+arg_shift+j}, j < n_arg
   float w[3];
+  int arg_shift;          // 0: the Q heads follow the supervised head (SQN / SMORL); SARM scores head i with arg_shift = i - 1
 };
 int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out);
 bool tc_heads_supported(const rec_engine *e);

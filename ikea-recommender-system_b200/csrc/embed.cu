@@ -276,7 +276,8 @@ int launch_adam_stream(rec_engine *e, float *p, float *m, float *v, int64_t rows
 __global__ void __launch_bounds__(256) q_grad_rows_kernel(const int64_t *__restrict__ a, const float *__restrict__ dq,
                                                           const float *__restrict__ h, int B, int D, int n_q, int Vloc,
                                                           int vocab_lo, float *__restrict__ grad_rows,
-                                                          float *__restrict__ bgrad, int32_t *__restrict__ slot_of_row) {
+                                                          float *__restrict__ bgrad, int32_t *__restrict__ slot_of_row,
+                                                          int dq_stride) {
   // the action ids of the whole batch are staged in shared memory: the two scans below are latency chains
   // (load -> ballot -> next) and ran at L2 latency per iteration when they read global memory
   extern __shared__ int32_t sa[];
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(256) q_grad_rows_kernel(const int64_t *__restr
           hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (i0 + u < cnt) {
             const int q = plist[wid][i0 + u];
-            g[u] = dq[q * 3 + j];
+            g[u] = dq[q * dq_stride + j];
             if (col < D) hv[u] = *reinterpret_cast<const float4 *>(h + (int64_t)q * D + col);
           }
         }
@@ -356,30 +357,40 @@ __global__ void q_slot_reset_kernel(const int64_t *__restrict__ a, int B, int Vl
   if (loc >= 0 && loc < Vloc) slot_of_row[loc] = -1;
 }
 
-// Adam on every Q head (heads 1..n_q) of net `net_id`: streaming sweep with row-sparse gradients.
-int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
-                        float bc2_sqrt, const rec_train_hparams *hp, int wait_mark) {
-  const int n_q = e->cfg.n_heads - 1, D = e->D;
+// Adam on heads first_head .. first_head + n - 1 of net `net_id`: streaming sweep with row-sparse gradients
+// (dL/dQ_j(s_b, a_b) = dq[b * dq_stride + j]).  At most 3 tensors share one sweep launch.
+int launch_q_heads_adam_ex(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                           float bc2_sqrt, const rec_train_hparams *hp, int first_head, int n, const float *dq,
+                           int dq_stride, int wait_mark) {
+  const int D = e->D;
   const rec_net_params &p = e->nets[net_id].p;
   if ((size_t)B * sizeof(int32_t) > 48 * 1024) REC_FAIL(e, REC_EINVAL, "Q-head gradient rows: batch of %d sessions exceeds the 12288 supported", B);
-  q_grad_rows_kernel<<<cdiv(B * n_q, 8), 256, (size_t)B * sizeof(int32_t), e->stream>>>(b->a, e->dq, h, B, D, n_q, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
-                                                       e->q_bgrad, e->q_slot);
+  q_grad_rows_kernel<<<cdiv(B * n, 8), 256, (size_t)B * sizeof(int32_t), e->stream>>>(b->a, dq, h, B, D, n, e->Vloc, e->cfg.vocab_lo, e->q_grad_rows,
+                                                       e->q_bgrad, e->q_slot, dq_stride);
   REC_LAUNCH_CHECK(e);
   if (wait_mark >= 0) side_wait_mark(e, wait_mark);
-  {
+  for (int j0 = 0; j0 < n; j0 += 3) {
+    const int nj = n - j0 < 3 ? n - j0 : 3;
     AdamStreamSet ts = {};
-    for (int j = 0; j < n_q; ++j) {
-      ts.p[j] = (float4 *)p.head_w[1 + j]; ts.m[j] = (float4 *)p.head_w_m[1 + j]; ts.v[j] = (float4 *)p.head_w_v[1 + j];
-      ts.grad_rows[j] = (const float4 *)(e->q_grad_rows + (int64_t)j * D);
-      ts.bp[j] = p.head_b[1 + j]; ts.bm[j] = p.head_b_m[1 + j]; ts.bv[j] = p.head_b_v[1 + j];
-      ts.bgrad[j] = e->q_bgrad + j;
+    for (int j = 0; j < nj; ++j) {
+      const int hd = first_head + j0 + j;
+      ts.p[j] = (float4 *)p.head_w[hd]; ts.m[j] = (float4 *)p.head_w_m[hd]; ts.v[j] = (float4 *)p.head_w_v[hd];
+      ts.grad_rows[j] = (const float4 *)(e->q_grad_rows + (int64_t)(j0 + j) * D);
+      ts.bp[j] = p.head_b[hd]; ts.bm[j] = p.head_b_m[hd]; ts.bv[j] = p.head_b_v[hd];
+      ts.bgrad[j] = e->q_bgrad + j0 + j;
     }
-    int rc = launch_adam_stream_set(e, ts, n_q, true, e->Vloc, D, e->q_slot, n_q * D, n_q, hp, step_size, bc2_sqrt, 3);
+    int rc = launch_adam_stream_set(e, ts, nj, true, e->Vloc, D, e->q_slot, n * D, n, hp, step_size, bc2_sqrt, j0 == 0 ? 3 : -1);
     if (rc) return rc;
   }
   q_slot_reset_kernel<<<cdiv(B, 256), 256, 0, e->stream>>>(b->a, B, e->Vloc, e->cfg.vocab_lo, e->q_slot);
   REC_LAUNCH_CHECK(e);
   return REC_OK;
+}
+
+// Adam on every Q head (heads 1..n_q) of net `net_id` (SQN / SMORL).
+int launch_q_heads_adam(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
+                        float bc2_sqrt, const rec_train_hparams *hp, int wait_mark) {
+  return launch_q_heads_adam_ex(e, net_id, h, b, B, step_size, bc2_sqrt, hp, 1, e->cfg.n_heads - 1, e->dq, 3, wait_mark);
 }
 
 __global__ void emb_reset_kernel(const int32_t *__restrict__ keys, int P, int32_t *__restrict__ slot_of_row) {

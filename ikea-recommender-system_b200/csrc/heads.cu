@@ -989,7 +989,8 @@ __global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, co
                                                             int vocab_lo, int n_tiles, float inv_B,
                                                             float *__restrict__ dh_part, float b1, float b2,
                                                             float eps, float step_size, float bc2_sqrt,
-                                                            int head_begin, const float *__restrict__ sc) {
+                                                            int head_begin, const float *__restrict__ sc,
+                                                            const float *__restrict__ extra) {
   if (sc) { step_size = sc[0]; bc2_sqrt = 1.f / sc[1]; }
   extern __shared__ __align__(16) float dyn[];
   const int DP = D + 4;
@@ -1028,6 +1029,7 @@ __global__ void __launch_bounds__(256) head_bwd_adam_kernel(HeadTrainPtrs hp, co
             if (row < B && col < Vloc) {
               float l = acc[a][c] + __ldg(hp.b[0] + col);
               dl = (__expf(l - lse) - ((int64_t)col == trow ? 1.f : 0.f)) * inv_B;
+              if (extra && (int64_t)col == trow) dl += extra[row];
             }
             DL[m][n] = dl;
             DLT[n][m] = dl;
@@ -1189,7 +1191,12 @@ int launch_head_stats(rec_engine *e, const HeadStatsArgs &a, int *n_split_out) {
   int per = cdiv(n_tiles, n_split);
   n_split = cdiv(n_tiles, per);
   dim3 grid(n_split, nb);
-  head_stats_kernel<<<grid, 256, 0, e->stream>>>(head_ptrs(e, a.net_id), a.h, a.B, e->D, e->Vloc, e->cfg.vocab_lo, n_tiles,
+  HeadPtrs hps = head_ptrs(e, a.net_id);
+  if (a.n_arg > 0 && a.arg_shift != 0) {  // the kernel scores heads 1 + j: present the requested heads there
+    const HeadPtrs all = hps;
+    for (int j = 0; j < a.n_arg; ++j) { hps.w[1 + j] = all.w[1 + a.arg_shift + j]; hps.b[1 + j] = all.b[1 + a.arg_shift + j]; }
+  }
+  head_stats_kernel<<<grid, 256, 0, e->stream>>>(hps, a.h, a.B, e->D, e->Vloc, e->cfg.vocab_lo, n_tiles,
                                                 a.do_stats, a.stats_head, a.target, a.topk, a.n_arg, a.w[0], a.w[1],
                                                 a.w[2], e->part, e->part_stride);
   REC_LAUNCH_CHECK(e);
@@ -1208,7 +1215,7 @@ static RescoreSrc rescore_src(const rec_engine *e, const HeadStatsArgs *src, int
   R.h = src->h;
   R.n_arg = src->n_arg;
   if (src->n_arg > 0) {
-    for (int j = 0; j < src->n_arg && j < 3; ++j) { R.w[j] = p.head_w[1 + j]; R.b[j] = p.head_b[1 + j]; R.wq[j] = src->w[j]; }
+    for (int j = 0; j < src->n_arg && j < 3; ++j) { R.w[j] = p.head_w[1 + src->arg_shift + j]; R.b[j] = p.head_b[1 + src->arg_shift + j]; R.wq[j] = src->w[j]; }
   } else {
     R.w[0] = p.head_w[src->stats_head]; R.b[0] = p.head_b[src->stats_head];
   }
@@ -1325,7 +1332,7 @@ int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_bat
     dim3 grid(head_bwd_dense_slices(e, B), 1);
     head_bwd_adam_kernel<<<grid, 256, smem, e->stream>>>(t, h, b->a, e->row_stats, e->dq, B, e->D, e->Vloc, e->cfg.vocab_lo,
                                                         n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
-                                                        step_size, bc2_sqrt, 0, e->d_sc);
+                                                        step_size, bc2_sqrt, 0, e->d_sc, e->bwd_extra);
     REC_LAUNCH_CHECK(e);
   }
   if (e->timing) cudaEventRecord(e->ev[1], e->stream);

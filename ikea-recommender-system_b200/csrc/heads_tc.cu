@@ -661,7 +661,7 @@ static int launch_stats_tc_kernel(rec_engine *e, const HeadStatsArgs &a, dim3 gr
     attr_smem[e->dev] = smem;
   }
   head_stats_tc_kernel<NB, NT, ARG, RING><<<grid, NT + (RING ? (ARG ? 64 : 128) : 32), smem, e->stream>>>(
-      tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo, n_tiles, ARG ? 0 : a.do_stats, ARG ? 1 : a.stats_head,
+      tc_head_ptrs(e, a.net_id), a.h, a.B, e->Vloc, e->cfg.vocab_lo, n_tiles, ARG ? 0 : a.do_stats, ARG ? 1 + a.arg_shift : a.stats_head,
       ARG ? a.n_arg : 1, a.w[0], a.w[1], a.w[2], a.target, topk, e->part, e->part_stride, trace_sel() == (ARG ? 2 : 1) ? e->trace : nullptr,
       n_slots);
   REC_LAUNCH_CHECK(e);
@@ -773,7 +773,9 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
                                                                            float *__restrict__ dh_part, float b1, float b2,
                                                                            float eps, float step_size, float inv_bc2_sqrt,
                                                                            long long *__restrict__ trace,
-                                                                           const float *__restrict__ sc) {
+                                                                           const float *__restrict__ sc,
+                                                                           const float *__restrict__ extra) {
+  // extra (optional, [B]): a per-row gradient added to dlogits at the target column (SARM: head 0 is a Q head too)
   if (sc) { step_size = sc[0]; inv_bc2_sqrt = sc[1]; }
   extern __shared__ uint8_t raw[];
   uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);  // 1024-aligned, provably shared
@@ -1093,8 +1095,9 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
               l[j4 * 4 + 3] = tc::ex2_ftz(fmaf(l[j4 * 4 + 3] + b4.w, LOG2E_F, cst));
             }
             if (tj >= 0 && tj < 32) {
+              const float sub = inv_B - ((extra && rv) ? __ldg(extra + r0 + rl) : 0.f);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= inv_B;
+              for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= sub;
             }
             if (nvalid < 32) {
 #pragma unroll
@@ -1205,7 +1208,7 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   head_bwd_adam_tc2_kernel<<<n_cta, BWD2_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo,
                                                                     n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
                                                                     step_size, 1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr,
-                                                                    e->d_sc);
+                                                                    e->d_sc, e->bwd_extra);
   REC_LAUNCH_CHECK(e);
   *n_slices = n_cta;
   return REC_OK;

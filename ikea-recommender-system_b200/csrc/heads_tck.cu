@@ -45,6 +45,7 @@ struct FwdParams {
   float *cmax;                 // HeadTopk<.., CM>: chunk maxima [B][cmax_ld >= n_tiles * 4]
   int64_t cmax_ld;
   int n_sb, per;               // HeadCmaxFlat: session blocks, units per CTA of the flattened (session block, tile) space
+  const float *extra;          // DL: optional per-row gradient added at the target column (SARM)
 };
 
 enum { M_STATS = 0, M_ARG = 1, M_DL = 2 };
@@ -150,8 +151,9 @@ struct HeadFwd {
 #pragma unroll
           for (int j = 0; j < 32; ++j) l[j] = tc::ex2_ftz(fmaf(l[j], LOG2E, cst));
           if (tj >= 0 && tj < 32) {
+            const float sub = p.inv_B - ((p.extra && rv) ? __ldg(p.extra + row) : 0.f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= p.inv_B;
+            for (int j = 0; j < 32; ++j) if (j == tj) l[j] -= sub;
           }
           if (nvalid < 32) {
 #pragma unroll
@@ -929,15 +931,15 @@ static int tck_pack(rec_engine *e, const tck::PackSrc &s, int R, int C, uint8_t 
 
 // Weight image of one head (head >= 0 -> k_wimg[0]) or of the pre-combined greedy-action heads sum_j w_j Q_j
 // (head < 0 -> k_wimg[1], + combined bias).
-static int tck_pack_head_image(rec_engine *e, int net_id, int head, int n_arg, const float *w) {
+static int tck_pack_head_image(rec_engine *e, int net_id, int head, int n_arg, const float *w, int arg_shift = 0) {
   const rec_net_params &np = e->nets[net_id].p;
   tck::PackSrc ws = {};
   if (head < 0) {
     ws.n = n_arg;
-    for (int j = 0; j < n_arg; ++j) { ws.p[j] = np.head_w[1 + j]; ws.w[j] = n_arg > 1 ? w[j] : 1.f; }
+    for (int j = 0; j < n_arg; ++j) { ws.p[j] = np.head_w[1 + arg_shift + j]; ws.w[j] = n_arg > 1 ? w[j] : 1.f; }
     if (n_arg > 1) {
       tck::PackSrc bs = ws;
-      for (int j = 0; j < n_arg; ++j) bs.p[j] = np.head_b[1 + j];
+      for (int j = 0; j < n_arg; ++j) bs.p[j] = np.head_b[1 + arg_shift + j];
       tck::bias_combine_kernel<<<cdiv(e->Vloc, 256), 256, 0, e->stream>>>(bs, e->Vloc, e->k_bias);
       REC_LAUNCH_CHECK(e);
     }
@@ -1035,10 +1037,10 @@ int launch_head_stats_tck(rec_engine *e, const HeadStatsArgs &a, int *n_split_ou
   if (arg && a.n_arg > 3) REC_FAIL(e, REC_EINVAL, "greedy-action pass supports at most 3 Q heads (got %d)", a.n_arg);
   // weight image of the scored head(s) -- unless tck_prepack_heads() already produced it on a side stream
   uint8_t *wimg = e->k_wimg[arg ? 1 : 0];
-  const float *bias = arg ? (a.n_arg > 1 ? e->k_bias : np.head_b[1]) : np.head_b[a.stats_head];
-  const bool fresh = arg ? e->k_fresh[1] : (e->k_fresh[0] && e->k_sup_net == a.net_id && e->k_sup_head == a.stats_head);
+  const float *bias = arg ? (a.n_arg > 1 ? e->k_bias : np.head_b[1 + a.arg_shift]) : np.head_b[a.stats_head];
+  const bool fresh = arg ? (e->k_fresh[1] && a.arg_shift == 0) : (e->k_fresh[0] && e->k_sup_net == a.net_id && e->k_sup_head == a.stats_head);
   e->k_fresh[arg ? 1 : 0] = false;
-  if (!fresh && (rc = tck_pack_head_image(e, a.net_id, arg ? -1 : a.stats_head, a.n_arg, a.w))) return rc;
+  if (!fresh && (rc = tck_pack_head_image(e, a.net_id, arg ? -1 : a.stats_head, a.n_arg, a.w, a.arg_shift))) return rc;
   // state image
   tck::PackSrc hs = {};
   hs.n = 1; hs.p[0] = a.h; hs.w[0] = 1.f;
@@ -1111,7 +1113,7 @@ int launch_head_bwd_adam_tck(rec_engine *e, int net_id, const float *h, const re
     tck::FwdParams p = {};
     p.himg = e->k_himg[0]; p.wimg = wimg; p.KB = KB; p.B = B; p.Vloc = e->Vloc; p.vocab_lo = e->cfg.vocab_lo; p.n_tiles = n_tiles;
     p.bias = np.head_b[0]; p.target = b->a; p.row_stats = e->row_stats; p.inv_B = inv_B;
-    p.dlT = e->k_dlT; p.dl_cb = KBS; p.db_part = e->k_db;
+    p.dlT = e->k_dlT; p.dl_cb = KBS; p.db_part = e->k_db; p.extra = e->bwd_extra;
     if ((rc = tck::launch_tck<tck::HeadFwd<tck::M_DL>>(e, dim3(n_split, n_sb), p))) return rc;
   }
   // (2) dh partial slices (reads the weight IMAGE: independent of the Adam update below)

@@ -200,6 +200,12 @@ class Engine:
                 self.lib.rec_train_step_q(self.handle, C.byref(batch), C.byref(hp), main_net, _ptr(losses_out)),
                 "rec_train_step_q")
 
+    def train_step_sarm(self, batch: N.RecBatch, hp: N.RecTrainHparams, losses_out: torch.Tensor):
+        self.ensure_batch(batch.B)
+        N.check(self.lib, self.handle,
+                self.lib.rec_train_step_sarm(self.handle, C.byref(batch), C.byref(hp), _ptr(losses_out)),
+                "rec_train_step_sarm")
+
     # host entry points: the batch holds HOST pointers, losses come back as python floats (synchronous)
     def train_step_supervised_host(self, batch: N.RecBatch, hp: N.RecTrainHparams) -> float:
         self.ensure_batch(batch.B)

@@ -25,16 +25,18 @@ ADAM_EPS = 1e-8
 class NativeSessionNet(nn.Module):
     """embedding -> GRU -> heads, executed by the native engine.
 
-    family: "gru4rec" | "bidir" | "sqn" | "smorl" | "bidir_sqn"
+    family: "gru4rec" | "bidir" | "sqn" | "smorl" | "bidir_sqn" | "sarm"
     """
 
-    _TRUNK = {"gru4rec": "gru", "bidir": "gru", "sqn": "base_model", "smorl": "base_model", "bidir_sqn": "base_model"}
+    _TRUNK = {"gru4rec": "gru", "bidir": "gru", "sqn": "base_model", "smorl": "base_model", "bidir_sqn": "base_model",
+              "sarm": "base_model"}
     _HEADS = {
         "gru4rec": ["output"],
         "bidir": ["output"],
         "sqn": ["sup_head_output", "q_head_output"],
         "bidir_sqn": ["sup_head_output", "q_head_output"],
         "smorl": ["sup_head_output", "q_head_acc", "q_head_div", "q_head_nov"],
+        "sarm": ["q_heads.0", "q_heads.1", "q_heads.2", "q_heads.3", "q_heads.4"],  # nn.ModuleList (sarm.py:58-60)
     }
 
     def _build(self, family, hidden_dim, embedding_dim, item_num, state_size, action_dim, gru_layers,
@@ -48,7 +50,7 @@ class NativeSessionNet(nn.Module):
         self.use_packed_seq = use_packed_seq
         self.gru_layers = gru_layers
         self._bidirectional = family in ("bidir", "bidir_sqn")
-        rl = family in ("sqn", "smorl", "bidir_sqn")
+        rl = family in ("sqn", "smorl", "bidir_sqn", "sarm")
         pad = self.item_num if padding_idx is None else padding_idx
         if rl and use_packed_seq:
             train_pad_embed = True  # sqn_gru.py:46-47
@@ -65,8 +67,11 @@ class NativeSessionNet(nn.Module):
         if family == "bidir":
             self.dropout = nn.Dropout(p=dropout)
         d = hidden_dim * (2 if self._bidirectional else 1)
-        for name in self._HEADS[family]:
-            setattr(self, name, nn.Linear(in_features=d, out_features=action_dim))
+        if family == "sarm":
+            self.q_heads = nn.ModuleList([nn.Linear(in_features=d, out_features=action_dim) for _ in range(5)])
+        else:
+            for name in self._HEADS[family]:
+                setattr(self, name, nn.Linear(in_features=d, out_features=action_dim))
         for p in self.parameters():
             p.requires_grad_(False)  # gradients never exist as tensors: Adam is fused into the kernels
         self._engine: Optional[Engine] = None
@@ -97,6 +102,8 @@ class NativeSessionNet(nn.Module):
         return getattr(self, self._TRUNK[self._family])
 
     def _head_modules(self) -> List[nn.Linear]:
+        if self._family == "sarm":
+            return list(self.q_heads)
         return [getattr(self, n) for n in self._HEADS[self._family]]
 
     def _net_tensors(self) -> NetTensors:
@@ -178,6 +185,8 @@ class NativeSessionNet(nn.Module):
 
     def forward(self, s, lengths):
         outs = self._all_logits(s, lengths)
+        if self._family == "sarm":
+            return outs  # the reference returns the list of the five heads' outputs (sarm.py:74-75)
         if len(outs) == 1:
             return outs[0]
         if len(outs) == 2:

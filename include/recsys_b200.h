@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define REC_ABI_VERSION 1
-#define REC_MAX_HEADS 4   /* supervised + up to 3 Q heads (SMORL) */
+#define REC_MAX_HEADS 5   /* supervised + up to 3 Q heads (SMORL); SARM: 5 Q heads, head 0 doubles as the supervised head */
 #define REC_MAX_NETS 2    /* double-Q twins */
 #define REC_MAX_TOPK 32   /* largest k of any top-k consumer */
 #define REC_MAX_KLIST 8   /* entries in topk_hr_ndcg / topk_cov lists */
@@ -54,7 +54,7 @@ typedef struct rec_config {
   int32_t hidden_dim;     /* H (multiple of 4) */
   int32_t state_size;     /* L */
   int32_t bidirectional;  /* 0 | 1 ; D = H * (1 + bidirectional) */
-  int32_t n_heads;        /* 1 supervised only | 2 SQN (sup,q) | 4 SMORL (sup,q_acc,q_div,q_nov) */
+  int32_t n_heads;        /* 1 supervised only | 2 SQN (sup,q) | 4 SMORL (sup,q_acc,q_div,q_nov) | 5 SARM (q_heads[0..4]) */
   int32_t n_nets;         /* 1 | 2 (double-Q twins) */
   int32_t use_packed_seq; /* 1: final state after exactly len tokens (pack_padded_sequence) */
   int32_t frozen_pad_row; /* -1: every embedding row trainable; else row that never gets gradient */
@@ -172,6 +172,13 @@ int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train
  * losses_out[0] = sup_loss, losses_out[1] = q_loss (device). */
 int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
                      float *losses_out);
+/* SARM_trainer.train_step (models/SARM/sarm.py:117-149) on a single-net engine with n_heads = 5 (MultiObjectiveQNetwork,
+ * sarm.py:5-76): for every head i  q_loss_i = mean_b (r + gamma * max_a Q_i(s', a) - Q_i(s, a))^2  with the next-state
+ * values detached (no is_end masking: the reference masks only a value it never uses), sup_loss = CE(Q_0(s, .), a),
+ * loss = sup_loss + mean_i q_loss_i, one Adam step on the net.  hp->gamma carries the trainer's 0.99 (sarm.py:112).
+ * losses_out[0] = sup_loss, losses_out[1] = mean_i q_loss_i (device).  The python RNG draw of the reference
+ * (random.randint, :123) only selects tensors that do not reach the loss; the host mirror consumes it. */
+int rec_train_step_sarm(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *losses_out);
 /* The same two steps called the way the reference's trainers are: every pointer of `host_b` is HOST memory
  * (the CPU tensors a DataLoader yields; hp->div_emb / hp->unpopular stay device pointers) and the losses come
  * back as host floats (the reference returns `loss.item()`).  Synchronous: the batch is packed into a pinned

@@ -22,8 +22,8 @@ Restated (not runnable in the reference at HEAD):
   * tie-stable top-k (score desc, id asc) -- `torch.topk` order among ties is unspecified.
 """
 
-from .nets import SessionNet, make_gru4rec, make_bidir_gru4rec, make_sqn, make_smorl, make_bidir_sqn  # noqa: F401
-from .trainers import GRUTrainer, SQNTrainer, SMORLTrainer  # noqa: F401
+from .nets import SessionNet, make_gru4rec, make_bidir_gru4rec, make_sqn, make_smorl, make_bidir_sqn, make_sarm  # noqa: F401
+from .trainers import GRUTrainer, SQNTrainer, SMORLTrainer, SARMTrainer  # noqa: F401
 from .evalproto import (  # noqa: F401
     stable_topk,
     evaluate,

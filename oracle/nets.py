@@ -12,6 +12,7 @@ reference so that `state_dict()` keys match and seeded init is bit-identical:
   SQN_Network    recommenders/models/SQN/sqn_gru.py:10-112       trunk "base_model", ["sup_head_output","q_head_output"]
   SMORL_GRU_Net  recommenders/models/SMORL/smorl_gru.py:14-139   trunk "base_model", ["sup_head_output","q_head_acc","q_head_div","q_head_nov"]
   Bidir-SQN      restatement for BASELINE cfg3: SQN heads on a bidirectional trunk
+  MultiObjectiveQNetwork  recommenders/models/SARM/sarm.py:5-76  trunk "base_model", ModuleList q_heads[0..4]
 """
 
 from __future__ import annotations
@@ -27,7 +28,7 @@ class SessionNet(nn.Module):
     def __init__(
         self,
         *,
-        family: str,  # "gru4rec" | "bidir" | "sqn" | "smorl" | "bidir_sqn"
+        family: str,  # "gru4rec" | "bidir" | "sqn" | "smorl" | "bidir_sqn" | "sarm"
         hidden_dim: int,
         embedding_dim: int,
         item_num: int,
@@ -49,7 +50,7 @@ class SessionNet(nn.Module):
         self.gru_layers = gru_layers
         self.use_packed_seq = use_packed_seq
         self.bidirectional = family in ("bidir", "bidir_sqn")
-        rl_family = family in ("sqn", "smorl", "bidir_sqn")
+        rl_family = family in ("sqn", "smorl", "bidir_sqn", "sarm")
 
         pad = self.item_num if padding_idx is None else padding_idx
         # SQN/SMORL force a trainable pad row under packing (sqn_gru.py:46-47, smorl_gru.py:51-52);
@@ -81,9 +82,12 @@ class SessionNet(nn.Module):
             "sqn": ["sup_head_output", "q_head_output"],
             "bidir_sqn": ["sup_head_output", "q_head_output"],
             "smorl": ["sup_head_output", "q_head_acc", "q_head_div", "q_head_nov"],
+            "sarm": [],
         }[family]
         for name in self.head_names:
             setattr(self, name, nn.Linear(in_features=d, out_features=action_dim))
+        if family == "sarm":  # sarm.py:58-60
+            self.q_heads = nn.ModuleList([nn.Linear(in_features=d, out_features=action_dim) for _ in range(5)])
 
     # -- pieces ------------------------------------------------------------------------------
     def final_state(self, s, lengths):
@@ -98,6 +102,8 @@ class SessionNet(nn.Module):
 
     def forward(self, s, lengths):
         h = self.final_state(s, lengths)
+        if self.family == "sarm":
+            return [head(h) for head in self.q_heads]  # sarm.py:74-75
         if self.family == "bidir":
             h = self.dropout(h)
         outs = [getattr(self, n)(h) for n in self.head_names]
@@ -130,3 +136,7 @@ def make_smorl(**kw):
 
 def make_bidir_sqn(**kw):
     return _mk("bidir_sqn", **kw)
+
+
+def make_sarm(**kw):
+    return _mk("sarm", **kw)

@@ -174,3 +174,40 @@ class SMORLTrainer(_TwinTrainer):
         total.backward()
         opt.step()
         return sup_loss.item(), q_loss.item()
+
+
+class SARMTrainer:
+    """SARM_trainer (recommenders/models/SARM/sarm.py:78-158): one net with five Q heads, head 0 doubles as the
+    supervised head; gamma is fixed to 0.99 (:112); the `random.randint` draw (:123) only selects tensors that never
+    reach the loss, but it is consumed like in the reference."""
+
+    def __init__(self, *, hidden_dim, embedding_dim, train_pad_embed, use_packed_seq, learning_rate, item_num,
+                 state_size, action_dim, gru_layers, device="cpu", padding_idx=None, torch_rand_seed=118,
+                 python_rand_seed=999):
+        _seed(torch_rand_seed, python_rand_seed)
+        self.network = SessionNet(family="sarm", hidden_dim=hidden_dim, embedding_dim=embedding_dim, item_num=item_num,
+                                  state_size=state_size, action_dim=action_dim, gru_layers=gru_layers,
+                                  use_packed_seq=use_packed_seq, train_pad_embed=train_pad_embed, padding_idx=padding_idx)
+        self.device = device
+        self.gamma = 0.99
+        self.cross_entropy_loss = nn.CrossEntropyLoss(reduction="mean")
+        self.optimizer = torch.optim.Adam(self.network.parameters(), lr=learning_rate)
+        self.last_main_idx = None
+
+    def train_step(self, s, a, r, s_next, true_len, true_next_len, is_end):
+        r = r.unsqueeze(1)
+        outputs = self.network(s, true_len)
+        self.last_main_idx = random.randint(0, 4)  # :123
+        a_idx = a.unsqueeze(1)
+        with torch.no_grad():
+            outputs_next = self.network(s_next, true_next_len)
+        q_losses = []
+        for i in range(5):  # :133-135 (no is_end masking: the masked tensor of :131 is never used)
+            nxt = outputs_next[i].gather(1, torch.argmax(outputs_next[i], dim=1).unsqueeze(1))
+            q_losses.append(torch.mean((r + self.gamma * nxt - outputs[i].gather(1, a_idx)) ** 2))
+        sup_loss = self.cross_entropy_loss(outputs[0], a)
+        total = sup_loss + sum(q_losses) * (1.0 / len(q_losses))
+        self.optimizer.zero_grad()
+        total.backward()
+        self.optimizer.step()
+        return sup_loss.item(), sum(q.item() for q in q_losses) / len(q_losses)

@@ -546,3 +546,52 @@ def test_sharded_step_graphs_survive_engine_regrowth(pkg):
     mid-run evaluation batch larger than the engine's max_batch."""
     from test_gpu_parity import _run_dist_equivalence
     _run_dist_equivalence(1, 29617, {"REC_NO_DP_TRUNK": "1", "DIST_REGROW": "1"})
+
+
+# ------------------------------------------------------------------------------------ N4: SARM (sarm.py:5-158)
+@pytest.mark.parametrize("name", ["sarm_small", "sarm_unpacked", "sarm_64"])
+def test_sarm_train_steps_match_reference_fixture(pkg, name):
+    """SARM_trainer (five Q heads, head 0 doubles as the supervised head) against the fixtures written from the REAL
+    reference class: seeded init bit-identical, (sup, mean q) losses and all parameters after 4 Adam steps."""
+    from helpers import load_golden, sd_from_golden, rows_from_golden
+    g = load_golden(name)
+    m = g["meta"]
+    cfg = dict(item_num=int(m[0]), action_dim=int(m[1]), embedding_dim=int(m[2]), hidden_dim=int(m[3]), state_size=int(m[4]))
+    B, steps, packed, train_pad = int(m[5]), int(m[6]), bool(m[7]), bool(m[8])
+    t = pkg.SARM_trainer(train_pad_embed=train_pad, use_packed_seq=packed, learning_rate=0.01, gru_layers=1, device=DEV, **cfg)
+    init = sd_from_golden(g, "init")
+    assert list(t.network.state_dict().keys()) == list(init.keys())
+    assert_state_close({k: v.cpu() for k, v in t.network.state_dict().items()}, init, rtol=0, atol=0)
+    rows = rows_from_golden(g)
+    losses = [t.train_step(*_syn().as_torch_batch(rows, i * B, (i + 1) * B)) for i in range(steps)]
+    assert_close(losses, g["losses"], rtol=RTOL, atol=1e-5, what="(sup, mean q) losses")
+    assert_state_close(t.network.state_dict(), sd_from_golden(g, "final"), rtol=RTOL, atol=2e-5,
+                       outlier_frac=1e-3, outlier_atol=0.02 * 0.01 * steps)
+
+
+@pytest.mark.parametrize("V,H,B", [(5000, 64, 200), (3000, 128, 96)])
+def test_sarm_against_live_oracle(pkg, V, H, B):
+    """SARM at catalogue sizes where the tensor-core head kernels run (D = 64: head_stats_tc / head_bwd_adam_tc2 with the
+    extra target-column gradient; D = 128: the K-loop kernels), forward list of five outputs included."""
+    kw = dict(hidden_dim=H, embedding_dim=H, train_pad_embed=True, use_packed_seq=True, learning_rate=0.005, item_num=V,
+              state_size=10, action_dim=V, gru_layers=1)
+    ref = oracle.SARMTrainer(**kw)
+    t = pkg.SARM_trainer(device=DEV, **kw)
+    rows = _syn().make_replay_rows(3 * B, V, 10, seed=5)
+    s0, _, _, _, ln0, _, _ = _syn().as_torch_batch(rows, 0, 16)
+    with torch.no_grad():
+        want = ref.network(s0, ln0)
+    got = t.network(s0, ln0)
+    assert isinstance(got, list) and len(got) == 5
+    for g_, w_ in zip(got, want):
+        assert_close(g_, w_, rtol=1e-4, atol=1e-5, what="SARM forward outputs")
+    rng = synced_random()
+    for i in range(3):
+        b = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+        rng.replay(); want_l = ref.train_step(*b)
+        rng.replay(); got_l = t.train_step(*b)
+        rng.advance()
+        assert t.last_main_idx == ref.last_main_idx
+        assert_close(got_l, want_l, rtol=RTOL, atol=1e-5, what=f"step {i} (sup, mean q) losses")
+    assert_state_close(t.network.state_dict(), ref.network.state_dict(), rtol=RTOL, atol=2e-5,
+                       outlier_frac=1e-3, outlier_atol=0.02 * 0.005 * 3)

@@ -62,6 +62,18 @@ def test_oracle_sqn_matches_reference_fixture(name, pkg):
     assert_state_close(t.DQN_2.state_dict(), sd_from_golden(g, "final2"), rtol=1e-3, atol=2e-5)
 
 
+@pytest.mark.parametrize("name", ["sarm_small", "sarm_unpacked", "sarm_64"])
+def test_oracle_sarm_matches_reference_fixture(name, pkg):
+    """oracle.SARMTrainer against the fixtures written from the REAL SARM_trainer (oracle/make_golden_sarm.py)."""
+    g = load_golden(name)
+    cfg, B, steps, packed, train_pad, layers = _meta(g)
+    t = oracle.SARMTrainer(train_pad_embed=train_pad, use_packed_seq=packed, learning_rate=0.01, gru_layers=layers, **cfg)
+    assert_state_close(t.network.state_dict(), sd_from_golden(g, "init"), rtol=0, atol=0)
+    losses = [t.train_step(*b) for b in _batches(rows_from_golden(g), B, steps)]
+    assert_close(losses, g["losses"], rtol=1e-5, atol=1e-6, what="losses")
+    assert_state_close(t.network.state_dict(), sd_from_golden(g, "final"), rtol=1e-3, atol=2e-5)
+
+
 def test_oracle_smorl_fixture(pkg):
     g = load_golden("smorl_small")
     cfg, B, steps, *_ = _meta(g)
