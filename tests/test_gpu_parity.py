@@ -374,10 +374,11 @@ def _virtual_rank_step(trainers, hp_fn, batch, main, has_q=True):
     return [l[:2].tolist() for l in losses]
 
 
-def test_vocab_sharded_phases_equal_unsharded_and_oracle(pkg):
+@pytest.mark.parametrize("H", [64, 128])  # 128: the wide-layer kernels (K-loop heads incl. top-k, tensor-core GRU) under sharding
+def test_vocab_sharded_phases_equal_unsharded_and_oracle(pkg, H):
     from ikea_recommender_system_b200.sharded import shard_bounds
     G, V = 3, 1000
-    kw = dict(hidden_dim=64, embedding_dim=64, padding_pos="end", train_pad_embed=True, use_packed_seq=True,
+    kw = dict(hidden_dim=H, embedding_dim=H, padding_pos="end", train_pad_embed=True, use_packed_seq=True,
               learning_rate=0.01, item_num=V, state_size=10, action_dim=V, gamma=0.5, gru_layers=1,
               q_weights=torch.tensor([1.0, 0.6, 0.3]), alpha=0.9, topk_div=2, topk_nov=1, nov_rew_sig=1.0)
     rows = _syn().make_replay_rows(3 * 96, V, 10, seed=8)
