@@ -471,13 +471,13 @@ def eval_bench(args, wl, local, with_cpu):
             "e2e": {"value": sessions / e2e_s, "unit": "sessions/s", "h2d_bytes_per_step": B * (L + 2) * 8,
                     "d2h_bytes_per_step": 8 * 27 + 4 * 8 * ((N + 31) // 32) // max(1, n_batches)},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "head_stats_tc_kernel (logits + online softmax + running top-k per tile)",
+            "roofline": {"bound": "tensor", "kernel": "tck_kernel<HeadCmaxFlat> (logits + online softmax + chunk maxima per tile; exact top-k from the best chunks in chunk_select / chunk_score) -- head_stats_tc_kernel / HeadTopk below 1024 sessions or 32768 items",
                          "achieved": flops_alg / (head_ms / 1e3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": flops_alg / (head_ms / 1e3) / 1e12 / peak_tf,
                          "traffic": None, "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / (reps * n_batches)),
                          "algorithmic_flops_per_launch": flops_alg,
-                         "note": "algorithmic 2*D*V FLOP per session (executed: 3 bf16 passes); the epilogue (one ex2 + "
-                                 "top-k compare per logit on the CUDA cores) is co-limiting at D = 64"},
+                         "note": "algorithmic 2*D*V FLOP per session (executed: 3 bf16 passes); the epilogue (one ex2 + max per logit on "
+                                 "the CUDA cores: ~8 instructions per logit, issue- and power-bound) is the limiter at D = 64"},
             "metrics_sample": {"hr": [float(x) for x in out[1]], "ndcg": [float(x) for x in out[2]]},
             "cpu_baseline": None}
     del net, eng

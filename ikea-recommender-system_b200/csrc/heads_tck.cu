@@ -243,12 +243,11 @@ __device__ __noinline__ void topk_insert(float v, int id, float *lv, int *li, in
   tau = cnt == topk ? lv[(topk - 1) * stride] : REC_NEG_INF;
 }
 
-// CM (chunk maxima, large evaluation batches): no lists at all in this pass -- every thread writes the maximum of its
-// 32-column chunk to cmax[chunk][row]; chunk_select_kernel + chunk_rescore_kernel (below) then find the k + margin chunks
-// with the largest maxima per row (every top-k element lies in one of the k chunks with the largest maxima) and score
-// those chunks exactly in fp32.  The tensor-core pass becomes a divergence-free streaming epilogue.
-template <bool ARES, bool CM = false>
+// (Large evaluation batches over large catalogues use HeadCmaxFlat + chunk_select / chunk_score below instead: no lists,
+// no divergence in the tensor-core pass.)
+template <bool ARES>
 struct HeadTopk {
+  static constexpr bool CM = false;
   using Params = FwdParams;
   static constexpr bool CLUSTERED = false;
   static constexpr int EPI_WARPS = 16, NT = 512, CS = 4, KMAX = 20;
@@ -433,7 +432,7 @@ struct HeadCmaxFlat {
     tc::bulk_g2s(stage + BLK2, p.wimg + ((int64_t)t * p.KB + ks) * BLK2, BLK2, bar);
   }
   __device__ static __forceinline__ void mma(const Params &, int, int, uint32_t st, uint32_t tacc, bool first) {
-    HeadTopk<false, true>::mma_ab(st, st + BLK2, tacc, first);
+    HeadTopk<false>::mma_ab(st, st + BLK2, tacc, first);
   }
   struct Epi {
     float *xs;

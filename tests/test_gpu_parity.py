@@ -244,10 +244,12 @@ def test_evaluate_matches_reference_fixture(pkg):
     assert all(isinstance(v, set) for v in out[2].values())
 
 
-@pytest.mark.parametrize("hidden", [8, 64])  # 8: CUDA-core head kernels, 64: tcgen05 head kernels
-def test_topk_ties_lowest_id_first(pkg, hidden):
-    """Exact ties: zero head weights, bias with repeated values -> logits == bias for every session."""
-    N, V, B, K = 50, 300, 70, 20
+@pytest.mark.parametrize("hidden,V,B", [(8, 300, 70), (64, 300, 70), (64, 40000, 1030), (128, 40000, 1030)])
+def test_topk_ties_lowest_id_first(pkg, hidden, V, B):
+    """Exact ties: zero head weights, bias with repeated values -> logits == bias for every session.
+    hidden 8: CUDA-core head kernels; 64 / small: tcgen05 head kernels; B >= 1024 and V >= 32768: the chunk-maxima path
+    (massive ties overflow its candidate list: the exact fallback must still return the lowest ids)."""
+    N, K = 50, 20
     net = pkg.GRU4Rec(hidden_size=hidden, embedding_dim=hidden, item_num=N, state_size=5, action_dim=V)
     rng = np.random.default_rng(0)
     bias = torch.from_numpy(rng.integers(0, 6, size=V).astype(np.float32))
