@@ -99,6 +99,7 @@ SYMBOLS = {
     "rec_unpack_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(RecBatch)]),
     "rec_eval_batch": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.POINTER(RecEvalOpts),
                                  C.POINTER(RecEvalAccum), _P, _P]),
+    "rec_eval_hold_params": (C.c_int, [_P, C.c_int]),
     "rec_eval_shard_candidates": (C.c_int, [_P, C.c_int, C.POINTER(RecBatch), C.c_int, C.c_int, _P]),
     "rec_eval_merge": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecEvalOpts), _P, C.c_int,
                                  C.POINTER(RecEvalAccum), _P, _P]),

@@ -252,6 +252,7 @@ static int check_net(rec_engine *e, int net_id, bool need_opt) {
 }
 
 extern "C" int rec_bind_params(rec_engine *e, int net_id, const rec_net_params *p) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e || !p) return REC_EINVAL;
   if (net_id < 0 || net_id >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "net_id %d out of range", net_id);
@@ -302,6 +303,7 @@ extern "C" int rec_set_cuda_graphs(rec_engine *e, int on) {
   return REC_OK;
 }
 extern "C" int rec_set_tensor_cores(rec_engine *e, int on) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   e->use_tc = on != 0;
@@ -583,6 +585,7 @@ static int supervised_body(rec_engine *e, const rec_batch *b, const rec_train_hp
 }
 
 extern "C" int rec_train_step_supervised(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *loss_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   int rc = check_net(e, 0, true);
   if (rc) return rc;
@@ -605,6 +608,7 @@ static int finish_host_step(rec_engine *e, int rc, float *out, int n) {
 }
 
 extern "C" int rec_train_step_supervised_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp, float *loss_host) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   int rc = check_net(e, 0, true);
   if (rc) return rc;
@@ -705,6 +709,7 @@ static int q_step_body(rec_engine *e, const rec_batch *b, const rec_train_hparam
 }
 
 extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net, float *losses_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q needs a twin-net engine with Q heads");
@@ -730,6 +735,7 @@ extern "C" int rec_train_step_q(rec_engine *e, const rec_batch *b, const rec_tra
 
 extern "C" int rec_train_step_q_host(rec_engine *e, const rec_batch *host_b, const rec_train_hparams *hp, int main_net,
                                      float *losses_host) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cfg.n_nets != 2 || e->cfg.n_heads < 2) REC_FAIL(e, REC_EINVAL, "rec_train_step_q_host needs a twin-net engine with Q heads");
@@ -870,6 +876,7 @@ __global__ void __launch_bounds__(256) sarm_rows_entry(SarmPtrs P, const float *
 }
 
 extern "C" int rec_train_step_sarm(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, float *losses_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cfg.n_heads != 5 || e->cfg.n_nets != 1) REC_FAIL(e, REC_EINVAL, "rec_train_step_sarm needs a single-net engine with 5 heads");
@@ -892,6 +899,13 @@ static int eval_kmax(const rec_eval_opts *o) {
   if (o->div_emb && o->topk_div > k) k = o->topk_div;
   if (o->unpopular && o->topk_nov > k) k = o->topk_nov;
   return k;
+}
+
+extern "C" int rec_eval_hold_params(rec_engine *e, int on) {
+  if (!e) return REC_EINVAL;
+  e->k_hold = on != 0;
+  e->k_img_epoch = -1;  // the first evaluation call after a change of state packs afresh
+  return REC_OK;
 }
 
 extern "C" int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, const rec_eval_opts *o,
@@ -995,6 +1009,7 @@ static int phase_a_body(rec_engine *e, const rec_batch *b, const rec_train_hpara
 
 extern "C" int rec_train_phase_a(rec_engine *e, const rec_batch *b, const rec_train_hparams *hp, int main_net,
                                  float *records_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (e) e->dp_active = false;
   return phase_a_body(e, b, hp, main_net, records_out, false);
@@ -1047,6 +1062,7 @@ extern "C" int64_t rec_dp_grad_floats(const rec_engine *e) {
 }
 
 extern "C" int rec_dp_forward(rec_engine *e, const rec_batch *local, int main_net, void *packed_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   const int n_q = e->cfg.n_heads - 1;
@@ -1102,12 +1118,14 @@ extern "C" int rec_dp_unpack(rec_engine *e, const void *gathered, int n_ranks, i
 
 extern "C" int rec_train_phase_a_heads(rec_engine *e, const rec_batch *global_b, const rec_train_hparams *hp, int main_net,
                                        float *records_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (e) e->dp_active = true;
   return phase_a_body(e, global_b, hp, main_net, records_out, true);
 }
 
 extern "C" int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank, float *gru_grads_out, float *dx_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 3 || !e->dp_active) REC_FAIL(e, REC_EINVAL, "rec_dp_backward called out of order");
@@ -1128,6 +1146,7 @@ extern "C" int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank,
 }
 
 extern "C" int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const float *dx_gathered) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 4) REC_FAIL(e, REC_EINVAL, "rec_dp_apply called out of order");
@@ -1151,6 +1170,7 @@ extern "C" int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const
 }
 
 extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_shards, float *q_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 1) REC_FAIL(e, REC_EINVAL, "rec_train_phase_b called out of order");
@@ -1169,6 +1189,7 @@ extern "C" int rec_train_phase_b(rec_engine *e, const float *gathered, int n_sha
 }
 
 extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, float *losses_out, float *dh_out) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 2) REC_FAIL(e, REC_EINVAL, "rec_train_phase_c called out of order");
@@ -1196,6 +1217,7 @@ extern "C" int rec_train_phase_c(rec_engine *e, const float *boot_q_reduced, flo
 }
 
 extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
+  if (e) e->param_epoch++;  // parameters may change: derived operand images are stale (rec_eval_hold_params)
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;
   if (e->cur_phase != 3) REC_FAIL(e, REC_EINVAL, "rec_train_phase_d called out of order");

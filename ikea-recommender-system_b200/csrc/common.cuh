@@ -116,6 +116,11 @@ struct rec_engine {
   float *k_bias;         // combined bias of the greedy-action heads
   int k_sup_net, k_sup_head;  // which (net, head) k_wimg[0] / k_himg[0] currently hold (-1: none)
   float *k_cmax;         // chunk maxima [B][V/32] of the evaluation top-k (HeadTopk<.., CM>)
+  bool k_hold;           // rec_eval_hold_params: parameters are frozen by the caller, images may be reused
+  int64_t param_epoch, k_img_epoch;  // bumped by every entry point that may write parameters / epoch of the cached image
+  int k_img_net, k_img_head;
+  uint8_t *k_bblk;       // bias operand blocks of HeadCmaxPair [tiles + 1][4 KB]
+  float *k_cmax2;        // level-2 maxima [B][2 * ceil(tiles / 8)] (HeadCmaxPair)
   int *k_chosen;         // [B][KC] the chunks with the largest maxima per row
   // SARM (5 Q heads, rec_train_step_sarm)
   float *sarm_qmax;      // [5][maxB] max_a Q_i(s', a), exact (re-scored)

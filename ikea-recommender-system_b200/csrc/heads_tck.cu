@@ -21,6 +21,7 @@
 // hi*hi + hi*lo + lo*hi with fp32 accumulation ("bf16x3", ~1e-5 relative) exactly like the D = 64 kernels.
 // Reference semantics: nn.Linear heads + CrossEntropyLoss + Adam of models/SQN/sqn_gru.py:78-112,183-254 and
 // models/BidirGRU4Rec/model.py:51-99 (cfg3 = SQN heads on the concatenated bidirectional state).
+#include <stdio.h>
 #include <stdlib.h>
 #include "tck.cuh"
 
@@ -44,6 +45,10 @@ struct FwdParams {
   int topk;                    // HeadTopk: k of the running top-k (<= 20)
   float *cmax;                 // HeadTopk<.., CM>: chunk maxima [B][cmax_ld >= n_tiles * 4]
   int64_t cmax_ld;
+  long long *trace;            // HeadCmaxPair: clock64 stamps [8 kinds][64 units] of one CTA (debugging; normally null)
+  const uint8_t *bblk;         // HeadCmaxPair: bias operand blocks [n_tiles + 1][4 KB] (block n_tiles = the "ones" operand)
+  float *cmax2;                // HeadCmaxPair: level-2 maxima [B][cmax2_ld >= 2 * ceil(n_tiles / 8)]
+  int64_t cmax2_ld;
   int n_sb, per;               // HeadCmaxFlat: session blocks, units per CTA of the flattened (session block, tile) space
   const float *extra;          // DL: optional per-row gradient added at the target column (SARM)
 };
@@ -510,6 +515,166 @@ struct HeadCmaxFlat {
   };
 };
 
+// Bias operand blocks of HeadCmaxPair: block t = [128 items of tile t][K = 16] with (hi, lo, lo2) of the fp32 bias in
+// k = 0..2 (the three bf16 terms add up to the fp32 value), zeros elsewhere; items beyond the catalogue get -1e30 (their
+// weight rows are zero: the column vanishes from the maxima and the sum).  Block n_tiles is the "ones" operand.
+__global__ void __launch_bounds__(128) pack_bias_blocks_kernel(const float *__restrict__ bias, int Vloc, int n_tiles,
+                                                              uint8_t *__restrict__ out) {
+  const int t = blockIdx.x, r = threadIdx.x;
+  uint32_t *o = reinterpret_cast<uint32_t *>(out + (int64_t)t * 4096);
+  // row r of the block: two 16-byte chunks (k = 0..7 at nosw_off(r, 0), k = 8..15 at nosw_off(r, 8))
+  uint4 *c0 = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(o) + tc::nosw_off(r, 0));
+  uint4 *c1 = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(o) + tc::nosw_off(r, 8));
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (t == n_tiles) {
+    v.x = 0x3f803f80u; v.y = 0x00003f80u;  // bf16 1.0 in k = 0, 1, 2
+  } else {
+    const int item = t * 128 + r;
+    const float b = item < Vloc ? bias[item] : -1e30f;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(b);
+    const float r1 = b - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+    v.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    v.y = (uint32_t)__bfloat16_as_ushort(h2);
+  }
+  *c0 = v;
+  *c1 = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// D = 64: the chunk-maxima pass with TWO session blocks per CTA.  Grid = (vocabulary splits, session-block pairs): a CTA
+// keeps the state blocks of its pair RESIDENT in shared memory and streams every weight tile of its split ONCE for both
+// blocks (HeadCmaxFlat re-loads a state block AND a weight tile per 128 x 128 unit: 64 KB from L2 per 768 tensor cycles,
+// above the ~42 B/clk/SM the L2 delivers; and its CTAs walk the catalogue out of phase, so the 256 MB weight image is
+// streamed from HBM once per session block).  All CTAs of a split sweep the same tiles at about the same time: the weight
+// image is read from HBM once.  Per unit (tile) the issuer fills two accumulators (256 TMEM columns, double-buffered =
+// all 512); 16 epilogue warps = (lane quadrant, session block of the pair, column half): 64 logits per thread and unit.
+// Besides the 32-column chunk maxima every thread keeps the maximum of its 64 columns over 8 consecutive tiles: the
+// level-2 maxima [B][2 * ceil(n_tiles / 8)] that chunk_select2_kernel reads first (a row's 31 k chunk maxima are then
+// only touched inside the ~30 best groups).
+// PV (REC_CMAX_EXP, experiments behind DESIGN.md 4.7): 0 = the product; 4 = every 4th exponential through tc::ex2_poly on
+// the FMA pipe; 10 = no epilogue, 11 = no MMAs (which side of the pipeline bounds the kernel); 30 = a single issuer warp.
+template <int PV>
+struct HeadCmaxPairT {
+  using Params = FwdParams;
+  static constexpr bool CLUSTERED = false;
+  static constexpr int EPI_WARPS = 16, NT = 512;
+  static constexpr int ISSUERS = PV == 30 ? 1 : 2;
+  static constexpr int BB = 4096;  // one un-swizzled [128][16] bf16 operand (tc::nosw_off)
+  static constexpr int RESIDENT_BYTES = 2 * BLK2 + BB;           // state blocks of the pair + the "ones" operand
+  static constexpr const char *NAME = "tck:head_cmax_pair";
+  static constexpr int STAGES = 4, STAGE_BYTES = BLK2 + BB, ACC_COLS = 256, TMEM_COLS = 512;  // weight tile + its bias operand
+  static constexpr int EXTRA_BYTES = 256 * 3 * 4;
+  static constexpr int GROUP = 8;  // tiles per level-2 maximum
+  __device__ static __forceinline__ void units(const Params &p, int &lo, int &hi) {
+    lo = blockIdx.x * p.per;  // p.per % GROUP == 0: a level-2 group belongs to one CTA
+    hi = min(p.n_tiles, lo + p.per);
+    if (hi < lo) hi = lo;
+  }
+  __device__ static __forceinline__ int k_steps(const Params &, int) { return 1; }
+  __device__ static void trace(const Params &p, int kind, int i) {
+    if (p.trace && blockIdx.x == 1 && blockIdx.y == 1 && i >= 64 && i < 128) p.trace[kind * 64 + (i - 64)] = clock64();
+  }
+  __device__ static __forceinline__ bool has_second(const Params &p) { return 2 * (int)blockIdx.y + 1 < p.n_sb; }
+  __device__ static __forceinline__ void load_resident(const Params &p, uint8_t *res, uint64_t *bar) {
+    const uint32_t bytes = has_second(p) ? 2 * BLK2 : BLK2;  // consecutive blocks of the state image
+    tc::mbar_expect_tx(bar, bytes + BB);
+    tc::bulk_g2s(res, p.himg + (int64_t)(2 * blockIdx.y) * BLK2, bytes, bar);
+    tc::bulk_g2s(res + 2 * BLK2, p.bblk + (int64_t)p.n_tiles * BB, BB, bar);
+  }
+  __device__ static __forceinline__ void load(const Params &p, int u, int, uint8_t *stage, uint64_t *bar) {
+    tc::mbar_expect_tx(bar, BLK2 + BB);
+    tc::bulk_g2s(stage, p.wimg + (int64_t)u * BLK2, BLK2, bar);
+    tc::bulk_g2s(stage + BLK2, p.bblk + (int64_t)u * BB, BB, bar);
+  }
+  __device__ static __forceinline__ void mma(const Params &p, int, int, uint32_t st, uint32_t res, uint32_t tacc, bool) {
+    if (PV == 11) return;  // timing experiment: no MMAs
+    // + bias[item] for every session: ones[128][16] . (b_hi, b_lo, b_lo2, 0 ...)[128][16]^T, one K = 16 MMA per block
+    const uint32_t id = tc::instr_desc(128, 128, 0, 0);
+    const uint64_t ones = tc::smem_desc_nosw(res + 2 * BLK2, 128, 256), bb = tc::smem_desc_nosw(st + BLK2, 128, 256);
+    HeadTopk<false>::mma_ab(res, st, tacc, true);
+    tc::mma_bf16(tacc, ones, bb, id, true);
+    if (has_second(p)) {
+      HeadTopk<false>::mma_ab(res + BLK2, st, tacc + 128, true);
+      tc::mma_bf16(tacc + 128, ones, bb, id, true);
+    }
+  }
+  struct Epi {
+    float *xs;
+    int q, sbi, half, lane, row, trow;
+    float m_run, s_run, tgt, g2;
+    bool rv, active;
+    __device__ __forceinline__ Epi(const Params &p, uint8_t *extra, int tid) {
+      xs = reinterpret_cast<float *>(extra);
+      const int warp = tid >> 5;
+      lane = tid & 31; q = warp & 3; sbi = (warp >> 2) & 1; half = warp >> 3;
+      const int sb = 2 * blockIdx.y + sbi;
+      active = sb < p.n_sb;
+      row = sb * 128 + q * 32 + lane;
+      rv = active && row < p.B;
+      trow = (p.target && rv) ? (int)(p.target[row] - p.vocab_lo) : -1;
+      m_run = REC_NEG_INF; s_run = 0.f; tgt = REC_NEG_INF; g2 = REC_NEG_INF;
+    }
+    __device__ __forceinline__ float chunk(const Params &, int c_lo, uint32_t taddr) {
+      float l[32];
+      tc::tmem_ld32(taddr, l);
+      // (the bias arrived through the tensor cores; columns beyond the catalogue carry -1e30)
+      float tmax = fmaxf(l[0], l[1]);
+#pragma unroll
+      for (int j = 2; j < 32; ++j) tmax = fmaxf(tmax, l[j]);
+      const float nm = fmaxf(m_run, tmax), nml = -fmaxf(nm, -1e30f) * LOG2E;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = fmaf(l[j], LOG2E, nml);
+        const bool poly = PV == 4 && (j & 3) == 3;
+        ps[j & 3] += poly ? tc::ex2_poly(x) : tc::ex2_ftz(x);
+      }
+      s_run = fmaf(s_run, tc::ex2_ftz((m_run - nm) * LOG2E), (ps[0] + ps[1]) + (ps[2] + ps[3]));
+      m_run = nm;
+      if (trow >= c_lo && trow < c_lo + 32) {
+        const int tj = trow - c_lo;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j == tj) tgt = l[j];
+      }
+      return tmax;
+    }
+    __device__ __forceinline__ void tile(const Params &p, int u, int, uint32_t tacc) {
+      if (!active) return;  // odd number of session blocks: the second half of the last pair idles (warp-uniform)
+      if (PV == 10) return;  // timing experiment: no epilogue
+      const int c_lo = u * 128 + half * 64;
+      const uint32_t ta = tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)(sbi * 128 + half * 64);
+      const float c0 = chunk(p, c_lo, ta);
+      const float c1 = chunk(p, c_lo + 32, ta + 32);
+      g2 = fmaxf(g2, fmaxf(c0, c1));
+      if (rv) {
+        *reinterpret_cast<float2 *>(p.cmax + (int64_t)row * p.cmax_ld + (u * 4 + half * 2)) = make_float2(c0, c1);
+        if ((u & (GROUP - 1)) == GROUP - 1 || u == p.n_tiles - 1) {
+          p.cmax2[(int64_t)row * p.cmax2_ld + ((u / GROUP) * 2 + half)] = g2;
+          g2 = REC_NEG_INF;
+        }
+      }
+    }
+    __device__ __forceinline__ void finish(const Params &p) {
+      // one statistics record per (split, row): the two column halves meet in shared memory
+      float *x = xs + ((sbi * 128 + q * 32 + lane)) * 3;
+      if (half == 1) { x[0] = m_run; x[1] = s_run; x[2] = tgt; }
+      epi_bar<NT>();
+      if (half == 0 && rv) {
+        const float m1 = x[0], s1 = x[1], t1 = x[2];
+        const float m = fmaxf(m_run, m1);
+        float ssum = 0.f;
+        if (s_run > 0.f) ssum += s_run * __expf(m_run - m);
+        if (s1 > 0.f) ssum += s1 * __expf(m1 - m);
+        float *o = p.part + ((int64_t)blockIdx.x * p.B + row) * p.part_stride;
+        o[0] = m; o[1] = ssum; o[2] = fmaxf(tgt, t1);
+      }
+    }
+  };
+};
+
+using HeadCmaxPair = HeadCmaxPairT<0>;
+
 // ---- exact top-k from chunk maxima ------------------------------------------------------------------------------------
 constexpr int KC = 24;      // chunks kept per row: k <= 20 plus a margin for the ~1e-5 relative error of the bf16x3 maxima
 constexpr int CCAP = 512;   // candidate list of the threshold pass (expected ~50 entries)
@@ -654,6 +819,172 @@ __global__ void __launch_bounds__(256) chunk_score_kernel(const int *__restrict_
       ids[r] = vocab_lo + v;
     }
     sc[r] = acc;
+  }
+  float pv = 3.402823466e+38f;
+  int pi = -1;
+  float *sm = summary ? summary + (int64_t)row * part_stride : nullptr;
+  for (int k = 0; k < topk; ++k) {
+    float bv = REC_NEG_INF;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < KC; ++r)
+      if (ids[r] != 0x7fffffff && better(pv, pi, sc[r], ids[r]) && better(sc[r], ids[r], bv, bi)) { bv = sc[r]; bi = ids[r]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv;
+      if (sm) { sm[TOPK_OFF + k] = bv; sm[TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(bi); }
+    }
+    pv = bv; pi = bi;
+  }
+}
+
+// Selection over the two-level maxima written by HeadCmaxPair (warp = row):
+//  (1) lane-strided pass over the row's LEVEL-2 maxima (group = 64 columns x 8 tiles = 16 chunks); t0 = KC-th largest of
+//      the 32 lane maxima: at least KC groups reach t0, every one of them holds a chunk >= t0, so the KC best chunks all
+//      reach t0 and lie in groups >= t0;
+//  (2) second pass over the level-2 row (L1 / L2 hits): for every group >= t0 sixteen lanes fetch its chunk maxima and
+//      the chunks >= t0 go to the shared-memory list; KC rounds of a warp argmax pick the KC best by (maximum desc,
+//      chunk asc).  A list overflow (a row of massive ties) falls back to KC full passes over the chunk maxima.
+__global__ void __launch_bounds__(256) chunk_select2_kernel(const float *__restrict__ cmax, int64_t ld, int n_chunks,
+                                                           const float *__restrict__ cmax2, int64_t ld2, int n_tiles, int B,
+                                                           int *__restrict__ chosen) {
+  constexpr int GROUP = HeadCmaxPair::GROUP;
+  __shared__ float lv_all[8 * CCAP];
+  __shared__ int lc_all[8 * CCAP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + wid;
+  if (row >= B) return;
+  float *lv = lv_all + wid * CCAP;
+  int *lc = lc_all + wid * CCAP;
+  const float *cm = cmax + (int64_t)row * ld;
+  const float *cm2 = cmax2 + (int64_t)row * ld2;
+  const int n2 = ((n_tiles + GROUP - 1) / GROUP) * 2;
+  float lm = REC_NEG_INF;
+  for (int g = lane; g < n2; g += 32 * 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = g + 32 * j < n2 ? __ldg(cm2 + g + 32 * j) : REC_NEG_INF;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lm = fmaxf(lm, v[j]);
+  }
+  int rank = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float o = __shfl_sync(0xffffffffu, lm, j);
+    rank += (o > lm || (o == lm && j < lane)) ? 1 : 0;
+  }
+  const int src = __ffs(__ballot_sync(0xffffffffu, rank == KC - 1)) - 1;
+  const float t0 = __shfl_sync(0xffffffffu, lm, src);
+  int n_list = 0;
+  bool overflow = false;
+  for (int g0 = 0; g0 < n2 && !overflow; g0 += 32) {
+    const float v2 = g0 + lane < n2 ? __ldg(cm2 + g0 + lane) : REC_NEG_INF;
+    unsigned gm = __ballot_sync(0xffffffffu, v2 >= t0);
+    while (gm && !overflow) {
+      // two groups per iteration: lanes 0..15 the lowest set bit, lanes 16..31 the next one
+      const int b0 = __ffs(gm) - 1;
+      gm &= gm - 1;
+      const int b1 = gm ? __ffs(gm) - 1 : -1;
+      if (gm) gm &= gm - 1;
+      const int bsel = lane < 16 ? b0 : b1;
+      const int g = g0 + bsel, l16 = lane & 15;
+      const int t = (g >> 1) * GROUP + (l16 >> 1);
+      const int c = t * 4 + (g & 1) * 2 + (l16 & 1);
+      float v = REC_NEG_INF;
+      if (bsel >= 0 && t < n_tiles) v = __ldg(cm + c);
+      const bool take = v >= t0 && bsel >= 0 && t < n_tiles;
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m) {
+        const int pos = n_list + __popc(m & ((1u << lane) - 1u));
+        if (take && pos < CCAP) { lv[pos] = v; lc[pos] = c; }
+        n_list += __popc(m);
+        if (n_list > CCAP) overflow = true;
+      }
+    }
+  }
+  __syncwarp();
+  float lastv = 3.402823466e+38f;
+  int lastc = -1;
+  for (int r = 0; r < KC; ++r) {
+    float bv = REC_NEG_INF;
+    int bc = 0x7fffffff;
+    if (!overflow) {
+      for (int e = lane; e < n_list; e += 32) {
+        const float v = lv[e];
+        const int c = lc[e];
+        if (better(lastv, lastc, v, c) && better(v, c, bv, bc)) { bv = v; bc = c; }
+      }
+    } else {
+      for (int c = lane; c < n_chunks; c += 32) {
+        const float v = __ldg(cm + c);
+        if (better(lastv, lastc, v, c) && better(v, c, bv, bc)) { bv = v; bc = c; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (better(ov, oc, bv, bc)) { bv = ov; bc = oc; }
+    }
+    if (lane == 0) chosen[(int64_t)row * KC + r] = bc;
+    lastv = bv; lastc = bc;
+  }
+}
+
+// Exact scores of the kept chunks with COALESCED loads (D = 64): the 32 weight rows of a chunk are 8 KB of contiguous
+// memory; load instruction i of a warp covers rows 2i and 2i + 1 (lane = 16 * (row & 1) + float4 index), every lane
+// multiplies by ITS float4 of the state row and the sixteen partial sums of a row meet in a fixed xor butterfly -- the
+// same order for every row, so identical weight rows score identically wherever they sit.  (The lane-per-column version
+// above touches 32 different 128-byte lines per load instruction: 8 x the L1 tag traffic, 380 us per 5000 rows.)
+// Lane j ends up with the score of column 2 * (j & 15) + (j >> 4) of each chunk.
+__global__ void __launch_bounds__(128) chunk_score64_kernel(const int *__restrict__ chosen,
+                                                           const float *__restrict__ W, const float *__restrict__ bias,
+                                                           const float *__restrict__ h, int B, int Vloc, int vocab_lo,
+                                                           int topk, int32_t *__restrict__ row_ids, float *__restrict__ row_topv,
+                                                           float *__restrict__ summary, int part_stride) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + wid;
+  if (row >= B) return;
+  const int mine = lane < KC ? chosen[(int64_t)row * KC + lane] : 0x7fffffff;  // lane r holds the r-th best chunk
+  const float4 hq = __ldg(reinterpret_cast<const float4 *>(h + (int64_t)row * 64) + (lane & 15));
+  const int col = 2 * (lane & 15) + (lane >> 4);
+  float sc[KC];
+  int ids[KC];
+#pragma unroll
+  for (int r = 0; r < KC; ++r) {
+    const int c = __shfl_sync(0xffffffffu, mine, r);
+    float my = REC_NEG_INF;
+    ids[r] = 0x7fffffff;
+    if (c != 0x7fffffff) {  // warp-uniform
+      const int v0 = c * 32;
+      const float4 *wc = reinterpret_cast<const float4 *>(W + (int64_t)v0 * 64) + lane;
+      float4 w4[16];
+      if (v0 + 32 <= Vloc) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w4[i] = __ldg(wc + i * 32);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          w4[i] = (v0 + 2 * i + (lane >> 4) < Vloc) ? __ldg(wc + i * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float pr = w4[i].x * hq.x;
+        pr = fmaf(w4[i].y, hq.y, pr); pr = fmaf(w4[i].z, hq.z, pr); pr = fmaf(w4[i].w, hq.w, pr);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
+        if ((lane & 15) == i) my = pr;
+      }
+      const int v = v0 + col;
+      if (v < Vloc) { my += __ldg(bias + v); ids[r] = vocab_lo + v; }
+      else my = REC_NEG_INF;
+    }
+    sc[r] = my;
   }
   float pv = 3.402823466e+38f;
   int pi = -1;
@@ -914,7 +1245,7 @@ static int tck_ensure(rec_engine *e, int what) {
 }
 
 void tck_free(rec_engine *e) {
-  void *ptrs[] = {e->k_wimg[0], e->k_wimg[1], e->k_himg[0], e->k_himg[1], e->k_hT, e->k_dlT, e->k_db, e->k_bias, e->k_cmax, e->k_chosen};
+  void *ptrs[] = {e->k_wimg[0], e->k_wimg[1], e->k_himg[0], e->k_himg[1], e->k_hT, e->k_dlT, e->k_db, e->k_bias, e->k_cmax, e->k_cmax2, e->k_chosen, e->k_bblk};
   for (void *p : ptrs) if (p) cudaFree(p);
 }
 
@@ -982,41 +1313,92 @@ int launch_head_topk_chunks(rec_engine *e, const HeadStatsArgs &a, int *n_split_
   const int64_t mb = e->cfg.max_batch;
   const int64_t cld = (n_chunks + 31) / 32 * 32;  // row pitch of the chunk maxima: whole 128-byte lines
   if ((rc = tck_alloc(e, (void **)&e->k_cmax, sizeof(float) * (size_t)cld * mb))) return rc;
-  if ((rc = tck_pack_head_image(e, a.net_id, a.stats_head, 0, a.w))) return rc;
+  // inside an evaluation sweep (rec_eval_hold_params) the weight image and the bias operand blocks are packed once
+  const bool reuse = e->k_hold && e->k_img_epoch == e->param_epoch && e->k_img_net == a.net_id && e->k_img_head == a.stats_head &&
+                     e->k_sup_net == a.net_id && e->k_sup_head == a.stats_head;
+  if (!reuse && (rc = tck_pack_head_image(e, a.net_id, a.stats_head, 0, a.w))) return rc;
   tck::PackSrc hs = {};
   hs.n = 1; hs.p[0] = a.h; hs.w[0] = 1.f;
   if ((rc = tck_pack(e, hs, a.B, e->D, e->k_himg[0]))) return rc;
-  // flattened (session block, tile) unit space: one persistent CTA per SM, equal shares
-  const int total = n_sb * n_tiles;
-  int n_cta = e->sm_count < total ? e->sm_count : total;
-  const int per = cdiv(total, n_cta);
-  n_cta = cdiv(total, per);
-  int n_split = cdiv(n_tiles, per) + 1;  // records per row: the CTAs that can touch one session block
-  if (n_split > n_cta) n_split = n_cta;
   tck::FwdParams p = {};
   p.himg = e->k_himg[0]; p.wimg = e->k_wimg[0]; p.KB = KB; p.B = a.B; p.Vloc = e->Vloc; p.vocab_lo = e->cfg.vocab_lo; p.n_tiles = n_tiles;
   p.bias = np.head_b[a.stats_head]; p.target = a.target; p.part = e->part; p.part_stride = e->part_stride;
-  p.topk = a.topk; p.cmax = e->k_cmax; p.cmax_ld = cld; p.n_sb = n_sb; p.per = per;
-  if ((int64_t)n_split * a.B > ((int64_t)e->sm_count * 4 * 128 + 4 * (int64_t)e->cfg.max_batch))
-    REC_FAIL(e, REC_EINVAL, "chunk-maxima pass: %d records per row exceed the statistics workspace", n_split);
-  tck::fill_neutral_records_kernel<<<(int)cdiv64((int64_t)n_split * a.B, 256), 256, 0, e->stream>>>(e->part, (int64_t)n_split * a.B, e->part_stride);
-  REC_LAUNCH_CHECK(e);
-  if (e->timing) cudaEventRecord(e->ev[2], e->stream);  // slot 1 (evaluation head kernel): this ONE launch
-  if ((rc = tck::launch_tck<tck::HeadCmaxFlat>(e, dim3(n_cta), p))) return rc;
-  if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+  p.topk = a.topk; p.cmax = e->k_cmax; p.cmax_ld = cld; p.n_sb = n_sb;
+  const int64_t rec_cap = (int64_t)e->sm_count * 4 * 128 + 4 * (int64_t)e->cfg.max_batch;
+  const bool pair = KB == 1 && !getenv("REC_NO_CMAX_PAIR");
+  int n_split;
   if ((rc = tck_alloc(e, (void **)&e->k_chosen, sizeof(int) * (size_t)mb * tck::KC))) return rc;
-  tck::chunk_select_kernel<<<cdiv(a.B, 8), 256, 0, e->stream>>>(e->k_cmax, cld, n_chunks, a.B, e->k_chosen);
-  REC_LAUNCH_CHECK(e);
-  const size_t smem = 8 * (size_t)e->D * sizeof(float);
-  if (e->D == 64)
-    tck::chunk_score_kernel<16><<<cdiv(a.B, 8), 256, smem, e->stream>>>(e->k_chosen, np.head_w[a.stats_head], np.head_b[a.stats_head], a.h, a.B,
-                                                                       e->D, e->Vloc, e->cfg.vocab_lo, a.topk, e->row_ids, e->row_topv,
-                                                                       summary, e->part_stride);
-  else
+  if (pair) {
+    // grid = (vocabulary splits, session-block pairs); a split is a multiple of 8 tiles (level-2 groups are CTA-local)
+    constexpr int GROUP = tck::HeadCmaxPair::GROUP;
+    const int n_pairs = cdiv(n_sb, 2);
+    int splits = e->sm_count / n_pairs;
+    if (splits < 1) splits = 1;
+    while ((int64_t)splits * a.B > rec_cap && splits > 1) --splits;
+    const int per = cdiv(cdiv(n_tiles, splits), GROUP) * GROUP;
+    n_split = cdiv(n_tiles, per);
+    const int64_t cld2 = (2 * cdiv(n_tiles, GROUP) + 31) / 32 * 32;
+    if ((rc = tck_alloc(e, (void **)&e->k_cmax2, sizeof(float) * (size_t)cld2 * mb))) return rc;
+    if ((rc = tck_alloc(e, (void **)&e->k_bblk, (size_t)(n_tiles + 1) * 4096))) return rc;
+    if (!reuse) {
+      tck::pack_bias_blocks_kernel<<<n_tiles + 1, 128, 0, e->stream>>>(np.head_b[a.stats_head], e->Vloc, n_tiles, e->k_bblk);
+      REC_LAUNCH_CHECK(e);
+    }
+    p.per = per; p.cmax2 = e->k_cmax2; p.cmax2_ld = cld2; p.bblk = e->k_bblk;
+    if ((int64_t)n_split * a.B > rec_cap)
+      REC_FAIL(e, REC_EINVAL, "chunk-maxima pass: %d records per row exceed the statistics workspace", n_split);
+    if (e->timing) cudaEventRecord(e->ev[2], e->stream);  // slot 1 (evaluation head kernel): this ONE launch
+    static const int pv = getenv("REC_CMAX_EXP") ? atoi(getenv("REC_CMAX_EXP")) : 0;
+    static const char *trace_path = getenv("REC_CMAX_TRACE");  // debugging: clock64 phase stamps of one CTA -> file
+    static long long *d_trace = nullptr;
+    if (trace_path && !d_trace) cudaMalloc(&d_trace, sizeof(long long) * 8 * 64);
+    if (trace_path) { cudaMemsetAsync(d_trace, 0, sizeof(long long) * 8 * 64, e->stream); p.trace = d_trace; }
+    const dim3 grid(n_split, n_pairs);
+    switch (pv) {
+      case 4: rc = tck::launch_tck<tck::HeadCmaxPairT<4>>(e, grid, p); break;
+      case 10: rc = tck::launch_tck<tck::HeadCmaxPairT<10>>(e, grid, p); break;
+      case 11: rc = tck::launch_tck<tck::HeadCmaxPairT<11>>(e, grid, p); break;
+      case 30: rc = tck::launch_tck<tck::HeadCmaxPairT<30>>(e, grid, p); break;
+      default: rc = tck::launch_tck<tck::HeadCmaxPair>(e, grid, p); break;
+    }
+    if (rc) return rc;
+    if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+    if (trace_path) {
+      long long host[8 * 64];
+      cudaStreamSynchronize(e->stream);
+      cudaMemcpy(host, d_trace, sizeof(host), cudaMemcpyDeviceToHost);
+      if (FILE *f = fopen(trace_path, "wb")) { fwrite(host, sizeof(host), 1, f); fclose(f); }
+    }
+    tck::chunk_select2_kernel<<<cdiv(a.B, 8), 256, 0, e->stream>>>(e->k_cmax, cld, n_chunks, e->k_cmax2, cld2, n_tiles, a.B, e->k_chosen);
+    REC_LAUNCH_CHECK(e);
+    tck::chunk_score64_kernel<<<cdiv(a.B, 4), 128, 0, e->stream>>>(e->k_chosen, np.head_w[a.stats_head], np.head_b[a.stats_head], a.h, a.B,
+                                                                  e->Vloc, e->cfg.vocab_lo, a.topk, e->row_ids, e->row_topv, summary,
+                                                                  e->part_stride);
+  } else {
+    // flattened (session block, tile) unit space: one persistent CTA per SM, equal shares
+    const int total = n_sb * n_tiles;
+    int n_cta = e->sm_count < total ? e->sm_count : total;
+    const int per = cdiv(total, n_cta);
+    n_cta = cdiv(total, per);
+    n_split = cdiv(n_tiles, per) + 1;  // records per row: the CTAs that can touch one session block
+    if (n_split > n_cta) n_split = n_cta;
+    p.per = per;
+    if ((int64_t)n_split * a.B > rec_cap)
+      REC_FAIL(e, REC_EINVAL, "chunk-maxima pass: %d records per row exceed the statistics workspace", n_split);
+    tck::fill_neutral_records_kernel<<<(int)cdiv64((int64_t)n_split * a.B, 256), 256, 0, e->stream>>>(e->part, (int64_t)n_split * a.B, e->part_stride);
+    REC_LAUNCH_CHECK(e);
+    if (e->timing) cudaEventRecord(e->ev[2], e->stream);  // slot 1 (evaluation head kernel): this ONE launch
+    if ((rc = tck::launch_tck<tck::HeadCmaxFlat>(e, dim3(n_cta), p))) return rc;
+    if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+    tck::chunk_select_kernel<<<cdiv(a.B, 8), 256, 0, e->stream>>>(e->k_cmax, cld, n_chunks, a.B, e->k_chosen);
+    REC_LAUNCH_CHECK(e);
+    const size_t smem = 8 * (size_t)e->D * sizeof(float);
     tck::chunk_score_kernel<0><<<cdiv(a.B, 8), 256, smem, e->stream>>>(e->k_chosen, np.head_w[a.stats_head], np.head_b[a.stats_head], a.h, a.B,
                                                                       e->D, e->Vloc, e->cfg.vocab_lo, a.topk, e->row_ids, e->row_topv,
                                                                       summary, e->part_stride);
+  }
   REC_LAUNCH_CHECK(e);
+  e->k_img_epoch = e->param_epoch; e->k_img_net = a.net_id; e->k_img_head = a.stats_head;
   *n_split_out = n_split;
   e->st_approx = false;  // the ids / scores in row_ids / row_topv are exact
   e->st_kpub = 0;

@@ -118,6 +118,21 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
   return d;
 }
+// Un-swizzled K-major operand [rows][16 bf16] (one K = 16 slice, 32 bytes per row): core matrices of 8 rows x 16 bytes
+// are contiguous (128 B); the two K chunks of a row group sit `lbo` bytes apart, row groups `sbo` bytes apart
+// (layout type 0 = SWIZZLE_NONE).  Used for the 4 KB "bias as one more K slice" operands (nosw_off below).
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// byte offset of element (row, k < 16) in the un-swizzled [rows][16 bf16] operand described with lbo = 128, sbo = 256
+__device__ __host__ __forceinline__ uint32_t nosw_off(int row, int k) {
+  return (uint32_t)((row >> 3) * 256 + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
+}
 // K-major operand: MN = rows of the block (8-row groups 1024 B apart), K = 64 columns of the block
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t block_saddr, int k16) {
   return smem_desc(block_saddr + k16 * 32, 16, 1024);
@@ -159,6 +174,20 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, a cubic for 2^f on
+// [-0.5, 0.5] (relative error 8.1e-5: enough for the terms of a log-sum-exp whose SUM is needed to 1e-3), n added to the
+// exponent field by one integer multiply-add ((bits of 1.5 * 2^23 + n) << 23 == n << 23 mod 2^32).  x <= ~0; x below
+// -125 (incl. -inf of masked columns) is clamped: 2^-125 vanishes next to the row maximum's 2^0.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05533474684f, 0.2426231205f);  // minimax cubic (relative error), scratch fit: max 8.1e-5
+  p = fmaf(p, f, 0.6932122111f);
+  p = fmaf(p, f, 0.9999210238f);
+  return __int_as_float(__float_as_int(t) * 0x800000 + __float_as_int(p));
 }
 
 // ---- operand staging -----------------------------------------------------------------------------

@@ -4,6 +4,8 @@
 //   mode 0: C[128,128] = A[128,64] . B[128,64]^T        (A, B K-major)            -- logits GEMM
 //   mode 1: C[128, 64] = P[128k,128m]^T . Q[128k,64n]   (A, B MN-major)            -- dW GEMM
 //   mode 2: C[128, 64] = P[128m,128k] . R[128k,64n]     (A K-major, B MN-major)    -- dh GEMM
+//   mode 3 (+8: lbo / sbo swapped, must FAIL): mode 0 + bias[j] added by ONE more K = 16 MMA over two un-swizzled 4 KB
+//           operands (ones[128][16] . (b_hi, b_lo, b_lo2, 0...)[128][16]^T); bias = B + 128 * 64
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -17,6 +19,10 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float 
   constexpr int BLK = 128 * 128;  // bytes of one [128][64 bf16] block
   // operand A: up to two blocks (hi) + two blocks (lo); operand B likewise
   uint8_t *a_hi = sm, *a_lo = sm + 2 * BLK, *b_hi = sm + 4 * BLK, *b_lo = sm + 6 * BLK;
+  const int variant = mode >> 3;
+  mode &= 7;
+  const bool with_bias = mode == 3;
+  if (with_bias) mode = 0;
   const int a_cols = (mode == 0) ? 64 : 128;   // fp32 columns of the A source matrix (128 rows)
   const int b_rows = 128, b_cols = 64;
   // stage A: [128][a_cols] fp32 -> blocks of [128][64]
@@ -30,6 +36,22 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float 
     int row = e / (b_cols / 8), ch = e % (b_cols / 8);
     const float4 *src = reinterpret_cast<const float4 *>(B + (size_t)row * b_cols + ch * 8);
     tc::store_split8(b_hi, b_lo, row, ch, src[0], src[1]);
+  }
+  uint8_t *ones = sm + BLK, *bblk = sm + 3 * BLK;  // second blocks of the A regions (unused by mode 0)
+  if (with_bias) {
+    for (int e = tid; e < 4096 / 4; e += 128) { reinterpret_cast<uint32_t *>(ones)[e] = 0u; reinterpret_cast<uint32_t *>(bblk)[e] = 0u; }
+    __syncthreads();
+    const float b = B[128 * 64 + tid];
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(b);
+    const float r1 = b - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+    const __nv_bfloat16 hv[3] = {h0, h1, h2};
+    for (int k = 0; k < 3; ++k) {
+      *reinterpret_cast<__nv_bfloat16 *>(ones + tc::nosw_off(tid, k)) = one;
+      *reinterpret_cast<__nv_bfloat16 *>(bblk + tc::nosw_off(tid, k)) = hv[k];
+    }
   }
   if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
@@ -47,6 +69,10 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float 
       for (int pass = 0; pass < 3; ++pass) {
         uint32_t a = pass == 2 ? al : ah, b = pass == 1 ? bl : bh;
         for (int k = 0; k < 4; ++k) { tc::mma_bf16(tmem, tc::desc_kmajor(a, k), tc::desc_kmajor(b, k), id, acc); acc = true; }
+      }
+      if (with_bias) {
+        const uint32_t lbo = variant ? 256 : 128, sbo = variant ? 128 : 256;
+        tc::mma_bf16(tmem, tc::smem_desc_nosw(tc::smem_u32(ones), lbo, sbo), tc::smem_desc_nosw(tc::smem_u32(bblk), lbo, sbo), id, true);
       }
     } else if (mode == 1) {
       const uint32_t id = tc::instr_desc(128, 64, 1, 1);
@@ -83,7 +109,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float 
 }
 
 extern "C" int rec_debug_tc_gemm(int mode, const float *A, const float *B, float *C, void *stream) {
-  if (mode < 0 || mode > 2 || !A || !B || !C) return REC_EINVAL;
+  if (mode < 0 || (mode > 3 && mode != 11) || !A || !B || !C) return REC_EINVAL;
   const size_t smem = 8 * 128 * 128 + 1024;
   cudaError_t st = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (st != cudaSuccess) return REC_ECUDA;

@@ -2,6 +2,7 @@
 // format): packing kernels, the warp-specialised kernel template and its launcher.  Included by heads_tck.cu (wide
 // heads) and gru_tc.cu (GRU trunk for E, H >= 128).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -141,9 +142,32 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 //   RESIDENT_BYTES              > 0: an operand that is the same for every unit (the recurrent weights of this CTA's
 //                               hidden units) is loaded ONCE by load_resident(p, smem, bar) and stays in shared memory;
 //                               mma() receives its address
+// Optional clock64 phase stamps: an OP may define  static void trace(const Params &, int kind, int i)  (kinds: 0 issuer
+// has its accumulator, 1 issuer has its stage, 2 MMAs issued, 3 / 4 epilogue warp 0 starts / ends a unit, 5 loader has
+// a free stage, 6 / 7 the last epilogue warp).  OPs without it compile to nothing.
+template <class OP, class = void>
+struct op_has_trace : std::false_type {};
 template <class OP>
-__global__ void __launch_bounds__(OP::EPI_WARPS * 32 + 64, 1) tck_kernel(const typename OP::Params p) {
-  constexpr int EPI_WARPS = OP::EPI_WARPS;  // 8 (default) or 16 epilogue warps + issuer warp + loader warp
+struct op_has_trace<OP, std::void_t<decltype(&OP::trace)>> : std::true_type {};
+template <class OP>
+__device__ __forceinline__ void op_trace(const typename OP::Params &p, int kind, int i) {
+  if constexpr (op_has_trace<OP>::value) OP::trace(p, kind, i);
+}
+
+// Optional  static constexpr int ISSUERS = 2:  two MMA-issuer warps take alternate units (= alternate accumulators).  The
+// issuing thread blocks in tcgen05.mma for about as long as the tensor pipe is busy and then spends ~1000 cycles per unit
+// in commit / mbarrier-wait / fence round trips (clock64 stamps of HeadCmaxPair: 26 MMAs = 1970 cycles issuing + 1080
+// cycles of synchronisation during which the tensor pipe idles); with two issuers one warp's round trips overlap the
+// other's MMAs.  Units are independent (different accumulators, per-thread tcgen05.commit): no ordering between them.
+template <class OP, class = void>
+struct op_issuers : std::integral_constant<int, 1> {};
+template <class OP>
+struct op_issuers<OP, std::void_t<decltype(OP::ISSUERS)>> : std::integral_constant<int, OP::ISSUERS> {};
+
+template <class OP>
+__global__ void __launch_bounds__(OP::EPI_WARPS * 32 + 32 + 32 * op_issuers<OP>::value, 1) tck_kernel(const typename OP::Params p) {
+  constexpr int EPI_WARPS = OP::EPI_WARPS;  // 8 (default) or 16 epilogue warps + issuer warp(s) + loader warp
+  constexpr int ISSUERS = op_issuers<OP>::value;
   extern __shared__ uint8_t raw[];
   uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
   __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2], stepbar, resbar;
@@ -168,7 +192,7 @@ __global__ void __launch_bounds__(OP::EPI_WARPS * 32 + 64, 1) tck_kernel(const t
   uint8_t *resident = sm + OP::STAGES * OP::STAGE_BYTES;
   uint8_t *extra = resident + OP::RESIDENT_BYTES;
 
-  if (warp == EPI_WARPS + 1) {
+  if (warp == EPI_WARPS + ISSUERS) {
     // ---- TMA loader ----
     if (lane == 0) {
       int s = 0, i = 0;
@@ -191,30 +215,41 @@ __global__ void __launch_bounds__(OP::EPI_WARPS * 32 + 64, 1) tck_kernel(const t
         } else {
           for (int ks = 0; ks < nk; ++ks) {
             if (round > 0) tc::mbar_wait(&empty[s], (round - 1) & 1);  // the MMAs that read this stage are complete
+            op_trace<OP>(p, 5, i);
             OP::load(p, u, ks, sm + s * OP::STAGE_BYTES, &full[s]);
             if (++s == OP::STAGES) { s = 0; ++round; }
           }
         }
       }
     }
-  } else if (warp == EPI_WARPS) {
-    // ---- MMA issuer ----
+  } else if (warp >= EPI_WARPS) {
+    // ---- MMA issuer(s) ----
     int s = 0, i = 0;
     uint32_t round = 0;
     for (int u = u_lo; u < u_hi; ++u, ++i) {
       const int b = i & 1;
-      if (i >= 2) tc::mbar_wait(&tempty[b], ((i - 2) >> 1) & 1);  // the epilogue has read this accumulator
-      tc::tc_fence_after();
       const int nk = OP::k_steps(p, u);
-      if constexpr (OP::RESIDENT_BYTES > 0) { if (i == 0) tc::mbar_wait(&resbar, 0); }
+      if (ISSUERS > 1 && (i % ISSUERS) != warp - EPI_WARPS) {  // the other issuer's unit: only track the stage ring
+        for (int ks = 0; ks < nk; ++ks) if (++s == OP::STAGES) { s = 0; ++round; }
+        continue;
+      }
+      if constexpr (OP::RESIDENT_BYTES > 0) { if (i < ISSUERS) tc::mbar_wait(&resbar, 0); }
       for (int ks = 0; ks < nk; ++ks) {
+        // the stage has usually landed long ago: its wait (an mbarrier round trip of ~150 cycles even when satisfied)
+        // comes BEFORE the wait for the accumulator, which is the one on the critical path
         tc::mbar_wait(&full[s], round & 1);
+        if (ks == 0) {
+          if (lane == 0) op_trace<OP>(p, 0, i);
+          if (i >= 2) tc::mbar_wait(&tempty[b], ((i - 2) >> 1) & 1);  // the epilogue has read this accumulator
+        }
         tc::tc_fence_after();
         if (lane == 0) {
+          op_trace<OP>(p, 1, i);
           if constexpr (OP::RESIDENT_BYTES > 0)
             OP::mma(p, u, ks, tc::smem_u32(sm + s * OP::STAGE_BYTES), tc::smem_u32(resident), tmem + (uint32_t)(b * OP::ACC_COLS), ks == 0);
           else
             OP::mma(p, u, ks, tc::smem_u32(sm + s * OP::STAGE_BYTES), tmem + (uint32_t)(b * OP::ACC_COLS), ks == 0);
+          op_trace<OP>(p, 2, i);
           tc::mma_commit(&empty[s]);
         }
         __syncwarp();
@@ -231,7 +266,11 @@ __global__ void __launch_bounds__(OP::EPI_WARPS * 32 + 64, 1) tck_kernel(const t
       const int b = i & 1;
       tc::mbar_wait(&tfull[b], (i >> 1) & 1);
       tc::tc_fence_after();
+      if (tid == 0) op_trace<OP>(p, 3, i);
+      if (tid == EPI_WARPS * 32 - 32) op_trace<OP>(p, 6, i);
       epi.tile(p, u, i, tmem + (uint32_t)(b * OP::ACC_COLS));
+      if (tid == 0) op_trace<OP>(p, 4, i);
+      if (tid == EPI_WARPS * 32 - 32) op_trace<OP>(p, 7, i);
       tc::tc_fence_before();
       if (OP::CLUSTERED) __threadfence();
       __syncwarp();
@@ -255,6 +294,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 template <class OP>
 static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
   const size_t smem = 1024 + (size_t)OP::STAGES * OP::STAGE_BYTES + OP::RESIDENT_BYTES + OP::EXTRA_BYTES;
+  constexpr int NTHREADS = OP::EPI_WARPS * 32 + 32 + 32 * op_issuers<OP>::value;
   static bool attr_set[REC_MAX_DEVICES] = {};
   if (!attr_set[e->dev]) {
     REC_CUDA(e, cudaFuncSetAttribute(tck_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -262,14 +302,14 @@ static int launch_tck(rec_engine *e, dim3 grid, const typename OP::Params &p) {
   }
   if (OP::CLUSTERED) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(OP::EPI_WARPS * 32 + 64); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+    cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = grid.x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     REC_CUDA(e, cudaLaunchKernelEx(&cfg, tck_kernel<OP>, p));
   } else {
-    tck_kernel<OP><<<grid, OP::EPI_WARPS * 32 + 64, smem, e->stream>>>(p);
+    tck_kernel<OP><<<grid, NTHREADS, smem, e->stream>>>(p);
   }
   e->launches++;
   if (e->tl_on) rec_timeline_record(e, OP::NAME, 0);

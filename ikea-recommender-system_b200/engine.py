@@ -227,6 +227,10 @@ class Engine:
         mb, L = self.cfg["max_batch"], self.cfg["state_size"]
         return mb * (2 * L + 3) * 8 + mb * 5
 
+    def eval_hold_params(self, on: bool):
+        """Evaluation sweep: parameters are frozen between on=True and on=False (operand images are reused)."""
+        N.check(self.lib, self.handle, self.lib.rec_eval_hold_params(self.handle, 1 if on else 0), "rec_eval_hold_params")
+
     def eval_batch(self, net_id, batch: N.RecBatch, opts: N.RecEvalOpts, acc: N.RecEvalAccum, topk_ids=None,
                    topk_scores=None):
         self.ensure_batch(batch.B)

@@ -148,14 +148,22 @@ def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, 
                           unpopular_actions_set, input_tokenizer, output_tokenizer)
     acc = EvalAccumulators(dev, model.action_dim)
     n_total, n_batches = 0, 0
-    for s, a, s_len in evaluation_data_loader:
-        B = int(s.shape[0])
-        ds, dl = model._dev_inputs(s, s_len)
-        da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-        eng = model._ready(B)
-        _eval_one_batch(model, eng, eng._batch(B, ds, da, dl), o, acc, kmax)
-        n_total += B
-        n_batches += 1
+    held = None  # the engine that was told "parameters are frozen for this sweep" (model.eval(): nothing trains here)
+    try:
+        for s, a, s_len in evaluation_data_loader:
+            B = int(s.shape[0])
+            ds, dl = model._dev_inputs(s, s_len)
+            da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+            eng = model._ready(B)
+            if (eng, eng.handle) != held:  # first batch, or the engine was re-created for a larger batch
+                eng.eval_hold_params(True)
+                held = (eng, eng.handle)
+            _eval_one_batch(model, eng, eng._batch(B, ds, da, dl), o, acc, kmax)
+            n_total += B
+            n_batches += 1
+    finally:
+        if held is not None and held[0].handle == held[1]:
+            held[0].eval_hold_params(False)
     r = acc.read()
     nk = len(topk_hr_ndcg)
     hr = r["hits"][:nk] / n_total

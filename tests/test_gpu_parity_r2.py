@@ -595,3 +595,66 @@ def test_sarm_against_live_oracle(pkg, V, H, B):
         assert_close(got_l, want_l, rtol=RTOL, atol=1e-5, what=f"step {i} (sup, mean q) losses")
     assert_state_close(t.network.state_dict(), ref.network.state_dict(), rtol=RTOL, atol=2e-5,
                        outlier_frac=1e-3, outlier_atol=0.02 * 0.005 * 3)
+
+
+# ------------------------------------------------- evaluation sweep: operand images held across batches, not across updates
+def test_eval_hold_params_reuses_images_only_while_parameters_are_frozen(pkg):
+    """rec_eval_hold_params lets the chunk-maxima path (B >= 1024, V >= 32768) keep the packed head image across the
+    batches of a sweep.  (1) held and un-held calls agree bit for bit; (2) a training entry point inside a hold, and an
+    in-place change of the weights between two evaluate() sweeps, are both picked up (ids follow the NEW weights)."""
+    V, B = 40_000, 1100
+    torch.manual_seed(11)
+    tr = pkg.SQN_trainer(hidden_dim=64, embedding_dim=64, train_pad_embed=True, use_packed_seq=True,
+                         learning_rate=0.05, item_num=V, state_size=10, action_dim=V, gamma=0.5, gru_layers=1, device=DEV)
+    tr.send_to_device()
+    net = tr.DQN_1
+    rows = _syn().make_replay_rows_fast(B, V, 10, seed=2)
+    batch = _syn().as_torch_batch(rows, 0, B)
+    s, a, ln = batch[0], batch[1], batch[4]
+    from ikea_recommender_system_b200 import _native as N_
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    o = N_.RecEvalOpts()
+    o.head_idx, o.n_k, o.n_cov = 0, 1, 0
+    o.ks[0] = 20
+
+    def topk_now(hold):
+        eng = net._ready(B)
+        acc = EvalAccumulators(torch.device(DEV), V)
+        ids = torch.empty(B, 20, dtype=torch.int32, device=DEV)
+        sc = torch.empty(B, 20, dtype=torch.float32, device=DEV)
+        ds, dl = net._dev_inputs(s, ln)
+        if hold is not None:
+            eng.eval_hold_params(hold)
+        eng.eval_batch(net._net_id, eng._batch(B, ds, a.to(DEV), dl), o, acc.struct, topk_ids=ids, topk_scores=sc)
+        torch.cuda.synchronize()
+        return ids.cpu(), sc.cpu(), float(acc.read()["loss_sum"])
+
+    plain = topk_now(None)
+    held1 = topk_now(True)    # packs
+    held2 = topk_now(None)    # reuses the image
+    for got in (held1, held2):
+        assert torch.equal(got[0], plain[0]) and torch.equal(got[1], plain[1]) and got[2] == plain[2]
+    # a training step inside the hold: both twins may move; the next evaluation must see the new weights
+    random.seed(0)
+    for _ in range(3):
+        tr.train_step(*[t for t in batch[:7]])
+    after_held = topk_now(None)           # hold still on, epoch bumped by the train steps -> repacked
+    net._ready(B).eval_hold_params(False)
+    after_plain = topk_now(None)
+    assert torch.equal(after_held[0], after_plain[0]) and torch.equal(after_held[1], after_plain[1])
+    assert not torch.equal(after_plain[1], plain[1]), "the train steps did not change the scores: test is vacuous"
+    # in-place change by the caller BETWEEN two evaluate() sweeps (evaluate() drops its hold when it returns)
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 8, generator=torch.Generator().manual_seed(1)), freeze=True)
+    kw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1, topk_to_consider_nov=1,
+              topk_to_consider_cov=[1, 5], novelty_rew_signal=1)
+    ce = torch.nn.CrossEntropyLoss()
+    first = pkg.evaluate([(s, a, ln)] * 2, net, DEV, ce, "end", e_div, unpop, **kw)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            if p_.dim() == 2 and p_.shape[0] == V:  # the heads
+                p_.mul_(-1.0)
+    second = pkg.evaluate([(s, a, ln)] * 2, net, DEV, ce, "end", e_div, unpop, **kw)
+    again = topk_now(None)
+    assert not torch.equal(again[0], after_plain[0]), "flipping the head weights did not change the top-k ids"
+    assert float(first[0]) != float(second[0])
