@@ -1302,7 +1302,8 @@ int tck_prepack_heads(rec_engine *e, int net_id, int n_arg, const float *w) {
 // launch_head_merge(topk = 0)) and row_ids / row_topv (+ the candidate slots of `summary`).
 bool tck_chunk_topk_supported(const rec_engine *e, const HeadStatsArgs &a) {
   static const int off = getenv("REC_NO_CHUNK_TOPK") ? 1 : 0;
-  return !off && tck_topk_supported(e, a) && a.B >= 1024 && e->Vloc >= 32768;
+  static const int min_b = getenv("REC_CHUNK_MIN_B") ? atoi(getenv("REC_CHUNK_MIN_B")) : 1024;
+  return !off && tck_topk_supported(e, a) && a.B >= min_b && e->Vloc >= 32768;
 }
 
 int launch_head_topk_chunks(rec_engine *e, const HeadStatsArgs &a, int *n_split_out, float *summary) {

@@ -40,16 +40,19 @@ def _as_div_table(diversity_embedding, device):
     return _cache[key][1]
 
 
-def _unpopular_bitmap(unpopular_actions_set, action_dim, device):
-    """python set -> uint8[V] membership table on the device (novelty.py:5-9 `in unpopular_items`)."""
+def _unpopular_bitmap(unpopular_actions_set, action_dim, device, packed=False):
+    """python set -> uint8[V] membership table on the device (novelty.py:5-9 `in unpopular_items`); packed=True: the
+    same set as uint32 bit words on the host (bit i of word w = action 32 w + i), the layout of the coverage bitmaps."""
     key = ("unpop", id(unpopular_actions_set), len(unpopular_actions_set), action_dim, str(device))
     if key not in _cache:
         bm = np.zeros(action_dim, dtype=np.uint8)
         ids = np.fromiter((int(i) for i in unpopular_actions_set), dtype=np.int64, count=len(unpopular_actions_set))
         ids = ids[(ids >= 0) & (ids < action_dim)]
         bm[ids] = 1
-        _cache[key] = (unpopular_actions_set, torch.from_numpy(bm).to(device))
-    return _cache[key][1]
+        bits = np.packbits(bm, bitorder="little")
+        words = np.concatenate([bits, np.zeros((-len(bits)) % 4, dtype=np.uint8)]).view(np.uint32)
+        _cache[key] = (unpopular_actions_set, torch.from_numpy(bm).to(device), words)
+    return _cache[key][2 if packed else 1]
 
 
 def _token_lut(input_tokenizer, output_tokenizer, action_dim, device):
@@ -101,11 +104,16 @@ def get_preds(states, true_len, model, head_idx):
     return out[head_idx] if isinstance(out, tuple) else out
 
 
-def _coverage(cov_bits, topk_cov, unpop_bitmap_np, num_actions, n_unpop):
+def _coverage(cov_bits, topk_cov, unpop_words, num_actions, n_unpop):
+    """{k: (share of the unpopular actions covered, share of all actions covered)} (coverage.py:24-53) from the device
+    bitmaps: population counts on the packed words (unpacking 4 x 1 M bits cost 5 ms per evaluate() at 1 M items)."""
     res = {}
+    n_words = (num_actions + 31) // 32
+    tail = np.uint32(0xFFFFFFFF >> ((32 - num_actions % 32) % 32))  # bits of the last word that are actions
     for i, k in enumerate(topk_cov):
-        bits = np.unpackbits(cov_bits[i].view(np.uint8), bitorder="little")[:num_actions]
-        res[k] = (int((bits & unpop_bitmap_np).sum()) / n_unpop, int(bits.sum()) / num_actions)
+        w = cov_bits[i][:n_words].copy()
+        w[-1] &= tail
+        res[k] = (int(np.bitwise_count(w & unpop_words[:n_words]).sum()) / n_unpop, int(np.bitwise_count(w).sum()) / num_actions)
     return res
 
 
@@ -172,8 +180,8 @@ def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, 
     loss = torch.tensor(r["loss_sum"] / n_batches, dtype=torch.float32, device=dev)
     avg_div = torch.tensor(r["div_sum"] / n_total, dtype=torch.float32, device=dev)
     avg_nov = np.float64(r["nov_sum"] / n_total)
-    unpop_np = keep[1].cpu().numpy()
-    cov = _coverage(r["cov_bits"], topk_to_consider_cov, unpop_np, model.action_dim, len(unpopular_actions_set))
+    unpop_words = _unpopular_bitmap(unpopular_actions_set, model.action_dim, dev, packed=True)
+    cov = _coverage(r["cov_bits"], topk_to_consider_cov, unpop_words, model.action_dim, len(unpopular_actions_set))
     return loss, hr, ndcg, cov, avg_div, avg_nov, reps
 
 

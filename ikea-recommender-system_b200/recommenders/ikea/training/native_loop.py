@@ -96,7 +96,7 @@ def train_native(trainer, train_buffer, val_set, epochs, batch_size, val_batch_s
         best_model_metric = f"Val_HR@{max(topk_hr_ndcg)}"
     opts, kmax, keep = EP._opts(m1, dev, head_idx, topk_hr_ndcg, topk_div, topk_nov, topk_cov, nov_rew_sig, padding_pos,
                                 diversity_embedding, unpopular_actions_set, input_tokenizer, output_tokenizer)
-    unpop_np = keep[1].cpu().numpy()
+    unpop_np = EP._unpopular_bitmap(unpopular_actions_set, m1.action_dim, dev, packed=True)  # packed bit words
     nk = len(topk_hr_ndcg)
     history, best, log_counter = [], 0.0, 0
 

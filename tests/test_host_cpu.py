@@ -274,3 +274,22 @@ def test_bench_algorithmic_bytes_follow_survey_8d():
     assert ab["sup_stats"] == 4 * (H + 1) * V and ab["greedy_stats"] == 3 * ab["sup_stats"]
     big = bench.algorithmic_bytes(bench.WORKLOADS["cfg4"])
     assert 9.0e9 < big["step"] < 9.1e9  # 9.06 GB at 1 M items
+
+
+def test_coverage_from_packed_bitmaps_equals_the_reference_counts(pkg):
+    """`_coverage` counts bits of the device bitmaps with population counts on packed words; the result must equal the
+    reference's set arithmetic (evaluate/coverage.py:24-53) -- here restated on unpacked bits -- including catalogue
+    sizes that are not a multiple of 32 and stray bits beyond the last action."""
+    from ikea_recommender_system_b200.recommenders.evaluate import eval_protocol as EP
+    for n in (37, 1024, 70852, 1_000_001):
+        words = (n + 31) // 32
+        rng = np.random.default_rng(n)
+        cov = rng.integers(0, 2 ** 32, size=(4, words), dtype=np.uint32)
+        unpop_set = set(int(i) for i in np.nonzero(rng.random(n) < 0.3)[0])
+        packed = EP._unpopular_bitmap(unpop_set, n, "cpu", packed=True)
+        table = EP._unpopular_bitmap(unpop_set, n, "cpu").numpy()
+        got = EP._coverage(cov, [1, 5, 10, 20], packed, n, len(unpop_set))
+        for i, k in enumerate([1, 5, 10, 20]):
+            covered = set(int(j) for j in np.nonzero(np.unpackbits(cov[i].view(np.uint8), bitorder="little")[:n])[0])
+            assert got[k] == (len(covered & unpop_set) / len(unpop_set), len(covered) / n), (n, k)
+        assert table.sum() == len(unpop_set)
