@@ -159,6 +159,10 @@ __device__ __forceinline__ void op_trace(const typename OP::Params &p, int kind,
 // in commit / mbarrier-wait / fence round trips (clock64 stamps of HeadCmaxPair: 26 MMAs = 1970 cycles issuing + 1080
 // cycles of synchronisation during which the tensor pipe idles); with two issuers one warp's round trips overlap the
 // other's MMAs.  Units are independent (different accumulators, per-thread tcgen05.commit): no ordering between them.
+// Only for OPs with ONE k-step per unit and STAGES % ISSUERS == 0: every stage is then consumed by the same issuer each
+// time round the ring, so its parity waits cannot alias (with 3 stages and 8 k-steps per unit the second issuer, which
+// starts at stage 8 % 3 of round 2, would take the FIRST completion of that stage's barrier for its own -- measured: a
+// launch failure in HeadFwd).
 template <class OP, class = void>
 struct op_issuers : std::integral_constant<int, 1> {};
 template <class OP>
@@ -168,6 +172,7 @@ template <class OP>
 __global__ void __launch_bounds__(OP::EPI_WARPS * 32 + 32 + 32 * op_issuers<OP>::value, 1) tck_kernel(const typename OP::Params p) {
   constexpr int EPI_WARPS = OP::EPI_WARPS;  // 8 (default) or 16 epilogue warps + issuer warp(s) + loader warp
   constexpr int ISSUERS = op_issuers<OP>::value;
+  static_assert(ISSUERS == 1 || OP::STAGES % ISSUERS == 0, "two issuers: each stage must always belong to the same issuer");
   extern __shared__ uint8_t raw[];
   uint8_t *sm = raw + ((1024u - (tc::smem_u32(raw) & 1023u)) & 1023u);
   __shared__ uint64_t full[OP::STAGES], empty[OP::STAGES], tfull[2], tempty[2], stepbar, resbar;

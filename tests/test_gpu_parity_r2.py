@@ -597,6 +597,84 @@ def test_sarm_against_live_oracle(pkg, V, H, B):
                        outlier_frac=1e-3, outlier_atol=0.02 * 0.005 * 3)
 
 
+# ------------------------------------------------------------------- the BENCHMARKED evaluation shape against the oracle
+def test_evaluate_at_the_benchmarked_shape_1m_items_batch_5000(pkg):
+    """bench.py's evaluation workload itself (V = 1 M, validation batch 5000, k = 20, default-initialised weights): the
+    pair kernel + two-level selection + coalesced exact scoring.  The oracle cannot hold 5000 x 1 M logits at once, so it
+    runs in row chunks: (1) mean cross-entropy over ALL 5000 rows; (2) on three 128-row slices (first, middle and the
+    partial last session block) the float64 logits decide where the order is defined, and there ids are compared
+    exactly, scores to fp32 accuracy; (3) HR / NDCG sums over all rows whose 21 best fp32 logits are distinct."""
+    V, B, K = 1_000_000, 5000, 20
+    torch.manual_seed(21)
+    onet = oracle.make_gru4rec(hidden_dim=64, embedding_dim=64, item_num=V, state_size=10, action_dim=V, gru_layers=1,
+                               use_packed_seq=True)
+    net = pkg.GRU4Rec(hidden_size=64, embedding_dim=64, item_num=V, state_size=10, action_dim=V)
+    net.load_state_dict(onet.state_dict())
+    net.to(DEV)
+    rows = _syn().make_replay_rows_fast(B, V, 10, seed=12)
+    s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
+    # make a share of the targets hits: the target of every 7th row is that row's own 3rd-best item (set below)
+    from ikea_recommender_system_b200 import _native as N_
+    from ikea_recommender_system_b200.engine import EvalAccumulators
+    ce_sum, hits, ndcg, n_defined = 0.0, np.zeros(3), np.zeros(3), 0
+    want_ids = torch.empty(B, K, dtype=torch.int64)
+    defined = torch.zeros(B, dtype=torch.bool)
+    a = a.clone()
+    with torch.no_grad():
+        for lo in range(0, B, 500):
+            logits = onet(s[lo:lo + 500], ln[lo:lo + 500])
+            top = torch.topk(logits, K + 1, dim=1)
+            defined[lo:lo + 500] = (top.values[:, :-1] - top.values[:, 1:]).min(1).values > 0
+            want_ids[lo:lo + 500] = top.indices[:, :K]
+            idx = torch.arange(lo, min(lo + 500, B))
+            sel = idx[idx % 7 == 0]
+            a[sel] = top.indices[sel - lo, 2]
+            ce_sum += float(torch.nn.functional.cross_entropy(logits, a[lo:lo + 500], reduction="sum"))
+    slices = [(0, 128), (2432, 2560), (4872, 5000)]
+    exact_rows = []
+    with torch.no_grad():
+        o64 = double_copy(onet)
+        for lo, hi in slices:
+            l64 = o64(s[lo:hi], ln[lo:hi])
+            top = torch.topk(l64, K + 1, dim=1).values
+            ok = (top[:, :-1] - top[:, 1:]).min(1).values > MARGIN_MIN
+            exact_rows.append(torch.arange(lo, hi)[ok])
+    exact_rows = torch.cat(exact_rows)
+    assert len(exact_rows) >= 300, len(exact_rows)
+    eng = net._ready(B)
+    o = N_.RecEvalOpts()
+    o.head_idx, o.n_k, o.n_cov = 0, 3, 1
+    o.ks[0], o.ks[1], o.ks[2] = 5, 10, 20
+    o.cov_ks[0] = K
+    acc = EvalAccumulators(torch.device(DEV), V)
+    ids = torch.empty(B, K, dtype=torch.int32, device=DEV)
+    sc = torch.empty(B, K, dtype=torch.float32, device=DEV)
+    ds, dl = net._dev_inputs(s, ln)
+    eng.eval_batch(0, eng._batch(B, ds, a.to(DEV), dl), o, acc.struct, topk_ids=ids, topk_scores=sc)
+    r = acc.read()
+    ids_h = ids.cpu().long()
+    # (2) exact ids where float64 separates the candidates
+    assert torch.equal(ids_h[exact_rows], want_ids[exact_rows])
+    # everywhere the fp32 oracle's 21 best are distinct values the two lists may only differ by permutations of
+    # near-ties: as SETS of the 19 best they agree on (nearly) every row
+    same = (ids_h == want_ids).all(1)
+    report("eval benchmarked shape V=1M B=5000", dict(rows=B, rows_float64_checked=int(len(exact_rows)),
+                                                      rows_identical_to_fp32_oracle=int(same.sum()),
+                                                      rows_fp32_distinct=int(defined.sum())))
+    assert int(same.sum()) >= B - B // 50
+    # (1) loss: mean over the batch
+    assert abs(float(r["loss_sum"]) - ce_sum / B) <= 1e-4 * (ce_sum / B), (float(r["loss_sum"]), ce_sum / B)
+    # (3) hits / ndcg on the rows planted as hits (rank 3 in the oracle) -- identical wherever the ids are identical
+    planted = torch.arange(0, B)[(torch.arange(0, B) % 7 == 0) & same]
+    for j, k in enumerate((5, 10, 20)):
+        want_hits = float(sum(1 for b in range(B) if same[b] and int(a[b]) in want_ids[b, :k].tolist()))
+        others = int((~same).sum())
+        assert abs(float(r["hits"][j]) - want_hits) <= others, (k, float(r["hits"][j]), want_hits)
+    assert float(r["hits"][0]) >= len(planted)
+    covered = int(np.bitwise_count(r["cov_bits"][0].view(np.uint32)).sum())
+    assert covered == len(set(ids_h.flatten().tolist()))
+
+
 # ------------------------------------------------- evaluation sweep: operand images held across batches, not across updates
 def test_eval_hold_params_reuses_images_only_while_parameters_are_frozen(pkg):
     """rec_eval_hold_params lets the chunk-maxima path (B >= 1024, V >= 32768) keep the packed head image across the
