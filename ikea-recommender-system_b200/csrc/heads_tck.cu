@@ -986,15 +986,18 @@ __global__ void __launch_bounds__(128) chunk_score64_kernel(const int *__restric
     }
     sc[r] = my;
   }
-  float pv = 3.402823466e+38f;
-  int pi = -1;
+  // top-k of the KC x 32 exact scores by (score desc, id asc).  Every lane keeps the best of ITS candidates; a round is a
+  // warp argmax over the 32 lane bests, and only the winning lane rescans its registers (ids are unique: a column is
+  // scored once).  (Rescanning all KC candidates in every lane and round was half of this kernel's instructions.)
+  float lbv = REC_NEG_INF;
+  int lbi = 0x7fffffff;
+#pragma unroll
+  for (int r = 0; r < KC; ++r)
+    if (ids[r] != 0x7fffffff && better(sc[r], ids[r], lbv, lbi)) { lbv = sc[r]; lbi = ids[r]; }
   float *sm = summary ? summary + (int64_t)row * part_stride : nullptr;
   for (int k = 0; k < topk; ++k) {
-    float bv = REC_NEG_INF;
-    int bi = 0x7fffffff;
-#pragma unroll
-    for (int r = 0; r < KC; ++r)
-      if (ids[r] != 0x7fffffff && better(pv, pi, sc[r], ids[r]) && better(sc[r], ids[r], bv, bi)) { bv = sc[r]; bi = ids[r]; }
+    float bv = lbv;
+    int bi = lbi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -1005,7 +1008,14 @@ __global__ void __launch_bounds__(128) chunk_score64_kernel(const int *__restric
       row_ids[(int64_t)row * REC_MAX_TOPK + k] = bi; row_topv[(int64_t)row * REC_MAX_TOPK + k] = bv;
       if (sm) { sm[TOPK_OFF + k] = bv; sm[TOPK_OFF + REC_MAX_TOPK + k] = __int_as_float(bi); }
     }
-    pv = bv; pi = bi;
+    if (bi == lbi && bi != 0x7fffffff) {  // this lane held the winner: retire it, find the lane's next best
+      lbv = REC_NEG_INF; lbi = 0x7fffffff;
+#pragma unroll
+      for (int r = 0; r < KC; ++r) {
+        if (ids[r] == bi) ids[r] = 0x7fffffff;
+        if (ids[r] != 0x7fffffff && better(sc[r], ids[r], lbv, lbi)) { lbv = sc[r]; lbi = ids[r]; }
+      }
+    }
   }
 }
 
