@@ -465,6 +465,9 @@ def eval_bench(args, wl, local, with_cpu):
     flops_alg = 2.0 * wl["H"] * N * B           # 2*D*V per session
     _, _, pk = _peaks()
     peak_tf = pk.get("bf16_tflops_sustained", 1391.5)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    tj, eval_traffic_src = _traffic("eval" if N > 500_000 else "eval70k")
+    eval_traffic = (tj or {}).get("head_kernel")
     line = {"metric": EVAL_METRIC, "value": value, "unit": "sessions/s", "n_gpus": 1,
             "steps": reps * n_batches, "warmup": args.warmup, "ms_per_step": ms / (reps * n_batches),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32 accumulate, fp32 re-score of the top-k candidates)",
@@ -473,13 +476,21 @@ def eval_bench(args, wl, local, with_cpu):
             "e2e": {"value": sessions / e2e_s, "unit": "sessions/s", "h2d_bytes_per_step": B * (L + 2) * 8,
                     "d2h_bytes_per_step": 8 * 27 + 4 * 8 * ((N + 31) // 32) // max(1, n_batches)},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "tck_kernel<HeadCmaxFlat> (logits + online softmax + chunk maxima per tile; exact top-k from the best chunks in chunk_select / chunk_score) -- head_stats_tc_kernel / HeadTopk below 1024 sessions or 32768 items",
+            "roofline": {"bound": "tensor", "kernel": "tck_kernel<HeadCmaxPair> (two session blocks per CTA: logits + bias on the tensor cores, online "
+                                   "softmax + chunk maxima per tile; exact top-k from the best chunks in chunk_select2 / chunk_score64) -- "
+                                   "HeadCmaxFlat for D > 64, head_stats_tc_kernel / HeadTopk below 1024 sessions or 32768 items",
                          "achieved": flops_alg / (head_ms / 1e3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": flops_alg / (head_ms / 1e3) / 1e12 / peak_tf,
-                         "traffic": None, "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / (reps * n_batches)),
+                         "traffic": eval_traffic, "traffic_source": eval_traffic_src,
+                         "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / (reps * n_batches)),
                          "algorithmic_flops_per_launch": flops_alg,
-                         "note": "algorithmic 2*D*V FLOP per session (executed: 3 bf16 passes); the epilogue (one ex2 + max per logit on "
-                                 "the CUDA cores: ~8 instructions per logit, issue- and power-bound) is the limiter at D = 64"},
+                         "executed_flops_per_launch": 3.25 * flops_alg,
+                         "executed_frac_of_peak": 3.25 * flops_alg / (head_ms / 1e3) / 1e12 / peak_tf,
+                         "sfu_floor_ms": 128.0 * ((B + 127) // 128) * 128.0 * ((N + 127) // 128) / (sm_count * 16.0) / (clk.get("sm_mhz") or 1965.0) / 1e3,
+                         "note": "frac = ALGORITHMIC 2*D*V FLOP per session against the measured bf16 peak; the kernel executes 3.25x that "
+                                 "(bf16 hi/lo: three passes for fp32-class logits + the bias as one more K = 16 slice), executed_frac_of_peak; "
+                                 "sfu_floor_ms = one MUFU.EX2 per logit (the cross-entropy's log-sum-exp) at 16 per clock and SM, at the "
+                                 "sampled SM clock: the pipe ncu shows busiest (XU 75 %, tensor 59 %, profiles/r02_d_ncu_full_top_kernels_summary.csv)"},
             "metrics_sample": {"hr": [float(x) for x in out[1]], "ndcg": [float(x) for x in out[2]]},
             "cpu_baseline": None}
     del net, eng

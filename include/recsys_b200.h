@@ -254,7 +254,7 @@ int rec_unpack_batch(rec_engine *e, const void *gathered, int n_ranks, int B_loc
 int rec_eval_batch(rec_engine *e, int net_id, const rec_batch *b, const rec_eval_opts *o,
                    const rec_eval_accum *acc, int32_t *topk_ids, float *topk_scores);
 /* An evaluation sweep calls rec_eval_batch / rec_eval_shard_candidates many times with unchanged parameters
- * (evaluate(), eval_protocol.py:178-200: model.eval(), one pass over the validation loader).  on = 1: the caller
+ * (evaluate(), eval_protocol.py:154-171: model.eval(), one pass over the validation loader).  on = 1: the caller
  * promises not to modify the bound parameter tensors until on = 0; the engine may then keep operand images derived from
  * them (the packed bf16 hi/lo image of the scored head: 512 MB of traffic per batch at 1 M items) across calls.  Any
  * training entry point of this engine ends the reuse by itself. */
