@@ -417,21 +417,25 @@ def test_native_training_loop_matches_oracle_loop(pkg, tmp_path):
 
 
 # ------------------------------------------------------------------------------------ sharded evaluation (E2)
-def test_sharded_evaluation_virtual_ranks_equals_unsharded_and_oracle(pkg):
+@pytest.mark.parametrize("G,V,B", [(3, 70852, 300), (2, 140_000, 1100)])  # second case: the chunk-maxima path per shard
+def test_sharded_evaluation_virtual_ranks_equals_unsharded_and_oracle(pkg, G, V, B):
     """BASELINE configs[4] protocol on one GPU: G engines hold vocabulary slices of the same net;
     rec_eval_shard_candidates per shard -> stacked records (the all-gather) -> rec_eval_merge on every shard.
-    Default-init weights (unscaled): ids exact vs the oracle, metrics equal to the unsharded rec_eval_batch."""
+    Default-init weights (unscaled): ids exact vs the oracle, metrics equal to the unsharded rec_eval_batch.
+    (G, V, B) = (2, 140 000, 1100) is the shape class of the multi-GPU bench: every shard runs the pair kernel +
+    chunk selection + exact scoring and publishes its candidates through the record's top-k slots."""
     from ikea_recommender_system_b200.sharded import shard_bounds
     from ikea_recommender_system_b200.recommenders.evaluate import eval_protocol as EP
     from ikea_recommender_system_b200.engine import EvalAccumulators
-    G, V, B = 3, 70852, 300
     torch.manual_seed(3)
     onet = oracle.make_sqn(hidden_dim=64, embedding_dim=64, item_num=V, state_size=10, action_dim=V, gru_layers=1,
                            use_packed_seq=True)
     rows = _syn().make_replay_rows_fast(B, V, 10, seed=0)
     s, a, _, _, ln, _, _ = _syn().as_torch_batch(rows, 0, B)
     with torch.no_grad():
-        assert topk_margin(double_copy(onet)(s, ln)[0], 20) > MARGIN_MIN
+        top = torch.topk(double_copy(onet)(s, ln)[0], 21, dim=1).values
+    ok_rows = (top[:, :-1] - top[:, 1:]).min(1).values > MARGIN_MIN  # rows whose order every fp32 implementation shares
+    assert int(ok_rows.sum()) >= B - max(0 if B <= 512 else 2, B // 50), int(ok_rows.sum())
     unpop = _syn().unpopular_set_from_actions(rows["action"])
     e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16, generator=torch.Generator().manual_seed(1)),
                                                freeze=True)
@@ -470,12 +474,19 @@ def test_sharded_evaluation_virtual_ranks_equals_unsharded_and_oracle(pkg):
         outs.append((ids.cpu(), acc.read()))
     with torch.no_grad():
         want_ids = oracle.stable_topk(onet(s, ln)[0], kmax)
+    # the unsharded engine's own id lists: sharded == unsharded on EVERY row (same exact fp32 scores, same order)
+    eng_full = full._ready(B)
+    acc_f = EvalAccumulators(dev, V)
+    ids_full = torch.empty(B, kmax, dtype=torch.int32, device=DEV)
+    eng_full.eval_batch(0, eng_full._batch(B, ds, da, dl), o, acc_f.struct, topk_ids=ids_full)
     for ids, r in outs:
-        assert torch.equal(ids.long(), want_ids)
+        assert torch.equal(ids.long()[ok_rows], want_ids[ok_rows])
+        assert torch.equal(ids, ids_full.cpu())
         assert np.array_equal(r["hits"][:3] / B, got_full[1]) and np.allclose(r["ndcg"][:3] / B, got_full[2], rtol=1e-12)
         assert np.array_equal(r["cov_bits"], outs[0][1]["cov_bits"])
         assert abs(r["loss_sum"] - float(got_full[0])) <= 1e-5 * abs(float(got_full[0]))
-    assert np.array_equal(got_full[1], want[1]) and got_full[3] == want[3]
+    if bool(ok_rows.all()):
+        assert np.array_equal(got_full[1], want[1]) and got_full[3] == want[3]
     # and through the public evaluate() on a sharded module (virtual all-gather hook)
     for g in range(G):
         acc = EvalAccumulators(dev, V)
