@@ -976,6 +976,7 @@ static int phase_a_body(rec_engine *e, const rec_batch *b, const rec_train_hpara
                         bool skip_gru) {
   if (!e) return REC_EINVAL;
   if (!b || !hp || !records_out) REC_FAIL(e, REC_EINVAL, "rec_train_phase_a: null argument");
+  if (hp->dropout_p < 0.f || hp->dropout_p >= 1.f) REC_FAIL(e, REC_EINVAL, "dropout_p must be in [0, 1)");
   const int n_q = e->cfg.n_heads - 1;
   if (main_net < 0 || main_net >= e->cfg.n_nets) REC_FAIL(e, REC_EINVAL, "main_net out of range");
   int rc = check_net(e, main_net, true);
@@ -1003,6 +1004,9 @@ static int phase_a_body(rec_engine *e, const rec_batch *b, const rec_train_hpara
   } else {
     if ((rc = launch_gru_forward(e, main_net, b->s, b->true_len, B, e->h_state[0], true))) return rc;
   }
+  // BidirGRU4Rec dropout (supervised step only): the keep mask is a function of (seed, Adam step, element of the GLOBAL
+  // batch) or injected for the global batch, so every rank drops the same elements without a collective
+  if (n_q == 0 && hp->dropout_p > 0.f && (rc = launch_dropout(e, main_net, e->h_state[0], nullptr, B, hp, false))) return rc;
   float w[3] = {n_q == 3 ? hp->q_weights[0] : 1.f, hp->q_weights[1], hp->q_weights[2]};
   return shard_head_pass(e, main_net, e->h_state[0], b, 0, e->cur_topk, n_q, w, true, records_out);
 }
@@ -1133,8 +1137,14 @@ extern "C" int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank,
   const rec_batch &lb = e->dp_local;
   const int B = lb.B, main_net = e->cur_main;
   if ((rank + 1) * B > e->cur_batch.B) REC_FAIL(e, REC_EINVAL, "rec_dp_backward: rank %d outside the global batch", rank);
-  int rc = launch_gru_backward(e, main_net, lb.s, lb.true_len, B, dh_reduced + (size_t)rank * B * e->D, e->cur_step_size,
-                               e->cur_bc2_sqrt, &e->cur_hp, 1 | 2);
+  const float *dh_local = dh_reduced + (size_t)rank * B * e->D;
+  int rc;
+  if (e->cfg.n_heads == 1 && e->cur_hp.dropout_p > 0.f) {  // dL/dh of this rank's rows through their part of the keep mask
+    REC_CUDA(e, cudaMemcpyAsync(e->dh, dh_local, sizeof(float) * (size_t)B * e->D, cudaMemcpyDeviceToDevice, e->stream));
+    if ((rc = launch_dropout(e, main_net, nullptr, e->dh, B, &e->cur_hp, true, rank * B))) return rc;
+    dh_local = e->dh;
+  }
+  rc = launch_gru_backward(e, main_net, lb.s, lb.true_len, B, dh_local, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, 1 | 2);
   if (rc) return rc;
   const int n = (int)rec_dp_grad_floats(e);
   sum_splits_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(e->wgrad_part, e->wgrad_used, n, gru_grads_out);
@@ -1225,7 +1235,14 @@ extern "C" int rec_train_phase_d(rec_engine *e, const float *dh_reduced) {
   const rec_batch *b = &e->cur_batch;
   const int main_net = e->cur_main;
   e->cur_phase = 0;
-  int rc = trunk_backward(e, main_net, b->s, b->true_len, b->B, dh_reduced, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, false);
+  int rc;
+  if (e->cfg.n_heads == 1 && e->cur_hp.dropout_p > 0.f) {  // dL/dh through the keep mask of phase A
+    if (dh_reduced != e->dh)
+      REC_CUDA(e, cudaMemcpyAsync(e->dh, dh_reduced, sizeof(float) * (size_t)b->B * e->D, cudaMemcpyDeviceToDevice, e->stream));
+    if ((rc = launch_dropout(e, main_net, nullptr, e->dh, b->B, &e->cur_hp, true))) return rc;
+    dh_reduced = e->dh;
+  }
+  rc = trunk_backward(e, main_net, b->s, b->true_len, b->B, dh_reduced, e->cur_step_size, e->cur_bc2_sqrt, &e->cur_hp, false);
   for (int i = 0; i < 3; ++i) side_join(e, i);  // the Q-head sweep forked in phase C rejoins here
   return rc;
 }

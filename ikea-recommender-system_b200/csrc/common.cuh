@@ -344,6 +344,7 @@ int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_bat
 int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                           float bc2_sqrt, const rec_train_hparams *hp, int wait_mark = -1);
 int launch_dh_reduce(rec_engine *e, int B);
-int launch_dropout(rec_engine *e, int net_id, float *h, float *dh, int B, const rec_train_hparams *hp, bool backward);
+int launch_dropout(rec_engine *e, int net_id, float *h, float *dh, int B, const rec_train_hparams *hp, bool backward,
+                   int mask_row0 = 0);
 int launch_q_rows_fused(rec_engine *e, int main_net, const rec_batch *b, const rec_train_hparams *hp, int n_split,
                         float alpha_eff, float *q_loss_rows, const HeadStatsArgs *src);

@@ -91,9 +91,13 @@ __global__ void dropout_bwd_kernel(float *__restrict__ dh, int n, float p, const
   if (i >= n) return;
   dh[i] = mask[i] ? dh[i] / (1.f - p) : 0.f;
 }
-int launch_dropout(rec_engine *e, int net_id, float *h, float *dh, int B, const rec_train_hparams *hp, bool backward) {
+// mask_row0: first row of the saved keep mask that `dh` corresponds to (data-parallel trunk: a rank back-propagates
+// only its own rows of the global batch).
+int launch_dropout(rec_engine *e, int net_id, float *h, float *dh, int B, const rec_train_hparams *hp, bool backward,
+                   int mask_row0) {
   const int n = B * e->D;
-  if (backward) dropout_bwd_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(dh, n, hp->dropout_p, e->drop_mask);
+  if (backward)
+    dropout_bwd_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(dh, n, hp->dropout_p, e->drop_mask + (size_t)mask_row0 * e->D);
   else dropout_fwd_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(h, n, hp->dropout_p, hp->dropout_seed, e->d_step + net_id,
                                                               hp->dropout_mask, e->drop_mask);
   REC_LAUNCH_CHECK(e);

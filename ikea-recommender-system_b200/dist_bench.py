@@ -30,10 +30,13 @@ def _replicated_params_identical(trainer, dev):
 
 
 def _eval_secondary(args, pkg, trainer, wl, eval_kw, eval_metric, synthetic, dev, rank, world):
-    """BASELINE configs[4]: full-catalogue evaluation with vocabulary-sharded heads through the public evaluate():
-    per batch one all-gather of per-shard candidate records, merge + metrics replicated on every rank."""
+    """BASELINE configs[4]: full-catalogue evaluation of the vocabulary-sharded trainer through the public evaluate().
+    Default: sharded by SESSIONS (every rank scores every world-th batch against an all-gathered copy of the scored head,
+    one reduction of the accumulators at the end); REC_EVAL_SHARD=vocab: per batch one all-gather of per-shard candidate
+    records, merge + metrics replicated on every rank."""
     N, B, L = wl["item_num"], wl["batch"], wl["L"]
-    n_batches = 4
+    n_batches = max(8, world)  # the single-GPU evaluation object sweeps 8 batches too
+    by_sessions = os.environ.get("REC_EVAL_SHARD", "sessions") != "vocab"
     rows = synthetic.make_replay_rows_fast(n_batches * B, N, L, seed=7)
     unpop = synthetic.unpopular_set_from_actions(rows["action"])
     e_div = trainer.div_embedding
@@ -43,7 +46,8 @@ def _eval_secondary(args, pkg, trainer, wl, eval_kw, eval_metric, synthetic, dev
         loader.append((s_, a_, ln_))
     ce = torch.nn.CrossEntropyLoss()
     net = trainer._nets[0]
-    pkg.evaluate(loader[:1], net, dev, ce, "end", e_div, unpop, **eval_kw)  # grows the engine workspace to B
+    # grows the engine workspace to B on every rank (sharded by sessions, rank r takes batch r of the warm-up sweep)
+    pkg.evaluate(loader[:world], net, dev, ce, "end", e_div, unpop, **eval_kw)
     torch.cuda.synchronize()
     dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -61,9 +65,13 @@ def _eval_secondary(args, pkg, trainer, wl, eval_kw, eval_metric, synthetic, dev
     sessions = n_batches * B
     return {"metric": eval_metric, "value": sessions / float(wall[1]), "unit": "sessions/s", "n_gpus": world,
             "steps": n_batches, "ms_per_step": 1e3 * float(wall[1]) / n_batches, "higher_is_better": True,
-            "scaling": "strong (the same validation set on every rank, vocabulary split 1/G)",
-            "config": {"workload": wl["name"], "parallelism": f"vocab-sharded heads x{world}: per batch one all-gather of "
-                       "per-shard records (max, sum-exp, target logit, fp32-exact top-k candidates), merge + metrics replicated"},
+            "scaling": "strong (one validation set of %d batches for the whole job)" % n_batches,
+            "config": {"workload": wl["name"], "parallelism": (
+                f"sharded by sessions x{world}: the scored head all-gathered once per sweep (part of the timed region), every "
+                "rank scores every world-th batch against the full catalogue, accumulators summed / coverage bitmaps OR-ed once"
+                if by_sessions else
+                f"vocab-sharded heads x{world}: per batch one all-gather of per-shard records (max, sum-exp, target logit, "
+                "fp32-exact top-k candidates), merge + metrics replicated")},
             "e2e": {"value": sessions / float(wall[0]), "unit": "sessions/s", "h2d_bytes_per_step": B * (L + 2) * 8,
                     "d2h_bytes_per_step": 8 * 27 + 4 * 8 * ((N + 31) // 32) // n_batches},
             "ranks_agree_on_metrics": bool(torch.equal(hr_lo, hr_hi)),

@@ -140,6 +140,102 @@ def _eval_one_batch(model, eng, batch, o, acc, kmax, topk_ids=None, virtual_gath
     eng.eval_merge(batch, o, gathered, int(gathered.shape[0]), acc.struct, topk_ids=topk_ids)
 
 
+class _FullHeadReplica:
+    """Evaluation of a vocabulary-sharded net sharded by SESSIONS instead (sessions are independent): every
+    rank gets an unsharded copy of the ONE head `evaluate` scores (one all-gather of the shards' rows per sweep: 256 MB at
+    1 M items, a fraction of a millisecond over NVLink), binds it with the replicated embedding + GRU to a second,
+    unsharded engine and evaluates every world-th batch against the full catalogue with the single-GPU kernels;
+    accumulators are summed and coverage bitmaps OR-ed once at the end.  Per-batch collectives and the replicated work of
+    the vocabulary-sharded sweep (GRU forward, exact scoring, merge, metrics on every rank for every batch) disappear, so
+    the sweep scales with the number of GPUs.  Duck-types what `evaluate` needs of a NativeSessionNet."""
+
+    is_sharded = False
+    _net_id = 0
+
+    def __init__(self, model, head_idx):
+        import torch.distributed as dist
+        from ...sharded import shard_bounds
+        self.src, self.head_idx, self.group = model, head_idx, model._group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.action_dim = model.action_dim
+        self.bounds = [shard_bounds(model.action_dim, g, self.world) for g in range(self.world)]
+        dev = model._param_device()
+        D = model._head_modules()[head_idx].weight.shape[1]
+        self.rows_max = max(hi - lo for lo, hi in self.bounds)
+        self.send = torch.zeros(self.rows_max, D + 1, dtype=torch.float32, device=dev)
+        self.recv = torch.empty(self.world, self.rows_max, D + 1, dtype=torch.float32, device=dev)
+        self.W = torch.empty(model.action_dim, D, dtype=torch.float32, device=dev)
+        self.b = torch.empty(model.action_dim, dtype=torch.float32, device=dev)
+        self._engine = None
+
+    @staticmethod
+    def plan(model, head_idx):
+        """The replica of `model` for this sweep, or None when the sweep runs on `model` itself (unsharded model, no
+        process group, REC_EVAL_SHARD=vocab, or shards that are not the balanced split of the group)."""
+        import os
+        import torch.distributed as dist
+        from ...sharded import shard_bounds
+        if not model.is_sharded or os.environ.get("REC_EVAL_SHARD", "sessions") == "vocab":
+            return None
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        world, rank = dist.get_world_size(model._group), dist.get_rank(model._group)
+        if world < 2 or shard_bounds(model.action_dim, rank, world) != (model._vocab_lo, model._vocab_hi):
+            return None
+        rep = getattr(model, "_eval_replica", None)
+        if rep is None or rep.head_idx != head_idx or rep.world != world or rep.W.device != model._param_device():
+            rep = model._eval_replica = _FullHeadReplica(model, head_idx)
+        rep.refresh()
+        return rep
+
+    def refresh(self):
+        """All-gather the scored head's rows (weights | bias) of every shard into the full [V, D] / [V] copies."""
+        import torch.distributed as dist
+        h = self.src._head_modules()[self.head_idx]
+        n, D = h.weight.shape
+        self.send[:n, :D].copy_(h.weight.data)
+        self.send[:n, D].copy_(h.bias.data)
+        dist.all_gather_into_tensor(self.recv.view(-1), self.send.view(-1), group=self.group)
+        for g, (lo, hi) in enumerate(self.bounds):
+            self.W[lo:hi].copy_(self.recv[g, :hi - lo, :D])
+            self.b[lo:hi].copy_(self.recv[g, :hi - lo, D])
+
+    def mine(self, batch_index):
+        return batch_index % self.world == self.rank
+
+    def _param_device(self):
+        return self.src._param_device()
+
+    def _dev_inputs(self, s, lengths):
+        return self.src._dev_inputs(s, lengths)
+
+    def _ready(self, batch_hint=256):
+        from ...engine import Engine
+        m = self.src
+        if self._engine is None:
+            self._engine = Engine(item_num=m.item_num, action_dim=m.action_dim, embedding_dim=m.embedding_dim,
+                                  hidden_dim=m.hidden_dim, state_size=m.state_size, bidirectional=m._bidirectional,
+                                  n_heads=len(m._HEADS[m._family]), n_nets=1, use_packed_seq=m.use_packed_seq,
+                                  frozen_pad_row=m._frozen_pad_row, device=self._param_device(),
+                                  max_batch=max(256, batch_hint))
+        nt = m._net_tensors()  # embedding + GRU: the replicated tensors themselves; every head slot: the scored head
+        nt.head_w, nt.head_b = [self.W for _ in nt.head_w], [self.b for _ in nt.head_b]
+        nt.m = nt.v = None
+        self._engine.bind(0, nt)
+        return self._engine
+
+    def reduce(self, acc):
+        """Sum of the ranks' accumulators, OR of their coverage bitmaps (in place, identical on every rank)."""
+        import torch.distributed as dist
+        dist.all_reduce(acc.f64, group=self.group)
+        allcov = torch.empty(self.world, acc.cov.numel(), dtype=torch.int32, device=acc.cov.device)
+        dist.all_gather_into_tensor(allcov.view(-1), acc.cov.view(-1), group=self.group)
+        out = allcov[0]
+        for g in range(1, self.world):
+            out = torch.bitwise_or(out, allcov[g])
+        acc.cov.copy_(out)
+
+
 def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, diversity_embedding,
              unpopular_actions_set, head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=1,
              topk_to_consider_nov=1, topk_to_consider_cov=[1, 5, 10], novelty_rew_signal=1, input_tokenizer=None,
@@ -157,21 +253,28 @@ def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, 
     acc = EvalAccumulators(dev, model.action_dim)
     n_total, n_batches = 0, 0
     held = None  # the engine that was told "parameters are frozen for this sweep" (model.eval(): nothing trains here)
+    # a vocabulary-sharded model under a process group evaluates sharded by SESSIONS: this rank scores every world-th
+    # batch against the full catalogue (REC_EVAL_SHARD=vocab keeps the per-batch candidate exchange)
+    replica = _FullHeadReplica.plan(model, head_idx)
+    net = model if replica is None else replica
     try:
         for s, a, s_len in evaluation_data_loader:
             B = int(s.shape[0])
-            ds, dl = model._dev_inputs(s, s_len)
-            da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-            eng = model._ready(B)
-            if (eng, eng.handle) != held:  # first batch, or the engine was re-created for a larger batch
-                eng.eval_hold_params(True)
-                held = (eng, eng.handle)
-            _eval_one_batch(model, eng, eng._batch(B, ds, da, dl), o, acc, kmax)
+            if replica is None or replica.mine(n_batches):
+                ds, dl = net._dev_inputs(s, s_len)
+                da = a.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+                eng = net._ready(B)
+                if (eng, eng.handle) != held:  # first batch, or the engine was re-created for a larger batch
+                    eng.eval_hold_params(True)
+                    held = (eng, eng.handle)
+                _eval_one_batch(net, eng, eng._batch(B, ds, da, dl), o, acc, kmax)
             n_total += B
             n_batches += 1
     finally:
         if held is not None and held[0].handle == held[1]:
             held[0].eval_hold_params(False)
+    if replica is not None:
+        replica.reduce(acc)
     r = acc.read()
     nk = len(topk_hr_ndcg)
     hr = r["hits"][:nk] / n_total

@@ -14,11 +14,11 @@ def _supervised_hparams(trainer):
     net = trainer.gru_model
     hp = make_hparams(trainer.learning_rate)
     if net._family == "bidir" and net.training and net.dropout.p > 0:
-        if trainer._shard is not None:
-            raise NotImplementedError("dropout > 0 is not implemented for the vocabulary-sharded step")
         hp.dropout_p = float(net.dropout.p)
         hp.dropout_seed = int(getattr(trainer, "_dropout_seed", 118))
-        mask = getattr(trainer, "dropout_mask_override", None)  # device uint8 [B, 2H], 1 = keep (parity tests)
+        # device uint8 [B, 2H], 1 = keep (parity tests); vocabulary-sharded trainer: the mask of the GLOBAL batch
+        # [world * B, 2H], rows in rank order (every rank drops the same elements, no collective needed)
+        mask = getattr(trainer, "dropout_mask_override", None)
         if mask is not None:
             trainer._dropout_mask_keepalive = mask = mask.to(device=net._param_device(), dtype=torch.uint8).contiguous()
             hp.dropout_mask = mask.data_ptr()

@@ -114,7 +114,8 @@ class ShardedStep:
             # kernels on freed workspace pointers
             self._graphs.clear()
             self._eng_generation = eng.generation
-        key = (int(main_net), bool(has_q), float(hp.lr), id(losses_out))
+        key = (int(main_net), bool(has_q), float(hp.lr), id(losses_out), float(hp.dropout_p), int(hp.dropout_seed),
+               int(hp.dropout_mask or 0))  # everything of `hp` that a captured sequence bakes in
         ent = self._graphs.setdefault(key, {"seen": 0, "graph": None, "launches": 0})
         if os.environ.get("REC_NO_GRAPH") or not self.use_graphs or eng.timing:
             return self._sequence(hp, main_net, losses_out, has_q)

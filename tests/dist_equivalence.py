@@ -3,6 +3,10 @@ oracle on the concatenated global batch.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
         tests/dist_equivalence.py
+
+DIST_BACKEND=gloo DIST_ONE_GPU=1: the same ranks as separate processes that SHARE cuda:0 and talk over gloo (NCCL refuses
+two ranks on one device).  Everything above the transport is the production path: `ShardedStep`, the phase entry points of
+the C ABI, sharded `evaluate()`; the step runs eagerly (a gloo collective cannot be captured into a CUDA graph).
 """
 import os
 import random
@@ -16,6 +20,27 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def _stage_collectives_through_host():
+    """gloo transport for CUDA tensors: copy to the host, run the collective there, copy back (test harness only)."""
+    real = dict(ag=dist.all_gather_into_tensor, ar=dist.all_reduce, bc=dist.broadcast, agl=dist.all_gather)
+
+    def all_gather_into_tensor(out, inp, group=None, **kw):
+        o = out.cpu(); real["ag"](o, inp.cpu(), group=group); out.copy_(o)
+
+    def all_reduce(t, op=dist.ReduceOp.SUM, group=None, **kw):
+        c = t.cpu(); real["ar"](c, op=op, group=group); t.copy_(c)
+
+    def broadcast(t, src=0, group=None, **kw):
+        c = t.cpu(); real["bc"](c, src=src, group=group); t.copy_(c)
+
+    def all_gather(lst, t, group=None, **kw):
+        cl = [x.cpu() for x in lst]; real["agl"](cl, t.cpu(), group=group)
+        for x, c in zip(lst, cl):
+            x.copy_(c)
+
+    dist.all_gather_into_tensor, dist.all_reduce, dist.broadcast, dist.all_gather = all_gather_into_tensor, all_reduce, broadcast, all_gather
+
+
 def main():
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("DIST_HANG_DUMP_S", "150")), exit=True)  # a hang prints where
@@ -26,10 +51,15 @@ def main():
     from ikea_recommender_system_b200 import synthetic
     from ikea_recommender_system_b200.sharded import shard_bounds
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
+    local = 0 if os.environ.get("DIST_ONE_GPU") else int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if os.environ.get("DIST_BACKEND", "nccl") == "gloo":
+        os.environ["REC_NO_GRAPH"] = "1"
+        dist.init_process_group("gloo")
+        _stage_collectives_through_host()
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     V, L, B, steps = 5000, 10, 64, int(os.environ.get("DIST_STEPS", "12"))  # > 2 x warm: both twins get captured + replayed
     kw = dict(hidden_dim=64, embedding_dim=64, padding_pos="end", train_pad_embed=True, use_packed_seq=True,
               learning_rate=0.01, item_num=V, state_size=L, action_dim=V, gamma=0.5, gru_layers=1,
@@ -83,7 +113,13 @@ def main():
         loader.append((s_, a_, ln_))
     ekw = dict(head_idx=0, topk_hr_ndcg=[5, 10, 20], topk_to_consider_div=2, topk_to_consider_nov=1,
                topk_to_consider_cov=[1, 5, 10, 20], novelty_rew_signal=1)
-    got_e = pkg.evaluate(loader, t.SMORL_1, dev, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **ekw)
+    got_by_mode = {}
+    for mode in ("sessions", "vocab"):  # sharded by sessions (default; rank r scores batch r) / per-batch candidate exchange
+        os.environ["REC_EVAL_SHARD"] = mode
+        got_by_mode[mode] = pkg.evaluate(loader, t.SMORL_1, dev, torch.nn.CrossEntropyLoss(), "end", e_div, unpop, **ekw)
+    os.environ.pop("REC_EVAL_SHARD")
+    if world > 1:  # the session-sharded sweep really ran on an all-gathered copy of the scored head
+        assert getattr(t.SMORL_1, "_eval_replica", None) is not None and t.SMORL_1._eval_replica.world == world
     # the oracle net with THIS run's trained parameters (gathered from all shards)
     import copy
     onet = copy.deepcopy(ref.SMORL_1)
@@ -103,10 +139,16 @@ def main():
     with torch.no_grad():
         o64 = double_copy(onet)
         assert min(topk_margin(o64(s_, ln_)[0], 20) for s_, a_, ln_ in loader) > MARGIN_MIN  # ids are well-posed
-    assert abs(float(got_e[0]) - float(want_e[0])) <= 1e-4 * abs(float(want_e[0])), (got_e[0], want_e[0])
-    assert np.array_equal(got_e[1], want_e[1]) and np.allclose(got_e[2], want_e[2], rtol=1e-12), (got_e[1], want_e[1])
-    assert got_e[3] == want_e[3] and np.array_equal(got_e[6], want_e[6])
-    assert abs(float(got_e[4]) - float(want_e[4])) <= 1e-4 and np.isclose(got_e[5], want_e[5])
+    for mode, got_e in got_by_mode.items():
+        assert abs(float(got_e[0]) - float(want_e[0])) <= 1e-4 * abs(float(want_e[0])), (mode, got_e[0], want_e[0])
+        assert np.array_equal(got_e[1], want_e[1]) and np.allclose(got_e[2], want_e[2], rtol=1e-12), (mode, got_e[1], want_e[1])
+        assert got_e[3] == want_e[3] and np.array_equal(got_e[6], want_e[6]), mode
+        assert abs(float(got_e[4]) - float(want_e[4])) <= 1e-4 and np.isclose(got_e[5], want_e[5]), mode
+    # every rank holds the same reduced result (sum of accumulators, OR of coverage bitmaps)
+    mine_hr = torch.tensor(np.concatenate([got_by_mode["sessions"][1], got_by_mode["sessions"][2]]), device=dev)
+    lo_hr, hi_hr = mine_hr.clone(), mine_hr.clone()
+    dist.all_reduce(lo_hr, op=dist.ReduceOp.MIN); dist.all_reduce(hi_hr, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo_hr, hi_hr)
     dist.barrier()
     if rank == 0:
         print(f"dist_equivalence ok: world={world}")

@@ -146,3 +146,63 @@ def test_sharding_protocol_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out.get(r) == "ok" for r in range(world)), dict(out)
+
+
+def _replica_worker(rank, world, port, out):
+    """Host logic of the session-sharded evaluation (eval_protocol._FullHeadReplica) on CPU tensors over gloo: the
+    all-gather of UNEVEN head shards into the full [V, D] / [V] copy, the batch assignment, and the final reduction
+    (sum of the float64 accumulators, OR of the coverage bitmaps)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import b200pkg
+        pkg = b200pkg.load()
+        from ikea_recommender_system_b200.sharded import shard_bounds
+        from ikea_recommender_system_b200.engine import EvalAccumulators
+        from ikea_recommender_system_b200.recommenders.evaluate.eval_protocol import _FullHeadReplica
+        V, D = 1001, 64  # 1001 rows over 3 ranks: 333 / 334 / 334
+        t = pkg.SQN_trainer(hidden_dim=D, embedding_dim=D, train_pad_embed=True, use_packed_seq=True, learning_rate=0.01,
+                            item_num=V, state_size=5, action_dim=V, gamma=0.5, gru_layers=1, device="cpu")
+        full_w = t.DQN_1.sup_head_output.weight.data.clone()
+        full_b = t.DQN_1.sup_head_output.bias.data.clone()
+        assert _FullHeadReplica.plan(t.DQN_1, 0) is None  # unsharded model: evaluate() runs on the model itself
+        t.shard_vocabulary(rank, world)
+        lo, hi = shard_bounds(V, rank, world)
+        assert t.DQN_1.sup_head_output.weight.shape[0] == hi - lo
+        rep = _FullHeadReplica.plan(t.DQN_1, 0)
+        assert rep is not None and rep.world == world and rep.rank == rank
+        assert torch.equal(rep.W, full_w) and torch.equal(rep.b, full_b)  # seeded init is identical on every rank
+        t.DQN_1.sup_head_output.weight.data.add_(1.0 + rank)             # parameters changed since the last sweep
+        rep2 = _FullHeadReplica.plan(t.DQN_1, 0)
+        assert rep2 is rep                                              # buffers are reused, contents re-gathered
+        for g in range(world):
+            glo, ghi = shard_bounds(V, g, world)
+            assert torch.equal(rep.W[glo:ghi], full_w[glo:ghi] + (1.0 + g))
+        assert [rep.mine(i) for i in range(2 * world)] == [i % world == rank for i in range(2 * world)]
+        os.environ["REC_EVAL_SHARD"] = "vocab"
+        assert _FullHeadReplica.plan(t.DQN_1, 0) is None
+        os.environ.pop("REC_EVAL_SHARD")
+        acc = EvalAccumulators("cpu", V)
+        acc.f64 += float(rank + 1)
+        acc.cov[rank] = 1 << rank
+        acc.cov[5] = 7 if rank == 0 else 8
+        rep.reduce(acc)
+        assert torch.all(acc.f64 == float(sum(range(1, world + 1))))
+        assert [int(acc.cov[g]) for g in range(world)] == [1 << g for g in range(world)] and int(acc.cov[5]) == 15
+        out[rank] = "ok"
+    except Exception:  # pragma: no cover
+        import traceback
+        out[rank] = traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_session_sharded_evaluation_host_logic_world3_gloo():
+    world = 3
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_replica_worker, args=(world, port, out), nprocs=world, join=True)
+    assert all(out.get(r) == "ok" for r in range(world)), dict(out)
