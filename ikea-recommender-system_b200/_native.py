@@ -92,6 +92,9 @@ SYMBOLS = {
     "rec_train_phase_a_heads": (C.c_int, [_P, C.POINTER(RecBatch), C.POINTER(RecTrainHparams), C.c_int, _P]),
     "rec_dp_backward": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "rec_dp_apply": (C.c_int, [_P, _P, _P]),
+    "rec_set_embedding_shard": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "rec_emb_rows_gather": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),
+    "rec_emb_rows_scatter": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),
     "rec_packed_batch_bytes": (C.c_int64, [_P, C.c_int]),
     "rec_gather_batch": (C.c_int, [_P, C.POINTER(RecBatch), C.c_int64, _P, C.c_int, C.POINTER(RecBatch)]),
     "rec_build_replay_rows": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64, C.c_int, C.POINTER(RecBatch)]),

@@ -296,6 +296,41 @@ extern "C" int rec_set_stream(rec_engine *e, void *stream) {
   return REC_OK;
 }
 
+// ---- row-sharded embedding table -----------------------------------------------------------------------------------
+static void drop_step_graphs(rec_engine *e) {
+  for (int i = 0; i < e->n_graphs; ++i)
+    if (e->graphs[i].exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graphs[i].exec);
+  e->n_graphs = 0;
+}
+
+extern "C" int rec_set_embedding_shard(rec_engine *e, int64_t row_lo, int64_t row_hi) {
+  DevGuard dev_guard(e);
+  if (!e) return REC_EINVAL;
+  const int64_t n_rows = (int64_t)e->cfg.item_num + 1;
+  if (row_lo < 0 || row_hi > n_rows || row_lo >= row_hi) REC_FAIL(e, REC_EINVAL, "rec_set_embedding_shard: bad row range");
+  if (e->cfg.embedding_dim % 4) REC_FAIL(e, REC_EINVAL, "rec_set_embedding_shard: embedding_dim must be a multiple of 4");
+  const bool all = row_lo == 0 && row_hi == n_rows;
+  e->emb_row_lo = all ? 0 : row_lo;
+  e->emb_row_hi = all ? 0 : row_hi;
+  drop_step_graphs(e);  // a captured step bakes the swept row range in
+  return REC_OK;
+}
+
+static int emb_rows_call(rec_engine *e, int net_id, const int64_t *ids, int64_t n, float *rows, bool scatter) {
+  DevGuard dev_guard(e);
+  int rc = check_net(e, net_id, false);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!ids || !rows))) REC_FAIL(e, REC_EINVAL, "rec_emb_rows_%s: bad argument", scatter ? "scatter" : "gather");
+  return launch_emb_rows(e, net_id, ids, n, rows, scatter);
+}
+extern "C" int rec_emb_rows_gather(rec_engine *e, int net_id, const int64_t *ids, int64_t n, float *rows_out) {
+  return emb_rows_call(e, net_id, ids, n, rows_out, false);
+}
+extern "C" int rec_emb_rows_scatter(rec_engine *e, int net_id, const int64_t *ids, int64_t n, const float *rows) {
+  if (e) e->param_epoch++;  // writes parameters: derived operand images are stale (rec_eval_hold_params)
+  return emb_rows_call(e, net_id, ids, n, const_cast<float *>(rows), true);
+}
+
 extern "C" int rec_set_cuda_graphs(rec_engine *e, int on) {
   DevGuard dev_guard(e);
   if (!e) return REC_EINVAL;

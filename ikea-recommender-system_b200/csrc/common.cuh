@@ -118,6 +118,9 @@ struct rec_engine {
   float *k_cmax;         // chunk maxima [B][V/32] of the evaluation top-k (HeadTopk<.., CM>)
   bool k_hold;           // rec_eval_hold_params: parameters are frozen by the caller, images may be reused
   int64_t param_epoch, k_img_epoch;  // bumped by every entry point that may write parameters / epoch of the cached image
+  // rec_set_embedding_shard: rows [emb_row_lo, emb_row_hi) of every net's embedding table are OWNED by this rank (the
+  // Adam sweep touches no other row); emb_row_hi == 0: all rows (unsharded, the default)
+  int64_t emb_row_lo, emb_row_hi;
   int k_img_net, k_img_head;
   uint8_t *k_bblk;       // bias operand blocks of HeadCmaxPair [tiles + 1][4 KB]
   float *k_cmax2;        // level-2 maxima [B][2 * ceil(tiles / 8)] (HeadCmaxPair)
@@ -344,6 +347,7 @@ int launch_sup_head_bwd(rec_engine *e, int net_id, const float *h, const rec_bat
 int launch_q_heads_update(rec_engine *e, int net_id, const float *h, const rec_batch *b, int B, float step_size,
                           float bc2_sqrt, const rec_train_hparams *hp, int wait_mark = -1);
 int launch_dh_reduce(rec_engine *e, int B);
+int launch_emb_rows(rec_engine *e, int net_id, const int64_t *ids, int64_t n, float *rows, bool scatter);
 int launch_dropout(rec_engine *e, int net_id, float *h, float *dh, int B, const rec_train_hparams *hp, bool backward,
                    int mask_row0 = 0);
 int launch_q_rows_fused(rec_engine *e, int main_net, const rec_batch *b, const rec_train_hparams *hp, int n_split,

@@ -680,12 +680,57 @@ int launch_embedding_update(rec_engine *e, int net_id, const int64_t *s, const i
   }
   if (stages & 4) {
     if (e->timing) cudaEventRecord(e->ev[4], e->stream);
-    int rc = launch_adam_stream(e, nb.p.emb, nb.p.emb_m, nb.p.emb_v, (int64_t)c.item_num + 1, E, e->emb_slot,
+    // row-sharded table (rec_set_embedding_shard): this rank sweeps the rows it owns; the other rows of its copy are
+    // refreshed from their owners before they are read (rec_emb_rows_gather / _scatter)
+    const int64_t lo = e->emb_row_hi > 0 ? e->emb_row_lo : 0, hi = e->emb_row_hi > 0 ? e->emb_row_hi : (int64_t)c.item_num + 1;
+    int rc = launch_adam_stream(e, nb.p.emb + lo * E, nb.p.emb_m + lo * E, nb.p.emb_v + lo * E, hi - lo, E, e->emb_slot + lo,
                                 e->emb_grad_rows, E, nullptr, nullptr, nullptr, nullptr, 0, hp, step_size, bc2_sqrt);
     if (rc) return rc;
     if (e->timing) cudaEventRecord(e->ev[5], e->stream);
     emb_reset_kernel<<<cdiv(P, 256), 256, 0, e->stream>>>(e->emb_keys, P, e->emb_slot);
     REC_LAUNCH_CHECK(e);
   }
+  return REC_OK;
+}
+
+
+// ---- row-sharded embedding table -----------------------------------------------------
+// Every rank keeps a full-size copy of the table but OWNS -- sweeps with Adam -- only rows [lo, hi).  Before a step
+// reads token rows, their current values travel from the owners: every rank gathers the rows it owns into a
+// [n, E] buffer (zeros elsewhere), ONE all-reduce(sum) of that buffer delivers each row from its single owner
+// bit-exactly (x + 0 + ... + 0), and the rows a rank does not own are written into its copy.
+__global__ void emb_rows_gather_kernel(const float4 *__restrict__ table, const int64_t *__restrict__ ids, int64_t n, int E4,
+                                       int64_t lo, int64_t hi, float4 *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * E4) return;
+  const int64_t r = i / E4;
+  const int c = (int)(i - r * E4);
+  const int64_t id = ids[r];
+  out[i] = (id >= lo && id < hi) ? table[id * E4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__global__ void emb_rows_scatter_kernel(float4 *__restrict__ table, const int64_t *__restrict__ ids, int64_t n, int E4,
+                                        int64_t lo, int64_t hi, int64_t n_rows, const float4 *__restrict__ rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * E4) return;
+  const int64_t r = i / E4;
+  const int c = (int)(i - r * E4);
+  const int64_t id = ids[r];
+  if (id < 0 || id >= n_rows || (id >= lo && id < hi)) return;  // owned rows are already current
+  table[id * E4 + c] = rows[i];  // a token that occurs twice writes the same bits twice
+}
+
+int launch_emb_rows(rec_engine *e, int net_id, const int64_t *ids, int64_t n, float *rows, bool scatter) {
+  const rec_config &c = e->cfg;
+  const int E4 = c.embedding_dim / 4;
+  const int64_t n_rows = (int64_t)c.item_num + 1;
+  const int64_t lo = e->emb_row_hi > 0 ? e->emb_row_lo : 0, hi = e->emb_row_hi > 0 ? e->emb_row_hi : n_rows;
+  if (n == 0) return REC_OK;
+  const unsigned blocks = (unsigned)((n * E4 + 255) / 256);
+  if (scatter)
+    emb_rows_scatter_kernel<<<blocks, 256, 0, e->stream>>>((float4 *)e->nets[net_id].p.emb, ids, n, E4, lo, hi, n_rows,
+                                                          (const float4 *)rows);
+  else
+    emb_rows_gather_kernel<<<blocks, 256, 0, e->stream>>>((const float4 *)e->nets[net_id].p.emb, ids, n, E4, lo, hi, (float4 *)rows);
+  REC_LAUNCH_CHECK(e);
   return REC_OK;
 }

@@ -225,6 +225,20 @@ int rec_train_phase_a_heads(rec_engine *e, const rec_batch *global_b, const rec_
 int rec_dp_backward(rec_engine *e, const float *dh_reduced, int rank, float *gru_grads_out, float *dx_out);
 int rec_dp_apply(rec_engine *e, const float *gru_grads_reduced, const float *dx_gathered);
 
+/* Row-sharded embedding table ("the same row slice of the embedding table (+m,v) so the dense-Adam sweep
+ * scales 1/G"; collectives C1 / C5).  The reference has one nn.Embedding per net (models/SQN/sqn_gru.py:50-62) updated by
+ * dense Adam (sqn_gru.py:173-181).  rec_set_embedding_shard makes this rank the OWNER of rows [row_lo, row_hi) of every
+ * net's table: its Adam sweep touches only those rows (+ their m, v); (0, item_num + 1) restores the unsharded sweep.
+ * The rank keeps a full-size copy; rows it does not own go stale and are refreshed from their owners before they are read:
+ *   rec_emb_rows_gather(net, ids[n])  -> rows_out[n, E]: the current row where this rank owns ids[i], zeros elsewhere
+ *   all-reduce(sum) of rows_out by the caller (exactly one owner contributes a non-zero row: the sum is bit-exact)
+ *   rec_emb_rows_scatter(net, ids[n], rows[n, E]): writes the rows this rank does NOT own into its copy
+ * Gradient rows need no extra exchange: every rank already sees the dx rows of the global batch (phase D /
+ * rec_dp_apply) and applies the ones that fall into its row range. */
+int rec_set_embedding_shard(rec_engine *e, int64_t row_lo, int64_t row_hi);
+int rec_emb_rows_gather(rec_engine *e, int net_id, const int64_t *ids, int64_t n, float *rows_out);
+int rec_emb_rows_scatter(rec_engine *e, int net_id, const int64_t *ids, int64_t n, const float *rows);
+
 /* Input plumbing of sharded runs: one rank's batch packed into ONE byte buffer (so a single all-gather moves
  * every field), and the inverse for the gathered [n_ranks][rec_packed_batch_bytes] buffer -> field arrays of
  * n_ranks*B_local rows (caller-owned; out->B is ignored). */

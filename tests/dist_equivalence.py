@@ -25,7 +25,7 @@ def _stage_collectives_through_host():
     real = dict(ag=dist.all_gather_into_tensor, ar=dist.all_reduce, bc=dist.broadcast, agl=dist.all_gather)
 
     def all_gather_into_tensor(out, inp, group=None, **kw):
-        o = out.cpu(); real["ag"](o, inp.cpu(), group=group); out.copy_(o)
+        o = out.cpu().view(-1); real["ag"](o, inp.cpu().contiguous().view(-1), group=group); out.copy_(o.view_as(out))
 
     def all_reduce(t, op=dist.ReduceOp.SUM, group=None, **kw):
         c = t.cpu(); real["ar"](c, op=op, group=group); t.copy_(c)

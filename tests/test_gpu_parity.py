@@ -427,7 +427,10 @@ def _run_dist_equivalence(nproc, port, env_extra):
            "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "dist_equivalence.py")]
     env = dict(os.environ, **env_extra)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-    assert out.returncode == 0 and "dist_equivalence ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    if out.returncode != 0 or "dist_equivalence ok" not in out.stdout:
+        err = out.stderr
+        first = err.find("Traceback")  # the failing rank's own traceback comes before torchrun's summary of it
+        raise AssertionError(out.stdout[-1500:] + (err[first:first + 4000] if first >= 0 else "") + err[-1500:])
 
 
 @pytest.mark.parametrize("trunk", ["replicated", "data_parallel"])

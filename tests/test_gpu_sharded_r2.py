@@ -128,8 +128,11 @@ def test_bidir_dropout_in_the_vocabulary_sharded_step(pkg, trunk):
     for g in range(G):
         lo, hi = shard_bounds(V, g, G)
         want_sd = {k: (sd[k][lo:hi] if k.startswith("output") else sd[k]) for k in sd}
+        # outliers (<= 0.1 % of a tensor): elements whose gradient nearly cancels -- Adam's first steps move every element by
+        # ~lr whatever the gradient's size, so summation-order noise in such an element shows up as a fraction of lr; the
+        # shard-wise dh sums add one more reordering here.  Bound: a tenth of ONE step's movement (observed: 0.07 lr).
         assert_state_close(shards[g].gru_model.state_dict(), want_sd, rtol=RTOL, atol=ATOL_P, outlier_frac=1e-3,
-                           outlier_atol=0.02 * 0.01 * steps)
+                           outlier_atol=0.1 * 0.01)
     assert torch.equal(shards[0].gru_model.state_dict()["embedding.weight"], shards[1].gru_model.state_dict()["embedding.weight"])
 
     # the device-side draw: same (seed, step, element) on every rank -> identical losses, and dropout is active
