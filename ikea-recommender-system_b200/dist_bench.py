@@ -161,7 +161,9 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "global_batch": B * world,
-                           "parallelism": f"vocab-sharded heads x{world}, embedding+GRU replicated, trunk "
+                           "parallelism": f"vocab-sharded heads x{world}, "
+                                          + ("embedding table row-sharded (token rows all-reduced from their owners every step), GRU replicated, trunk "
+                                             if trainer._sharded_step.shard_embedding else "embedding+GRU replicated, trunk ")
                                           + ("data-parallel (6 collectives/step)" if trainer._sharded_step.dp_trunk
                                              else "on the global batch (4 collectives/step)")
                                           + " over NCCL, whole step replayed as one CUDA graph",
@@ -177,9 +179,12 @@ def run(args, wl, metric, make_data, trainer_kwargs, algorithmic_bytes, peaks, C
                              "kernel_ms": head_ms, "kernel_share_of_step": head_ms / (ms / K)},
                 "replicated_params_bit_identical_across_ranks": replicas_ok,
                 "cpu_baseline": None}
-        line["roofline"]["step"] = {"algorithmic_bytes_per_rank": (ab["step"] - 24 * (wl["item_num"] + 1) * wl["E"]) / world
-                                    + 24 * (wl["item_num"] + 1) * wl["E"],
-                                    "note": "heads 1/G per rank, embedding table replicated"}
+        emb_bytes = 24 * (wl["item_num"] + 1) * wl["E"]
+        emb_sharded = trainer._sharded_step.shard_embedding
+        line["roofline"]["step"] = {"algorithmic_bytes_per_rank": (ab["step"] - emb_bytes) / world
+                                    + (emb_bytes / world if emb_sharded else emb_bytes),
+                                    "note": "heads 1/G per rank, embedding table "
+                                            + ("row-sharded 1/G per rank" if emb_sharded else "replicated")}
         line["roofline"]["step"]["achieved"] = line["roofline"]["step"]["algorithmic_bytes_per_rank"] / (ms / K / 1e3) / 1e9
         line["roofline"]["step"]["frac"] = line["roofline"]["step"]["achieved"] / peak
         if secondary is not None:

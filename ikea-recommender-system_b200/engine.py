@@ -71,6 +71,7 @@ class Engine:
         self._keep = []  # keeps ctypes structs / tensors of the last call alive
         self.generation = 0  # bumped whenever the native handle (and with it every workspace pointer) is re-created
         self._tc_on, self._graphs_on = True, None
+        self._emb_shard = None  # (row_lo, row_hi) owned by this rank (rec_set_embedding_shard); None: all rows
         self._create()
 
     # -- lifetime ----------------------------------------------------------------------------
@@ -92,6 +93,26 @@ class Engine:
             self.lib.rec_set_cuda_graphs(h, int(self._graphs_on))
         if self.timing:
             self.lib.rec_enable_kernel_timing(h, 1)
+        if self._emb_shard is not None:
+            self.set_embedding_shard(*self._emb_shard)
+
+    def set_embedding_shard(self, row_lo: int, row_hi: int):
+        """This rank owns rows [row_lo, row_hi) of every net's embedding table: its Adam sweep touches no other row."""
+        self._emb_shard = (int(row_lo), int(row_hi))
+        N.check(self.lib, self.handle, self.lib.rec_set_embedding_shard(self.handle, int(row_lo), int(row_hi)),
+                "rec_set_embedding_shard")
+
+    def emb_rows_gather(self, net_id, ids, rows_out):
+        """rows_out[i] = table[ids[i]] where this rank owns the row, zeros elsewhere (ids: contiguous int64 on the device)."""
+        self.follow_stream()
+        N.check(self.lib, self.handle,
+                self.lib.rec_emb_rows_gather(self.handle, net_id, _ptr(ids), int(ids.numel()), _ptr(rows_out)), "rec_emb_rows_gather")
+
+    def emb_rows_scatter(self, net_id, ids, rows):
+        """table[ids[i]] = rows[i] for the rows this rank does NOT own (refresh from the owners after the all-reduce)."""
+        self.follow_stream()
+        N.check(self.lib, self.handle,
+                self.lib.rec_emb_rows_scatter(self.handle, net_id, _ptr(ids), int(ids.numel()), _ptr(rows)), "rec_emb_rows_scatter")
 
     def follow_stream(self):
         """Launch on torch's CURRENT stream of the engine's device (called at the top of every compute call: work

@@ -80,6 +80,10 @@ class NativeSessionNet(nn.Module):
         self._opt_v: Optional[NetTensors] = None
         self._vocab_lo, self._vocab_hi = 0, int(action_dim)
         self._group = None
+        # row-sharded embedding table (trainer.shard_vocabulary(..., shard_embedding=True)): (rank, world) of the owner
+        # split; after a sharded train step the rows this rank does not own are stale until _sync_embedding()
+        self._emb_shard = None
+        self._emb_stale = self._emb_moments_stale = False
 
     def shard_vocabulary(self, lo: int, hi: int, group=None):
         """Keep only rows [lo, hi) of every head on this rank (vocabulary sharding, multi-GPU).
@@ -95,6 +99,31 @@ class NativeSessionNet(nn.Module):
     @property
     def is_sharded(self):
         return (self._vocab_lo, self._vocab_hi) != (0, int(self.action_dim))
+
+    def _sync_embedding(self, with_moments: bool = False):
+        """Row-sharded embedding table: make this rank's full-size copy current again -- every owner broadcasts its row
+        slice (a COLLECTIVE: all ranks of the group must get here together, as they do in evaluate() / state_dict() of
+        a sharded run).  The train step itself never needs this: it refreshes exactly the token rows it reads."""
+        if self._emb_shard is None or not (self._emb_stale or (with_moments and self._emb_moments_stale)):
+            return
+        import torch.distributed as dist
+        from ..sharded import shard_bounds
+        rank, world = self._emb_shard
+        tensors = [self.embedding.weight.data] if self._emb_stale else []
+        if with_moments and self._emb_moments_stale and self._opt_m is not None:
+            tensors += [self._opt_m.emb, self._opt_v.emb]
+        for g in range(world):
+            lo, hi = shard_bounds(self.item_num + 1, g, world)
+            src = g if self._group is None else dist.get_global_rank(self._group, g)
+            for t in tensors:
+                dist.broadcast(t[lo:hi], src=src, group=self._group)
+        self._emb_stale = False
+        if with_moments:
+            self._emb_moments_stale = False
+
+    def state_dict(self, *a, **kw):
+        self._sync_embedding()
+        return super().state_dict(*a, **kw)
 
     # -- engine plumbing -------------------------------------------------------------------
     @property
@@ -139,6 +168,7 @@ class NativeSessionNet(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("this model executes on a B200 through the native engine; move it to a CUDA "
                                "device first (model.to('cuda') / trainer.send_to_device()). No CPU fallback.")
+        self._sync_embedding()  # forward / evaluation on this net read arbitrary rows of the table
         if self._engine is None or self._engine.device != dev:
             self._engine = Engine(item_num=self.item_num, action_dim=self.action_dim,
                                   embedding_dim=self.embedding_dim, hidden_dim=self.hidden_dim,
@@ -153,6 +183,7 @@ class NativeSessionNet(nn.Module):
 
     def load_state_dict(self, *a, **kw):
         out = super().load_state_dict(*a, **kw)
+        self._emb_stale = False  # every row was just written
         if self._engine is not None:  # GRU transposes inside the engine are stale now
             self._engine.bind(self._net_id, self._net_tensors(), force=True)
         return out
@@ -374,6 +405,9 @@ class NativeTrainerBase:
                 n._attach(self._engine, i)
                 self._engine.bind(i, n._net_tensors(), force=True)
                 self._engine.set_adam_step(i, self._pending_steps[i])
+            if n0._emb_shard is not None:
+                from ..sharded import shard_bounds
+                self._engine.set_embedding_shard(*shard_bounds(n0.item_num + 1, *n0._emb_shard))
             self._stager = BatchStager(dev, n0.state_size)
             self._loss_dev = torch.zeros(8, dtype=torch.float32, device=dev)
         else:
@@ -387,14 +421,22 @@ class NativeTrainerBase:
         if st is not None:
             st.release_graphs()
 
-    def shard_vocabulary(self, rank: int, world: int, group=None):
-        """Vocabulary-shard every head of every net over `world` ranks (call before send_to_device)."""
+    def shard_vocabulary(self, rank: int, world: int, group=None, shard_embedding=None):
+        """Vocabulary-shard every head of every net over `world` ranks (call before send_to_device).
+        shard_embedding: also row-shard the embedding table's Adam sweep (rows [(N+1) r / G, (N+1)(r+1) / G) are
+        owned by rank r, token rows travel from their owners before each step; None: REC_SHARD_EMBEDDING=1 enables)."""
+        import os
         from ..sharded import shard_bounds
         V = self._nets[0].action_dim
         lo, hi = shard_bounds(V, rank, world)
+        if shard_embedding is None:
+            shard_embedding = os.environ.get("REC_SHARD_EMBEDDING", "0") == "1"
+        if self._nets[0].embedding_dim % 4:
+            shard_embedding = False
         self._drop_engine()
         for n in self._nets:
             n.shard_vocabulary(lo, hi, group)
+            n._emb_shard = (rank, world) if shard_embedding else None
         self._shard = (rank, world, group)
 
     def _set_mode(self, train: bool):
@@ -411,6 +453,7 @@ class NativeTrainerBase:
     def optimizer_state(self):
         out = []
         for i, n in enumerate(self._nets):
+            n._sync_embedding(with_moments=True)  # row-sharded table: a collective (see _sync_embedding)
             step = self._engine.adam_step(i) if self._engine is not None else self._pending_steps[i]
             out.append(dict(step=step, exp_avg=None if n._opt_m is None else [t.clone() for t in n._opt_m.all()],
                             exp_avg_sq=None if n._opt_v is None else [t.clone() for t in n._opt_v.all()]))

@@ -90,10 +90,13 @@ def _sharded_step(trainer, hp, main, s, a, true_len, r=None, s_next=None, true_n
     st = getattr(trainer, "_sharded_step", None)
     if st is None or st.eng is not eng or st.B_local != B:
         n0 = trainer._nets[0]
-        st = trainer._sharded_step = ShardedStep(eng, world, group, n0.hidden_dim * (2 if n0._bidirectional else 1), rank=rank)
+        st = trainer._sharded_step = ShardedStep(eng, world, group, n0.hidden_dim * (2 if n0._bidirectional else 1), rank=rank,
+                                                 shard_embedding=n0._emb_shard is not None)
         st.alloc_inputs(B, L, ds.device)
     local = eng._batch(B, ds, da, dln, dr, dsn, dnl, de)
     st.step(local, hp, main, trainer._loss_dev, has_q=r is not None)
+    if st.shard_embedding:  # the owners moved every row of the trained table: the other rows of this rank's copy are stale
+        trainer._nets[main]._emb_stale = trainer._nets[main]._emb_moments_stale = True
     return trainer._loss_dev[:2]
 
 

@@ -31,7 +31,7 @@ def shard_bounds(V: int, rank: int, world: int):
 class ShardedStep:
     """Drives rec_train_phase_a..d of one engine with the three collectives in between."""
 
-    def __init__(self, engine, world, group, D, rank=0, dp_trunk=None):
+    def __init__(self, engine, world, group, D, rank=0, dp_trunk=None, shard_embedding=False):
         self.eng, self.world, self.group, self.D = engine, world, group, D
         # dp_trunk: embedding + GRU run on each rank's own sessions (two more, small, collectives) instead of on
         # the all-gathered global batch on every rank.  Measured on B200 (cfg2, B = 256 per GPU): the replicated
@@ -46,6 +46,10 @@ class ShardedStep:
         if os.environ.get("REC_NO_DP_TRUNK"):
             dp_trunk = False
         self.dp_trunk = bool(dp_trunk)
+        # row-sharded embedding sweep (the engine was told its row range by rec_set_embedding_shard): one more all-reduce
+        # per step carries the token rows of the step from their owners (and, with the data-parallel trunk, one more
+        # small all-gather the token ids)
+        self.shard_embedding = bool(shard_embedding)
         self.rec = engine.record_floats()
         self.cap = 0
         self.B_local = -1
@@ -66,6 +70,13 @@ class ShardedStep:
         self.g_r = torch.zeros(Bg, dtype=torch.float32, device=dev)
         self.g_e = torch.zeros(Bg, dtype=torch.uint8, device=dev)
         self.global_batch = self.eng._batch(Bg, self.g_s, self.g_a, self.g_ln, self.g_r, self.g_sn, self.g_nl, self.g_e)
+        if self.shard_embedding:
+            E = self.eng.cfg["embedding_dim"]
+            self.emb_rows = torch.zeros(3 * Bg * L, E, dtype=torch.float32, device=dev)  # main(s) | main(s') | boot(s')
+            if self.dp_trunk:
+                self.ids_send = torch.zeros(2 * B_local * L, **i64)
+                self.ids_all = torch.zeros(self.world * 2 * B_local * L, **i64)
+                self.ids_s, self.ids_sn = torch.zeros(Bg * L, **i64), torch.zeros(Bg * L, **i64)
         if self.dp_trunk:
             self.local_packed = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
             self.l_s, self.l_sn = torch.zeros(B_local, L, **i64), torch.zeros(B_local, L, **i64)
@@ -148,6 +159,18 @@ class ShardedStep:
         self._graphs.clear()
         gc.collect()
 
+    def _refresh_rows(self, main_net, has_q, ids_s, ids_sn):
+        """Row-sharded embedding table: the token rows this step reads -- main net on s (and s'), bootstrap net on s' --
+        travel from their owners into this rank's copy: owned rows gathered (zeros elsewhere) -> ONE all-reduce(sum)
+        (bit-exact: a single owner per row) -> rows this rank does not own written into its table."""
+        eng, n = self.eng, ids_s.numel()
+        nets_ids = [(main_net, ids_s)] + ([(main_net, ids_sn), (1 - main_net, ids_sn)] if has_q else [])
+        for k, (net, ids) in enumerate(nets_ids):
+            eng.emb_rows_gather(net, ids, self.emb_rows[k * n:(k + 1) * n])
+        dist.all_reduce(self.emb_rows[:len(nets_ids) * n].view(-1), group=self.group)
+        for k, (net, ids) in enumerate(nets_ids):
+            eng.emb_rows_scatter(net, ids, self.emb_rows[k * n:(k + 1) * n])
+
     def _sequence(self, hp, main_net, losses_out, has_q):
         if self.dp_trunk:
             return self._sequence_dp(hp, main_net, losses_out, has_q)
@@ -157,6 +180,8 @@ class ShardedStep:
         N.check(eng.lib, eng.handle,
                 eng.lib.rec_unpack_batch(eng.handle, C.c_void_p(self.gathered_in.data_ptr()), self.world, self.B_local,
                                          C.byref(gb)), "rec_unpack_batch")
+        if self.shard_embedding:
+            self._refresh_rows(main_net, has_q, self.g_s.view(-1), self.g_sn.view(-1))
         if not has_q:
             gb = eng._batch(self.B_local * self.world, self.g_s, self.g_a, self.g_ln)
         self.run(gb, hp, main_net, losses_out, has_q)
@@ -171,6 +196,16 @@ class ShardedStep:
                 eng.lib.rec_unpack_batch(eng.handle, C.c_void_p(self.local_packed.data_ptr()), 1, B, C.byref(self.local_batch)),
                 "rec_unpack_batch")
         lb = self.local_batch if has_q else eng._batch(B, self.l_s, self.l_a, self.l_ln)
+        if self.shard_embedding:
+            # the owners need every rank's token ids before the local GRU passes: one more (20 KB per rank) all-gather
+            nl = self.l_s.numel()
+            self.ids_send[:nl].copy_(self.l_s.view(-1))
+            self.ids_send[nl:].copy_(self.l_sn.view(-1))
+            dist.all_gather_into_tensor(self.ids_all, self.ids_send, group=self.group)
+            v = self.ids_all.view(world, 2, nl)
+            self.ids_s.view(world, nl).copy_(v[:, 0])
+            self.ids_sn.view(world, nl).copy_(v[:, 1])
+            self._refresh_rows(main_net, has_q, self.ids_s, self.ids_sn)
         eng.dp_forward(lb, main_net, self.packed)
         dist.all_gather_into_tensor(self.gathered_in, self.packed, group=self.group)
         eng.dp_unpack(self.gathered_in, world, B, self.global_batch)

@@ -91,6 +91,9 @@ def main():
             gen0 = t._engine.generation
             _ = t.SMORL_1.final_state(sb, lb)
             assert t._engine.generation > gen0
+    if os.environ.get("REC_SHARD_EMBEDDING") == "1":  # the row-sharded sweep really was in effect
+        assert t._sharded_step.shard_embedding and t._engine._emb_shard == shard_bounds(V + 1, rank, world)
+        assert t.SMORL_1._emb_stale or t.SMORL_2._emb_stale
     lo, hi = shard_bounds(V, rank, world)
     for mine, full in ((t.SMORL_1, ref.SMORL_1), (t.SMORL_2, ref.SMORL_2)):
         sd, fsd = mine.state_dict(), full.state_dict()

@@ -143,12 +143,101 @@ def test_bidir_dropout_in_the_vocabulary_sharded_step(pkg, trunk):
     assert l_drop[0] == l_drop[1]
 
 
+@pytest.mark.parametrize("emb", ["replicated_table", "row_sharded_table"])
 @pytest.mark.parametrize("trunk", ["replicated", "data_parallel"])
-def test_two_ranks_on_one_gpu_over_gloo_equal_the_oracle(pkg, trunk):
+def test_two_ranks_on_one_gpu_over_gloo_equal_the_oracle(pkg, trunk, emb):
     """tests/dist_equivalence.py with TWO real ranks (two processes, torch.distributed over gloo, both on cuda:0):
     SMORL training through `ShardedStep` + sharded `evaluate()` against the oracle on the concatenated global batch.
-    The driver's one-GPU box runs this; on a multi-GPU box the NCCL variant (`test_multi_gpu_equals_oracle_...`) runs too."""
+    The driver's one-GPU box runs this; on a multi-GPU box the NCCL variant (`test_multi_gpu_equals_oracle_...`) runs too.
+    `row_sharded_table`: the embedding table's Adam sweep is row-sharded as well (token rows travel from their owners every
+    step, `state_dict()` / `evaluate()` re-assemble the table with one broadcast per owner)."""
     from test_gpu_parity import _run_dist_equivalence
-    env = {"DIST_BACKEND": "gloo", "DIST_ONE_GPU": "1", "DIST_STEPS": "6"}
+    env = {"DIST_BACKEND": "gloo", "DIST_ONE_GPU": "1", "DIST_STEPS": "6",
+           "REC_SHARD_EMBEDDING": "1" if emb == "row_sharded_table" else "0"}
     env.update({"REC_DP_TRUNK": "1"} if trunk == "data_parallel" else {"REC_NO_DP_TRUNK": "1"})
-    _run_dist_equivalence(2, 29631 if trunk == "replicated" else 29632, env)
+    _run_dist_equivalence(2, 29631 + 2 * (trunk != "replicated") + (emb != "replicated_table"), env)
+
+
+def test_row_sharded_embedding_sweep_virtual_ranks(pkg):
+    """SURVEY 8e C1 / C5 through the C ABI with G virtual ranks on one GPU: every rank owns a row slice of both twins'
+    embedding tables (rec_set_embedding_shard: 1001 rows over 3 ranks), the token rows of a step travel from their owners
+    (rec_emb_rows_gather -> sum = the all-reduce -> rec_emb_rows_scatter) before phase A, phase D sweeps the owned rows
+    only.  Losses equal the oracle's every step; the table assembled from the owners' slices equals the oracle's; rows a
+    rank does not own and never read keep their initial bits (the sweep really is restricted)."""
+    from ikea_recommender_system_b200.sharded import shard_bounds
+    G, V, L, B, steps = 3, 1000, 10, 96, 4
+    kw = dict(hidden_dim=64, embedding_dim=64, padding_pos="end", train_pad_embed=True, use_packed_seq=True,
+              learning_rate=0.01, item_num=V, state_size=L, action_dim=V, gamma=0.5, gru_layers=1,
+              q_weights=torch.tensor([1.0, 0.6, 0.3]), alpha=0.9, topk_div=2, topk_nov=1, nov_rew_sig=1.0)
+    rows = _syn().make_replay_rows(steps * B, V, L, seed=8)
+    unpop = _syn().unpopular_set_from_actions(rows["action"])
+    torch.manual_seed(2)
+    e_div = torch.nn.Embedding.from_pretrained(torch.randn(V + 1, 16), freeze=True)
+    ref = oracle.SMORLTrainer(div_embedding=e_div, unpopular_actions_set=unpop, **kw)
+    init_emb = [ref.SMORL_1.state_dict()["embedding.weight"].clone(), ref.SMORL_2.state_dict()["embedding.weight"].clone()]
+    shards, own = [], []
+    for g in range(G):
+        t = pkg.SMORL_trainer(div_embedding=e_div, unpopular_actions_set=unpop, device=DEV, **kw)
+        lo, hi = shard_bounds(V, g, G)
+        for n in t._nets:
+            n.shard_vocabulary(lo, hi)
+        t.send_to_device()
+        eng = t._ready(B)
+        own.append(shard_bounds(V + 1, g, G))
+        eng.set_embedding_shard(*own[g])
+        shards.append(t)
+    assert [hi - lo for lo, hi in own] == [333, 334, 334]
+    from helpers import synced_random
+    from test_gpu_parity import _virtual_rank_step
+    rng = synced_random()
+    touched = [set(), set()]  # rows of each twin's table that any step read or updated
+    mains = []
+    for i in range(steps):
+        batch = _syn().as_torch_batch(rows, i * B, (i + 1) * B)
+        rng.replay(); want = ref.train_step(*batch)
+        main = ref.last_main - 1
+        mains.append(main)
+        rng.advance()
+        s, sn = batch[0].to(DEV).reshape(-1).contiguous(), batch[3].to(DEV).reshape(-1).contiguous()
+        touched[main] |= set(s.tolist()) | set(sn.tolist())
+        touched[1 - main] |= set(sn.tolist())
+        for net, ids in ((main, s), (main, sn), (1 - main, sn)):
+            parts = [torch.empty(ids.numel(), 64, device=DEV) for _ in range(G)]
+            for g in range(G):
+                shards[g]._engine.emb_rows_gather(net, ids, parts[g])
+            # exactly one owner per row: every other contribution is an exact zero
+            assert all(int(((p_ != 0).any(1)).sum()) <= ids.numel() for p_ in parts)
+            total = torch.stack(parts).sum(0).contiguous()
+            for g in range(G):
+                shards[g]._engine.emb_rows_scatter(net, ids, total)
+        got = _virtual_rank_step(shards, lambda t: t._hp(), batch, main)
+        for g in range(G):
+            assert_close(got[g], want, rtol=RTOL, atol=1e-5, what=f"step {i} rank {g} losses (row-sharded embedding)")
+    for net_i, full in enumerate([ref.SMORL_1, ref.SMORL_2]):
+        want_emb = full.state_dict()["embedding.weight"]
+        tables = [shards[g]._nets[net_i].embedding.weight.data.cpu() for g in range(G)]
+        assembled = torch.cat([tables[g][own[g][0]:own[g][1]] for g in range(G)])
+        assert_state_close({"embedding.weight": assembled}, {"embedding.weight": want_emb}, rtol=RTOL, atol=ATOL_P,
+                           outlier_frac=1e-3, outlier_atol=0.1 * 0.01)
+        for g in range(G):
+            lo, hi = own[g]
+            foreign = torch.ones(V + 1, dtype=torch.bool)
+            foreign[lo:hi] = False
+            untouched = [r for r in range(V + 1) if foreign[r] and r not in touched[net_i]]
+            assert len(untouched) > 50
+            assert torch.equal(tables[g][untouched], init_emb[net_i][untouched])  # never read and never swept on this rank
+            if net_i in mains:
+                # the owners kept moving (momentum) rows that this rank last refreshed in an earlier step: its copy is
+                # stale there -- with an unrestricted sweep every copy would equal the owners' (all ranks see all gradients)
+                assert int((tables[g][foreign] != assembled[foreign]).any(1).sum()) > 0
+
+
+@pytest.mark.parametrize("trunk", ["replicated", "data_parallel"])
+def test_row_sharded_embedding_sequence_under_graph_capture_world1(pkg, trunk):
+    """The row-refresh sequence (id all-gather, gather, all-reduce, scatter) inside the CAPTURED sharded step: one NCCL rank
+    (owner of every row, so the values are those of the replicated table) through warm-up, capture and replay of both
+    twins' graphs against the oracle.  The two-rank gloo test above covers the exchange itself, eagerly."""
+    from test_gpu_parity import _run_dist_equivalence
+    env = {"REC_SHARD_EMBEDDING": "1"}
+    env.update({"REC_DP_TRUNK": "1"} if trunk == "data_parallel" else {"REC_NO_DP_TRUNK": "1"})
+    _run_dist_equivalence(1, 29641 + (trunk != "replicated"), env)
