@@ -424,13 +424,14 @@ class NativeTrainerBase:
     def shard_vocabulary(self, rank: int, world: int, group=None, shard_embedding=None):
         """Vocabulary-shard every head of every net over `world` ranks (call before send_to_device).
         shard_embedding: also row-shard the embedding table's Adam sweep (rows [(N+1) r / G, (N+1)(r+1) / G) are
-        owned by rank r, token rows travel from their owners before each step; None: REC_SHARD_EMBEDDING=1 enables)."""
+        owned by rank r, token rows travel from their owners before each step).  None: on for world > 1 (measured on cfg4:
+        +1.5 % sessions/s at 2 GPUs, +7.5 % at 4), REC_SHARD_EMBEDDING=0 / 1 forces either."""
         import os
         from ..sharded import shard_bounds
         V = self._nets[0].action_dim
         lo, hi = shard_bounds(V, rank, world)
         if shard_embedding is None:
-            shard_embedding = os.environ.get("REC_SHARD_EMBEDDING", "0") == "1"
+            shard_embedding = os.environ.get("REC_SHARD_EMBEDDING", "1" if world > 1 else "0") == "1"
         if self._nets[0].embedding_dim % 4:
             shard_embedding = False
         self._drop_engine()

@@ -255,7 +255,17 @@ def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, 
     held = None  # the engine that was told "parameters are frozen for this sweep" (model.eval(): nothing trains here)
     # a vocabulary-sharded model under a process group evaluates sharded by SESSIONS: this rank scores every world-th
     # batch against the full catalogue (REC_EVAL_SHARD=vocab keeps the per-batch candidate exchange)
+    import os
+    import time
+    trace = [("start", time.perf_counter())] if os.environ.get("REC_EVAL_TRACE") else None  # per-phase wall clock (debug)
+
+    def stamp(what):
+        if trace is not None:
+            torch.cuda.synchronize(dev)
+            trace.append((what, time.perf_counter()))
+
     replica = _FullHeadReplica.plan(model, head_idx)
+    stamp("plan")
     net = model if replica is None else replica
     try:
         for s, a, s_len in evaluation_data_loader:
@@ -268,6 +278,7 @@ def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, 
                     eng.eval_hold_params(True)
                     held = (eng, eng.handle)
                 _eval_one_batch(net, eng, eng._batch(B, ds, da, dl), o, acc, kmax)
+                stamp(f"batch{n_batches}")
             n_total += B
             n_batches += 1
     finally:
@@ -275,7 +286,11 @@ def evaluate(evaluation_data_loader, model, device, loss_function, padding_pos, 
             held[0].eval_hold_params(False)
     if replica is not None:
         replica.reduce(acc)
+        stamp("reduce")
     r = acc.read()
+    if trace is not None:
+        stamp("read")
+        print("REC_EVAL_TRACE", " ".join(f"{w}={1e3 * (t1 - t0):.3f}ms" for (_, t0), (w, t1) in zip(trace, trace[1:])), flush=True)
     nk = len(topk_hr_ndcg)
     hr = r["hits"][:nk] / n_total
     ndcg = r["ndcg"][:nk] / n_total
