@@ -34,36 +34,37 @@ def save_best_checkpoint(path, epoch, model, model_idx):
                 "model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}}, path)
 
 
+# wandb / tensorboard key schema of one evaluation point (`get_logging_dict_train`, utils/logging_SMORL.py:1-71), as data:
+# (key template, argument it reads, index into that argument).  "{p}" is the second twin's prefix, "{k}" a top-k value;
+# a key without "Val" in it exists only in the first twin's (un-prefixed) record.
+_LOG_SCALARS = [("Supervised Train Loss", "train_sup_loss"), ("Q-Modification-Signal", "train_q_loss"),
+                ("{p} Supervised Val Loss", "val_loss")]
+_LOG_PER_K = [("Train_HR@{k}", "train_hr"), ("Train_NDCG@{k}", "train_ndcg"), ("{p}Val_HR@{k}", "val_hr"),
+              ("{p}Val_NDCG@{k}", "val_ndcg"), ("{p}Train_R@{k}", "train_reps"), ("{p}Val_R@{k}", "val_reps")]
+_LOG_PER_COV_K = [("Train_NOV_CV@{k}", "train_coverage_res", 0), ("Train_DIV_CV@{k}", "train_coverage_res", 1),
+                  ("{p}Val_NOV_CV@{k}", "val_coverage_res", 0), ("{p}Val_DIV_CV@{k}", "val_coverage_res", 1)]
+_LOG_REWARDS = [("Train_Nov_Reward", "train_nov_rew"), ("Train_Div_Reward", "train_div_rew"),
+                ("{p}Val_Nov_Reward", "val_nov_rew"), ("{p}Val_Div_Reward", "val_div_rew")]
+
+
 def logging_dict_train(train_sup_loss, train_q_loss, val_loss, topk_hr_ndcg, train_hr, train_ndcg, val_hr, val_ndcg,
                        train_coverage_res, val_coverage_res, topk_cov, train_nov_rew, train_div_rew, val_nov_rew,
                        val_div_rew, train_reps, val_reps, q_included=True, prefix=""):
-    """The wandb / tensorboard record of one evaluation point with the reference's key names
-    (`get_logging_dict_train`, utils/logging_SMORL.py:1-71); with a prefix (second twin) only the validation keys stay."""
-    res = {"Supervised Train Loss": train_sup_loss}
-    if q_included:
-        res["Q-Modification-Signal"] = train_q_loss
-    res[f"{prefix + ' '}Supervised Val Loss"] = val_loss
+    """The record of one evaluation point under the reference's key names (schema tables above)."""
+    src = locals()
+    res = {}
+    for tmpl, name in _LOG_SCALARS:
+        if name != "train_q_loss" or q_included:
+            res[tmpl.format(p=prefix)] = src[name]
     for i, k in enumerate(topk_hr_ndcg):
-        res[f"Train_HR@{k}"] = float(train_hr[i])
-        res[f"Train_NDCG@{k}"] = float(train_ndcg[i])
-        res[f"{prefix}Val_HR@{k}"] = float(val_hr[i])
-        res[f"{prefix}Val_NDCG@{k}"] = float(val_ndcg[i])
-        res[f"{prefix}Train_R@{k}"] = float(train_reps[i])
-        res[f"{prefix}Val_R@{k}"] = float(val_reps[i])
+        for tmpl, name in _LOG_PER_K:
+            res[tmpl.format(p=prefix, k=k)] = float(src[name][i])
     for k in topk_cov:
-        res[f"Train_NOV_CV@{k}"] = float(train_coverage_res[k][0])
-        res[f"Train_DIV_CV@{k}"] = float(train_coverage_res[k][1])
-        res[f"{prefix}Val_NOV_CV@{k}"] = float(val_coverage_res[k][0])
-        res[f"{prefix}Val_DIV_CV@{k}"] = float(val_coverage_res[k][1])
-    res["Train_Nov_Reward"] = float(train_nov_rew)
-    res["Train_Div_Reward"] = float(train_div_rew)
-    res[f"{prefix}Val_Nov_Reward"] = float(val_nov_rew)
-    res[f"{prefix}Val_Div_Reward"] = float(val_div_rew)
-    if prefix != "":
-        for key in list(res.keys()):
-            if "Val" not in key:
-                res.pop(key)
-    return res
+        for tmpl, name, j in _LOG_PER_COV_K:
+            res[tmpl.format(p=prefix, k=k)] = float(src[name][k][j])
+    for tmpl, name in _LOG_REWARDS:
+        res[tmpl.format(p=prefix)] = float(src[name])
+    return res if prefix == "" else {key: v for key, v in res.items() if "Val" in key}
 
 
 def eval_points(n_batches, eval_at):
