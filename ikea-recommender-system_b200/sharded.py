@@ -1,16 +1,20 @@
 """Vocabulary-sharded multi-GPU execution (one process per GPU, torch.distributed for the plumbing).
 
 Partitioning: rank g of G owns rows [V*g/G, V*(g+1)/G) of EVERY head (weights,
-bias and their Adam state) -- the dominant HBM term (24 B/param/step of dense Adam) scales 1/G.
-Embedding table and GRU are replicated and updated identically on every rank.  Sessions are
-data-parallel at the input: each rank contributes its local batch, the (tiny) batches are all-gathered
-and every rank multiplies the full batch by its vocabulary slice.
+bias and their Adam state) -- the dominant HBM term (24 B/param/step of dense Adam) scales 1/G -- and, with
+`shard_embedding`, rows [(N+1)*g/G, (N+1)*(g+1)/G) of the embedding tables' Adam sweep (every rank keeps a full-size copy
+whose foreign rows are refreshed from their owners when a step reads them).  The GRU is replicated and updated
+identically on every rank.  Sessions are data-parallel at the input: each rank contributes its local batch, the (tiny)
+batches are all-gathered and every rank multiplies the full batch by its vocabulary slice.
 
-Collectives per train step (all <= 1 MB, latency-bound):
+Collectives per train step (latency-bound; all <= 1 MB except the row refresh):
     1. all_gather  packed local batches (rec_pack_batch: one byte buffer per rank)
+    1a. all_reduce token rows of the step from their owners, [3 * G*B*L, E] (row-sharded embedding sweep only)
     2. all_gather  per-shard head records (max, sum-exp, target logit, argmax, top-k candidates)
     3. all_reduce  Q(s,a) / Q_boot(s',a*) contributions         [2, G*B, 3]
     4. all_reduce  dL/dh partials                                [G*B, D]
+(data-parallel trunk, world > 4: + all_reduce GRU gradients, all_gather dx rows, and -- row-sharded sweep -- one 20 KB
+all_gather of the token ids ahead of the local GRU passes)
 """
 
 from __future__ import annotations
