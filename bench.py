@@ -188,6 +188,15 @@ def algorithmic_bytes(wl):
                 sup_stats=4 * (D + 1) * V, greedy_stats=4 * (Kh - 1) * (D + 1) * V)
 
 
+def algorithmic_flops(wl):
+    """FLOPs/step = 2*B*D*V*(3 + (K_h - 1)) + 5*2*B*L*3H(E+H)*dirs (supervised head forward + two
+    backward GEMMs, the K_h - 1 Q heads on s' forward only; three GRU forwards + one backward at twice a forward)."""
+    bidir = wl.get("family") == "bidir_sqn"
+    dirs = 2 if bidir else 1
+    B, L, V, E, H, D, Kh = wl["batch"], wl["L"], wl["item_num"], wl["E"], wl["H"], wl["H"] * dirs, (2 if bidir else 4)
+    return 2 * B * D * V * (3 + (Kh - 1)) + 5 * 2 * B * L * 3 * H * (E + H) * dirs
+
+
 def _traffic(workload_key):
     """DRAM bytes per launch from the committed `ncu --set full` capture of this round (profiles/r02_traffic.json,
     stamped with the commit it was captured at); None when there is no capture for this workload."""
@@ -342,8 +351,10 @@ def train_bench(args, wl, wl_key, K, W, local, with_cpu):
             kms[which].append(eng.last_kernel_ms(which))
     eng.enable_kernel_timing(False)
     ab = algorithmic_bytes(wl)
-    peak, peak_src, _ = _peaks()
+    peak, peak_src, peaks_json = _peaks()
     traffic, traffic_src = _traffic(wl_key)
+    if wl["batch"] != WORKLOADS[wl_key]["batch"]:
+        traffic = None  # the committed capture was taken at the workload's own batch size
     kernels = {}
     for which, (label, key) in slots.items():
         t_ms = sum(kms[which]) / len(kms[which])
@@ -360,6 +371,14 @@ def train_bench(args, wl, wl_key, K, W, local, with_cpu):
                 "dominant": dict(kernel=dom, **kernels[dom]), "kernels": kernels,
                 "note": "per-kernel times are taken in kernel-timing mode (branches serialised), so their shares add "
                         "up to more than the overlapped step"}
+    # the other roofline of SURVEY 8d: at B = 256 the step is HBM-bound by a wide margin, the tensor side takes over with
+    # the batch size (crossover near B = 2.5 k at cfg4) -- `--batch` measures that regime
+    tf_peak = float(peaks_json.get("bf16_tflops_sustained", 1391.5))  # a kernel timed inside a long step: the sustained figure
+    fl = algorithmic_flops(wl)
+    roofline["tensor_side"] = {"algorithmic_flops_per_step": fl, "achieved_tflops": fl / (step_ms / 1e3) / 1e12,
+                               "peak_tflops": tf_peak, "frac": fl / (step_ms / 1e3) / 1e12 / tf_peak,
+                               "hbm_floor_ms": ab["step"] / peak / 1e6, "tensor_floor_ms": fl / tf_peak / 1e9,
+                               "note": "algorithmic FLOP (one pass); the head GEMMs execute 3 bf16 passes (hi/lo split)"}
 
     # ---- e2e: public API, host tensors in, python floats out ------------------------------------
     for i in range(max(W, 16)):  # both twins must have been captured (first sighting eager, second captures)
@@ -522,6 +541,8 @@ def run_native(args):
         print(json.dumps(line), flush=True)
         return
     wl = WORKLOADS[args.workload]
+    if args.batch is not None and args.batch != wl["batch"]:
+        wl = dict(wl, batch=int(args.batch), name=wl["name"].replace("B=256 per GPU", f"B={args.batch}").replace("B=256", f"B={args.batch}"))
     line = train_bench(args, wl, args.workload, args.steps, args.warmup, local, with_cpu)
     if not args.no_secondary:
         sec = {}
@@ -541,6 +562,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + sorted(EVAL_WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None,
+                    help="sessions per step of the train workload on ONE GPU (default: the workload's own, 256): SURVEY 8d's "
+                         "single-GPU runs at B in {1024, 4096} that show the tensor-bound regime")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="only the primary workload (no cfg2 / eval objects)")
     args = ap.parse_args()

@@ -274,6 +274,12 @@ def test_bench_algorithmic_bytes_follow_survey_8d():
     assert ab["sup_stats"] == 4 * (H + 1) * V and ab["greedy_stats"] == 3 * ab["sup_stats"]
     big = bench.algorithmic_bytes(bench.WORKLOADS["cfg4"])
     assert 9.0e9 < big["step"] < 9.1e9  # 9.06 GB at 1 M items
+    # FLOPs/step = 2 B D V (3 + (K_h - 1)) + 5 * 2 B L 3H (E + H) dirs: SURVEY 8d quotes 197 GF (cfg4) and 363 GF (cfg3)
+    assert round(bench.algorithmic_flops(bench.WORKLOADS["cfg4"]) / 1e9) == 197
+    assert round(bench.algorithmic_flops(bench.WORKLOADS["cfg3"]) / 1e9) == 363
+    w4 = dict(bench.WORKLOADS["cfg4"], batch=4096)  # `--batch 4096`: 16x the head FLOPs, the same bytes
+    assert bench.algorithmic_flops(w4) == 16 * bench.algorithmic_flops(bench.WORKLOADS["cfg4"])
+    assert bench.algorithmic_bytes(w4)["step"] == big["step"]
 
 
 def test_coverage_from_packed_bitmaps_equals_the_reference_counts(pkg):
