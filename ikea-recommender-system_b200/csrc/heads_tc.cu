@@ -766,6 +766,9 @@ __global__ void __launch_bounds__(256) h_prepack_kernel(const float *__restrict_
 #define BWD2_COMPUTE 512
 #define BWD2_THREADS (BWD2_COMPUTE + 32 + 256)
 
+// CHUNKED = more than 256 sessions (a compile-time split: the resident instantiation -- every single-GPU configuration of the
+// reference -- carries none of the chunk bookkeeping in its registers).
+template <bool CHUNKED>
 __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTrainPtrs hp, const uint8_t *__restrict__ hpack,
                                                                            const int64_t *__restrict__ target,
                                                                            const float *__restrict__ row_stats, int B, int Vloc,
@@ -800,8 +803,8 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
   const int q = warp & 3, cq = (warp >> 2) & 3;  // TMEM lane quarter; column quarter (4 warps share a lane quarter)
   // batches beyond 256 sessions run in chunks of 256 per tile: the h chunk is re-read (TMA, from L2) per (tile, chunk),
   // dW/db accumulate over the chunks in TMEM, dh leaves TMEM per (tile, chunk) into this CTA's slice
-  const int n_chunks = (B + 255) / 256;
-  const bool resident = n_chunks == 1;  // dh stays in TMEM across all tiles of the CTA
+  const int n_chunks = CHUNKED ? (B + 255) / 256 : 1;
+  constexpr bool resident = !CHUNKED;  // dh stays in TMEM across all tiles of the CTA
   const int nbb0 = min(2, (B + 127) / 128);  // 128-session blocks of chunk 0
   const float log2_inv_B = __log2f(inv_B);
 
@@ -1032,6 +1035,31 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
     uint32_t phG = 0, phL[2] = {0, 0};
     float bias_p = 0.f;
     if (tid < 128 && (int)blockIdx.x < n_tiles && (int)blockIdx.x * 128 + tid < Vloc) bias_p = hp.b[blockIdx.x * 128 + tid];
+    // Chunked mode (more than 256 sessions): dh of a (tile, chunk) leaves TMEM into this CTA's slice (first tile stores,
+    // later tiles add).  The read-modify-write (64 KB each way, one 256-byte row per lane) used to sit between the
+    // chunk's last gradient MMA and the next chunk's first logits MMA; it now runs BEHIND this warp's next
+    // publish(MB_WREADY), i.e. while the issuer loads the next h chunk and issues its logits.  Safe: the next dh MMA
+    // is issued only after every compute warp arrived at MB_DL, which each does after its own read-out.
+    int pend_r0 = -1, pend_nbb = 0, pend_k = 0;
+    auto flush_dh = [&]() {
+      if (resident || pend_r0 < 0) return;
+      float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
+      for (int bb = 0; bb < pend_nbb; ++bb) {
+        const int row = pend_r0 + bb * 128 + q * 32 + lane;
+        float g[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + cq * 16), g);
+        if (row < B) {
+          float4 *dst = reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+            if (pend_k > 0) { float4 p = dst[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            dst[j] = o;
+          }
+        }
+      }
+      pend_r0 = -1;
+    };
     int k = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
       const int v0 = t * 128;
@@ -1062,6 +1090,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
           tgt_c[tid] = row < B ? (int)(target[row] - vocab_lo) : -1;
         }
         publish(MB_WREADY);
+        flush_dh();  // dh of the previous (tile, chunk) leaves TMEM while the issuer loads the next h chunk / issues its logits
         if (c == 0 && tid < 128) {  // logits bias of the next tile (its Adam update belongs to a later tile: no hazard)
           const int nt = t + gridDim.x;
           bias_p = (nt < n_tiles && nt * 128 + tid < Vloc) ? hp.b[nt * 128 + tid] : 0.f;
@@ -1124,26 +1153,10 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
         phG ^= 1;
         tc::tc_fence_after();
         TRACE2(10);
-        if (!resident) {
-          // dh of this (tile, chunk): TMEM -> this CTA's slice (first tile stores, later tiles add)
-          float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
-          for (int bb = 0; bb < nbb; ++bb) {
-            const int row = r0 + bb * 128 + q * 32 + lane;
-            float g[16];
-            tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + cq * 16), g);
-            if (row < B) {
-              float4 *dst = reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-                if (k > 0) { float4 p = dst[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                dst[j] = o;
-              }
-            }
-          }
-        }
+        if (!resident) { pend_r0 = r0; pend_nbb = nbb; pend_k = k; }  // read out behind the next publish(MB_WREADY)
       }
     }
+    flush_dh();
     // ---- resident dh of this CTA: TMEM -> its slice ---------------------------------------------------
     float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
     for (int bb = 0; resident && bb < nbb0; ++bb) {
@@ -1197,7 +1210,8 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
   const size_t smem = 1024 + 12 * (size_t)BLK + 4096 + 3072 + 2048 + 8 * 32 * 20 * 4;
   static bool attr_set[REC_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
   if (!attr_set[e->dev]) {
-    REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    REC_CUDA(e, cudaFuncSetAttribute(head_bwd_adam_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[e->dev] = true;
   }
   if (!e->hpack_ready) {
@@ -1205,10 +1219,10 @@ int launch_head_bwd_adam_tc(rec_engine *e, int net_id, const float *h, const rec
     REC_LAUNCH_CHECK(e);
   }
   e->hpack_ready = false;
-  head_bwd_adam_tc2_kernel<<<n_cta, BWD2_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo,
-                                                                    n_tiles, inv_B, e->dh_part, hp->beta1, hp->beta2, hp->eps,
-                                                                    step_size, 1.f / bc2_sqrt, trace_sel() == 0 ? e->trace : nullptr,
-                                                                    e->d_sc, e->bwd_extra);
+  auto kernel = B > 256 ? head_bwd_adam_tc2_kernel<true> : head_bwd_adam_tc2_kernel<false>;
+  kernel<<<n_cta, BWD2_THREADS, smem, e->stream>>>(t, e->hpack, b->a, e->row_stats, B, e->Vloc, e->cfg.vocab_lo, n_tiles, inv_B,
+                                                  e->dh_part, hp->beta1, hp->beta2, hp->eps, step_size, 1.f / bc2_sqrt,
+                                                  trace_sel() == 0 ? e->trace : nullptr, e->d_sc, e->bwd_extra);
   REC_LAUNCH_CHECK(e);
   *n_slices = n_cta;
   return REC_OK;
