@@ -1041,20 +1041,34 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
     // publish(MB_WREADY), i.e. while the issuer loads the next h chunk and issues its logits.  Safe: the next dh MMA
     // is issued only after every compute warp arrived at MB_DL, which each does after its own read-out.
     int pend_r0 = -1, pend_nbb = 0, pend_k = 0;
+    float nx_lse = 0.f;  // log-sum-exp / target of this thread's row in the next chunk, loaded one chunk ahead
+    int nx_tgt = -1;
+    bool nx_valid = false;
     auto flush_dh = [&]() {
       if (resident || pend_r0 < 0) return;
       float *slice = dh_part + (int64_t)blockIdx.x * B * 64;
       for (int bb = 0; bb < pend_nbb; ++bb) {
-        const int row = pend_r0 + bb * 128 + q * 32 + lane;
+        const int row_base = pend_r0 + bb * 128 + q * 32;  // the warp's 32 rows; this lane holds 16 columns of row_base + lane
         float g[16];
         tc::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + T_DH + (uint32_t)(bb * 64 + cq * 16), g);
-        if (row < B) {
-          float4 *dst = reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16);
+        // lane = row means every lane of a load / store touches another 128-byte line (32 L1 wavefronts per instruction:
+        // ~8 k LSU cycles per chunk).  Quad transpose through shuffles instead: instruction i covers rows 8i .. 8i + 7,
+        // the four lanes of a quad write the four float4 of ONE row = 64 contiguous bytes (8 lines per instruction).
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int src = 8 * i + (lane >> 2);
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-            if (pend_k > 0) { float4 p = dst[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-            dst[j] = o;
+            const float x = __shfl_sync(0xffffffffu, g[4 * j], src), y = __shfl_sync(0xffffffffu, g[4 * j + 1], src);
+            const float z = __shfl_sync(0xffffffffu, g[4 * j + 2], src), w = __shfl_sync(0xffffffffu, g[4 * j + 3], src);
+            if ((lane & 3) == j) o = make_float4(x, y, z, w);
+          }
+          const int row = row_base + src;
+          if (row < B) {
+            float4 *dst = reinterpret_cast<float4 *>(slice + (int64_t)row * 64 + cq * 16) + (lane & 3);
+            if (pend_k > 0) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            *dst = o;
           }
         }
       }
@@ -1085,12 +1099,22 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) head_bwd_adam_tc2_kernel(TcTr
         float *lse_c = lse_s + (resident ? 0 : (c & 1) * 256);
         int *tgt_c = tgt_s + (resident ? 0 : (c & 1) * 256);
         if (!resident && tid < 256) {  // this chunk's rows (the other buffer may still be read by a slower warp)
-          const int row = r0 + tid;
-          lse_c[tid] = row < B ? row_stats[(int64_t)row * 8] : 0.f;
-          tgt_c[tid] = row < B ? (int)(target[row] - vocab_lo) : -1;
+          if (!nx_valid) {  // very first chunk of the CTA; afterwards the values were requested one chunk ahead
+            const int row = r0 + tid;
+            nx_lse = row < B ? row_stats[(int64_t)row * 8] : 0.f;
+            nx_tgt = row < B ? (int)(target[row] - vocab_lo) : -1;
+          }
+          lse_c[tid] = nx_lse;
+          tgt_c[tid] = nx_tgt;
         }
         publish(MB_WREADY);
         flush_dh();  // dh of the previous (tile, chunk) leaves TMEM while the issuer loads the next h chunk / issues its logits
+        if (!resident && tid < 256) {  // rows of the NEXT (tile, chunk): in flight during this chunk's epilogues
+          const int row = (c + 1 < n_chunks ? c + 1 : 0) * 256 + tid;
+          nx_lse = row < B ? row_stats[(int64_t)row * 8] : 0.f;
+          nx_tgt = row < B ? (int)(target[row] - vocab_lo) : -1;
+          nx_valid = true;
+        }
         if (c == 0 && tid < 128) {  // logits bias of the next tile (its Adam update belongs to a later tile: no hazard)
           const int nt = t + gridDim.x;
           bias_p = (nt < n_tiles && nt * 128 + tid < Vloc) ? hp.b[nt * 128 + tid] : 0.f;
