@@ -3,7 +3,7 @@
 (BASELINE.json configs[3], the north-star target config; it fits one B200), plus top-k evaluation sessions/s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                    [--workload cfg4|cfg2|eval|eval70k] [--no-secondary] [--no-cpu-baseline]
+                    [--workload cfg4|cfg2|cfg3|eval|eval70k] [--batch B] [--no-secondary] [--no-cpu-baseline]
 
 Prints ONE JSON line (rank 0).
   value     device-timed throughput, batches already resident in HBM (CUDA events on the engine's stream)
@@ -11,14 +11,17 @@ Prints ONE JSON line (rank 0).
             read of the losses every step)
   roofline  whole train step: algorithmic bytes (24 P + 4 (K_h + 1) D V) / step time against the measured
             HBM peak; `kernels` lists every timed kernel (exactly ONE launch between its two CUDA events) with its own
-            algorithmic bytes and fraction, `dominant` is the slowest of them
+            algorithmic bytes and fraction, `dominant` is the slowest of them; `tensor_side` is the other roofline of
+            SURVEY 8d (algorithmic FLOP against the measured sustained bf16 peak, HBM and tensor floors) -- it takes over
+            from B ~ 2.5 k sessions per step, which `--batch B` measures on one GPU
   cpu_baseline  the CPU oracle (torch-CPU restatement pinned bit-exact to the reference) on this box's host cores
   secondary the other measurements of BASELINE.json's metric in the same line: "cfg2" (configs[1]: 70 852 items,
             the reference's own catalogue size), "cfg3" (configs[2]: BidirGRU4Rec-SQN, 250 k items, L = 50, H = 256) and
             "eval" (configs[4]: full-catalogue top-k evaluation sweep over 1 M items), each with its own value / e2e /
             roofline.
 `--impl reference` times the CPU oracle alone (the reference is pure Python/PyTorch; no GPU code is imported).
-Under torchrun (N > 1): vocabulary-sharded step, see ikea-recommender-system_b200/dist_bench.py.
+Under torchrun (N > 1): vocabulary-sharded heads + row-sharded embedding sweep, evaluation sharded by sessions (median of
+three sweeps), see ikea-recommender-system_b200/dist_bench.py.
 """
 from __future__ import annotations
 
