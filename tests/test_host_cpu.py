@@ -299,3 +299,55 @@ def test_coverage_from_packed_bitmaps_equals_the_reference_counts(pkg):
             covered = set(int(j) for j in np.nonzero(np.unpackbits(cov[i].view(np.uint8), bitorder="little")[:n])[0])
             assert got[k] == (len(covered & unpop_set) / len(unpop_set), len(covered) / n), (n, k)
         assert table.sum() == len(unpop_set)
+
+
+def test_built_library_contains_the_tcgen05_and_tma_kernels():
+    """SASS of the in-tree librecsys_b200.so (cuobjdump; no GPU needed): built for sm_100a only, and the kernels DESIGN.md
+    section 4 calls tensor-core kernels really issue tcgen05 MMAs (UTCHMMA), read their accumulators back from TMEM (LDTM),
+    commit to mbarriers (UTCBAR) and stage operands with TMA bulk copies (UBLKCP) -- a library recompiled around
+    mma.sync / plain loads would pass every numerics test and fail here."""
+    import re
+    import shutil
+    import subprocess
+    from ikea_recommender_system_b200 import _native as N
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", N.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
+    per_fn, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_fn[name] = {"UTCHMMA": 0, "LDTM": 0, "UTCBAR": 0, "UBLKCP": 0}
+        elif name is not None:
+            for op in per_fn[name]:
+                if op in line:
+                    per_fn[name][op] += 1
+
+    def kernels(fragment):
+        ks = {k: v for k, v in per_fn.items() if fragment in k}
+        assert ks, f"no kernel named *{fragment}* in the library"
+        return ks
+
+    # D = 64 head kernels (heads_tc.cu): statistics / greedy action (every instantiation) and both backward instantiations
+    for frag in ("head_stats_tc_kernel", "head_bwd_adam_tc2_kernel"):
+        for k, ops in kernels(frag).items():
+            assert ops["UTCHMMA"] > 0 and ops["LDTM"] > 0 and ops["UTCBAR"] > 0, (k, ops)
+            # template <NB, NT, ARG, RING>: the RING instantiations stream the weight tiles through the TMA slot ring
+            if frag == "head_bwd_adam_tc2_kernel" or re.search(r"Lb[01]ELb1EE", k):
+                assert ops["UBLKCP"] > 0, (k, ops)
+    assert any(re.search(r"Lb[01]ELb1EE", k) for k in kernels("head_stats_tc_kernel"))
+    assert len(kernels("head_bwd_adam_tc2_kernel")) == 2  # resident (<= 256 sessions) and chunked
+    # the K-loop skeleton (tck.cuh): wide heads, evaluation chunk maxima, tensor-core GRU trunk
+    # (HeadCmaxPairT<n != 0> are the experiment variants of DESIGN 4.7 -- "no MMAs", "no epilogue", ... -- not product kernels)
+    product = ["GruBptt", "GruStep", "4GemmE", "HeadDwAdam", "HeadDhE", "HeadFwdILi0E", "HeadFwdILi1E", "HeadFwdILi2E",
+               "HeadTopkILb0E", "HeadTopkILb1E", "HeadCmaxFlat", "HeadCmaxPairTILi0E"]
+    tck = kernels("tck_kernel")
+    for frag in product:
+        ks = {k: v for k, v in tck.items() if frag in k}
+        assert len(ks) == 1, (frag, list(ks))
+        for k, ops in ks.items():
+            assert ops["UTCHMMA"] > 0 and ops["LDTM"] > 0 and ops["UBLKCP"] > 0, (k, ops)
